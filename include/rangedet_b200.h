@@ -1,0 +1,103 @@
+/* rangedet_b200.h -- C-ABI of librangedet_b200.so (sm_100a CUDA kernels for the RangeDet hot path).
+ *
+ * Conventions (all entry points):
+ *   - plain pointers + sizes, no torch / MXNet types; every tensor pointer is a DEVICE pointer
+ *     owned by the caller (the reference's engine owns all buffers too:
+ *     operator_cxx/contrib/decode_3d_bbox-inl.h:279-283), dense row-major fp32 unless stated
+ *   - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream); kernels are
+ *     enqueued on it and the call returns without synchronising unless stated
+ *   - return 0 on success, non-zero on error; rd_last_error() gives a thread-local message
+ *     (the reference's CHECK_* / LOG(FATAL) -> dmlc::Error, decode_3d_bbox.cc:30-60)
+ *   - no allocation inside: scratch space is a caller-provided workspace whose size the
+ *     matching *_workspace_bytes() query returns
+ *   - there is NO CPU fallback: without an sm_100 device every compute entry point fails
+ */
+#ifndef RANGEDET_B200_H_
+#define RANGEDET_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef void* rd_stream_t;
+
+/* ---- library ---------------------------------------------------------------------------- */
+int rd_version(void);                 /* ABI version, currently 1 */
+const char* rd_last_error(void);      /* thread-local, never NULL */
+/* 0 if the current CUDA device is compute capability 10.x, else non-zero (+ rd_last_error). */
+int rd_check_device(void);
+/* Number of kernel launches issued by this library on the calling thread since load
+ * (bench.py's `gpu_launches`). */
+uint64_t rd_launch_count(void);
+
+/* ---- Meta-Kernel -------------------------------------------------------------------------
+ * Replaces MetaKernel.meta_baseline_bias, rangedet/symbol/backbone/meta_kernel.py:166-240
+ * (two mx.sym.im2col + two 1x1 Convolution + broadcast_minus + elemwise mul, all MXNet):
+ *   out[b, c*9+k, h, w] = data[b,c,h+dy,w+dx] * (W1 . relu(W0 . rel + b0) + b1)[c]
+ *   rel = coord[b,:,h+dy,w+dx] (0 outside the image) - coord[b,:,h,w],  k = ky*3+kx
+ * data (B,C,H,W)  coord (B,3,H,W)  w0 (32,3)  b0 (32)  w1 (C,32)  b1 (C)  out (B,9C,H,W)
+ * C must be a multiple of 8, <= 128.  impl: 0 = default, 1 = CUDA-core fp32, 2 = tcgen05.
+ */
+int rd_meta_kernel_fwd(const float* data, const float* coord, const float* w0, const float* b0,
+                       const float* w1, const float* b1, float* out,
+                       int B, int C, int H, int W, int impl, rd_stream_t stream);
+
+/* Backward of the same op w.r.t. data and the four MLP parameters (coord is a graph input with
+ * grad_req null, rangedet/symbol/head/builder.py:20-37).  grad_* are overwritten (kWriteTo). */
+size_t rd_meta_kernel_bwd_workspace_bytes(int B, int C, int H, int W);
+int rd_meta_kernel_bwd(const float* grad_out, const float* data, const float* coord,
+                       const float* w0, const float* b0, const float* w1, const float* b1,
+                       float* grad_data, float* grad_w0, float* grad_b0, float* grad_w1,
+                       float* grad_b1, void* workspace, size_t workspace_bytes,
+                       int B, int C, int H, int W, int impl, rd_stream_t stream);
+
+/* ---- Decode3DBbox ------------------------------------------------------------------------
+ * Replaces _contrib_Decode3DBbox: Decode3DBboxForward, operator_cxx/contrib/
+ * decode_3d_bbox-inl.h:279-305 (functors :169-277 and, is_bin, :64-167).
+ * delta (n_total, is_bin?7:8)  pc (n_total,3)  out (n_total,10); n_total = B*N.
+ */
+int rd_decode_3d_bbox(const float* delta, const float* pc, float* out, int64_t n_total,
+                      int is_bin, rd_stream_t stream);
+
+/* ---- RotatedIOU --------------------------------------------------------------------------
+ * Replaces _contrib_RotatedIOU: RotatedIOUForward, operator_cxx/contrib/rotated_iou-inl.h:525-547.
+ * boxes1 (n1,T) boxes2 (n2,T) -> ious (n1,n2);  T = box_type in {5,7,8}.
+ */
+int rd_rotated_iou(const float* boxes1, const float* boxes2, float* ious, int64_t n1, int64_t n2,
+                   int box_type, rd_stream_t stream);
+
+/* Replaces the Python CustomOp 'batch_rotated_iou' (operator_py/batch_rotated_iou.py:11-49):
+ * per image RotatedIOU(proposal[:, :8], gt) -> NaN/inf/>1/<0 -> 0 -> max over GT, fused.
+ * proposal (B,N,10)  gt (B,G,8) [iou_type 0 = 'bev'] or (B,G,7) [1 = '3d']  out (B,N).
+ */
+int rd_batch_rotated_iou_max(const float* proposal, const float* gt, float* out, int B, int64_t N,
+                             int G, int iou_type, rd_stream_t stream);
+
+/* ---- weighted NMS ------------------------------------------------------------------------
+ * Replaces processing_cxx.wnms_4c: point4_wnms_4c / trtplus::wnms_4c,
+ * operator_cxx/src_cxx/nms.h:781-794, :452-577.
+ * dets (n,12) [8 BEV corner coords, yaw, z0, h, score] -> out_dets (K,12), keep_inds (K) indices
+ * into the INPUT array, in descending-score order.  *out_count (HOST int) = K.  Synchronises the
+ * stream before returning (K is data dependent).  out_dets / keep_inds must hold n rows.
+ */
+size_t rd_wnms_4c_workspace_bytes(int n);
+int rd_wnms_4c(const float* dets, int n, float thresh, float thresh_vote, int is_3d,
+               int hash_scale, float* out_dets, int32_t* keep_inds, int* out_count,
+               void* workspace, size_t workspace_bytes, rd_stream_t stream);
+
+/* ---- tcgen05 self-test -------------------------------------------------------------------
+ * D(128 x n) = A(128 x k) . B(n x k)^T with bf16 operands staged in shared memory in the
+ * canonical no-swizzle K-major core-matrix layout, tcgen05.mma into TMEM, tcgen05.ld back.
+ * Used by tests to validate the descriptor encodings the fused kernels rely on.
+ * a (128,k) b (n,k) fp32 (rounded to bf16 inside), d (128,n) fp32; k % 16 == 0, k <= 128,
+ * n % 16 == 0, 16 <= n <= 256.
+ */
+int rd_tc_probe_gemm(const float* a, const float* b, float* d, int n, int k, rd_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RANGEDET_B200_H_ */

@@ -1,0 +1,228 @@
+// Meta-Kernel forward, impl 2: fused kernel with the 32->64 MLP layer on tcgen05 tensor cores.
+//
+// Replaces MetaKernel.meta_baseline_bias (/root/reference rangedet/symbol/backbone/
+// meta_kernel.py:166-240).  Per CTA: one image row x 128 pixels.  Per tap k (9 of them):
+//   A  (CUDA cores) relative xyz -> hidden = relu(W0 rel + b0) in fp32 (K=3: not worth an MMA),
+//      split into bf16 hi + lo and written to shared memory in the canonical K-major layout
+//   MMA (1 thread)  D[128 px x 64 ch] = [h_hi|h_lo] x [W1_hi|W1_lo]^T (all four cross terms,
+//      K = 8 x 16) + 1 x [b1_hi,b1_lo] (bias as a 9th K-slice), fp32 accumulate in TMEM.
+//      The hi/lo split keeps the result within ~2^-16 of the fp32 product, far inside the 1e-3
+//      parity tolerance, while using the bf16 tensor pipe.
+//   epilogue (all threads) tcgen05.ld the pixel's 64 weights, multiply by the neighbour's
+//      feature value, store the 64 output planes of this tap (128 B coalesced per warp store).
+// Two A buffers and two 64-column TMEM accumulators pipeline tap k's MMA under tap k-1's epilogue;
+// four CTAs per SM (4 x 128 TMEM columns = 512) hide the remaining latencies.
+#include "../../include/rangedet_b200.h"
+#include "rd_common.cuh"
+#include "tc_common.cuh"
+
+namespace mktc {
+
+constexpr int HID = 32, CCH = 3, C = 64;
+constexpr int TW = 128, NT = 128, ROW = TW + 2;
+constexpr int A_CHUNK = TW * 16;      // bytes of one 16-byte K-chunk over all 128 rows
+constexpr int A_BYTES = 8 * A_CHUNK;  // [h_hi(4 chunks) | h_lo(4 chunks)]
+constexpr int B_CHUNK = C * 16;
+constexpr int B_BYTES = 10 * B_CHUNK;  // W1_hi(4) | W1_lo(4) | bias chunk | zero chunk
+constexpr int ONES_BYTES = 2 * A_CHUNK;
+constexpr uint32_t TMEM_COLS = 128;    // two accumulators of 64 fp32 columns
+
+struct Smem {
+  alignas(128) unsigned char a[2][A_BYTES];
+  alignas(128) unsigned char bw[B_BYTES];
+  alignas(128) unsigned char ones[ONES_BYTES];
+  alignas(16) float4 w0b[HID];
+  alignas(16) float cs[3 * CCH * ROW];
+  alignas(8) uint64_t mbar[2];
+  uint32_t tmem_slot;
+};
+
+__global__ void __launch_bounds__(NT, 4)
+meta_fwd_tc_kernel(const float* __restrict__ data, const float* __restrict__ coord,
+                   const float* __restrict__ w0, const float* __restrict__ b0,
+                   const float* __restrict__ w1, const float* __restrict__ b1, float* __restrict__ out,
+                   int B, int H, int W, int tiles_w, int ntiles) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  Smem& S = *reinterpret_cast<Smem*>(smem_raw);
+  const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+  const int64_t plane = (int64_t)H * W;
+
+  // ---- one-time setup ----------------------------------------------------------------------
+  if (t == 0) {
+    tc::mbar_init(&S.mbar[0], 1);
+    tc::mbar_init(&S.mbar[1], 1);
+    tc::fence_mbar_init();
+  }
+  if (warp == 0) {
+    tc::tmem_alloc(&S.tmem_slot, TMEM_COLS);
+    tc::tmem_relinquish();
+  }
+  for (int j = t; j < HID; j += NT)
+    S.w0b[j] = make_float4(__ldg(w0 + j * 3 + 0), __ldg(w0 + j * 3 + 1), __ldg(w0 + j * 3 + 2), __ldg(b0 + j));
+  // W1 (C x 32) -> hi/lo chunks: chunk q (0..3) holds k = 8q..8q+7 of row c at  q*B_CHUNK + c*16
+  for (int e = t; e < C * 4; e += NT) {
+    const int c = e % C, q = e / C;
+    uint32_t hi[4], lo[4];
+#pragma unroll
+    for (int p = 0; p < 4; ++p) {
+      const float x0 = __ldg(w1 + c * HID + q * 8 + 2 * p), x1 = __ldg(w1 + c * HID + q * 8 + 2 * p + 1);
+      float h0, l0, h1, l1;
+      tc::split_bf16(x0, h0, l0);
+      tc::split_bf16(x1, h1, l1);
+      hi[p] = tc::pack_bf16x2(h0, h1);
+      lo[p] = tc::pack_bf16x2(l0, l1);
+    }
+    *reinterpret_cast<uint4*>(S.bw + q * B_CHUNK + c * 16) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+    *reinterpret_cast<uint4*>(S.bw + (4 + q) * B_CHUNK + c * 16) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+  }
+  for (int c = t; c < C; c += NT) {  // bias K-slice: [b1_hi, b1_lo, 0...] | zeros
+    float h, l;
+    tc::split_bf16(__ldg(b1 + c), h, l);
+    *reinterpret_cast<uint4*>(S.bw + 8 * B_CHUNK + c * 16) = make_uint4(tc::pack_bf16x2(h, l), 0u, 0u, 0u);
+    *reinterpret_cast<uint4*>(S.bw + 9 * B_CHUNK + c * 16) = make_uint4(0u, 0u, 0u, 0u);
+  }
+  {  // matching A K-slice: [1, 1, 0...] | zeros   (row = thread)
+    *reinterpret_cast<uint4*>(S.ones + t * 16) = make_uint4(tc::pack_bf16x2(1.f, 1.f), 0u, 0u, 0u);
+    *reinterpret_cast<uint4*>(S.ones + A_CHUNK + t * 16) = make_uint4(0u, 0u, 0u, 0u);
+  }
+  tc::fence_proxy_async_smem();
+  tc::tc_fence_before();
+  __syncthreads();
+  tc::tc_fence_after();
+  const uint32_t tmem_base = S.tmem_slot;
+  const uint32_t idesc = tc::make_idesc_bf16(128, C);
+  const uint32_t a_base0 = tc::smem_u32(S.a[0]), a_base1 = tc::smem_u32(S.a[1]);
+  const uint32_t b_base = tc::smem_u32(S.bw), ones_base = tc::smem_u32(S.ones);
+  const uint32_t lane_sel = (uint32_t)(warp * 32) << 16;
+
+  uint32_t g_base = 0;  // taps issued so far by this CTA (slot = g & 1, mbarrier parity = (g >> 1) & 1)
+  for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const int wt = tile % tiles_w;
+    const int h = (tile / tiles_w) % H;
+    const int b = tile / (tiles_w * H);
+    const int w0px = wt * TW;
+    const int w = w0px + t;
+    // coordinate tile with zero halo (all readers of the previous tile passed a barrier)
+    for (int e = t; e < 3 * CCH * ROW; e += NT) {
+      const int col = e % ROW, d = (e / ROW) % CCH, r = e / (ROW * CCH);
+      const int hh = h + r - 1, ww = w0px + col - 1;
+      float v = 0.f;
+      if (hh >= 0 && hh < H && ww >= 0 && ww < W) v = __ldg(coord + (((int64_t)b * CCH + d) * H + hh) * W + ww);
+      S.cs[(r * CCH + d) * ROW + col] = v;
+    }
+    __syncthreads();
+    const float c0 = S.cs[(1 * CCH + 0) * ROW + t + 1];
+    const float c1 = S.cs[(1 * CCH + 1) * ROW + t + 1];
+    const float c2 = S.cs[(1 * CCH + 2) * ROW + t + 1];
+
+    for (int k = 0; k <= 9; ++k) {
+      const uint32_t g = g_base + (uint32_t)k;
+      if (k < 9) {  // ---- phase A: hidden activations of tap k for this thread's pixel
+        const int dy = k / 3 - 1, dx = k % 3 - 1;
+        const int col = t + 1 + dx, r = dy + 1;
+        const float r0 = S.cs[(r * CCH + 0) * ROW + col] - c0;
+        const float r1 = S.cs[(r * CCH + 1) * ROW + col] - c1;
+        const float r2 = S.cs[(r * CCH + 2) * ROW + col] - c2;
+        unsigned char* abuf = S.a[g & 1];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          uint32_t hi[4], lo[4];
+#pragma unroll
+          for (int p = 0; p < 4; ++p) {
+            float hv[2], hh[2], hl[2];
+#pragma unroll
+            for (int u = 0; u < 2; ++u) {
+              const float4 wv = S.w0b[q * 8 + 2 * p + u];
+              float z = wv.w;
+              z = fmaf(wv.x, r0, z);
+              z = fmaf(wv.y, r1, z);
+              z = fmaf(wv.z, r2, z);
+              hv[u] = fmaxf(z, 0.f);
+              tc::split_bf16(hv[u], hh[u], hl[u]);
+            }
+            hi[p] = tc::pack_bf16x2(hh[0], hh[1]);
+            lo[p] = tc::pack_bf16x2(hl[0], hl[1]);
+          }
+          *reinterpret_cast<uint4*>(abuf + q * A_CHUNK + t * 16) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+          *reinterpret_cast<uint4*>(abuf + (4 + q) * A_CHUNK + t * 16) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+        }
+        tc::fence_proxy_async_smem();
+      }
+      tc::tc_fence_before();
+      __syncthreads();
+      if (k < 9 && t == 0) {  // ---- MMA issue for tap k
+        tc::tc_fence_after();
+        const uint32_t d_tmem = tmem_base + (g & 1) * C;
+        const uint32_t ab = (g & 1) ? a_base1 : a_base0;
+        uint32_t accum = 0;
+#pragma unroll
+        for (int bp = 0; bp < 2; ++bp)
+#pragma unroll
+          for (int ap = 0; ap < 2; ++ap)
+#pragma unroll
+            for (int ks = 0; ks < 2; ++ks) {
+              const uint64_t ad = tc::make_smem_desc(ab + (ap * 4 + ks * 2) * A_CHUNK, A_CHUNK, 128, tc::LAYOUT_NONE);
+              const uint64_t bd = tc::make_smem_desc(b_base + (bp * 4 + ks * 2) * B_CHUNK, B_CHUNK, 128, tc::LAYOUT_NONE);
+              tc::mma_bf16_ss(d_tmem, ad, bd, idesc, accum);
+              accum = 1;
+            }
+        {
+          const uint64_t ad = tc::make_smem_desc(ones_base, A_CHUNK, 128, tc::LAYOUT_NONE);
+          const uint64_t bd = tc::make_smem_desc(b_base + 8 * B_CHUNK, B_CHUNK, 128, tc::LAYOUT_NONE);
+          tc::mma_bf16_ss(d_tmem, ad, bd, idesc, 1u);
+        }
+        tc::umma_commit(&S.mbar[g & 1]);
+      }
+      if (k >= 1) {  // ---- epilogue of tap k-1
+        const uint32_t ge = g - 1;
+        const int kk = k - 1;
+        const int dy = kk / 3 - 1, dx = kk % 3 - 1;
+        const int nh = h + dy, nw = w + dx;
+        const bool ld_ok = w < W && nh >= 0 && nh < H && nw >= 0 && nw < W;
+        const float* dptr = data + (int64_t)b * C * plane + (int64_t)nh * W + nw;
+        float* optr = out + ((int64_t)b * C * 9 + kk) * plane + (int64_t)h * W + w;
+        tc::mbar_wait(&S.mbar[ge & 1], (ge >> 1) & 1);
+        __syncwarp();
+        tc::tc_fence_after();
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+          float dv[32];
+#pragma unroll
+          for (int i = 0; i < 32; ++i) dv[i] = ld_ok ? __ldg(dptr + (int64_t)(half * 32 + i) * plane) : 0.f;
+          float v[32];
+          tc::tmem_ld_x32(tmem_base + lane_sel + (ge & 1) * C + half * 32, v);
+          if (w < W) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) __stcs(optr + (int64_t)(half * 32 + i) * 9 * plane, dv[i] * v[i]);
+          }
+        }
+      }
+    }
+    g_base += 9;
+  }
+  tc::tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tc::tmem_dealloc(tmem_base, TMEM_COLS);
+  (void)lane;
+}
+
+}  // namespace mktc
+
+int rd_meta_kernel_fwd_tc(const float* data, const float* coord, const float* w0, const float* b0,
+                          const float* w1, const float* b1, float* out, int B, int C, int H, int W,
+                          cudaStream_t stream) {
+  RD_REQUIRE(C == mktc::C, "rd_meta_kernel_fwd(impl=2): tcgen05 path is specialised for C == 64 (got %d)", C);
+  const int tiles_w = (W + mktc::TW - 1) / mktc::TW;
+  const int64_t ntiles = (int64_t)B * H * tiles_w;
+  RD_REQUIRE(ntiles <= 0x7fffffffLL, "rd_meta_kernel_fwd: too many tiles");
+  int dev = 0, sms = 0;
+  RD_CUDA(cudaGetDevice(&dev));
+  RD_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  const size_t smem = sizeof(mktc::Smem) + 128;
+  RD_CUDA(cudaFuncSetAttribute(mktc::meta_fwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const int64_t grid = ntiles < (int64_t)sms * 4 ? ntiles : (int64_t)sms * 4;
+  mktc::meta_fwd_tc_kernel<<<(unsigned)grid, mktc::NT, smem, stream>>>(data, coord, w0, b0, w1, b1, out, B, H,
+                                                                        W, tiles_w, (int)ntiles);
+  rd::count_launch();
+  return rd::check_launch("rd_meta_kernel_fwd(tcgen05)");
+}

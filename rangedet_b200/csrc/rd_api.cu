@@ -1,0 +1,62 @@
+// Library-level entry points of librangedet_b200.so (see include/rangedet_b200.h).
+#include <stdarg.h>
+#include <string.h>
+
+#include "../../include/rangedet_b200.h"
+#include "rd_common.cuh"
+
+namespace rd {
+
+static thread_local char g_err[512] = "";
+static thread_local uint64_t g_launches = 0;
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+void count_launch(int n) { g_launches += (uint64_t)n; }
+
+int check_launch(const char* what) {
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) {
+    set_error("%s: launch failed: %s", what, cudaGetErrorString(e));
+    return 1;
+  }
+  return 0;
+}
+
+}  // namespace rd
+
+extern "C" {
+
+int rd_version(void) { return 1; }
+
+const char* rd_last_error(void) { return rd::g_err; }
+
+uint64_t rd_launch_count(void) { return rd::g_launches; }
+
+int rd_check_device(void) {
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) {
+    rd::set_error("no CUDA device: %s (librangedet_b200 has no CPU fallback)", cudaGetErrorString(e));
+    cudaGetLastError();
+    return 1;
+  }
+  cudaDeviceProp p;
+  e = cudaGetDeviceProperties(&p, dev);
+  if (e != cudaSuccess) {
+    rd::set_error("cudaGetDeviceProperties: %s", cudaGetErrorString(e));
+    return 1;
+  }
+  if (p.major != 10) {
+    rd::set_error("device %d is sm_%d%d; this library is built for sm_100a only", dev, p.major, p.minor);
+    return 1;
+  }
+  return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,134 @@
+"""Synthetic inputs with the shapes / statistics of the reference's data path.
+
+Pure numpy; shared by tests/ and bench.py.  Layout sources in the reference:
+  * range image 64x2650 padded to 2656, normalised coords: config/rangedet/
+    rangedet_veh_wo_aug_4_18e.py:38,42,257-267 and rangedet/core/input.py:200-213,522-544
+  * 10-dim decoded box  [Ax,Ay,Bx,By,Cx,Cy,Dx,Dy,z0,z1]: operator_cxx/contrib/decode_3d_bbox-inl.h:244-274
+  * 12-dim wNMS det     [8 corners, yaw, z0, h, score]:   tools/test.py:56-81,209
+  * fixed-length GT padding [0,0,0,e,e,e,e,0], e=1e-3:     rangedet/core/input.py:264-265
+"""
+import numpy as np
+
+H_RANGE = 64
+W_RANGE = 2650
+W_PADDED = 2656
+
+
+def range_image_coords(batch, seed=0, h=H_RANGE, w=W_RANGE, w_pad=W_PADDED, missing=0.10):
+    """(B,3,h,w_pad) float32 normalised xyz of a synthetic LiDAR sweep; columns w..w_pad-1 zero."""
+    rng = np.random.default_rng(seed)
+    incl = np.linspace(-0.31, 0.04, h, dtype=np.float64)[:, None]
+    azim = np.linspace(np.pi, -np.pi, w, dtype=np.float64)[None, :]
+    out = np.zeros((batch, 3, h, w_pad), np.float32)
+    for b in range(batch):
+        r = rng.uniform(2.0, 75.0, size=(h, w))
+        x = r * np.cos(incl) * np.cos(azim)
+        y = r * np.cos(incl) * np.sin(azim)
+        z = r * np.sin(incl)
+        # per-axis mean / std of the order used by NormData (config :257-267)
+        xyz = np.stack([(x - 0.0) / 25.0, (y - 0.0) / 25.0, (z - 1.0) / 2.0], 0)
+        hole = rng.uniform(size=(h, w)) < missing
+        xyz[:, hole] = 0.0
+        out[b, :, :, :w] = xyz.astype(np.float32)
+    return out
+
+
+def feature_map(batch, channels, seed=1, h=H_RANGE, w=W_RANGE, w_pad=W_PADDED):
+    rng = np.random.default_rng(seed)
+    out = np.zeros((batch, channels, h, w_pad), np.float32)
+    out[..., :w] = rng.standard_normal((batch, channels, h, w), dtype=np.float32)
+    return out
+
+
+def meta_mlp_params(seed=2, coord_channels=3, hidden=32, out_channels=64):
+    """Xavier(in, gaussian, 2) like tools/train.py:198; biases small non-zero so they are exercised."""
+    rng = np.random.default_rng(seed)
+    w0 = (rng.standard_normal((hidden, coord_channels)) * np.sqrt(2.0 / coord_channels)).astype(np.float32)
+    b0 = (rng.standard_normal(hidden) * 0.1).astype(np.float32)
+    w1 = (rng.standard_normal((out_channels, hidden)) * np.sqrt(2.0 / hidden)).astype(np.float32)
+    b1 = (rng.standard_normal(out_channels) * 0.1).astype(np.float32)
+    return w0, b0, w1, b1
+
+
+def boxes7(n, seed=0, clustered=False):
+    """(n,7) float32 [cx,cy,cz,l,w,h,yaw] vehicles."""
+    rng = np.random.default_rng(seed)
+    if not clustered:
+        cx = rng.uniform(-75, 75, n)
+        cy = rng.uniform(-75, 75, n)
+        yaw = rng.uniform(-np.pi, np.pi, n)
+    else:
+        per = 50
+        nc = (n + per - 1) // per
+        ccx = np.repeat(rng.uniform(-75, 75, nc), per)[:n]
+        ccy = np.repeat(rng.uniform(-75, 75, nc), per)[:n]
+        cyaw = np.repeat(rng.uniform(-np.pi, np.pi, nc), per)[:n]
+        cx = ccx + rng.normal(0, 0.3, n)
+        cy = ccy + rng.normal(0, 0.3, n)
+        yaw = cyaw + rng.normal(0, 0.1, n)
+    cz = rng.uniform(-1, 2, n)
+    l = rng.uniform(3.5, 5.5, n)
+    w = rng.uniform(1.6, 2.2, n)
+    h = rng.uniform(1.4, 2.0, n)
+    return np.stack([cx, cy, cz, l, w, h, yaw], 1).astype(np.float32)
+
+
+def boxes7_to_corners10(b7):
+    """[cx,cy,cz,l,w,h,yaw] -> 10-dim corner box with the decode convention (A,B,C,D, z0, z1)."""
+    b7 = np.asarray(b7, np.float32)
+    cx, cy, cz, l, w, h, yaw = [b7[:, i] for i in range(7)]
+    s, c = np.sin(yaw), np.cos(yaw)
+    out = np.empty((b7.shape[0], 10), np.float32)
+    for k, (sx, sy) in enumerate([(0.5, -0.5), (-0.5, -0.5), (-0.5, 0.5), (0.5, 0.5)]):
+        x, y = sx * l, sy * w
+        out[:, 2 * k] = x * c - y * s + cx
+        out[:, 2 * k + 1] = x * s + y * c + cy
+    out[:, 8] = cz - h / 2
+    out[:, 9] = out[:, 8] + h
+    return out
+
+
+def corners10_to_dets12(c10, scores):
+    """tools/test.py:56-81 (10 -> 11 dims) + score column (:209)."""
+    c10 = np.asarray(c10, np.float32)
+    yaw = np.arctan2(c10[:, 1] - c10[:, 3], c10[:, 0] - c10[:, 2]).astype(np.float32)
+    return np.concatenate([c10[:, :8], yaw[:, None], c10[:, 8:9], (c10[:, 9:10] - c10[:, 8:9]),
+                           np.asarray(scores, np.float32)[:, None]], 1).astype(np.float32)
+
+
+def distinct_scores(n, seed=0):
+    """Random permutation of {1..n}/n: all distinct (nms.h:791 uses an unstable sort)."""
+    rng = np.random.default_rng(seed + 7919)
+    return (rng.permutation(n).astype(np.float64) + 1.0).astype(np.float32) / np.float32(n)
+
+
+def wnms_dets(n, seed=0, clustered=True):
+    return corners10_to_dets12(boxes7_to_corners10(boxes7(n, seed, clustered)), distinct_scores(n, seed))
+
+
+def gt_boxes8(batch, n_real=50, n_total=200, seed=3):
+    """(B,200,8) BEV corner GT, first n_real real, rest padded per input.py:264-265."""
+    out = np.zeros((batch, n_total, 8), np.float32)
+    eps = np.float32(1e-3)
+    out[:, :, 3:7] = eps
+    for b in range(batch):
+        out[b, :n_real] = boxes7_to_corners10(boxes7(n_real, seed + b))[:, :8]
+    return out
+
+
+def decode_inputs(batch, n, seed=4):
+    """bbox_deltas (B,N,8) + pc_laser_frame (B,N,3) in the value ranges the head produces."""
+    rng = np.random.default_rng(seed)
+    delta = np.empty((batch, n, 8), np.float32)
+    delta[..., 0:2] = rng.normal(0, 1.2, (batch, n, 2))
+    delta[..., 2] = rng.normal(np.log(1.9), 0.15, (batch, n))
+    delta[..., 3] = rng.normal(np.log(4.5), 0.15, (batch, n))
+    ang = rng.uniform(-np.pi, np.pi, (batch, n))
+    delta[..., 4] = np.cos(ang)
+    delta[..., 5] = np.sin(ang)
+    delta[..., 6] = rng.uniform(-2, 1, (batch, n))
+    delta[..., 7] = rng.normal(np.log(1.7), 0.1, (batch, n))
+    r = rng.uniform(2, 75, (batch, n))
+    az = rng.uniform(-np.pi, np.pi, (batch, n))
+    pc = np.stack([r * np.cos(az), r * np.sin(az), rng.uniform(-2, 3, (batch, n))], -1).astype(np.float32)
+    return delta, pc
