@@ -1,0 +1,347 @@
+#!/usr/bin/env python
+"""bench.py -- RangeDet hot-path benchmark (BASELINE.json configs[1]).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--mk-impl 0|1|2]
+
+A "step" is one pass of the Meta-Kernel hot path over one batch of synthetic range images:
+forward + backward (grad w.r.t. features and the four MLP parameters) of
+MetaKernel.meta_baseline_bias at B=4 frames per GPU, C=64, 64x2650 padded to 2656, fp32
+(SURVEY.md 8d cfg-2).  N>1 (launched by torchrun, one rank per GPU): frames are sharded across ranks
+(weak scaling, no data-path collective); the only exchange is the data-parallel all-reduce of the
+MLP parameter gradients over NCCL, as in the reference's Horovod loop (tools/train.py:364-368).
+
+Printed JSON line: see the task contract.  `value` = whole-job frames/s with inputs resident in
+HBM; `e2e` = same metric through the C-ABI with HOST (pinned) buffers, H2D/D2H copies timed;
+`roofline` = dominant kernel vs measured HBM peak; `cpu_baseline` = the CPU oracle port (torch
+fp32 restatement; the reference's own CPU path is MXNet, not installable here) on a bounded sample.
+
+--impl reference: times that CPU restatement on all host cores (rank 0 only).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "range-image frames/s (fwd+bwd, 64x2650)"
+UNIT = "frames/s"
+B_PER_GPU, C, H, W, W_PAD = 4, 64, 64, 2650, 2656
+WORKLOAD = "meta_kernel_fwd_bwd cfg-2: B=4/GPU, C=64, 64x2650 (padded 2656), fp32, NCHW"
+# algorithmic HBM bytes per pixel at the op boundary (DESIGN.md "Meta-Kernel")
+BYTES_FWD = 64 * 4 + 3 * 4 + 576 * 4          # 2572
+BYTES_BWD_DATA = 576 * 4 + 3 * 4 + 64 * 4      # grad_out + coord -> grad_data            2572
+BYTES_BWD_PARAM = 576 * 4 + 64 * 4 + 3 * 4     # grad_out + data + coord -> (tiny) grads   2572
+PIXELS_PER_FRAME = H * W_PAD                   # counted on the padded grid the kernels process
+
+
+def measured_peak_gbs():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index = index
+        self.samples = []
+        self.stop_flag = False
+        self.proc = None
+
+    def run(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
+                 "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            for line in self.proc.stdout:
+                if self.stop_flag:
+                    break
+                self.samples.append([x.strip() for x in line.split(",")])
+        except Exception:
+            pass
+
+    def finish(self):
+        self.stop_flag = True
+        if self.proc is not None:
+            try:
+                self.proc.terminate()
+            except Exception:
+                pass
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for s in self.samples:
+            try:
+                sm.append(float(s[0]))
+                mx.append(float(s[1]))
+                for n, v in zip(names, s[2:6]):
+                    if v.lower().startswith("active"):
+                        reasons.add(n)
+            except Exception:
+                continue
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def cpu_oracle_fwd_bwd(frames, reps, threads=None):
+    """The CPU port (oracle/meta_kernel_ref.py) on `frames` frames; returns (frames/s, threads)."""
+    import torch
+    from oracle import meta_kernel_ref
+    from rangedet_b200 import synth
+    if threads:
+        torch.set_num_threads(threads)
+    t = [torch.from_numpy(x) for x in (synth.feature_map(frames, C, seed=1), synth.range_image_coords(frames, seed=0))]
+    ps = [torch.from_numpy(p) for p in synth.meta_mlp_params(seed=2)]
+    go = torch.randn(frames, 9 * C, H, W_PAD)
+    best = None
+    for _ in range(reps):
+        t0 = time.perf_counter()
+        meta_kernel_ref.meta_baseline_bias_fwd_bwd(t[0], t[1], *ps, go)
+        dt = time.perf_counter() - t0
+        best = dt if best is None else min(best, dt)
+    return frames / best, torch.get_num_threads()
+
+
+def run_reference(args, rank, world):
+    if rank != 0:
+        return
+    import torch
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    cpu_oracle_fwd_bwd(1, 1)  # one warm-up pass is enough on CPU (first call pays allocator start-up)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        cpu_oracle_fwd_bwd(1, 1)
+    dt = time.perf_counter() - t0
+    val = args.steps * 1.0 / dt
+    sample = "each step = 1 frame (of the B=4 batch) fwd+bwd, torch fp32 CPU restatement of meta_kernel.py:166-240"
+    line = {
+        "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "note": "reference CPU path is MXNet (not installable here, no network); "
+                   "timed: op-for-op torch CPU port on all host cores"},
+        "cpu_baseline": {"value": val, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port", "sample": sample},
+        "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def run_ours(args, rank, local_rank, world):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    from rangedet_b200 import _lib, ops, synth
+
+    assert torch.cuda.is_available(), "bench.py (impl ours) needs a CUDA device: there is no CPU fallback"
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    impl = args.mk_impl
+    B = B_PER_GPU
+    # synthetic inputs, resident in HBM (different frames per rank)
+    data = torch.from_numpy(synth.feature_map(B, C, seed=100 + rank)).to(dev)
+    coord = torch.from_numpy(synth.range_image_coords(B, seed=200 + rank)).to(dev)
+    w0, b0, w1, b1 = [torch.from_numpy(p).to(dev) for p in synth.meta_mlp_params(seed=2)]
+    gen = torch.Generator(device=dev).manual_seed(300 + rank)
+    grad_out = torch.randn((B, 9 * C, H, W_PAD), device=dev, generator=gen)
+    flat_grads = torch.empty(32 * 3 + 32 + C * 32 + C, device=dev)
+
+    def step():
+        out = ops.meta_kernel_forward(data, coord, w0, b0, w1, b1, impl=impl)
+        gd, gw0, gb0, gw1, gb1 = ops.meta_kernel_backward(grad_out, data, coord, w0, b0, w1, b1, impl=impl)
+        if world > 1:  # data-parallel exchange: average the MLP parameter gradients
+            torch.cat([gw0.reshape(-1), gb0, gw1.reshape(-1), gb1], out=flat_grads)
+            dist.all_reduce(flat_grads, op=dist.ReduceOp.SUM)
+            flat_grads.div_(world)
+        return out, gd
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+        time.sleep(0.15)
+    launches0 = _lib.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for _ in range(args.steps):
+        step()
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    launches = _lib.launch_count() - launches0
+    clocks = sampler.finish() if rank == 0 else None
+    if world > 1:
+        t = torch.tensor([ms], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    value = B * world * args.steps / (ms * 1e-3)
+
+    # ---- per-kernel timing (CUDA events on the launching stream) for the roofline ----------
+    L = _lib.lib()
+    out = torch.empty((B, 9 * C, H, W_PAD), device=dev)
+    gd = torch.empty_like(data)
+    gws = [torch.empty(32 * 3, device=dev), torch.empty(32, device=dev), torch.empty(C * 32, device=dev),
+           torch.empty(C, device=dev)]
+    ws = torch.empty(int(L.rd_meta_kernel_bwd_workspace_bytes(B, C, H, W_PAD)) // 4 + 1, device=dev)
+    P, S = ops._p, ops._stream
+    import ctypes
+
+    def k_fwd():
+        _lib.check(L.rd_meta_kernel_fwd(P(data), P(coord), P(w0), P(b0), P(w1), P(b1), P(out), B, C, H, W_PAD, impl, S()), "fwd")
+
+    def k_bwd_data():
+        _lib.check(L.rd_meta_kernel_bwd_data(P(grad_out), P(coord), P(w0), P(b0), P(w1), P(b1), P(gd), B, C, H, W_PAD,
+                                             impl, S()), "bwd_data")
+
+    def k_bwd_param():
+        _lib.check(L.rd_meta_kernel_bwd_params(P(grad_out), P(data), P(coord), P(w0), P(b0), P(w1), P(b1), P(gws[0]),
+                                               P(gws[1]), P(gws[2]), P(gws[3]), P(ws), ctypes.c_size_t(ws.numel() * 4),
+                                               B, C, H, W_PAD, impl, S()), "bwd_params")
+
+    kernels = {}
+    px = B * PIXELS_PER_FRAME
+    for name, fn, bpp in [("meta_fwd", k_fwd, BYTES_FWD), ("meta_bwd_data", k_bwd_data, BYTES_BWD_DATA),
+                          ("meta_bwd_params", k_bwd_param, BYTES_BWD_PARAM)]:
+        reps = max(3, min(args.steps, 10))
+        fn()
+        torch.cuda.synchronize()
+        a, b_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(reps):
+            fn()
+        b_.record()
+        torch.cuda.synchronize()
+        kms = a.elapsed_time(b_) / reps
+        kernels[name] = {"ms": kms, "algorithmic_bytes": px * bpp, "GBps": px * bpp / (kms * 1e-3) / 1e9}
+    peak, peak_src = measured_peak_gbs()
+    dom = max(kernels, key=lambda k: kernels[k]["ms"])
+    roofline = {"bound": "hbm", "kernel": dom, "achieved": kernels[dom]["GBps"], "peak": peak, "unit": "GB/s",
+                "frac": kernels[dom]["GBps"] / peak, "traffic": None, "peak_source": peak_src,
+                "kernels": {k: {"ms": round(v["ms"], 4), "GBps": round(v["GBps"], 1), "frac": round(v["GBps"] / peak, 4)}
+                            for k, v in kernels.items()},
+                "step_algorithmic_GBps": px * (BYTES_FWD + 576 * 4 + 64 * 4 + 12 + 256) / (ms / args.steps * 1e-3) / 1e9}
+    del out, gd, ws
+
+    # ---- e2e: host (pinned) buffers through the public API, copies inside the timed region --
+    e2e = None
+    try:
+        h_data, h_coord = data.cpu().pin_memory(), coord.cpu().pin_memory()
+        h_go = torch.empty((B, 9 * C, H, W_PAD), pin_memory=True)
+        h_go.copy_(grad_out)
+        h_out = torch.empty((B, 9 * C, H, W_PAD), pin_memory=True)
+        h_gd = torch.empty((B, C, H, W_PAD), pin_memory=True)
+        h_gp = torch.empty(flat_grads.numel(), pin_memory=True)
+        h2d = (h_data.numel() + h_coord.numel() + h_go.numel()) * 4
+        d2h = (h_out.numel() + h_gd.numel() + h_gp.numel()) * 4
+
+        def e2e_step():
+            d_ = h_data.to(dev, non_blocking=True)
+            c_ = h_coord.to(dev, non_blocking=True)
+            g_ = h_go.to(dev, non_blocking=True)
+            o_ = ops.meta_kernel_forward(d_, c_, w0, b0, w1, b1, impl=impl)
+            gd_, a_, b__, c__, d__ = ops.meta_kernel_backward(g_, d_, c_, w0, b0, w1, b1, impl=impl)
+            if world > 1:
+                torch.cat([a_.reshape(-1), b__, c__.reshape(-1), d__], out=flat_grads)
+                dist.all_reduce(flat_grads, op=dist.ReduceOp.SUM)
+                flat_grads.div_(world)
+            else:
+                torch.cat([a_.reshape(-1), b__, c__.reshape(-1), d__], out=flat_grads)
+            h_out.copy_(o_, non_blocking=True)
+            h_gd.copy_(gd_, non_blocking=True)
+            h_gp.copy_(flat_grads, non_blocking=True)
+
+        e2e_steps = max(2, min(args.steps, 5))
+        e2e_step()
+        barrier()
+        a, b_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(e2e_steps):
+            e2e_step()
+        b_.record()
+        barrier()
+        ems = a.elapsed_time(b_)
+        if world > 1:
+            t = torch.tensor([ems], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ems = float(t.item())
+        e2e = {"value": B * world * e2e_steps / (ems * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d,
+               "d2h_bytes_per_step": d2h, "steps": e2e_steps,
+               "note": "pinned host data/coord/grad_out -> device, fwd+bwd, out/grad_data/param grads -> pinned host"}
+    except Exception as ex:  # report, never fake
+        e2e = {"value": None, "unit": UNIT, "error": repr(ex)[:200]}
+
+    # ---- CPU baseline (rank 0, N == 1 only): the oracle port on a bounded sample -------------
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        v, th = cpu_oracle_fwd_bwd(1, 2)
+        cpu = {"value": v, "unit": UNIT, "cores": th, "kind": "port",
+               "sample": "1 frame (B=1 of the B=4 batch) fwd+bwd, best of 2, torch fp32 CPU port of meta_kernel.py:166-240 "
+                         "(reference CPU path = MXNet, not installable: no network)"}
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "batch_per_gpu": B, "global_batch": B * world,
+                       "parallelism": "dp%d (frames sharded; NCCL all-reduce of MLP param grads)" % world,
+                       "mk_impl": {0: "default", 1: "cuda-core fp32", 2: "tcgen05"}[impl],
+                       "l2": "inputs larger than L2 (3.5 GB touched per step vs 126 MB L2)"},
+            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "clocks": clocks, "gpu_launches": int(launches),
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--mk-impl", type=int, default=0, choices=[0, 1, 2])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.impl == "reference":
+        if args.steps > 30:
+            args.steps = 30  # keep the CPU arm within minutes
+        run_reference(args, rank, world)
+        return
+    if world == 1 and args.gpus > 1:
+        # convenience: re-launch under torchrun
+        cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(args.gpus),
+               "--master-addr", "127.0.0.1", "--master-port", os.environ.get("MASTER_PORT", "29511"), __file__] + sys.argv[1:]
+        sys.exit(subprocess.call(cmd))
+    run_ours(args, rank, local_rank, world)
+
+
+if __name__ == "__main__":
+    main()

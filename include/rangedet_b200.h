@@ -39,7 +39,7 @@ uint64_t rd_launch_count(void);
  *   out[b, c*9+k, h, w] = data[b,c,h+dy,w+dx] * (W1 . relu(W0 . rel + b0) + b1)[c]
  *   rel = coord[b,:,h+dy,w+dx] (0 outside the image) - coord[b,:,h,w],  k = ky*3+kx
  * data (B,C,H,W)  coord (B,3,H,W)  w0 (32,3)  b0 (32)  w1 (C,32)  b1 (C)  out (B,9C,H,W)
- * C must be a multiple of 8, <= 128.  impl: 0 = default, 1 = CUDA-core fp32, 2 = tcgen05.
+ * C must be a multiple of 8, <= 64.  impl: 0 = default, 1 = CUDA-core fp32, 2 = tcgen05 (C == 64).
  */
 int rd_meta_kernel_fwd(const float* data, const float* coord, const float* w0, const float* b0,
                        const float* w1, const float* b1, float* out,
@@ -53,6 +53,16 @@ int rd_meta_kernel_bwd(const float* grad_out, const float* data, const float* co
                        float* grad_data, float* grad_w0, float* grad_b0, float* grad_w1,
                        float* grad_b1, void* workspace, size_t workspace_bytes,
                        int B, int C, int H, int W, int impl, rd_stream_t stream);
+
+/* The two halves of rd_meta_kernel_bwd, separately callable (grad_req 'null' on either side). */
+int rd_meta_kernel_bwd_data(const float* grad_out, const float* coord, const float* w0,
+                            const float* b0, const float* w1, const float* b1, float* grad_data,
+                            int B, int C, int H, int W, int impl, rd_stream_t stream);
+int rd_meta_kernel_bwd_params(const float* grad_out, const float* data, const float* coord,
+                              const float* w0, const float* b0, const float* w1, const float* b1,
+                              float* grad_w0, float* grad_b0, float* grad_w1, float* grad_b1,
+                              void* workspace, size_t workspace_bytes,
+                              int B, int C, int H, int W, int impl, rd_stream_t stream);
 
 /* ---- Decode3DBbox ------------------------------------------------------------------------
  * Replaces _contrib_Decode3DBbox: Decode3DBboxForward, operator_cxx/contrib/

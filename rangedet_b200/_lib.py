@@ -1,0 +1,66 @@
+"""ctypes binding of librangedet_b200.so (the C-ABI in include/rangedet_b200.h).
+
+There is no CPU or eager-PyTorch fallback: if the library is missing, or a compute entry point
+reports an error, a RuntimeError is raised.
+"""
+import ctypes
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "librangedet_b200.so")
+
+_lib = None
+
+_vp = ctypes.c_void_p
+_i = ctypes.c_int
+_i64 = ctypes.c_int64
+_sz = ctypes.c_size_t
+_f = ctypes.c_float
+
+# name -> (restype, argtypes); mirrors include/rangedet_b200.h one to one
+SIGNATURES = {
+    "rd_version": (_i, []),
+    "rd_last_error": (ctypes.c_char_p, []),
+    "rd_check_device": (_i, []),
+    "rd_launch_count": (ctypes.c_uint64, []),
+    "rd_meta_kernel_fwd": (_i, [_vp] * 7 + [_i] * 5 + [_vp]),
+    "rd_meta_kernel_bwd_workspace_bytes": (_sz, [_i] * 4),
+    "rd_meta_kernel_bwd": (_i, [_vp] * 12 + [_vp, _sz] + [_i] * 5 + [_vp]),
+    "rd_meta_kernel_bwd_data": (_i, [_vp] * 7 + [_i] * 5 + [_vp]),
+    "rd_meta_kernel_bwd_params": (_i, [_vp] * 11 + [_vp, _sz] + [_i] * 5 + [_vp]),
+    "rd_decode_3d_bbox": (_i, [_vp, _vp, _vp, _i64, _i, _vp]),
+    "rd_rotated_iou": (_i, [_vp, _vp, _vp, _i64, _i64, _i, _vp]),
+    "rd_batch_rotated_iou_max": (_i, [_vp, _vp, _vp, _i, _i64, _i, _i, _vp]),
+    "rd_wnms_4c_workspace_bytes": (_sz, [_i]),
+    "rd_wnms_4c": (_i, [_vp, _i, _f, _f, _i, _i, _vp, _vp, ctypes.POINTER(_i), _vp, _sz, _vp]),
+    "rd_tc_probe_gemm": (_i, [_vp, _vp, _vp, _i, _i, _vp]),
+}
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.isfile(LIB_PATH):
+            raise RuntimeError(
+                "rangedet_b200: %s not found. Build it with `python -m rangedet_b200.build` "
+                "(there is no CPU fallback)." % LIB_PATH)
+        L = ctypes.CDLL(LIB_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(L, name)  # AttributeError if the .so lacks a declared symbol
+            fn.restype = res
+            fn.argtypes = args
+        _lib = L
+    return _lib
+
+
+def last_error():
+    return lib().rd_last_error().decode("utf-8", "replace")
+
+
+def check(status, what):
+    if status != 0:
+        raise RuntimeError("rangedet_b200.%s failed: %s" % (what, last_error()))
+
+
+def launch_count():
+    return int(lib().rd_launch_count())

@@ -514,24 +514,40 @@ size_t rd_meta_kernel_bwd_workspace_bytes(int B, int C, int H, int W) {
   return (size_t)mk::P_GRID * 2 * (size_t)(C * mk::HID + C + mk::HID * 4) * sizeof(float);
 }
 
-int rd_meta_kernel_bwd(const float* grad_out, const float* data, const float* coord, const float* w0,
-                       const float* b0, const float* w1, const float* b1, float* grad_data,
-                       float* grad_w0, float* grad_b0, float* grad_w1, float* grad_b1, void* workspace,
-                       size_t workspace_bytes, int B, int C, int H, int W, int impl,
-                       rd_stream_t stream) {
-  RD_REQUIRE(B >= 0 && H > 0 && W > 0, "rd_meta_kernel_bwd: bad shape B=%d H=%d W=%d", B, H, W);
+int rd_meta_kernel_bwd_data(const float* grad_out, const float* coord, const float* w0, const float* b0,
+                            const float* w1, const float* b1, float* grad_data, int B, int C, int H, int W,
+                            int impl, rd_stream_t stream) {
+  RD_REQUIRE(B >= 0 && H > 0 && W > 0, "rd_meta_kernel_bwd_data: bad shape B=%d H=%d W=%d", B, H, W);
   RD_REQUIRE(C > 0 && C % 8 == 0 && C <= mk::MAXC,
-             "rd_meta_kernel_bwd: C must be a multiple of 8 and <= %d (got %d)", mk::MAXC, C);
-  RD_REQUIRE(impl >= 0 && impl <= 2, "rd_meta_kernel_bwd: impl must be 0, 1 or 2");
-  RD_REQUIRE(grad_out && data && coord && w0 && b0 && w1 && b1 && grad_data && grad_w0 && grad_b0 &&
-                 grad_w1 && grad_b1, "rd_meta_kernel_bwd: null pointer");
-  RD_REQUIRE(workspace && workspace_bytes >= rd_meta_kernel_bwd_workspace_bytes(B, C, H, W),
-             "rd_meta_kernel_bwd: workspace too small (%zu < %zu)", workspace_bytes,
-             rd_meta_kernel_bwd_workspace_bytes(B, C, H, W));
+             "rd_meta_kernel_bwd_data: C must be a multiple of 8 and <= %d (got %d)", mk::MAXC, C);
+  RD_REQUIRE(impl >= 0 && impl <= 2, "rd_meta_kernel_bwd_data: impl must be 0, 1 or 2");
+  if (B == 0) return 0;
+  RD_REQUIRE(grad_out && coord && w0 && b0 && w1 && b1 && grad_data, "rd_meta_kernel_bwd_data: null pointer");
   if (rd_check_device()) return 1;
+  const int tiles_w = (W + mk::G_TW - 1) / mk::G_TW;
+  const int64_t ntiles = (int64_t)B * H * tiles_w;
+  RD_REQUIRE(ntiles <= 0x7fffffffLL, "rd_meta_kernel_bwd_data: too many tiles");
+  const size_t smem = sizeof(mk::GdSmem);
+  RD_CUDA(cudaFuncSetAttribute(mk::meta_bwd_data_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  mk::meta_bwd_data_kernel<<<(unsigned)ntiles, mk::NT, smem, rd::as_stream(stream)>>>(
+      grad_out, coord, w0, b0, w1, b1, grad_data, B, C, H, W, tiles_w);
+  rd::count_launch();
+  return rd::check_launch("rd_meta_kernel_bwd_data");
+}
+
+int rd_meta_kernel_bwd_params(const float* grad_out, const float* data, const float* coord, const float* w0,
+                              const float* b0, const float* w1, const float* b1, float* grad_w0,
+                              float* grad_b0, float* grad_w1, float* grad_b1, void* workspace,
+                              size_t workspace_bytes, int B, int C, int H, int W, int impl,
+                              rd_stream_t stream) {
+  (void)b1;
+  RD_REQUIRE(B >= 0 && H > 0 && W > 0, "rd_meta_kernel_bwd_params: bad shape B=%d H=%d W=%d", B, H, W);
+  RD_REQUIRE(C > 0 && C % 8 == 0 && C <= mk::MAXC,
+             "rd_meta_kernel_bwd_params: C must be a multiple of 8 and <= %d (got %d)", mk::MAXC, C);
+  RD_REQUIRE(impl >= 0 && impl <= 2, "rd_meta_kernel_bwd_params: impl must be 0, 1 or 2");
+  RD_REQUIRE(grad_w0 && grad_b0 && grad_w1 && grad_b1, "rd_meta_kernel_bwd_params: null output pointer");
   cudaStream_t st = rd::as_stream(stream);
-  float* partial = static_cast<float*>(workspace);
-  const int nout = C * mk::HID + C + mk::HID * 4;
+  if (rd_check_device()) return 1;
   if (B == 0) {
     RD_CUDA(cudaMemsetAsync(grad_w0, 0, sizeof(float) * mk::HID * 3, st));
     RD_CUDA(cudaMemsetAsync(grad_b0, 0, sizeof(float) * mk::HID, st));
@@ -539,33 +555,37 @@ int rd_meta_kernel_bwd(const float* grad_out, const float* data, const float* co
     RD_CUDA(cudaMemsetAsync(grad_b1, 0, sizeof(float) * C, st));
     return 0;
   }
-  {  // grad_data
-    const int tiles_w = (W + mk::G_TW - 1) / mk::G_TW;
-    const int64_t ntiles = (int64_t)B * H * tiles_w;
-    RD_REQUIRE(ntiles <= 0x7fffffffLL, "rd_meta_kernel_bwd: too many tiles");
-    const size_t smem = sizeof(mk::GdSmem);
-    RD_CUDA(cudaFuncSetAttribute(mk::meta_bwd_data_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    mk::meta_bwd_data_kernel<<<(unsigned)ntiles, mk::NT, smem, st>>>(grad_out, coord, w0, b0, w1, b1,
-                                                                      grad_data, B, C, H, W, tiles_w);
-    rd::count_launch();
-    if (rd::check_launch("rd_meta_kernel_bwd(data)")) return 1;
-  }
-  {  // MLP parameter gradients
-    const int tiles_w = (W + mk::P_TW - 1) / mk::P_TW;
-    const int64_t ntiles = (int64_t)B * H * tiles_w;
-    const size_t smem = sizeof(mk::GpSmem);
-    RD_CUDA(cudaFuncSetAttribute(mk::meta_bwd_param_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    RD_CUDA(cudaMemsetAsync(partial, 0, (size_t)mk::P_GRID * 2 * nout * sizeof(float), st));
-    mk::meta_bwd_param_kernel<<<mk::P_GRID, mk::NT, smem, st>>>(grad_out, data, coord, w0, b0, w1, partial,
-                                                                B, C, H, W, tiles_w, (int)ntiles);
-    rd::count_launch();
-    if (rd::check_launch("rd_meta_kernel_bwd(param)")) return 1;
-    mk::meta_bwd_param_reduce_kernel<<<(nout + 255) / 256, 256, 0, st>>>(partial, mk::P_GRID * 2, C, grad_w0,
-                                                                         grad_b0, grad_w1, grad_b1);
-    rd::count_launch();
-    if (rd::check_launch("rd_meta_kernel_bwd(reduce)")) return 1;
-  }
-  return 0;
+  RD_REQUIRE(grad_out && data && coord && w0 && b0 && w1, "rd_meta_kernel_bwd_params: null pointer");
+  RD_REQUIRE(workspace && workspace_bytes >= rd_meta_kernel_bwd_workspace_bytes(B, C, H, W),
+             "rd_meta_kernel_bwd_params: workspace too small (%zu < %zu)", workspace_bytes,
+             rd_meta_kernel_bwd_workspace_bytes(B, C, H, W));
+  float* partial = static_cast<float*>(workspace);
+  const int nout = C * mk::HID + C + mk::HID * 4;
+  const int tiles_w = (W + mk::P_TW - 1) / mk::P_TW;
+  const int64_t ntiles = (int64_t)B * H * tiles_w;
+  RD_REQUIRE(ntiles <= 0x7fffffffLL, "rd_meta_kernel_bwd_params: too many tiles");
+  const size_t smem = sizeof(mk::GpSmem);
+  RD_CUDA(cudaFuncSetAttribute(mk::meta_bwd_param_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  RD_CUDA(cudaMemsetAsync(partial, 0, (size_t)mk::P_GRID * 2 * nout * sizeof(float), st));
+  mk::meta_bwd_param_kernel<<<mk::P_GRID, mk::NT, smem, st>>>(grad_out, data, coord, w0, b0, w1, partial, B, C,
+                                                              H, W, tiles_w, (int)ntiles);
+  rd::count_launch();
+  if (rd::check_launch("rd_meta_kernel_bwd_params")) return 1;
+  mk::meta_bwd_param_reduce_kernel<<<(nout + 255) / 256, 256, 0, st>>>(partial, mk::P_GRID * 2, C, grad_w0,
+                                                                       grad_b0, grad_w1, grad_b1);
+  rd::count_launch();
+  return rd::check_launch("rd_meta_kernel_bwd_params(reduce)");
+}
+
+int rd_meta_kernel_bwd(const float* grad_out, const float* data, const float* coord, const float* w0,
+                       const float* b0, const float* w1, const float* b1, float* grad_data,
+                       float* grad_w0, float* grad_b0, float* grad_w1, float* grad_b1, void* workspace,
+                       size_t workspace_bytes, int B, int C, int H, int W, int impl,
+                       rd_stream_t stream) {
+  RD_REQUIRE(grad_data != nullptr, "rd_meta_kernel_bwd: null grad_data");
+  if (rd_meta_kernel_bwd_data(grad_out, coord, w0, b0, w1, b1, grad_data, B, C, H, W, impl, stream)) return 1;
+  return rd_meta_kernel_bwd_params(grad_out, data, coord, w0, b0, w1, b1, grad_w0, grad_b0, grad_w1, grad_b1,
+                                   workspace, workspace_bytes, B, C, H, W, impl, stream);
 }
 
 }  // extern "C"

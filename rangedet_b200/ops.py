@@ -1,0 +1,189 @@
+"""Host-side operator surface of the RangeDet hot path over torch CUDA tensors.
+
+Each function mirrors one reference operator (same argument meaning, shapes and error behaviour)
+and calls the sm_100a kernels through the C-ABI (include/rangedet_b200.h).  torch is used only for
+device memory and streams.  No function here has a CPU path.
+
+  reference operator                                         here
+  ---------------------------------------------------------  -------------------------------
+  MetaKernel.meta_baseline_bias (meta_kernel.py:166-240)     meta_kernel / MetaKernelFunction
+  mx.sym.contrib.Decode3DBbox   (decode_3d_bbox.cc:15-65)    decode_3d_bbox
+  mx.nd.contrib.RotatedIOU      (rotated_iou.cc:12-60)       rotated_iou
+  Custom op 'batch_rotated_iou' (batch_rotated_iou.py)       batch_rotated_iou
+  processing_cxx.wnms_4c        (pybinding.cpp:8)            rangedet_b200.processing_cxx.wnms_4c
+"""
+import ctypes
+
+import torch
+
+from . import _lib
+
+IMPL_DEFAULT, IMPL_FP32, IMPL_TCGEN05 = 0, 1, 2
+
+
+def _stream():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _p(t):
+    return ctypes.c_void_p(t.data_ptr())
+
+
+def _chk(t, name, ndim=None, last=None):
+    if not isinstance(t, torch.Tensor) or not t.is_cuda:
+        raise RuntimeError("%s must be a CUDA tensor (rangedet_b200 has no CPU fallback)" % name)
+    if t.dtype != torch.float32:
+        raise TypeError("%s must be float32, got %s" % (name, t.dtype))
+    if ndim is not None and t.dim() != ndim:
+        raise ValueError("%s must have %d dims, got shape %s" % (name, ndim, tuple(t.shape)))
+    if last is not None and t.shape[-1] not in (last if isinstance(last, tuple) else (last,)):
+        raise ValueError("%s last dim must be %s, got shape %s" % (name, last, tuple(t.shape)))
+    return t.contiguous()
+
+
+# ------------------------------------------------------------------------------------------------
+# Meta-Kernel
+# ------------------------------------------------------------------------------------------------
+def meta_kernel_forward(data, coord, w0, b0, w1, b1, impl=IMPL_DEFAULT):
+    """(B,C,H,W),(B,3,H,W),(32,3),(32),(C,32),(C) -> (B, 9C, H, W)."""
+    data = _chk(data, "data", 4)
+    coord = _chk(coord, "coord", 4)
+    B, C, H, W = data.shape
+    if tuple(coord.shape) != (B, 3, H, W):
+        raise ValueError("coord must be (B,3,H,W)=%s, got %s" % ((B, 3, H, W), tuple(coord.shape)))
+    w0 = _chk(w0.reshape(w0.shape[0], -1), "w0", 2)
+    w1 = _chk(w1.reshape(w1.shape[0], -1), "w1", 2)
+    b0, b1 = _chk(b0, "b0", 1), _chk(b1, "b1", 1)
+    if tuple(w0.shape) != (32, 3) or b0.shape[0] != 32 or tuple(w1.shape) != (C, 32) or b1.shape[0] != C:
+        raise ValueError("MLP parameter shapes must be w0 (32,3) b0 (32) w1 (C,32) b1 (C)")
+    out = torch.empty((B, 9 * C, H, W), device=data.device, dtype=torch.float32)
+    with torch.cuda.device(data.device):
+        st = _lib.lib().rd_meta_kernel_fwd(_p(data), _p(coord), _p(w0), _p(b0), _p(w1), _p(b1), _p(out),
+                                           B, C, H, W, int(impl), _stream())
+    _lib.check(st, "meta_kernel_forward")
+    return out
+
+
+def meta_kernel_backward(grad_out, data, coord, w0, b0, w1, b1, impl=IMPL_DEFAULT):
+    """-> (grad_data, grad_w0, grad_b0, grad_w1, grad_b1)."""
+    data = _chk(data, "data", 4)
+    coord = _chk(coord, "coord", 4)
+    B, C, H, W = data.shape
+    grad_out = _chk(grad_out, "grad_out", 4)
+    if tuple(grad_out.shape) != (B, 9 * C, H, W):
+        raise ValueError("grad_out must be (B,9C,H,W)")
+    w0 = _chk(w0.reshape(w0.shape[0], -1), "w0", 2)
+    w1 = _chk(w1.reshape(w1.shape[0], -1), "w1", 2)
+    b0, b1 = _chk(b0, "b0", 1), _chk(b1, "b1", 1)
+    L = _lib.lib()
+    dev = data.device
+    gd = torch.empty_like(data)
+    gw0, gb0 = torch.empty((32, 3), device=dev), torch.empty((32,), device=dev)
+    gw1, gb1 = torch.empty((C, 32), device=dev), torch.empty((C,), device=dev)
+    nbytes = int(L.rd_meta_kernel_bwd_workspace_bytes(B, C, H, W))
+    ws = torch.empty((max(nbytes, 4) + 3) // 4, device=dev, dtype=torch.float32)
+    with torch.cuda.device(dev):
+        st = L.rd_meta_kernel_bwd(_p(grad_out), _p(data), _p(coord), _p(w0), _p(b0), _p(w1), _p(b1),
+                                  _p(gd), _p(gw0), _p(gb0), _p(gw1), _p(gb1), _p(ws),
+                                  ctypes.c_size_t(ws.numel() * 4), B, C, H, W, int(impl), _stream())
+    _lib.check(st, "meta_kernel_backward")
+    return gd, gw0, gb0, gw1, gb1
+
+
+class MetaKernelFunction(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, data, coord, w0, b0, w1, b1, impl):
+        ctx.save_for_backward(data, coord, w0, b0, w1, b1)
+        ctx.impl = impl
+        ctx.shapes = (w0.shape, w1.shape)
+        return meta_kernel_forward(data, coord, w0, b0, w1, b1, impl)
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        data, coord, w0, b0, w1, b1 = ctx.saved_tensors
+        gd, gw0, gb0, gw1, gb1 = meta_kernel_backward(grad_out, data, coord, w0, b0, w1, b1, ctx.impl)
+        return gd, None, gw0.reshape(ctx.shapes[0]), gb0, gw1.reshape(ctx.shapes[1]), gb1, None
+
+
+def meta_kernel(data, coord, w0, b0, w1, b1, impl=IMPL_DEFAULT):
+    """Differentiable Meta-Kernel (gradients to data and the four MLP parameters)."""
+    return MetaKernelFunction.apply(data, coord, w0, b0, w1, b1, impl)
+
+
+# ------------------------------------------------------------------------------------------------
+# Decode3DBbox / RotatedIOU / batch_rotated_iou
+# ------------------------------------------------------------------------------------------------
+def decode_3d_bbox(bbox_deltas, pc_laser_frame, is_bin=False):
+    """_contrib_Decode3DBbox: (B,N,8|7) + (B,N,3) -> (B,N,10).  Shape rules as FInferShape
+    (decode_3d_bbox.cc:30-60).  Zero gradient (decode_3d_bbox.cc:62): output is detached."""
+    d = _chk(bbox_deltas, "bbox_deltas", 3, 7 if is_bin else 8)
+    p = _chk(pc_laser_frame, "pc_laser_frame", 3, 3)
+    if d.shape[:2] != p.shape[:2]:
+        raise ValueError("bbox_deltas and pc_laser_frame must agree on (B,N)")
+    out = torch.empty(d.shape[:2] + (10,), device=d.device, dtype=torch.float32)
+    with torch.cuda.device(d.device):
+        st = _lib.lib().rd_decode_3d_bbox(_p(d), _p(p), _p(out), d.shape[0] * d.shape[1], int(bool(is_bin)),
+                                          _stream())
+    _lib.check(st, "decode_3d_bbox")
+    return out
+
+
+def rotated_iou(boxes1, boxes2):
+    """_contrib_RotatedIOU: (N1,T),(N2,T) -> (N1,N2), T in {5,7,8} (rotated_iou.cc:25-50)."""
+    a = _chk(boxes1, "boxes1", 2, (5, 7, 8))
+    b = _chk(boxes2, "boxes2", 2, (5, 7, 8))
+    if a.shape[1] != b.shape[1]:
+        raise ValueError("boxes1 and boxes2 must have the same box type")
+    out = torch.empty((a.shape[0], b.shape[0]), device=a.device, dtype=torch.float32)
+    with torch.cuda.device(a.device):
+        st = _lib.lib().rd_rotated_iou(_p(a), _p(b), _p(out), a.shape[0], b.shape[0], a.shape[1], _stream())
+    _lib.check(st, "rotated_iou")
+    return out
+
+
+def batch_rotated_iou(proposal, gt_bbox, iou_type="bev"):
+    """Custom op 'batch_rotated_iou' (operator_py/batch_rotated_iou.py): (B,N,10) + (B,G,8|7) ->
+    (B,N) max-over-GT IoU target; shape checks as BatchRotatedIOUProp.infer_shape (:84-104)."""
+    if iou_type not in ("bev", "3d"):
+        raise ValueError("Unknown iou type!")
+    pr = _chk(proposal, "proposal", 3, 10)
+    gt = _chk(gt_bbox, "gt_bbox", 3, 8 if iou_type == "bev" else 7)
+    if pr.shape[0] != gt.shape[0]:
+        raise ValueError("proposal and gt_bbox must agree on the batch size")
+    out = torch.empty(pr.shape[:2], device=pr.device, dtype=torch.float32)
+    with torch.cuda.device(pr.device):
+        st = _lib.lib().rd_batch_rotated_iou_max(_p(pr), _p(gt), _p(out), pr.shape[0], pr.shape[1],
+                                                 gt.shape[1], 0 if iou_type == "bev" else 1, _stream())
+    _lib.check(st, "batch_rotated_iou")
+    return out
+
+
+def wnms_4c_device(dets, thresh, thresh_vote, is_3d=False, hash_scale=100):
+    """Device-resident weighted NMS: dets (N,12) CUDA float32 -> (out_dets (K,12), keep_inds (K) int32)."""
+    d = _chk(dets, "dets", 2, 12)
+    n = d.shape[0]
+    if n == 0:
+        return (torch.empty((0, 12), device=d.device), torch.empty((0,), device=d.device, dtype=torch.int32))
+    L = _lib.lib()
+    out = torch.empty((n, 12), device=d.device, dtype=torch.float32)
+    keep = torch.empty((n,), device=d.device, dtype=torch.int32)
+    nbytes = int(L.rd_wnms_4c_workspace_bytes(n))
+    ws = torch.empty(((nbytes + 7) // 8,), device=d.device, dtype=torch.int64)
+    cnt = ctypes.c_int(0)
+    with torch.cuda.device(d.device):
+        st = L.rd_wnms_4c(_p(d), n, float(thresh), float(thresh_vote), int(bool(is_3d)), int(hash_scale),
+                          _p(out), _p(keep), ctypes.byref(cnt), _p(ws), ctypes.c_size_t(ws.numel() * 8),
+                          _stream())
+    _lib.check(st, "wnms_4c")
+    k = cnt.value
+    return out[:k], keep[:k]
+
+
+def tc_probe_gemm(a, b):
+    """D = A . B^T through tcgen05 (bf16 operands): a (128,k), b (n,k) -> (128,n)."""
+    a, b = _chk(a, "a", 2), _chk(b, "b", 2)
+    d = torch.empty((128, b.shape[0]), device=a.device, dtype=torch.float32)
+    with torch.cuda.device(a.device):
+        st = _lib.lib().rd_tc_probe_gemm(_p(a), _p(b), _p(d), b.shape[0], a.shape[1], _stream())
+    _lib.check(st, "tc_probe_gemm")
+    return d

@@ -1,0 +1,70 @@
+"""Regenerates tests/golden/*.npz.  Run HERE (build container, /root/reference present):
+
+    python tests/golden/make_golden.py
+
+Post-process vectors come from the reference's OWN C++ (oracle/_ref/librd_ref.so, compiled from
+/root/reference by oracle/build_ref.py).  Meta-Kernel vectors come from the torch fp32 restatement
+(oracle/meta_kernel_ref.py) -- the reference's arithmetic for that part lives in MXNet, which is not
+available ("parity unpinned" at that boundary).
+"""
+import os
+import sys
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, ROOT)
+import oracle  # noqa: E402
+from oracle import meta_kernel_ref  # noqa: E402
+from rangedet_b200 import synth  # noqa: E402
+
+OUT = os.path.dirname(os.path.abspath(__file__))
+
+
+def main():
+    ref = oracle.reference()
+    assert ref is not None, "needs /root/reference"
+    # decode (8-dim and bin)
+    d, pc = synth.decode_inputs(2, 300, seed=4)
+    dbin = np.concatenate([d[..., :2], d[..., 6:7], d[..., 2:4], d[..., 7:8],
+                           np.arctan2(d[..., 5:6], d[..., 4:5])], -1).astype(np.float32)
+    np.savez_compressed(os.path.join(OUT, "decode.npz"), delta=d, pc=pc, out=ref.decode_3d_bbox(d, pc),
+                        delta_bin=dbin, out_bin=ref.decode_3d_bbox(dbin, pc, is_bin=True))
+    # rotated IoU, three box types; clustered so that many pairs overlap; plus padded GT rows
+    b7 = synth.boxes7(600, seed=11, clustered=True)
+    c8 = synth.boxes7_to_corners10(b7)[:, :8]
+    gt8 = np.concatenate([c8[:60] + np.float32(0.07), synth.gt_boxes8(1, 10, 40, seed=5)[0]], 0)
+    x5 = np.stack([b7[:, 0], b7[:, 1], b7[:, 3], b7[:, 4], b7[:, 6]], 1)
+    np.savez_compressed(os.path.join(OUT, "rotated_iou.npz"),
+                        a8=c8, b8=gt8, iou8=ref.rotated_iou(c8, gt8),
+                        a5=x5[:200], b5=x5[100:260], iou5=ref.rotated_iou(x5[:200], x5[100:260]),
+                        a7=b7[:200], b7=b7[100:260], iou7=ref.rotated_iou(b7[:200], b7[100:260]))
+    # weighted NMS
+    items = {}
+    for tag, n, cl in [("clustered", 3000, True), ("uniform", 1500, False)]:
+        dets = synth.wnms_dets(n, seed=5, clustered=cl)
+        od, ok = ref.wnms_4c(dets, 0.1, 0.5, False, 100)
+        od3, ok3 = ref.wnms_4c(dets, 0.1, 0.5, True, 100)
+        items.update({tag + "_dets": dets, tag + "_out": od, tag + "_keep": ok,
+                      tag + "_out3d": od3, tag + "_keep3d": ok3})
+    np.savez_compressed(os.path.join(OUT, "wnms.npz"), **items)
+    # Meta-Kernel fwd + bwd (torch fp32 restatement)
+    torch.manual_seed(0)
+    B, C, H, W = 1, 64, 5, 28
+    coord = torch.from_numpy(synth.range_image_coords(B, seed=0, h=H, w=W - 3, w_pad=W))
+    data = torch.from_numpy(synth.feature_map(B, C, seed=1, h=H, w=W - 3, w_pad=W))
+    w0, b0, w1, b1 = [torch.from_numpy(p) for p in synth.meta_mlp_params(seed=2)]
+    go = torch.randn(B, C * 9, H, W)
+    out, gd, gw0, gb0, gw1, gb1 = meta_kernel_ref.meta_baseline_bias_fwd_bwd(data, coord, w0, b0, w1, b1, go)
+    np.savez_compressed(os.path.join(OUT, "meta_kernel.npz"), data=data.numpy(), coord=coord.numpy(),
+                        w0=w0.numpy(), b0=b0.numpy(), w1=w1.numpy(), b1=b1.numpy(), grad_out=go.numpy(),
+                        out=out.numpy(), grad_data=gd.numpy(), grad_w0=gw0.numpy(), grad_b0=gb0.numpy(),
+                        grad_w1=gw1.numpy(), grad_b1=gb1.numpy())
+    for f in sorted(os.listdir(OUT)):
+        if f.endswith(".npz"):
+            print(f, os.path.getsize(os.path.join(OUT, f)))
+
+
+if __name__ == "__main__":
+    main()
