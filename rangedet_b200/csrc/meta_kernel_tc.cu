@@ -14,6 +14,8 @@
 // four CTAs per SM (4 x 128 TMEM columns = 512) hide the remaining latencies.
 #include "../../include/rangedet_b200.h"
 #include "rd_common.cuh"
+#include <stdlib.h>
+
 #include "tc_common.cuh"
 
 namespace mktc {
@@ -37,6 +39,9 @@ struct Smem {
   uint32_t tmem_slot;
 };
 
+// DBG (diagnostic builds selected with RD_MK_TC_DEBUG, never by default): 1 = no feature loads,
+// 2 = no output stores, 4 = no hidden-layer math, 8 = no TMEM read.
+template <int DBG>
 __global__ void __launch_bounds__(NT, 4)
 meta_fwd_tc_kernel(const float* __restrict__ data, const float* __restrict__ coord,
                    const float* __restrict__ w0, const float* __restrict__ b0,
@@ -133,12 +138,17 @@ meta_fwd_tc_kernel(const float* __restrict__ data, const float* __restrict__ coo
 #pragma unroll
             for (int u = 0; u < 2; ++u) {
               const float4 wv = S.w0b[q * 8 + 2 * p + u];
-              float z = wv.w;
-              z = fmaf(wv.x, r0, z);
-              z = fmaf(wv.y, r1, z);
-              z = fmaf(wv.z, r2, z);
-              hv[u] = fmaxf(z, 0.f);
-              tc::split_bf16(hv[u], hh[u], hl[u]);
+              if (DBG & 4) {
+                hh[u] = r0;
+                hl[u] = r1;
+              } else {
+                float z = wv.w;
+                z = fmaf(wv.x, r0, z);
+                z = fmaf(wv.y, r1, z);
+                z = fmaf(wv.z, r2, z);
+                hv[u] = fmaxf(z, 0.f);
+                tc::split_bf16(hv[u], hh[u], hl[u]);
+              }
             }
             hi[p] = tc::pack_bf16x2(hh[0], hh[1]);
             lo[p] = tc::pack_bf16x2(hl[0], hl[1]);
@@ -188,12 +198,21 @@ meta_fwd_tc_kernel(const float* __restrict__ data, const float* __restrict__ coo
         for (int half = 0; half < 2; ++half) {
           float dv[32];
 #pragma unroll
-          for (int i = 0; i < 32; ++i) dv[i] = ld_ok ? __ldg(dptr + (int64_t)(half * 32 + i) * plane) : 0.f;
+          for (int i = 0; i < 32; ++i)
+            dv[i] = (DBG & 1) ? 1.f : (ld_ok ? __ldg(dptr + (int64_t)(half * 32 + i) * plane) : 0.f);
           float v[32];
-          tc::tmem_ld_x32(tmem_base + lane_sel + (ge & 1) * C + half * 32, v);
+          if (DBG & 8) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) v[i] = c0 + (float)i;
+          } else {
+            tc::tmem_ld_x32(tmem_base + lane_sel + (ge & 1) * C + half * 32, v);
+          }
           if (w < W) {
 #pragma unroll
-            for (int i = 0; i < 32; ++i) __stcs(optr + (int64_t)(half * 32 + i) * 9 * plane, dv[i] * v[i]);
+            for (int i = 0; i < 32; ++i) {
+              const float o = dv[i] * v[i];
+              if (!(DBG & 2) || o == 123456.789f) __stcs(optr + (int64_t)(half * 32 + i) * 9 * plane, o);
+            }
           }
         }
       }
@@ -219,10 +238,28 @@ int rd_meta_kernel_fwd_tc(const float* data, const float* coord, const float* w0
   RD_CUDA(cudaGetDevice(&dev));
   RD_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
   const size_t smem = sizeof(mktc::Smem) + 128;
-  RD_CUDA(cudaFuncSetAttribute(mktc::meta_fwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int64_t grid = ntiles < (int64_t)sms * 4 ? ntiles : (int64_t)sms * 4;
-  mktc::meta_fwd_tc_kernel<<<(unsigned)grid, mktc::NT, smem, stream>>>(data, coord, w0, b0, w1, b1, out, B, H,
-                                                                        W, tiles_w, (int)ntiles);
+  int dbg = 0;
+  if (const char* e = getenv("RD_MK_TC_DEBUG")) dbg = atoi(e);
+#define RD_LAUNCH_TC(D)                                                                                     \
+  do {                                                                                                      \
+    RD_CUDA(cudaFuncSetAttribute(mktc::meta_fwd_tc_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                 (int)smem));                                                               \
+    mktc::meta_fwd_tc_kernel<D><<<(unsigned)grid, mktc::NT, smem, stream>>>(data, coord, w0, b0, w1, b1,   \
+                                                                            out, B, H, W, tiles_w,          \
+                                                                            (int)ntiles);                   \
+  } while (0)
+  switch (dbg) {
+    case 1: RD_LAUNCH_TC(1); break;
+    case 2: RD_LAUNCH_TC(2); break;
+    case 3: RD_LAUNCH_TC(3); break;
+    case 4: RD_LAUNCH_TC(4); break;
+    case 8: RD_LAUNCH_TC(8); break;
+    case 11: RD_LAUNCH_TC(11); break;
+    case 15: RD_LAUNCH_TC(15); break;
+    default: RD_LAUNCH_TC(0); break;
+  }
+#undef RD_LAUNCH_TC
   rd::count_launch();
   return rd::check_launch("rd_meta_kernel_fwd(tcgen05)");
 }

@@ -22,9 +22,15 @@
 //      parallel (one pair per thread), sets suppression bits in a shared-memory bitmap and appends
 //      the voting neighbours.  Only rows of KEPT boxes are ever evaluated.
 //   4. merge: one thread per kept box (neighbour sort by rank, median yaw, weighted mean).
-// Pairs whose AABBs are disjoint are not evaluated; for those the reference's half-plane
-// intersection yields 0 (or NaN for parallel far-apart edges), i.e. neither `ovr >= thresh` nor
-// `ovr > thresh_vote` -- verified empirically against the compiled reference (tests).
+// Which pairs must be evaluated: the reference evaluates every (kept i, unsuppressed later j) pair
+// that shares a hash cell.  Its half-plane intersection is only well behaved when the 8 edge
+// directions are distinct: for AABB-disjoint boxes it then returns 0 / NaN (no effect), BUT when
+// the two rectangles are parallel within EPS=1e-5 rad (mod pi/2) the duplicate-angle removal
+// (nms.h:105-107) leaves 4 lines and the routine returns the area of the GAP between the boxes --
+// e.g. ovr = 1.3 for two boxes 23 m apart, which the reference then suppresses.  An exhaustive
+// scan of 1.3e9 disjoint pairs found no other source of non-zero overlap.  So the candidate set is
+//     (AABB-near  OR  edge direction equal within 1e-4 rad mod pi/2)  AND  shared hash key,
+// and the quirk is reproduced bit for bit.
 #include <cub/cub.cuh>
 #include <float.h>
 #include <math.h>
@@ -40,6 +46,8 @@ constexpr int GRID_DIM_MAX = 1024;
 constexpr int NT = 256;         // threads of the greedy CTA
 constexpr int LCAP = 4 * NT;    // candidate list capacity
 constexpr float AABB_MARGIN = 0.05f;
+constexpr float HALF_PI = 1.5707963f;
+constexpr float THETA_TOL = 1e-4f;  // >> EPS (1e-5) + float noise of the four edge angles
 
 // ---------------------------------------------------------------------------------------------
 // glibc-compatible atan2f (fdlibm e_atan2f.c / s_atanf.c)
@@ -275,7 +283,8 @@ struct Counters {
 
 struct Layout {
   size_t keys_in, keys_out, idx_in, order, bx, aabb, hashr, cell_id, cell_id_s, rank_in, cell_rank,
-      cell_start, cell_end, params, counters, kept_rank, nb_start, nb_list, cub_temp, total;
+      cell_start, cell_end, params, counters, kept_rank, nb_start, nb_list, theta, theta_s, theta_rank,
+      cub_temp, total;
   size_t cub_bytes, nb_cap;
 };
 
@@ -294,6 +303,7 @@ __host__ inline Layout make_layout(int n) {
   L.kept_rank = take(N * 4); L.nb_start = take((N + 1) * 4);
   L.nb_cap = N + 4096;
   L.nb_list = take(L.nb_cap * 4);
+  L.theta = take(N * 4); L.theta_s = take(N * 4); L.theta_rank = take(N * 4);
   L.cub_bytes = (size_t)(16u << 20) + N * 32;
   L.cub_temp = take(L.cub_bytes);
   L.total = o;
@@ -328,7 +338,7 @@ __global__ void init_kernel(const float* __restrict__ dets, int n, float* keys, 
 // rank-ordered copies + AABB + BBoxHash cell ranges (nms.h:268-291) + global bounds
 __global__ void prep_kernel(const float* __restrict__ dets, const int* __restrict__ order, int n,
                             float hash_scale, float* __restrict__ bx, float4* __restrict__ aabb,
-                            short4* __restrict__ hashr, Counters* ctr) {
+                            short4* __restrict__ hashr, float* __restrict__ theta, Counters* ctr) {
   const int r = blockIdx.x * blockDim.x + threadIdx.x;
   if (r >= n) return;
   const int i = order[r];
@@ -356,6 +366,13 @@ __global__ void prep_kernel(const float* __restrict__ dets, const int* __restric
   hr.z = (short)__float2int_rz(ceilf(__fdiv_rn(mxx, hash_scale)));
   hr.w = (short)__float2int_rz(ceilf(__fdiv_rn(mxy, hash_scale)));
   hashr[r] = hr;
+  {  // direction of the first edge, folded into [0, pi/2): parallel-rectangle detector
+    float a = atan2f_glibc(v[3] - v[1], v[2] - v[0]);
+    a = a - floorf(a * 0.63661977f) * HALF_PI;
+    if (!(a >= 0.f)) a = 0.f;          // also catches NaN
+    if (a >= HALF_PI) a = 0.f;
+    theta[r] = a;
+  }
   aabb[r] = make_float4(tx0 - AABB_MARGIN, ty0 - AABB_MARGIN, tx1 + AABB_MARGIN, ty1 + AABB_MARGIN);
   if (isfinite(tx0) && isfinite(tx1) && isfinite(ty0) && isfinite(ty1)) {
     atomicMin(&ctr->min_x, f2ord(tx0));
@@ -441,7 +458,9 @@ struct GreedySmem {
 __global__ void __launch_bounds__(NT, 1)
 greedy_kernel(const float* __restrict__ bx, const float4* __restrict__ aabb, const short4* __restrict__ hashr,
               const int* __restrict__ cell_rank, const int* __restrict__ cell_start,
-              const int* __restrict__ cell_end, const GridParams* gpp, int n, float thresh,
+              const int* __restrict__ cell_end, const float* __restrict__ theta,
+              const float* __restrict__ theta_s, const int* __restrict__ theta_rank,
+              const GridParams* gpp, int n, float thresh,
               float thresh_vote, int is3d, int* __restrict__ kept_rank, int* __restrict__ nb_start,
               int* __restrict__ nb_list, int nb_cap, Counters* ctr) {
   extern __shared__ unsigned bitmap[];
@@ -485,7 +504,7 @@ greedy_kernel(const float* __restrict__ bx, const float4* __restrict__ aabb, con
     }
     __syncthreads();
     const float4 ai = S.aabb_i;
-    const short4 hi = S.hash_i;
+    const short4 hi_key = S.hash_i;
     int cx, cy;
     cell_of(gp, ai.x, ai.y, &cx, &cy);
     for (int dy = -1; dy <= 1; ++dy) {
@@ -503,7 +522,7 @@ greedy_kernel(const float* __restrict__ bx, const float4* __restrict__ aabb, con
             if (rb > ri && !((bitmap[rb >> 5] >> (rb & 31)) & 1u)) {
               const float4 ab = aabb[rb];
               const bool near = !(ai.z < ab.x || ab.z < ai.x || ai.w < ab.y || ab.w < ai.y);
-              if (near && share_key(hi, hashr[rb])) {
+              if (near && share_key(hi_key, hashr[rb])) {
                 const int pos = atomicAdd(&S.ncand, 1);
                 S.cand[pos] = rb;
               }
@@ -511,6 +530,42 @@ greedy_kernel(const float* __restrict__ bx, const float4* __restrict__ aabb, con
           }
           __syncthreads();
           if (S.ncand > LCAP - NT) {  // uniform decision
+            evaluate();
+            __syncthreads();
+            if (t == 0) S.ncand = 0;
+            __syncthreads();
+          }
+        }
+      }
+    }
+    {  // parallel boxes (any distance): ranges of the theta-sorted array around theta_i, with wrap
+      const float th = theta[ri];
+      for (int seg = 0; seg < 3; ++seg) {
+        float lo, hi;
+        if (seg == 0) { lo = th - THETA_TOL; hi = th + THETA_TOL; }
+        else if (seg == 1) { lo = th - THETA_TOL + HALF_PI; hi = HALF_PI + 1.f; if (!(th < THETA_TOL)) continue; }
+        else { lo = -1.f; hi = th + THETA_TOL - HALF_PI; if (!(th + THETA_TOL > HALF_PI)) continue; }
+        int a = 0, b = n;  // lower_bound(lo)
+        while (a < b) { const int mid = (a + b) >> 1; if (theta_s[mid] < lo) a = mid + 1; else b = mid; }
+        const int first = a;
+        a = first; b = n;  // upper_bound(hi)
+        while (a < b) { const int mid = (a + b) >> 1; if (theta_s[mid] <= hi) a = mid + 1; else b = mid; }
+        const int last = a;
+        for (int base = first; base < last; base += NT) {
+          const int e = base + t;
+          if (e < last) {
+            const int rb = theta_rank[e];
+            if (rb > ri && !((bitmap[rb >> 5] >> (rb & 31)) & 1u)) {
+              const float4 ab = aabb[rb];
+              const bool near = !(ai.z < ab.x || ab.z < ai.x || ai.w < ab.y || ab.w < ai.y);
+              if (!near && share_key(hi_key, hashr[rb])) {  // near ones came through the grid
+                const int pos = atomicAdd(&S.ncand, 1);
+                S.cand[pos] = rb;
+              }
+            }
+          }
+          __syncthreads();
+          if (S.ncand > LCAP - NT) {
             evaluate();
             __syncthreads();
             if (t == 0) S.ncand = 0;
@@ -667,6 +722,9 @@ int rd_wnms_4c(const float* dets, int n, float thresh, float thresh_vote, int is
   int* kept_rank = (int*)(ws + L.kept_rank);
   int* nb_start = (int*)(ws + L.nb_start);
   int* nb_list = (int*)(ws + L.nb_list);
+  float* theta = (float*)(ws + L.theta);
+  float* theta_s = (float*)(ws + L.theta_s);
+  int* theta_rank = (int*)(ws + L.theta_rank);
   void* cub_temp = ws + L.cub_temp;
 
   const int TB = 256, nb = (n + TB - 1) / TB;
@@ -680,7 +738,7 @@ int rd_wnms_4c(const float* dets, int n, float thresh, float thresh_vote, int is
     RD_CUDA(cub::DeviceRadixSort::SortPairsDescending(cub_temp, tb, keys_in, keys_out, idx_in, order, n, 0, 32, st));
     rd::count_launch(3);
   }
-  prep_kernel<<<nb, TB, 0, st>>>(dets, order, n, (float)hash_scale, bx, aabb, hashr, ctr);
+  prep_kernel<<<nb, TB, 0, st>>>(dets, order, n, (float)hash_scale, bx, aabb, hashr, theta, ctr);
   grid_setup_kernel<<<1, 1, 0, st>>>(ctr, gp);
   cell_kernel<<<nb, TB, 0, st>>>(aabb, n, gp, cell_id, rank_in);
   rd::count_launch(3);
@@ -692,12 +750,18 @@ int rd_wnms_4c(const float* dets, int n, float thresh, float thresh_vote, int is
     RD_CUDA(cub::DeviceRadixSort::SortPairs(cub_temp, tb, cell_id, cell_id_s, rank_in, cell_rank, n, 0, 21, st));
     rd::count_launch(3);
   }
+  {  // boxes sorted by folded edge direction (rank_in still holds 0..n-1)
+    size_t tb = L.cub_bytes;
+    RD_CUDA(cub::DeviceRadixSort::SortPairs(cub_temp, tb, theta, theta_s, rank_in, theta_rank, n, 0, 32, st));
+    rd::count_launch(3);
+  }
   RD_CUDA(cudaMemsetAsync(cell_start, 0, (size_t)(NCELL_MAX + 1) * 4, st));
   RD_CUDA(cudaMemsetAsync(cell_end, 0, (size_t)(NCELL_MAX + 1) * 4, st));
   cell_bounds_kernel<<<nb, TB, 0, st>>>(cell_id_s, n, cell_start, cell_end);
   rd::count_launch();
   RD_CUDA(cudaFuncSetAttribute(greedy_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bitmap_bytes));
-  greedy_kernel<<<1, NT, bitmap_bytes, st>>>(bx, aabb, hashr, cell_rank, cell_start, cell_end, gp, n, thresh,
+  greedy_kernel<<<1, NT, bitmap_bytes, st>>>(bx, aabb, hashr, cell_rank, cell_start, cell_end, theta, theta_s,
+                                             theta_rank, gp, n, thresh,
                                              thresh_vote, is_3d, kept_rank, nb_start, nb_list, (int)L.nb_cap, ctr);
   rd::count_launch();
   if (rd::check_launch("rd_wnms_4c(greedy)")) return 1;

@@ -16,6 +16,8 @@ bench) timeout 900 python bench.py --steps 10 --warmup 3 --mk-impl 1 > gpurun_ou
        timeout 600 python bench.py --steps 10 --warmup 3 --mk-impl 2 --no-cpu-baseline > gpurun_out/bench_impl2.json 2> gpurun_out/bench_impl2.err; echo "bench2 exit $?" >> gpurun_out/status.txt ;;
 ncu)   timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 80 --csv --log-file gpurun_out/launches.csv python bench.py --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_launch.log 2>&1; echo "ncu-list exit $?" >> gpurun_out/status.txt
        timeout 900 ncu --set full --clock-control none --import-source on -k regex:meta_ -s 8 -c 4 -o gpurun_out/prof_meta -f python bench.py --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_full.log 2>&1; echo "ncu-full exit $?" >> gpurun_out/status.txt ;;
+diag)  timeout 600 python scripts/mk_tc_diag.py > gpurun_out/mk_tc_diag.json 2> gpurun_out/mk_tc_diag.err; echo "diag exit $?" >> gpurun_out/status.txt ;;
+ncutc) timeout 900 ncu --set full --clock-control none --import-source on -k regex:meta_fwd_tc -s 3 -c 1 -o gpurun_out/prof_meta_tc -f python scripts/mk_tc_diag.py 0 > gpurun_out/ncu_tc.log 2>&1; echo "ncu-tc exit $?" >> gpurun_out/status.txt ;;
 esac
 done
 cat gpurun_out/status.txt

@@ -36,10 +36,15 @@ def main():
     c8 = synth.boxes7_to_corners10(b7)[:, :8]
     gt8 = np.concatenate([c8[:60] + np.float32(0.07), synth.gt_boxes8(1, 10, 40, seed=5)[0]], 0)
     x5 = np.stack([b7[:, 0], b7[:, 1], b7[:, 3], b7[:, 4], b7[:, 6]], 1)
+    # Types 5/7 go through sin/cos: for bit-identical boxes the reference's inclusive point-in-box
+    # test sits exactly on the boundary and flips with the last ulp of sinf/cosf (glibc vs CUDA), so
+    # the second set is a jittered copy (type 8 keeps exact duplicates: no trig involved there).
+    b5 = x5[100:260] + np.float32([0.013, -0.007, 0.004, 0.002, 0.003])
+    b7j = b7[100:260] + np.float32([0.013, -0.007, 0.02, 0.004, 0.002, 0.01, 0.003])
     np.savez_compressed(os.path.join(OUT, "rotated_iou.npz"),
                         a8=c8, b8=gt8, iou8=ref.rotated_iou(c8, gt8),
-                        a5=x5[:200], b5=x5[100:260], iou5=ref.rotated_iou(x5[:200], x5[100:260]),
-                        a7=b7[:200], b7=b7[100:260], iou7=ref.rotated_iou(b7[:200], b7[100:260]))
+                        a5=x5[:200], b5=b5, iou5=ref.rotated_iou(x5[:200], b5),
+                        a7=b7[:200], b7=b7j, iou7=ref.rotated_iou(b7[:200], b7j))
     # weighted NMS
     items = {}
     for tag, n, cl in [("clustered", 3000, True), ("uniform", 1500, False)]:

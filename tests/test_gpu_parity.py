@@ -130,7 +130,12 @@ def _check_wnms(ops, dets, want_out, want_keep, is3d, tag):
     report(test="wnms", tag=tag, is3d=bool(is3d), n=int(dets.shape[0]), K=int(len(want_keep)), K_gpu=int(len(keep)),
            keep_bit_exact=bool(same))
     assert same, "%s: keep indices differ (K %d vs %d)" % (tag, len(keep), len(want_keep))
-    assert np.array_equal(out, want_out, equal_nan=True), "%s: merged boxes differ" % tag
+    eq = (out == want_out) | (np.isnan(out) & np.isnan(want_out))
+    if not eq.all():
+        rows = np.where(~eq.all(1))[0]
+        report(test="wnms_mismatch", tag=tag, n_rows=int(len(rows)), rows=rows[:5].tolist(),
+               got=out[rows[:3]].tolist(), want=want_out[rows[:3]].tolist())
+    assert eq.all(), "%s: merged boxes differ in %d rows" % (tag, int((~eq.all(1)).sum()))
 
 
 @pytest.mark.parametrize("tag", ["clustered", "uniform"])
