@@ -39,6 +39,8 @@ const char* rd_last_error(void) { return rd::g_err; }
 uint64_t rd_launch_count(void) { return rd::g_launches; }
 
 int rd_check_device(void) {
+  // Result cached per device: cudaGetDeviceProperties costs ~1 ms and this guards every launch.
+  static int cached[64];  // 0 = unknown, 1 = ok
   int dev = 0;
   cudaError_t e = cudaGetDevice(&dev);
   if (e != cudaSuccess) {
@@ -46,16 +48,20 @@ int rd_check_device(void) {
     cudaGetLastError();
     return 1;
   }
-  cudaDeviceProp p;
-  e = cudaGetDeviceProperties(&p, dev);
+  if (dev >= 0 && dev < 64 && cached[dev] == 1) return 0;
+  int major = 0, minor = 0;
+  e = cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev);
+  if (e == cudaSuccess) e = cudaDeviceGetAttribute(&minor, cudaDevAttrComputeCapabilityMinor, dev);
   if (e != cudaSuccess) {
-    rd::set_error("cudaGetDeviceProperties: %s", cudaGetErrorString(e));
+    rd::set_error("cudaDeviceGetAttribute: %s", cudaGetErrorString(e));
+    cudaGetLastError();
     return 1;
   }
-  if (p.major != 10) {
-    rd::set_error("device %d is sm_%d%d; this library is built for sm_100a only", dev, p.major, p.minor);
+  if (major != 10) {
+    rd::set_error("device %d is sm_%d%d; this library is built for sm_100a only", dev, major, minor);
     return 1;
   }
+  if (dev >= 0 && dev < 64) cached[dev] = 1;
   return 0;
 }
 
