@@ -39,7 +39,8 @@ uint64_t rd_launch_count(void);
  *   out[b, c*9+k, h, w] = data[b,c,h+dy,w+dx] * (W1 . relu(W0 . rel + b0) + b1)[c]
  *   rel = coord[b,:,h+dy,w+dx] (0 outside the image) - coord[b,:,h,w],  k = ky*3+kx
  * data (B,C,H,W)  coord (B,3,H,W)  w0 (32,3)  b0 (32)  w1 (C,32)  b1 (C)  out (B,9C,H,W)
- * C must be a multiple of 8, <= 64.  impl: 0 = default, 1 = CUDA-core fp32, 2 = tcgen05 (C == 64).
+ * C must be a multiple of 8, <= 64.  impl: 0 = default, 1 = CUDA-core fp32, 2 = tcgen05 (C == 64),
+ * 3 = TMA-fed warp-specialised tcgen05 (C == 64, W % 4 == 0).
  */
 int rd_meta_kernel_fwd(const float* data, const float* coord, const float* w0, const float* b0,
                        const float* w1, const float* b1, float* out,

@@ -479,7 +479,13 @@ __global__ void meta_bwd_param_reduce_kernel(const float* __restrict__ partial, 
 
 }  // namespace mk
 
-// implemented in meta_kernel_tc.cu
+// implemented in meta_kernel_ws.cu (impl 3)
+int rd_meta_kernel_fwd_ws(const float* data, const float* coord, const float* w0, const float* b0, const float* w1,
+                          const float* b1, float* out, int B, int C, int H, int W, cudaStream_t stream);
+int rd_meta_kernel_bwd_data_ws(const float* grad_out, const float* coord, const float* w0, const float* b0,
+                               const float* w1, const float* b1, float* grad_data, int B, int C, int H, int W,
+                               cudaStream_t stream);
+// implemented in meta_kernel_tc.cu (impl 2)
 int rd_meta_kernel_fwd_tc(const float* data, const float* coord, const float* w0, const float* b0,
                           const float* w1, const float* b1, float* out, int B, int C, int H, int W,
                           cudaStream_t stream);
@@ -492,10 +498,11 @@ int rd_meta_kernel_fwd(const float* data, const float* coord, const float* w0, c
   RD_REQUIRE(B >= 0 && H > 0 && W > 0, "rd_meta_kernel_fwd: bad shape B=%d H=%d W=%d", B, H, W);
   RD_REQUIRE(C > 0 && C % 8 == 0 && C <= mk::MAXC,
              "rd_meta_kernel_fwd: C must be a multiple of 8 and <= %d (got %d)", mk::MAXC, C);
-  RD_REQUIRE(impl >= 0 && impl <= 2, "rd_meta_kernel_fwd: impl must be 0, 1 or 2");
+  RD_REQUIRE(impl >= 0 && impl <= 3, "rd_meta_kernel_fwd: impl must be 0..3");
   if (B == 0) return 0;
   RD_REQUIRE(data && coord && w0 && b0 && w1 && b1 && out, "rd_meta_kernel_fwd: null pointer");
   if (rd_check_device()) return 1;
+  if (impl == 3) return rd_meta_kernel_fwd_ws(data, coord, w0, b0, w1, b1, out, B, C, H, W, rd::as_stream(stream));
   if (impl == 2) return rd_meta_kernel_fwd_tc(data, coord, w0, b0, w1, b1, out, B, C, H, W, rd::as_stream(stream));
   const int tiles_w = (W + mk::F_TW - 1) / mk::F_TW;
   const int64_t ntiles = (int64_t)B * H * tiles_w;
@@ -520,10 +527,12 @@ int rd_meta_kernel_bwd_data(const float* grad_out, const float* coord, const flo
   RD_REQUIRE(B >= 0 && H > 0 && W > 0, "rd_meta_kernel_bwd_data: bad shape B=%d H=%d W=%d", B, H, W);
   RD_REQUIRE(C > 0 && C % 8 == 0 && C <= mk::MAXC,
              "rd_meta_kernel_bwd_data: C must be a multiple of 8 and <= %d (got %d)", mk::MAXC, C);
-  RD_REQUIRE(impl >= 0 && impl <= 2, "rd_meta_kernel_bwd_data: impl must be 0, 1 or 2");
+  RD_REQUIRE(impl >= 0 && impl <= 3, "rd_meta_kernel_bwd_data: impl must be 0..3");
   if (B == 0) return 0;
   RD_REQUIRE(grad_out && coord && w0 && b0 && w1 && b1 && grad_data, "rd_meta_kernel_bwd_data: null pointer");
   if (rd_check_device()) return 1;
+  if (impl == 3)
+    return rd_meta_kernel_bwd_data_ws(grad_out, coord, w0, b0, w1, b1, grad_data, B, C, H, W, rd::as_stream(stream));
   const int tiles_w = (W + mk::G_TW - 1) / mk::G_TW;
   const int64_t ntiles = (int64_t)B * H * tiles_w;
   RD_REQUIRE(ntiles <= 0x7fffffffLL, "rd_meta_kernel_bwd_data: too many tiles");
@@ -544,7 +553,7 @@ int rd_meta_kernel_bwd_params(const float* grad_out, const float* data, const fl
   RD_REQUIRE(B >= 0 && H > 0 && W > 0, "rd_meta_kernel_bwd_params: bad shape B=%d H=%d W=%d", B, H, W);
   RD_REQUIRE(C > 0 && C % 8 == 0 && C <= mk::MAXC,
              "rd_meta_kernel_bwd_params: C must be a multiple of 8 and <= %d (got %d)", mk::MAXC, C);
-  RD_REQUIRE(impl >= 0 && impl <= 2, "rd_meta_kernel_bwd_params: impl must be 0, 1 or 2");
+  RD_REQUIRE(impl >= 0 && impl <= 3, "rd_meta_kernel_bwd_params: impl must be 0..3");
   RD_REQUIRE(grad_w0 && grad_b0 && grad_w1 && grad_b1, "rd_meta_kernel_bwd_params: null output pointer");
   cudaStream_t st = rd::as_stream(stream);
   if (rd_check_device()) return 1;

@@ -1,0 +1,374 @@
+// Meta-Kernel impl 3: persistent, warp-specialised, TMA-fed tcgen05 kernel (forward and grad_data).
+//
+// Replaces MetaKernel.meta_baseline_bias (/root/reference rangedet/symbol/backbone/
+// meta_kernel.py:166-240) and its data-gradient.  One CTA per SM walks (row, 128-pixel) tiles; per
+// tile 9 taps flow through four mbarrier-synchronised rings:
+//
+//   warp 0      TMA producer    feature (fwd) / grad_out (bwd) tap tile [64 ch][128 px] fp32 -> smem,
+//                               box shifted by (dy,dx): the image border is TMA's zero fill
+//   warps 2-5   hidden layer    rel xyz -> relu(W0 rel + b0) fp32 -> bf16 hi|lo, K-major core-matrix
+//                               layout (A operand ring)
+//   warp 1      MMA issuer      9 x tcgen05.mma M128 N64 K16: [h_hi|h_lo] x [W1_hi|W1_lo]^T (+ bias
+//                               K-slice) -> fp32 accumulator ring in TMEM (4 x 64 columns)
+//   warps 6-9   epilogue        tcgen05.ld -> x tap tile (smem, conflict-free) ->
+//                                 fwd: product tile -> smem -> TMA store (4-D map over (W,H,9,B*C))
+//                                 bwd: accumulate over the 9 taps in registers -> smem -> TMA store
+// HBM traffic = algorithmic (2572 B/pixel either direction); every global access is a TMA bulk
+// transfer, so bytes in flight per SM are bounded by the rings (96 KB loads + 64 KB stores), not by
+// per-thread load/store queues.
+#include <stdlib.h>
+
+#include "../../include/rangedet_b200.h"
+#include "rd_common.cuh"
+#include "tc_common.cuh"
+#include "tma_common.cuh"
+
+namespace mkws {
+
+constexpr int HID = 32, CCH = 3, C = 64;
+constexpr int TW = 128, ROW = TW + 2;
+constexpr int NTHREADS = 320;                // 10 warps
+constexpr int A_CHUNK = TW * 16;             // one 16-byte K-chunk over 128 rows
+constexpr int A_BYTES = 8 * A_CHUNK;         // h_hi (4 chunks) | h_lo (4 chunks)
+constexpr int B_CHUNK = C * 16;
+constexpr int B_BYTES = 10 * B_CHUNK;        // W1_hi | W1_lo | bias chunk | zero chunk
+constexpr int ONES_BYTES = 2 * A_CHUNK;
+constexpr int TILE_BYTES = C * TW * 4;       // 32 KB tap tile
+constexpr int NS_D = 3, NS_O = 2, NS_A = 2, NS_T = 4;
+constexpr uint32_t TMEM_COLS = NS_T * C;     // 256
+constexpr int BAR_HID = 1, BAR_EPI = 2;      // named barriers (0 = __syncthreads)
+
+struct Smem {
+  alignas(1024) float dtile[NS_D][C * TW];
+  alignas(1024) float otile[NS_O][C * TW];
+  alignas(1024) unsigned char a[NS_A][A_BYTES];
+  alignas(1024) unsigned char bw[B_BYTES];
+  alignas(1024) unsigned char ones[ONES_BYTES];
+  alignas(16) float4 w0b[HID];
+  alignas(16) float cs[3 * CCH * ROW];
+  alignas(8) uint64_t d_full[NS_D], d_empty[NS_D], a_full[NS_A], a_empty[NS_A], t_full[NS_T], t_empty[NS_T];
+  uint32_t tmem_slot;
+};
+
+// MODE 0: forward (tap tile = features, output = 9 product planes per channel)
+// MODE 1: grad_data (tap tile = grad_out plane 8-k at the mirrored pixel, output = sum over taps)
+template <int MODE>
+__global__ void __launch_bounds__(NTHREADS, 1)
+meta_ws_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant__ CUtensorMap tm_out,
+               const float* __restrict__ coord, const float* __restrict__ w0, const float* __restrict__ b0,
+               const float* __restrict__ w1, const float* __restrict__ b1, int B, int H, int W, int tiles_w,
+               int ntiles) {
+  extern __shared__ __align__(1024) unsigned char smem_raw[];
+  Smem& S = *reinterpret_cast<Smem*>(smem_raw);
+  const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+
+  // ---- setup ---------------------------------------------------------------------------------
+  if (t == 0) {
+    for (int i = 0; i < NS_D; ++i) { tc::mbar_init(&S.d_full[i], 1); tc::mbar_init(&S.d_empty[i], 4); }
+    for (int i = 0; i < NS_A; ++i) { tc::mbar_init(&S.a_full[i], 4); tc::mbar_init(&S.a_empty[i], 1); }
+    for (int i = 0; i < NS_T; ++i) { tc::mbar_init(&S.t_full[i], 1); tc::mbar_init(&S.t_empty[i], 4); }
+    tc::fence_mbar_init();
+    tma::prefetch_map(&tm_in);
+    tma::prefetch_map(&tm_out);
+  }
+  if (warp == 1) {
+    tc::tmem_alloc(&S.tmem_slot, TMEM_COLS);
+    tc::tmem_relinquish();
+  }
+  if (warp >= 2 && warp < 6) {  // constant operands: W1 hi/lo, bias slice, ones slice, layer-0 params
+    const int ht = t - 64;
+    for (int j = ht; j < HID; j += 128)
+      S.w0b[j] = make_float4(__ldg(w0 + j * 3 + 0), __ldg(w0 + j * 3 + 1), __ldg(w0 + j * 3 + 2), __ldg(b0 + j));
+    for (int e = ht; e < C * 4; e += 128) {
+      const int c = e % C, q = e / C;
+      uint32_t hi[4], lo[4];
+#pragma unroll
+      for (int p = 0; p < 4; ++p) {
+        float h0, l0, h1, l1;
+        tc::split_bf16(__ldg(w1 + c * HID + q * 8 + 2 * p), h0, l0);
+        tc::split_bf16(__ldg(w1 + c * HID + q * 8 + 2 * p + 1), h1, l1);
+        hi[p] = tc::pack_bf16x2(h0, h1);
+        lo[p] = tc::pack_bf16x2(l0, l1);
+      }
+      *reinterpret_cast<uint4*>(S.bw + q * B_CHUNK + c * 16) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+      *reinterpret_cast<uint4*>(S.bw + (4 + q) * B_CHUNK + c * 16) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+    }
+    for (int c = ht; c < C; c += 128) {
+      float h, l;
+      tc::split_bf16(__ldg(b1 + c), h, l);
+      *reinterpret_cast<uint4*>(S.bw + 8 * B_CHUNK + c * 16) = make_uint4(tc::pack_bf16x2(h, l), 0u, 0u, 0u);
+      *reinterpret_cast<uint4*>(S.bw + 9 * B_CHUNK + c * 16) = make_uint4(0u, 0u, 0u, 0u);
+    }
+    *reinterpret_cast<uint4*>(S.ones + ht * 16) = make_uint4(tc::pack_bf16x2(1.f, 1.f), 0u, 0u, 0u);
+    *reinterpret_cast<uint4*>(S.ones + A_CHUNK + ht * 16) = make_uint4(0u, 0u, 0u, 0u);
+    tc::fence_proxy_async_smem();
+  }
+  tc::tc_fence_before();
+  __syncthreads();
+  tc::tc_fence_after();
+  const uint32_t tmem_base = S.tmem_slot;
+
+  // ---- roles ---------------------------------------------------------------------------------
+  if (warp == 0) {
+    // ===== TMA producer =====
+    if (lane == 0) {
+      uint32_t g = 0;
+      for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const int wt = tile % tiles_w, h = (tile / tiles_w) % H, b = tile / (tiles_w * H);
+        const int w0px = wt * TW;
+        for (int k = 0; k < 9; ++k, ++g) {
+          const int dy = k / 3 - 1, dx = k % 3 - 1;
+          const uint32_t s = g % NS_D, ph = (g / NS_D) & 1;
+          tc::mbar_wait(&S.d_empty[s], ph ^ 1);
+          tc::mbar_arrive_expect_tx(&S.d_full[s], TILE_BYTES);
+          if (MODE == 0) tma::load_3d(S.dtile[s], &tm_in, &S.d_full[s], w0px + dx, h + dy, b * C);
+          else tma::load_4d(S.dtile[s], &tm_in, &S.d_full[s], w0px + dx, h + dy, 8 - k, b * C);
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    // ===== MMA issuer =====
+    if (lane == 0) {
+      const uint32_t idesc = tc::make_idesc_bf16(128, C);
+      const uint32_t b_base = tc::smem_u32(S.bw), ones_base = tc::smem_u32(S.ones);
+      uint32_t g = 0;
+      for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        for (int k = 0; k < 9; ++k, ++g) {
+          const uint32_t sa = g % NS_A, pha = (g / NS_A) & 1, st = g % NS_T, pht = (g / NS_T) & 1;
+          tc::mbar_wait(&S.a_full[sa], pha);
+          tc::mbar_wait(&S.t_empty[st], pht ^ 1);
+          tc::tc_fence_after();
+          const uint32_t d_tmem = tmem_base + st * C;
+          const uint32_t ab = tc::smem_u32(S.a[sa]);
+          uint32_t accum = 0;
+#pragma unroll
+          for (int bp = 0; bp < 2; ++bp)
+#pragma unroll
+            for (int ap = 0; ap < 2; ++ap)
+#pragma unroll
+              for (int ks = 0; ks < 2; ++ks) {
+                const uint64_t ad = tc::make_smem_desc(ab + (ap * 4 + ks * 2) * A_CHUNK, A_CHUNK, 128, tc::LAYOUT_NONE);
+                const uint64_t bd = tc::make_smem_desc(b_base + (bp * 4 + ks * 2) * B_CHUNK, B_CHUNK, 128, tc::LAYOUT_NONE);
+                tc::mma_bf16_ss(d_tmem, ad, bd, idesc, accum);
+                accum = 1;
+              }
+          tc::mma_bf16_ss(d_tmem, tc::make_smem_desc(ones_base, A_CHUNK, 128, tc::LAYOUT_NONE),
+                          tc::make_smem_desc(b_base + 8 * B_CHUNK, B_CHUNK, 128, tc::LAYOUT_NONE), idesc, 1u);
+          tc::umma_commit(&S.a_empty[sa]);  // A slot reusable once these MMAs have read it
+          tc::umma_commit(&S.t_full[st]);   // accumulator ready
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp < 6) {
+    // ===== hidden-layer producers (128 threads, thread = pixel) =====
+    const int ht = t - 64;
+    uint32_t g = 0;
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+      const int wt = tile % tiles_w, h = (tile / tiles_w) % H, b = tile / (tiles_w * H);
+      const int w0px = wt * TW;
+      tma::named_bar_sync(BAR_HID, 128);  // everyone finished reading the previous coordinate tile
+      for (int e = ht; e < 3 * CCH * ROW; e += 128) {
+        const int col = e % ROW, d = (e / ROW) % CCH, r = e / (ROW * CCH);
+        const int hh = h + r - 1, ww = w0px + col - 1;
+        float v = 0.f;
+        if (hh >= 0 && hh < H && ww >= 0 && ww < W) v = __ldg(coord + (((int64_t)b * CCH + d) * H + hh) * W + ww);
+        S.cs[(r * CCH + d) * ROW + col] = v;
+      }
+      tma::named_bar_sync(BAR_HID, 128);
+      const float c0 = S.cs[(1 * CCH + 0) * ROW + ht + 1];
+      const float c1 = S.cs[(1 * CCH + 1) * ROW + ht + 1];
+      const float c2 = S.cs[(1 * CCH + 2) * ROW + ht + 1];
+      for (int k = 0; k < 9; ++k, ++g) {
+        const int dy = k / 3 - 1, dx = k % 3 - 1;
+        const int col = ht + 1 + dx, r = dy + 1;
+        float r0 = S.cs[(r * CCH + 0) * ROW + col] - c0;
+        float r1 = S.cs[(r * CCH + 1) * ROW + col] - c1;
+        float r2 = S.cs[(r * CCH + 2) * ROW + col] - c2;
+        if (MODE == 1) { r0 = -r0; r1 = -r1; r2 = -r2; }  // rel seen from the mirrored pixel
+        const uint32_t sa = g % NS_A, pha = (g / NS_A) & 1;
+        tc::mbar_wait(&S.a_empty[sa], pha ^ 1);
+        unsigned char* abuf = S.a[sa];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          uint32_t hi[4], lo[4];
+#pragma unroll
+          for (int p = 0; p < 4; ++p) {
+            float hh[2], hl[2];
+#pragma unroll
+            for (int u = 0; u < 2; ++u) {
+              const float4 wv = S.w0b[q * 8 + 2 * p + u];
+              float z = wv.w;
+              z = fmaf(wv.x, r0, z);
+              z = fmaf(wv.y, r1, z);
+              z = fmaf(wv.z, r2, z);
+              tc::split_bf16(fmaxf(z, 0.f), hh[u], hl[u]);
+            }
+            hi[p] = tc::pack_bf16x2(hh[0], hh[1]);
+            lo[p] = tc::pack_bf16x2(hl[0], hl[1]);
+          }
+          *reinterpret_cast<uint4*>(abuf + q * A_CHUNK + ht * 16) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+          *reinterpret_cast<uint4*>(abuf + (4 + q) * A_CHUNK + ht * 16) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+        }
+        tc::fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) tc::mbar_arrive(&S.a_full[sa]);
+      }
+    }
+  } else {
+    // ===== epilogue (128 threads, thread = TMEM lane = pixel) =====
+    const int q4 = warp & 3;                 // TMEM lane quadrant this warp may read
+    const int px = q4 * 32 + lane;
+    const uint32_t lane_sel = (uint32_t)(q4 * 32) << 16;
+    const bool leader = (warp == 6 && lane == 0);
+    uint32_t g = 0, n_store = 0;
+    float gd[MODE == 1 ? C : 1];
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+      const int wt = tile % tiles_w, h = (tile / tiles_w) % H, b = tile / (tiles_w * H);
+      const int w0px = wt * TW;
+      if (MODE == 1) {
+#pragma unroll
+        for (int i = 0; i < C; ++i) gd[i] = 0.f;
+      }
+      for (int k = 0; k < 9; ++k, ++g) {
+        const uint32_t st = g % NS_T, pht = (g / NS_T) & 1, sd = g % NS_D, phd = (g / NS_D) & 1;
+        tc::mbar_wait(&S.t_full[st], pht);
+        tc::mbar_wait(&S.d_full[sd], phd);
+        __syncwarp();
+        tc::tc_fence_after();
+        const float* dt = S.dtile[sd];
+        if (MODE == 0) {
+          const uint32_t so = n_store % NS_O;
+          if (leader) tma::store_wait_read<NS_O - 1>();  // the store that last used otile[so] has read it
+          tma::named_bar_sync(BAR_EPI, 128);
+          float* ot = S.otile[so];
+#pragma unroll
+          for (int half = 0; half < 2; ++half) {
+            float v[32];
+            tc::tmem_ld_x32(tmem_base + lane_sel + st * C + half * 32, v);
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+              const int c = half * 32 + i;
+              ot[c * TW + px] = dt[c * TW + px] * v[i];
+            }
+          }
+          tc::tc_fence_before();
+          tc::fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0) {
+            tc::mbar_arrive(&S.t_empty[st]);
+            tc::mbar_arrive(&S.d_empty[sd]);
+          }
+          tma::named_bar_sync(BAR_EPI, 128);
+          if (leader) {
+            tma::store_4d(&tm_out, ot, w0px, h, k, b * C);
+            tma::store_commit();
+          }
+          ++n_store;
+        } else {
+#pragma unroll
+          for (int half = 0; half < 2; ++half) {
+            float v[32];
+            tc::tmem_ld_x32(tmem_base + lane_sel + st * C + half * 32, v);
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+              const int c = half * 32 + i;
+              gd[c] = fmaf(dt[c * TW + px], v[i], gd[c]);
+            }
+          }
+          tc::tc_fence_before();
+          __syncwarp();
+          if (lane == 0) {
+            tc::mbar_arrive(&S.t_empty[st]);
+            tc::mbar_arrive(&S.d_empty[sd]);
+          }
+        }
+      }
+      if (MODE == 1) {  // one output tile per image tile
+        const uint32_t so = n_store % NS_O;
+        if (leader) tma::store_wait_read<NS_O - 1>();
+        tma::named_bar_sync(BAR_EPI, 128);
+        float* ot = S.otile[so];
+#pragma unroll
+        for (int c = 0; c < C; ++c) ot[c * TW + px] = gd[c];
+        tc::fence_proxy_async_smem();
+        tma::named_bar_sync(BAR_EPI, 128);
+        if (leader) {
+          tma::store_3d(&tm_out, ot, w0px, h, b * C);
+          tma::store_commit();
+        }
+        ++n_store;
+      }
+    }
+    if (leader) tma::store_wait_all<0>();
+  }
+
+  // ---- teardown ------------------------------------------------------------------------------
+  tc::tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tc::tmem_dealloc(tmem_base, TMEM_COLS);
+}
+
+inline int launch(int mode, const float* tap_src, float* dst, const float* coord, const float* w0, const float* b0,
+                  const float* w1, const float* b1, int B, int Cc, int H, int W, cudaStream_t stream) {
+  RD_REQUIRE(Cc == C, "Meta-Kernel impl 3 (TMA/tcgen05) is specialised for C == 64 (got %d)", Cc);
+  RD_REQUIRE(W % 4 == 0, "Meta-Kernel impl 3 needs W %% 4 == 0 (TMA row stride must be a multiple of 16 B); W=%d", W);
+  RD_REQUIRE((reinterpret_cast<uintptr_t>(tap_src) & 15) == 0 && (reinterpret_cast<uintptr_t>(dst) & 15) == 0,
+             "Meta-Kernel impl 3 needs 16-byte aligned tensors");
+  const int tiles_w = (W + TW - 1) / TW;
+  const int64_t ntiles = (int64_t)B * H * tiles_w;
+  RD_REQUIRE(ntiles <= 0x7fffffffLL, "rd_meta_kernel: too many tiles");
+  CUtensorMap tm_in, tm_out;
+  const uint64_t plane = (uint64_t)H * W * 4;
+  // features / grad_data viewed as (W, H, B*C); out / grad_out viewed as (W, H, 9, B*C)
+  const uint64_t d3[3] = {(uint64_t)W, (uint64_t)H, (uint64_t)B * C};
+  const uint64_t s3[2] = {(uint64_t)W * 4, plane};
+  const uint32_t b3[3] = {(uint32_t)TW, 1u, (uint32_t)C};
+  const uint64_t d4[4] = {(uint64_t)W, (uint64_t)H, 9u, (uint64_t)B * C};
+  const uint64_t s4[3] = {(uint64_t)W * 4, plane, plane * 9};
+  const uint32_t b4[4] = {(uint32_t)TW, 1u, 1u, (uint32_t)C};
+  if (mode == 0) {
+    if (tma::make_map(&tm_in, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, tap_src, 3, d3, s3, b3, CU_TENSOR_MAP_SWIZZLE_NONE)) return 1;
+    if (tma::make_map(&tm_out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, dst, 4, d4, s4, b4, CU_TENSOR_MAP_SWIZZLE_NONE)) return 1;
+  } else {
+    if (tma::make_map(&tm_in, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, tap_src, 4, d4, s4, b4, CU_TENSOR_MAP_SWIZZLE_NONE)) return 1;
+    if (tma::make_map(&tm_out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, dst, 3, d3, s3, b3, CU_TENSOR_MAP_SWIZZLE_NONE)) return 1;
+  }
+  int dev = 0, sms = 0;
+  RD_CUDA(cudaGetDevice(&dev));
+  RD_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  const size_t smem = sizeof(Smem) + 1024;
+  const int64_t grid = ntiles < sms ? ntiles : sms;
+  if (mode == 0) {
+    static bool attr0 = false;
+    if (!attr0) {
+      RD_CUDA(cudaFuncSetAttribute(meta_ws_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      attr0 = true;
+    }
+    meta_ws_kernel<0><<<(unsigned)grid, NTHREADS, smem, stream>>>(tm_in, tm_out, coord, w0, b0, w1, b1, B, H, W, tiles_w,
+                                                                  (int)ntiles);
+  } else {
+    static bool attr1 = false;
+    if (!attr1) {
+      RD_CUDA(cudaFuncSetAttribute(meta_ws_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      attr1 = true;
+    }
+    meta_ws_kernel<1><<<(unsigned)grid, NTHREADS, smem, stream>>>(tm_in, tm_out, coord, w0, b0, w1, b1, B, H, W, tiles_w,
+                                                                  (int)ntiles);
+  }
+  rd::count_launch();
+  return rd::check_launch(mode == 0 ? "rd_meta_kernel_fwd(impl 3)" : "rd_meta_kernel_bwd_data(impl 3)");
+}
+
+}  // namespace mkws
+
+int rd_meta_kernel_fwd_ws(const float* data, const float* coord, const float* w0, const float* b0, const float* w1,
+                          const float* b1, float* out, int B, int C, int H, int W, cudaStream_t stream) {
+  return mkws::launch(0, data, out, coord, w0, b0, w1, b1, B, C, H, W, stream);
+}
+int rd_meta_kernel_bwd_data_ws(const float* grad_out, const float* coord, const float* w0, const float* b0,
+                               const float* w1, const float* b1, float* grad_data, int B, int C, int H, int W,
+                               cudaStream_t stream) {
+  return mkws::launch(1, grad_out, grad_data, coord, w0, b0, w1, b1, B, C, H, W, stream);
+}

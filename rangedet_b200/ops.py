@@ -18,7 +18,7 @@ import torch
 
 from . import _lib
 
-IMPL_DEFAULT, IMPL_FP32, IMPL_TCGEN05 = 0, 1, 2
+IMPL_DEFAULT, IMPL_FP32, IMPL_TCGEN05, IMPL_TMA_WS = 0, 1, 2, 3
 
 
 def _stream():

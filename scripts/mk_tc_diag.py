@@ -1,24 +1,36 @@
-"""Times the tcgen05 Meta-Kernel forward under the diagnostic switches (RD_MK_TC_DEBUG)."""
-import json, os, sys
+"""Times the Meta-Kernel kernels per implementation (CUDA events, inputs resident, B=4)."""
+import ctypes, json, os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
-from rangedet_b200 import ops, synth
-B, C = 4, 64
+from rangedet_b200 import _lib, ops, synth
+B, C, H, W = 4, 64, 64, 2656
 dev = "cuda"
 data = torch.from_numpy(synth.feature_map(B, C, seed=1)).to(dev)
 coord = torch.from_numpy(synth.range_image_coords(B, seed=0)).to(dev)
-ps = [torch.from_numpy(p).to(dev) for p in synth.meta_mlp_params(seed=2)]
-res = {}
-for dbg in sys.argv[1:] or ["0", "1", "2", "3", "4", "8", "11", "15"]:
-    os.environ["RD_MK_TC_DEBUG"] = dbg
-    for _ in range(3):
-        ops.meta_kernel_forward(data, coord, *ps, impl=2)
+w0, b0, w1, b1 = [torch.from_numpy(p).to(dev) for p in synth.meta_mlp_params(seed=2)]
+go = torch.randn(B, 9 * C, H, W, device=dev)
+out = torch.empty(B, 9 * C, H, W, device=dev)
+gd = torch.empty_like(data)
+L = _lib.lib()
+P, S = ops._p, ops._stream
+def timeit(fn, reps=10):
+    for _ in range(3): fn()
     torch.cuda.synchronize()
     a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     a.record()
-    for _ in range(10):
-        ops.meta_kernel_forward(data, coord, *ps, impl=2)
-    b.record()
-    torch.cuda.synchronize()
-    res[dbg] = a.elapsed_time(b) / 10
-print(json.dumps(res))
+    for _ in range(reps): fn()
+    b.record(); torch.cuda.synchronize()
+    return a.elapsed_time(b) / reps
+res = {}
+px = B * H * W
+for impl in (1, 2, 3):
+    os.environ.pop("RD_MK_TC_DEBUG", None)
+    ms = timeit(lambda: _lib.check(L.rd_meta_kernel_fwd(P(data), P(coord), P(w0), P(b0), P(w1), P(b1), P(out), B, C, H, W, impl, S()), "fwd"))
+    res["fwd_impl%d" % impl] = {"ms": ms, "GBps": px * 2572 / ms / 1e6}
+for impl in (1, 3):
+    ms = timeit(lambda: _lib.check(L.rd_meta_kernel_bwd_data(P(go), P(coord), P(w0), P(b0), P(w1), P(b1), P(gd), B, C, H, W, impl, S()), "bwd_data"))
+    res["bwd_data_impl%d" % impl] = {"ms": ms, "GBps": px * 2572 / ms / 1e6}
+for dbg in sys.argv[1:]:
+    os.environ["RD_MK_TC_DEBUG"] = dbg
+    res["fwd_impl2_dbg" + dbg] = {"ms": timeit(lambda: _lib.check(L.rd_meta_kernel_fwd(P(data), P(coord), P(w0), P(b0), P(w1), P(b1), P(out), B, C, H, W, 2, S()), "fwd"))}
+print(json.dumps(res, indent=1))
