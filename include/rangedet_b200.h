@@ -108,6 +108,15 @@ int rd_wnms_4c(const float* dets, int n, float thresh, float thresh_vote, int is
  */
 int rd_tc_probe_gemm(const float* a, const float* b, float* d, int n, int k, rd_stream_t stream);
 
+/* ---- TMA self-test -----------------------------------------------------------------------
+ * Loads the box (box_w, 1, 64) of a (W, H, C) fp32 tensor at signed coordinates (c0, c1, c2) through
+ * cp.async.bulk.tensor into shared memory (zero fill outside the tensor), copies it to dst
+ * (64 x box_w) and TMA-stores it to the same coordinates of dst2 (same shape as src; out-of-bound
+ * parts are dropped).  W % 4 == 0, box_w % 4 == 0, 4 <= box_w <= 256, C >= 64.
+ */
+int rd_tma_probe(const float* src, float* dst, float* dst2, int W, int H, int C, int box_w, int c0,
+                 int c1, int c2, rd_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

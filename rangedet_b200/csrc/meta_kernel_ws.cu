@@ -4,8 +4,12 @@
 // meta_kernel.py:166-240) and its data-gradient.  One CTA per SM walks (row, 128-pixel) tiles; per
 // tile 9 taps flow through four mbarrier-synchronised rings:
 //
-//   warp 0      TMA producer    feature (fwd) / grad_out (bwd) tap tile [64 ch][128 px] fp32 -> smem,
-//                               box shifted by (dy,dx): the image border is TMA's zero fill
+//   warp 0      TMA producer    feature rows (fwd: one [64 ch][136 px] box per neighbour ROW, shared by
+//                               its three dx taps) / grad_out tap planes (bwd) -> smem.  TMA tile mode
+//                               on this part faults on negative or non-16-byte-aligned coordinates
+//                               (probed: tests/test_gpu_parity.py::test_tma_probe), so boxes start at
+//                               max(w0-4, 0); rows outside the image are not loaded (treated as 0)
+//                               and the right border is TMA's zero fill
 //   warps 2-5   hidden layer    rel xyz -> relu(W0 rel + b0) fp32 -> bf16 hi|lo, K-major core-matrix
 //                               layout (A operand ring)
 //   warp 1      MMA issuer      9 x tcgen05.mma M128 N64 K16: [h_hi|h_lo] x [W1_hi|W1_lo]^T (+ bias
@@ -33,13 +37,15 @@ constexpr int A_BYTES = 8 * A_CHUNK;         // h_hi (4 chunks) | h_lo (4 chunks
 constexpr int B_CHUNK = C * 16;
 constexpr int B_BYTES = 10 * B_CHUNK;        // W1_hi | W1_lo | bias chunk | zero chunk
 constexpr int ONES_BYTES = 2 * A_CHUNK;
-constexpr int TILE_BYTES = C * TW * 4;       // 32 KB tap tile
+constexpr int DTW = TW + 8;                  // input box width: pixels [w0-4, w0+132)
+constexpr int IN_BYTES = C * DTW * 4;        // 34 KB input box
+constexpr int TILE_BYTES = C * TW * 4;       // 32 KB output tile
 constexpr int NS_D = 3, NS_O = 2, NS_A = 2, NS_T = 4;
 constexpr uint32_t TMEM_COLS = NS_T * C;     // 256
 constexpr int BAR_HID = 1, BAR_EPI = 2;      // named barriers (0 = __syncthreads)
 
 struct Smem {
-  alignas(1024) float dtile[NS_D][C * TW];
+  alignas(1024) float dtile[NS_D][C * DTW];
   alignas(1024) float otile[NS_O][C * TW];
   alignas(1024) unsigned char a[NS_A][A_BYTES];
   alignas(1024) unsigned char bw[B_BYTES];
@@ -58,8 +64,9 @@ meta_ws_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant_
                const float* __restrict__ coord, const float* __restrict__ w0, const float* __restrict__ b0,
                const float* __restrict__ w1, const float* __restrict__ b1, int B, int H, int W, int tiles_w,
                int ntiles) {
-  extern __shared__ __align__(1024) unsigned char smem_raw[];
-  Smem& S = *reinterpret_cast<Smem*>(smem_raw);
+  extern __shared__ unsigned char smem_raw[];
+  // TMA destinations need 128-byte (we use 1024) alignment; the dynamic window is only guaranteed 16
+  Smem& S = *reinterpret_cast<Smem*>(smem_raw + ((1024u - (tc::smem_u32(smem_raw) & 1023u)) & 1023u));
   const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
 
   // ---- setup ---------------------------------------------------------------------------------
@@ -116,13 +123,20 @@ meta_ws_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant_
       for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
         const int wt = tile % tiles_w, h = (tile / tiles_w) % H, b = tile / (tiles_w * H);
         const int w0px = wt * TW;
-        for (int k = 0; k < 9; ++k, ++g) {
-          const int dy = k / 3 - 1, dx = k % 3 - 1;
+        const int bs = w0px >= 4 ? w0px - 4 : 0;  // aligned, non-negative box start
+        constexpr int UNITS = MODE == 0 ? 3 : 9;  // fwd: one box per neighbour row; bwd: one per tap
+        for (int u = 0; u < UNITS; ++u, ++g) {
+          const int dy = MODE == 0 ? u - 1 : u / 3 - 1;
           const uint32_t s = g % NS_D, ph = (g / NS_D) & 1;
           tc::mbar_wait(&S.d_empty[s], ph ^ 1);
-          tc::mbar_arrive_expect_tx(&S.d_full[s], TILE_BYTES);
-          if (MODE == 0) tma::load_3d(S.dtile[s], &tm_in, &S.d_full[s], w0px + dx, h + dy, b * C);
-          else tma::load_4d(S.dtile[s], &tm_in, &S.d_full[s], w0px + dx, h + dy, 8 - k, b * C);
+          const int hh = h + dy;
+          if (hh >= 0 && hh < H) {
+            tc::mbar_arrive_expect_tx(&S.d_full[s], IN_BYTES);
+            if (MODE == 0) tma::load_3d(S.dtile[s], &tm_in, &S.d_full[s], bs, hh, b * C);
+            else tma::load_4d(S.dtile[s], &tm_in, &S.d_full[s], bs, hh, 8 - u, b * C);
+          } else {
+            tc::mbar_arrive(&S.d_full[s]);  // row outside the image: nothing to load, consumers use 0
+          }
         }
       }
     }
@@ -231,13 +245,21 @@ meta_ws_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant_
 #pragma unroll
         for (int i = 0; i < C; ++i) gd[i] = 0.f;
       }
+      const int bs = w0px >= 4 ? w0px - 4 : 0;
       for (int k = 0; k < 9; ++k, ++g) {
-        const uint32_t st = g % NS_T, pht = (g / NS_T) & 1, sd = g % NS_D, phd = (g / NS_D) & 1;
+        const int dy = k / 3 - 1, dx = k % 3 - 1;
+        const uint32_t st = g % NS_T, pht = (g / NS_T) & 1;
+        const uint32_t gu = MODE == 0 ? g / 3 : g;  // input unit (row box / tap box) this tap reads
+        const uint32_t sd = gu % NS_D, phd = (gu / NS_D) & 1;
         tc::mbar_wait(&S.t_full[st], pht);
-        tc::mbar_wait(&S.d_full[sd], phd);
+        if (MODE == 1 || dx == -1) tc::mbar_wait(&S.d_full[sd], phd);
         __syncwarp();
         tc::tc_fence_after();
-        const float* dt = S.dtile[sd];
+        // pixel read by this thread for this tap, as a column of the input box (or: outside -> 0)
+        const int col = w0px + px + dx - bs;
+        const bool ok = (h + dy >= 0) && (h + dy < H) && col >= 0;
+        const float* dt = S.dtile[sd] + (ok ? col : 0);
+        const bool last_use = MODE == 1 || dx == 1;
         if (MODE == 0) {
           const uint32_t so = n_store % NS_O;
           if (leader) tma::store_wait_read<NS_O - 1>();  // the store that last used otile[so] has read it
@@ -250,7 +272,8 @@ meta_ws_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant_
 #pragma unroll
             for (int i = 0; i < 32; ++i) {
               const int c = half * 32 + i;
-              ot[c * TW + px] = dt[c * TW + px] * v[i];
+              const float d = ok ? dt[c * DTW] : 0.f;
+              ot[c * TW + px] = d * v[i];
             }
           }
           tc::tc_fence_before();
@@ -258,7 +281,7 @@ meta_ws_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant_
           __syncwarp();
           if (lane == 0) {
             tc::mbar_arrive(&S.t_empty[st]);
-            tc::mbar_arrive(&S.d_empty[sd]);
+            if (last_use) tc::mbar_arrive(&S.d_empty[sd]);
           }
           tma::named_bar_sync(BAR_EPI, 128);
           if (leader) {
@@ -274,7 +297,8 @@ meta_ws_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant_
 #pragma unroll
             for (int i = 0; i < 32; ++i) {
               const int c = half * 32 + i;
-              gd[c] = fmaf(dt[c * TW + px], v[i], gd[c]);
+              const float d = ok ? dt[c * DTW] : 0.f;
+              gd[c] = fmaf(d, v[i], gd[c]);
             }
           }
           tc::tc_fence_before();
@@ -324,15 +348,17 @@ inline int launch(int mode, const float* tap_src, float* dst, const float* coord
   // features / grad_data viewed as (W, H, B*C); out / grad_out viewed as (W, H, 9, B*C)
   const uint64_t d3[3] = {(uint64_t)W, (uint64_t)H, (uint64_t)B * C};
   const uint64_t s3[2] = {(uint64_t)W * 4, plane};
-  const uint32_t b3[3] = {(uint32_t)TW, 1u, (uint32_t)C};
+  const uint32_t b3[3] = {(uint32_t)TW, 1u, (uint32_t)C};       // output tile
+  const uint32_t b3in[3] = {(uint32_t)DTW, 1u, (uint32_t)C};   // input row box
   const uint64_t d4[4] = {(uint64_t)W, (uint64_t)H, 9u, (uint64_t)B * C};
   const uint64_t s4[3] = {(uint64_t)W * 4, plane, plane * 9};
   const uint32_t b4[4] = {(uint32_t)TW, 1u, 1u, (uint32_t)C};
+  const uint32_t b4in[4] = {(uint32_t)DTW, 1u, 1u, (uint32_t)C};
   if (mode == 0) {
-    if (tma::make_map(&tm_in, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, tap_src, 3, d3, s3, b3, CU_TENSOR_MAP_SWIZZLE_NONE)) return 1;
+    if (tma::make_map(&tm_in, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, tap_src, 3, d3, s3, b3in, CU_TENSOR_MAP_SWIZZLE_NONE)) return 1;
     if (tma::make_map(&tm_out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, dst, 4, d4, s4, b4, CU_TENSOR_MAP_SWIZZLE_NONE)) return 1;
   } else {
-    if (tma::make_map(&tm_in, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, tap_src, 4, d4, s4, b4, CU_TENSOR_MAP_SWIZZLE_NONE)) return 1;
+    if (tma::make_map(&tm_in, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, tap_src, 4, d4, s4, b4in, CU_TENSOR_MAP_SWIZZLE_NONE)) return 1;
     if (tma::make_map(&tm_out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, dst, 3, d3, s3, b3, CU_TENSOR_MAP_SWIZZLE_NONE)) return 1;
   }
   int dev = 0, sms = 0;

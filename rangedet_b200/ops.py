@@ -187,3 +187,15 @@ def tc_probe_gemm(a, b):
         st = _lib.lib().rd_tc_probe_gemm(_p(a), _p(b), _p(d), b.shape[0], a.shape[1], _stream())
     _lib.check(st, "tc_probe_gemm")
     return d
+
+
+def tma_probe(src, box_w, c0, c1, c2):
+    """TMA self-test: returns (tile (64, box_w) loaded at signed coords, dst2 = zeros with the tile stored back)."""
+    src = _chk(src, "src", 3)
+    C, H, W = src.shape
+    dst = torch.zeros((64, box_w), device=src.device)
+    dst2 = torch.zeros_like(src)
+    with torch.cuda.device(src.device):
+        st = _lib.lib().rd_tma_probe(_p(src), _p(dst), _p(dst2), W, H, C, box_w, c0, c1, c2, _stream())
+    _lib.check(st, "tma_probe")
+    return dst, dst2

@@ -8,7 +8,10 @@ nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw --format=csv > gp
 PH="${PHASES:-base tc meta smoke bench ncu}"
 for ph in $PH; do
 case $ph in
-base)  timeout 900 python -m pytest tests/test_gpu_parity.py -m gpu -q --timeout 600 -k "not tc_probe and not meta_kernel" > gpurun_out/pytest_base.log 2>&1; echo "base exit $?" >> gpurun_out/status.txt ;;
+base)  timeout 900 python -m pytest tests/test_gpu_parity.py -m gpu -q --timeout 600 -k "not tc_probe and not tma_probe and not meta_kernel" > gpurun_out/pytest_base.log 2>&1; echo "base exit $?" >> gpurun_out/status.txt ;;
+tma)   RD_TMA_PROBE_VERBOSE=1 timeout 300 compute-sanitizer python -m pytest tests/test_gpu_parity.py -m gpu -q -x --timeout 120 -k "tma_probe" -s > gpurun_out/pytest_tma.log 2>&1; echo "tma exit $?" >> gpurun_out/status.txt ;;
+dbgws) timeout 300 python scripts/dbg_ws.py fwd > gpurun_out/dbg_ws_fwd.log 2>&1; echo "dbgws-fwd exit $?" >> gpurun_out/status.txt
+       timeout 300 python scripts/dbg_ws.py bwd > gpurun_out/dbg_ws_bwd.log 2>&1; echo "dbgws-bwd exit $?" >> gpurun_out/status.txt ;;
 tc)    timeout 300 python -m pytest tests/test_gpu_parity.py -m gpu -q --timeout 120 -k "tc_probe" > gpurun_out/pytest_tc.log 2>&1; echo "tc exit $?" >> gpurun_out/status.txt ;;
 meta)  timeout 900 python -m pytest tests/test_gpu_parity.py -m gpu -q --timeout 600 -k "meta_kernel" > gpurun_out/pytest_meta.log 2>&1; echo "meta exit $?" >> gpurun_out/status.txt ;;
 smoke) timeout 600 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/smoke.log 2>&1; echo "smoke exit $?" >> gpurun_out/status.txt ;;

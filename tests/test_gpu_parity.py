@@ -50,6 +50,26 @@ def test_tc_probe_gemm(ops, n, k):
     assert err < 1e-5, err
 
 
+@pytest.mark.parametrize("box_w,c0,c1,c2", [(128, 0, 0, 0), (128, 4, 2, 0), (128, 200, 2, 0), (136, 132, 2, 0),
+                                            (128, 0, 5, 0), (128, 0, 2, 64), (64, 60, 4, 64)])
+def test_tma_probe(ops, box_w, c0, c1, c2):
+    """TMA tile-mode rules this library relies on (probed on B200, scripts/tma_case.py): boxes may hang
+    over the HIGH side of any dimension (zero fill on load, dropped on store); coordinates must be
+    non-negative and the inner one 16-byte aligned (c0 = 1, -4, -128 and c1 = -1 all fault with
+    'illegal instruction', which is why the Meta-Kernel loads start at max(w0 - 4, 0))."""
+    C, H, W = 128, 5, 264
+    src = torch.randn(C, H, W, device="cuda")
+    tile, back = ops.tma_probe(src, box_w, c0, c1, c2)
+    want = torch.zeros(64, box_w, device="cuda")
+    want_back = torch.zeros_like(src)
+    if 0 <= c1 < H:
+        lo, hi = max(c0, 0), min(c0 + box_w, W)
+        want[:, lo - c0:hi - c0] = src[c2:c2 + 64, c1, lo:hi]
+        want_back[c2:c2 + 64, c1, lo:hi] = src[c2:c2 + 64, c1, lo:hi]
+    assert torch.equal(tile, want)          # out-of-bound elements are zero-filled
+    assert torch.equal(back, want_back)     # out-of-bound parts of a store are dropped
+
+
 # ---------------------------------------------------------------------------------------------
 # decode
 # ---------------------------------------------------------------------------------------------
