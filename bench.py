@@ -309,7 +309,7 @@ def run_ours(args, rank, local_rank, world):
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": WORKLOAD, "batch_per_gpu": B, "global_batch": B * world,
                        "parallelism": "dp%d (frames sharded; NCCL all-reduce of MLP param grads)" % world,
-                       "mk_impl": {0: "default", 1: "cuda-core fp32", 2: "tcgen05"}[impl],
+                       "mk_impl": {0: "default (TMA+tcgen05 warp-specialised)", 1: "cuda-core fp32", 2: "tcgen05", 3: "TMA+tcgen05 warp-specialised"}[impl],
                        "l2": "inputs larger than L2 (3.5 GB touched per step vs 126 MB L2)"},
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "clocks": clocks, "gpu_launches": int(launches),
         }
@@ -324,7 +324,7 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--mk-impl", type=int, default=0, choices=[0, 1, 2])
+    ap.add_argument("--mk-impl", type=int, default=0, choices=[0, 1, 2, 3])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))

@@ -103,10 +103,12 @@ int rd_wnms_4c(const float* dets, int n, float thresh, float thresh_vote, int is
  * D(128 x n) = A(128 x k) . B(n x k)^T with bf16 operands staged in shared memory in the
  * canonical no-swizzle K-major core-matrix layout, tcgen05.mma into TMEM, tcgen05.ld back.
  * Used by tests to validate the descriptor encodings the fused kernels rely on.
+ * mn_major = 1 stages both operands in the MN-major canonical layout instead (same math).
  * a (128,k) b (n,k) fp32 (rounded to bf16 inside), d (128,n) fp32; k % 16 == 0, k <= 128,
  * n % 16 == 0, 16 <= n <= 256.
  */
-int rd_tc_probe_gemm(const float* a, const float* b, float* d, int n, int k, rd_stream_t stream);
+int rd_tc_probe_gemm(const float* a, const float* b, float* d, int n, int k, int mn_major,
+                     rd_stream_t stream);
 
 /* ---- TMA self-test -----------------------------------------------------------------------
  * Loads the box (box_w, 1, 64) of a (W, H, C) fp32 tensor at signed coordinates (c0, c1, c2) through

@@ -485,6 +485,9 @@ int rd_meta_kernel_fwd_ws(const float* data, const float* coord, const float* w0
 int rd_meta_kernel_bwd_data_ws(const float* grad_out, const float* coord, const float* w0, const float* b0,
                                const float* w1, const float* b1, float* grad_data, int B, int C, int H, int W,
                                cudaStream_t stream);
+int rd_meta_kernel_bwd_params_ws(const float* grad_out, const float* data, const float* coord, const float* w0,
+                                 const float* b0, const float* w1, float* partial, int* nparts, int B, int C, int H,
+                                 int W, cudaStream_t stream);
 // implemented in meta_kernel_tc.cu (impl 2)
 int rd_meta_kernel_fwd_tc(const float* data, const float* coord, const float* w0, const float* b0,
                           const float* w1, const float* b1, float* out, int B, int C, int H, int W,
@@ -502,6 +505,8 @@ int rd_meta_kernel_fwd(const float* data, const float* coord, const float* w0, c
   if (B == 0) return 0;
   RD_REQUIRE(data && coord && w0 && b0 && w1 && b1 && out, "rd_meta_kernel_fwd: null pointer");
   if (rd_check_device()) return 1;
+  if (impl == 0)  // default: TMA/tcgen05 kernel when its preconditions hold, generic fp32 kernel otherwise
+    impl = (C == 64 && W % 4 == 0 && ((reinterpret_cast<uintptr_t>(data) | reinterpret_cast<uintptr_t>(out)) & 15) == 0) ? 3 : 1;
   if (impl == 3) return rd_meta_kernel_fwd_ws(data, coord, w0, b0, w1, b1, out, B, C, H, W, rd::as_stream(stream));
   if (impl == 2) return rd_meta_kernel_fwd_tc(data, coord, w0, b0, w1, b1, out, B, C, H, W, rd::as_stream(stream));
   const int tiles_w = (W + mk::F_TW - 1) / mk::F_TW;
@@ -531,6 +536,8 @@ int rd_meta_kernel_bwd_data(const float* grad_out, const float* coord, const flo
   if (B == 0) return 0;
   RD_REQUIRE(grad_out && coord && w0 && b0 && w1 && b1 && grad_data, "rd_meta_kernel_bwd_data: null pointer");
   if (rd_check_device()) return 1;
+  if (impl == 0)
+    impl = (C == 64 && W % 4 == 0 && ((reinterpret_cast<uintptr_t>(grad_out) | reinterpret_cast<uintptr_t>(grad_data)) & 15) == 0) ? 3 : 1;
   if (impl == 3)
     return rd_meta_kernel_bwd_data_ws(grad_out, coord, w0, b0, w1, b1, grad_data, B, C, H, W, rd::as_stream(stream));
   const int tiles_w = (W + mk::G_TW - 1) / mk::G_TW;
@@ -570,6 +577,16 @@ int rd_meta_kernel_bwd_params(const float* grad_out, const float* data, const fl
              rd_meta_kernel_bwd_workspace_bytes(B, C, H, W));
   float* partial = static_cast<float*>(workspace);
   const int nout = C * mk::HID + C + mk::HID * 4;
+  if (impl == 0)
+    impl = (C == 64 && W % 4 == 0 && ((reinterpret_cast<uintptr_t>(grad_out) | reinterpret_cast<uintptr_t>(data)) & 15) == 0) ? 3 : 1;
+  if (impl == 3) {
+    int nparts = 0;
+    if (rd_meta_kernel_bwd_params_ws(grad_out, data, coord, w0, b0, w1, partial, &nparts, B, C, H, W, st)) return 1;
+    mk::meta_bwd_param_reduce_kernel<<<(nout + 255) / 256, 256, 0, st>>>(partial, nparts, C, grad_w0, grad_b0, grad_w1,
+                                                                         grad_b1);
+    rd::count_launch();
+    return rd::check_launch("rd_meta_kernel_bwd_params(reduce)");
+  }
   const int tiles_w = (W + mk::P_TW - 1) / mk::P_TW;
   const int64_t ntiles = (int64_t)B * H * tiles_w;
   RD_REQUIRE(ntiles <= 0x7fffffffLL, "rd_meta_kernel_bwd_params: too many tiles");

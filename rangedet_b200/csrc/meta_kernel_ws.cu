@@ -267,14 +267,15 @@ meta_ws_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant_
           float* ot = S.otile[so];
 #pragma unroll
           for (int half = 0; half < 2; ++half) {
+            // all 32 tap-tile loads first: the stores below may alias them as far as the compiler
+            // knows, so interleaving would expose the full shared-memory latency per element
+            float d[32];
+#pragma unroll
+            for (int i = 0; i < 32; ++i) d[i] = ok ? dt[(half * 32 + i) * DTW] : 0.f;
             float v[32];
             tc::tmem_ld_x32(tmem_base + lane_sel + st * C + half * 32, v);
 #pragma unroll
-            for (int i = 0; i < 32; ++i) {
-              const int c = half * 32 + i;
-              const float d = ok ? dt[c * DTW] : 0.f;
-              ot[c * TW + px] = d * v[i];
-            }
+            for (int i = 0; i < 32; ++i) ot[(half * 32 + i) * TW + px] = d[i] * v[i];
           }
           tc::tc_fence_before();
           tc::fence_proxy_async_smem();
@@ -292,14 +293,13 @@ meta_ws_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant_
         } else {
 #pragma unroll
           for (int half = 0; half < 2; ++half) {
+            float d[32];
+#pragma unroll
+            for (int i = 0; i < 32; ++i) d[i] = ok ? dt[(half * 32 + i) * DTW] : 0.f;
             float v[32];
             tc::tmem_ld_x32(tmem_base + lane_sel + st * C + half * 32, v);
 #pragma unroll
-            for (int i = 0; i < 32; ++i) {
-              const int c = half * 32 + i;
-              const float d = ok ? dt[c * DTW] : 0.f;
-              gd[c] = fmaf(d, v[i], gd[c]);
-            }
+            for (int i = 0; i < 32; ++i) gd[half * 32 + i] = fmaf(d[i], v[i], gd[half * 32 + i]);
           }
           tc::tc_fence_before();
           __syncwarp();

@@ -1,0 +1,388 @@
+// Meta-Kernel impl 3, MLP-parameter gradients: persistent, warp-specialised, TMA-fed tcgen05 kernel.
+//
+// Gradient of MetaKernel.meta_baseline_bias (/root/reference rangedet/symbol/backbone/
+// meta_kernel.py:166-240) w.r.t. mlp0/mlp1 weights and biases.  Per (row, 128-pixel) tile and tap k:
+//   gw[p][c]   = grad_out[p, c*9+k] * data[p+dk, c]                      (CUDA cores, fp32)
+//   hid[p][j]  = relu(W0 . rel + b0)                                     (recomputed, fp32)
+//   G1  ghid[p][j] = sum_c gw[p][c] W1[c][j]      tcgen05  M=128 px, N=32, K=64(x hi/lo)  -> TMEM D1
+//   G2  gW1[c][j] += sum_p gw[p][c] hid[p][j]     tcgen05  M=128 (c x hi/lo), N=80 (j x hi/lo | 1),
+//                   gb1[c] += sum_p gw[p][c]       K=128 px, MN-major views of the SAME smem tiles,
+//                                                  accumulated in TMEM across all taps and tiles
+//   gW0[j][d] += sum_p relu'(.) ghid[p][j] rel[p][d], gb0 likewise        (fp32 register accumulators)
+// bf16 hi+lo splits of gw / hid / W1 keep every product within ~2^-16 of fp32.
+// Roles: warp 0 TMA producer (grad_out tap tiles + feature row boxes), warp 1 MMA issuer,
+// warps 2-5 builders (operand tiles, D1 consumption).  One partial result row per CTA goes to the
+// workspace; the deterministic reduce kernel of meta_kernel.cu finishes the sum.
+#include "../../include/rangedet_b200.h"
+#include "rd_common.cuh"
+#include "tc_common.cuh"
+#include "tma_common.cuh"
+
+namespace mkwp {
+
+constexpr int HID = 32, CCH = 3, C = 64;
+constexpr int TW = 128, ROW = TW + 2, DTW = TW + 8;
+constexpr int NTHREADS = 192;                 // warp 0 TMA, warp 1 MMA, warps 2-5 builders
+constexpr int CHUNK = TW * 16;                // one 16-byte chunk over 128 pixel rows (2048 B)
+constexpr int GW_BYTES = 16 * CHUNK;          // gw_hi (8 chunks of 8 channels) | gw_lo (8 chunks)
+constexpr int H_BYTES = 10 * CHUNK;           // h_hi (4) | h_lo (4) | ones chunk | zero chunk
+constexpr int W1T_CHUNK = HID * 16;           // W1^T[j][c]: 32 rows per 16-byte chunk
+constexpr int W1T_BYTES = 16 * W1T_CHUNK;     // hi (8 chunks over c) | lo (8 chunks)
+constexpr int GO_BYTES = C * TW * 4;          // 32 KB grad_out tap tile
+constexpr int DROW_BYTES = C * DTW * 4;       // 34 KB feature row box
+constexpr int NS_G = 2, NS_R = 2;
+constexpr uint32_t TMEM_COLS = 256;           // D1: 2 x 32 columns at 0/32, D2: 80 columns at 64
+constexpr uint32_t D2_COL = 64;
+constexpr int BAR_BLD = 1;
+constexpr int NOUT = C * HID + C + HID * 4;
+
+struct Smem {
+  alignas(1024) float go[NS_G][C * TW];
+  alignas(1024) float drow[NS_R][C * DTW];
+  alignas(1024) unsigned char gw[GW_BYTES];
+  alignas(1024) unsigned char h[H_BYTES];
+  alignas(1024) unsigned char w1t[W1T_BYTES];
+  alignas(16) float4 w0b[HID];
+  alignas(16) float cs[3 * CCH * ROW];
+  alignas(8) uint64_t go_full[NS_G], go_empty[NS_G], dr_full[NS_R], dr_empty[NS_R], ops_full, ops_free,
+      d1_full[2], d1_empty[2];
+  uint32_t tmem_slot;
+};
+
+__global__ void __launch_bounds__(NTHREADS, 1)
+meta_ws_params_kernel(const __grid_constant__ CUtensorMap tm_go, const __grid_constant__ CUtensorMap tm_data,
+                      const float* __restrict__ coord, const float* __restrict__ w0, const float* __restrict__ b0,
+                      const float* __restrict__ w1, float* __restrict__ partial, int B, int H, int W, int tiles_w,
+                      int ntiles) {
+  extern __shared__ unsigned char smem_raw[];
+  Smem& S = *reinterpret_cast<Smem*>(smem_raw + ((1024u - (tc::smem_u32(smem_raw) & 1023u)) & 1023u));
+  const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+
+  if (t == 0) {
+    for (int i = 0; i < NS_G; ++i) { tc::mbar_init(&S.go_full[i], 1); tc::mbar_init(&S.go_empty[i], 4); }
+    for (int i = 0; i < NS_R; ++i) { tc::mbar_init(&S.dr_full[i], 1); tc::mbar_init(&S.dr_empty[i], 4); }
+    tc::mbar_init(&S.ops_full, 4);
+    tc::mbar_init(&S.ops_free, 1);
+    for (int i = 0; i < 2; ++i) { tc::mbar_init(&S.d1_full[i], 1); tc::mbar_init(&S.d1_empty[i], 4); }
+    tc::fence_mbar_init();
+    tma::prefetch_map(&tm_go);
+    tma::prefetch_map(&tm_data);
+  }
+  if (warp == 1) {
+    tc::tmem_alloc(&S.tmem_slot, TMEM_COLS);
+    tc::tmem_relinquish();
+  }
+  if (warp >= 2) {  // constants: layer-0 params, W1^T hi/lo in K-major core-matrix layout, ones/zero chunks of H
+    const int bt = t - 64;
+    for (int j = bt; j < HID; j += 128)
+      S.w0b[j] = make_float4(__ldg(w0 + j * 3 + 0), __ldg(w0 + j * 3 + 1), __ldg(w0 + j * 3 + 2), __ldg(b0 + j));
+    for (int e = bt; e < HID * 8; e += 128) {  // chunk q (8 channels c = 8q..8q+7) of row j
+      const int j = e % HID, q = e / HID;
+      uint32_t hi[4], lo[4];
+#pragma unroll
+      for (int p = 0; p < 4; ++p) {
+        float h0, l0, h1, l1;
+        tc::split_bf16(__ldg(w1 + (q * 8 + 2 * p) * HID + j), h0, l0);
+        tc::split_bf16(__ldg(w1 + (q * 8 + 2 * p + 1) * HID + j), h1, l1);
+        hi[p] = tc::pack_bf16x2(h0, h1);
+        lo[p] = tc::pack_bf16x2(l0, l1);
+      }
+      *reinterpret_cast<uint4*>(S.w1t + q * W1T_CHUNK + j * 16) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+      *reinterpret_cast<uint4*>(S.w1t + (8 + q) * W1T_CHUNK + j * 16) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+    }
+    *reinterpret_cast<uint4*>(S.h + 8 * CHUNK + bt * 16) = make_uint4(tc::pack_bf16x2(1.f, 0.f), 0u, 0u, 0u);
+    *reinterpret_cast<uint4*>(S.h + 9 * CHUNK + bt * 16) = make_uint4(0u, 0u, 0u, 0u);
+    tc::fence_proxy_async_smem();
+  }
+  tc::tc_fence_before();
+  __syncthreads();
+  tc::tc_fence_after();
+  const uint32_t tmem_base = S.tmem_slot;
+
+  if (warp == 0) {
+    // ===== TMA producer: per tile 3 feature row boxes + 9 grad_out tap tiles, in consumption order =====
+    if (lane == 0) {
+      uint32_t gg = 0, gr = 0;
+      for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const int wt = tile % tiles_w, h = (tile / tiles_w) % H, b = tile / (tiles_w * H);
+        const int w0px = wt * TW;
+        const int bs = w0px >= 4 ? w0px - 4 : 0;
+        for (int k = 0; k < 9; ++k, ++gg) {
+          if (k % 3 == 0) {
+            const int hh = h + k / 3 - 1;
+            const uint32_t s = gr % NS_R, ph = (gr / NS_R) & 1;
+            tc::mbar_wait(&S.dr_empty[s], ph ^ 1);
+            if (hh >= 0 && hh < H) {
+              tc::mbar_arrive_expect_tx(&S.dr_full[s], DROW_BYTES);
+              tma::load_3d(S.drow[s], &tm_data, &S.dr_full[s], bs, hh, b * C);
+            } else {
+              tc::mbar_arrive(&S.dr_full[s]);
+            }
+            ++gr;
+          }
+          const uint32_t s = gg % NS_G, ph = (gg / NS_G) & 1;
+          tc::mbar_wait(&S.go_empty[s], ph ^ 1);
+          tc::mbar_arrive_expect_tx(&S.go_full[s], GO_BYTES);
+          tma::load_4d(S.go[s], &tm_go, &S.go_full[s], w0px, h, k, b * C);
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    // ===== MMA issuer =====
+    if (lane == 0) {
+      const uint32_t idesc1 = tc::make_idesc_bf16(128, HID);            // G1: K-major A and B
+      const uint32_t idesc2 = tc::make_idesc_bf16(128, 80, 1, 1);       // G2: MN-major A and B
+      const uint32_t gw_base = tc::smem_u32(S.gw), h_base = tc::smem_u32(S.h), w1t_base = tc::smem_u32(S.w1t);
+      uint32_t g = 0;
+      for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        for (int k = 0; k < 9; ++k, ++g) {
+          const uint32_t s1 = g & 1, ph1 = (g >> 1) & 1;
+          tc::mbar_wait(&S.ops_full, g & 1);
+          tc::mbar_wait(&S.d1_empty[s1], ph1 ^ 1);
+          tc::tc_fence_after();
+          // G1: D1[px][j] = gw[px][c] . W1T[j][c]^T   (all four hi/lo cross terms)
+          uint32_t accum = 0;
+#pragma unroll
+          for (int bp = 0; bp < 2; ++bp)
+#pragma unroll
+            for (int ap = 0; ap < 2; ++ap)
+#pragma unroll
+              for (int ks = 0; ks < 4; ++ks) {
+                const uint64_t ad = tc::make_smem_desc(gw_base + (ap * 8 + ks * 2) * CHUNK, CHUNK, 128, tc::LAYOUT_NONE);
+                const uint64_t bd = tc::make_smem_desc(w1t_base + (bp * 8 + ks * 2) * W1T_CHUNK, W1T_CHUNK, 128, tc::LAYOUT_NONE);
+                tc::mma_bf16_ss(tmem_base + s1 * HID, ad, bd, idesc1, accum);
+                accum = 1;
+              }
+          tc::umma_commit(&S.d1_full[s1]);
+          // G2: D2[(c,part)][(j,part)|1] += gw^T . [h | 1]   -- MN-major views: MN block stride = CHUNK
+          // (8 channels / hidden units per chunk), K block (8 pixels) stride = 128 B, K step = 16 px
+#pragma unroll
+          for (int ks = 0; ks < 8; ++ks) {
+            const uint64_t ad = tc::make_smem_desc(gw_base + ks * 256, 128, CHUNK, tc::LAYOUT_NONE);
+            const uint64_t bd = tc::make_smem_desc(h_base + ks * 256, 128, CHUNK, tc::LAYOUT_NONE);
+            tc::mma_bf16_ss(tmem_base + D2_COL, ad, bd, idesc2, (g > 0 || ks > 0) ? 1u : 0u);
+          }
+          tc::umma_commit(&S.ops_free);
+        }
+      }
+    }
+    __syncwarp();
+  } else {
+    // ===== builders (128 threads, thread = pixel = TMEM lane) =====
+    const int bt = t - 64;
+    const int q4 = warp & 3;
+    const int px = q4 * 32 + lane;  // NOTE: bt != px in general; tiles are indexed by px everywhere below
+    const uint32_t lane_sel = (uint32_t)(q4 * 32) << 16;
+    float acc0[HID][4];  // gW0[j][d], d == 3 -> gb0[j]
+#pragma unroll
+    for (int j = 0; j < HID; ++j)
+#pragma unroll
+      for (int d = 0; d < 4; ++d) acc0[j][d] = 0.f;
+    uint32_t g = 0, gr = 0;
+    bool have_prev = false;
+    uint32_t prev_mask = 0, prev_g = 0;
+    float prev_rel[3] = {0.f, 0.f, 0.f};
+
+    auto consume_d1 = [&](uint32_t gp, uint32_t mask, const float* rel) {
+      const uint32_t s1 = gp & 1, ph1 = (gp >> 1) & 1;
+      tc::mbar_wait(&S.d1_full[s1], ph1);
+      __syncwarp();
+      tc::tc_fence_after();
+      float v[32];
+      tc::tmem_ld_x32(tmem_base + lane_sel + s1 * HID, v);
+      tc::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) tc::mbar_arrive(&S.d1_empty[s1]);
+#pragma unroll
+      for (int j = 0; j < HID; ++j) {
+        const float gh = ((mask >> j) & 1u) ? v[j] : 0.f;
+        acc0[j][0] = fmaf(gh, rel[0], acc0[j][0]);
+        acc0[j][1] = fmaf(gh, rel[1], acc0[j][1]);
+        acc0[j][2] = fmaf(gh, rel[2], acc0[j][2]);
+        acc0[j][3] += gh;
+      }
+    };
+
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+      const int wt = tile % tiles_w, h = (tile / tiles_w) % H, b = tile / (tiles_w * H);
+      const int w0px = wt * TW;
+      const int bs = w0px >= 4 ? w0px - 4 : 0;
+      tma::named_bar_sync(BAR_BLD, 128);
+      for (int e = bt; e < 3 * CCH * ROW; e += 128) {
+        const int col = e % ROW, d = (e / ROW) % CCH, r = e / (ROW * CCH);
+        const int hh = h + r - 1, ww = w0px + col - 1;
+        float v = 0.f;
+        if (hh >= 0 && hh < H && ww >= 0 && ww < W) v = __ldg(coord + (((int64_t)b * CCH + d) * H + hh) * W + ww);
+        S.cs[(r * CCH + d) * ROW + col] = v;
+      }
+      tma::named_bar_sync(BAR_BLD, 128);
+      const float c0 = S.cs[(1 * CCH + 0) * ROW + px + 1];
+      const float c1 = S.cs[(1 * CCH + 1) * ROW + px + 1];
+      const float c2 = S.cs[(1 * CCH + 2) * ROW + px + 1];
+      const bool px_ok = (w0px + px) < W;  // tile overhang: these pixels contribute nothing
+
+      for (int k = 0; k < 9; ++k, ++g) {
+        const int dy = k / 3 - 1, dx = k % 3 - 1;
+        // ---- hidden layer of (pixel, tap), kept packed in registers
+        const int ccol = px + 1 + dx, r = dy + 1;
+        const float r0 = S.cs[(r * CCH + 0) * ROW + ccol] - c0;
+        const float r1 = S.cs[(r * CCH + 1) * ROW + ccol] - c1;
+        const float r2 = S.cs[(r * CCH + 2) * ROW + ccol] - c2;
+        uint32_t hhi[16], hlo[16], mask = 0;
+#pragma unroll
+        for (int jp = 0; jp < 16; ++jp) {
+          float hh[2], hl[2];
+#pragma unroll
+          for (int u = 0; u < 2; ++u) {
+            const float4 wv = S.w0b[jp * 2 + u];
+            float z = wv.w;
+            z = fmaf(wv.x, r0, z);
+            z = fmaf(wv.y, r1, z);
+            z = fmaf(wv.z, r2, z);
+            const float hv = fmaxf(z, 0.f);
+            mask |= (hv > 0.f ? 1u : 0u) << (jp * 2 + u);
+            tc::split_bf16(hv, hh[u], hl[u]);
+          }
+          hhi[jp] = tc::pack_bf16x2(hh[0], hh[1]);
+          hlo[jp] = tc::pack_bf16x2(hl[0], hl[1]);
+        }
+        // ---- inputs of this tap
+        const uint32_t sg = g % NS_G, phg = (g / NS_G) & 1;
+        const uint32_t sr = gr % NS_R, phr = (gr / NS_R) & 1;
+        tc::mbar_wait(&S.go_full[sg], phg);
+        if (dx == -1) tc::mbar_wait(&S.dr_full[sr], phr);
+        const int col = w0px + px + dx - bs;
+        const bool ok = px_ok && (h + dy >= 0) && (h + dy < H) && col >= 0;
+        const float* gt = S.go[sg] + px;
+        const float* dt = S.drow[sr] + (ok ? col : 0);
+        // ---- operand tiles may be overwritten once the previous tap's MMAs have read them
+        tc::mbar_wait(&S.ops_free, (g & 1) ^ 1);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          *reinterpret_cast<uint4*>(S.h + q * CHUNK + px * 16) =
+              make_uint4(hhi[q * 4 + 0], hhi[q * 4 + 1], hhi[q * 4 + 2], hhi[q * 4 + 3]);
+          *reinterpret_cast<uint4*>(S.h + (4 + q) * CHUNK + px * 16) =
+              make_uint4(hlo[q * 4 + 0], hlo[q * 4 + 1], hlo[q * 4 + 2], hlo[q * 4 + 3]);
+        }
+#pragma unroll
+        for (int cb = 0; cb < 8; ++cb) {  // 8 channels per 16-byte chunk
+          float gv[8], dv[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            gv[i] = gt[(cb * 8 + i) * TW];
+            dv[i] = ok ? dt[(cb * 8 + i) * DTW] : 0.f;
+          }
+          uint32_t hi[4], lo[4];
+#pragma unroll
+          for (int p = 0; p < 4; ++p) {
+            float h0, l0, h1, l1;
+            tc::split_bf16(gv[2 * p] * dv[2 * p], h0, l0);
+            tc::split_bf16(gv[2 * p + 1] * dv[2 * p + 1], h1, l1);
+            hi[p] = tc::pack_bf16x2(h0, h1);
+            lo[p] = tc::pack_bf16x2(l0, l1);
+          }
+          *reinterpret_cast<uint4*>(S.gw + cb * CHUNK + px * 16) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+          *reinterpret_cast<uint4*>(S.gw + (8 + cb) * CHUNK + px * 16) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+        }
+        tc::fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) {
+          tc::mbar_arrive(&S.ops_full);
+          tc::mbar_arrive(&S.go_empty[sg]);
+          if (dx == 1) tc::mbar_arrive(&S.dr_empty[sr]);
+        }
+        if (dx == 1) ++gr;
+        // ---- consume the previous tap's D1 while this tap's MMAs run
+        if (have_prev) consume_d1(prev_g, prev_mask, prev_rel);
+        have_prev = true;
+        prev_g = g;
+        prev_mask = ok ? mask : 0u;  // (gw is 0 for !ok pixels, so ghid is 0 anyway)
+        prev_rel[0] = r0; prev_rel[1] = r1; prev_rel[2] = r2;
+      }
+    }
+    if (have_prev) consume_d1(prev_g, prev_mask, prev_rel);
+    const uint32_t g_total = g;
+
+    // ---- CTA result: gW0/gb0 from registers (cross-thread sum through smem), gW1/gb1 from TMEM D2
+    tma::named_bar_sync(BAR_BLD, 128);                 // all builders finished with go / drow tiles
+    float* red = reinterpret_cast<float*>(S.go);       // 128 x 128 floats = 64 KB = the two go stages
+#pragma unroll
+    for (int j = 0; j < HID; ++j)
+#pragma unroll
+      for (int d = 0; d < 4; ++d) red[(j * 4 + d) * 128 + px] = acc0[j][d];
+    tma::named_bar_sync(BAR_BLD, 128);
+    float* prow = partial + (int64_t)blockIdx.x * NOUT;
+    {
+      float s = 0.f;
+      for (int i = 0; i < 128; ++i) s += red[bt * 128 + ((i + bt) & 127)];
+      prow[C * HID + C + bt] = s;  // (j,d) -> j*4+d, as the reduce kernel expects
+    }
+    tma::named_bar_sync(BAR_BLD, 128);
+    if (g_total > 0) {
+      tc::mbar_wait(&S.ops_free, (g_total - 1) & 1);   // last G2 complete
+      __syncwarp();
+      tc::tc_fence_after();
+      float v[32], u[32], wv[16];
+      tc::tmem_ld_x32(tmem_base + lane_sel + D2_COL, v);        // x h_hi
+      tc::tmem_ld_x32(tmem_base + lane_sel + D2_COL + 32, u);   // x h_lo
+      tc::tmem_ld_x16(tmem_base + lane_sel + D2_COL + 64, wv);  // x [1, 0...]
+      float* stage = red;  // [128 rows][33]
+#pragma unroll
+      for (int j = 0; j < 32; ++j) stage[px * 33 + j] = v[j] + u[j];
+      stage[px * 33 + 32] = wv[0];
+    } else {
+      for (int j = 0; j < 33; ++j) red[px * 33 + j] = 0.f;
+    }
+    tma::named_bar_sync(BAR_BLD, 128);
+    if (bt < C) {
+      const float* a = red + bt * 33;
+      const float* bb = red + (bt + C) * 33;   // gw_lo rows
+      for (int j = 0; j < HID; ++j) prow[bt * HID + j] = a[j] + bb[j];
+      prow[C * HID + bt] = a[32] + bb[32];
+    }
+  }
+
+  tc::tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tc::tmem_dealloc(tmem_base, TMEM_COLS);
+}
+
+}  // namespace mkwp
+
+// partial must hold gridDim rows of NOUT floats; returns the number of rows written in *nparts
+int rd_meta_kernel_bwd_params_ws(const float* grad_out, const float* data, const float* coord, const float* w0,
+                                 const float* b0, const float* w1, float* partial, int* nparts, int B, int C, int H,
+                                 int W, cudaStream_t stream) {
+  using namespace mkwp;
+  RD_REQUIRE(C == mkwp::C, "Meta-Kernel impl 3 (TMA/tcgen05) is specialised for C == 64 (got %d)", C);
+  RD_REQUIRE(W % 4 == 0, "Meta-Kernel impl 3 needs W %% 4 == 0; W=%d", W);
+  const int tiles_w = (W + TW - 1) / TW;
+  const int64_t ntiles = (int64_t)B * H * tiles_w;
+  RD_REQUIRE(ntiles <= 0x7fffffffLL, "rd_meta_kernel_bwd_params: too many tiles");
+  CUtensorMap tm_go, tm_data;
+  const uint64_t plane = (uint64_t)H * W * 4;
+  const uint64_t d3[3] = {(uint64_t)W, (uint64_t)H, (uint64_t)B * C};
+  const uint64_t s3[2] = {(uint64_t)W * 4, plane};
+  const uint32_t b3in[3] = {(uint32_t)DTW, 1u, (uint32_t)C};
+  const uint64_t d4[4] = {(uint64_t)W, (uint64_t)H, 9u, (uint64_t)B * C};
+  const uint64_t s4[3] = {(uint64_t)W * 4, plane, plane * 9};
+  const uint32_t b4[4] = {(uint32_t)TW, 1u, 1u, (uint32_t)C};
+  if (tma::make_map(&tm_go, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, grad_out, 4, d4, s4, b4, CU_TENSOR_MAP_SWIZZLE_NONE)) return 1;
+  if (tma::make_map(&tm_data, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, data, 3, d3, s3, b3in, CU_TENSOR_MAP_SWIZZLE_NONE)) return 1;
+  int dev = 0, sms = 0;
+  RD_CUDA(cudaGetDevice(&dev));
+  RD_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  const size_t smem = sizeof(Smem) + 1024;
+  const int64_t grid = ntiles < sms ? ntiles : sms;
+  static bool attr = false;
+  if (!attr) {
+    RD_CUDA(cudaFuncSetAttribute(meta_ws_params_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr = true;
+  }
+  meta_ws_params_kernel<<<(unsigned)grid, NTHREADS, smem, stream>>>(tm_go, tm_data, coord, w0, b0, w1, partial, B, H, W,
+                                                                     tiles_w, (int)ntiles);
+  rd::count_launch();
+  *nparts = (int)grid;
+  return rd::check_launch("rd_meta_kernel_bwd_params(impl 3)");
+}

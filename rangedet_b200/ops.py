@@ -179,12 +179,12 @@ def wnms_4c_device(dets, thresh, thresh_vote, is_3d=False, hash_scale=100):
     return out[:k], keep[:k]
 
 
-def tc_probe_gemm(a, b):
+def tc_probe_gemm(a, b, mn_major=False):
     """D = A . B^T through tcgen05 (bf16 operands): a (128,k), b (n,k) -> (128,n)."""
     a, b = _chk(a, "a", 2), _chk(b, "b", 2)
     d = torch.empty((128, b.shape[0]), device=a.device, dtype=torch.float32)
     with torch.cuda.device(a.device):
-        st = _lib.lib().rd_tc_probe_gemm(_p(a), _p(b), _p(d), b.shape[0], a.shape[1], _stream())
+        st = _lib.lib().rd_tc_probe_gemm(_p(a), _p(b), _p(d), b.shape[0], a.shape[1], int(bool(mn_major)), _stream())
     _lib.check(st, "tc_probe_gemm")
     return d
 

@@ -15,13 +15,12 @@ dbgws) timeout 300 python scripts/dbg_ws.py fwd > gpurun_out/dbg_ws_fwd.log 2>&1
 tc)    timeout 300 python -m pytest tests/test_gpu_parity.py -m gpu -q --timeout 120 -k "tc_probe" > gpurun_out/pytest_tc.log 2>&1; echo "tc exit $?" >> gpurun_out/status.txt ;;
 meta)  timeout 900 python -m pytest tests/test_gpu_parity.py -m gpu -q --timeout 600 -k "meta_kernel" > gpurun_out/pytest_meta.log 2>&1; echo "meta exit $?" >> gpurun_out/status.txt ;;
 smoke) timeout 600 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/smoke.log 2>&1; echo "smoke exit $?" >> gpurun_out/status.txt ;;
-bench) timeout 900 python bench.py --steps 10 --warmup 3 --mk-impl 1 > gpurun_out/bench_impl1.json 2> gpurun_out/bench_impl1.err; echo "bench1 exit $?" >> gpurun_out/status.txt
-       timeout 600 python bench.py --steps 10 --warmup 3 --mk-impl 2 --no-cpu-baseline > gpurun_out/bench_impl2.json 2> gpurun_out/bench_impl2.err; echo "bench2 exit $?" >> gpurun_out/status.txt ;;
+bench) timeout 900 python bench.py --steps 20 --warmup 3 > gpurun_out/bench_default.json 2> gpurun_out/bench_default.err; echo "bench exit $?" >> gpurun_out/status.txt ;;
 ncu)   timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 80 --csv --log-file gpurun_out/launches.csv python bench.py --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_launch.log 2>&1; echo "ncu-list exit $?" >> gpurun_out/status.txt
        timeout 900 ncu --set full --clock-control none --import-source on -k regex:meta_ -s 8 -c 4 -o gpurun_out/prof_meta -f python bench.py --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_full.log 2>&1; echo "ncu-full exit $?" >> gpurun_out/status.txt ;;
 diag)  timeout 600 python scripts/mk_tc_diag.py > gpurun_out/mk_tc_diag.json 2> gpurun_out/mk_tc_diag.err; echo "diag exit $?" >> gpurun_out/status.txt ;;
 ncutc) timeout 900 ncu --set full --clock-control none --import-source on -k regex:meta_fwd_tc -s 3 -c 1 -o gpurun_out/prof_meta_tc -f python scripts/mk_tc_diag.py 0 > gpurun_out/ncu_tc.log 2>&1; echo "ncu-tc exit $?" >> gpurun_out/status.txt ;;
-ncuws) timeout 900 ncu --set full --clock-control none --import-source on -k regex:meta_ws -s 6 -c 2 -o gpurun_out/prof_meta_ws -f python scripts/mk_tc_diag.py > gpurun_out/ncu_ws.log 2>&1; echo "ncu-ws exit $?" >> gpurun_out/status.txt ;;
+ncuws) timeout 900 ncu --set full --clock-control none --import-source on -k regex:meta_ws -s 3 -c 5 -o gpurun_out/prof_meta_ws -f python scripts/mk_tc_diag.py > gpurun_out/ncu_ws.log 2>&1; echo "ncu-ws exit $?" >> gpurun_out/status.txt ;;
 esac
 done
 cat gpurun_out/status.txt

@@ -30,6 +30,11 @@ for impl in (1, 2, 3):
 for impl in (1, 3):
     ms = timeit(lambda: _lib.check(L.rd_meta_kernel_bwd_data(P(go), P(coord), P(w0), P(b0), P(w1), P(b1), P(gd), B, C, H, W, impl, S()), "bwd_data"))
     res["bwd_data_impl%d" % impl] = {"ms": ms, "GBps": px * 2572 / ms / 1e6}
+gws = [torch.empty(96, device=dev), torch.empty(32, device=dev), torch.empty(C * 32, device=dev), torch.empty(C, device=dev)]
+ws = torch.empty(int(L.rd_meta_kernel_bwd_workspace_bytes(B, C, H, W)) // 4 + 1, device=dev)
+for impl in (1, 3):
+    ms = timeit(lambda: _lib.check(L.rd_meta_kernel_bwd_params(P(go), P(data), P(coord), P(w0), P(b0), P(w1), P(b1), P(gws[0]), P(gws[1]), P(gws[2]), P(gws[3]), P(ws), ctypes.c_size_t(ws.numel() * 4), B, C, H, W, impl, S()), "bwd_params"))
+    res["bwd_params_impl%d" % impl] = {"ms": ms, "GBps": px * 2572 / ms / 1e6}
 for dbg in sys.argv[1:]:
     os.environ["RD_MK_TC_DEBUG"] = dbg
     res["fwd_impl2_dbg" + dbg] = {"ms": timeit(lambda: _lib.check(L.rd_meta_kernel_fwd(P(data), P(coord), P(w0), P(b0), P(w1), P(b1), P(out), B, C, H, W, 2, S()), "fwd"))}

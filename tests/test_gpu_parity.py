@@ -38,15 +38,16 @@ def ops():
 # ---------------------------------------------------------------------------------------------
 # tcgen05 descriptor self-test
 # ---------------------------------------------------------------------------------------------
-@pytest.mark.parametrize("n,k", [(64, 16), (64, 32), (64, 96), (16, 16), (128, 64), (256, 128)])
-def test_tc_probe_gemm(ops, n, k):
+@pytest.mark.parametrize("mn_major", [False, True])
+@pytest.mark.parametrize("n,k", [(64, 16), (64, 32), (64, 96), (16, 16), (128, 64), (256, 128), (80, 128)])
+def test_tc_probe_gemm(ops, n, k, mn_major):
     g = torch.Generator().manual_seed(n * 1000 + k)
     a = torch.randn(128, k, generator=g)
     b = torch.randn(n, k, generator=g)
     want = a.bfloat16().float() @ b.bfloat16().float().t()
-    got = ops.tc_probe_gemm(a.cuda(), b.cuda()).cpu()
+    got = ops.tc_probe_gemm(a.cuda(), b.cuda(), mn_major=mn_major).cpu()
     err = rel_err(got.numpy(), want.numpy())
-    report(test="tc_probe", n=n, k=k, rel_err=err)
+    report(test="tc_probe", n=n, k=k, mn_major=mn_major, rel_err=err)
     assert err < 1e-5, err
 
 
@@ -275,7 +276,7 @@ def test_meta_kernel_autograd_and_properties(ops):
         assert torch.equal(o2, o1 * 2)
         assert torch.equal(ops.meta_kernel_forward(d, *args, impl=impl), o1)  # deterministic
         assert not ops.meta_kernel_forward(torch.zeros_like(d), *args, impl=impl).any()
-        assert not o1[..., W:].any()  # padded columns (zero features) stay zero
+        assert not o1[..., W + 1:].any()  # columns whose whole 3x3 window has zero features stay zero
         del o1, o2
     dd = d[:, :, :8, :256].clone().requires_grad_(True)
     ps = [p.clone().requires_grad_(True) for p in args[1:]]
