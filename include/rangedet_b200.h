@@ -99,6 +99,21 @@ int rd_wnms_4c(const float* dets, int n, float thresh, float thresh_vote, int is
                int hash_scale, float* out_dets, int32_t* keep_inds, int* out_count,
                void* workspace, size_t workspace_bytes, rd_stream_t stream);
 
+/* ---- Convolution (DLA backbone / RPN head) ---------------------------------------------------
+ * Replaces mx.sym.Convolution (+ inference-form BatchNorm, ReLU, residual add) as used by
+ * mxnext/simple.py:123-158 from rangedet/symbol/backbone/dla_backbone.py:17-56 and
+ * rangedet/symbol/head/builder.py:198-266.  Stride 1; ksize 3 (pad 1) or 1.
+ *   x_pad        bf16 [N][H+2][W+2][Cin]   NHWC with a one-pixel ZERO halo
+ *   w_packed     bf16 [ksize*ksize][Cout][Cin]     (tap = ky*ksize + kx, cross-correlation)
+ *   scale, shift fp32 [Cout] or NULL (-> 1, 0):  y = relu?( conv * scale + shift (+ residual) )
+ *   residual_pad bf16 [N][H+2][W+2][Cout] or NULL
+ *   y_pad        bf16 [N][H+2][W+2][Cout]  interior written, halo left untouched (keep it zero)
+ * Cin, Cout in {64, 128} (pad narrower layers with zero channels).
+ */
+int rd_conv2d_nhwc_bf16(const void* x_pad, const void* w_packed, const float* scale, const float* shift,
+                        const void* residual_pad, void* y_pad, int N, int H, int W, int Cin, int Cout,
+                        int ksize, int relu, rd_stream_t stream);
+
 /* ---- tcgen05 self-test -------------------------------------------------------------------
  * D(128 x n) = A(128 x k) . B(n x k)^T with bf16 operands staged in shared memory in the
  * canonical no-swizzle K-major core-matrix layout, tcgen05.mma into TMEM, tcgen05.ld back.

@@ -199,3 +199,58 @@ def tma_probe(src, box_w, c0, c1, c2):
         st = _lib.lib().rd_tma_probe(_p(src), _p(dst), _p(dst2), W, H, C, box_w, c0, c1, c2, _stream())
     _lib.check(st, "tma_probe")
     return dst, dst2
+
+
+# ------------------------------------------------------------------------------------------------
+# Convolutions (NHWC bf16, zero-haloed activations)
+# ------------------------------------------------------------------------------------------------
+def to_nhwc_padded(x_nchw, channels=None):
+    """(N,C,H,W) float -> haloed NHWC bf16 (N,H+2,W+2,C') with zero halo (and zero channel padding)."""
+    N, C, H, W = x_nchw.shape
+    Cp = channels or C
+    out = torch.zeros((N, H + 2, W + 2, Cp), device=x_nchw.device, dtype=torch.bfloat16)
+    out[:, 1:H + 1, 1:W + 1, :C] = x_nchw.permute(0, 2, 3, 1).to(torch.bfloat16)
+    return out
+
+
+def from_nhwc_padded(y_pad, channels=None):
+    """haloed NHWC bf16 -> (N,C,H,W) float32 interior."""
+    y = y_pad[:, 1:-1, 1:-1, :channels] if channels else y_pad[:, 1:-1, 1:-1, :]
+    return y.permute(0, 3, 1, 2).float().contiguous()
+
+
+def pack_conv_weight(w_oihw, cin=None, cout=None):
+    """(Cout,Cin,kh,kw) -> bf16 [kh*kw][Cout'][Cin'] (zero padded), the layout rd_conv2d_nhwc_bf16 expects."""
+    co, ci, kh, kw = w_oihw.shape
+    cin, cout = cin or ci, cout or co
+    out = torch.zeros((kh * kw, cout, cin), device=w_oihw.device, dtype=torch.bfloat16)
+    out[:, :co, :ci] = w_oihw.permute(2, 3, 0, 1).reshape(kh * kw, co, ci).to(torch.bfloat16)
+    return out
+
+
+def conv2d_nhwc(x_pad, w_packed, scale=None, shift=None, relu=False, residual_pad=None, out=None):
+    """y = relu?(conv(x) * scale + shift (+ residual)); x_pad / residual_pad / result are haloed NHWC bf16."""
+    if x_pad.dtype != torch.bfloat16 or w_packed.dtype != torch.bfloat16 or not x_pad.is_cuda:
+        raise TypeError("conv2d_nhwc expects CUDA bf16 tensors")
+    x_pad, w_packed = x_pad.contiguous(), w_packed.contiguous()
+    N, Hp, Wp, Cin = x_pad.shape
+    taps, Cout, Cin2 = w_packed.shape
+    if Cin2 != Cin or taps not in (1, 9):
+        raise ValueError("weight shape %s does not match input channels %d" % (tuple(w_packed.shape), Cin))
+    H, W = Hp - 2, Wp - 2
+    if out is None:
+        out = torch.zeros((N, Hp, Wp, Cout), device=x_pad.device, dtype=torch.bfloat16)
+    f = lambda v: _p(v.float().contiguous()) if v is not None else None
+    sc = scale.float().contiguous() if scale is not None else None
+    sh = shift.float().contiguous() if shift is not None else None
+    if residual_pad is not None:
+        residual_pad = residual_pad.contiguous()
+        if tuple(residual_pad.shape) != (N, Hp, Wp, Cout) or residual_pad.dtype != torch.bfloat16:
+            raise ValueError("residual must be haloed NHWC bf16 with Cout channels")
+    with torch.cuda.device(x_pad.device):
+        st = _lib.lib().rd_conv2d_nhwc_bf16(_p(x_pad), _p(w_packed), _p(sc) if sc is not None else None,
+                                            _p(sh) if sh is not None else None,
+                                            _p(residual_pad) if residual_pad is not None else None, _p(out),
+                                            N, H, W, Cin, Cout, 3 if taps == 9 else 1, int(bool(relu)), _stream())
+    _lib.check(st, "conv2d_nhwc")
+    return out

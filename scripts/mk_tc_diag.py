@@ -38,4 +38,12 @@ for impl in (1, 3):
 for dbg in sys.argv[1:]:
     os.environ["RD_MK_TC_DEBUG"] = dbg
     res["fwd_impl2_dbg" + dbg] = {"ms": timeit(lambda: _lib.check(L.rd_meta_kernel_fwd(P(data), P(coord), P(w0), P(b0), P(w1), P(b1), P(out), B, C, H, W, 2, S()), "fwd"))}
+# convolutions: the two dominant shapes of the DLA backbone / head
+for (n, cin, cout, h, w) in [(4, 64, 64, 64, 2656), (4, 128, 128, 64, 664), (4, 128, 128, 64, 2656)]:
+    x = ops.to_nhwc_padded(torch.randn(n, cin, h, w, device=dev))
+    wt = ops.pack_conv_weight(torch.randn(cout, cin, 3, 3, device=dev) * 0.05)
+    y = torch.zeros((n, h + 2, w + 2, cout), device=dev, dtype=torch.bfloat16)
+    ms = timeit(lambda: ops.conv2d_nhwc(x, wt, None, None, relu=True, out=y))
+    fl = 2.0 * n * h * w * cin * cout * 9
+    res["conv3x3_%d_%d_w%d" % (cin, cout, w)] = {"ms": ms, "TFLOPs": fl / ms / 1e9}
 print(json.dumps(res, indent=1))
