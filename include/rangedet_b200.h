@@ -99,20 +99,28 @@ int rd_wnms_4c(const float* dets, int n, float thresh, float thresh_vote, int is
                int hash_scale, float* out_dets, int32_t* keep_inds, int* out_count,
                void* workspace, size_t workspace_bytes, rd_stream_t stream);
 
-/* ---- Convolution (DLA backbone / RPN head) ---------------------------------------------------
- * Replaces mx.sym.Convolution (+ inference-form BatchNorm, ReLU, residual add) as used by
- * mxnext/simple.py:123-158 from rangedet/symbol/backbone/dla_backbone.py:17-56 and
- * rangedet/symbol/head/builder.py:198-266.  Stride 1; ksize 3 (pad 1) or 1.
- *   x_pad        bf16 [N][H+2][W+2][Cin]   NHWC with a one-pixel ZERO halo
- *   w_packed     bf16 [ksize*ksize][Cout][Cin]     (tap = ky*ksize + kx, cross-correlation)
- *   scale, shift fp32 [Cout] or NULL (-> 1, 0):  y = relu?( conv * scale + shift (+ residual) )
- *   residual_pad bf16 [N][H+2][W+2][Cout] or NULL
- *   y_pad        bf16 [N][H+2][W+2][Cout]  interior written, halo left untouched (keep it zero)
- * Cin, Cout in {64, 128} (pad narrower layers with zero channels).
+/* ---- Convolution family (DLA backbone / RPN head) -------------------------------------------
+ * Replaces mx.sym.Convolution / mx.sym.Deconvolution (+ inference-form BatchNorm, ReLU, residual
+ * add) as emitted by mxnext/simple.py:123-158,545-580 for rangedet/symbol/backbone/
+ * dla_backbone.py:17-56,95,116-127 and rangedet/symbol/head/builder.py:198-266.
+ *   x_pad        bf16 [N][H+2][W+2][Cin]    NHWC with a one-pixel ZERO halo
+ *   w_packed     bf16 [taps][Cout][Cin]     conv: tap = ky*ksize + kx (cross-correlation);
+ *                                            deconv: tap = ky*kw + kx of the (Cin,Cout,3,kw) weight
+ *   scale, shift fp32 [Cout] or NULL (-> 1, 0)
+ *   residual_pad bf16 haloed NHWC at OUTPUT resolution, or NULL
+ *   y_pad        bf16 haloed NHWC; interior written, halo left untouched (keep it zero)
+ * rd_conv2d:   y = relu?( conv(x) * scale + shift + residual ); ksize 3 (pad 1) or 1; H-stride 1,
+ *              W-stride stride_w in {1,2} (W even); output width W / stride_w.
+ * rd_deconv2d: y = relu?( deconv(x) * scale + shift ) + residual; kernel (3,kw), stride (1,kw/2),
+ *              pad (1,kw/4) for kw in {8,4} (the two shapes of agg_stage); output width W * kw/2.
+ * Cin: multiple of 64 (<= 1024); Cout: 64 or 128.  Pad narrower layers with zero channels.
  */
 int rd_conv2d_nhwc_bf16(const void* x_pad, const void* w_packed, const float* scale, const float* shift,
                         const void* residual_pad, void* y_pad, int N, int H, int W, int Cin, int Cout,
-                        int ksize, int relu, rd_stream_t stream);
+                        int ksize, int stride_w, int relu, rd_stream_t stream);
+int rd_deconv2d_nhwc_bf16(const void* x_pad, const void* w_packed, const float* scale, const float* shift,
+                          const void* residual_pad, void* y_pad, int N, int H, int W, int Cin, int Cout,
+                          int kw, int relu, rd_stream_t stream);
 
 /* ---- tcgen05 self-test -------------------------------------------------------------------
  * D(128 x n) = A(128 x k) . B(n x k)^T with bf16 operands staged in shared memory in the

@@ -33,7 +33,8 @@ SIGNATURES = {
     "rd_batch_rotated_iou_max": (_i, [_vp, _vp, _vp, _i, _i64, _i, _i, _vp]),
     "rd_wnms_4c_workspace_bytes": (_sz, [_i]),
     "rd_wnms_4c": (_i, [_vp, _i, _f, _f, _i, _i, _vp, _vp, ctypes.POINTER(_i), _vp, _sz, _vp]),
-    "rd_conv2d_nhwc_bf16": (_i, [_vp] * 6 + [_i] * 7 + [_vp]),
+    "rd_conv2d_nhwc_bf16": (_i, [_vp] * 6 + [_i] * 8 + [_vp]),
+    "rd_deconv2d_nhwc_bf16": (_i, [_vp] * 6 + [_i] * 7 + [_vp]),
     "rd_tc_probe_gemm": (_i, [_vp, _vp, _vp, _i, _i, _i, _vp]),
     "rd_tma_probe": (_i, [_vp, _vp, _vp] + [_i] * 7 + [_vp]),
 }

@@ -1,22 +1,29 @@
-// Implicit-GEMM 2-D convolution (3x3 pad 1 or 1x1, stride 1) on tcgen05 tensor cores, NHWC bf16.
+// Implicit-GEMM 2-D convolution family on tcgen05 tensor cores, NHWC bf16 (sm_100a).
 //
 // Replaces the dense contractions of the DLA backbone / RPN head that the reference delegates to
-// mx.sym.Convolution -> cuDNN (/root/reference mxnext/simple.py:123-158; call sites
-// rangedet/symbol/backbone/dla_backbone.py:23-50,95 and rangedet/symbol/head/builder.py:198-266),
-// with the following BatchNorm (inference form: per-channel scale/shift), ReLU and residual add
-// (dla_backbone.py:31-56) folded into the epilogue.
+// MXNet/cuDNN: mx.sym.Convolution (/root/reference mxnext/simple.py:123-158) and
+// mx.sym.Deconvolution (mxnext/simple.py:545-580); call sites rangedet/symbol/backbone/
+// dla_backbone.py:23-56 (3x3, stride (1,1) and (1,2), 1x1 projections), :95 (1x1 576->64
+// aggregation conv after the Meta-Kernel), :120-127 (deconv (3,8)/(1,4)/(1,2) and (3,4)/(1,2)/(1,1))
+// and rangedet/symbol/head/builder.py:198-266.  The following inference-form BatchNorm (per-channel
+// scale/shift), ReLU and residual add are folded into the epilogue.
 //
-// GEMM view per output tile:  M = 128 consecutive pixels of one image row, N = Cout (64 | 128),
-// K = taps x Cin.  Activations live in HBM as zero-haloed NHWC bf16 [N][H+2][W+2][C] so that every
-// tap is a plain TMA box (this part's TMA faults on negative coordinates); a box is 64 channels
-// (128 B, one 128B-swizzle atom) x 128 pixels = the K-major A operand of four K=16 MMAs.  Weights
-// are pre-packed [tap][Cout][Cin] bf16; when all taps fit (<= 80 KB) they stay resident in shared
-// memory for the whole persistent CTA, otherwise they stream with the activations.
-//   warp 0  TMA producer      warp 1  MMA issuer (tcgen05.mma M128 x Cout x K16, fp32 in TMEM,
-//   warps 2-5 epilogue         two accumulators so tile i+1's MMAs overlap tile i's epilogue)
-// Epilogue: tcgen05.ld -> x scale[c] + shift[c] (+ residual) -> ReLU -> bf16 -> 128B-swizzled
-// staging tile -> TMA store into the interior view of the haloed output.
+// GEMM view per tile: M = 128 consecutive output-resolution columns of one image row, N = Cout,
+// K = taps x Cin.  Activations are zero-haloed NHWC bf16 [N][H+2][W+2][C], so every tap is a plain
+// TMA box with non-negative coordinates (this part's TMA faults on negative ones): 64 channels
+// (128 B = one 128B-swizzle atom) x 128 pixels = the K-major A operand of four K=16 MMAs; a W-stride
+// of 2 is the tensor map's element stride.  A transposed convolution with W-stride S is S phase
+// convolutions that share input tiles: each phase gets its own TMEM accumulator.
+// The per-tile work is a small "tap program" (Params::loads): for each input tile offset, the list
+// of (accumulator, weight tap) pairs that consume it.  Weights are pre-packed [tap][Cout][Cin]; when
+// they all fit in shared memory they stay resident for the whole persistent CTA, otherwise each
+// use streams its 64-channel weight tile through the same ring as the activations.
+//   warp 0  TMA producer      warp 1  MMA issuer (tcgen05.mma M128 x Cout x K16, fp32 in TMEM)
+//   warps 2-5 epilogue: tcgen05.ld -> x scale + shift (+ residual) -> ReLU -> bf16 ->
+//       conv: 128B-swizzled staging tile -> TMA store into the interior view of the haloed output
+//       deconv: each thread owns S consecutive output pixels -> direct 16-byte stores
 #include <cuda_bf16.h>
+#include <string.h>
 
 #include "../../include/rangedet_b200.h"
 #include "rd_common.cuh"
@@ -25,38 +32,50 @@
 
 namespace conv {
 
-constexpr int TM = 128;              // pixels per tile
-constexpr int KC = 64;               // channels per TMA box / swizzle atom
-constexpr int A_BYTES = TM * KC * 2; // 16 KB
+constexpr int TM = 128;               // GEMM rows per tile
+constexpr int KC = 64;                // channels per TMA box / swizzle atom
+constexpr int SLOT = TM * KC * 2;     // 16 KB ring slot (A tile, or a 128-row weight tile)
 constexpr int NTHREADS = 192;
 constexpr int BAR_EPI = 1;
+constexpr int MAX_LOADS = 9, MAX_USES = 4, MAX_STAGES = 12;
+
+struct Load {
+  int8_t dy, dx;            // offsets in the haloed input frame (already >= 0)
+  uint8_t nuse;
+  uint8_t acc[MAX_USES];    // accumulator (phase) fed by this input tile
+  uint8_t tap[MAX_USES];    // packed weight tap
+};
 
 struct Params {
-  int N, H, W, Cin, Cout, taps;      // taps = 9 (3x3, pad 1) or 1 (1x1)
+  int N, H, W_out_tiles;    // W_out_tiles: GEMM-row extent along W (output cols for conv, input cols for deconv)
+  int Cin, Cout;
   int tiles_w, ntiles;
-  int relu, has_residual;
-  int b_resident, nstages;
-  int a_off, b_off, o_off, misc_off; // byte offsets into the 1024-aligned dynamic shared memory
-  int stage_bytes;
+  int in_stride_w;          // input pixels advanced per GEMM row (1, or 2 for W-strided conv)
+  int nacc, nloads, ntaps;
+  int relu, has_residual, res_after_relu;
+  int deconv_s;             // 0: convolution (TMA-store epilogue); S>0: transposed conv, phase count S
+  int b_resident, nstages, acc_bufs;
+  int ring_off, w_off, o_off, misc_off;
+  int64_t y_row, y_img;     // element strides of the haloed output (deconv / residual addressing)
+  Load loads[MAX_LOADS];
 };
 
 __global__ void __launch_bounds__(NTHREADS, 1)
-conv_fprop_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_w,
-                  const __grid_constant__ CUtensorMap tm_y, const float* __restrict__ scale,
-                  const float* __restrict__ shift, const __nv_bfloat16* __restrict__ residual,
-                  int64_t res_row_stride, int64_t res_img_stride, const Params P) {
+conv_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_w,
+            const __grid_constant__ CUtensorMap tm_y, const float* __restrict__ scale,
+            const float* __restrict__ shift, const __nv_bfloat16* __restrict__ residual,
+            __nv_bfloat16* __restrict__ y_interior, const __grid_constant__ Params P) {
   extern __shared__ unsigned char smem_raw[];
   unsigned char* base = smem_raw + ((1024u - (tc::smem_u32(smem_raw) & 1023u)) & 1023u);
   const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
-  const int kh = P.Cin / KC;                    // K boxes per tap
-  const int nh = P.Cout / KC;                   // output halves
-  const int b_tile = P.Cout * KC * 2;           // one (tap, k-half) weight tile
-  unsigned char* sA = base + P.a_off;           // stages: [A boxes | (B tiles if streaming)]
-  unsigned char* sB = base + P.b_off;           // resident weights
-  unsigned char* sO = base + P.o_off;           // epilogue staging, nh x 16 KB
+  const int kh = P.Cin / KC, nh = P.Cout / KC;
+  const int b_tile = P.Cout * KC * 2;
+  unsigned char* ring = base + P.ring_off;
+  unsigned char* sW = base + P.w_off;
+  unsigned char* sO = base + P.o_off;
   uint64_t* full = reinterpret_cast<uint64_t*>(base + P.misc_off);
-  uint64_t* empty = full + 8;
-  uint64_t* t_full = empty + 8;
+  uint64_t* empty = full + MAX_STAGES;
+  uint64_t* t_full = empty + MAX_STAGES;
   uint64_t* t_empty = t_full + 2;
   uint64_t* w_full = t_empty + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(w_full + 1);
@@ -70,10 +89,10 @@ conv_fprop_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
     tc::fence_mbar_init();
     tma::prefetch_map(&tm_x);
     tma::prefetch_map(&tm_w);
-    tma::prefetch_map(&tm_y);
+    if (!P.deconv_s) tma::prefetch_map(&tm_y);
   }
   if (warp == 1) {
-    tc::tmem_alloc(tmem_slot, 256);
+    tc::tmem_alloc(tmem_slot, 512);
     tc::tmem_relinquish();
   }
   for (int c = t; c < P.Cout; c += NTHREADS) {
@@ -84,32 +103,39 @@ conv_fprop_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
   __syncthreads();
   tc::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  const int units = P.taps * kh;  // pipeline stages consumed per tile
+  const uint32_t acc_stride = (uint32_t)P.Cout;             // columns per accumulator
+  const uint32_t buf_stride = (uint32_t)(P.nacc * P.Cout);  // columns per accumulator set
 
   if (warp == 0) {
     // ===== TMA producer =====
     if (lane == 0) {
-      if (P.b_resident) {  // all weight tiles once
-        tc::mbar_arrive_expect_tx(w_full, (uint32_t)(units * b_tile));
-        for (int tap = 0; tap < P.taps; ++tap)
-          for (int q = 0; q < kh; ++q)
-            tma::load_3d(sB + (tap * kh + q) * b_tile, &tm_w, w_full, q * KC, 0, tap);
+      if (P.b_resident) {
+        tc::mbar_arrive_expect_tx(w_full, (uint32_t)(P.ntaps * kh * b_tile));
+        for (int tap = 0; tap < P.ntaps; ++tap)
+          for (int q = 0; q < kh; ++q) tma::load_3d(sW + (tap * kh + q) * b_tile, &tm_w, w_full, q * KC, 0, tap);
       }
       uint32_t g = 0;
       for (int tile = blockIdx.x; tile < P.ntiles; tile += gridDim.x) {
         const int wt = tile % P.tiles_w, h = (tile / P.tiles_w) % P.H, n = tile / (P.tiles_w * P.H);
         const int w0 = wt * TM;
-        for (int tap = 0; tap < P.taps; ++tap) {
-          const int dy = P.taps == 9 ? tap / 3 : 1, dx = P.taps == 9 ? tap % 3 : 1;  // offsets into the halo frame
-          for (int q = 0; q < kh; ++q, ++g) {
-            const uint32_t s = g % P.nstages, ph = (g / P.nstages) & 1;
-            tc::mbar_wait(&empty[s], ph ^ 1);
-            unsigned char* st = sA + s * P.stage_bytes;
-            tc::mbar_arrive_expect_tx(&full[s], (uint32_t)(A_BYTES + (P.b_resident ? 0 : b_tile)));
-            tma::load_4d(st, &tm_x, &full[s], q * KC, w0 + dx, h + dy, n);
-            if (!P.b_resident) tma::load_3d(st + A_BYTES, &tm_w, &full[s], q * KC, 0, tap);
+        for (int q = 0; q < kh; ++q)
+          for (int l = 0; l < P.nloads; ++l) {
+            const Load& L = P.loads[l];
+            {
+              const uint32_t s = g % P.nstages, ph = (g / P.nstages) & 1;
+              tc::mbar_wait(&empty[s], ph ^ 1);
+              tc::mbar_arrive_expect_tx(&full[s], (uint32_t)SLOT);
+              tma::load_4d(ring + s * SLOT, &tm_x, &full[s], q * KC, w0 * P.in_stride_w + L.dx, h + L.dy, n);
+              ++g;
+            }
+            if (!P.b_resident)
+              for (int u = 0; u < L.nuse; ++u, ++g) {
+                const uint32_t s = g % P.nstages, ph = (g / P.nstages) & 1;
+                tc::mbar_wait(&empty[s], ph ^ 1);
+                tc::mbar_arrive_expect_tx(&full[s], (uint32_t)b_tile);
+                tma::load_3d(ring + s * SLOT, &tm_w, &full[s], q * KC, 0, L.tap[u]);
+              }
           }
-        }
       }
     }
     __syncwarp();
@@ -120,31 +146,49 @@ conv_fprop_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
       if (P.b_resident) tc::mbar_wait(w_full, 0);
       uint32_t g = 0, it = 0;
       for (int tile = blockIdx.x; tile < P.ntiles; tile += gridDim.x, ++it) {
-        const uint32_t acc = it & 1, pha = (it >> 1) & 1;
-        tc::mbar_wait(&t_empty[acc], pha ^ 1);
+        const uint32_t buf = P.acc_bufs == 2 ? (it & 1) : 0;
+        const uint32_t use_n = P.acc_bufs == 2 ? (it >> 1) : it;  // how many times this buffer was used before
+        tc::mbar_wait(&t_empty[buf], (use_n & 1) ^ 1);
         tc::tc_fence_after();
-        const uint32_t d_tmem = tmem_base + acc * 128;
-        for (int u = 0; u < units; ++u, ++g) {
-          const uint32_t s = g % P.nstages, ph = (g / P.nstages) & 1;
-          tc::mbar_wait(&full[s], ph);
-          tc::tc_fence_after();
-          const uint32_t a_addr = tc::smem_u32(sA + s * P.stage_bytes);
-          const uint32_t b_addr = P.b_resident ? tc::smem_u32(sB + u * b_tile) : a_addr + A_BYTES;
+        uint32_t started = 0;  // accumulators that already hold a partial sum for this tile
+        for (int q = 0; q < kh; ++q)
+          for (int l = 0; l < P.nloads; ++l) {
+            const Load& L = P.loads[l];
+            const uint32_t sa = g % P.nstages, pha = (g / P.nstages) & 1;
+            tc::mbar_wait(&full[sa], pha);
+            ++g;
+            const uint32_t a_addr = tc::smem_u32(ring + sa * SLOT);
+            for (int u = 0; u < L.nuse; ++u) {
+              uint32_t b_addr, sb = 0;
+              if (P.b_resident) {
+                b_addr = tc::smem_u32(sW + (L.tap[u] * kh + q) * b_tile);
+              } else {
+                sb = g % P.nstages;
+                tc::mbar_wait(&full[sb], (g / P.nstages) & 1);
+                ++g;
+                b_addr = tc::smem_u32(ring + sb * SLOT);
+              }
+              tc::tc_fence_after();
+              const uint32_t d_tmem = tmem_base + buf * buf_stride + L.acc[u] * acc_stride;
+              const uint32_t bit = 1u << L.acc[u];
 #pragma unroll
-          for (int ks = 0; ks < KC / 16; ++ks) {
-            // 128B-swizzled K-major tiles: 8-row groups 1024 B apart, K advances 32 B inside the atom
-            const uint64_t ad = tc::make_smem_desc(a_addr + ks * 32, 0, 1024, tc::LAYOUT_SW128);
-            const uint64_t bd = tc::make_smem_desc(b_addr + ks * 32, 0, 1024, tc::LAYOUT_SW128);
-            tc::mma_bf16_ss(d_tmem, ad, bd, idesc, (u > 0 || ks > 0) ? 1u : 0u);
+              for (int ks = 0; ks < KC / 16; ++ks) {
+                // 128B-swizzled K-major tiles: 8-row groups 1024 B apart, K advances 32 B inside the atom
+                const uint64_t ad = tc::make_smem_desc(a_addr + ks * 32, 0, 1024, tc::LAYOUT_SW128);
+                const uint64_t bd = tc::make_smem_desc(b_addr + ks * 32, 0, 1024, tc::LAYOUT_SW128);
+                tc::mma_bf16_ss(d_tmem, ad, bd, idesc, ((started & bit) || ks > 0) ? 1u : 0u);
+              }
+              started |= bit;
+              if (!P.b_resident) tc::umma_commit(&empty[sb]);
+            }
+            tc::umma_commit(&empty[sa]);
           }
-          tc::umma_commit(&empty[s]);
-        }
-        tc::umma_commit(&t_full[acc]);
+        tc::umma_commit(&t_full[buf]);
       }
     }
     __syncwarp();
   } else {
-    // ===== epilogue: thread = pixel row = TMEM lane =====
+    // ===== epilogue: thread = GEMM row = TMEM lane =====
     const int q4 = warp & 3;
     const int px = q4 * 32 + lane;
     const uint32_t lane_sel = (uint32_t)(q4 * 32) << 16;
@@ -153,140 +197,226 @@ conv_fprop_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
     for (int tile = blockIdx.x; tile < P.ntiles; tile += gridDim.x, ++it) {
       const int wt = tile % P.tiles_w, h = (tile / P.tiles_w) % P.H, n = tile / (P.tiles_w * P.H);
       const int w0 = wt * TM;
-      const uint32_t acc = it & 1, pha = (it >> 1) & 1;
-      tc::mbar_wait(&t_full[acc], pha);
+      const uint32_t buf = P.acc_bufs == 2 ? (it & 1) : 0;
+      const uint32_t use_n = P.acc_bufs == 2 ? (it >> 1) : it;
+      tc::mbar_wait(&t_full[buf], use_n & 1);
       __syncwarp();
       tc::tc_fence_after();
-      if (leader) tma::store_wait_read<0>();  // previous tile's stores have read the staging buffer
-      tma::named_bar_sync(BAR_EPI, 128);
-      const bool in_img = (w0 + px) < P.W;
-      const __nv_bfloat16* rrow =
-          P.has_residual ? residual + (int64_t)n * res_img_stride + (int64_t)h * res_row_stride + (int64_t)(w0 + px) * P.Cout
-                         : nullptr;
-      for (int c0 = 0; c0 < P.Cout; c0 += 32) {
-        float v[32];
-        tc::tmem_ld_x32(tmem_base + lane_sel + acc * 128 + c0, v);
-        uint4 rv[4];
-        if (P.has_residual && in_img) {
+      const bool in_img = (w0 + px) < P.W_out_tiles;
+      if (!P.deconv_s) {
+        if (leader) tma::store_wait_read<0>();  // previous tile's stores have read the staging buffer
+        tma::named_bar_sync(BAR_EPI, 128);
+      }
+      const int nphase = P.deconv_s ? P.deconv_s : 1;
+      for (int ph = 0; ph < nphase; ++ph) {
+        // output pixel of this thread for this phase (interior coordinates)
+        const int64_t opix = P.deconv_s ? (int64_t)(w0 + px) * P.deconv_s + ph : (int64_t)(w0 + px);
+        const int64_t ooff = (int64_t)n * P.y_img + (int64_t)h * P.y_row + opix * P.Cout;
+        for (int c0 = 0; c0 < P.Cout; c0 += 32) {
+          float v[32];
+          tc::tmem_ld_x32(tmem_base + lane_sel + buf * buf_stride + ph * acc_stride + c0, v);
+          uint4 rv[4];
+          if (P.has_residual && in_img) {
 #pragma unroll
-          for (int j = 0; j < 4; ++j) rv[j] = __ldg(reinterpret_cast<const uint4*>(rrow + c0) + j);
-        }
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {  // 8 channels -> one 16-byte chunk
-          uint32_t pk[4];
-#pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            const int c = c0 + j * 8 + 2 * e;
-            float a = fmaf(v[j * 8 + 2 * e], s_scale[c], s_shift[c]);
-            float b = fmaf(v[j * 8 + 2 * e + 1], s_scale[c + 1], s_shift[c + 1]);
-            if (P.has_residual && in_img) {
-              const uint32_t w = reinterpret_cast<const uint32_t*>(&rv[j])[e];
-              const __nv_bfloat162 r2 = *reinterpret_cast<const __nv_bfloat162*>(&w);
-              a += __bfloat162float(r2.x);
-              b += __bfloat162float(r2.y);
-            }
-            if (P.relu) {
-              a = fmaxf(a, 0.f);
-              b = fmaxf(b, 0.f);
-            }
-            pk[e] = tc::pack_bf16x2(a, b);
+            for (int j = 0; j < 4; ++j) rv[j] = __ldg(reinterpret_cast<const uint4*>(residual + ooff + c0) + j);
           }
-          const int half = (c0 + j * 8) / KC;
-          const int chunk = ((c0 + j * 8) % KC) / 8;
-          // 128B swizzle: 16-byte chunk index XOR (row % 8)
-          *reinterpret_cast<uint4*>(sO + half * A_BYTES + px * 128 + ((chunk ^ (px & 7)) << 4)) =
-              make_uint4(pk[0], pk[1], pk[2], pk[3]);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {  // 8 channels -> one 16-byte chunk
+            uint32_t pk[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const int c = c0 + j * 8 + 2 * e;
+              float a = fmaf(v[j * 8 + 2 * e], s_scale[c], s_shift[c]);
+              float b = fmaf(v[j * 8 + 2 * e + 1], s_scale[c + 1], s_shift[c + 1]);
+              float ra = 0.f, rb = 0.f;
+              if (P.has_residual && in_img) {
+                const uint32_t w = reinterpret_cast<const uint32_t*>(&rv[j])[e];
+                const __nv_bfloat162 r2 = *reinterpret_cast<const __nv_bfloat162*>(&w);
+                ra = __bfloat162float(r2.x);
+                rb = __bfloat162float(r2.y);
+              }
+              if (!P.res_after_relu) { a += ra; b += rb; }
+              if (P.relu) { a = fmaxf(a, 0.f); b = fmaxf(b, 0.f); }
+              if (P.res_after_relu) { a += ra; b += rb; }
+              pk[e] = tc::pack_bf16x2(a, b);
+            }
+            if (P.deconv_s) {
+              if (in_img) *reinterpret_cast<uint4*>(y_interior + ooff + c0 + j * 8) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+            } else {
+              const int half = (c0 + j * 8) / KC, chunk = ((c0 + j * 8) % KC) / 8;
+              // 128B swizzle: 16-byte chunk index XOR (row % 8)
+              *reinterpret_cast<uint4*>(sO + half * SLOT + px * 128 + ((chunk ^ (px & 7)) << 4)) =
+                  make_uint4(pk[0], pk[1], pk[2], pk[3]);
+            }
+          }
         }
       }
       tc::tc_fence_before();
-      tc::fence_proxy_async_smem();
+      if (!P.deconv_s) tc::fence_proxy_async_smem();
       __syncwarp();
-      if (lane == 0) tc::mbar_arrive(&t_empty[acc]);
-      tma::named_bar_sync(BAR_EPI, 128);
-      if (leader) {
-        for (int hf = 0; hf < nh; ++hf) tma::store_4d(&tm_y, sO + hf * A_BYTES, hf * KC, w0, h, n);
-        tma::store_commit();
+      if (lane == 0) tc::mbar_arrive(&t_empty[buf]);
+      if (!P.deconv_s) {
+        tma::named_bar_sync(BAR_EPI, 128);
+        if (leader) {
+          for (int hf = 0; hf < nh; ++hf) tma::store_4d(&tm_y, sO + hf * SLOT, hf * KC, w0, h, n);
+          tma::store_commit();
+        }
       }
     }
-    if (leader) tma::store_wait_all<0>();
+    if (!P.deconv_s && leader) tma::store_wait_all<0>();
   }
   tc::tc_fence_before();
   __syncthreads();
-  if (warp == 1) tc::tmem_dealloc(tmem_base, 256);
+  if (warp == 1) tc::tmem_dealloc(tmem_base, 512);
 }
 
-}  // namespace conv
-
-extern "C" int rd_conv2d_nhwc_bf16(const void* x_pad, const void* w_packed, const float* scale, const float* shift,
-                                   const void* residual_pad, void* y_pad, int N, int H, int W, int Cin, int Cout,
-                                   int ksize, int relu, rd_stream_t stream) {
-  using namespace conv;
-  RD_REQUIRE(x_pad && w_packed && y_pad, "rd_conv2d_nhwc_bf16: null pointer");
-  RD_REQUIRE(ksize == 3 || ksize == 1, "rd_conv2d_nhwc_bf16: kernel size must be 3 (pad 1) or 1 (got %d)", ksize);
-  RD_REQUIRE((Cin == 64 || Cin == 128) && (Cout == 64 || Cout == 128),
-             "rd_conv2d_nhwc_bf16: Cin and Cout must be 64 or 128 (got %d, %d); pad the channels", Cin, Cout);
-  RD_REQUIRE(N > 0 && H > 0 && W > 0, "rd_conv2d_nhwc_bf16: bad shape");
+// mode: 0 = conv ksize x ksize (pad ksize/2), W-stride stride_w in {1,2}; 1 = deconv (3,8)/(1,4)/(1,2);
+//       2 = deconv (3,4)/(1,2)/(1,1)
+static int run(int mode, const void* x_pad, const void* w_packed, const float* scale, const float* shift,
+               const void* residual_pad, void* y_pad, int N, int H, int W_in, int Cin, int Cout, int ksize,
+               int stride_w, int relu, int res_after_relu, cudaStream_t stream) {
+  RD_REQUIRE(x_pad && w_packed && y_pad, "rd_conv: null pointer");
+  RD_REQUIRE(Cin >= 64 && Cin % 64 == 0 && Cin <= 1024, "rd_conv: Cin must be a multiple of 64 (got %d); pad the channels", Cin);
+  RD_REQUIRE(Cout == 64 || Cout == 128, "rd_conv: Cout must be 64 or 128 (got %d); pad the channels", Cout);
+  RD_REQUIRE(N > 0 && H > 0 && W_in > 0, "rd_conv: bad shape");
   if (rd_check_device()) return 1;
   Params P;
-  P.N = N; P.H = H; P.W = W; P.Cin = Cin; P.Cout = Cout; P.taps = ksize * ksize;
-  P.tiles_w = (W + TM - 1) / TM;
-  const int64_t ntiles = (int64_t)N * H * P.tiles_w;
-  RD_REQUIRE(ntiles <= 0x7fffffffLL, "rd_conv2d_nhwc_bf16: too many tiles");
-  P.ntiles = (int)ntiles;
+  memset(&P, 0, sizeof(P));
+  P.N = N; P.H = H; P.Cin = Cin; P.Cout = Cout;
   P.relu = relu ? 1 : 0;
   P.has_residual = residual_pad ? 1 : 0;
+  P.res_after_relu = res_after_relu ? 1 : 0;
+  int W_out;  // output width in pixels
+  if (mode == 0) {
+    RD_REQUIRE(ksize == 3 || ksize == 1, "rd_conv2d: kernel size must be 3 (pad 1) or 1 (got %d)", ksize);
+    RD_REQUIRE(stride_w == 1 || stride_w == 2, "rd_conv2d: W stride must be 1 or 2 (got %d)", stride_w);
+    RD_REQUIRE(stride_w == 1 || W_in % 2 == 0, "rd_conv2d: W must be even for W-stride 2");
+    W_out = W_in / stride_w;
+    P.W_out_tiles = W_out;
+    P.in_stride_w = stride_w;
+    P.nacc = 1;
+    P.deconv_s = 0;
+    P.ntaps = ksize * ksize;
+    P.nloads = P.ntaps;
+    for (int tap = 0; tap < P.ntaps; ++tap) {
+      Load& L = P.loads[tap];
+      L.dy = (int8_t)(ksize == 3 ? tap / 3 : 1);
+      L.dx = (int8_t)(ksize == 3 ? tap % 3 : 1);
+      L.nuse = 1; L.acc[0] = 0; L.tap[0] = (uint8_t)tap;
+    }
+  } else {
+    // out[oh, ow] += x[ih, iw] w[ky, kx]  with  oh = ih - 1 + ky,  ow = iw*S - pad + kx
+    const int S = mode == 1 ? 4 : 2, KW = mode == 1 ? 8 : 4, pad = mode == 1 ? 2 : 1;
+    RD_REQUIRE(S * Cout <= 512, "rd_deconv: S*Cout accumulators exceed TMEM");
+    W_out = W_in * S;
+    P.W_out_tiles = W_in;
+    P.in_stride_w = 1;
+    P.nacc = S;
+    P.deconv_s = S;
+    P.ntaps = 3 * KW;
+    // distinct input tiles: dih in {-1,0,1} x diw in {-1,0,1}
+    int nl = 0;
+    for (int dih = -1; dih <= 1; ++dih)
+      for (int diw = -1; diw <= 1; ++diw) {
+        Load L;
+        memset(&L, 0, sizeof(L));
+        L.dy = (int8_t)(dih + 1);
+        L.dx = (int8_t)(diw + 1);
+        const int ky = 1 - dih;  // ih = oh + 1 - ky
+        for (int ph = 0; ph < S; ++ph)
+          for (int kx = 0; kx < KW; ++kx) {
+            // ow = j*S + ph = iw*S - pad + kx  with iw = j + diw  ->  kx = ph + pad - diw*S
+            if (kx == ph + pad - diw * S) {
+              RD_REQUIRE(L.nuse < MAX_USES, "rd_deconv: tap program overflow");
+              L.acc[L.nuse] = (uint8_t)ph;
+              L.tap[L.nuse] = (uint8_t)(ky * KW + kx);
+              L.nuse++;
+            }
+          }
+        if (L.nuse) P.loads[nl++] = L;
+      }
+    P.nloads = nl;
+  }
+  P.tiles_w = (P.W_out_tiles + TM - 1) / TM;
+  const int64_t ntiles = (int64_t)N * H * P.tiles_w;
+  RD_REQUIRE(ntiles <= 0x7fffffffLL, "rd_conv: too many tiles");
+  P.ntiles = (int)ntiles;
   const int kh = Cin / KC, nh = Cout / KC;
   const int b_tile = Cout * KC * 2;
-  const int w_bytes = P.taps * kh * b_tile;
-  P.b_resident = w_bytes <= 80 * 1024 ? 1 : 0;
-  P.stage_bytes = A_BYTES + (P.b_resident ? 0 : b_tile);
-  const int o_bytes = nh * A_BYTES;
+  const int w_bytes = P.ntaps * kh * b_tile;
+  const int o_bytes = P.deconv_s ? 0 : nh * SLOT;
   const int misc = 2048;
-  const int budget = 220 * 1024 - o_bytes - misc - (P.b_resident ? w_bytes : 0);
-  int ns = budget / P.stage_bytes;
-  if (ns > 8) ns = 8;
-  RD_REQUIRE(ns >= 2, "rd_conv2d_nhwc_bf16: shared memory budget too small");
+  const int total_budget = 222 * 1024;
+  P.b_resident = (w_bytes <= total_budget - o_bytes - misc - 4 * SLOT && w_bytes <= 96 * 1024) ? 1 : 0;
+  int ns = (total_budget - o_bytes - misc - (P.b_resident ? w_bytes : 0)) / SLOT;
+  if (ns > MAX_STAGES) ns = MAX_STAGES;
+  RD_REQUIRE(ns >= 6, "rd_conv: shared memory budget too small (%d stages)", ns);
   P.nstages = ns;
-  P.a_off = 0;
-  P.b_off = ns * P.stage_bytes;
-  P.o_off = P.b_off + (P.b_resident ? w_bytes : 0);
+  P.acc_bufs = (2 * P.nacc * Cout <= 512) ? 2 : 1;
+  P.ring_off = 0;
+  P.w_off = ns * SLOT;
+  P.o_off = P.w_off + (P.b_resident ? w_bytes : 0);
   P.misc_off = P.o_off + o_bytes;
   const size_t smem = (size_t)P.misc_off + misc + 1024;
+  const uint64_t Wp_in = (uint64_t)W_in + 2, Hp = (uint64_t)H + 2, Wp_out = (uint64_t)W_out + 2;
+  P.y_row = (int64_t)Wp_out * Cout;
+  P.y_img = (int64_t)Hp * Wp_out * Cout;
 
   CUtensorMap tm_x, tm_w, tm_y;
-  const uint64_t Wp = (uint64_t)W + 2, Hp = (uint64_t)H + 2;
-  {  // haloed input (C, W+2, H+2, N)
-    const uint64_t d[4] = {(uint64_t)Cin, Wp, Hp, (uint64_t)N};
-    const uint64_t s[3] = {(uint64_t)Cin * 2, Wp * Cin * 2, Hp * Wp * Cin * 2};
-    const uint32_t b[4] = {(uint32_t)KC, (uint32_t)TM, 1u, 1u};
-    if (tma::make_map(&tm_x, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, x_pad, 4, d, s, b, CU_TENSOR_MAP_SWIZZLE_128B)) return 1;
+  {  // haloed input (C, W+2, H+2, N); a W-stride of 2 is the element stride of dimension 1
+    const uint64_t d[4] = {(uint64_t)Cin, Wp_in, Hp, (uint64_t)N};
+    const uint64_t s[3] = {(uint64_t)Cin * 2, Wp_in * Cin * 2, Hp * Wp_in * Cin * 2};
+    const uint32_t b[4] = {(uint32_t)KC, (uint32_t)(TM * P.in_stride_w), 1u, 1u};
+    const uint32_t es[4] = {1u, (uint32_t)P.in_stride_w, 1u, 1u};
+    if (tma::make_map_es(&tm_x, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, x_pad, 4, d, s, b, es, CU_TENSOR_MAP_SWIZZLE_128B)) return 1;
   }
   {  // packed weights (Cin, Cout, taps)
-    const uint64_t d[3] = {(uint64_t)Cin, (uint64_t)Cout, (uint64_t)P.taps};
+    const uint64_t d[3] = {(uint64_t)Cin, (uint64_t)Cout, (uint64_t)P.ntaps};
     const uint64_t s[2] = {(uint64_t)Cin * 2, (uint64_t)Cin * Cout * 2};
     const uint32_t b[3] = {(uint32_t)KC, (uint32_t)Cout, 1u};
     if (tma::make_map(&tm_w, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, w_packed, 3, d, s, b, CU_TENSOR_MAP_SWIZZLE_128B)) return 1;
   }
-  {  // interior view of the haloed output (C, W, H, N): stores are clipped at W, never touch the halo
-    const uint64_t d[4] = {(uint64_t)Cout, (uint64_t)W, (uint64_t)H, (uint64_t)N};
-    const uint64_t s[3] = {(uint64_t)Cout * 2, Wp * Cout * 2, Hp * Wp * Cout * 2};
+  char* y_int = static_cast<char*>(y_pad) + (Wp_out + 1) * Cout * 2;  // interior origin of the haloed output
+  {  // interior view (C, W_out, H, N): stores are clipped at W_out, never touch the halo
+    const uint64_t d[4] = {(uint64_t)Cout, (uint64_t)W_out, (uint64_t)H, (uint64_t)N};
+    const uint64_t s[3] = {(uint64_t)Cout * 2, Wp_out * Cout * 2, Hp * Wp_out * Cout * 2};
     const uint32_t b[4] = {(uint32_t)KC, (uint32_t)TM, 1u, 1u};
-    const char* y_int = static_cast<const char*>(y_pad) + (Wp + 1) * Cout * 2;
     if (tma::make_map(&tm_y, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, y_int, 4, d, s, b, CU_TENSOR_MAP_SWIZZLE_128B)) return 1;
   }
   const __nv_bfloat16* res = nullptr;
-  if (residual_pad) res = static_cast<const __nv_bfloat16*>(residual_pad) + (Wp + 1) * Cout;  // interior origin
+  if (residual_pad) res = static_cast<const __nv_bfloat16*>(residual_pad) + (Wp_out + 1) * Cout;
   int dev = 0, sms = 0;
   RD_CUDA(cudaGetDevice(&dev));
   RD_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
   static size_t smem_set = 0;
   if (smem > smem_set) {
-    RD_CUDA(cudaFuncSetAttribute(conv_fprop_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    RD_CUDA(cudaFuncSetAttribute(conv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     smem_set = smem;
   }
   const int grid = P.ntiles < sms ? P.ntiles : sms;
-  conv_fprop_kernel<<<grid, NTHREADS, smem, rd::as_stream(stream)>>>(tm_x, tm_w, tm_y, scale, shift, res,
-                                                                      (int64_t)Wp * Cout, (int64_t)Hp * Wp * Cout, P);
+  conv_kernel<<<grid, NTHREADS, smem, stream>>>(tm_x, tm_w, tm_y, scale, shift, res,
+                                                reinterpret_cast<__nv_bfloat16*>(y_int), P);
   rd::count_launch();
-  return rd::check_launch("rd_conv2d_nhwc_bf16");
+  return rd::check_launch("rd_conv");
 }
+
+}  // namespace conv
+
+extern "C" {
+
+int rd_conv2d_nhwc_bf16(const void* x_pad, const void* w_packed, const float* scale, const float* shift,
+                        const void* residual_pad, void* y_pad, int N, int H, int W, int Cin, int Cout, int ksize,
+                        int stride_w, int relu, rd_stream_t stream) {
+  return conv::run(0, x_pad, w_packed, scale, shift, residual_pad, y_pad, N, H, W, Cin, Cout, ksize, stride_w, relu, 0,
+                   rd::as_stream(stream));
+}
+
+int rd_deconv2d_nhwc_bf16(const void* x_pad, const void* w_packed, const float* scale, const float* shift,
+                          const void* residual_pad, void* y_pad, int N, int H, int W, int Cin, int Cout, int kw,
+                          int relu, rd_stream_t stream) {
+  RD_REQUIRE(kw == 8 || kw == 4, "rd_deconv2d_nhwc_bf16: supported kernels are (3,8)/(1,4)/(1,2) and (3,4)/(1,2)/(1,1)");
+  return conv::run(kw == 8 ? 1 : 2, x_pad, w_packed, scale, shift, residual_pad, y_pad, N, H, W, Cin, Cout, 3, 1, relu, 1,
+                   rd::as_stream(stream));
+}
+
+}  // extern "C"

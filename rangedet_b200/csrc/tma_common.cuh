@@ -50,6 +50,33 @@ inline int make_map(CUtensorMap* m, CUtensorMapDataType dt, const void* base, in
   return 0;
 }
 
+// Same with explicit traversal (element) strides: dimension i visits every es[i]-th element, so a
+// box of box[i] elements loads ceil(box[i] / es[i]) of them (used for W-strided convolutions).
+inline int make_map_es(CUtensorMap* m, CUtensorMapDataType dt, const void* base, int rank, const uint64_t* dims,
+                       const uint64_t* strides_bytes, const uint32_t* box, const uint32_t* es_in,
+                       CUtensorMapSwizzle swz) {
+  auto fn = encode_fn();
+  if (!fn) {
+    rd::set_error("cuTensorMapEncodeTiled entry point not available");
+    return 1;
+  }
+  cuuint64_t gd[5], gs[5];
+  cuuint32_t bx[5], es[5];
+  for (int i = 0; i < rank; ++i) {
+    gd[i] = dims[i];
+    bx[i] = box[i];
+    es[i] = es_in[i];
+    if (i + 1 < rank) gs[i] = strides_bytes[i];
+  }
+  CUresult r = fn(m, dt, (cuuint32_t)rank, const_cast<void*>(base), gd, gs, bx, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  swz, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    rd::set_error("cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
+    return 1;
+  }
+  return 0;
+}
+
 #ifdef __CUDACC__
 __device__ __forceinline__ void prefetch_map(const CUtensorMap* m) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(m)) : "memory");

@@ -228,29 +228,68 @@ def pack_conv_weight(w_oihw, cin=None, cout=None):
     return out
 
 
-def conv2d_nhwc(x_pad, w_packed, scale=None, shift=None, relu=False, residual_pad=None, out=None):
-    """y = relu?(conv(x) * scale + shift (+ residual)); x_pad / residual_pad / result are haloed NHWC bf16."""
+def pack_deconv_weight(w_iohw, cin=None, cout=None):
+    """MXNet/torch transposed-conv weight (Cin,Cout,kh,kw) -> bf16 [kh*kw][Cout'][Cin'] (zero padded)."""
+    ci, co, kh, kw = w_iohw.shape
+    cin, cout = cin or ci, cout or co
+    out = torch.zeros((kh * kw, cout, cin), device=w_iohw.device, dtype=torch.bfloat16)
+    out[:, :co, :ci] = w_iohw.permute(2, 3, 1, 0).reshape(kh * kw, co, ci).to(torch.bfloat16)
+    return out
+
+
+def _conv_common(x_pad, w_packed, scale, shift, residual_pad, out, w_out, what):
     if x_pad.dtype != torch.bfloat16 or w_packed.dtype != torch.bfloat16 or not x_pad.is_cuda:
-        raise TypeError("conv2d_nhwc expects CUDA bf16 tensors")
+        raise TypeError("%s expects CUDA bf16 tensors" % what)
     x_pad, w_packed = x_pad.contiguous(), w_packed.contiguous()
     N, Hp, Wp, Cin = x_pad.shape
     taps, Cout, Cin2 = w_packed.shape
-    if Cin2 != Cin or taps not in (1, 9):
+    if Cin2 != Cin:
         raise ValueError("weight shape %s does not match input channels %d" % (tuple(w_packed.shape), Cin))
-    H, W = Hp - 2, Wp - 2
     if out is None:
-        out = torch.zeros((N, Hp, Wp, Cout), device=x_pad.device, dtype=torch.bfloat16)
-    f = lambda v: _p(v.float().contiguous()) if v is not None else None
+        out = torch.zeros((N, Hp, w_out + 2, Cout), device=x_pad.device, dtype=torch.bfloat16)
     sc = scale.float().contiguous() if scale is not None else None
     sh = shift.float().contiguous() if shift is not None else None
     if residual_pad is not None:
         residual_pad = residual_pad.contiguous()
-        if tuple(residual_pad.shape) != (N, Hp, Wp, Cout) or residual_pad.dtype != torch.bfloat16:
-            raise ValueError("residual must be haloed NHWC bf16 with Cout channels")
+        if tuple(residual_pad.shape) != (N, Hp, w_out + 2, Cout) or residual_pad.dtype != torch.bfloat16:
+            raise ValueError("residual must be haloed NHWC bf16 at output resolution with Cout channels")
+    return x_pad, w_packed, sc, sh, residual_pad, out
+
+
+def conv2d_nhwc(x_pad, w_packed, scale=None, shift=None, relu=False, residual_pad=None, out=None, stride_w=1):
+    """y = relu?(conv(x) * scale + shift + residual); haloed NHWC bf16 in / out; W-stride 1 or 2."""
+    N, Hp, Wp, Cin = x_pad.shape
+    taps = w_packed.shape[0]
+    if taps not in (1, 9):
+        raise ValueError("conv2d_nhwc supports 1x1 and 3x3 kernels")
+    H, W = Hp - 2, Wp - 2
+    x_pad, w_packed, sc, sh, residual_pad, out = _conv_common(x_pad, w_packed, scale, shift, residual_pad, out,
+                                                              W // stride_w, "conv2d_nhwc")
     with torch.cuda.device(x_pad.device):
         st = _lib.lib().rd_conv2d_nhwc_bf16(_p(x_pad), _p(w_packed), _p(sc) if sc is not None else None,
                                             _p(sh) if sh is not None else None,
                                             _p(residual_pad) if residual_pad is not None else None, _p(out),
-                                            N, H, W, Cin, Cout, 3 if taps == 9 else 1, int(bool(relu)), _stream())
+                                            N, H, W, Cin, w_packed.shape[1], 3 if taps == 9 else 1, int(stride_w),
+                                            int(bool(relu)), _stream())
     _lib.check(st, "conv2d_nhwc")
+    return out
+
+
+def deconv2d_nhwc(x_pad, w_packed, scale=None, shift=None, relu=False, residual_pad=None, out=None):
+    """y = relu?(deconv(x) * scale + shift) + residual for the two agg_stage shapes: weight packed from
+    (Cin,Cout,3,8) -> stride (1,4) pad (1,2), or (Cin,Cout,3,4) -> stride (1,2) pad (1,1)."""
+    N, Hp, Wp, Cin = x_pad.shape
+    taps = w_packed.shape[0]
+    if taps not in (24, 12):
+        raise ValueError("deconv2d_nhwc supports (3,8) and (3,4) kernels")
+    kw = taps // 3
+    H, W = Hp - 2, Wp - 2
+    x_pad, w_packed, sc, sh, residual_pad, out = _conv_common(x_pad, w_packed, scale, shift, residual_pad, out,
+                                                              W * (kw // 2), "deconv2d_nhwc")
+    with torch.cuda.device(x_pad.device):
+        st = _lib.lib().rd_deconv2d_nhwc_bf16(_p(x_pad), _p(w_packed), _p(sc) if sc is not None else None,
+                                              _p(sh) if sh is not None else None,
+                                              _p(residual_pad) if residual_pad is not None else None, _p(out),
+                                              N, H, W, Cin, w_packed.shape[1], kw, int(bool(relu)), _stream())
+    _lib.check(st, "deconv2d_nhwc")
     return out

@@ -307,31 +307,30 @@ def test_meta_kernel_class_surface(ops):
 # tcgen05 implicit-GEMM convolution (torch fp32 conv of the same bf16-rounded operands is the
 # reference for this floating-point kernel; outputs are bf16: tolerance 2^-7 relative + small abs)
 # ---------------------------------------------------------------------------------------------
-@pytest.mark.parametrize("shape", [(1, 64, 64, 5, 300, 3), (2, 128, 128, 4, 200, 3), (1, 64, 128, 3, 130, 3),
-                                   (1, 128, 64, 3, 257, 3), (2, 64, 64, 3, 128, 1), (1, 576, 64, 2, 140, 1),
-                                   (1, 8, 64, 4, 96, 3), (1, 64, 64, 64, 2656, 3)])
+@pytest.mark.parametrize("shape", [(1, 64, 64, 5, 300, 3, 1), (2, 128, 128, 4, 200, 3, 1), (1, 64, 128, 3, 130, 3, 1),
+                                   (1, 128, 64, 3, 257, 3, 1), (2, 64, 64, 3, 128, 1, 1), (1, 576, 64, 2, 140, 1, 1),
+                                   (1, 8, 64, 4, 96, 3, 1), (1, 64, 64, 4, 300, 3, 2), (2, 64, 128, 3, 132, 1, 2),
+                                   (1, 128, 128, 3, 258, 3, 2), (1, 72, 128, 3, 100, 3, 1), (1, 64, 64, 64, 2656, 3, 1)])
 def test_conv2d_nhwc_vs_torch(ops, shape):
     import torch.nn.functional as F
-    N, Cin, Cout, H, W, ks = shape
+    N, Cin, Cout, H, W, ks, sw = shape
     g = torch.Generator(device="cuda").manual_seed(sum(shape))
     x = torch.randn(N, Cin, H, W, device="cuda", generator=g).bfloat16().float()
     w = (torch.randn(Cout, Cin, ks, ks, device="cuda", generator=g) / (Cin * ks * ks) ** 0.5).bfloat16().float()
     scale = torch.rand(Cout, device="cuda", generator=g) + 0.5
     shift = torch.randn(Cout, device="cuda", generator=g) * 0.1
-    res = torch.randn(N, Cout, H, W, device="cuda", generator=g).bfloat16().float()
+    res = torch.randn(N, Cout, H, W // sw, device="cuda", generator=g).bfloat16().float()
     cin_p = ((Cin + 63) // 64) * 64
-    if cin_p not in (64, 128):
-        # wide 1x1 (e.g. the 576 -> 64 aggregation conv): sum of <=128-channel slices, fp32 reference only
-        pytest.skip("Cin > 128 is covered by channel slicing at the graph level (next round)")
     xp = ops.to_nhwc_padded(x, cin_p)
     wp = ops.pack_conv_weight(w, cin_p, Cout)
     for relu, use_res in [(False, False), (True, True)]:
-        want = F.conv2d(x, w, padding=ks // 2) * scale[None, :, None, None] + shift[None, :, None, None]
+        want = F.conv2d(x, w, padding=ks // 2, stride=(1, sw)) * scale[None, :, None, None] + shift[None, :, None, None]
         if use_res:
             want = want + res
         if relu:
             want = want.relu()
-        yp = ops.conv2d_nhwc(xp, wp, scale, shift, relu=relu, residual_pad=ops.to_nhwc_padded(res) if use_res else None)
+        yp = ops.conv2d_nhwc(xp, wp, scale, shift, relu=relu, residual_pad=ops.to_nhwc_padded(res) if use_res else None,
+                             stride_w=sw)
         got = ops.from_nhwc_padded(yp)
         # halo must stay zero (the next layer's padding)
         assert not yp[:, 0].any() and not yp[:, -1].any() and not yp[:, :, 0].any() and not yp[:, :, -1].any()
@@ -340,3 +339,30 @@ def test_conv2d_nhwc_vs_torch(ops, shape):
         report(test="conv2d", shape=list(shape), relu=relu, residual=use_res, max_abs_err=float(err.max()),
                rel_err=rel_err(got.cpu().numpy(), want.cpu().numpy()))
         assert bool((err <= tol).all()), float((err - tol).max())
+
+
+@pytest.mark.parametrize("shape", [(1, 128, 128, 4, 166, 8), (2, 128, 64, 3, 140, 8), (1, 128, 64, 3, 200, 4),
+                                   (2, 64, 64, 5, 130, 4), (1, 64, 64, 3, 40, 8)])
+def test_deconv2d_nhwc_vs_torch(ops, shape):
+    """agg_stage transposed convolutions (dla_backbone.py:116-127): (3,8)/(1,4)/(1,2) and (3,4)/(1,2)/(1,1),
+    followed by BN -> ReLU -> + skip."""
+    import torch.nn.functional as F
+    N, Cin, Cout, H, W, kw = shape
+    S, pad = kw // 2, kw // 4
+    g = torch.Generator(device="cuda").manual_seed(sum(shape))
+    x = torch.randn(N, Cin, H, W, device="cuda", generator=g).bfloat16().float()
+    w = (torch.randn(Cin, Cout, 3, kw, device="cuda", generator=g) / (Cin * 3 * 2) ** 0.5).bfloat16().float()
+    scale = torch.rand(Cout, device="cuda", generator=g) + 0.5
+    shift = torch.randn(Cout, device="cuda", generator=g) * 0.1
+    skip = torch.randn(N, Cout, H, W * S, device="cuda", generator=g).bfloat16().float()
+    want = F.conv_transpose2d(x, w, stride=(1, S), padding=(1, pad)) * scale[None, :, None, None] + shift[None, :, None, None]
+    want = want.relu() + skip
+    yp = ops.deconv2d_nhwc(ops.to_nhwc_padded(x), ops.pack_deconv_weight(w), scale, shift, relu=True,
+                           residual_pad=ops.to_nhwc_padded(skip))
+    got = ops.from_nhwc_padded(yp)
+    assert got.shape == want.shape
+    assert not yp[:, 0].any() and not yp[:, -1].any() and not yp[:, :, 0].any() and not yp[:, :, -1].any()
+    err = (got - want).abs()
+    tol = 2.0 ** -7 * want.abs() + 2e-2
+    report(test="deconv2d", shape=list(shape), max_abs_err=float(err.max()), rel_err=rel_err(got.cpu().numpy(), want.cpu().numpy()))
+    assert bool((err <= tol).all()), float((err - tol).max())
