@@ -366,3 +366,34 @@ def test_deconv2d_nhwc_vs_torch(ops, shape):
     tol = 2.0 ** -7 * want.abs() + 2e-2
     report(test="deconv2d", shape=list(shape), max_abs_err=float(err.max()), rel_err=rel_err(got.cpu().numpy(), want.cpu().numpy()))
     assert bool((err <= tol).all()), float((err - tol).max())
+
+
+# ---------------------------------------------------------------------------------------------
+# full DLA backbone + Meta-Kernel + RPN head forward (inference form) vs the torch restatement
+# ---------------------------------------------------------------------------------------------
+def test_dla_backbone_and_head_forward(ops):
+    from oracle import dla_ref
+    from rangedet_b200 import dla
+    B, H, W = 1, 8, 512
+    P = dla_ref.make_params(seed=0, device="cuda")
+    g = torch.Generator(device="cuda").manual_seed(1)
+    data = torch.randn(B, 8, H, W, device="cuda", generator=g)
+    coord = cu(synth.range_image_coords(B, seed=3, h=H, w=W - 6, w_pad=W))
+    ref = dla_ref.Ref(P, bf16=True)
+    want_feats = ref.backbone(data, coord)
+    want_cls, want_reg = ref.head(want_feats)
+    bb = dla.DLABackbone(P)
+    feats = bb.get_rpn_feature(data, coord)
+    got_feats = [ops.from_nhwc_padded(feats[0], 72), ops.from_nhwc_padded(feats[1]), ops.from_nhwc_padded(feats[2])]
+    for lvl, (gf, wf) in enumerate(zip(got_feats, want_feats)):
+        assert gf.shape == wf.shape
+        e = rel_err(gf.cpu().numpy(), wf.cpu().numpy())
+        report(test="dla_backbone", level=lvl, shape=list(wf.shape), rel_err=e)
+        assert e < 3e-2, (lvl, e)   # bf16 activations through ~45 layers
+    cls, reg = dla.RangeRpnHead(P).get_fpn_output(feats)
+    for lvl in range(3):
+        for name, gq, wq in (("cls", cls[lvl], want_cls[lvl]), ("reg", reg[lvl], want_reg[lvl])):
+            assert gq.shape == wq.shape
+            e = rel_err(gq.cpu().numpy(), wq.cpu().numpy())
+            report(test="rpn_head", level=lvl, out=name, shape=list(wq.shape), rel_err=e)
+            assert e < 5e-2, (lvl, name, e)
