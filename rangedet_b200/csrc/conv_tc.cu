@@ -23,6 +23,7 @@
 //       conv: 128B-swizzled staging tile -> TMA store into the interior view of the haloed output
 //       deconv: each thread owns S consecutive output pixels -> direct 16-byte stores
 #include <cuda_bf16.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "../../include/rangedet_b200.h"
@@ -44,6 +45,7 @@ struct Load {
   uint8_t nuse;
   uint8_t acc[MAX_USES];    // accumulator (phase) fed by this input tile
   uint8_t tap[MAX_USES];    // packed weight tap
+  uint8_t off[MAX_USES];    // strip mode: first pixel row of the loaded strip this use starts at (dx)
 };
 
 struct Params {
@@ -56,6 +58,7 @@ struct Params {
   int deconv_s;             // 0: convolution (TMA-store epilogue); S>0: transposed conv, phase count S
   int b_resident, nstages, acc_bufs;
   int ring_off, w_off, o_off, misc_off;
+  int slot_bytes, a_bytes, use_base_offset;  // ring slot size, bytes of one activation load, descriptor variant
   int64_t y_row, y_img;     // element strides of the haloed output (deconv / residual addressing)
   Load loads[MAX_LOADS];
 };
@@ -124,8 +127,8 @@ conv_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CU
             {
               const uint32_t s = g % P.nstages, ph = (g / P.nstages) & 1;
               tc::mbar_wait(&empty[s], ph ^ 1);
-              tc::mbar_arrive_expect_tx(&full[s], (uint32_t)SLOT);
-              tma::load_4d(ring + s * SLOT, &tm_x, &full[s], q * KC, w0 * P.in_stride_w + L.dx, h + L.dy, n);
+              tc::mbar_arrive_expect_tx(&full[s], (uint32_t)P.a_bytes);
+              tma::load_4d(ring + s * P.slot_bytes, &tm_x, &full[s], q * KC, w0 * P.in_stride_w + L.dx, h + L.dy, n);
               ++g;
             }
             if (!P.b_resident)
@@ -133,7 +136,7 @@ conv_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CU
                 const uint32_t s = g % P.nstages, ph = (g / P.nstages) & 1;
                 tc::mbar_wait(&empty[s], ph ^ 1);
                 tc::mbar_arrive_expect_tx(&full[s], (uint32_t)b_tile);
-                tma::load_3d(ring + s * SLOT, &tm_w, &full[s], q * KC, 0, L.tap[u]);
+                tma::load_3d(ring + s * P.slot_bytes, &tm_w, &full[s], q * KC, 0, L.tap[u]);
               }
           }
       }
@@ -157,7 +160,7 @@ conv_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CU
             const uint32_t sa = g % P.nstages, pha = (g / P.nstages) & 1;
             tc::mbar_wait(&full[sa], pha);
             ++g;
-            const uint32_t a_addr = tc::smem_u32(ring + sa * SLOT);
+            const uint32_t a_addr = tc::smem_u32(ring + sa * P.slot_bytes);
             for (int u = 0; u < L.nuse; ++u) {
               uint32_t b_addr, sb = 0;
               if (P.b_resident) {
@@ -166,7 +169,7 @@ conv_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CU
                 sb = g % P.nstages;
                 tc::mbar_wait(&full[sb], (g / P.nstages) & 1);
                 ++g;
-                b_addr = tc::smem_u32(ring + sb * SLOT);
+                b_addr = tc::smem_u32(ring + sb * P.slot_bytes);
               }
               tc::tc_fence_after();
               const uint32_t d_tmem = tmem_base + buf * buf_stride + L.acc[u] * acc_stride;
@@ -174,7 +177,10 @@ conv_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CU
 #pragma unroll
               for (int ks = 0; ks < KC / 16; ++ks) {
                 // 128B-swizzled K-major tiles: 8-row groups 1024 B apart, K advances 32 B inside the atom
-                const uint64_t ad = tc::make_smem_desc(a_addr + ks * 32, 0, 1024, tc::LAYOUT_SW128);
+                // strip mode: the operand starts L.off[u] pixel rows (128 B each) into the loaded strip;
+                // TMA and tcgen05 both swizzle on absolute address bits, so the shifted view is consistent
+                uint64_t ad = tc::make_smem_desc(a_addr + L.off[u] * 128 + ks * 32, 0, 1024, tc::LAYOUT_SW128);
+                if (P.use_base_offset) ad |= (uint64_t)(L.off[u] & 7) << 49;
                 const uint64_t bd = tc::make_smem_desc(b_addr + ks * 32, 0, 1024, tc::LAYOUT_SW128);
                 tc::mma_bf16_ss(d_tmem, ad, bd, idesc, ((started & bit) || ks > 0) ? 1u : 0u);
               }
@@ -287,6 +293,7 @@ static int run(int mode, const void* x_pad, const void* w_packed, const float* s
   P.has_residual = residual_pad ? 1 : 0;
   P.res_after_relu = res_after_relu ? 1 : 0;
   int W_out;  // output width in pixels
+  bool strip = false;
   if (mode == 0) {
     RD_REQUIRE(ksize == 3 || ksize == 1, "rd_conv2d: kernel size must be 3 (pad 1) or 1 (got %d)", ksize);
     RD_REQUIRE(stride_w == 1 || stride_w == 2, "rd_conv2d: W stride must be 1 or 2 (got %d)", stride_w);
@@ -297,12 +304,24 @@ static int run(int mode, const void* x_pad, const void* w_packed, const float* s
     P.nacc = 1;
     P.deconv_s = 0;
     P.ntaps = ksize * ksize;
-    P.nloads = P.ntaps;
-    for (int tap = 0; tap < P.ntaps; ++tap) {
-      Load& L = P.loads[tap];
-      L.dy = (int8_t)(ksize == 3 ? tap / 3 : 1);
-      L.dx = (int8_t)(ksize == 3 ? tap % 3 : 1);
-      L.nuse = 1; L.acc[0] = 0; L.tap[0] = (uint8_t)tap;
+    const char* es = getenv("RD_CONV_STRIP");
+    strip = (ksize == 3 && stride_w == 1 && !(es && es[0] == '0'));
+    if (strip) {
+      // one 130-pixel row strip per dy serves the three dx taps as row-shifted views of the same tile
+      P.nloads = 3;
+      for (int dy = 0; dy < 3; ++dy) {
+        Load& L = P.loads[dy];
+        L.dy = (int8_t)dy; L.dx = 0; L.nuse = 3;
+        for (int dx = 0; dx < 3; ++dx) { L.acc[dx] = 0; L.tap[dx] = (uint8_t)(dy * 3 + dx); L.off[dx] = (uint8_t)dx; }
+      }
+    } else {
+      P.nloads = P.ntaps;
+      for (int tap = 0; tap < P.ntaps; ++tap) {
+        Load& L = P.loads[tap];
+        L.dy = (int8_t)(ksize == 3 ? tap / 3 : 1);
+        L.dx = (int8_t)(ksize == 3 ? tap % 3 : 1);
+        L.nuse = 1; L.acc[0] = 0; L.tap[0] = (uint8_t)tap;
+      }
     }
   } else {
     // out[oh, ow] += x[ih, iw] w[ky, kx]  with  oh = ih - 1 + ky,  ow = iw*S - pad + kx
@@ -347,14 +366,23 @@ static int run(int mode, const void* x_pad, const void* w_packed, const float* s
   const int o_bytes = P.deconv_s ? 0 : nh * SLOT;
   const int misc = 2048;
   const int total_budget = 222 * 1024;
-  P.b_resident = (w_bytes <= total_budget - o_bytes - misc - 4 * SLOT && w_bytes <= 96 * 1024) ? 1 : 0;
-  int ns = (total_budget - o_bytes - misc - (P.b_resident ? w_bytes : 0)) / SLOT;
+  P.b_resident = (w_bytes <= total_budget - o_bytes - misc - 4 * 17 * 1024 && w_bytes <= 96 * 1024) ? 1 : 0;
+  const int box_px = strip ? TM + 2 : TM * (mode == 0 ? stride_w : 1);
+  P.a_bytes = (strip ? TM + 2 : TM) * KC * 2;
+  P.slot_bytes = strip ? 17 * 1024 : SLOT;
+  {
+    // Probed on B200 (scripts/run_strip.sh): the 128B swizzle is a pure function of the shared-memory
+    // ADDRESS bits, so a row-shifted start address needs NO base_offset (setting it breaks parity).
+    const char* eb = getenv("RD_CONV_BASEOFF");
+    P.use_base_offset = (eb && eb[0] == '1') ? 1 : 0;
+  }
+  int ns = (total_budget - o_bytes - misc - (P.b_resident ? w_bytes : 0)) / P.slot_bytes;
   if (ns > MAX_STAGES) ns = MAX_STAGES;
   RD_REQUIRE(ns >= 6, "rd_conv: shared memory budget too small (%d stages)", ns);
   P.nstages = ns;
   P.acc_bufs = (2 * P.nacc * Cout <= 512) ? 2 : 1;
   P.ring_off = 0;
-  P.w_off = ns * SLOT;
+  P.w_off = ns * P.slot_bytes;
   P.o_off = P.w_off + (P.b_resident ? w_bytes : 0);
   P.misc_off = P.o_off + o_bytes;
   const size_t smem = (size_t)P.misc_off + misc + 1024;
@@ -366,7 +394,7 @@ static int run(int mode, const void* x_pad, const void* w_packed, const float* s
   {  // haloed input (C, W+2, H+2, N); a W-stride of 2 is the element stride of dimension 1
     const uint64_t d[4] = {(uint64_t)Cin, Wp_in, Hp, (uint64_t)N};
     const uint64_t s[3] = {(uint64_t)Cin * 2, Wp_in * Cin * 2, Hp * Wp_in * Cin * 2};
-    const uint32_t b[4] = {(uint32_t)KC, (uint32_t)(TM * P.in_stride_w), 1u, 1u};
+    const uint32_t b[4] = {(uint32_t)KC, (uint32_t)box_px, 1u, 1u};
     const uint32_t es[4] = {1u, (uint32_t)P.in_stride_w, 1u, 1u};
     if (tma::make_map_es(&tm_x, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, x_pad, 4, d, s, b, es, CU_TENSOR_MAP_SWIZZLE_128B)) return 1;
   }

@@ -51,12 +51,28 @@ class _Layer:
         self.deconv = deconv
 
 
+class _BufferPool:
+    """Output activations are reused across forward calls: the kernels only ever write the interior,
+    so a haloed buffer zero-initialised once keeps a valid zero halo forever."""
+
+    def __init__(self):
+        self.bufs = {}
+
+    def get(self, key, shape, device):
+        t = self.bufs.get(key)
+        if t is None or tuple(t.shape) != tuple(shape):
+            t = torch.zeros(shape, device=device, dtype=torch.bfloat16)
+            self.bufs[key] = t
+        return t
+
+
 class DLABackbone(object):
     """DLABackbone(pBackbone).get_rpn_feature(data) of the reference, over torch tensors."""
 
     def __init__(self, params, device="cuda", meta_impl=ops.IMPL_DEFAULT):
         self.P, self.device, self.meta_impl = params, device, meta_impl
         self.L = {}
+        self.pool = _BufferPool()
 
     def layer(self, wname, bnname=None, deconv=False):
         key = wname
@@ -66,7 +82,9 @@ class DLABackbone(object):
 
     def conv_bn(self, x, wname, bnname, stride_w=1, relu=True, residual=None):
         l = self.layer(wname, bnname)
-        return ops.conv2d_nhwc(x, l.w, l.scale, l.shift, relu=relu, residual_pad=residual, stride_w=stride_w)
+        N, Hp, Wp, _ = x.shape
+        out = self.pool.get(wname, (N, Hp, (Wp - 2) // stride_w + 2, l.cout_p), x.device)
+        return ops.conv2d_nhwc(x, l.w, l.scale, l.shift, relu=relu, residual_pad=residual, stride_w=stride_w, out=out)
 
     def meta_kernel_conv(self, x, coord, name):  # dla_backbone.py:58-103
         P, dev = self.P, self.device
@@ -96,7 +114,8 @@ class DLABackbone(object):
 
     def agg_stage(self, name, const, up):  # :116-127
         l = self.layer(name + "_deconv", name + "_deconv_bn", deconv=True)
-        y = ops.deconv2d_nhwc(up, l.w, l.scale, l.shift, relu=True, residual_pad=const)
+        y = ops.deconv2d_nhwc(up, l.w, l.scale, l.shift, relu=True, residual_pad=const,
+                              out=self.pool.get(name + "_deconv", const.shape, up.device))
         return self.res_stage(y, None, name + "_res", 1)
 
     def get_rpn_feature(self, data, coord):
@@ -113,7 +132,7 @@ class DLABackbone(object):
         agg2a = self.agg_stage("agg2a", res2a, agg2)
         agg3 = self.agg_stage("agg3", agg1, agg2a)
         c = data.shape[1]
-        cat = torch.zeros(agg3.shape[:3] + (128,), device=agg3.device, dtype=torch.bfloat16)  # concat(data, agg3): 72 ch
+        cat = self.pool.get("data_concat", agg3.shape[:3] + (128,), agg3.device)  # concat(data, agg3): 72 of 128 ch
         cat[..., :c] = x[..., :c]
         cat[..., c:c + 64] = agg3
         return [cat, agg2a, agg2]
@@ -125,6 +144,11 @@ class RangeRpnHead(object):
     def __init__(self, params, device="cuda"):
         self.P, self.device = params, device
         self.L = {}
+        self.pool = _BufferPool()
+
+    def _conv(self, x, l, name, relu):
+        N, Hp, Wp, _ = x.shape
+        return ops.conv2d_nhwc(x, l.w, l.scale, l.shift, relu=relu, out=self.pool.get(name, (N, Hp, Wp, l.cout_p), x.device))
 
     def _l(self, wname, bnname=None, bias=None):
         if wname not in self.L:
@@ -138,12 +162,12 @@ class RangeRpnHead(object):
             for i in range(4):
                 n = "rpn_cls_conv_%d_lvl_%d" % (i, lvl)
                 l = self._l(n, n + "_bn")
-                c = ops.conv2d_nhwc(c, l.w, l.scale, l.shift, relu=True)
+                c = self._conv(c, l, n, True)
                 n = "rpn_reg_conv_%d_lvl_%d" % (i, lvl)
                 l = self._l(n, n + "_bn")
-                r = ops.conv2d_nhwc(r, l.w, l.scale, l.shift, relu=True)
+                r = self._conv(r, l, n, True)
             l = self._l("rpn_cls_logit_lvl_%d" % lvl, None, "rpn_cls_logit_lvl_%d_bias" % lvl)
-            cls_logit.append(ops.from_nhwc_padded(ops.conv2d_nhwc(c, l.w, l.scale, l.shift), 1))
+            cls_logit.append(ops.from_nhwc_padded(self._conv(c, l, "rpn_cls_logit_lvl_%d" % lvl, False), 1))
             l = self._l("rpn_reg_delta_lvl_%d" % lvl, None, "rpn_reg_delta_lvl_%d_bias" % lvl)
-            bbox_delta.append(ops.from_nhwc_padded(ops.conv2d_nhwc(r, l.w, l.scale, l.shift), 8))
+            bbox_delta.append(ops.from_nhwc_padded(self._conv(r, l, "rpn_reg_delta_lvl_%d" % lvl, False), 8))
         return cls_logit, bbox_delta
