@@ -305,7 +305,10 @@ static int run(int mode, const void* x_pad, const void* w_packed, const float* s
     P.deconv_s = 0;
     P.ntaps = ksize * ksize;
     const char* es = getenv("RD_CONV_STRIP");
-    strip = (ksize == 3 && stride_w == 1 && !(es && es[0] == '0'));
+    // Strip mode is correct but measured SLOWER than nine aligned loads (0.160 vs 0.126 ms for 64->64
+    // @ 4x64x2656; 0.382 vs 0.237 ms for 128->128): views that straddle 1024-B swizzle atoms cost more
+    // in the MMA's shared-memory reads than the saved L2 traffic.  Opt-in only (RD_CONV_STRIP=1).
+    strip = (ksize == 3 && stride_w == 1 && es && es[0] == '1');
     if (strip) {
       // one 130-pixel row strip per dy serves the three dx taps as row-shifted views of the same tile
       P.nloads = 3;

@@ -22,6 +22,8 @@ conv)  timeout 600 python -m pytest tests/test_gpu_parity.py -m gpu -q --timeout
 ncuconv) timeout 900 ncu --set full --clock-control none --import-source on -k regex:conv_fprop -s 4 -c 3 -o gpurun_out/prof_conv -f python scripts/mk_tc_diag.py > gpurun_out/ncu_conv.log 2>&1; echo "ncu-conv exit $?" >> gpurun_out/status.txt ;;
 model) timeout 600 python -m pytest tests/test_gpu_parity.py -m gpu -q --timeout 300 -k "dla_backbone" > gpurun_out/pytest_model.log 2>&1; echo "model exit $?" >> gpurun_out/status.txt
        timeout 600 python scripts/fwd_bench.py 8 > gpurun_out/fwd_bench.json 2> gpurun_out/fwd_bench.err; echo "fwdbench exit $?" >> gpurun_out/status.txt ;;
+full)  timeout 1500 python -m pytest tests/ -x -q -m gpu --timeout 900 > gpurun_out/pytest_full.log 2>&1; echo "full exit $?" >> gpurun_out/status.txt ;;
+ncuall) timeout 900 ncu --set full --clock-control none -k regex:"meta_ws|conv_kernel" -s 20 -c 12 -o gpurun_out/prof_all -f python scripts/mk_tc_diag.py > gpurun_out/ncu_all.log 2>&1; echo "ncu-all exit $?" >> gpurun_out/status.txt ;;
 diag)  timeout 600 python scripts/mk_tc_diag.py > gpurun_out/mk_tc_diag.json 2> gpurun_out/mk_tc_diag.err; echo "diag exit $?" >> gpurun_out/status.txt ;;
 ncutc) timeout 900 ncu --set full --clock-control none --import-source on -k regex:meta_fwd_tc -s 3 -c 1 -o gpurun_out/prof_meta_tc -f python scripts/mk_tc_diag.py 0 > gpurun_out/ncu_tc.log 2>&1; echo "ncu-tc exit $?" >> gpurun_out/status.txt ;;
 ncuws) timeout 900 ncu --set full --clock-control none --import-source on -k regex:meta_ws -s 3 -c 5 -o gpurun_out/prof_meta_ws -f python scripts/mk_tc_diag.py > gpurun_out/ncu_ws.log 2>&1; echo "ncu-ws exit $?" >> gpurun_out/status.txt ;;
