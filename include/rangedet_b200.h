@@ -55,6 +55,15 @@ int rd_meta_kernel_bwd(const float* grad_out, const float* data, const float* co
                        float* grad_b1, void* workspace, size_t workspace_bytes,
                        int B, int C, int H, int W, int impl, rd_stream_t stream);
 
+/* Forward fused with the BatchNorm(9C)+ReLU that follows it in meta_kernel_conv
+ * (rangedet/symbol/backbone/dla_backbone.py:92-94): y = relu?(out * scale + shift), written as zero-haloed
+ * NHWC bf16 y_pad [B][H+2][W+2][9C] with TAP-MAJOR channels: y[..., k*C + c] = f(out[b, c*9+k, h, w]);
+ * scale/shift are indexed the same way (k*C + c).  C == 64, W % 4 == 0.  The halo is not written.
+ */
+int rd_meta_kernel_fwd_nhwc_bf16(const float* data, const float* coord, const float* w0, const float* b0,
+                                 const float* w1, const float* b1, const float* scale, const float* shift,
+                                 int relu, void* y_pad, int B, int C, int H, int W, rd_stream_t stream);
+
 /* The two halves of rd_meta_kernel_bwd, separately callable (grad_req 'null' on either side). */
 int rd_meta_kernel_bwd_data(const float* grad_out, const float* coord, const float* w0,
                             const float* b0, const float* w1, const float* b1, float* grad_data,
@@ -98,6 +107,18 @@ size_t rd_wnms_4c_workspace_bytes(int n);
 int rd_wnms_4c(const float* dets, int n, float thresh, float thresh_vote, int is_3d,
                int hash_scale, float* out_dets, int32_t* keep_inds, int* out_count,
                void* workspace, size_t workspace_bytes, rd_stream_t stream);
+
+/* ---- NMS3D (hard NMS) ---------------------------------------------------------------------
+ * Replaces _contrib_NMS3D: NMS3DForward<gpu>, operator_cxx/contrib/nms_3d.cu:470-534.
+ * boxes (B,N,10) [4 BEV corners, z0, z1] sorted by score -> keep_idx (B,max_keep) int32 indices in
+ * keep order, filled with -1; boxes_out (B,max_keep,10) the kept boxes, filled with 0.
+ * A box j > i is removed when iou(i, j) > iou_thres, iou = volumetric rotated IoU (nms_3d.cu:342-368)
+ * or, normal_iou != 0, axis-aligned IoU of boxes[:, :4] (:370-378).
+ */
+size_t rd_nms3d_workspace_bytes(int B, int N);
+int rd_nms3d(const float* boxes, int B, int N, float iou_thres, int max_keep, int normal_iou,
+             int32_t* keep_idx, float* boxes_out, void* workspace, size_t workspace_bytes,
+             rd_stream_t stream);
 
 /* ---- Convolution family (DLA backbone / RPN head) -------------------------------------------
  * Replaces mx.sym.Convolution / mx.sym.Deconvolution (+ inference-form BatchNorm, ReLU, residual

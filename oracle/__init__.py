@@ -112,6 +112,16 @@ class _OracleOps(_Ops):
         return out
 
 
+    def nms3d(self, boxes, iou_thres, max_keep, normal_iou=False):
+        boxes = _c32(boxes)
+        B, N, _ = boxes.shape
+        keep = np.empty((B, max_keep), np.int32)
+        out = np.empty((B, max_keep, 10), np.float32)
+        self.lib.orc_nms3d(_fp(boxes), B, N, ctypes.c_float(iou_thres), int(max_keep), int(bool(normal_iou)), _ip(keep),
+                           _fp(out))
+        return keep, out
+
+
 _oracle = None
 _ref = None
 

@@ -418,6 +418,106 @@ void hash_keys(const float* b, float scale, std::vector<int>* keys) {
     for (int j = y0; j < y1; ++j) keys->push_back(i * 100 + j);
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// NMS3D            operator_cxx/contrib/nms_3d.cu:30-534  (GPU-only op in the reference: the CPU
+//                  FCompute is LOG(FATAL), nms_3d.cc:11-18 -> nothing to compile here; restated)
+// ---------------------------------------------------------------------------------------------
+namespace n3 {
+const float EPS3 = 1e-8f;  // :27
+struct Pt { float x, y; };
+inline float cross2(Pt a, Pt b) { return a.x * b.y - a.y * b.x; }                        // :51-53
+inline float cross3(Pt p1, Pt p2, Pt p0) {                                                // :62-64
+  return (p1.x - p0.x) * (p2.y - p0.y) - (p2.x - p0.x) * (p1.y - p0.y);
+}
+inline int rect_cross(Pt p1, Pt p2, Pt q1, Pt q2) {                                       // :66-72
+  return fminf(p1.x, p2.x) <= fmaxf(q1.x, q2.x) && fminf(q1.x, q2.x) <= fmaxf(p1.x, p2.x) &&
+         fminf(p1.y, p2.y) <= fmaxf(q1.y, q2.y) && fminf(q1.y, q2.y) <= fmaxf(p1.y, p2.y);
+}
+inline int in_box(const float* box, Pt P) {                                               // check_in_box3d_anotherway :93-150
+  const float MARGIN = -1e-2f;
+  const Pt A = {box[0], box[1]}, B = {box[2], box[3]}, C = {box[4], box[5]}, D = {box[6], box[7]};
+  const Pt AB = {B.x - A.x, B.y - A.y}, BC = {C.x - B.x, C.y - B.y}, CD = {D.x - C.x, D.y - C.y}, DA = {A.x - D.x, A.y - D.y};
+  const float cw = cross2(AB, BC);
+  const Pt PA = {A.x - P.x, A.y - P.y};
+  if (cross2(PA, AB) * cw < MARGIN) return 0;
+  const Pt PB = {B.x - P.x, B.y - P.y};
+  if (cross2(PB, BC) * cw < MARGIN) return 0;
+  const Pt PC = {C.x - P.x, C.y - P.y};
+  if (cross2(PC, CD) * cw < MARGIN) return 0;
+  const Pt PD = {D.x - P.x, D.y - P.y};
+  if (cross2(PD, DA) * cw < MARGIN) return 0;
+  return 1;
+}
+inline int isect(Pt p1, Pt p0, Pt q1, Pt q0, Pt* ans) {                                   // intersection :152-181
+  if (!rect_cross(p0, p1, q0, q1)) return 0;
+  const float s1 = cross3(q0, p1, p0), s2 = cross3(p1, q1, p0), s3 = cross3(p0, q1, q0), s4 = cross3(q1, p1, q0);
+  if (!(s1 * s2 > 0 && s3 * s4 > 0)) return 0;
+  const float s5 = cross3(q1, p1, p0);
+  if (fabsf(s5 - s1) > EPS3) {
+    ans->x = (s5 * q0.x - s1 * q1.x) / (s5 - s1);
+    ans->y = (s5 * q0.y - s1 * q1.y) / (s5 - s1);
+  } else {
+    const float a0 = p0.y - p1.y, b0 = p1.x - p0.x, c0 = p0.x * p1.y - p1.x * p0.y;
+    const float a1 = q0.y - q1.y, b1 = q1.x - q0.x, c1 = q0.x * q1.y - q1.x * q0.y;
+    const float Dd = a0 * b1 - a1 * b0;
+    ans->x = (b0 * c1 - b1 * c0) / Dd;
+    ans->y = (a1 * c0 - a0 * c1) / Dd;
+  }
+  return 1;
+}
+inline float area_of(const float* b) {                                                    // get_area :193-198
+  const float e1 = (b[0] - b[2]) * (b[0] - b[2]) + (b[1] - b[3]) * (b[1] - b[3]);
+  const float e2 = (b[4] - b[2]) * (b[4] - b[2]) + (b[5] - b[3]) * (b[5] - b[3]);
+  return sqrtf(e1 * e2);
+}
+inline float overlap(const float* a, const float* b) {                                    // box_overlap :218-336
+  Pt ca[5], cb[5];
+  for (int k = 0; k < 4; ++k) { ca[k] = {a[2 * k], a[2 * k + 1]}; cb[k] = {b[2 * k], b[2 * k + 1]}; }
+  ca[4] = ca[0]; cb[4] = cb[0];
+  Pt pts[24], ctr = {0, 0};
+  int cnt = 0;
+  for (int i = 0; i < 4; ++i)
+    for (int j = 0; j < 4; ++j) {
+      Pt x;
+      if (isect(ca[i + 1], ca[i], cb[j + 1], cb[j], &x)) { ctr.x += x.x; ctr.y += x.y; if (cnt < 24) pts[cnt] = x; cnt++; }
+    }
+  for (int k = 0; k < 4; ++k) {
+    if (in_box(a, cb[k])) { ctr.x += cb[k].x; ctr.y += cb[k].y; if (cnt < 24) pts[cnt] = cb[k]; cnt++; }
+    if (in_box(b, ca[k])) { ctr.x += ca[k].x; ctr.y += ca[k].y; if (cnt < 24) pts[cnt] = ca[k]; cnt++; }
+  }
+  ctr.x /= cnt; ctr.y /= cnt;
+  const int n = cnt < 24 ? cnt : 24;
+  float ang[24];
+  for (int i = 0; i < n; ++i) ang[i] = atan2f(pts[i].y - ctr.y, pts[i].x - ctr.x);
+  for (int j = 0; j < n - 1; ++j)
+    for (int i = 0; i < n - j - 1; ++i)
+      if (ang[i] > ang[i + 1]) { std::swap(ang[i], ang[i + 1]); std::swap(pts[i], pts[i + 1]); }
+  float area = 0;
+  for (int k = 0; k < n - 1; ++k) {
+    const Pt u = {pts[k].x - pts[0].x, pts[k].y - pts[0].y}, v = {pts[k + 1].x - pts[0].x, pts[k + 1].y - pts[0].y};
+    area += cross2(u, v);
+  }
+  return fabsf(area) / 2.0f;
+}
+inline float iou_bev3d(const float* a, const float* b) {                                  // iou_bev :342-368
+  const float ha = a[9] - a[8], hb = b[9] - b[8];
+  float oh = fminf(a[9], b[9]) - fmaxf(a[8], b[8]);
+  if (oh < 0) oh = 0;
+  const float va = area_of(a) * ha, vb = area_of(b) * hb;
+  const float vo = overlap(a, b) * oh;
+  return vo / fmaxf(va + vb - vo, EPS3);
+}
+inline float iou_normal(const float* a, const float* b) {                                 // :370-378
+  const float left = fmaxf(a[0], b[0]), right = fminf(a[2], b[2]);
+  const float top = fmaxf(a[1], b[1]), bottom = fminf(a[3], b[3]);
+  const float w = fmaxf(right - left, 0.f), h = fmaxf(bottom - top, 0.f);
+  const float inter = w * h;
+  const float Sa = (a[2] - a[0]) * (a[3] - a[1]), Sb = (b[2] - b[0]) * (b[3] - b[1]);
+  return inter / fmaxf(Sa + Sb - inter, EPS3);
+}
+}  // namespace n3
+
 }  // namespace
 
 extern "C" {
@@ -554,6 +654,32 @@ int orc_wnms_4c(const float* dets, int n, float thresh, float thresh_vote, int i
     ++K;
   }
   return K;
+}
+
+// NMS3DForward<gpu> nms_3d.cu:470-534 + nms_kernel_3d :380-434 + prepare_output_kernel_3d :436-468.
+// boxes (B,N,10) sorted by score; keep_idx (B,max_keep) filled -1; boxes_out (B,max_keep,10) filled 0.
+void orc_nms3d(const float* boxes, int B, int N, float thr, int max_keep, int normal_iou, int* keep_idx,
+               float* boxes_out) {
+  for (long i = 0; i < (long)B * max_keep; ++i) keep_idx[i] = -1;
+  memset(boxes_out, 0, sizeof(float) * (size_t)B * max_keep * 10);
+  std::vector<char> removed(N);
+  for (int b = 0; b < B; ++b) {
+    const float* bx = boxes + (long)b * N * 10;
+    std::fill(removed.begin(), removed.end(), 0);
+    int kept = 0;
+    for (int i = 0; i < N; ++i) {
+      if (kept >= max_keep) break;
+      if (removed[i]) continue;
+      for (int k = 0; k < 10; ++k) boxes_out[((long)b * max_keep + kept) * 10 + k] = bx[i * 10 + k];
+      keep_idx[(long)b * max_keep + kept] = i;
+      ++kept;
+      for (int j = i + 1; j < N; ++j) {
+        if (removed[j]) continue;  // (the bitmask ORs all rows; already-removed columns stay removed)
+        const float v = normal_iou ? n3::iou_normal(bx + i * 10, bx + j * 10) : n3::iou_bev3d(bx + i * 10, bx + j * 10);
+        if (v > thr) removed[j] = 1;
+      }
+    }
+  }
 }
 
 }  // extern "C"

@@ -24,6 +24,7 @@ SIGNATURES = {
     "rd_check_device": (_i, []),
     "rd_launch_count": (ctypes.c_uint64, []),
     "rd_meta_kernel_fwd": (_i, [_vp] * 7 + [_i] * 5 + [_vp]),
+    "rd_meta_kernel_fwd_nhwc_bf16": (_i, [_vp] * 8 + [_i, _vp] + [_i] * 4 + [_vp]),
     "rd_meta_kernel_bwd_workspace_bytes": (_sz, [_i] * 4),
     "rd_meta_kernel_bwd": (_i, [_vp] * 12 + [_vp, _sz] + [_i] * 5 + [_vp]),
     "rd_meta_kernel_bwd_data": (_i, [_vp] * 7 + [_i] * 5 + [_vp]),
@@ -33,6 +34,8 @@ SIGNATURES = {
     "rd_batch_rotated_iou_max": (_i, [_vp, _vp, _vp, _i, _i64, _i, _i, _vp]),
     "rd_wnms_4c_workspace_bytes": (_sz, [_i]),
     "rd_wnms_4c": (_i, [_vp, _i, _f, _f, _i, _i, _vp, _vp, ctypes.POINTER(_i), _vp, _sz, _vp]),
+    "rd_nms3d_workspace_bytes": (_sz, [_i, _i]),
+    "rd_nms3d": (_i, [_vp, _i, _i, _f, _i, _i, _vp, _vp, _vp, _sz, _vp]),
     "rd_conv2d_nhwc_bf16": (_i, [_vp] * 6 + [_i] * 8 + [_vp]),
     "rd_deconv2d_nhwc_bf16": (_i, [_vp] * 6 + [_i] * 7 + [_vp]),
     "rd_tc_probe_gemm": (_i, [_vp, _vp, _vp, _i, _i, _i, _vp]),

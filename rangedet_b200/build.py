@@ -25,6 +25,7 @@ COMMON = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-st
 PER_FILE = {
     "decode_iou.cu": ["-fmad=false"],
     "wnms.cu": ["-fmad=false"],
+    "nms3d.cu": ["-fmad=false"],
 }
 
 

@@ -56,14 +56,18 @@ struct Smem {
   uint32_t tmem_slot;
 };
 
-// MODE 0: forward (tap tile = features, output = 9 product planes per channel)
+// MODE 0: forward (tap tile = features, output = 9 product planes per channel, NCHW fp32)
 // MODE 1: grad_data (tap tile = grad_out plane 8-k at the mirrored pixel, output = sum over taps)
+// MODE 2: forward fused with the point_wise_mlp BatchNorm + ReLU of meta_kernel_conv
+//         (dla_backbone.py:92-94): y = relu(out * scale + shift) written as haloed NHWC bf16 with
+//         TAP-MAJOR channels (k*64 + c) -- the aggregation 1x1 conv's weight is permuted to match --
+//         so each tap is one 64-channel x 128-pixel 128B-swizzled TMA store.
 template <int MODE>
 __global__ void __launch_bounds__(NTHREADS, 1)
 meta_ws_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant__ CUtensorMap tm_out,
                const float* __restrict__ coord, const float* __restrict__ w0, const float* __restrict__ b0,
-               const float* __restrict__ w1, const float* __restrict__ b1, int B, int H, int W, int tiles_w,
-               int ntiles) {
+               const float* __restrict__ w1, const float* __restrict__ b1, const float* __restrict__ ep_scale,
+               const float* __restrict__ ep_shift, int ep_relu, int B, int H, int W, int tiles_w, int ntiles) {
   extern __shared__ unsigned char smem_raw[];
   // TMA destinations need 128-byte (we use 1024) alignment; the dynamic window is only guaranteed 16
   Smem& S = *reinterpret_cast<Smem*>(smem_raw + ((1024u - (tc::smem_u32(smem_raw) & 1023u)) & 1023u));
@@ -124,15 +128,15 @@ meta_ws_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant_
         const int wt = tile % tiles_w, h = (tile / tiles_w) % H, b = tile / (tiles_w * H);
         const int w0px = wt * TW;
         const int bs = w0px >= 4 ? w0px - 4 : 0;  // aligned, non-negative box start
-        constexpr int UNITS = MODE == 0 ? 3 : 9;  // fwd: one box per neighbour row; bwd: one per tap
+        constexpr int UNITS = MODE != 1 ? 3 : 9;  // fwd: one box per neighbour row; bwd: one per tap
         for (int u = 0; u < UNITS; ++u, ++g) {
-          const int dy = MODE == 0 ? u - 1 : u / 3 - 1;
+          const int dy = MODE != 1 ? u - 1 : u / 3 - 1;
           const uint32_t s = g % NS_D, ph = (g / NS_D) & 1;
           tc::mbar_wait(&S.d_empty[s], ph ^ 1);
           const int hh = h + dy;
           if (hh >= 0 && hh < H) {
             tc::mbar_arrive_expect_tx(&S.d_full[s], IN_BYTES);
-            if (MODE == 0) tma::load_3d(S.dtile[s], &tm_in, &S.d_full[s], bs, hh, b * C);
+            if (MODE != 1) tma::load_3d(S.dtile[s], &tm_in, &S.d_full[s], bs, hh, b * C);
             else tma::load_4d(S.dtile[s], &tm_in, &S.d_full[s], bs, hh, 8 - u, b * C);
           } else {
             tc::mbar_arrive(&S.d_full[s]);  // row outside the image: nothing to load, consumers use 0
@@ -249,7 +253,7 @@ meta_ws_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant_
       for (int k = 0; k < 9; ++k, ++g) {
         const int dy = k / 3 - 1, dx = k % 3 - 1;
         const uint32_t st = g % NS_T, pht = (g / NS_T) & 1;
-        const uint32_t gu = MODE == 0 ? g / 3 : g;  // input unit (row box / tap box) this tap reads
+        const uint32_t gu = MODE != 1 ? g / 3 : g;  // input unit (row box / tap box) this tap reads
         const uint32_t sd = gu % NS_D, phd = (gu / NS_D) & 1;
         tc::mbar_wait(&S.t_full[st], pht);
         if (MODE == 1 || dx == -1) tc::mbar_wait(&S.d_full[sd], phd);
@@ -260,7 +264,49 @@ meta_ws_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant_
         const bool ok = (h + dy >= 0) && (h + dy < H) && col >= 0;
         const float* dt = S.dtile[sd] + (ok ? col : 0);
         const bool last_use = MODE == 1 || dx == 1;
-        if (MODE == 0) {
+        if (MODE == 2) {
+          const uint32_t so = n_store % NS_O;
+          if (leader) tma::store_wait_read<NS_O - 1>();
+          tma::named_bar_sync(BAR_EPI, 128);
+          unsigned char* ot = reinterpret_cast<unsigned char*>(S.otile[so]);  // [128 px][64 ch] bf16, 128B swizzle
+          const float* esc = ep_scale + k * C;
+          const float* esh = ep_shift + k * C;
+#pragma unroll
+          for (int half = 0; half < 2; ++half) {
+            float d[32];
+#pragma unroll
+            for (int i = 0; i < 32; ++i) d[i] = ok ? dt[(half * 32 + i) * DTW] : 0.f;
+            float v[32];
+            tc::tmem_ld_x32(tmem_base + lane_sel + st * C + half * 32, v);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              uint32_t pk[4];
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                const int c = half * 32 + j * 8 + 2 * e;
+                float a = fmaf(d[j * 8 + 2 * e] * v[j * 8 + 2 * e], __ldg(esc + c), __ldg(esh + c));
+                float bb = fmaf(d[j * 8 + 2 * e + 1] * v[j * 8 + 2 * e + 1], __ldg(esc + c + 1), __ldg(esh + c + 1));
+                if (ep_relu) { a = fmaxf(a, 0.f); bb = fmaxf(bb, 0.f); }
+                pk[e] = tc::pack_bf16x2(a, bb);
+              }
+              const int chunk = half * 4 + j;
+              *reinterpret_cast<uint4*>(ot + px * 128 + ((chunk ^ (px & 7)) << 4)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+            }
+          }
+          tc::tc_fence_before();
+          tc::fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0) {
+            tc::mbar_arrive(&S.t_empty[st]);
+            if (last_use) tc::mbar_arrive(&S.d_empty[sd]);
+          }
+          tma::named_bar_sync(BAR_EPI, 128);
+          if (leader) {
+            tma::store_4d(&tm_out, ot, k * C, w0px, h, b);
+            tma::store_commit();
+          }
+          ++n_store;
+        } else if (MODE == 0) {
           const uint32_t so = n_store % NS_O;
           if (leader) tma::store_wait_read<NS_O - 1>();  // the store that last used otile[so] has read it
           tma::named_bar_sync(BAR_EPI, 128);
@@ -334,8 +380,9 @@ meta_ws_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant_
   if (warp == 1) tc::tmem_dealloc(tmem_base, TMEM_COLS);
 }
 
-inline int launch(int mode, const float* tap_src, float* dst, const float* coord, const float* w0, const float* b0,
-                  const float* w1, const float* b1, int B, int Cc, int H, int W, cudaStream_t stream) {
+inline int launch(int mode, const float* tap_src, void* dst, const float* coord, const float* w0, const float* b0,
+                  const float* w1, const float* b1, const float* ep_scale, const float* ep_shift, int ep_relu, int B,
+                  int Cc, int H, int W, cudaStream_t stream) {
   RD_REQUIRE(Cc == C, "Meta-Kernel impl 3 (TMA/tcgen05) is specialised for C == 64 (got %d)", Cc);
   RD_REQUIRE(W % 4 == 0, "Meta-Kernel impl 3 needs W %% 4 == 0 (TMA row stride must be a multiple of 16 B); W=%d", W);
   RD_REQUIRE((reinterpret_cast<uintptr_t>(tap_src) & 15) == 0 && (reinterpret_cast<uintptr_t>(dst) & 15) == 0,
@@ -357,9 +404,18 @@ inline int launch(int mode, const float* tap_src, float* dst, const float* coord
   if (mode == 0) {
     if (tma::make_map(&tm_in, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, tap_src, 3, d3, s3, b3in, CU_TENSOR_MAP_SWIZZLE_NONE)) return 1;
     if (tma::make_map(&tm_out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, dst, 4, d4, s4, b4, CU_TENSOR_MAP_SWIZZLE_NONE)) return 1;
-  } else {
+  } else if (mode == 1) {
     if (tma::make_map(&tm_in, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, tap_src, 4, d4, s4, b4in, CU_TENSOR_MAP_SWIZZLE_NONE)) return 1;
     if (tma::make_map(&tm_out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, dst, 3, d3, s3, b3, CU_TENSOR_MAP_SWIZZLE_NONE)) return 1;
+  } else {
+    if (tma::make_map(&tm_in, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, tap_src, 3, d3, s3, b3in, CU_TENSOR_MAP_SWIZZLE_NONE)) return 1;
+    // interior view of the haloed NHWC bf16 output (9C, W, H, B)
+    const uint64_t Wp = (uint64_t)W + 2, Hp = (uint64_t)H + 2, CO = 9u * C;
+    const uint64_t dn[4] = {CO, (uint64_t)W, (uint64_t)H, (uint64_t)B};
+    const uint64_t sn[3] = {CO * 2, Wp * CO * 2, Hp * Wp * CO * 2};
+    const uint32_t bn[4] = {(uint32_t)C, (uint32_t)TW, 1u, 1u};
+    const char* y_int = static_cast<const char*>(dst) + (Wp + 1) * CO * 2;
+    if (tma::make_map(&tm_out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, y_int, 4, dn, sn, bn, CU_TENSOR_MAP_SWIZZLE_128B)) return 1;
   }
   int dev = 0, sms = 0;
   RD_CUDA(cudaGetDevice(&dev));
@@ -372,29 +428,46 @@ inline int launch(int mode, const float* tap_src, float* dst, const float* coord
       RD_CUDA(cudaFuncSetAttribute(meta_ws_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
       attr0 = true;
     }
-    meta_ws_kernel<0><<<(unsigned)grid, NTHREADS, smem, stream>>>(tm_in, tm_out, coord, w0, b0, w1, b1, B, H, W, tiles_w,
-                                                                  (int)ntiles);
+    meta_ws_kernel<0><<<(unsigned)grid, NTHREADS, smem, stream>>>(tm_in, tm_out, coord, w0, b0, w1, b1, nullptr, nullptr, 0,
+                                                                  B, H, W, tiles_w, (int)ntiles);
+  } else if (mode == 2) {
+    static bool attr2 = false;
+    if (!attr2) {
+      RD_CUDA(cudaFuncSetAttribute(meta_ws_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      attr2 = true;
+    }
+    meta_ws_kernel<2><<<(unsigned)grid, NTHREADS, smem, stream>>>(tm_in, tm_out, coord, w0, b0, w1, b1, ep_scale, ep_shift,
+                                                                  ep_relu, B, H, W, tiles_w, (int)ntiles);
   } else {
     static bool attr1 = false;
     if (!attr1) {
       RD_CUDA(cudaFuncSetAttribute(meta_ws_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
       attr1 = true;
     }
-    meta_ws_kernel<1><<<(unsigned)grid, NTHREADS, smem, stream>>>(tm_in, tm_out, coord, w0, b0, w1, b1, B, H, W, tiles_w,
-                                                                  (int)ntiles);
+    meta_ws_kernel<1><<<(unsigned)grid, NTHREADS, smem, stream>>>(tm_in, tm_out, coord, w0, b0, w1, b1, nullptr, nullptr, 0,
+                                                                  B, H, W, tiles_w, (int)ntiles);
   }
   rd::count_launch();
-  return rd::check_launch(mode == 0 ? "rd_meta_kernel_fwd(impl 3)" : "rd_meta_kernel_bwd_data(impl 3)");
+  return rd::check_launch(mode == 1 ? "rd_meta_kernel_bwd_data(impl 3)" : "rd_meta_kernel_fwd(impl 3)");
 }
 
 }  // namespace mkws
 
 int rd_meta_kernel_fwd_ws(const float* data, const float* coord, const float* w0, const float* b0, const float* w1,
                           const float* b1, float* out, int B, int C, int H, int W, cudaStream_t stream) {
-  return mkws::launch(0, data, out, coord, w0, b0, w1, b1, B, C, H, W, stream);
+  return mkws::launch(0, data, out, coord, w0, b0, w1, b1, nullptr, nullptr, 0, B, C, H, W, stream);
 }
 int rd_meta_kernel_bwd_data_ws(const float* grad_out, const float* coord, const float* w0, const float* b0,
                                const float* w1, const float* b1, float* grad_data, int B, int C, int H, int W,
                                cudaStream_t stream) {
-  return mkws::launch(1, grad_out, grad_data, coord, w0, b0, w1, b1, B, C, H, W, stream);
+  return mkws::launch(1, grad_out, grad_data, coord, w0, b0, w1, b1, nullptr, nullptr, 0, B, C, H, W, stream);
+}
+
+extern "C" int rd_meta_kernel_fwd_nhwc_bf16(const float* data, const float* coord, const float* w0, const float* b0,
+                                            const float* w1, const float* b1, const float* scale, const float* shift,
+                                            int relu, void* y_pad, int B, int C, int H, int W, rd_stream_t stream) {
+  RD_REQUIRE(data && coord && w0 && b0 && w1 && b1 && scale && shift && y_pad, "rd_meta_kernel_fwd_nhwc_bf16: null pointer");
+  RD_REQUIRE(B > 0 && H > 0 && W > 0, "rd_meta_kernel_fwd_nhwc_bf16: bad shape");
+  if (rd_check_device()) return 1;
+  return mkws::launch(2, data, y_pad, coord, w0, b0, w1, b1, scale, shift, relu, B, C, H, W, rd::as_stream(stream));
 }

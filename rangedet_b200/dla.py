@@ -9,9 +9,10 @@ kernel (ops.conv2d_nhwc / ops.deconv2d_nhwc) with BatchNorm (moving statistics, 
 mxnext/complicate.py:14,32-43) + ReLU + residual folded into its epilogue, and the Meta-Kernel unit
 runs the fused TMA/tcgen05 Meta-Kernel.  Activations stay in HBM as zero-haloed NHWC bf16.
 
-Not yet fused (round-1 glue, plain torch elementwise ops on the Meta-Kernel boundary): the
-(B,576,H,W) fp32 Meta-Kernel output -> BN(576)+ReLU -> NHWC bf16 conversion, and the NCHW<->NHWC
-conversion of the network input.  Training-mode BatchNorm (batch statistics) and the backward
+The Meta-Kernel unit (meta_kernel_conv) runs as: NHWC bf16 -> NCHW fp32 conversion of the 64-channel
+input (torch, the op boundary of the Meta-Kernel) -> ONE fused kernel (Meta-Kernel + BN(576) + ReLU,
+NHWC bf16 out) -> tcgen05 1x1 aggregation conv.  `fuse_meta=False` keeps the reference op boundary
+((B,576,H,W) fp32) with torch glue, for comparison.  Training-mode BatchNorm (batch statistics) and the backward
 convolutions are next-round work.
 """
 import torch
@@ -69,8 +70,8 @@ class _BufferPool:
 class DLABackbone(object):
     """DLABackbone(pBackbone).get_rpn_feature(data) of the reference, over torch tensors."""
 
-    def __init__(self, params, device="cuda", meta_impl=ops.IMPL_DEFAULT):
-        self.P, self.device, self.meta_impl = params, device, meta_impl
+    def __init__(self, params, device="cuda", meta_impl=ops.IMPL_DEFAULT, fuse_meta=True):
+        self.P, self.device, self.meta_impl, self.fuse_meta = params, device, meta_impl, fuse_meta
         self.L = {}
         self.pool = _BufferPool()
 
@@ -88,15 +89,28 @@ class DLABackbone(object):
 
     def meta_kernel_conv(self, x, coord, name):  # dla_backbone.py:58-103
         P, dev = self.P, self.device
-        feat = ops.from_nhwc_padded(x)  # (B,64,H,W) fp32
-        m = ops.meta_kernel_forward(feat, coord, P[name + "_2656_mlp0_weight"].to(dev).reshape(32, 3),
-                                    P[name + "_2656_mlp0_bias"].to(dev), P[name + "_2656_mlp1_weight"].to(dev).reshape(-1, 32),
-                                    P[name + "_2656_mlp1_bias"].to(dev), impl=self.meta_impl)
+        feat = ops.from_nhwc_padded(x)  # (B,64,H,W) fp32 -- op boundary of the Meta-Kernel
         bn = name + "point_wise_mlp_bn1"
         s = P[bn + "_gamma"].to(dev) / torch.sqrt(P[bn + "_moving_var"].to(dev) + EPS)
         b = P[bn + "_beta"].to(dev) - P[bn + "_moving_mean"].to(dev) * s
+        args = (P[name + "_2656_mlp0_weight"].to(dev).reshape(32, 3), P[name + "_2656_mlp0_bias"].to(dev),
+                P[name + "_2656_mlp1_weight"].to(dev).reshape(-1, 32), P[name + "_2656_mlp1_bias"].to(dev))
+        B, C, H, W = feat.shape
+        wname = name + "aggregation_conv1"
+        if self.fuse_meta and C == 64 and W % 4 == 0:
+            # Meta-Kernel + BN(576) + ReLU in one kernel, NHWC bf16 out with tap-major channels (k*64+c);
+            # the 1x1 aggregation conv's input channels are permuted to match
+            m = ops.meta_kernel_forward_nhwc(feat, coord, *args, s, b, relu=True,
+                                             out=self.pool.get(name + "_meta", (B, H + 2, W + 2, 9 * C), dev))
+            if wname + "#tapmajor" not in self.L:
+                Pt = {wname + "_weight": ops.tap_major_weight(P[wname + "_weight"].to(dev), C)}
+                Pt.update({k: v for k, v in P.items() if k.startswith(name + "aggregation_bn1")})
+                self.L[wname + "#tapmajor"] = _Layer(Pt, wname, name + "aggregation_bn1", device=dev)
+            l = self.L[wname + "#tapmajor"]
+            return ops.conv2d_nhwc(m, l.w, l.scale, l.shift, relu=True, out=self.pool.get(wname, (B, H + 2, W + 2, l.cout_p), dev))
+        m = ops.meta_kernel_forward(feat, coord, *args, impl=self.meta_impl)
         m = torch.relu_(m.mul_(s[None, :, None, None]).add_(b[None, :, None, None]))
-        return self.conv_bn(ops.to_nhwc_padded(m), name + "aggregation_conv1", name + "aggregation_bn1")
+        return self.conv_bn(ops.to_nhwc_padded(m), wname, name + "aggregation_bn1")
 
     def basicblock(self, x, coord, name, stride_w, proj):  # dla_backbone.py:17-56
         if name in META_UNITS:

@@ -64,6 +64,33 @@ def meta_kernel_forward(data, coord, w0, b0, w1, b1, impl=IMPL_DEFAULT):
     return out
 
 
+def meta_kernel_forward_nhwc(data, coord, w0, b0, w1, b1, scale, shift, relu=True, out=None):
+    """Meta-Kernel forward fused with the following per-channel scale/shift (+ReLU), written as haloed NHWC
+    bf16 (B,H+2,W+2,9C) with tap-major channels k*C+c; `scale`/`shift` are given in the REFERENCE order
+    (c*9+k, i.e. the BatchNorm(576) parameters of dla_backbone.py:93) and permuted here."""
+    data = _chk(data, "data", 4)
+    coord = _chk(coord, "coord", 4)
+    B, C, H, W = data.shape
+    w0 = _chk(w0.reshape(w0.shape[0], -1), "w0", 2)
+    w1 = _chk(w1.reshape(w1.shape[0], -1), "w1", 2)
+    b0, b1 = _chk(b0, "b0", 1), _chk(b1, "b1", 1)
+    sc = scale.float().reshape(C, 9).t().contiguous().reshape(-1)   # (c*9+k) -> (k*C+c)
+    sh = shift.float().reshape(C, 9).t().contiguous().reshape(-1)
+    if out is None:
+        out = torch.zeros((B, H + 2, W + 2, 9 * C), device=data.device, dtype=torch.bfloat16)
+    with torch.cuda.device(data.device):
+        st = _lib.lib().rd_meta_kernel_fwd_nhwc_bf16(_p(data), _p(coord), _p(w0), _p(b0), _p(w1), _p(b1), _p(sc), _p(sh),
+                                                     int(bool(relu)), _p(out), B, C, H, W, _stream())
+    _lib.check(st, "meta_kernel_forward_nhwc")
+    return out
+
+
+def tap_major_weight(w_oihw, C=64):
+    """Permute the input channels of the aggregation conv weight (Cout, 9C, 1, 1) from c*9+k to k*C+c."""
+    co = w_oihw.shape[0]
+    return w_oihw.reshape(co, C, 9, *w_oihw.shape[2:]).transpose(1, 2).reshape(co, 9 * C, *w_oihw.shape[2:]).contiguous()
+
+
 def meta_kernel_backward(grad_out, data, coord, w0, b0, w1, b1, impl=IMPL_DEFAULT):
     """-> (grad_data, grad_w0, grad_b0, grad_w1, grad_b1)."""
     data = _chk(data, "data", 4)
@@ -177,6 +204,23 @@ def wnms_4c_device(dets, thresh, thresh_vote, is_3d=False, hash_scale=100):
     _lib.check(st, "wnms_4c")
     k = cnt.value
     return out[:k], keep[:k]
+
+
+def nms3d(boxes, iou_thres, max_keep, normal_iou=False):
+    """_contrib_NMS3D (nms_3d.cc:22-66): boxes (B,N,10) sorted by score -> (keep_idx (B,max_keep) int32 with -1
+    fill, boxes_after_nms (B,max_keep,10) with 0 fill)."""
+    bx = _chk(boxes, "boxes", 3, 10)
+    B, N, _ = bx.shape
+    keep = torch.empty((B, max_keep), device=bx.device, dtype=torch.int32)
+    out = torch.empty((B, max_keep, 10), device=bx.device, dtype=torch.float32)
+    L = _lib.lib()
+    nbytes = int(L.rd_nms3d_workspace_bytes(B, N))
+    ws = torch.empty((max(nbytes, 16) + 15) // 16 * 4, device=bx.device, dtype=torch.float32)
+    with torch.cuda.device(bx.device):
+        st = L.rd_nms3d(_p(bx), B, N, float(iou_thres), int(max_keep), int(bool(normal_iou)), _p(keep), _p(out), _p(ws),
+                        ctypes.c_size_t(ws.numel() * 4), _stream())
+    _lib.check(st, "nms3d")
+    return keep, out
 
 
 def tc_probe_gemm(a, b, mn_major=False):

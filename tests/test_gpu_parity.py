@@ -196,6 +196,24 @@ def test_wnms_edge_cases_and_plugin_surface(ops, orc):
 
 
 # ---------------------------------------------------------------------------------------------
+# NMS3D (hard NMS): keep indices bit-exact against the restated reference kernels
+# ---------------------------------------------------------------------------------------------
+def test_nms3d(ops, orc):
+    for n, cl, thr, mk in [(3000, True, 0.1, 500), (20000, False, 0.25, 4096), (50000, True, 0.1, 1000)]:
+        b = np.stack([synth.boxes7_to_corners10(synth.boxes7(n, seed=70 + i, clustered=cl)) for i in range(2)], 0)
+        wk, wb = orc.nms3d(b, thr, mk, False)
+        gk, gb = ops.nms3d(cu(b), thr, mk, False)
+        same = np.array_equal(gk.cpu().numpy(), wk)
+        report(test="nms3d", n=n, clustered=cl, kept=int((wk >= 0).sum()), keep_bit_exact=bool(same))
+        assert same and np.array_equal(gb.cpu().numpy(), wb)
+    wk, wb = orc.nms3d(b[:, :4000], 0.3, 300, True)
+    gk, gb = ops.nms3d(cu(b[:, :4000]), 0.3, 300, True)
+    assert np.array_equal(gk.cpu().numpy(), wk) and np.array_equal(gb.cpu().numpy(), wb)
+    k0, b0 = ops.nms3d(torch.zeros(1, 0, 10).cuda(), 0.1, 8)
+    assert (k0.cpu().numpy() == -1).all() and not b0.any()
+
+
+# ---------------------------------------------------------------------------------------------
 # Meta-Kernel
 # ---------------------------------------------------------------------------------------------
 def _mk_inputs(B, C, H, W, wpad, seed):
@@ -289,6 +307,23 @@ def test_meta_kernel_autograd_and_properties(ops):
         p.grad = None
     ops.meta_kernel(dd, args[0][:, :, :8, :256].contiguous(), *ps).square().sum().backward()
     assert all(torch.equal(a, p.grad) for a, p in zip(g1, ps))  # deterministic reduction
+
+
+def test_meta_kernel_fused_nhwc_output(ops):
+    """MODE 2: Meta-Kernel + per-channel scale/shift + ReLU -> haloed NHWC bf16, tap-major channels."""
+    from oracle import meta_kernel_ref
+    B, C, H, W, wpad = 2, 64, 6, 300, 304
+    data, coord, (w0, b0, w1, b1) = _mk_inputs(B, C, H, W, wpad, seed=50)
+    g = torch.Generator().manual_seed(3)
+    scale, shift = torch.rand(9 * C, generator=g) + 0.5, torch.randn(9 * C, generator=g) * 0.2
+    ref = meta_kernel_ref.meta_baseline_bias(*[torch.from_numpy(x) for x in (data, coord, w0, b0, w1, b1)])
+    want = (ref * scale[None, :, None, None] + shift[None, :, None, None]).relu()          # (B, c*9+k, H, W)
+    yp = ops.meta_kernel_forward_nhwc(cu(data), cu(coord), cu(w0), cu(b0), cu(w1), cu(b1), scale.cuda(), shift.cuda())
+    assert not yp[:, 0].any() and not yp[:, -1].any() and not yp[:, :, 0].any() and not yp[:, :, -1].any()
+    got = yp[:, 1:-1, 1:-1, :].float().cpu().reshape(B, H, wpad, 9, C).permute(0, 4, 3, 1, 2).reshape(B, 9 * C, H, wpad)
+    err = (got - want).abs()
+    assert bool((err <= 2.0 ** -7 * want.abs() + 1e-2).all()), float(err.max())
+    report(test="meta_fwd_nhwc_fused", rel_err=rel_err(got.numpy(), want.numpy()))
 
 
 def test_meta_kernel_class_surface(ops):
