@@ -11,7 +11,8 @@
 //   gW0[j][d] += sum_p relu'(.) ghid[p][j] rel[p][d], gb0 likewise        (fp32 register accumulators)
 // bf16 hi+lo splits of gw / hid / W1 keep every product within ~2^-16 of fp32.
 // Roles: warp 0 TMA producer (grad_out tap tiles + feature row boxes), warp 1 MMA issuer,
-// warps 2-5 builders (operand tiles, D1 consumption).  One partial result row per CTA goes to the
+// warps 2-9 builders (two threads per pixel: operand tiles, D1 consumption; they are the
+// critical resource -- ncu showed producer and MMA warps spinning on builder-signalled barriers).  One partial result row per CTA goes to the
 // workspace; the deterministic reduce kernel of meta_kernel.cu finishes the sum.
 #include "../../include/rangedet_b200.h"
 #include "rd_common.cuh"
@@ -22,7 +23,8 @@ namespace mkwp {
 
 constexpr int HID = 32, CCH = 3, C = 64;
 constexpr int TW = 128, ROW = TW + 2, DTW = TW + 8;
-constexpr int NTHREADS = 192;                 // warp 0 TMA, warp 1 MMA, warps 2-5 builders
+constexpr int NTHREADS = 320;                 // warp 0 TMA, warp 1 MMA, warps 2-9 builders
+constexpr int NBUILD = 256;
 constexpr int CHUNK = TW * 16;                // one 16-byte chunk over 128 pixel rows (2048 B)
 constexpr int GW_BYTES = 16 * CHUNK;          // gw_hi (8 chunks of 8 channels) | gw_lo (8 chunks)
 constexpr int H_BYTES = 10 * CHUNK;           // h_hi (4) | h_lo (4) | ones chunk | zero chunk
@@ -59,11 +61,11 @@ meta_ws_params_kernel(const __grid_constant__ CUtensorMap tm_go, const __grid_co
   const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
 
   if (t == 0) {
-    for (int i = 0; i < NS_G; ++i) { tc::mbar_init(&S.go_full[i], 1); tc::mbar_init(&S.go_empty[i], 4); }
-    for (int i = 0; i < NS_R; ++i) { tc::mbar_init(&S.dr_full[i], 1); tc::mbar_init(&S.dr_empty[i], 4); }
-    tc::mbar_init(&S.ops_full, 4);
+    for (int i = 0; i < NS_G; ++i) { tc::mbar_init(&S.go_full[i], 1); tc::mbar_init(&S.go_empty[i], 8); }
+    for (int i = 0; i < NS_R; ++i) { tc::mbar_init(&S.dr_full[i], 1); tc::mbar_init(&S.dr_empty[i], 8); }
+    tc::mbar_init(&S.ops_full, 8);
     tc::mbar_init(&S.ops_free, 1);
-    for (int i = 0; i < 2; ++i) { tc::mbar_init(&S.d1_full[i], 1); tc::mbar_init(&S.d1_empty[i], 4); }
+    for (int i = 0; i < 2; ++i) { tc::mbar_init(&S.d1_full[i], 1); tc::mbar_init(&S.d1_empty[i], 8); }
     tc::fence_mbar_init();
     tma::prefetch_map(&tm_go);
     tma::prefetch_map(&tm_data);
@@ -74,9 +76,9 @@ meta_ws_params_kernel(const __grid_constant__ CUtensorMap tm_go, const __grid_co
   }
   if (warp >= 2) {  // constants: layer-0 params, W1^T hi/lo in K-major core-matrix layout, ones/zero chunks of H
     const int bt = t - 64;
-    for (int j = bt; j < HID; j += 128)
+    for (int j = bt; j < HID; j += NBUILD)
       S.w0b[j] = make_float4(__ldg(w0 + j * 3 + 0), __ldg(w0 + j * 3 + 1), __ldg(w0 + j * 3 + 2), __ldg(b0 + j));
-    for (int e = bt; e < HID * 8; e += 128) {  // chunk q (8 channels c = 8q..8q+7) of row j
+    for (int e = bt; e < HID * 8; e += NBUILD) {  // chunk q (8 channels c = 8q..8q+7) of row j
       const int j = e % HID, q = e / HID;
       uint32_t hi[4], lo[4];
 #pragma unroll
@@ -90,8 +92,10 @@ meta_ws_params_kernel(const __grid_constant__ CUtensorMap tm_go, const __grid_co
       *reinterpret_cast<uint4*>(S.w1t + q * W1T_CHUNK + j * 16) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
       *reinterpret_cast<uint4*>(S.w1t + (8 + q) * W1T_CHUNK + j * 16) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
     }
-    *reinterpret_cast<uint4*>(S.h + 8 * CHUNK + bt * 16) = make_uint4(tc::pack_bf16x2(1.f, 0.f), 0u, 0u, 0u);
-    *reinterpret_cast<uint4*>(S.h + 9 * CHUNK + bt * 16) = make_uint4(0u, 0u, 0u, 0u);
+    if (bt < TW) {
+      *reinterpret_cast<uint4*>(S.h + 8 * CHUNK + bt * 16) = make_uint4(tc::pack_bf16x2(1.f, 0.f), 0u, 0u, 0u);
+      *reinterpret_cast<uint4*>(S.h + 9 * CHUNK + bt * 16) = make_uint4(0u, 0u, 0u, 0u);
+    }
     tc::fence_proxy_async_smem();
   }
   tc::tc_fence_before();
@@ -169,14 +173,18 @@ meta_ws_params_kernel(const __grid_constant__ CUtensorMap tm_go, const __grid_co
     }
     __syncwarp();
   } else {
-    // ===== builders (128 threads, thread = pixel = TMEM lane) =====
-    const int bt = t - 64;
-    const int q4 = warp & 3;
-    const int px = q4 * 32 + lane;  // NOTE: bt != px in general; tiles are indexed by px everywhere below
+    // ===== builders: 8 warps = 2 threads per pixel (TMEM lane); thread `hf` owns hidden units
+    // [16hf, 16hf+16) and channels [32hf, 32hf+32) of its pixel =====
+    const int bt = t - 64;                 // 0..255
+    const int hf = (warp - 2) >> 2;        // which half of the per-pixel work
+    const int q4 = warp & 3;               // TMEM lane quadrant of this warp
+    const int px = q4 * 32 + lane;
     const uint32_t lane_sel = (uint32_t)(q4 * 32) << 16;
-    float acc0[HID][4];  // gW0[j][d], d == 3 -> gb0[j]
+    constexpr int HJ = HID / 2;            // hidden units per thread
+    constexpr int CS_PER_THREAD = (3 * CCH * ROW + NBUILD - 1) / NBUILD;
+    float acc0[HJ][4];  // gW0[j][d], d == 3 -> gb0[j], for j = 16hf + jj
 #pragma unroll
-    for (int j = 0; j < HID; ++j)
+    for (int j = 0; j < HJ; ++j)
 #pragma unroll
       for (int d = 0; d < 4; ++d) acc0[j][d] = 0.f;
     uint32_t g = 0, gr = 0;
@@ -189,13 +197,13 @@ meta_ws_params_kernel(const __grid_constant__ CUtensorMap tm_go, const __grid_co
       tc::mbar_wait(&S.d1_full[s1], ph1);
       __syncwarp();
       tc::tc_fence_after();
-      float v[32];
-      tc::tmem_ld_x32(tmem_base + lane_sel + s1 * HID, v);
+      float v[16];
+      tc::tmem_ld_x16(tmem_base + lane_sel + s1 * HID + hf * HJ, v);
       tc::tc_fence_before();
       __syncwarp();
       if (lane == 0) tc::mbar_arrive(&S.d1_empty[s1]);
 #pragma unroll
-      for (int j = 0; j < HID; ++j) {
+      for (int j = 0; j < HJ; ++j) {
         const float gh = ((mask >> j) & 1u) ? v[j] : 0.f;
         acc0[j][0] = fmaf(gh, rel[0], acc0[j][0]);
         acc0[j][1] = fmaf(gh, rel[1], acc0[j][1]);
@@ -203,20 +211,37 @@ meta_ws_params_kernel(const __grid_constant__ CUtensorMap tm_go, const __grid_co
         acc0[j][3] += gh;
       }
     };
-
-    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    // coordinate tile of `tile` -> registers (software prefetch: issued one tile ahead)
+    auto load_coords = [&](int tile, float (&cp)[CS_PER_THREAD]) {
       const int wt = tile % tiles_w, h = (tile / tiles_w) % H, b = tile / (tiles_w * H);
       const int w0px = wt * TW;
-      const int bs = w0px >= 4 ? w0px - 4 : 0;
-      tma::named_bar_sync(BAR_BLD, 128);
-      for (int e = bt; e < 3 * CCH * ROW; e += 128) {
-        const int col = e % ROW, d = (e / ROW) % CCH, r = e / (ROW * CCH);
-        const int hh = h + r - 1, ww = w0px + col - 1;
+#pragma unroll
+      for (int i = 0; i < CS_PER_THREAD; ++i) {
+        const int e = bt + i * NBUILD;
         float v = 0.f;
-        if (hh >= 0 && hh < H && ww >= 0 && ww < W) v = __ldg(coord + (((int64_t)b * CCH + d) * H + hh) * W + ww);
-        S.cs[(r * CCH + d) * ROW + col] = v;
+        if (e < 3 * CCH * ROW) {
+          const int col = e % ROW, d = (e / ROW) % CCH, r = e / (ROW * CCH);
+          const int hh = h + r - 1, ww = w0px + col - 1;
+          if (hh >= 0 && hh < H && ww >= 0 && ww < W) v = __ldg(coord + (((int64_t)b * CCH + d) * H + hh) * W + ww);
+        }
+        cp[i] = v;
       }
-      tma::named_bar_sync(BAR_BLD, 128);
+    };
+    float cpre[CS_PER_THREAD];
+    if ((int)blockIdx.x < ntiles) load_coords(blockIdx.x, cpre);
+
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+      const int wt = tile % tiles_w, h = (tile / tiles_w) % H;
+      const int w0px = wt * TW;
+      const int bs = w0px >= 4 ? w0px - 4 : 0;
+      tma::named_bar_sync(BAR_BLD, NBUILD);  // everyone finished reading the previous coordinate tile
+#pragma unroll
+      for (int i = 0; i < CS_PER_THREAD; ++i) {
+        const int e = bt + i * NBUILD;
+        if (e < 3 * CCH * ROW) S.cs[e] = cpre[i];
+      }
+      tma::named_bar_sync(BAR_BLD, NBUILD);
+      if (tile + (int)gridDim.x < ntiles) load_coords(tile + gridDim.x, cpre);  // in flight during this tile
       const float c0 = S.cs[(1 * CCH + 0) * ROW + px + 1];
       const float c1 = S.cs[(1 * CCH + 1) * ROW + px + 1];
       const float c2 = S.cs[(1 * CCH + 2) * ROW + px + 1];
@@ -224,18 +249,18 @@ meta_ws_params_kernel(const __grid_constant__ CUtensorMap tm_go, const __grid_co
 
       for (int k = 0; k < 9; ++k, ++g) {
         const int dy = k / 3 - 1, dx = k % 3 - 1;
-        // ---- hidden layer of (pixel, tap), kept packed in registers
+        // ---- this thread's 16 hidden units of (pixel, tap), kept packed in registers
         const int ccol = px + 1 + dx, r = dy + 1;
         const float r0 = S.cs[(r * CCH + 0) * ROW + ccol] - c0;
         const float r1 = S.cs[(r * CCH + 1) * ROW + ccol] - c1;
         const float r2 = S.cs[(r * CCH + 2) * ROW + ccol] - c2;
-        uint32_t hhi[16], hlo[16], mask = 0;
+        uint32_t hhi[HJ / 2], hlo[HJ / 2], mask = 0;
 #pragma unroll
-        for (int jp = 0; jp < 16; ++jp) {
+        for (int jp = 0; jp < HJ / 2; ++jp) {
           float hh[2], hl[2];
 #pragma unroll
           for (int u = 0; u < 2; ++u) {
-            const float4 wv = S.w0b[jp * 2 + u];
+            const float4 wv = S.w0b[hf * HJ + jp * 2 + u];
             float z = wv.w;
             z = fmaf(wv.x, r0, z);
             z = fmaf(wv.y, r1, z);
@@ -256,43 +281,51 @@ meta_ws_params_kernel(const __grid_constant__ CUtensorMap tm_go, const __grid_co
         const bool ok = px_ok && (h + dy >= 0) && (h + dy < H) && col >= 0;
         const float* gt = S.go[sg] + px;
         const float* dt = S.drow[sr] + (ok ? col : 0);
-        // ---- operand tiles may be overwritten once the previous tap's MMAs have read them
-        tc::mbar_wait(&S.ops_free, (g & 1) ^ 1);
+        // products first (registers), so the shared-memory loads are not serialised behind the stores
+        uint32_t ghi[4][4], glo[4][4];
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          *reinterpret_cast<uint4*>(S.h + q * CHUNK + px * 16) =
-              make_uint4(hhi[q * 4 + 0], hhi[q * 4 + 1], hhi[q * 4 + 2], hhi[q * 4 + 3]);
-          *reinterpret_cast<uint4*>(S.h + (4 + q) * CHUNK + px * 16) =
-              make_uint4(hlo[q * 4 + 0], hlo[q * 4 + 1], hlo[q * 4 + 2], hlo[q * 4 + 3]);
-        }
-#pragma unroll
-        for (int cb = 0; cb < 8; ++cb) {  // 8 channels per 16-byte chunk
+        for (int cq = 0; cq < 4; ++cq) {  // 8 channels per 16-byte chunk; this thread: chunks 4hf .. 4hf+3
           float gv[8], dv[8];
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
-            gv[i] = gt[(cb * 8 + i) * TW];
-            dv[i] = ok ? dt[(cb * 8 + i) * DTW] : 0.f;
+            const int c = (hf * 4 + cq) * 8 + i;
+            gv[i] = gt[c * TW];
+            dv[i] = ok ? dt[c * DTW] : 0.f;
           }
-          uint32_t hi[4], lo[4];
 #pragma unroll
           for (int p = 0; p < 4; ++p) {
             float h0, l0, h1, l1;
             tc::split_bf16(gv[2 * p] * dv[2 * p], h0, l0);
             tc::split_bf16(gv[2 * p + 1] * dv[2 * p + 1], h1, l1);
-            hi[p] = tc::pack_bf16x2(h0, h1);
-            lo[p] = tc::pack_bf16x2(l0, l1);
+            ghi[cq][p] = tc::pack_bf16x2(h0, h1);
+            glo[cq][p] = tc::pack_bf16x2(l0, l1);
           }
-          *reinterpret_cast<uint4*>(S.gw + cb * CHUNK + px * 16) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-          *reinterpret_cast<uint4*>(S.gw + (8 + cb) * CHUNK + px * 16) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
         }
-        tc::fence_proxy_async_smem();
         __syncwarp();
-        if (lane == 0) {
-          tc::mbar_arrive(&S.ops_full);
+        if (lane == 0) {  // input tiles fully read by this warp
           tc::mbar_arrive(&S.go_empty[sg]);
           if (dx == 1) tc::mbar_arrive(&S.dr_empty[sr]);
         }
         if (dx == 1) ++gr;
+        // ---- operand tiles may be overwritten once the previous tap's MMAs have read them
+        tc::mbar_wait(&S.ops_free, (g & 1) ^ 1);
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {  // h chunks: hi 2hf, 2hf+1 ; lo 4+2hf, 4+2hf+1
+          *reinterpret_cast<uint4*>(S.h + (hf * 2 + q) * CHUNK + px * 16) =
+              make_uint4(hhi[q * 4 + 0], hhi[q * 4 + 1], hhi[q * 4 + 2], hhi[q * 4 + 3]);
+          *reinterpret_cast<uint4*>(S.h + (4 + hf * 2 + q) * CHUNK + px * 16) =
+              make_uint4(hlo[q * 4 + 0], hlo[q * 4 + 1], hlo[q * 4 + 2], hlo[q * 4 + 3]);
+        }
+#pragma unroll
+        for (int cq = 0; cq < 4; ++cq) {
+          *reinterpret_cast<uint4*>(S.gw + (hf * 4 + cq) * CHUNK + px * 16) =
+              make_uint4(ghi[cq][0], ghi[cq][1], ghi[cq][2], ghi[cq][3]);
+          *reinterpret_cast<uint4*>(S.gw + (8 + hf * 4 + cq) * CHUNK + px * 16) =
+              make_uint4(glo[cq][0], glo[cq][1], glo[cq][2], glo[cq][3]);
+        }
+        tc::fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) tc::mbar_arrive(&S.ops_full);
         // ---- consume the previous tap's D1 while this tap's MMAs run
         if (have_prev) consume_d1(prev_g, prev_mask, prev_rel);
         have_prev = true;
@@ -305,36 +338,37 @@ meta_ws_params_kernel(const __grid_constant__ CUtensorMap tm_go, const __grid_co
     const uint32_t g_total = g;
 
     // ---- CTA result: gW0/gb0 from registers (cross-thread sum through smem), gW1/gb1 from TMEM D2
-    tma::named_bar_sync(BAR_BLD, 128);                 // all builders finished with go / drow tiles
+    tma::named_bar_sync(BAR_BLD, NBUILD);              // all builders finished with go / drow tiles
     float* red = reinterpret_cast<float*>(S.go);       // 128 x 128 floats = 64 KB = the two go stages
 #pragma unroll
-    for (int j = 0; j < HID; ++j)
+    for (int j = 0; j < HJ; ++j)
 #pragma unroll
-      for (int d = 0; d < 4; ++d) red[(j * 4 + d) * 128 + px] = acc0[j][d];
-    tma::named_bar_sync(BAR_BLD, 128);
+      for (int d = 0; d < 4; ++d) red[((hf * HJ + j) * 4 + d) * 128 + px] = acc0[j][d];
+    tma::named_bar_sync(BAR_BLD, NBUILD);
     float* prow = partial + (int64_t)blockIdx.x * NOUT;
-    {
+    if (bt < 128) {
       float s = 0.f;
       for (int i = 0; i < 128; ++i) s += red[bt * 128 + ((i + bt) & 127)];
       prow[C * HID + C + bt] = s;  // (j,d) -> j*4+d, as the reduce kernel expects
     }
-    tma::named_bar_sync(BAR_BLD, 128);
-    if (g_total > 0) {
-      tc::mbar_wait(&S.ops_free, (g_total - 1) & 1);   // last G2 complete
-      __syncwarp();
-      tc::tc_fence_after();
-      float v[32], u[32], wv[16];
-      tc::tmem_ld_x32(tmem_base + lane_sel + D2_COL, v);        // x h_hi
-      tc::tmem_ld_x32(tmem_base + lane_sel + D2_COL + 32, u);   // x h_lo
-      tc::tmem_ld_x16(tmem_base + lane_sel + D2_COL + 64, wv);  // x [1, 0...]
-      float* stage = red;  // [128 rows][33]
+    tma::named_bar_sync(BAR_BLD, NBUILD);
+    if (hf == 0) {  // warps 2-5 cover the 128 TMEM lanes once
+      if (g_total > 0) {
+        tc::mbar_wait(&S.ops_free, (g_total - 1) & 1);   // last G2 complete
+        __syncwarp();
+        tc::tc_fence_after();
+        float v[32], u[32], wv[16];
+        tc::tmem_ld_x32(tmem_base + lane_sel + D2_COL, v);        // x h_hi
+        tc::tmem_ld_x32(tmem_base + lane_sel + D2_COL + 32, u);   // x h_lo
+        tc::tmem_ld_x16(tmem_base + lane_sel + D2_COL + 64, wv);  // x [1, 0...]
 #pragma unroll
-      for (int j = 0; j < 32; ++j) stage[px * 33 + j] = v[j] + u[j];
-      stage[px * 33 + 32] = wv[0];
-    } else {
-      for (int j = 0; j < 33; ++j) red[px * 33 + j] = 0.f;
+        for (int j = 0; j < 32; ++j) red[px * 33 + j] = v[j] + u[j];
+        red[px * 33 + 32] = wv[0];
+      } else {
+        for (int j = 0; j < 33; ++j) red[px * 33 + j] = 0.f;
+      }
     }
-    tma::named_bar_sync(BAR_BLD, 128);
+    tma::named_bar_sync(BAR_BLD, NBUILD);
     if (bt < C) {
       const float* a = red + bt * 33;
       const float* bb = red + (bt + C) * 33;   // gw_lo rows
