@@ -23,6 +23,16 @@ for _ in range(reps): step()
 b.record(); torch.cuda.synchronize()
 ms = a.elapsed_time(b) / reps
 flops = 1.114e12 * B
-print(json.dumps({"workload": "DLA backbone + Meta-Kernel + RPN head forward, bf16, B=%d, 64x2656" % B, "ms": ms,
+eager_ms = ms
+# the same forward captured once in a CUDA graph (static buffers: the activation pool) and replayed
+g = torch.cuda.CUDAGraph()
+with torch.cuda.graph(g):
+    out = step()
+g.replay(); torch.cuda.synchronize()
+a.record()
+for _ in range(reps): g.replay()
+b.record(); torch.cuda.synchronize()
+ms = a.elapsed_time(b) / reps
+print(json.dumps({"eager_ms": eager_ms, "timing": "CUDA graph replay of the whole forward", "workload": "DLA backbone + Meta-Kernel + RPN head forward, bf16, B=%d, 64x2656" % B, "ms": ms,
                   "frames_per_s": B / ms * 1e3, "TFLOPs_algorithmic": flops / ms / 1e9,
                   "frac_of_bf16_peak_1710": flops / ms / 1e9 / 1710.1, "rd_kernel_launches_per_step": (_lib.launch_count() - l0) / reps}))

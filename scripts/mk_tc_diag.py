@@ -14,13 +14,19 @@ gd = torch.empty_like(data)
 L = _lib.lib()
 P, S = ops._p, ops._stream
 def timeit(fn, reps=10):
+    """Device time per call: `reps` launches captured in ONE CUDA graph (no Python/ctypes launch gaps),
+    replayed 3x, timed with CUDA events on the replay stream."""
     for _ in range(3): fn()
     torch.cuda.synchronize()
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        for _ in range(reps): fn()
+    g.replay(); torch.cuda.synchronize()
     a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     a.record()
-    for _ in range(reps): fn()
+    for _ in range(3): g.replay()
     b.record(); torch.cuda.synchronize()
-    return a.elapsed_time(b) / reps
+    return a.elapsed_time(b) / (3 * reps)
 res = {}
 px = B * H * W
 for impl in (1, 2, 3):

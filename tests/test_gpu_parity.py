@@ -426,6 +426,11 @@ def test_dla_backbone_and_head_forward(ops):
         report(test="dla_backbone", level=lvl, shape=list(wf.shape), rel_err=e)
         assert e < 3e-2, (lvl, e)   # bf16 activations through ~45 layers
     cls, reg = dla.RangeRpnHead(P).get_fpn_output(feats)
+    # the CUDA-graph replay of the same forward gives the same numbers
+    gf = dla.GraphedForward(P, B, H, W)
+    gcls, greg = gf(data, coord)
+    torch.cuda.synchronize()
+    assert all(torch.equal(a, b) for a, b in zip(gcls, cls)) and all(torch.equal(a, b) for a, b in zip(greg, reg))
     for lvl in range(3):
         for name, gq, wq in (("cls", cls[lvl], want_cls[lvl]), ("reg", reg[lvl], want_reg[lvl])):
             assert gq.shape == wq.shape
