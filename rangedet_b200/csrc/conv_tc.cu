@@ -48,6 +48,11 @@ struct Load {
   uint8_t off[MAX_USES];    // strip mode: first pixel row of the loaded strip this use starts at (dx)
 };
 
+struct SLoad {  // shared-memory form of Load: the per-use bytes packed into words
+  uint32_t nuse, acc, tap, off;
+  int dy, dx;
+};
+
 struct Params {
   int N, H, W_out_tiles;    // W_out_tiles: GEMM-row extent along W (output cols for conv, input cols for deconv)
   int Cin, Cout;
@@ -60,9 +65,14 @@ struct Params {
   int ring_off, w_off, o_off, misc_off;
   int slot_bytes, a_bytes, use_base_offset;  // ring slot size, bytes of one activation load, descriptor variant
   int64_t y_row, y_img;     // element strides of the haloed output (deconv / residual addressing)
+  long long* prof;          // diagnostic builds only (RD_CONV_PROF=1), else null
   Load loads[MAX_LOADS];
 };
 
+// PROF: diagnostic build (RD_CONV_PROF=1) that accumulates clock64() cycles per role into P.prof
+// [block][16]: 0 producer total, 1 producer wait(empty); 4 MMA total, 5 wait(full), 6 wait(t_empty);
+// 8 epilogue total, 9 wait(t_full), 10 wait(store read)+barrier, 11 TMEM->smem body.
+template <bool PROF>
 __global__ void __launch_bounds__(NTHREADS, 1)
 conv_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_w,
             const __grid_constant__ CUtensorMap tm_y, const float* __restrict__ scale,
@@ -71,6 +81,9 @@ conv_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CU
   extern __shared__ unsigned char smem_raw[];
   unsigned char* base = smem_raw + ((1024u - (tc::smem_u32(smem_raw) & 1023u)) & 1023u);
   const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+  auto tick = [&]() -> long long { return PROF ? clock64() : 0ll; };
+  long long pc0 = 0, pc1 = 0, pc2 = 0, pc3 = 0;
+  const long long t_begin = tick();
   const int kh = P.Cin / KC, nh = P.Cout / KC;
   const int b_tile = P.Cout * KC * 2;
   unsigned char* ring = base + P.ring_off;
@@ -84,6 +97,20 @@ conv_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CU
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(w_full + 1);
   float* s_scale = reinterpret_cast<float*>(tmem_slot + 2);
   float* s_shift = s_scale + 128;
+  __shared__ SLoad s_loads[MAX_LOADS];  // tap program, packed (dynamic indexing of kernel parameters is slow)
+  if (t < P.nloads) {
+    SLoad L;
+    L.nuse = P.loads[t].nuse;
+    L.acc = L.tap = L.off = 0;
+    for (int u = 0; u < MAX_USES; ++u) {
+      L.acc |= (uint32_t)P.loads[t].acc[u] << (8 * u);
+      L.tap |= (uint32_t)P.loads[t].tap[u] << (8 * u);
+      L.off |= (uint32_t)P.loads[t].off[u] << (8 * u);
+    }
+    L.dy = P.loads[t].dy;
+    L.dx = P.loads[t].dx;
+    s_loads[t] = L;
+  }
 
   if (t == 0) {
     for (int i = 0; i < P.nstages; ++i) { tc::mbar_init(&full[i], 1); tc::mbar_init(&empty[i], 1); }
@@ -117,79 +144,98 @@ conv_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CU
         for (int tap = 0; tap < P.ntaps; ++tap)
           for (int q = 0; q < kh; ++q) tma::load_3d(sW + (tap * kh + q) * b_tile, &tm_w, w_full, q * KC, 0, tap);
       }
-      uint32_t g = 0;
+      uint32_t s = 0, ph = 1;  // next ring stage and the parity to wait on its `empty` barrier
+      const uint32_t nstages = (uint32_t)P.nstages;
+      const int nloads = P.nloads, resident = P.b_resident;
       for (int tile = blockIdx.x; tile < P.ntiles; tile += gridDim.x) {
         const int wt = tile % P.tiles_w, h = (tile / P.tiles_w) % P.H, n = tile / (P.tiles_w * P.H);
-        const int w0 = wt * TM;
+        const int wx = wt * TM * P.in_stride_w;
         for (int q = 0; q < kh; ++q)
-          for (int l = 0; l < P.nloads; ++l) {
-            const Load& L = P.loads[l];
-            {
-              const uint32_t s = g % P.nstages, ph = (g / P.nstages) & 1;
-              tc::mbar_wait(&empty[s], ph ^ 1);
-              tc::mbar_arrive_expect_tx(&full[s], (uint32_t)P.a_bytes);
-              tma::load_4d(ring + s * P.slot_bytes, &tm_x, &full[s], q * KC, w0 * P.in_stride_w + L.dx, h + L.dy, n);
-              ++g;
-            }
-            if (!P.b_resident)
-              for (int u = 0; u < L.nuse; ++u, ++g) {
-                const uint32_t s = g % P.nstages, ph = (g / P.nstages) & 1;
-                tc::mbar_wait(&empty[s], ph ^ 1);
+          for (int l = 0; l < nloads; ++l) {
+            const SLoad L = s_loads[l];
+            const long long ta = tick();
+            tc::mbar_wait(&empty[s], ph);
+            pc1 += tick() - ta;
+            tc::mbar_arrive_expect_tx(&full[s], (uint32_t)P.a_bytes);
+            tma::load_4d(ring + s * P.slot_bytes, &tm_x, &full[s], q * KC, wx + L.dx, h + L.dy, n);
+            if (++s == nstages) { s = 0; ph ^= 1; }
+            if (!resident)
+              for (int u = 0; u < (int)L.nuse; ++u) {
+                tc::mbar_wait(&empty[s], ph);
                 tc::mbar_arrive_expect_tx(&full[s], (uint32_t)b_tile);
-                tma::load_3d(ring + s * P.slot_bytes, &tm_w, &full[s], q * KC, 0, L.tap[u]);
+                tma::load_3d(ring + s * P.slot_bytes, &tm_w, &full[s], q * KC, 0, (int)((L.tap >> (8 * u)) & 0xff));
+                if (++s == nstages) { s = 0; ph ^= 1; }
               }
           }
       }
+      if (PROF) { P.prof[blockIdx.x * 16 + 0] = tick() - t_begin; P.prof[blockIdx.x * 16 + 1] = pc1; }
     }
     __syncwarp();
   } else if (warp == 1) {
     // ===== MMA issuer =====
+    // One thread issues everything, so this loop is kept lean: descriptors differ only in their
+    // 14-bit start-address field (one add per MMA), the tap program is read from shared memory.
     if (lane == 0) {
       const uint32_t idesc = tc::make_idesc_bf16(TM, P.Cout);
-      if (P.b_resident) tc::mbar_wait(w_full, 0);
-      uint32_t g = 0, it = 0;
+      const uint64_t desc_hi = tc::make_smem_desc(0, 0, 1024, tc::LAYOUT_SW128);  // everything but the address
+      const uint32_t ring_lo = tc::smem_u32(ring) >> 4, w_lo = tc::smem_u32(sW) >> 4;
+      const uint32_t slot_lo = (uint32_t)P.slot_bytes >> 4, btile_lo = (uint32_t)b_tile >> 4;
+      const uint32_t nstages = (uint32_t)P.nstages;
+      const int nloads = P.nloads, resident = P.b_resident;
+      if (resident) tc::mbar_wait(w_full, 0);
+      uint32_t s = 0, ph = 0;  // ring position of the next unit (stage index, phase parity)
+      uint32_t it = 0;
       for (int tile = blockIdx.x; tile < P.ntiles; tile += gridDim.x, ++it) {
         const uint32_t buf = P.acc_bufs == 2 ? (it & 1) : 0;
         const uint32_t use_n = P.acc_bufs == 2 ? (it >> 1) : it;  // how many times this buffer was used before
+        const long long te = tick();
         tc::mbar_wait(&t_empty[buf], (use_n & 1) ^ 1);
+        pc2 += tick() - te;
         tc::tc_fence_after();
+        const uint32_t d_base = tmem_base + buf * buf_stride;
         uint32_t started = 0;  // accumulators that already hold a partial sum for this tile
         for (int q = 0; q < kh; ++q)
-          for (int l = 0; l < P.nloads; ++l) {
-            const Load& L = P.loads[l];
-            const uint32_t sa = g % P.nstages, pha = (g / P.nstages) & 1;
-            tc::mbar_wait(&full[sa], pha);
-            ++g;
-            const uint32_t a_addr = tc::smem_u32(ring + sa * P.slot_bytes);
-            for (int u = 0; u < L.nuse; ++u) {
-              uint32_t b_addr, sb = 0;
-              if (P.b_resident) {
-                b_addr = tc::smem_u32(sW + (L.tap[u] * kh + q) * b_tile);
+          for (int l = 0; l < nloads; ++l) {
+            const SLoad L = s_loads[l];
+            const uint32_t sa = s;
+            const long long tf = tick();
+            tc::mbar_wait(&full[sa], ph);
+            pc1 += tick() - tf;
+            if (++s == nstages) { s = 0; ph ^= 1; }
+            const uint32_t a_lo = ring_lo + sa * slot_lo;
+            for (int u = 0; u < (int)L.nuse; ++u) {
+              const uint32_t acc = (L.acc >> (8 * u)) & 0xff, tap = (L.tap >> (8 * u)) & 0xff, off = (L.off >> (8 * u)) & 0xff;
+              uint32_t b_lo, sb = 0;
+              if (resident) {
+                b_lo = w_lo + (tap * kh + q) * btile_lo;
               } else {
-                sb = g % P.nstages;
-                tc::mbar_wait(&full[sb], (g / P.nstages) & 1);
-                ++g;
-                b_addr = tc::smem_u32(ring + sb * P.slot_bytes);
+                sb = s;
+                tc::mbar_wait(&full[sb], ph);
+                if (++s == nstages) { s = 0; ph ^= 1; }
+                b_lo = ring_lo + sb * slot_lo;
               }
               tc::tc_fence_after();
-              const uint32_t d_tmem = tmem_base + buf * buf_stride + L.acc[u] * acc_stride;
-              const uint32_t bit = 1u << L.acc[u];
-#pragma unroll
-              for (int ks = 0; ks < KC / 16; ++ks) {
-                // 128B-swizzled K-major tiles: 8-row groups 1024 B apart, K advances 32 B inside the atom
-                // strip mode: the operand starts L.off[u] pixel rows (128 B each) into the loaded strip;
-                // TMA and tcgen05 both swizzle on absolute address bits, so the shifted view is consistent
-                uint64_t ad = tc::make_smem_desc(a_addr + L.off[u] * 128 + ks * 32, 0, 1024, tc::LAYOUT_SW128);
-                if (P.use_base_offset) ad |= (uint64_t)(L.off[u] & 7) << 49;
-                const uint64_t bd = tc::make_smem_desc(b_addr + ks * 32, 0, 1024, tc::LAYOUT_SW128);
-                tc::mma_bf16_ss(d_tmem, ad, bd, idesc, ((started & bit) || ks > 0) ? 1u : 0u);
-              }
+              const uint32_t d_tmem = d_base + acc * acc_stride;
+              const uint32_t bit = 1u << acc;
+              // 128B-swizzled K-major tiles: K advances 32 B (2 address units) inside the atom; a strip-mode
+              // view starts `off` pixel rows (8 units each) into the loaded strip
+              const uint64_t ad0 = desc_hi | (uint64_t)((a_lo + off * 8) & 0x3FFF);
+              const uint64_t bd0 = desc_hi | (uint64_t)(b_lo & 0x3FFF);
+              tc::mma_bf16_ss(d_tmem, ad0, bd0, idesc, (started & bit) ? 1u : 0u);
+              tc::mma_bf16_ss(d_tmem, ad0 + 2, bd0 + 2, idesc, 1u);
+              tc::mma_bf16_ss(d_tmem, ad0 + 4, bd0 + 4, idesc, 1u);
+              tc::mma_bf16_ss(d_tmem, ad0 + 6, bd0 + 6, idesc, 1u);
               started |= bit;
-              if (!P.b_resident) tc::umma_commit(&empty[sb]);
+              if (!resident) tc::umma_commit(&empty[sb]);
             }
             tc::umma_commit(&empty[sa]);
           }
         tc::umma_commit(&t_full[buf]);
+      }
+      if (PROF) {
+        P.prof[blockIdx.x * 16 + 4] = tick() - t_begin;
+        P.prof[blockIdx.x * 16 + 5] = pc1;
+        P.prof[blockIdx.x * 16 + 6] = pc2;
       }
     }
     __syncwarp();
@@ -205,14 +251,19 @@ conv_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CU
       const int w0 = wt * TM;
       const uint32_t buf = P.acc_bufs == 2 ? (it & 1) : 0;
       const uint32_t use_n = P.acc_bufs == 2 ? (it >> 1) : it;
+      const long long e0 = tick();
       tc::mbar_wait(&t_full[buf], use_n & 1);
       __syncwarp();
       tc::tc_fence_after();
+      const long long e1 = tick();
       const bool in_img = (w0 + px) < P.W_out_tiles;
       if (!P.deconv_s) {
         if (leader) tma::store_wait_read<0>();  // previous tile's stores have read the staging buffer
         tma::named_bar_sync(BAR_EPI, 128);
       }
+      const long long e2 = tick();
+      pc1 += e1 - e0;
+      pc2 += e2 - e1;
       const int nphase = P.deconv_s ? P.deconv_s : 1;
       for (int ph = 0; ph < nphase; ++ph) {
         // output pixel of this thread for this phase (interior coordinates)
@@ -260,6 +311,7 @@ conv_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CU
       tc::tc_fence_before();
       if (!P.deconv_s) tc::fence_proxy_async_smem();
       __syncwarp();
+      pc3 += tick() - e2;
       if (lane == 0) tc::mbar_arrive(&t_empty[buf]);
       if (!P.deconv_s) {
         tma::named_bar_sync(BAR_EPI, 128);
@@ -270,6 +322,12 @@ conv_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CU
       }
     }
     if (!P.deconv_s && leader) tma::store_wait_all<0>();
+    if (PROF && leader) {
+      P.prof[blockIdx.x * 16 + 8] = tick() - t_begin;
+      P.prof[blockIdx.x * 16 + 9] = pc1;
+      P.prof[blockIdx.x * 16 + 10] = pc2;
+      P.prof[blockIdx.x * 16 + 11] = pc3;
+    }
   }
   tc::tc_fence_before();
   __syncthreads();
@@ -421,12 +479,35 @@ static int run(int mode, const void* x_pad, const void* w_packed, const float* s
   RD_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
   static size_t smem_set = 0;
   if (smem > smem_set) {
-    RD_CUDA(cudaFuncSetAttribute(conv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    RD_CUDA(cudaFuncSetAttribute(conv_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    RD_CUDA(cudaFuncSetAttribute(conv_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     smem_set = smem;
   }
   const int grid = P.ntiles < sms ? P.ntiles : sms;
-  conv_kernel<<<grid, NTHREADS, smem, stream>>>(tm_x, tm_w, tm_y, scale, shift, res,
-                                                reinterpret_cast<__nv_bfloat16*>(y_int), P);
+  static const bool prof = [] { const char* e = getenv("RD_CONV_PROF"); return e && e[0] == '1'; }();
+  if (prof) {  // diagnostic: per-role cycle counters, synchronous, printed to stderr
+    static long long* d_prof = nullptr;
+    if (!d_prof) RD_CUDA(cudaMalloc(&d_prof, 1024 * 16 * sizeof(long long)));
+    RD_CUDA(cudaMemsetAsync(d_prof, 0, 1024 * 16 * sizeof(long long), stream));
+    P.prof = d_prof;
+    conv_kernel<true><<<grid, NTHREADS, smem, stream>>>(tm_x, tm_w, tm_y, scale, shift, res,
+                                                        reinterpret_cast<__nv_bfloat16*>(y_int), P);
+    RD_CUDA(cudaStreamSynchronize(stream));
+    static long long h[1024 * 16];
+    RD_CUDA(cudaMemcpy(h, d_prof, sizeof(long long) * 16 * grid, cudaMemcpyDeviceToHost));
+    double m[16] = {0};
+    for (int b = 0; b < grid; ++b)
+      for (int k = 0; k < 16; ++k) m[k] += (double)h[b * 16 + k] / grid;
+    const double tiles = (double)P.ntiles / grid;
+    fprintf(stderr,
+            "[rd_conv prof] Cin=%d Cout=%d tiles/cta=%.1f nloads=%d nstages=%d | per tile: producer %.0f (wait empty %.0f) | "
+            "mma %.0f (wait full %.0f, wait t_empty %.0f) | epi %.0f (wait t_full %.0f, wait store+bar %.0f, body %.0f)\n",
+            P.Cin, P.Cout, tiles, P.nloads, P.nstages, m[0] / tiles, m[1] / tiles, m[4] / tiles, m[5] / tiles,
+            m[6] / tiles, m[8] / tiles, m[9] / tiles, m[10] / tiles, m[11] / tiles);
+  } else {
+    conv_kernel<false><<<grid, NTHREADS, smem, stream>>>(tm_x, tm_w, tm_y, scale, shift, res,
+                                                         reinterpret_cast<__nv_bfloat16*>(y_int), P);
+  }
   rd::count_launch();
   return rd::check_launch("rd_conv");
 }
