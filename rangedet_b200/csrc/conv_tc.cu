@@ -39,6 +39,7 @@ constexpr int SLOT = TM * KC * 2;     // 16 KB ring slot (A tile, or a 128-row w
 constexpr int NTHREADS = 192;
 constexpr int BAR_EPI = 1;
 constexpr int MAX_LOADS = 9, MAX_USES = 4, MAX_STAGES = 12;
+constexpr uint32_t USE_NEWLOAD = 1, USE_LASTOFLOAD = 2, USE_FIRST = 4;  // flags of a per-use record
 
 struct Load {
   int8_t dy, dx;            // offsets in the haloed input frame (already >= 0)
@@ -58,7 +59,7 @@ struct Params {
   int Cin, Cout;
   int tiles_w, ntiles;
   int in_stride_w;          // input pixels advanced per GEMM row (1, or 2 for W-strided conv)
-  int nacc, nloads, ntaps;
+  int nacc, nloads, ntaps, nuses_total;
   int relu, has_residual, res_after_relu;
   int deconv_s;             // 0: convolution (TMA-store epilogue); S>0: transposed conv, phase count S
   int b_resident, nstages, acc_bufs;
@@ -110,6 +111,23 @@ conv_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CU
     L.dy = P.loads[t].dy;
     L.dx = P.loads[t].dx;
     s_loads[t] = L;
+  }
+  __shared__ uint4 s_uses[MAX_LOADS * MAX_USES];  // flat per-use records for the MMA warp (one K-half)
+  if (t == 0) {
+    int i = 0;
+    uint32_t started = 0;
+    for (int l = 0; l < P.nloads; ++l)
+      for (int u = 0; u < P.loads[l].nuse; ++u, ++i) {
+        const uint32_t acc = P.loads[l].acc[u], tap = P.loads[l].tap[u], off = P.loads[l].off[u];
+        uint4 r;
+        r.x = off * 8;                                                        // pixel rows are 128 B = 8 units
+        r.y = (tc::smem_u32(base + P.w_off) >> 4) + tap * (uint32_t)(P.Cin / KC) * (uint32_t)((P.Cout * KC * 2) >> 4);
+        r.z = acc * (uint32_t)P.Cout;
+        r.w = (u == 0 ? USE_NEWLOAD : 0u) | (u == P.loads[l].nuse - 1 ? USE_LASTOFLOAD : 0u) |
+              ((started >> acc) & 1u ? 0u : USE_FIRST);
+        started |= 1u << acc;
+        s_uses[i] = r;
+      }
   }
 
   if (t == 0) {
@@ -173,15 +191,19 @@ conv_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CU
     __syncwarp();
   } else if (warp == 1) {
     // ===== MMA issuer =====
-    // One thread issues everything, so this loop is kept lean: descriptors differ only in their
-    // 14-bit start-address field (one add per MMA), the tap program is read from shared memory.
-    if (lane == 0) {
+    // The whole warp runs this loop CONVERGED and one elected lane issues.  Measured (scripts/mma_bench*.cu):
+    // tcgen05.mma itself sustains its floor (48 cycles at N=64 -- shared-memory operand reads --, 64 at
+    // N=128), but a loop that rebuilds descriptors, unpacks the tap program and polls per MMA spends
+    // 130-240 cycles of the issuing thread per MMA.  So: one 16-byte record per use, read as a broadcast,
+    // descriptors that differ only in their start-address field, four back-to-back MMAs per use.
+    {
       const uint32_t idesc = tc::make_idesc_bf16(TM, P.Cout);
       const uint64_t desc_hi = tc::make_smem_desc(0, 0, 1024, tc::LAYOUT_SW128);  // everything but the address
-      const uint32_t ring_lo = tc::smem_u32(ring) >> 4, w_lo = tc::smem_u32(sW) >> 4;
+      const uint32_t ring_lo = tc::smem_u32(ring) >> 4;
       const uint32_t slot_lo = (uint32_t)P.slot_bytes >> 4, btile_lo = (uint32_t)b_tile >> 4;
       const uint32_t nstages = (uint32_t)P.nstages;
-      const int nloads = P.nloads, resident = P.b_resident;
+      const int nuses = P.nuses_total, resident = P.b_resident;
+      const bool leader = tc::elect_one();
       if (resident) tc::mbar_wait(w_full, 0);
       uint32_t s = 0, ph = 0;  // ring position of the next unit (stage index, phase parity)
       uint32_t it = 0;
@@ -191,54 +213,53 @@ conv_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CU
         const long long te = tick();
         tc::mbar_wait(&t_empty[buf], (use_n & 1) ^ 1);
         pc2 += tick() - te;
-        tc::tc_fence_after();
         const uint32_t d_base = tmem_base + buf * buf_stride;
-        uint32_t started = 0;  // accumulators that already hold a partial sum for this tile
-        for (int q = 0; q < kh; ++q)
-          for (int l = 0; l < nloads; ++l) {
-            const SLoad L = s_loads[l];
-            const uint32_t sa = s;
-            const long long tf = tick();
-            tc::mbar_wait(&full[sa], ph);
-            pc1 += tick() - tf;
-            if (++s == nstages) { s = 0; ph ^= 1; }
-            const uint32_t a_lo = ring_lo + sa * slot_lo;
-            for (int u = 0; u < (int)L.nuse; ++u) {
-              const uint32_t acc = (L.acc >> (8 * u)) & 0xff, tap = (L.tap >> (8 * u)) & 0xff, off = (L.off >> (8 * u)) & 0xff;
-              uint32_t b_lo, sb = 0;
-              if (resident) {
-                b_lo = w_lo + (tap * kh + q) * btile_lo;
-              } else {
-                sb = s;
-                tc::mbar_wait(&full[sb], ph);
-                if (++s == nstages) { s = 0; ph ^= 1; }
-                b_lo = ring_lo + sb * slot_lo;
-              }
-              tc::tc_fence_after();
-              const uint32_t d_tmem = d_base + acc * acc_stride;
-              const uint32_t bit = 1u << acc;
-              // 128B-swizzled K-major tiles: K advances 32 B (2 address units) inside the atom; a strip-mode
-              // view starts `off` pixel rows (8 units each) into the loaded strip
-              const uint64_t ad0 = desc_hi | (uint64_t)((a_lo + off * 8) & 0x3FFF);
-              const uint64_t bd0 = desc_hi | (uint64_t)(b_lo & 0x3FFF);
-              tc::mma_bf16_ss(d_tmem, ad0, bd0, idesc, (started & bit) ? 1u : 0u);
-              tc::mma_bf16_ss(d_tmem, ad0 + 2, bd0 + 2, idesc, 1u);
-              tc::mma_bf16_ss(d_tmem, ad0 + 4, bd0 + 4, idesc, 1u);
-              tc::mma_bf16_ss(d_tmem, ad0 + 6, bd0 + 6, idesc, 1u);
-              started |= bit;
-              if (!resident) tc::umma_commit(&empty[sb]);
+        for (int q = 0; q < kh; ++q) {
+          uint32_t a_lo = 0, sa = 0;
+          const uint32_t bq = (uint32_t)q * btile_lo;
+#pragma unroll 1
+          for (int i = 0; i < nuses; ++i) {
+            const uint4 r = s_uses[i];  // x: A offset (16-B units), y: resident B address, z: TMEM column, w: flags
+            if (r.w & USE_NEWLOAD) {
+              sa = s;
+              const long long tf = tick();
+              tc::mbar_wait(&full[s], ph);
+              pc1 += tick() - tf;
+              a_lo = ring_lo + s * slot_lo;
+              if (++s == nstages) { s = 0; ph ^= 1; }
             }
-            tc::umma_commit(&empty[sa]);
+            uint32_t b_lo = r.y + bq, sb = 0;
+            if (!resident) {
+              sb = s;
+              tc::mbar_wait(&full[s], ph);
+              b_lo = ring_lo + s * slot_lo;
+              if (++s == nstages) { s = 0; ph ^= 1; }
+            }
+            tc::tc_fence_after();
+            if (leader) {
+              // 128B-swizzled K-major tiles: K advances 32 B (2 address units) inside the swizzle atom
+              const uint64_t ad = desc_hi | (uint64_t)((a_lo + r.x) & 0x3FFF);
+              const uint64_t bd = desc_hi | (uint64_t)(b_lo & 0x3FFF);
+              const uint32_t d_tmem = d_base + r.z;
+              tc::mma_bf16_ss(d_tmem, ad, bd, idesc, ((r.w & USE_FIRST) && q == 0) ? 0u : 1u);
+              tc::mma_bf16_ss_acc(d_tmem, ad + 2, bd + 2, idesc);
+              tc::mma_bf16_ss_acc(d_tmem, ad + 4, bd + 4, idesc);
+              tc::mma_bf16_ss_acc(d_tmem, ad + 6, bd + 6, idesc);
+              if (!resident) tc::umma_commit(&empty[sb]);
+              if (r.w & USE_LASTOFLOAD) tc::umma_commit(&empty[sa]);
+            }
+            __syncwarp();
           }
-        tc::umma_commit(&t_full[buf]);
+        }
+        if (leader) tc::umma_commit(&t_full[buf]);
+        __syncwarp();
       }
-      if (PROF) {
+      if (PROF && lane == 0) {
         P.prof[blockIdx.x * 16 + 4] = tick() - t_begin;
         P.prof[blockIdx.x * 16 + 5] = pc1;
         P.prof[blockIdx.x * 16 + 6] = pc2;
       }
     }
-    __syncwarp();
   } else {
     // ===== epilogue: thread = GEMM row = TMEM lane =====
     const int q4 = warp & 3;
@@ -363,10 +384,11 @@ static int run(int mode, const void* x_pad, const void* w_packed, const float* s
     P.deconv_s = 0;
     P.ntaps = ksize * ksize;
     const char* es = getenv("RD_CONV_STRIP");
-    // Strip mode is correct but measured SLOWER than nine aligned loads (0.160 vs 0.126 ms for 64->64
-    // @ 4x64x2656; 0.382 vs 0.237 ms for 128->128): views that straddle 1024-B swizzle atoms cost more
-    // in the MMA's shared-memory reads than the saved L2 traffic.  Opt-in only (RD_CONV_STRIP=1).
-    strip = (ksize == 3 && stride_w == 1 && es && es[0] == '1');
+    // Strip mode (default): one 130-pixel row strip per dy serves the three dx taps as row-shifted views,
+    // 3 activation loads per K-half instead of 9.  Measured 0.086 vs 0.095 ms (64->64 @ 4x64x2656) and
+    // 0.202 vs 0.258 ms (128->128) once the MMA issue loop stopped being the bound.  RD_CONV_STRIP=0
+    // selects nine aligned loads (diagnostic).
+    strip = (ksize == 3 && stride_w == 1 && !(es && es[0] == '0'));
     if (strip) {
       // one 130-pixel row strip per dy serves the three dx taps as row-shifted views of the same tile
       P.nloads = 3;
@@ -418,6 +440,8 @@ static int run(int mode, const void* x_pad, const void* w_packed, const float* s
     P.nloads = nl;
   }
   P.tiles_w = (P.W_out_tiles + TM - 1) / TM;
+  P.nuses_total = 0;
+  for (int l = 0; l < P.nloads; ++l) P.nuses_total += P.loads[l].nuse;
   const int64_t ntiles = (int64_t)N * H * P.tiles_w;
   RD_REQUIRE(ntiles <= 0x7fffffffLL, "rd_conv: too many tiles");
   P.ntiles = (int)ntiles;

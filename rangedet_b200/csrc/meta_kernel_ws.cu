@@ -67,7 +67,15 @@ __global__ void __launch_bounds__(NTHREADS, 1)
 meta_ws_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant__ CUtensorMap tm_out,
                const float* __restrict__ coord, const float* __restrict__ w0, const float* __restrict__ b0,
                const float* __restrict__ w1, const float* __restrict__ b1, const float* __restrict__ ep_scale,
-               const float* __restrict__ ep_shift, int ep_relu, int B, int H, int W, int tiles_w, int ntiles) {
+               const float* __restrict__ ep_shift, int ep_relu, int B, int H, int W, int tiles_w, int ntiles,
+               long long* __restrict__ prof) {
+  // prof (diagnostic, RD_MK_PROF=1, else null): per-CTA clock64() sums, [block][16]:
+  // 0 producer total, 1 wait d_empty | 2 builders total, 3 wait a_empty, 4 coordinate staging |
+  // 5 MMA total, 6 wait a_full, 7 wait t_empty | 8 epilogue total, 9 wait t_full, 10 wait d_full,
+  // 11 wait store-read + barrier, 12 body, 13 second barrier + store issue
+  auto tick = [&]() -> long long { return prof ? clock64() : 0ll; };
+  long long pa = 0, pb = 0, pc = 0, pd = 0, pe = 0;
+  const long long t_begin = tick();
   extern __shared__ unsigned char smem_raw[];
   // TMA destinations need 128-byte (we use 1024) alignment; the dynamic window is only guaranteed 16
   Smem& S = *reinterpret_cast<Smem*>(smem_raw + ((1024u - (tc::smem_u32(smem_raw) & 1023u)) & 1023u));
@@ -132,7 +140,9 @@ meta_ws_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant_
         for (int u = 0; u < UNITS; ++u, ++g) {
           const int dy = MODE != 1 ? u - 1 : u / 3 - 1;
           const uint32_t s = g % NS_D, ph = (g / NS_D) & 1;
+          const long long ta = tick();
           tc::mbar_wait(&S.d_empty[s], ph ^ 1);
+          pa += tick() - ta;
           const int hh = h + dy;
           if (hh >= 0 && hh < H) {
             tc::mbar_arrive_expect_tx(&S.d_full[s], IN_BYTES);
@@ -143,42 +153,60 @@ meta_ws_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant_
           }
         }
       }
+      if (prof) { prof[blockIdx.x * 16 + 0] = tick() - t_begin; prof[blockIdx.x * 16 + 1] = pa; }
     }
     __syncwarp();
   } else if (warp == 1) {
     // ===== MMA issuer =====
-    if (lane == 0) {
-      const uint32_t idesc = tc::make_idesc_bf16(128, C);
-      const uint32_t b_base = tc::smem_u32(S.bw), ones_base = tc::smem_u32(S.ones);
-      uint32_t g = 0;
+    // The warp runs converged and one elected lane issues: measured with scripts/mma_bench2.cu, a lean
+    // loop sustains the tensor-core floor (48 cycles per M128 N64 K16 MMA with both operands in shared
+    // memory), while per-MMA descriptor rebuilding under `if (lane == 0)` costs 130+ cycles of the issuing
+    // thread.  Descriptors differ only in their start-address field: one 64-bit add each.
+    // Split-bf16 product x.w ~ xh.wh + xl.wh + xh.wl ; the xl.wl term (2^-16 relative) is dropped.
+    {
+      constexpr uint32_t idesc = tc::make_idesc_bf16(128, C);
+      const uint64_t a_hi = tc::make_smem_desc(0, A_CHUNK, 128, tc::LAYOUT_NONE);
+      const uint64_t b_hi = tc::make_smem_desc(0, B_CHUNK, 128, tc::LAYOUT_NONE);
+      const uint64_t bdesc = b_hi | (uint64_t)(tc::smem_u32(S.bw) >> 4);
+      const uint64_t odesc = a_hi | (uint64_t)(tc::smem_u32(S.ones) >> 4);
+      constexpr uint32_t AC = A_CHUNK >> 4, BC = B_CHUNK >> 4;  // chunk strides in descriptor address units
+      const bool leader = tc::elect_one();
+      uint32_t sa = 0, pha = 0, st = 0, pht = 0;
       for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-        for (int k = 0; k < 9; ++k, ++g) {
-          const uint32_t sa = g % NS_A, pha = (g / NS_A) & 1, st = g % NS_T, pht = (g / NS_T) & 1;
+#pragma unroll 1
+        for (int k = 0; k < 9; ++k) {
+          const long long ta = tick();
           tc::mbar_wait(&S.a_full[sa], pha);
+          const long long tb = tick();
           tc::mbar_wait(&S.t_empty[st], pht ^ 1);
+          pa += tb - ta;
+          pb += tick() - tb;
           tc::tc_fence_after();
-          const uint32_t d_tmem = tmem_base + st * C;
-          const uint32_t ab = tc::smem_u32(S.a[sa]);
-          uint32_t accum = 0;
-#pragma unroll
-          for (int bp = 0; bp < 2; ++bp)
-#pragma unroll
-            for (int ap = 0; ap < 2; ++ap)
-#pragma unroll
-              for (int ks = 0; ks < 2; ++ks) {
-                const uint64_t ad = tc::make_smem_desc(ab + (ap * 4 + ks * 2) * A_CHUNK, A_CHUNK, 128, tc::LAYOUT_NONE);
-                const uint64_t bd = tc::make_smem_desc(b_base + (bp * 4 + ks * 2) * B_CHUNK, B_CHUNK, 128, tc::LAYOUT_NONE);
-                tc::mma_bf16_ss(d_tmem, ad, bd, idesc, accum);
-                accum = 1;
-              }
-          tc::mma_bf16_ss(d_tmem, tc::make_smem_desc(ones_base, A_CHUNK, 128, tc::LAYOUT_NONE),
-                          tc::make_smem_desc(b_base + 8 * B_CHUNK, B_CHUNK, 128, tc::LAYOUT_NONE), idesc, 1u);
-          tc::umma_commit(&S.a_empty[sa]);  // A slot reusable once these MMAs have read it
-          tc::umma_commit(&S.t_full[st]);   // accumulator ready
+          if (leader) {
+            const uint32_t d_tmem = tmem_base + st * C;
+            const uint64_t adesc = a_hi | (uint64_t)(tc::smem_u32(S.a[sa]) >> 4);
+            // (A part, B part): (hi,hi) (lo,hi) (hi,lo); two K=16 slices each; then the bias slice
+            tc::mma_bf16_ss(d_tmem, adesc, bdesc, idesc, 0u);
+            tc::mma_bf16_ss_acc(d_tmem, adesc + 2 * AC, bdesc + 2 * BC, idesc);
+            tc::mma_bf16_ss_acc(d_tmem, adesc + 4 * AC, bdesc, idesc);
+            tc::mma_bf16_ss_acc(d_tmem, adesc + 6 * AC, bdesc + 2 * BC, idesc);
+            tc::mma_bf16_ss_acc(d_tmem, adesc, bdesc + 4 * BC, idesc);
+            tc::mma_bf16_ss_acc(d_tmem, adesc + 2 * AC, bdesc + 6 * BC, idesc);
+            tc::mma_bf16_ss_acc(d_tmem, odesc, bdesc + 8 * BC, idesc);
+            tc::umma_commit(&S.a_empty[sa]);  // A slot reusable once these MMAs have read it
+            tc::umma_commit(&S.t_full[st]);   // accumulator ready
+          }
+          __syncwarp();
+          if (++sa == NS_A) { sa = 0; pha ^= 1; }
+          if (++st == NS_T) { st = 0; pht ^= 1; }
         }
       }
+      if (prof && lane == 0) {
+        prof[blockIdx.x * 16 + 5] = tick() - t_begin;
+        prof[blockIdx.x * 16 + 6] = pa;
+        prof[blockIdx.x * 16 + 7] = pb;
+      }
     }
-    __syncwarp();
   } else if (warp < 6) {
     // ===== hidden-layer producers (128 threads, thread = pixel) =====
     const int ht = t - 64;
@@ -186,6 +214,7 @@ meta_ws_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant_
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
       const int wt = tile % tiles_w, h = (tile / tiles_w) % H, b = tile / (tiles_w * H);
       const int w0px = wt * TW;
+      const long long tc0 = tick();
       tma::named_bar_sync(BAR_HID, 128);  // everyone finished reading the previous coordinate tile
       for (int e = ht; e < 3 * CCH * ROW; e += 128) {
         const int col = e % ROW, d = (e / ROW) % CCH, r = e / (ROW * CCH);
@@ -195,6 +224,7 @@ meta_ws_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant_
         S.cs[(r * CCH + d) * ROW + col] = v;
       }
       tma::named_bar_sync(BAR_HID, 128);
+      pb += tick() - tc0;
       const float c0 = S.cs[(1 * CCH + 0) * ROW + ht + 1];
       const float c1 = S.cs[(1 * CCH + 1) * ROW + ht + 1];
       const float c2 = S.cs[(1 * CCH + 2) * ROW + ht + 1];
@@ -206,7 +236,9 @@ meta_ws_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant_
         float r2 = S.cs[(r * CCH + 2) * ROW + col] - c2;
         if (MODE == 1) { r0 = -r0; r1 = -r1; r2 = -r2; }  // rel seen from the mirrored pixel
         const uint32_t sa = g % NS_A, pha = (g / NS_A) & 1;
+        const long long ta = tick();
         tc::mbar_wait(&S.a_empty[sa], pha ^ 1);
+        pa += tick() - ta;
         unsigned char* abuf = S.a[sa];
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
@@ -234,6 +266,11 @@ meta_ws_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant_
         if (lane == 0) tc::mbar_arrive(&S.a_full[sa]);
       }
     }
+    if (prof && ht == 0) {
+      prof[blockIdx.x * 16 + 2] = tick() - t_begin;
+      prof[blockIdx.x * 16 + 3] = pa;
+      prof[blockIdx.x * 16 + 4] = pb;
+    }
   } else {
     // ===== epilogue (128 threads, thread = TMEM lane = pixel) =====
     const int q4 = warp & 3;                 // TMEM lane quadrant this warp may read
@@ -255,10 +292,15 @@ meta_ws_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant_
         const uint32_t st = g % NS_T, pht = (g / NS_T) & 1;
         const uint32_t gu = MODE != 1 ? g / 3 : g;  // input unit (row box / tap box) this tap reads
         const uint32_t sd = gu % NS_D, phd = (gu / NS_D) & 1;
+        const long long e0 = tick();
         tc::mbar_wait(&S.t_full[st], pht);
+        const long long e1 = tick();
         if (MODE == 1 || dx == -1) tc::mbar_wait(&S.d_full[sd], phd);
         __syncwarp();
         tc::tc_fence_after();
+        const long long e2 = tick();
+        pa += e1 - e0;
+        pb += e2 - e1;
         // pixel read by this thread for this tap, as a column of the input box (or: outside -> 0)
         const int col = w0px + px + dx - bs;
         const bool ok = (h + dy >= 0) && (h + dy < H) && col >= 0;
@@ -310,6 +352,8 @@ meta_ws_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant_
           const uint32_t so = n_store % NS_O;
           if (leader) tma::store_wait_read<NS_O - 1>();  // the store that last used otile[so] has read it
           tma::named_bar_sync(BAR_EPI, 128);
+          const long long e3 = tick();
+          pc += e3 - e2;
           float* ot = S.otile[so];
 #pragma unroll
           for (int half = 0; half < 2; ++half) {
@@ -326,6 +370,8 @@ meta_ws_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant_
           tc::tc_fence_before();
           tc::fence_proxy_async_smem();
           __syncwarp();
+          const long long e4 = tick();
+          pd += e4 - e3;
           if (lane == 0) {
             tc::mbar_arrive(&S.t_empty[st]);
             if (last_use) tc::mbar_arrive(&S.d_empty[sd]);
@@ -335,6 +381,7 @@ meta_ws_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant_
             tma::store_4d(&tm_out, ot, w0px, h, k, b * C);
             tma::store_commit();
           }
+          pe += tick() - e4;
           ++n_store;
         } else {
 #pragma unroll
@@ -372,6 +419,14 @@ meta_ws_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant_
       }
     }
     if (leader) tma::store_wait_all<0>();
+    if (prof && leader) {
+      prof[blockIdx.x * 16 + 8] = tick() - t_begin;
+      prof[blockIdx.x * 16 + 9] = pa;
+      prof[blockIdx.x * 16 + 10] = pb;
+      prof[blockIdx.x * 16 + 11] = pc;
+      prof[blockIdx.x * 16 + 12] = pd;
+      prof[blockIdx.x * 16 + 13] = pe;
+    }
   }
 
   // ---- teardown ------------------------------------------------------------------------------
@@ -422,6 +477,14 @@ inline int launch(int mode, const float* tap_src, void* dst, const float* coord,
   RD_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
   const size_t smem = sizeof(Smem) + 1024;
   const int64_t grid = ntiles < sms ? ntiles : sms;
+  static const bool want_prof = [] { const char* e = getenv("RD_MK_PROF"); return e && e[0] == '1'; }();
+  long long* d_prof = nullptr;
+  if (want_prof) {
+    static long long* buf = nullptr;
+    if (!buf) RD_CUDA(cudaMalloc(&buf, 1024 * 16 * sizeof(long long)));
+    RD_CUDA(cudaMemsetAsync(buf, 0, 1024 * 16 * sizeof(long long), stream));
+    d_prof = buf;
+  }
   if (mode == 0) {
     static bool attr0 = false;
     if (!attr0) {
@@ -429,7 +492,7 @@ inline int launch(int mode, const float* tap_src, void* dst, const float* coord,
       attr0 = true;
     }
     meta_ws_kernel<0><<<(unsigned)grid, NTHREADS, smem, stream>>>(tm_in, tm_out, coord, w0, b0, w1, b1, nullptr, nullptr, 0,
-                                                                  B, H, W, tiles_w, (int)ntiles);
+                                                                  B, H, W, tiles_w, (int)ntiles, d_prof);
   } else if (mode == 2) {
     static bool attr2 = false;
     if (!attr2) {
@@ -437,7 +500,7 @@ inline int launch(int mode, const float* tap_src, void* dst, const float* coord,
       attr2 = true;
     }
     meta_ws_kernel<2><<<(unsigned)grid, NTHREADS, smem, stream>>>(tm_in, tm_out, coord, w0, b0, w1, b1, ep_scale, ep_shift,
-                                                                  ep_relu, B, H, W, tiles_w, (int)ntiles);
+                                                                  ep_relu, B, H, W, tiles_w, (int)ntiles, d_prof);
   } else {
     static bool attr1 = false;
     if (!attr1) {
@@ -445,9 +508,24 @@ inline int launch(int mode, const float* tap_src, void* dst, const float* coord,
       attr1 = true;
     }
     meta_ws_kernel<1><<<(unsigned)grid, NTHREADS, smem, stream>>>(tm_in, tm_out, coord, w0, b0, w1, b1, nullptr, nullptr, 0,
-                                                                  B, H, W, tiles_w, (int)ntiles);
+                                                                  B, H, W, tiles_w, (int)ntiles, d_prof);
   }
   rd::count_launch();
+  if (want_prof) {  // diagnostic: synchronous, prints mean cycles per tile and role
+    RD_CUDA(cudaStreamSynchronize(stream));
+    static long long hbuf[1024 * 16];
+    RD_CUDA(cudaMemcpy(hbuf, d_prof, sizeof(long long) * 16 * grid, cudaMemcpyDeviceToHost));
+    double m[16] = {0};
+    for (int b = 0; b < grid; ++b)
+      for (int k = 0; k < 16; ++k) m[k] += (double)hbuf[b * 16 + k] / grid;
+    const double tl = (double)ntiles / grid;
+    fprintf(stderr,
+            "[rd_meta prof mode %d] tiles/cta=%.1f | per tile: producer %.0f (wait d_empty %.0f) | builders %.0f (wait a_empty "
+            "%.0f, coord staging %.0f) | mma %.0f (wait a_full %.0f, wait t_empty %.0f) | epi %.0f (wait t_full %.0f, wait d_full "
+            "%.0f, wait store+bar %.0f, body %.0f, bar+store %.0f)\n",
+            mode, tl, m[0] / tl, m[1] / tl, m[2] / tl, m[3] / tl, m[4] / tl, m[5] / tl, m[6] / tl, m[7] / tl, m[8] / tl,
+            m[9] / tl, m[10] / tl, m[11] / tl, m[12] / tl, m[13] / tl);
+  }
   return rd::check_launch(mode == 1 ? "rd_meta_kernel_bwd_data(impl 3)" : "rd_meta_kernel_fwd(impl 3)");
 }
 

@@ -134,44 +134,47 @@ meta_ws_params_kernel(const __grid_constant__ CUtensorMap tm_go, const __grid_co
     __syncwarp();
   } else if (warp == 1) {
     // ===== MMA issuer =====
-    if (lane == 0) {
-      const uint32_t idesc1 = tc::make_idesc_bf16(128, HID);            // G1: K-major A and B
-      const uint32_t idesc2 = tc::make_idesc_bf16(128, 80, 1, 1);       // G2: MN-major A and B
-      const uint32_t gw_base = tc::smem_u32(S.gw), h_base = tc::smem_u32(S.h), w1t_base = tc::smem_u32(S.w1t);
+    // Converged warp, one elected lane issues; descriptors precomputed (see meta_kernel_ws.cu: the issuing
+    // thread's own instruction latency, not the tensor core, bounded the per-MMA descriptor-building loop).
+    {
+      constexpr uint32_t idesc1 = tc::make_idesc_bf16(128, HID);         // G1: K-major A and B
+      constexpr uint32_t idesc2 = tc::make_idesc_bf16(128, 80, 1, 1);    // G2: MN-major A and B
+      constexpr uint32_t GC = CHUNK >> 4, WC = W1T_CHUNK >> 4;            // chunk strides in descriptor units
+      const uint64_t g1a = tc::make_smem_desc(0, CHUNK, 128, tc::LAYOUT_NONE) | (uint64_t)(tc::smem_u32(S.gw) >> 4);
+      const uint64_t g1b = tc::make_smem_desc(0, W1T_CHUNK, 128, tc::LAYOUT_NONE) | (uint64_t)(tc::smem_u32(S.w1t) >> 4);
+      const uint64_t g2a = tc::make_smem_desc(0, 128, CHUNK, tc::LAYOUT_NONE) | (uint64_t)(tc::smem_u32(S.gw) >> 4);
+      const uint64_t g2b = tc::make_smem_desc(0, 128, CHUNK, tc::LAYOUT_NONE) | (uint64_t)(tc::smem_u32(S.h) >> 4);
+      const bool leader = tc::elect_one();
       uint32_t g = 0;
       for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+#pragma unroll 1
         for (int k = 0; k < 9; ++k, ++g) {
           const uint32_t s1 = g & 1, ph1 = (g >> 1) & 1;
           tc::mbar_wait(&S.ops_full, g & 1);
           tc::mbar_wait(&S.d1_empty[s1], ph1 ^ 1);
           tc::tc_fence_after();
-          // G1: D1[px][j] = gw[px][c] . W1T[j][c]^T   (all four hi/lo cross terms)
-          uint32_t accum = 0;
+          if (leader) {
+            // G1: D1[px][j] = gw[px][c] . W1T[j][c]^T ; split-bf16 terms (hi,hi) (lo,hi) (hi,lo), 4 K slices each
+            const uint32_t d1 = tmem_base + s1 * HID;
+            tc::mma_bf16_ss(d1, g1a, g1b, idesc1, 0u);
 #pragma unroll
-          for (int bp = 0; bp < 2; ++bp)
+            for (int ks = 1; ks < 4; ++ks) tc::mma_bf16_ss_acc(d1, g1a + 2 * ks * GC, g1b + 2 * ks * WC, idesc1);
 #pragma unroll
-            for (int ap = 0; ap < 2; ++ap)
+            for (int ks = 0; ks < 4; ++ks) tc::mma_bf16_ss_acc(d1, g1a + (8 + 2 * ks) * GC, g1b + 2 * ks * WC, idesc1);
 #pragma unroll
-              for (int ks = 0; ks < 4; ++ks) {
-                const uint64_t ad = tc::make_smem_desc(gw_base + (ap * 8 + ks * 2) * CHUNK, CHUNK, 128, tc::LAYOUT_NONE);
-                const uint64_t bd = tc::make_smem_desc(w1t_base + (bp * 8 + ks * 2) * W1T_CHUNK, W1T_CHUNK, 128, tc::LAYOUT_NONE);
-                tc::mma_bf16_ss(tmem_base + s1 * HID, ad, bd, idesc1, accum);
-                accum = 1;
-              }
-          tc::umma_commit(&S.d1_full[s1]);
-          // G2: D2[(c,part)][(j,part)|1] += gw^T . [h | 1]   -- MN-major views: MN block stride = CHUNK
-          // (8 channels / hidden units per chunk), K block (8 pixels) stride = 128 B, K step = 16 px
+            for (int ks = 0; ks < 4; ++ks) tc::mma_bf16_ss_acc(d1, g1a + 2 * ks * GC, g1b + (8 + 2 * ks) * WC, idesc1);
+            tc::umma_commit(&S.d1_full[s1]);
+            // G2: D2[(c,part)][(j,part)|1] += gw^T . [h | 1]   -- MN-major views: MN block stride = CHUNK
+            // (8 channels / hidden units per chunk), K block (8 pixels) stride = 128 B, K step = 16 px = 256 B
+            tc::mma_bf16_ss(tmem_base + D2_COL, g2a, g2b, idesc2, g > 0 ? 1u : 0u);
 #pragma unroll
-          for (int ks = 0; ks < 8; ++ks) {
-            const uint64_t ad = tc::make_smem_desc(gw_base + ks * 256, 128, CHUNK, tc::LAYOUT_NONE);
-            const uint64_t bd = tc::make_smem_desc(h_base + ks * 256, 128, CHUNK, tc::LAYOUT_NONE);
-            tc::mma_bf16_ss(tmem_base + D2_COL, ad, bd, idesc2, (g > 0 || ks > 0) ? 1u : 0u);
+            for (int ks = 1; ks < 8; ++ks) tc::mma_bf16_ss_acc(tmem_base + D2_COL, g2a + 16 * ks, g2b + 16 * ks, idesc2);
+            tc::umma_commit(&S.ops_free);
           }
-          tc::umma_commit(&S.ops_free);
+          __syncwarp();
         }
       }
     }
-    __syncwarp();
   } else {
     // ===== builders: 8 warps = 2 threads per pixel (TMEM lane); thread `hf` owns hidden units
     // [16hf, 16hf+16) and channels [32hf, 32hf+32) of its pixel =====
