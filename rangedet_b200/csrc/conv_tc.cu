@@ -36,9 +36,9 @@ namespace conv {
 constexpr int TM = 128;               // GEMM rows per tile
 constexpr int KC = 64;                // channels per TMA box / swizzle atom
 constexpr int SLOT = TM * KC * 2;     // 16 KB ring slot (A tile, or a 128-row weight tile)
-constexpr int NTHREADS = 192;
+constexpr int NTHREADS = 384;
 constexpr int BAR_EPI = 1;
-constexpr int MAX_LOADS = 9, MAX_USES = 4, MAX_STAGES = 12;
+constexpr int MAX_LOADS = 9, MAX_USES = 4;
 constexpr uint32_t USE_NEWLOAD = 1, USE_LASTOFLOAD = 2, USE_FIRST = 4;  // flags of a per-use record
 
 struct Load {
@@ -54,6 +54,8 @@ struct SLoad {  // shared-memory form of Load: the per-use bytes packed into wor
   int dy, dx;
 };
 
+constexpr int MAX_PIPES = 2, MAX_SA = 4, MAX_SB = 8;
+
 struct Params {
   int N, H, W_out_tiles;    // W_out_tiles: GEMM-row extent along W (output cols for conv, input cols for deconv)
   int Cin, Cout;
@@ -62,17 +64,40 @@ struct Params {
   int nacc, nloads, ntaps, nuses_total;
   int relu, has_residual, res_after_relu;
   int deconv_s;             // 0: convolution (TMA-store epilogue); S>0: transposed conv, phase count S
-  int b_resident, nstages, acc_bufs;
-  int ring_off, w_off, o_off, misc_off;
-  int slot_bytes, a_bytes, use_base_offset;  // ring slot size, bytes of one activation load, descriptor variant
+  int b_resident, acc_bufs;
+  int npipes, nsa, nsb;     // pipelines, activation ring stages per pipeline, weight ring stages (shared)
+  int a_off[MAX_PIPES], o_off[MAX_PIPES], b_off, w_off, misc_off;
+  int slot_bytes, a_bytes;  // activation ring slot size, bytes of one activation load
   int64_t y_row, y_img;     // element strides of the haloed output (deconv / residual addressing)
   long long* prof;          // diagnostic builds only (RD_CONV_PROF=1), else null
   Load loads[MAX_LOADS];
 };
 
+struct Misc {  // barriers and small tables, at Params::misc_off of the dynamic shared memory
+  uint64_t a_full[MAX_PIPES][MAX_SA], a_empty[MAX_PIPES][MAX_SA];
+  uint64_t b_full[MAX_SB], b_empty[MAX_SB];
+  uint64_t t_full[MAX_PIPES][2], t_empty[MAX_PIPES][2];
+  uint64_t w_full;
+  uint32_t tmem_slot, pad;
+  float scale[128], shift[128];
+  uint4 uses[MAX_LOADS * MAX_USES];  // flat per-use records for the MMA warps (one K-half)
+  SLoad loads[MAX_LOADS];            // tap program for the producer
+};
+constexpr int MISC_BYTES = 3072;
+static_assert(sizeof(Misc) <= MISC_BYTES, "Misc grew past its reservation");
+
+// Two complete pipelines per CTA -- {MMA warp, four epilogue warps, TMEM accumulators, activation ring,
+// output staging tile} each -- fed by one TMA producer warp and sharing the weights (resident, or
+// streamed through ONE ring whose slots are released when both pipelines have used them: every weight
+// tile fetched from L2 serves two GEMM tiles).  Why two: one issuing thread sustains at best one MMA per
+// ~100-130 cycles in this loop (waits, commits, descriptor moves), the tensor core needs 48 (N=64) /
+// 64 (N=128); two issuers interleave on the same tensor core.
+//   warp 0 producer | warp 1 MMA pipe 0 | warps 2-5 epilogue pipe 0 | warp 6 MMA pipe 1 | warp 7 idle |
+//   warps 8-11 epilogue pipe 1.   A super-tile is npipes consecutive tiles; pipe p takes tile st*npipes+p.
 // PROF: diagnostic build (RD_CONV_PROF=1) that accumulates clock64() cycles per role into P.prof
-// [block][16]: 0 producer total, 1 producer wait(empty); 4 MMA total, 5 wait(full), 6 wait(t_empty);
-// 8 epilogue total, 9 wait(t_full), 10 wait(store read)+barrier, 11 TMEM->smem body.
+// [block][16]: 0 producer total, 1 producer wait(a_empty), 2 producer wait(b_empty); 4 MMA(pipe 0) total,
+// 5 wait(a_full), 6 wait(t_empty), 7 wait(b_full); 8 epilogue(pipe 0) total, 9 wait(t_full),
+// 10 wait(store read)+barrier, 11 TMEM->smem body.
 template <bool PROF>
 __global__ void __launch_bounds__(NTHREADS, 1)
 conv_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_w,
@@ -83,22 +108,16 @@ conv_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CU
   unsigned char* base = smem_raw + ((1024u - (tc::smem_u32(smem_raw) & 1023u)) & 1023u);
   const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
   auto tick = [&]() -> long long { return PROF ? clock64() : 0ll; };
-  long long pc0 = 0, pc1 = 0, pc2 = 0, pc3 = 0;
+  long long pc1 = 0, pc2 = 0, pc3 = 0;
   const long long t_begin = tick();
   const int kh = P.Cin / KC, nh = P.Cout / KC;
   const int b_tile = P.Cout * KC * 2;
-  unsigned char* ring = base + P.ring_off;
+  const int npipes = P.npipes;
+  const int nsuper = (P.ntiles + npipes - 1) / npipes;
   unsigned char* sW = base + P.w_off;
-  unsigned char* sO = base + P.o_off;
-  uint64_t* full = reinterpret_cast<uint64_t*>(base + P.misc_off);
-  uint64_t* empty = full + MAX_STAGES;
-  uint64_t* t_full = empty + MAX_STAGES;
-  uint64_t* t_empty = t_full + 2;
-  uint64_t* w_full = t_empty + 2;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(w_full + 1);
-  float* s_scale = reinterpret_cast<float*>(tmem_slot + 2);
-  float* s_shift = s_scale + 128;
-  __shared__ SLoad s_loads[MAX_LOADS];  // tap program, packed (dynamic indexing of kernel parameters is slow)
+  unsigned char* ringB = base + P.b_off;
+  Misc& M = *reinterpret_cast<Misc*>(base + P.misc_off);
+
   if (t < P.nloads) {
     SLoad L;
     L.nuse = P.loads[t].nuse;
@@ -110,130 +129,154 @@ conv_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CU
     }
     L.dy = P.loads[t].dy;
     L.dx = P.loads[t].dx;
-    s_loads[t] = L;
+    M.loads[t] = L;
   }
-  __shared__ uint4 s_uses[MAX_LOADS * MAX_USES];  // flat per-use records for the MMA warp (one K-half)
-  if (t == 0) {
+  if (t == 32) {
     int i = 0;
     uint32_t started = 0;
     for (int l = 0; l < P.nloads; ++l)
       for (int u = 0; u < P.loads[l].nuse; ++u, ++i) {
         const uint32_t acc = P.loads[l].acc[u], tap = P.loads[l].tap[u], off = P.loads[l].off[u];
         uint4 r;
-        r.x = off * 8;                                                        // pixel rows are 128 B = 8 units
-        r.y = (tc::smem_u32(base + P.w_off) >> 4) + tap * (uint32_t)(P.Cin / KC) * (uint32_t)((P.Cout * KC * 2) >> 4);
+        r.x = off * 8;  // strip mode: the view starts `off` pixel rows (128 B = 8 address units) into the tile
+        r.y = (tc::smem_u32(sW) >> 4) + tap * (uint32_t)kh * (uint32_t)(b_tile >> 4);  // resident weights
         r.z = acc * (uint32_t)P.Cout;
         r.w = (u == 0 ? USE_NEWLOAD : 0u) | (u == P.loads[l].nuse - 1 ? USE_LASTOFLOAD : 0u) |
               ((started >> acc) & 1u ? 0u : USE_FIRST);
         started |= 1u << acc;
-        s_uses[i] = r;
+        M.uses[i] = r;
       }
   }
-
   if (t == 0) {
-    for (int i = 0; i < P.nstages; ++i) { tc::mbar_init(&full[i], 1); tc::mbar_init(&empty[i], 1); }
-    for (int i = 0; i < 2; ++i) { tc::mbar_init(&t_full[i], 1); tc::mbar_init(&t_empty[i], 4); }
-    tc::mbar_init(w_full, 1);
+    for (int p = 0; p < MAX_PIPES; ++p) {
+      for (int i = 0; i < MAX_SA; ++i) { tc::mbar_init(&M.a_full[p][i], 1); tc::mbar_init(&M.a_empty[p][i], 1); }
+      for (int i = 0; i < 2; ++i) { tc::mbar_init(&M.t_full[p][i], 1); tc::mbar_init(&M.t_empty[p][i], 4); }
+    }
+    for (int i = 0; i < MAX_SB; ++i) { tc::mbar_init(&M.b_full[i], 1); tc::mbar_init(&M.b_empty[i], (uint32_t)npipes); }
+    tc::mbar_init(&M.w_full, 1);
     tc::fence_mbar_init();
     tma::prefetch_map(&tm_x);
     tma::prefetch_map(&tm_w);
     if (!P.deconv_s) tma::prefetch_map(&tm_y);
   }
   if (warp == 1) {
-    tc::tmem_alloc(tmem_slot, 512);
+    tc::tmem_alloc(&M.tmem_slot, 512);
     tc::tmem_relinquish();
   }
   for (int c = t; c < P.Cout; c += NTHREADS) {
-    s_scale[c] = scale ? __ldg(scale + c) : 1.f;
-    s_shift[c] = shift ? __ldg(shift + c) : 0.f;
+    M.scale[c] = scale ? __ldg(scale + c) : 1.f;
+    M.shift[c] = shift ? __ldg(shift + c) : 0.f;
   }
   tc::tc_fence_before();
   __syncthreads();
   tc::tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tmem_base = M.tmem_slot;
   const uint32_t acc_stride = (uint32_t)P.Cout;             // columns per accumulator
   const uint32_t buf_stride = (uint32_t)(P.nacc * P.Cout);  // columns per accumulator set
 
   if (warp == 0) {
-    // ===== TMA producer =====
+    // ===== TMA producer (both pipelines + the shared weight ring) =====
     if (lane == 0) {
       if (P.b_resident) {
-        tc::mbar_arrive_expect_tx(w_full, (uint32_t)(P.ntaps * kh * b_tile));
+        tc::mbar_arrive_expect_tx(&M.w_full, (uint32_t)(P.ntaps * kh * b_tile));
         for (int tap = 0; tap < P.ntaps; ++tap)
-          for (int q = 0; q < kh; ++q) tma::load_3d(sW + (tap * kh + q) * b_tile, &tm_w, w_full, q * KC, 0, tap);
+          for (int q = 0; q < kh; ++q) tma::load_3d(sW + (tap * kh + q) * b_tile, &tm_w, &M.w_full, q * KC, 0, tap);
       }
-      uint32_t s = 0, ph = 1;  // next ring stage and the parity to wait on its `empty` barrier
-      const uint32_t nstages = (uint32_t)P.nstages;
+      uint32_t sa0 = 0, pa0 = 1, sa1 = 0, pa1 = 1, sb = 0, pb = 1;  // ring positions, parity of the `empty` wait
+      const uint32_t nsa = (uint32_t)P.nsa, nsb = (uint32_t)P.nsb;
       const int nloads = P.nloads, resident = P.b_resident;
-      for (int tile = blockIdx.x; tile < P.ntiles; tile += gridDim.x) {
-        const int wt = tile % P.tiles_w, h = (tile / P.tiles_w) % P.H, n = tile / (P.tiles_w * P.H);
-        const int wx = wt * TM * P.in_stride_w;
+      unsigned char* ringA0 = base + P.a_off[0];
+      unsigned char* ringA1 = base + P.a_off[1];
+      for (int st = blockIdx.x; st < nsuper; st += gridDim.x) {
+        int tl0 = st * npipes, tl1 = tl0 + 1;
+        if (tl1 >= P.ntiles) tl1 = P.ntiles - 1;  // odd tail: pipe 1 recomputes the last tile, its store is skipped
+        const int wx0 = (tl0 % P.tiles_w) * TM * P.in_stride_w, h0 = (tl0 / P.tiles_w) % P.H, n0 = tl0 / (P.tiles_w * P.H);
+        const int wx1 = (tl1 % P.tiles_w) * TM * P.in_stride_w, h1 = (tl1 / P.tiles_w) % P.H, n1 = tl1 / (P.tiles_w * P.H);
         for (int q = 0; q < kh; ++q)
           for (int l = 0; l < nloads; ++l) {
-            const SLoad L = s_loads[l];
-            const long long ta = tick();
-            tc::mbar_wait(&empty[s], ph);
-            pc1 += tick() - ta;
-            tc::mbar_arrive_expect_tx(&full[s], (uint32_t)P.a_bytes);
-            tma::load_4d(ring + s * P.slot_bytes, &tm_x, &full[s], q * KC, wx + L.dx, h + L.dy, n);
-            if (++s == nstages) { s = 0; ph ^= 1; }
+            const SLoad L = M.loads[l];
+            {
+              const long long ta = tick();
+              tc::mbar_wait(&M.a_empty[0][sa0], pa0);
+              pc1 += tick() - ta;
+              tc::mbar_arrive_expect_tx(&M.a_full[0][sa0], (uint32_t)P.a_bytes);
+              tma::load_4d(ringA0 + sa0 * P.slot_bytes, &tm_x, &M.a_full[0][sa0], q * KC, wx0 + L.dx, h0 + L.dy, n0);
+              if (++sa0 == nsa) { sa0 = 0; pa0 ^= 1; }
+            }
+            if (npipes == 2) {
+              const long long ta = tick();
+              tc::mbar_wait(&M.a_empty[1][sa1], pa1);
+              pc1 += tick() - ta;
+              tc::mbar_arrive_expect_tx(&M.a_full[1][sa1], (uint32_t)P.a_bytes);
+              tma::load_4d(ringA1 + sa1 * P.slot_bytes, &tm_x, &M.a_full[1][sa1], q * KC, wx1 + L.dx, h1 + L.dy, n1);
+              if (++sa1 == nsa) { sa1 = 0; pa1 ^= 1; }
+            }
             if (!resident)
               for (int u = 0; u < (int)L.nuse; ++u) {
-                tc::mbar_wait(&empty[s], ph);
-                tc::mbar_arrive_expect_tx(&full[s], (uint32_t)b_tile);
-                tma::load_3d(ring + s * P.slot_bytes, &tm_w, &full[s], q * KC, 0, (int)((L.tap >> (8 * u)) & 0xff));
-                if (++s == nstages) { s = 0; ph ^= 1; }
+                const long long tb = tick();
+                tc::mbar_wait(&M.b_empty[sb], pb);
+                pc2 += tick() - tb;
+                tc::mbar_arrive_expect_tx(&M.b_full[sb], (uint32_t)b_tile);
+                tma::load_3d(ringB + sb * b_tile, &tm_w, &M.b_full[sb], q * KC, 0, (int)((L.tap >> (8 * u)) & 0xff));
+                if (++sb == nsb) { sb = 0; pb ^= 1; }
               }
           }
       }
-      if (PROF) { P.prof[blockIdx.x * 16 + 0] = tick() - t_begin; P.prof[blockIdx.x * 16 + 1] = pc1; }
+      if (PROF) {
+        P.prof[blockIdx.x * 16 + 0] = tick() - t_begin;
+        P.prof[blockIdx.x * 16 + 1] = pc1;
+        P.prof[blockIdx.x * 16 + 2] = pc2;
+      }
     }
     __syncwarp();
-  } else if (warp == 1) {
-    // ===== MMA issuer =====
+  } else if (warp == 1 || warp == 6) {
+    // ===== MMA issuer of pipeline p =====
     // The whole warp runs this loop CONVERGED and one elected lane issues.  Measured (scripts/mma_bench*.cu):
     // tcgen05.mma itself sustains its floor (48 cycles at N=64 -- shared-memory operand reads --, 64 at
     // N=128), but a loop that rebuilds descriptors, unpacks the tap program and polls per MMA spends
     // 130-240 cycles of the issuing thread per MMA.  So: one 16-byte record per use, read as a broadcast,
     // descriptors that differ only in their start-address field, four back-to-back MMAs per use.
-    {
+    const int p = warp == 1 ? 0 : 1;
+    if (p < npipes) {
       const uint32_t idesc = tc::make_idesc_bf16(TM, P.Cout);
       const uint64_t desc_hi = tc::make_smem_desc(0, 0, 1024, tc::LAYOUT_SW128);  // everything but the address
-      const uint32_t ring_lo = tc::smem_u32(ring) >> 4;
+      const uint32_t ringA_lo = tc::smem_u32(base + P.a_off[p]) >> 4, ringB_lo = tc::smem_u32(ringB) >> 4;
       const uint32_t slot_lo = (uint32_t)P.slot_bytes >> 4, btile_lo = (uint32_t)b_tile >> 4;
-      const uint32_t nstages = (uint32_t)P.nstages;
+      const uint32_t nsa = (uint32_t)P.nsa, nsb = (uint32_t)P.nsb;
       const int nuses = P.nuses_total, resident = P.b_resident;
       const bool leader = tc::elect_one();
-      if (resident) tc::mbar_wait(w_full, 0);
-      uint32_t s = 0, ph = 0;  // ring position of the next unit (stage index, phase parity)
+      if (resident) tc::mbar_wait(&M.w_full, 0);
+      uint32_t sa = 0, pha = 0, sb = 0, phb = 0;  // ring positions of the next units, phase parities
       uint32_t it = 0;
-      for (int tile = blockIdx.x; tile < P.ntiles; tile += gridDim.x, ++it) {
+      for (int st = blockIdx.x; st < nsuper; st += gridDim.x, ++it) {
         const uint32_t buf = P.acc_bufs == 2 ? (it & 1) : 0;
         const uint32_t use_n = P.acc_bufs == 2 ? (it >> 1) : it;  // how many times this buffer was used before
         const long long te = tick();
-        tc::mbar_wait(&t_empty[buf], (use_n & 1) ^ 1);
+        tc::mbar_wait(&M.t_empty[p][buf], (use_n & 1) ^ 1);
         pc2 += tick() - te;
-        const uint32_t d_base = tmem_base + buf * buf_stride;
+        const uint32_t d_base = tmem_base + ((uint32_t)p * P.acc_bufs + buf) * buf_stride;
         for (int q = 0; q < kh; ++q) {
-          uint32_t a_lo = 0, sa = 0;
+          uint32_t a_lo = 0, cur_sa = 0;
           const uint32_t bq = (uint32_t)q * btile_lo;
 #pragma unroll 1
           for (int i = 0; i < nuses; ++i) {
-            const uint4 r = s_uses[i];  // x: A offset (16-B units), y: resident B address, z: TMEM column, w: flags
+            const uint4 r = M.uses[i];  // x: A offset (16-B units), y: resident B address, z: TMEM column, w: flags
             if (r.w & USE_NEWLOAD) {
-              sa = s;
+              cur_sa = sa;
               const long long tf = tick();
-              tc::mbar_wait(&full[s], ph);
+              tc::mbar_wait(&M.a_full[p][sa], pha);
               pc1 += tick() - tf;
-              a_lo = ring_lo + s * slot_lo;
-              if (++s == nstages) { s = 0; ph ^= 1; }
+              a_lo = ringA_lo + sa * slot_lo;
+              if (++sa == nsa) { sa = 0; pha ^= 1; }
             }
-            uint32_t b_lo = r.y + bq, sb = 0;
+            uint32_t b_lo = r.y + bq, cur_sb = 0;
             if (!resident) {
-              sb = s;
-              tc::mbar_wait(&full[s], ph);
-              b_lo = ring_lo + s * slot_lo;
-              if (++s == nstages) { s = 0; ph ^= 1; }
+              cur_sb = sb;
+              const long long tf = tick();
+              tc::mbar_wait(&M.b_full[sb], phb);
+              pc3 += tick() - tf;
+              b_lo = ringB_lo + sb * btile_lo;
+              if (++sb == nsb) { sb = 0; phb ^= 1; }
             }
             tc::tc_fence_after();
             if (leader) {
@@ -245,109 +288,121 @@ conv_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CU
               tc::mma_bf16_ss_acc(d_tmem, ad + 2, bd + 2, idesc);
               tc::mma_bf16_ss_acc(d_tmem, ad + 4, bd + 4, idesc);
               tc::mma_bf16_ss_acc(d_tmem, ad + 6, bd + 6, idesc);
-              if (!resident) tc::umma_commit(&empty[sb]);
-              if (r.w & USE_LASTOFLOAD) tc::umma_commit(&empty[sa]);
+              if (!resident) tc::umma_commit(&M.b_empty[cur_sb]);
+              if (r.w & USE_LASTOFLOAD) tc::umma_commit(&M.a_empty[p][cur_sa]);
             }
             __syncwarp();
           }
         }
-        if (leader) tc::umma_commit(&t_full[buf]);
+        if (leader) tc::umma_commit(&M.t_full[p][buf]);
         __syncwarp();
       }
-      if (PROF && lane == 0) {
+      if (PROF && lane == 0 && p == 0) {
         P.prof[blockIdx.x * 16 + 4] = tick() - t_begin;
         P.prof[blockIdx.x * 16 + 5] = pc1;
         P.prof[blockIdx.x * 16 + 6] = pc2;
+        P.prof[blockIdx.x * 16 + 7] = pc3;
       }
     }
-  } else {
-    // ===== epilogue: thread = GEMM row = TMEM lane =====
-    const int q4 = warp & 3;
-    const int px = q4 * 32 + lane;
-    const uint32_t lane_sel = (uint32_t)(q4 * 32) << 16;
-    const bool leader = (warp == 2 && lane == 0);
-    uint32_t it = 0;
-    for (int tile = blockIdx.x; tile < P.ntiles; tile += gridDim.x, ++it) {
-      const int wt = tile % P.tiles_w, h = (tile / P.tiles_w) % P.H, n = tile / (P.tiles_w * P.H);
-      const int w0 = wt * TM;
-      const uint32_t buf = P.acc_bufs == 2 ? (it & 1) : 0;
-      const uint32_t use_n = P.acc_bufs == 2 ? (it >> 1) : it;
-      const long long e0 = tick();
-      tc::mbar_wait(&t_full[buf], use_n & 1);
-      __syncwarp();
-      tc::tc_fence_after();
-      const long long e1 = tick();
-      const bool in_img = (w0 + px) < P.W_out_tiles;
-      if (!P.deconv_s) {
-        if (leader) tma::store_wait_read<0>();  // previous tile's stores have read the staging buffer
-        tma::named_bar_sync(BAR_EPI, 128);
-      }
-      const long long e2 = tick();
-      pc1 += e1 - e0;
-      pc2 += e2 - e1;
-      const int nphase = P.deconv_s ? P.deconv_s : 1;
-      for (int ph = 0; ph < nphase; ++ph) {
-        // output pixel of this thread for this phase (interior coordinates)
-        const int64_t opix = P.deconv_s ? (int64_t)(w0 + px) * P.deconv_s + ph : (int64_t)(w0 + px);
-        const int64_t ooff = (int64_t)n * P.y_img + (int64_t)h * P.y_row + opix * P.Cout;
-        for (int c0 = 0; c0 < P.Cout; c0 += 32) {
-          float v[32];
-          tc::tmem_ld_x32(tmem_base + lane_sel + buf * buf_stride + ph * acc_stride + c0, v);
-          uint4 rv[4];
-          if (P.has_residual && in_img) {
+  } else if (warp != 7) {
+    // ===== epilogue of pipeline p: thread = GEMM row = TMEM lane =====
+    const int p = warp >= 8 ? 1 : 0;
+    if (p < npipes) {
+      const int q4 = warp & 3;  // TMEM lane quadrant this warp may read
+      const int px = q4 * 32 + lane;
+      const uint32_t lane_sel = (uint32_t)(q4 * 32) << 16;
+      const bool leader = ((warp == 2 || warp == 8) && lane == 0);
+      const int bar_id = BAR_EPI + p;
+      unsigned char* sO = base + P.o_off[p];
+      uint32_t it = 0;
+      for (int st = blockIdx.x; st < nsuper; st += gridDim.x, ++it) {
+        const int tile = st * npipes + p;
+        const bool real = tile < P.ntiles;  // odd tail: the duplicate tile of pipe 1 is computed but not stored
+        const int tl = real ? tile : P.ntiles - 1;
+        const int wt = tl % P.tiles_w, h = (tl / P.tiles_w) % P.H, n = tl / (P.tiles_w * P.H);
+        const int w0 = wt * TM;
+        const uint32_t buf = P.acc_bufs == 2 ? (it & 1) : 0;
+        const uint32_t use_n = P.acc_bufs == 2 ? (it >> 1) : it;
+        const long long e0 = tick();
+        tc::mbar_wait(&M.t_full[p][buf], use_n & 1);
+        __syncwarp();
+        tc::tc_fence_after();
+        const long long e1 = tick();
+        const bool in_img = real && (w0 + px) < P.W_out_tiles;
+        if (!P.deconv_s) {
+          if (leader) tma::store_wait_read<0>();  // previous tile's stores have read the staging buffer
+          tma::named_bar_sync(bar_id, 128);
+        }
+        const long long e2 = tick();
+        pc1 += e1 - e0;
+        pc2 += e2 - e1;
+        const uint32_t t_acc = tmem_base + lane_sel + ((uint32_t)p * P.acc_bufs + buf) * buf_stride;
+        const int nphase = P.deconv_s ? P.deconv_s : 1;
+        for (int ph = 0; ph < nphase; ++ph) {
+          // output pixel of this thread for this phase (interior coordinates)
+          const int64_t opix = P.deconv_s ? (int64_t)(w0 + px) * P.deconv_s + ph : (int64_t)(w0 + px);
+          const int64_t ooff = (int64_t)n * P.y_img + (int64_t)h * P.y_row + opix * P.Cout;
+          for (int c0 = 0; c0 < P.Cout; c0 += 32) {
+            float v[32];
+            tc::tmem_ld_x32(t_acc + ph * acc_stride + c0, v);
+            uint4 rv[4];
+            if (P.has_residual && in_img) {
 #pragma unroll
-            for (int j = 0; j < 4; ++j) rv[j] = __ldg(reinterpret_cast<const uint4*>(residual + ooff + c0) + j);
-          }
+              for (int j = 0; j < 4; ++j) rv[j] = __ldg(reinterpret_cast<const uint4*>(residual + ooff + c0) + j);
+            }
 #pragma unroll
-          for (int j = 0; j < 4; ++j) {  // 8 channels -> one 16-byte chunk
-            uint32_t pk[4];
+            for (int j = 0; j < 4; ++j) {  // 8 channels -> one 16-byte chunk
+              uint32_t pk[4];
 #pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              const int c = c0 + j * 8 + 2 * e;
-              float a = fmaf(v[j * 8 + 2 * e], s_scale[c], s_shift[c]);
-              float b = fmaf(v[j * 8 + 2 * e + 1], s_scale[c + 1], s_shift[c + 1]);
-              float ra = 0.f, rb = 0.f;
-              if (P.has_residual && in_img) {
-                const uint32_t w = reinterpret_cast<const uint32_t*>(&rv[j])[e];
-                const __nv_bfloat162 r2 = *reinterpret_cast<const __nv_bfloat162*>(&w);
-                ra = __bfloat162float(r2.x);
-                rb = __bfloat162float(r2.y);
+              for (int e = 0; e < 4; ++e) {
+                const int c = c0 + j * 8 + 2 * e;
+                float a = fmaf(v[j * 8 + 2 * e], M.scale[c], M.shift[c]);
+                float b = fmaf(v[j * 8 + 2 * e + 1], M.scale[c + 1], M.shift[c + 1]);
+                float ra = 0.f, rb = 0.f;
+                if (P.has_residual && in_img) {
+                  const uint32_t w = reinterpret_cast<const uint32_t*>(&rv[j])[e];
+                  const __nv_bfloat162 r2 = *reinterpret_cast<const __nv_bfloat162*>(&w);
+                  ra = __bfloat162float(r2.x);
+                  rb = __bfloat162float(r2.y);
+                }
+                if (!P.res_after_relu) { a += ra; b += rb; }
+                if (P.relu) { a = fmaxf(a, 0.f); b = fmaxf(b, 0.f); }
+                if (P.res_after_relu) { a += ra; b += rb; }
+                pk[e] = tc::pack_bf16x2(a, b);
               }
-              if (!P.res_after_relu) { a += ra; b += rb; }
-              if (P.relu) { a = fmaxf(a, 0.f); b = fmaxf(b, 0.f); }
-              if (P.res_after_relu) { a += ra; b += rb; }
-              pk[e] = tc::pack_bf16x2(a, b);
-            }
-            if (P.deconv_s) {
-              if (in_img) *reinterpret_cast<uint4*>(y_interior + ooff + c0 + j * 8) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
-            } else {
-              const int half = (c0 + j * 8) / KC, chunk = ((c0 + j * 8) % KC) / 8;
-              // 128B swizzle: 16-byte chunk index XOR (row % 8)
-              *reinterpret_cast<uint4*>(sO + half * SLOT + px * 128 + ((chunk ^ (px & 7)) << 4)) =
-                  make_uint4(pk[0], pk[1], pk[2], pk[3]);
+              if (P.deconv_s) {
+                if (in_img) *reinterpret_cast<uint4*>(y_interior + ooff + c0 + j * 8) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+              } else {
+                // staging tile + TMA store; direct 16-byte global stores were measured slower (epilogue body
+                // 5267 -> 9010 cycles per 128->128 tile: every warp-wide store touches 32 lines)
+                const int half = (c0 + j * 8) / KC, chunk = ((c0 + j * 8) % KC) / 8;
+                // 128B swizzle: 16-byte chunk index XOR (row % 8)
+                *reinterpret_cast<uint4*>(sO + half * SLOT + px * 128 + ((chunk ^ (px & 7)) << 4)) =
+                    make_uint4(pk[0], pk[1], pk[2], pk[3]);
+              }
             }
           }
         }
-      }
-      tc::tc_fence_before();
-      if (!P.deconv_s) tc::fence_proxy_async_smem();
-      __syncwarp();
-      pc3 += tick() - e2;
-      if (lane == 0) tc::mbar_arrive(&t_empty[buf]);
-      if (!P.deconv_s) {
-        tma::named_bar_sync(BAR_EPI, 128);
-        if (leader) {
-          for (int hf = 0; hf < nh; ++hf) tma::store_4d(&tm_y, sO + hf * SLOT, hf * KC, w0, h, n);
-          tma::store_commit();
+        tc::tc_fence_before();
+        if (!P.deconv_s) tc::fence_proxy_async_smem();
+        __syncwarp();
+        pc3 += tick() - e2;
+        if (lane == 0) tc::mbar_arrive(&M.t_empty[p][buf]);
+        if (!P.deconv_s) {
+          tma::named_bar_sync(bar_id, 128);
+          if (leader && real) {
+            for (int hf = 0; hf < nh; ++hf) tma::store_4d(&tm_y, sO + hf * SLOT, hf * KC, w0, h, n);
+            tma::store_commit();
+          }
         }
       }
-    }
-    if (!P.deconv_s && leader) tma::store_wait_all<0>();
-    if (PROF && leader) {
-      P.prof[blockIdx.x * 16 + 8] = tick() - t_begin;
-      P.prof[blockIdx.x * 16 + 9] = pc1;
-      P.prof[blockIdx.x * 16 + 10] = pc2;
-      P.prof[blockIdx.x * 16 + 11] = pc3;
+      if (!P.deconv_s && leader) tma::store_wait_all<0>();
+      if (PROF && leader && p == 0) {
+        P.prof[blockIdx.x * 16 + 8] = tick() - t_begin;
+        P.prof[blockIdx.x * 16 + 9] = pc1;
+        P.prof[blockIdx.x * 16 + 10] = pc2;
+        P.prof[blockIdx.x * 16 + 11] = pc3;
+      }
     }
   }
   tc::tc_fence_before();
@@ -448,29 +503,48 @@ static int run(int mode, const void* x_pad, const void* w_packed, const float* s
   const int kh = Cin / KC, nh = Cout / KC;
   const int b_tile = Cout * KC * 2;
   const int w_bytes = P.ntaps * kh * b_tile;
-  const int o_bytes = P.deconv_s ? 0 : nh * SLOT;
-  const int misc = 2048;
-  const int total_budget = 222 * 1024;
-  P.b_resident = (w_bytes <= total_budget - o_bytes - misc - 4 * 17 * 1024 && w_bytes <= 96 * 1024) ? 1 : 0;
   const int box_px = strip ? TM + 2 : TM * (mode == 0 ? stride_w : 1);
   P.a_bytes = (strip ? TM + 2 : TM) * KC * 2;
   P.slot_bytes = strip ? 17 * 1024 : SLOT;
+  // Pipelines: two whenever both accumulator sets fit in the 512 TMEM columns (RD_CONV_PIPES=1 forces one).
   {
-    // Probed on B200 (scripts/run_strip.sh): the 128B swizzle is a pure function of the shared-memory
-    // ADDRESS bits, so a row-shifted start address needs NO base_offset (setting it breaks parity).
-    const char* eb = getenv("RD_CONV_BASEOFF");
-    P.use_base_offset = (eb && eb[0] == '1') ? 1 : 0;
+    const char* ep = getenv("RD_CONV_PIPES");
+    P.npipes = (2 * P.nacc * Cout <= 512 && !(ep && ep[0] == '1') && P.ntiles >= 2) ? 2 : 1;
   }
-  int ns = (total_budget - o_bytes - misc - (P.b_resident ? w_bytes : 0)) / P.slot_bytes;
-  if (ns > MAX_STAGES) ns = MAX_STAGES;
-  RD_REQUIRE(ns >= 6, "rd_conv: shared memory budget too small (%d stages)", ns);
-  P.nstages = ns;
-  P.acc_bufs = (2 * P.nacc * Cout <= 512) ? 2 : 1;
-  P.ring_off = 0;
-  P.w_off = ns * P.slot_bytes;
-  P.o_off = P.w_off + (P.b_resident ? w_bytes : 0);
-  P.misc_off = P.o_off + o_bytes;
-  const size_t smem = (size_t)P.misc_off + misc + 1024;
+  P.acc_bufs = (2 * P.npipes * P.nacc * Cout <= 512) ? 2 : 1;
+  // Shared memory: [activation rings][weight ring | resident weights][output staging tiles][Misc]
+  const int o_bytes = P.deconv_s ? 0 : nh * SLOT;  // per pipeline
+  const int budget = 222 * 1024 - MISC_BYTES - P.npipes * o_bytes;
+  P.b_resident = (w_bytes <= 96 * 1024 && w_bytes <= budget - P.npipes * 2 * P.slot_bytes) ? 1 : 0;
+  if (P.b_resident) {
+    P.nsb = 0;
+    P.nsa = (budget - w_bytes) / (P.npipes * P.slot_bytes);
+  } else {
+    // weights stream: two activation stages per pipeline, the rest of the budget is the weight ring
+    // (measured 0.1728 ms with 2 + 5 stages vs 0.1767 ms with 3 + 3 for 128->128 @ 4x64x2656)
+    P.nsa = 2;
+    P.nsb = (budget - P.npipes * P.nsa * P.slot_bytes) / b_tile;
+  }
+  if (!P.b_resident) {  // diagnostic override of the split between activation and weight stages
+    const char* ea = getenv("RD_CONV_NSA");
+    if (ea && ea[0] >= '2' && ea[0] <= '4') {
+      P.nsa = ea[0] - '0';
+      P.nsb = (budget - P.npipes * P.nsa * P.slot_bytes) / b_tile;
+    }
+  }
+  if (P.nsa > MAX_SA) P.nsa = MAX_SA;
+  if (P.nsb > MAX_SB) P.nsb = MAX_SB;
+  RD_REQUIRE(P.nsa >= 2 && (P.b_resident || P.nsb >= 2), "rd_conv: shared memory budget too small (nsa %d, nsb %d)", P.nsa, P.nsb);
+  {
+    int off = 0;
+    for (int p = 0; p < MAX_PIPES; ++p) { P.a_off[p] = off; if (p < P.npipes) off += P.nsa * P.slot_bytes; }
+    P.b_off = P.w_off = off;
+    off += P.b_resident ? w_bytes : P.nsb * b_tile;
+    for (int p = 0; p < MAX_PIPES; ++p) { P.o_off[p] = off; if (p < P.npipes) off += o_bytes; }
+    P.misc_off = off;
+  }
+  const size_t smem = (size_t)P.misc_off + MISC_BYTES + 1024;
+  RD_REQUIRE(smem <= 227 * 1024, "rd_conv: shared memory layout exceeds 227 KB (%zu)", smem);
   const uint64_t Wp_in = (uint64_t)W_in + 2, Hp = (uint64_t)H + 2, Wp_out = (uint64_t)W_out + 2;
   P.y_row = (int64_t)Wp_out * Cout;
   P.y_img = (int64_t)Hp * Wp_out * Cout;
@@ -507,7 +581,8 @@ static int run(int mode, const void* x_pad, const void* w_packed, const float* s
     RD_CUDA(cudaFuncSetAttribute(conv_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     smem_set = smem;
   }
-  const int grid = P.ntiles < sms ? P.ntiles : sms;
+  const int nsuper = (P.ntiles + P.npipes - 1) / P.npipes;
+  const int grid = nsuper < sms ? nsuper : sms;
   static const bool prof = [] { const char* e = getenv("RD_CONV_PROF"); return e && e[0] == '1'; }();
   if (prof) {  // diagnostic: per-role cycle counters, synchronous, printed to stderr
     static long long* d_prof = nullptr;
@@ -522,12 +597,13 @@ static int run(int mode, const void* x_pad, const void* w_packed, const float* s
     double m[16] = {0};
     for (int b = 0; b < grid; ++b)
       for (int k = 0; k < 16; ++k) m[k] += (double)h[b * 16 + k] / grid;
-    const double tiles = (double)P.ntiles / grid;
+    const double tiles = (double)((P.ntiles + P.npipes - 1) / P.npipes) / grid;
     fprintf(stderr,
-            "[rd_conv prof] Cin=%d Cout=%d tiles/cta=%.1f nloads=%d nstages=%d | per tile: producer %.0f (wait empty %.0f) | "
-            "mma %.0f (wait full %.0f, wait t_empty %.0f) | epi %.0f (wait t_full %.0f, wait store+bar %.0f, body %.0f)\n",
-            P.Cin, P.Cout, tiles, P.nloads, P.nstages, m[0] / tiles, m[1] / tiles, m[4] / tiles, m[5] / tiles,
-            m[6] / tiles, m[8] / tiles, m[9] / tiles, m[10] / tiles, m[11] / tiles);
+            "[rd_conv prof] Cin=%d Cout=%d pipes=%d nsa=%d nsb=%d resident=%d super-tiles/cta=%.1f | per super-tile: producer %.0f "
+            "(wait a_empty %.0f, b_empty %.0f) | mma0 %.0f (wait a_full %.0f, b_full %.0f, t_empty %.0f) | epi0 %.0f (wait t_full "
+            "%.0f, wait store+bar %.0f, body %.0f)\n",
+            P.Cin, P.Cout, P.npipes, P.nsa, P.nsb, P.b_resident, tiles, m[0] / tiles, m[1] / tiles, m[2] / tiles, m[4] / tiles,
+            m[5] / tiles, m[7] / tiles, m[6] / tiles, m[8] / tiles, m[9] / tiles, m[10] / tiles, m[11] / tiles);
   } else {
     conv_kernel<false><<<grid, NTHREADS, smem, stream>>>(tm_x, tm_w, tm_y, scale, shift, res,
                                                          reinterpret_cast<__nv_bfloat16*>(y_int), P);
