@@ -211,19 +211,38 @@ meta_ws_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant_
     // ===== hidden-layer producers (128 threads, thread = pixel) =====
     const int ht = t - 64;
     uint32_t g = 0;
-    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    // Coordinate tile (3 rows x 3 channels x 130 columns) of a tile -> registers.  Issued one tile AHEAD:
+    // the per-role cycle profile (RD_MK_PROF) showed 10.9k of the builders' 25.5k cycles per tile spent in
+    // this staging step (exposed global-load latency between two barriers), and the builders are the
+    // critical path (the MMA warp waited 80 % of the time for operand tiles).
+    constexpr int CS_PER_THREAD = (3 * CCH * ROW + 127) / 128;
+    auto load_coords = [&](int tile, float (&cp)[CS_PER_THREAD]) {
       const int wt = tile % tiles_w, h = (tile / tiles_w) % H, b = tile / (tiles_w * H);
       const int w0px = wt * TW;
+#pragma unroll
+      for (int i = 0; i < CS_PER_THREAD; ++i) {
+        const int e = ht + i * 128;
+        float v = 0.f;
+        if (e < 3 * CCH * ROW) {
+          const int col = e % ROW, d = (e / ROW) % CCH, r = e / (ROW * CCH);
+          const int hh = h + r - 1, ww = w0px + col - 1;
+          if (hh >= 0 && hh < H && ww >= 0 && ww < W) v = __ldg(coord + (((int64_t)b * CCH + d) * H + hh) * W + ww);
+        }
+        cp[i] = v;
+      }
+    };
+    float cpre[CS_PER_THREAD];
+    if ((int)blockIdx.x < ntiles) load_coords(blockIdx.x, cpre);
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
       const long long tc0 = tick();
       tma::named_bar_sync(BAR_HID, 128);  // everyone finished reading the previous coordinate tile
-      for (int e = ht; e < 3 * CCH * ROW; e += 128) {
-        const int col = e % ROW, d = (e / ROW) % CCH, r = e / (ROW * CCH);
-        const int hh = h + r - 1, ww = w0px + col - 1;
-        float v = 0.f;
-        if (hh >= 0 && hh < H && ww >= 0 && ww < W) v = __ldg(coord + (((int64_t)b * CCH + d) * H + hh) * W + ww);
-        S.cs[(r * CCH + d) * ROW + col] = v;
+#pragma unroll
+      for (int i = 0; i < CS_PER_THREAD; ++i) {
+        const int e = ht + i * 128;
+        if (e < 3 * CCH * ROW) S.cs[e] = cpre[i];  // e == (r * CCH + d) * ROW + col
       }
       tma::named_bar_sync(BAR_HID, 128);
+      if (tile + (int)gridDim.x < ntiles) load_coords(tile + gridDim.x, cpre);  // in flight during this tile
       pb += tick() - tc0;
       const float c0 = S.cs[(1 * CCH + 0) * ROW + ht + 1];
       const float c1 = S.cs[(1 * CCH + 1) * ROW + ht + 1];
