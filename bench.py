@@ -239,8 +239,22 @@ def run_ours(args, rank, local_rank, world):
         kernels[name] = {"ms": kms, "algorithmic_bytes": px * bpp, "GBps": px * bpp / (kms * 1e-3) / 1e9}
     peak, peak_src = measured_peak_gbs()
     dom = max(kernels, key=lambda k: kernels[k]["ms"])
+    # DRAM bytes per launch of that kernel from the committed `ncu --set full` capture of this workload
+    # (profiles/r01_dram_traffic.json, written by scripts/ncu_summary.py); null for any other shape.
+    traffic = None
+    try:
+        tr = json.load(open(os.path.join(ROOT, "profiles", "r01_dram_traffic.json")))
+        if tr.get("workload") == [B, C, H, W_PAD]:
+            pat = {"meta_fwd": "meta_ws_kernel<0>", "meta_bwd_data": "meta_ws_kernel<1>",
+                   "meta_bwd_params": "meta_ws_params_kernel"}[dom]
+            for name, v in tr["kernels"].items():
+                if pat in name.replace(" ", ""):
+                    traffic = int(v["dram_read_bytes"] + v["dram_write_bytes"])
+    except (OSError, KeyError, ValueError):
+        traffic = None
     roofline = {"bound": "hbm", "kernel": dom, "achieved": kernels[dom]["GBps"], "peak": peak, "unit": "GB/s",
-                "frac": kernels[dom]["GBps"] / peak, "traffic": None, "peak_source": peak_src,
+                "frac": kernels[dom]["GBps"] / peak, "traffic": traffic, "traffic_unit": "bytes per launch (ncu dram read+write)",
+                "algorithmic_bytes": int(kernels[dom]["algorithmic_bytes"]), "peak_source": peak_src,
                 "kernels": {k: {"ms": round(v["ms"], 4), "GBps": round(v["GBps"], 1), "frac": round(v["GBps"] / peak, 4)}
                             for k, v in kernels.items()},
                 "step_algorithmic_GBps": px * (BYTES_FWD + 576 * 4 + 64 * 4 + 12 + 256) / (ms / args.steps * 1e-3) / 1e9}

@@ -264,7 +264,7 @@ meta_ws_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant_
           uint32_t hi[4], lo[4];
 #pragma unroll
           for (int p = 0; p < 4; ++p) {
-            float hh[2], hl[2];
+            float hv[2];
 #pragma unroll
             for (int u = 0; u < 2; ++u) {
               const float4 wv = S.w0b[q * 8 + 2 * p + u];
@@ -272,10 +272,9 @@ meta_ws_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant_
               z = fmaf(wv.x, r0, z);
               z = fmaf(wv.y, r1, z);
               z = fmaf(wv.z, r2, z);
-              tc::split_bf16(fmaxf(z, 0.f), hh[u], hl[u]);
+              hv[u] = fmaxf(z, 0.f);
             }
-            hi[p] = tc::pack_bf16x2(hh[0], hh[1]);
-            lo[p] = tc::pack_bf16x2(hl[0], hl[1]);
+            tc::split_pack_bf16x2(hv[0], hv[1], hi[p], lo[p]);
           }
           *reinterpret_cast<uint4*>(abuf + q * A_CHUNK + ht * 16) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
           *reinterpret_cast<uint4*>(abuf + (4 + q) * A_CHUNK + ht * 16) = make_uint4(lo[0], lo[1], lo[2], lo[3]);

@@ -11,9 +11,12 @@
 //   gW0[j][d] += sum_p relu'(.) ghid[p][j] rel[p][d], gb0 likewise        (fp32 register accumulators)
 // bf16 hi+lo splits of gw / hid / W1 keep every product within ~2^-16 of fp32.
 // Roles: warp 0 TMA producer (grad_out tap tiles + feature row boxes), warp 1 MMA issuer,
-// warps 2-9 builders (two threads per pixel: operand tiles, D1 consumption; they are the
+// warps 2-17 builders (four threads per pixel: operand tiles, D1 consumption; they are the
 // critical resource -- ncu showed producer and MMA warps spinning on builder-signalled barriers).  One partial result row per CTA goes to the
 // workspace; the deterministic reduce kernel of meta_kernel.cu finishes the sum.
+#include <stdio.h>
+#include <stdlib.h>
+
 #include "../../include/rangedet_b200.h"
 #include "rd_common.cuh"
 #include "tc_common.cuh"
@@ -23,8 +26,10 @@ namespace mkwp {
 
 constexpr int HID = 32, CCH = 3, C = 64;
 constexpr int TW = 128, ROW = TW + 2, DTW = TW + 8;
-constexpr int NTHREADS = 320;                 // warp 0 TMA, warp 1 MMA, warps 2-9 builders
-constexpr int NBUILD = 256;
+constexpr int TPP = 4;                        // builder threads per pixel
+constexpr int NBUILD = TW * TPP;              // 512: warps 2-17
+constexpr int NTHREADS = 64 + NBUILD;         // warp 0 TMA, warp 1 MMA, then the builders
+constexpr int NBW = NBUILD / 32;              // builder warps (mbarrier arrival counts)
 constexpr int CHUNK = TW * 16;                // one 16-byte chunk over 128 pixel rows (2048 B)
 constexpr int GW_BYTES = 16 * CHUNK;          // gw_hi (8 chunks of 8 channels) | gw_lo (8 chunks)
 constexpr int H_BYTES = 10 * CHUNK;           // h_hi (4) | h_lo (4) | ones chunk | zero chunk
@@ -55,17 +60,24 @@ __global__ void __launch_bounds__(NTHREADS, 1)
 meta_ws_params_kernel(const __grid_constant__ CUtensorMap tm_go, const __grid_constant__ CUtensorMap tm_data,
                       const float* __restrict__ coord, const float* __restrict__ w0, const float* __restrict__ b0,
                       const float* __restrict__ w1, float* __restrict__ partial, int B, int H, int W, int tiles_w,
-                      int ntiles) {
+                      int ntiles, long long* __restrict__ prof) {
+  // prof (diagnostic, RD_MK_PROF=1, else null): per-CTA clock64() sums, [block][16]: 0 producer total,
+  // 1 wait go_empty, 2 wait dr_empty | 3 MMA total, 4 wait ops_full, 5 wait d1_empty | 6 builder total,
+  // 7 hidden layer, 8 wait go_full/dr_full, 9 products, 10 wait ops_free, 11 operand stores, 12 wait d1_full,
+  // 13 D1 consumption, 14 coordinate staging
+  auto tick = [&]() -> long long { return prof ? clock64() : 0ll; };
+  long long q0 = 0, q1 = 0, q2 = 0, q3 = 0, q4c = 0, q5 = 0, q6 = 0, q7 = 0;
+  const long long t_begin = tick();
   extern __shared__ unsigned char smem_raw[];
   Smem& S = *reinterpret_cast<Smem*>(smem_raw + ((1024u - (tc::smem_u32(smem_raw) & 1023u)) & 1023u));
   const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
 
   if (t == 0) {
-    for (int i = 0; i < NS_G; ++i) { tc::mbar_init(&S.go_full[i], 1); tc::mbar_init(&S.go_empty[i], 8); }
-    for (int i = 0; i < NS_R; ++i) { tc::mbar_init(&S.dr_full[i], 1); tc::mbar_init(&S.dr_empty[i], 8); }
-    tc::mbar_init(&S.ops_full, 8);
+    for (int i = 0; i < NS_G; ++i) { tc::mbar_init(&S.go_full[i], 1); tc::mbar_init(&S.go_empty[i], NBW); }
+    for (int i = 0; i < NS_R; ++i) { tc::mbar_init(&S.dr_full[i], 1); tc::mbar_init(&S.dr_empty[i], NBW); }
+    tc::mbar_init(&S.ops_full, NBW);
     tc::mbar_init(&S.ops_free, 1);
-    for (int i = 0; i < 2; ++i) { tc::mbar_init(&S.d1_full[i], 1); tc::mbar_init(&S.d1_empty[i], 8); }
+    for (int i = 0; i < 2; ++i) { tc::mbar_init(&S.d1_full[i], 1); tc::mbar_init(&S.d1_empty[i], NBW); }
     tc::fence_mbar_init();
     tma::prefetch_map(&tm_go);
     tma::prefetch_map(&tm_data);
@@ -115,7 +127,9 @@ meta_ws_params_kernel(const __grid_constant__ CUtensorMap tm_go, const __grid_co
           if (k % 3 == 0) {
             const int hh = h + k / 3 - 1;
             const uint32_t s = gr % NS_R, ph = (gr / NS_R) & 1;
+            const long long ta = tick();
             tc::mbar_wait(&S.dr_empty[s], ph ^ 1);
+            q1 += tick() - ta;
             if (hh >= 0 && hh < H) {
               tc::mbar_arrive_expect_tx(&S.dr_full[s], DROW_BYTES);
               tma::load_3d(S.drow[s], &tm_data, &S.dr_full[s], bs, hh, b * C);
@@ -125,11 +139,14 @@ meta_ws_params_kernel(const __grid_constant__ CUtensorMap tm_go, const __grid_co
             ++gr;
           }
           const uint32_t s = gg % NS_G, ph = (gg / NS_G) & 1;
+          const long long tb = tick();
           tc::mbar_wait(&S.go_empty[s], ph ^ 1);
+          q0 += tick() - tb;
           tc::mbar_arrive_expect_tx(&S.go_full[s], GO_BYTES);
           tma::load_4d(S.go[s], &tm_go, &S.go_full[s], w0px, h, k, b * C);
         }
       }
+      if (prof) { prof[blockIdx.x * 16 + 0] = tick() - t_begin; prof[blockIdx.x * 16 + 1] = q0; prof[blockIdx.x * 16 + 2] = q1; }
     }
     __syncwarp();
   } else if (warp == 1) {
@@ -150,8 +167,12 @@ meta_ws_params_kernel(const __grid_constant__ CUtensorMap tm_go, const __grid_co
 #pragma unroll 1
         for (int k = 0; k < 9; ++k, ++g) {
           const uint32_t s1 = g & 1, ph1 = (g >> 1) & 1;
+          const long long ta = tick();
           tc::mbar_wait(&S.ops_full, g & 1);
+          const long long tb = tick();
           tc::mbar_wait(&S.d1_empty[s1], ph1 ^ 1);
+          q0 += tb - ta;
+          q1 += tick() - tb;
           tc::tc_fence_after();
           if (leader) {
             // G1: D1[px][j] = gw[px][c] . W1T[j][c]^T ; split-bf16 terms (hi,hi) (lo,hi) (hi,lo), 4 K slices each
@@ -174,16 +195,21 @@ meta_ws_params_kernel(const __grid_constant__ CUtensorMap tm_go, const __grid_co
           __syncwarp();
         }
       }
+      if (prof && lane == 0) { prof[blockIdx.x * 16 + 3] = tick() - t_begin; prof[blockIdx.x * 16 + 4] = q0; prof[blockIdx.x * 16 + 5] = q1; }
     }
   } else {
-    // ===== builders: 8 warps = 2 threads per pixel (TMEM lane); thread `hf` owns hidden units
-    // [16hf, 16hf+16) and channels [32hf, 32hf+32) of its pixel =====
-    const int bt = t - 64;                 // 0..255
-    const int hf = (warp - 2) >> 2;        // which half of the per-pixel work
+    // ===== builders: TPP threads per pixel (TMEM lane); thread `hf` of a pixel owns hidden units
+    // [HJ*hf, HJ*hf + HJ) and channels [CPT*hf, CPT*hf + CPT).  They are the critical resource (the producer
+    // and MMA warps spin on builder-signalled barriers), and with 2 warps per scheduler they ran at IPC 0.4:
+    // four threads per pixel = 4 warps per scheduler to hide the shared-memory / dependency latencies. =====
+    const int bt = t - 64;                 // 0..NBUILD-1
+    const int hf = (warp - 2) >> 2;        // which part of the per-pixel work
     const int q4 = warp & 3;               // TMEM lane quadrant of this warp
     const int px = q4 * 32 + lane;
     const uint32_t lane_sel = (uint32_t)(q4 * 32) << 16;
-    constexpr int HJ = HID / 2;            // hidden units per thread
+    constexpr int HJ = HID / TPP;          // hidden units per thread (8)
+    constexpr int CPT = C / TPP;           // channels per thread (16)
+    constexpr int NCQ = CPT / 8;           // 16-byte operand chunks of gw per thread and part (2)
     constexpr int CS_PER_THREAD = (3 * CCH * ROW + NBUILD - 1) / NBUILD;
     float acc0[HJ][4];  // gW0[j][d], d == 3 -> gb0[j], for j = 16hf + jj
 #pragma unroll
@@ -197,11 +223,14 @@ meta_ws_params_kernel(const __grid_constant__ CUtensorMap tm_go, const __grid_co
 
     auto consume_d1 = [&](uint32_t gp, uint32_t mask, const float* rel) {
       const uint32_t s1 = gp & 1, ph1 = (gp >> 1) & 1;
+      const long long tw = tick();
       tc::mbar_wait(&S.d1_full[s1], ph1);
+      const long long tw2 = tick();
+      q5 += tw2 - tw;
       __syncwarp();
       tc::tc_fence_after();
-      float v[16];
-      tc::tmem_ld_x16(tmem_base + lane_sel + s1 * HID + hf * HJ, v);
+      float v[HJ];
+      tc::tmem_ld_x8(tmem_base + lane_sel + s1 * HID + hf * HJ, v);
       tc::tc_fence_before();
       __syncwarp();
       if (lane == 0) tc::mbar_arrive(&S.d1_empty[s1]);
@@ -213,6 +242,7 @@ meta_ws_params_kernel(const __grid_constant__ CUtensorMap tm_go, const __grid_co
         acc0[j][2] = fmaf(gh, rel[2], acc0[j][2]);
         acc0[j][3] += gh;
       }
+      q6 += tick() - tw2;
     };
     // coordinate tile of `tile` -> registers (software prefetch: issued one tile ahead)
     auto load_coords = [&](int tile, float (&cp)[CS_PER_THREAD]) {
@@ -237,6 +267,7 @@ meta_ws_params_kernel(const __grid_constant__ CUtensorMap tm_go, const __grid_co
       const int wt = tile % tiles_w, h = (tile / tiles_w) % H;
       const int w0px = wt * TW;
       const int bs = w0px >= 4 ? w0px - 4 : 0;
+      const long long ts0 = tick();
       tma::named_bar_sync(BAR_BLD, NBUILD);  // everyone finished reading the previous coordinate tile
 #pragma unroll
       for (int i = 0; i < CS_PER_THREAD; ++i) {
@@ -245,6 +276,7 @@ meta_ws_params_kernel(const __grid_constant__ CUtensorMap tm_go, const __grid_co
       }
       tma::named_bar_sync(BAR_BLD, NBUILD);
       if (tile + (int)gridDim.x < ntiles) load_coords(tile + gridDim.x, cpre);  // in flight during this tile
+      q7 += tick() - ts0;
       const float c0 = S.cs[(1 * CCH + 0) * ROW + px + 1];
       const float c1 = S.cs[(1 * CCH + 1) * ROW + px + 1];
       const float c2 = S.cs[(1 * CCH + 2) * ROW + px + 1];
@@ -252,7 +284,8 @@ meta_ws_params_kernel(const __grid_constant__ CUtensorMap tm_go, const __grid_co
 
       for (int k = 0; k < 9; ++k, ++g) {
         const int dy = k / 3 - 1, dx = k % 3 - 1;
-        // ---- this thread's 16 hidden units of (pixel, tap), kept packed in registers
+        const long long b0t = tick();
+        // ---- this thread's hidden units of (pixel, tap), kept packed in registers
         const int ccol = px + 1 + dx, r = dy + 1;
         const float r0 = S.cs[(r * CCH + 0) * ROW + ccol] - c0;
         const float r1 = S.cs[(r * CCH + 1) * ROW + ccol] - c1;
@@ -260,7 +293,7 @@ meta_ws_params_kernel(const __grid_constant__ CUtensorMap tm_go, const __grid_co
         uint32_t hhi[HJ / 2], hlo[HJ / 2], mask = 0;
 #pragma unroll
         for (int jp = 0; jp < HJ / 2; ++jp) {
-          float hh[2], hl[2];
+          float hv[2];
 #pragma unroll
           for (int u = 0; u < 2; ++u) {
             const float4 wv = S.w0b[hf * HJ + jp * 2 + u];
@@ -268,41 +301,36 @@ meta_ws_params_kernel(const __grid_constant__ CUtensorMap tm_go, const __grid_co
             z = fmaf(wv.x, r0, z);
             z = fmaf(wv.y, r1, z);
             z = fmaf(wv.z, r2, z);
-            const float hv = fmaxf(z, 0.f);
-            mask |= (hv > 0.f ? 1u : 0u) << (jp * 2 + u);
-            tc::split_bf16(hv, hh[u], hl[u]);
+            hv[u] = fmaxf(z, 0.f);
+            mask |= (hv[u] > 0.f ? 1u : 0u) << (jp * 2 + u);
           }
-          hhi[jp] = tc::pack_bf16x2(hh[0], hh[1]);
-          hlo[jp] = tc::pack_bf16x2(hl[0], hl[1]);
+          tc::split_pack_bf16x2(hv[0], hv[1], hhi[jp], hlo[jp]);
         }
         // ---- inputs of this tap
         const uint32_t sg = g % NS_G, phg = (g / NS_G) & 1;
         const uint32_t sr = gr % NS_R, phr = (gr / NS_R) & 1;
+        const long long b1t = tick();
         tc::mbar_wait(&S.go_full[sg], phg);
         if (dx == -1) tc::mbar_wait(&S.dr_full[sr], phr);
+        const long long b2t = tick();
         const int col = w0px + px + dx - bs;
         const bool ok = px_ok && (h + dy >= 0) && (h + dy < H) && col >= 0;
         const float* gt = S.go[sg] + px;
         const float* dt = S.drow[sr] + (ok ? col : 0);
         // products first (registers), so the shared-memory loads are not serialised behind the stores
-        uint32_t ghi[4][4], glo[4][4];
+        uint32_t ghi[NCQ][4], glo[NCQ][4];
 #pragma unroll
-        for (int cq = 0; cq < 4; ++cq) {  // 8 channels per 16-byte chunk; this thread: chunks 4hf .. 4hf+3
+        for (int cq = 0; cq < NCQ; ++cq) {  // 8 channels per 16-byte chunk; this thread: chunks NCQ*hf ..
           float gv[8], dv[8];
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
-            const int c = (hf * 4 + cq) * 8 + i;
+            const int c = (hf * NCQ + cq) * 8 + i;
             gv[i] = gt[c * TW];
             dv[i] = ok ? dt[c * DTW] : 0.f;
           }
 #pragma unroll
-          for (int p = 0; p < 4; ++p) {
-            float h0, l0, h1, l1;
-            tc::split_bf16(gv[2 * p] * dv[2 * p], h0, l0);
-            tc::split_bf16(gv[2 * p + 1] * dv[2 * p + 1], h1, l1);
-            ghi[cq][p] = tc::pack_bf16x2(h0, h1);
-            glo[cq][p] = tc::pack_bf16x2(l0, l1);
-          }
+          for (int p = 0; p < 4; ++p)
+            tc::split_pack_bf16x2(gv[2 * p] * dv[2 * p], gv[2 * p + 1] * dv[2 * p + 1], ghi[cq][p], glo[cq][p]);
         }
         __syncwarp();
         if (lane == 0) {  // input tiles fully read by this warp
@@ -311,24 +339,30 @@ meta_ws_params_kernel(const __grid_constant__ CUtensorMap tm_go, const __grid_co
         }
         if (dx == 1) ++gr;
         // ---- operand tiles may be overwritten once the previous tap's MMAs have read them
+        const long long b3t = tick();
         tc::mbar_wait(&S.ops_free, (g & 1) ^ 1);
+        const long long b4t = tick();
 #pragma unroll
-        for (int q = 0; q < 2; ++q) {  // h chunks: hi 2hf, 2hf+1 ; lo 4+2hf, 4+2hf+1
-          *reinterpret_cast<uint4*>(S.h + (hf * 2 + q) * CHUNK + px * 16) =
+        for (int q = 0; q < HJ / 8; ++q) {  // h chunks of 8 hidden units: hi at [0,4), lo at [4,8)
+          *reinterpret_cast<uint4*>(S.h + (hf * (HJ / 8) + q) * CHUNK + px * 16) =
               make_uint4(hhi[q * 4 + 0], hhi[q * 4 + 1], hhi[q * 4 + 2], hhi[q * 4 + 3]);
-          *reinterpret_cast<uint4*>(S.h + (4 + hf * 2 + q) * CHUNK + px * 16) =
+          *reinterpret_cast<uint4*>(S.h + (4 + hf * (HJ / 8) + q) * CHUNK + px * 16) =
               make_uint4(hlo[q * 4 + 0], hlo[q * 4 + 1], hlo[q * 4 + 2], hlo[q * 4 + 3]);
         }
 #pragma unroll
-        for (int cq = 0; cq < 4; ++cq) {
-          *reinterpret_cast<uint4*>(S.gw + (hf * 4 + cq) * CHUNK + px * 16) =
+        for (int cq = 0; cq < NCQ; ++cq) {  // gw chunks of 8 channels: hi at [0,8), lo at [8,16)
+          *reinterpret_cast<uint4*>(S.gw + (hf * NCQ + cq) * CHUNK + px * 16) =
               make_uint4(ghi[cq][0], ghi[cq][1], ghi[cq][2], ghi[cq][3]);
-          *reinterpret_cast<uint4*>(S.gw + (8 + hf * 4 + cq) * CHUNK + px * 16) =
+          *reinterpret_cast<uint4*>(S.gw + (8 + hf * NCQ + cq) * CHUNK + px * 16) =
               make_uint4(glo[cq][0], glo[cq][1], glo[cq][2], glo[cq][3]);
         }
         tc::fence_proxy_async_smem();
         __syncwarp();
         if (lane == 0) tc::mbar_arrive(&S.ops_full);
+        {
+          const long long b5t = tick();
+          q0 += b1t - b0t; q1 += b2t - b1t; q2 += b3t - b2t; q3 += b4t - b3t; q4c += b5t - b4t;
+        }
         // ---- consume the previous tap's D1 while this tap's MMAs run
         if (have_prev) consume_d1(prev_g, prev_mask, prev_rel);
         have_prev = true;
@@ -339,6 +373,10 @@ meta_ws_params_kernel(const __grid_constant__ CUtensorMap tm_go, const __grid_co
     }
     if (have_prev) consume_d1(prev_g, prev_mask, prev_rel);
     const uint32_t g_total = g;
+    if (prof && bt == 0) {
+      long long* pr = prof + blockIdx.x * 16;
+      pr[6] = tick() - t_begin; pr[7] = q0; pr[8] = q1; pr[9] = q2; pr[10] = q3; pr[11] = q4c; pr[12] = q5; pr[13] = q6; pr[14] = q7;
+    }
 
     // ---- CTA result: gW0/gb0 from registers (cross-thread sum through smem), gW1/gb1 from TMEM D2
     tma::named_bar_sync(BAR_BLD, NBUILD);              // all builders finished with go / drow tiles
@@ -417,9 +455,32 @@ int rd_meta_kernel_bwd_params_ws(const float* grad_out, const float* data, const
     RD_CUDA(cudaFuncSetAttribute(meta_ws_params_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr = true;
   }
+  static const bool want_prof = [] { const char* e = getenv("RD_MK_PROF"); return e && e[0] == '1'; }();
+  long long* d_prof = nullptr;
+  if (want_prof) {
+    static long long* buf = nullptr;
+    if (!buf) RD_CUDA(cudaMalloc(&buf, 1024 * 16 * sizeof(long long)));
+    RD_CUDA(cudaMemsetAsync(buf, 0, 1024 * 16 * sizeof(long long), stream));
+    d_prof = buf;
+  }
   meta_ws_params_kernel<<<(unsigned)grid, NTHREADS, smem, stream>>>(tm_go, tm_data, coord, w0, b0, w1, partial, B, H, W,
-                                                                     tiles_w, (int)ntiles);
+                                                                     tiles_w, (int)ntiles, d_prof);
   rd::count_launch();
+  if (want_prof) {  // diagnostic: synchronous, mean cycles per TAP and role
+    RD_CUDA(cudaStreamSynchronize(stream));
+    static long long hbuf[1024 * 16];
+    RD_CUDA(cudaMemcpy(hbuf, d_prof, sizeof(long long) * 16 * grid, cudaMemcpyDeviceToHost));
+    double m[16] = {0};
+    for (int b = 0; b < grid; ++b)
+      for (int k = 0; k < 16; ++k) m[k] += (double)hbuf[b * 16 + k] / grid;
+    const double tp = 9.0 * (double)ntiles / grid;
+    fprintf(stderr,
+            "[rd_meta prof bwd_params] taps/cta=%.0f | per tap: producer %.0f (wait go_empty %.0f, dr_empty %.0f) | mma %.0f (wait "
+            "ops_full %.0f, d1_empty %.0f) | builder %.0f (hidden %.0f, wait inputs %.0f, products %.0f, wait ops_free %.0f, "
+            "stores %.0f, wait d1_full %.0f, D1 use %.0f, coord staging %.0f)\n",
+            tp, m[0] / tp, m[1] / tp, m[2] / tp, m[3] / tp, m[4] / tp, m[5] / tp, m[6] / tp, m[7] / tp, m[8] / tp, m[9] / tp,
+            m[10] / tp, m[11] / tp, m[12] / tp, m[13] / tp, m[14] / tp);
+  }
   *nparts = (int)grid;
   return rd::check_launch("rd_meta_kernel_bwd_params(impl 3)");
 }

@@ -159,6 +159,18 @@ __device__ __forceinline__ void tmem_ld_x16(uint32_t taddr, float (&v)[16]) {
   for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
 }
 
+__device__ __forceinline__ void tmem_ld_x8(uint32_t taddr, float (&v)[8]) {
+  uint32_t r[8];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+      : "r"(taddr)
+      : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[i]);
+}
+
 // ---- bf16 helpers ------------------------------------------------------------------------------
 // two floats -> packed bf16x2 (a in the low half = lower address)
 __device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
@@ -169,6 +181,14 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
 __device__ __forceinline__ void split_bf16(float x, float& hi, float& lo) {
   hi = __bfloat162float(__float2bfloat16_rn(x));
   lo = x - hi;  // exact in fp32; rounded to bf16 when packed
+}
+
+// two values at once: x = hi + lo per element, hi pair and lo pair packed as bf16x2 (6 instructions per
+// pair: one packed convert, two re-expansions, two subtractions, one packed convert)
+__device__ __forceinline__ void split_pack_bf16x2(float x0, float x1, uint32_t& hi, uint32_t& lo) {
+  hi = pack_bf16x2(x0, x1);
+  const float h0 = __uint_as_float(hi << 16), h1 = __uint_as_float(hi & 0xffff0000u);
+  lo = pack_bf16x2(x0 - h0, x1 - h1);
 }
 
 }  // namespace tc
