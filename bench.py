@@ -245,7 +245,7 @@ def run_ours(args, rank, local_rank, world):
     try:
         tr = json.load(open(os.path.join(ROOT, "profiles", "r01_dram_traffic.json")))
         if tr.get("workload") == [B, C, H, W_PAD]:
-            pat = {"meta_fwd": "meta_ws_kernel<0>", "meta_bwd_data": "meta_ws_kernel<1>",
+            pat = {"meta_fwd": "meta_ws_kernel<0,", "meta_bwd_data": "meta_ws_kernel<1,",
                    "meta_bwd_params": "meta_ws_params_kernel"}[dom]
             for name, v in tr["kernels"].items():
                 if pat in name.replace(" ", ""):

@@ -62,7 +62,7 @@ struct Smem {
 //         (dla_backbone.py:92-94): y = relu(out * scale + shift) written as haloed NHWC bf16 with
 //         TAP-MAJOR channels (k*64 + c) -- the aggregation 1x1 conv's weight is permuted to match --
 //         so each tap is one 64-channel x 128-pixel 128B-swizzled TMA store.
-template <int MODE>
+template <int MODE, bool PROF>
 __global__ void __launch_bounds__(NTHREADS, 1)
 meta_ws_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant__ CUtensorMap tm_out,
                const float* __restrict__ coord, const float* __restrict__ w0, const float* __restrict__ b0,
@@ -73,7 +73,7 @@ meta_ws_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant_
   // 0 producer total, 1 wait d_empty | 2 builders total, 3 wait a_empty, 4 coordinate staging |
   // 5 MMA total, 6 wait a_full, 7 wait t_empty | 8 epilogue total, 9 wait t_full, 10 wait d_full,
   // 11 wait store-read + barrier, 12 body, 13 second barrier + store issue
-  auto tick = [&]() -> long long { return prof ? clock64() : 0ll; };
+  auto tick = [&]() -> long long { return PROF ? clock64() : 0ll; };
   long long pa = 0, pb = 0, pc = 0, pd = 0, pe = 0;
   const long long t_begin = tick();
   extern __shared__ unsigned char smem_raw[];
@@ -153,7 +153,7 @@ meta_ws_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant_
           }
         }
       }
-      if (prof) { prof[blockIdx.x * 16 + 0] = tick() - t_begin; prof[blockIdx.x * 16 + 1] = pa; }
+      if (PROF) { prof[blockIdx.x * 16 + 0] = tick() - t_begin; prof[blockIdx.x * 16 + 1] = pa; }
     }
     __syncwarp();
   } else if (warp == 1) {
@@ -201,7 +201,7 @@ meta_ws_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant_
           if (++st == NS_T) { st = 0; pht ^= 1; }
         }
       }
-      if (prof && lane == 0) {
+      if (PROF && lane == 0) {
         prof[blockIdx.x * 16 + 5] = tick() - t_begin;
         prof[blockIdx.x * 16 + 6] = pa;
         prof[blockIdx.x * 16 + 7] = pb;
@@ -284,7 +284,7 @@ meta_ws_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant_
         if (lane == 0) tc::mbar_arrive(&S.a_full[sa]);
       }
     }
-    if (prof && ht == 0) {
+    if (PROF && ht == 0) {
       prof[blockIdx.x * 16 + 2] = tick() - t_begin;
       prof[blockIdx.x * 16 + 3] = pa;
       prof[blockIdx.x * 16 + 4] = pb;
@@ -437,7 +437,7 @@ meta_ws_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant_
       }
     }
     if (leader) tma::store_wait_all<0>();
-    if (prof && leader) {
+    if (PROF && leader) {
       prof[blockIdx.x * 16 + 8] = tick() - t_begin;
       prof[blockIdx.x * 16 + 9] = pa;
       prof[blockIdx.x * 16 + 10] = pb;
@@ -503,33 +503,30 @@ inline int launch(int mode, const float* tap_src, void* dst, const float* coord,
     RD_CUDA(cudaMemsetAsync(buf, 0, 1024 * 16 * sizeof(long long), stream));
     d_prof = buf;
   }
-  if (mode == 0) {
-    static bool attr0 = false;
-    if (!attr0) {
-      RD_CUDA(cudaFuncSetAttribute(meta_ws_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      attr0 = true;
-    }
-    meta_ws_kernel<0><<<(unsigned)grid, NTHREADS, smem, stream>>>(tm_in, tm_out, coord, w0, b0, w1, b1, nullptr, nullptr, 0,
-                                                                  B, H, W, tiles_w, (int)ntiles, d_prof);
-  } else if (mode == 2) {
-    static bool attr2 = false;
-    if (!attr2) {
-      RD_CUDA(cudaFuncSetAttribute(meta_ws_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      attr2 = true;
-    }
-    meta_ws_kernel<2><<<(unsigned)grid, NTHREADS, smem, stream>>>(tm_in, tm_out, coord, w0, b0, w1, b1, ep_scale, ep_shift,
-                                                                  ep_relu, B, H, W, tiles_w, (int)ntiles, d_prof);
-  } else {
-    static bool attr1 = false;
-    if (!attr1) {
-      RD_CUDA(cudaFuncSetAttribute(meta_ws_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      attr1 = true;
-    }
-    meta_ws_kernel<1><<<(unsigned)grid, NTHREADS, smem, stream>>>(tm_in, tm_out, coord, w0, b0, w1, b1, nullptr, nullptr, 0,
-                                                                  B, H, W, tiles_w, (int)ntiles, d_prof);
+  static bool attr = false;
+  if (!attr) {
+    RD_CUDA(cudaFuncSetAttribute(meta_ws_kernel<0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    RD_CUDA(cudaFuncSetAttribute(meta_ws_kernel<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    RD_CUDA(cudaFuncSetAttribute(meta_ws_kernel<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    RD_CUDA(cudaFuncSetAttribute(meta_ws_kernel<0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    RD_CUDA(cudaFuncSetAttribute(meta_ws_kernel<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr = true;
   }
+#define RD_MKWS_LAUNCH(M, PR, SC, SH, RELU)                                                                              \
+  meta_ws_kernel<M, PR><<<(unsigned)grid, NTHREADS, smem, stream>>>(tm_in, tm_out, coord, w0, b0, w1, b1, SC, SH, RELU, B, H, \
+                                                                    W, tiles_w, (int)ntiles, d_prof)
+  if (mode == 0) {
+    if (want_prof) RD_MKWS_LAUNCH(0, true, nullptr, nullptr, 0);
+    else RD_MKWS_LAUNCH(0, false, nullptr, nullptr, 0);
+  } else if (mode == 2) {
+    RD_MKWS_LAUNCH(2, false, ep_scale, ep_shift, ep_relu);
+  } else {
+    if (want_prof) RD_MKWS_LAUNCH(1, true, nullptr, nullptr, 0);
+    else RD_MKWS_LAUNCH(1, false, nullptr, nullptr, 0);
+  }
+#undef RD_MKWS_LAUNCH
   rd::count_launch();
-  if (want_prof) {  // diagnostic: synchronous, prints mean cycles per tile and role
+  if (want_prof && mode != 2) {  // diagnostic: synchronous, prints mean cycles per tile and role
     RD_CUDA(cudaStreamSynchronize(stream));
     static long long hbuf[1024 * 16];
     RD_CUDA(cudaMemcpy(hbuf, d_prof, sizeof(long long) * 16 * grid, cudaMemcpyDeviceToHost));

@@ -56,6 +56,9 @@ struct Smem {
   uint32_t tmem_slot;
 };
 
+// PROF: diagnostic instantiation (RD_MK_PROF=1).  It must be a template parameter: with 576 threads the
+// register cap is 96, and the eight 64-bit cycle counters of a runtime switch spilled (0.57 -> 0.80 ms).
+template <bool PROF>
 __global__ void __launch_bounds__(NTHREADS, 1)
 meta_ws_params_kernel(const __grid_constant__ CUtensorMap tm_go, const __grid_constant__ CUtensorMap tm_data,
                       const float* __restrict__ coord, const float* __restrict__ w0, const float* __restrict__ b0,
@@ -65,7 +68,7 @@ meta_ws_params_kernel(const __grid_constant__ CUtensorMap tm_go, const __grid_co
   // 1 wait go_empty, 2 wait dr_empty | 3 MMA total, 4 wait ops_full, 5 wait d1_empty | 6 builder total,
   // 7 hidden layer, 8 wait go_full/dr_full, 9 products, 10 wait ops_free, 11 operand stores, 12 wait d1_full,
   // 13 D1 consumption, 14 coordinate staging
-  auto tick = [&]() -> long long { return prof ? clock64() : 0ll; };
+  auto tick = [&]() -> long long { return PROF ? clock64() : 0ll; };
   long long q0 = 0, q1 = 0, q2 = 0, q3 = 0, q4c = 0, q5 = 0, q6 = 0, q7 = 0;
   const long long t_begin = tick();
   extern __shared__ unsigned char smem_raw[];
@@ -146,7 +149,7 @@ meta_ws_params_kernel(const __grid_constant__ CUtensorMap tm_go, const __grid_co
           tma::load_4d(S.go[s], &tm_go, &S.go_full[s], w0px, h, k, b * C);
         }
       }
-      if (prof) { prof[blockIdx.x * 16 + 0] = tick() - t_begin; prof[blockIdx.x * 16 + 1] = q0; prof[blockIdx.x * 16 + 2] = q1; }
+      if (PROF) { prof[blockIdx.x * 16 + 0] = tick() - t_begin; prof[blockIdx.x * 16 + 1] = q0; prof[blockIdx.x * 16 + 2] = q1; }
     }
     __syncwarp();
   } else if (warp == 1) {
@@ -195,7 +198,7 @@ meta_ws_params_kernel(const __grid_constant__ CUtensorMap tm_go, const __grid_co
           __syncwarp();
         }
       }
-      if (prof && lane == 0) { prof[blockIdx.x * 16 + 3] = tick() - t_begin; prof[blockIdx.x * 16 + 4] = q0; prof[blockIdx.x * 16 + 5] = q1; }
+      if (PROF && lane == 0) { prof[blockIdx.x * 16 + 3] = tick() - t_begin; prof[blockIdx.x * 16 + 4] = q0; prof[blockIdx.x * 16 + 5] = q1; }
     }
   } else {
     // ===== builders: TPP threads per pixel (TMEM lane); thread `hf` of a pixel owns hidden units
@@ -373,7 +376,7 @@ meta_ws_params_kernel(const __grid_constant__ CUtensorMap tm_go, const __grid_co
     }
     if (have_prev) consume_d1(prev_g, prev_mask, prev_rel);
     const uint32_t g_total = g;
-    if (prof && bt == 0) {
+    if (PROF && bt == 0) {
       long long* pr = prof + blockIdx.x * 16;
       pr[6] = tick() - t_begin; pr[7] = q0; pr[8] = q1; pr[9] = q2; pr[10] = q3; pr[11] = q4c; pr[12] = q5; pr[13] = q6; pr[14] = q7;
     }
@@ -452,7 +455,8 @@ int rd_meta_kernel_bwd_params_ws(const float* grad_out, const float* data, const
   const int64_t grid = ntiles < sms ? ntiles : sms;
   static bool attr = false;
   if (!attr) {
-    RD_CUDA(cudaFuncSetAttribute(meta_ws_params_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    RD_CUDA(cudaFuncSetAttribute(meta_ws_params_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    RD_CUDA(cudaFuncSetAttribute(meta_ws_params_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr = true;
   }
   static const bool want_prof = [] { const char* e = getenv("RD_MK_PROF"); return e && e[0] == '1'; }();
@@ -463,8 +467,12 @@ int rd_meta_kernel_bwd_params_ws(const float* grad_out, const float* data, const
     RD_CUDA(cudaMemsetAsync(buf, 0, 1024 * 16 * sizeof(long long), stream));
     d_prof = buf;
   }
-  meta_ws_params_kernel<<<(unsigned)grid, NTHREADS, smem, stream>>>(tm_go, tm_data, coord, w0, b0, w1, partial, B, H, W,
-                                                                     tiles_w, (int)ntiles, d_prof);
+  if (want_prof)
+    meta_ws_params_kernel<true><<<(unsigned)grid, NTHREADS, smem, stream>>>(tm_go, tm_data, coord, w0, b0, w1, partial, B, H,
+                                                                             W, tiles_w, (int)ntiles, d_prof);
+  else
+    meta_ws_params_kernel<false><<<(unsigned)grid, NTHREADS, smem, stream>>>(tm_go, tm_data, coord, w0, b0, w1, partial, B,
+                                                                              H, W, tiles_w, (int)ntiles, nullptr);
   rd::count_launch();
   if (want_prof) {  // diagnostic: synchronous, mean cycles per TAP and role
     RD_CUDA(cudaStreamSynchronize(stream));
