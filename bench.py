@@ -272,29 +272,27 @@ def run_ours(args, rank, local_rank, world):
         h2d = (h_data.numel() + h_coord.numel() + h_go.numel()) * 4
         d2h = (h_out.numel() + h_gd.numel() + h_gp.numel()) * 4
 
+        pipe = ops.MetaKernelHostPipeline(C, H, W_PAD, dev, impl=impl)
+
         def e2e_step():
-            d_ = h_data.to(dev, non_blocking=True)
-            c_ = h_coord.to(dev, non_blocking=True)
-            g_ = h_go.to(dev, non_blocking=True)
-            o_ = ops.meta_kernel_forward(d_, c_, w0, b0, w1, b1, impl=impl)
-            gd_, a_, b__, c__, d__ = ops.meta_kernel_backward(g_, d_, c_, w0, b0, w1, b1, impl=impl)
-            if world > 1:
-                torch.cat([a_.reshape(-1), b__, c__.reshape(-1), d__], out=flat_grads)
+            # the public host-buffer call: per-frame upload / fwd+bwd / download pipeline on three streams
+            pipe(h_data, h_coord, h_go, w0, b0, w1, b1, h_out, h_gd, h_gp)
+            if world > 1:  # data-parallel exchange of the (already summed) parameter gradients
+                pipe.wait()
+                flat_grads.copy_(pipe.gp_sum)
                 dist.all_reduce(flat_grads, op=dist.ReduceOp.SUM)
                 flat_grads.div_(world)
-            else:
-                torch.cat([a_.reshape(-1), b__, c__.reshape(-1), d__], out=flat_grads)
-            h_out.copy_(o_, non_blocking=True)
-            h_gd.copy_(gd_, non_blocking=True)
-            h_gp.copy_(flat_grads, non_blocking=True)
+                h_gp.copy_(flat_grads, non_blocking=True)
 
-        e2e_steps = max(2, min(args.steps, 5))
+        e2e_steps = max(2, min(args.steps, 8))
         e2e_step()
+        pipe.wait()
         barrier()
         a, b_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         a.record()
         for _ in range(e2e_steps):
             e2e_step()
+        pipe.wait()
         b_.record()
         barrier()
         ems = a.elapsed_time(b_)
@@ -304,7 +302,8 @@ def run_ours(args, rank, local_rank, world):
             ems = float(t.item())
         e2e = {"value": B * world * e2e_steps / (ems * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d,
                "d2h_bytes_per_step": d2h, "steps": e2e_steps,
-               "note": "pinned host data/coord/grad_out -> device, fwd+bwd, out/grad_data/param grads -> pinned host"}
+               "note": "ops.MetaKernelHostPipeline: pinned host data/coord/grad_out -> device, fwd+bwd per frame, out/grad_data/param "
+                       "grads -> pinned host; uploads of frame i+1 overlap downloads of frame i (PCIe full duplex)"}
     except Exception as ex:  # report, never fake
         e2e = {"value": None, "unit": UNIT, "error": repr(ex)[:200]}
 

@@ -137,6 +137,92 @@ def meta_kernel(data, coord, w0, b0, w1, b1, impl=IMPL_DEFAULT):
     return MetaKernelFunction.apply(data, coord, w0, b0, w1, b1, impl)
 
 
+class MetaKernelHostPipeline(object):
+    """Meta-Kernel forward + backward over HOST (pinned) tensors: the call a host-side framework makes.
+
+    The op moves ~0.87 GB per frame across PCIe in EACH direction and computes for 0.3 ms, so the call is
+    a copy pipeline: frames flow through `slots` device buffers on three streams -- host->device, compute
+    (rd_meta_kernel_fwd + rd_meta_kernel_bwd per frame), device->host -- so that the uploads of frame
+    i+1 overlap the downloads of frame i (PCIe is full duplex).  Parameter gradients are summed over the
+    frames on the device, as a batched call would.  Streams keep running across calls: nothing here
+    synchronises the host; `wait()` makes the caller's stream wait for everything issued so far.
+    """
+
+    def __init__(self, C, H, W, device, slots=2, impl=IMPL_DEFAULT):
+        self.C, self.H, self.W, self.dev, self.impl, self.slots = C, H, W, torch.device(device), impl, slots
+        dev = self.dev
+        mk = lambda *shape: torch.empty(shape, device=dev, dtype=torch.float32)
+        self.d_data = [mk(1, C, H, W) for _ in range(slots)]
+        self.d_coord = [mk(1, 3, H, W) for _ in range(slots)]
+        self.d_go = [mk(1, 9 * C, H, W) for _ in range(slots)]
+        self.d_out = [mk(1, 9 * C, H, W) for _ in range(slots)]
+        self.d_gd = [mk(1, C, H, W) for _ in range(slots)]
+        self.gp = [mk(32, 3), mk(32), mk(C, 32), mk(C)]          # per-frame parameter gradients
+        self.gp_sum = mk(32 * 3 + 32 + C * 32 + C)
+        L = _lib.lib()
+        self.ws = mk((int(L.rd_meta_kernel_bwd_workspace_bytes(1, C, H, W)) + 3) // 4 + 1)
+        self.s_in, self.s_comp, self.s_out = (torch.cuda.Stream(dev) for _ in range(3))
+        self.ev_in = [torch.cuda.Event() for _ in range(slots)]      # inputs of the slot are on the device
+        self.ev_comp = [torch.cuda.Event() for _ in range(slots)]    # kernels of the slot are done
+        self.ev_out = [torch.cuda.Event() for _ in range(slots)]     # results of the slot are on the host
+        self.ev_gp = torch.cuda.Event()                              # summed parameter gradients are on the host
+        self.n = 0
+
+    def __call__(self, h_data, h_coord, h_grad_out, w0, b0, w1, b1, h_out, h_grad_data, h_grad_params):
+        """All h_* are pinned CPU tensors: data (B,C,H,W), coord (B,3,H,W), grad_out / out (B,9C,H,W),
+        grad_data (B,C,H,W), grad_params (96+32+32C+C,) = [gW0, gb0, gW1, gb1] flattened."""
+        for t in (h_data, h_coord, h_grad_out, h_out, h_grad_data, h_grad_params):
+            if t.device.type != "cpu" or not t.is_pinned():
+                raise ValueError("MetaKernelHostPipeline needs pinned host tensors")
+        L, C, H, W = _lib.lib(), self.C, self.H, self.W
+        B = h_data.shape[0]
+        cur = torch.cuda.current_stream(self.dev)
+        self.s_in.wait_stream(cur)      # the caller may just have filled / be done with the host buffers
+        self.s_comp.wait_stream(cur)    # parameters produced on the caller's stream
+        for b in range(B):
+            s = self.n % self.slots
+            self.n += 1
+            with torch.cuda.stream(self.s_in):
+                self.s_in.wait_event(self.ev_comp[s])   # kernels that last read this slot's inputs are done
+                self.d_data[s].copy_(h_data[b:b + 1], non_blocking=True)
+                self.d_coord[s].copy_(h_coord[b:b + 1], non_blocking=True)
+                self.d_go[s].copy_(h_grad_out[b:b + 1], non_blocking=True)
+                self.ev_in[s].record(self.s_in)
+            with torch.cuda.stream(self.s_comp):
+                self.s_comp.wait_event(self.ev_in[s])
+                self.s_comp.wait_event(self.ev_out[s])  # previous results of this slot have left the device
+                st = L.rd_meta_kernel_fwd(_p(self.d_data[s]), _p(self.d_coord[s]), _p(w0), _p(b0), _p(w1), _p(b1),
+                                          _p(self.d_out[s]), 1, C, H, W, int(self.impl), _stream())
+                _lib.check(st, "meta_kernel_fwd (host pipeline)")
+                st = L.rd_meta_kernel_bwd(_p(self.d_go[s]), _p(self.d_data[s]), _p(self.d_coord[s]), _p(w0), _p(b0), _p(w1),
+                                          _p(b1), _p(self.d_gd[s]), _p(self.gp[0]), _p(self.gp[1]), _p(self.gp[2]),
+                                          _p(self.gp[3]), _p(self.ws), ctypes.c_size_t(self.ws.numel() * 4), 1, C, H, W,
+                                          int(self.impl), _stream())
+                _lib.check(st, "meta_kernel_bwd (host pipeline)")
+                flat = torch.cat([g.reshape(-1) for g in self.gp])
+                if b == 0:
+                    self.s_comp.wait_event(self.ev_gp)  # the previous call's sum has been downloaded
+                    self.gp_sum.copy_(flat)
+                else:
+                    self.gp_sum.add_(flat)
+                self.ev_comp[s].record(self.s_comp)
+            with torch.cuda.stream(self.s_out):
+                self.s_out.wait_event(self.ev_comp[s])
+                h_out[b:b + 1].copy_(self.d_out[s], non_blocking=True)
+                h_grad_data[b:b + 1].copy_(self.d_gd[s], non_blocking=True)
+                if b == B - 1:
+                    h_grad_params.copy_(self.gp_sum, non_blocking=True)
+                    self.ev_gp.record(self.s_out)
+                self.ev_out[s].record(self.s_out)
+
+    def wait(self):
+        """Make the current stream wait for every copy / kernel issued so far."""
+        cur = torch.cuda.current_stream(self.dev)
+        cur.wait_stream(self.s_out)
+        cur.wait_stream(self.s_comp)
+        cur.wait_stream(self.s_in)
+
+
 # ------------------------------------------------------------------------------------------------
 # Decode3DBbox / RotatedIOU / batch_rotated_iou
 # ------------------------------------------------------------------------------------------------
