@@ -120,6 +120,20 @@ int rd_nms3d(const float* boxes, int B, int N, float iou_thres, int max_keep, in
              int32_t* keep_idx, float* boxes_out, void* workspace, size_t workspace_bytes,
              rd_stream_t stream);
 
+/* ---- get_sorted_foreground (test-time proposal selection) --------------------------------------
+ * Replaces the Python CustomOp GetSortedFGOperator.forward, operator_py/get_sorted_foreground.py:11-40
+ * (registered as 'get_sorted_foreground' :47-84; call site rangedet/symbol/head/builder.py:512-521).
+ * cls_score (B,N), bbox_delta (B,N,8), pc (B,N,3), mask (B,N) ->
+ * out_score (B,K) = the K = num_fgs largest cls_score*mask per row in descending order,
+ * out_delta (B,K,8), out_pc (B,K,3) = the rows of those points.  Equal scores keep ascending point
+ * index (stable; MXNet's tie order is unspecified).  num_fgs > N is an error (:66).  No gradient (:42-44).
+ */
+size_t rd_get_sorted_foreground_workspace_bytes(int B, int N);
+int rd_get_sorted_foreground(const float* cls_score, const float* bbox_delta, const float* pc,
+                             const float* mask, int B, int N, int num_fgs, float* out_score,
+                             float* out_delta, float* out_pc, void* workspace, size_t workspace_bytes,
+                             rd_stream_t stream);
+
 /* ---- Convolution family (DLA backbone / RPN head) -------------------------------------------
  * Replaces mx.sym.Convolution / mx.sym.Deconvolution (+ inference-form BatchNorm, ReLU, residual
  * add) as emitted by mxnext/simple.py:123-158,545-580 for rangedet/symbol/backbone/

@@ -36,6 +36,8 @@ SIGNATURES = {
     "rd_wnms_4c": (_i, [_vp, _i, _f, _f, _i, _i, _vp, _vp, ctypes.POINTER(_i), _vp, _sz, _vp]),
     "rd_nms3d_workspace_bytes": (_sz, [_i, _i]),
     "rd_nms3d": (_i, [_vp, _i, _i, _f, _i, _i, _vp, _vp, _vp, _sz, _vp]),
+    "rd_get_sorted_foreground_workspace_bytes": (_sz, [_i, _i]),
+    "rd_get_sorted_foreground": (_i, [_vp] * 4 + [_i] * 3 + [_vp] * 4 + [_sz, _vp]),
     "rd_conv2d_nhwc_bf16": (_i, [_vp] * 6 + [_i] * 8 + [_vp]),
     "rd_deconv2d_nhwc_bf16": (_i, [_vp] * 6 + [_i] * 7 + [_vp]),
     "rd_tc_probe_gemm": (_i, [_vp, _vp, _vp, _i, _i, _i, _vp]),

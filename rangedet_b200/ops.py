@@ -292,6 +292,32 @@ def wnms_4c_device(dets, thresh, thresh_vote, is_3d=False, hash_scale=100):
     return out[:k], keep[:k]
 
 
+def get_sorted_foreground(cls_score, bbox_delta, pc, mask, num_fgs):
+    """operator_py/get_sorted_foreground.py:11-40: (B,N), (B,N,8), (B,N,3), (B,N) ->
+    (sorted_fg_score (B,K), sorted_fg_bbox_delta (B,K,8), sorted_fg_pc (B,K,3)), K = num_fgs.
+    `num_fgs` may arrive as a string, as CustomOp kwargs do (:51)."""
+    num_fgs = int(num_fgs)
+    cls_score = _chk(cls_score, "cls_score", 2)
+    B, N = cls_score.shape
+    bbox_delta = _chk(bbox_delta, "bbox_delta", 3, 8)
+    pc = _chk(pc, "pc", 3, 3)
+    mask = _chk(mask, "mask", 2)
+    if tuple(bbox_delta.shape[:2]) != (B, N) or tuple(pc.shape[:2]) != (B, N) or tuple(mask.shape) != (B, N):
+        raise ValueError("get_sorted_foreground: inconsistent shapes")
+    L = _lib.lib()
+    dev = cls_score.device
+    out_s = torch.empty((B, num_fgs), device=dev)
+    out_d = torch.empty((B, num_fgs, 8), device=dev)
+    out_p = torch.empty((B, num_fgs, 3), device=dev)
+    nbytes = int(L.rd_get_sorted_foreground_workspace_bytes(B, N))
+    ws = torch.empty(max(nbytes, 4), device=dev, dtype=torch.uint8)
+    with torch.cuda.device(dev):
+        st = L.rd_get_sorted_foreground(_p(cls_score), _p(bbox_delta), _p(pc), _p(mask), B, N, num_fgs, _p(out_s), _p(out_d),
+                                        _p(out_p), _p(ws), ctypes.c_size_t(ws.numel()), _stream())
+    _lib.check(st, "get_sorted_foreground")
+    return out_s, out_d, out_p
+
+
 def nms3d(boxes, iou_thres, max_keep, normal_iou=False):
     """_contrib_NMS3D (nms_3d.cc:22-66): boxes (B,N,10) sorted by score -> (keep_idx (B,max_keep) int32 with -1
     fill, boxes_after_nms (B,max_keep,10) with 0 fill)."""

@@ -281,6 +281,34 @@ def test_meta_kernel_bwd_vs_oracle(ops, shape, impl):
         assert err < (1e-4 if impl == 1 else 2e-4), (name, err)
 
 
+@pytest.mark.parametrize("B,N,K", [(1, 297472, 50000), (3, 5000, 700), (2, 17, 17), (1, 1, 1)])
+def test_get_sorted_foreground_vs_oracle(ops, B, N, K):
+    """Bit-exact (index work): distinct scores, a 60 % zero mask (massive ties at 0 incl. -0.0 from negative
+    logits), duplicated scores."""
+    from oracle import sorted_fg_ref
+    rng = np.random.default_rng(B * 1000 + N)
+    score = rng.standard_normal((B, N)).astype(np.float32)
+    score[:, ::7] = np.round(score[:, ::7], 1)       # many exact duplicates
+    mask = (rng.random((B, N)) > 0.6).astype(np.float32)
+    delta = rng.standard_normal((B, N, 8)).astype(np.float32)
+    pc = rng.standard_normal((B, N, 3)).astype(np.float32)
+    want = sorted_fg_ref.get_sorted_foreground(score, delta, pc, mask, K)
+    got = ops.get_sorted_foreground(cu(score), cu(delta), cu(pc), cu(mask), str(K))   # kwargs arrive as strings
+    for g_, w_, name in zip(got, want, ("score", "bbox_delta", "pc")):
+        assert np.array_equal(g_.cpu().numpy(), w_), name
+    s = got[0].cpu().numpy()
+    assert (np.diff(s, axis=1) <= 0).all()           # descending
+    report(test="get_sorted_foreground", B=B, N=N, K=K, exact=True)
+
+
+def test_get_sorted_foreground_errors(ops):
+    z = lambda *s: torch.zeros(*s, device="cuda")
+    with pytest.raises(RuntimeError):
+        ops.get_sorted_foreground(z(1, 10), z(1, 10, 8), z(1, 10, 3), z(1, 10), 11)   # num_fgs > N (:66)
+    with pytest.raises(ValueError):
+        ops.get_sorted_foreground(z(1, 10), z(1, 9, 8), z(1, 10, 3), z(1, 10), 5)
+
+
 def test_meta_kernel_host_pipeline(ops):
     """Host-buffer call (pinned tensors, copy/compute pipeline) == device-resident call; twice, to cover
     slot reuse across calls."""

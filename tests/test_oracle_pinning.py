@@ -143,3 +143,20 @@ def test_meta_kernel_ref_matches_golden():
                                                      t("grad_out"))
     for got, key in zip(res, ["out", "grad_data", "grad_w0", "grad_b0", "grad_w1", "grad_b1"]):
         assert rel_err(got.numpy(), g[key]) < 1e-5, key
+
+
+def test_sorted_foreground_restatement_small_case():
+    """oracle/sorted_fg_ref.py against the reference's text worked by hand (get_sorted_foreground.py:20-37):
+    mask, top-k, descending, gather; ties keep ascending index."""
+    from oracle import sorted_fg_ref
+    score = np.array([[0.2, 0.9, -0.5, 0.9, 0.1, 0.7]], np.float32)
+    mask = np.array([[1, 1, 1, 1, 0, 1]], np.float32)
+    delta = np.arange(48, dtype=np.float32).reshape(1, 6, 8)
+    pc = np.arange(18, dtype=np.float32).reshape(1, 6, 3)
+    s, d, p = sorted_fg_ref.get_sorted_foreground(score, delta, pc, mask, "4")
+    assert s.tolist() == [[np.float32(0.9), np.float32(0.9), np.float32(0.7), np.float32(0.2)]]
+    assert d[0, :, 0].tolist() == [8.0, 24.0, 40.0, 0.0]      # points 1, 3, 5, 0
+    assert p[0, :, 0].tolist() == [3.0, 9.0, 15.0, 0.0]
+    # masked-out and negative scores rank below: a fifth pick is the masked point (score 0), then -0.5
+    s5, d5, _ = sorted_fg_ref.get_sorted_foreground(score, delta, pc, mask, 6)
+    assert d5[0, 4:, 0].tolist() == [32.0, 16.0] and s5[0, 4] == 0.0
