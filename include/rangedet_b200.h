@@ -148,6 +148,8 @@ int rd_get_sorted_foreground(const float* cls_score, const float* bbox_delta, co
  *              W-stride stride_w in {1,2} (W even); output width W / stride_w.
  * rd_deconv2d: y = relu?( deconv(x) * scale + shift ) + residual; kernel (3,kw), stride (1,kw/2),
  *              pad (1,kw/4) for kw in {8,4} (the two shapes of agg_stage); output width W * kw/2.
+ *              kw = 3: kernel (3,3), stride (1,2), pad (1,1), output width 2*W -- the data gradient of
+ *              the 3x3 W-stride-2 convolutions (weights [ky*3+kx][Cin_of_conv][Cout_of_conv], no flip).
  * Cin: multiple of 64 (<= 1024); Cout: 64 or 128.  Pad narrower layers with zero channels.
  */
 int rd_conv2d_nhwc_bf16(const void* x_pad, const void* w_packed, const float* scale, const float* shift,
@@ -156,6 +158,56 @@ int rd_conv2d_nhwc_bf16(const void* x_pad, const void* w_packed, const float* sc
 int rd_deconv2d_nhwc_bf16(const void* x_pad, const void* w_packed, const float* scale, const float* shift,
                           const void* residual_pad, void* y_pad, int N, int H, int W, int Cin, int Cout,
                           int kw, int relu, rd_stream_t stream);
+
+/* ---- Training path of the convolution family ---------------------------------------------------
+ * What the reference gets from MXNet autograd + cuDNN for every conv / BatchNorm / ReLU / add of the
+ * DLA backbone and RPN head in training (mxnext/simple.py:123-158,545-580, mxnext/complicate.py:14,
+ * 32-43; graph: rangedet/symbol/backbone/dla_backbone.py:17-127, rangedet/symbol/head/builder.py:
+ * 198-266).  The data gradient of a convolution is itself a member of the forward family
+ * (rd_conv2d / rd_deconv2d with transposed weights); the pieces below are the rest.
+ * All activation tensors: zero-haloed NHWC bf16 [N][H+2][W+2][C], interior written only.
+ *
+ * rd_conv2d_wgrad_nhwc_bf16:  G[tap][a][b] = sum_{n,h,w} A[n,h,w][a] * B[n, h+ky-pad, w*stride_w+kx-pad][b]
+ *   (tap = ky*ksize+kx, pad = ksize/2), fp32 [ksize*ksize][CA][CB] -- the packed layout of the forward
+ *   weights when A = gradient of the conv output (CA = Cout) and B = the conv input (CB = Cin).
+ *   A is at resolution (H, W), B at (H, W*stride_w).  CA in {64,128}; CB multiple of 64, <= 1024;
+ *   ksize in {1,3}; stride_w in {1,2}.  tcgen05 (both operands MN-major), deterministic.
+ */
+size_t rd_conv2d_wgrad_workspace_bytes(int N, int H, int W, int CA, int CB, int ksize, int stride_w);
+int rd_conv2d_wgrad_nhwc_bf16(const void* a_pad, const void* b_pad, float* g, int N, int H, int W, int CA,
+                              int CB, int ksize, int stride_w, void* workspace, size_t workspace_bytes,
+                              rd_stream_t stream);
+
+/* Training-mode BatchNorm (batch statistics per GPU, biased variance, eps added to the variance,
+ * moving = moving*momentum + batch*(1-momentum)) fused with ReLU and the residual adds.
+ * coef: fp32 [6][C] = a (gamma*invstd) | b (beta - mean*a) | mean | invstd | var | sum -- produced by
+ * rd_bn_train_stats, consumed by rd_bn_act_fwd / rd_bn_act_bwd.  gamma/beta NULL -> 1/0; moving_* NULL ->
+ * not updated.  Workspace: rd_bn_workspace_bytes(C) (+ 8*C floats for the backward / channel sums).
+ *   rd_bn_act_fwd : y = relu?(z*a + b + res_before) + res_after         (either residual may be NULL)
+ *   rd_bn_act_bwd : g = dy * mask; dz = a*(g - mean(g) - xhat*mean(g*xhat)); dgamma, dbeta;
+ *                   mask_mode 0: none, 1: (y_mask > 0), 2: (z*a + b > 0) recomputed (res_after layers);
+ *                   dz is written with a W halo of dz_halo_w pixels (S for the phase-grouped view a
+ *                   transposed convolution's backward reads, else 1); g_out (optional) receives g,
+ *                   the gradient that flows into res_before.
+ *   rd_channel_sums: sums[c] = sum over pixels of x (bias gradient of the un-normalised head convs)
+ *   rd_add_nhwc_bf16: y = x0 + x1 (gradient accumulation at fan-out points)
+ */
+size_t rd_bn_workspace_bytes(int C);
+int rd_bn_train_stats_nhwc_bf16(const void* z_pad, int N, int H, int W, int C, const float* gamma,
+                                const float* beta, float eps, float momentum, float* moving_mean,
+                                float* moving_var, float* coef, void* workspace, size_t workspace_bytes,
+                                rd_stream_t stream);
+int rd_bn_act_fwd_nhwc_bf16(const void* z_pad, const float* coef, const void* res_before,
+                            const void* res_after, void* y_pad, int N, int H, int W, int C, int relu,
+                            rd_stream_t stream);
+int rd_bn_act_bwd_nhwc_bf16(const void* dy_pad, const void* y_mask_pad, const void* z_pad, const float* coef,
+                            int mask_mode, void* dz_pad, int dz_halo_w, void* g_out_pad, float* dgamma,
+                            float* dbeta, int N, int H, int W, int C, void* workspace,
+                            size_t workspace_bytes, rd_stream_t stream);
+int rd_channel_sums_nhwc_bf16(const void* x_pad, int N, int H, int W, int C, float* sums, void* workspace,
+                              size_t workspace_bytes, rd_stream_t stream);
+int rd_add_nhwc_bf16(const void* x0_pad, const void* x1_pad, void* y_pad, int N, int H, int W, int C,
+                     rd_stream_t stream);
 
 /* ---- tcgen05 self-test -------------------------------------------------------------------
  * D(128 x n) = A(128 x k) . B(n x k)^T with bf16 operands staged in shared memory in the

@@ -40,6 +40,14 @@ SIGNATURES = {
     "rd_get_sorted_foreground": (_i, [_vp] * 4 + [_i] * 3 + [_vp] * 4 + [_sz, _vp]),
     "rd_conv2d_nhwc_bf16": (_i, [_vp] * 6 + [_i] * 8 + [_vp]),
     "rd_deconv2d_nhwc_bf16": (_i, [_vp] * 6 + [_i] * 7 + [_vp]),
+    "rd_conv2d_wgrad_workspace_bytes": (_sz, [_i] * 7),
+    "rd_conv2d_wgrad_nhwc_bf16": (_i, [_vp] * 3 + [_i] * 7 + [_vp, _sz, _vp]),
+    "rd_bn_workspace_bytes": (_sz, [_i]),
+    "rd_bn_train_stats_nhwc_bf16": (_i, [_vp] + [_i] * 4 + [_vp, _vp, _f, _f, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "rd_bn_act_fwd_nhwc_bf16": (_i, [_vp] * 5 + [_i] * 5 + [_vp]),
+    "rd_bn_act_bwd_nhwc_bf16": (_i, [_vp] * 4 + [_i, _vp, _i, _vp, _vp, _vp] + [_i] * 4 + [_vp, _sz, _vp]),
+    "rd_channel_sums_nhwc_bf16": (_i, [_vp] + [_i] * 4 + [_vp, _vp, _sz, _vp]),
+    "rd_add_nhwc_bf16": (_i, [_vp] * 3 + [_i] * 4 + [_vp]),
     "rd_tc_probe_gemm": (_i, [_vp, _vp, _vp, _i, _i, _i, _vp]),
     "rd_tma_probe": (_i, [_vp, _vp, _vp] + [_i] * 7 + [_vp]),
 }

@@ -1,0 +1,423 @@
+// Training-mode BatchNorm + ReLU + residual, forward and backward, over zero-haloed NHWC bf16 (sm_100a).
+//
+// Replaces what the reference gets from MXNet around every convolution of the DLA backbone / RPN head
+// in training: mx.sym.BatchNorm with batch statistics per GPU (/root/reference mxnext/complicate.py:14,
+// 32-43: eps 1e-5 + 1e-10, momentum 0.9, fix_gamma False, use_global_stats False), mx.sym.Activation
+// relu (mxnext/simple.py:49) and the elementwise add of the residual branches
+// (rangedet/symbol/backbone/dla_backbone.py:42-56 block: relu(bn2 + shortcut); :121-124 agg_stage:
+// const + relu(bn(deconv))).  All of these are HBM-bound passes over the activation: each kernel here
+// reads / writes every tensor exactly once with 16-byte accesses (8 channels per thread), per-channel
+// reductions are two-stage and deterministic (per-block partial rows, then a fixed-order sum).
+//
+//   forward :  stats(z) -> finalize (mean, var, a = gamma*invstd, b = beta - mean*a, moving stats)
+//              y = relu?(z*a + b + res_before) + res_after
+//   backward:  g = dy * [pre-activation > 0]          (mask from y, or recomputed from z when res_after)
+//              reduce  S1 = sum g, S2 = sum g*(z - mean)
+//              dz = a * (g - S1/M - (z - mean) * invstd^2 * S2/M),  dgamma = invstd*S2,  dbeta = S1
+#include <cuda_bf16.h>
+
+#include "../../include/rangedet_b200.h"
+#include "rd_common.cuh"
+
+namespace bn {
+
+constexpr int MAX_BLOCKS = 296;  // 2 per SM: partial rows of the two-stage reductions
+constexpr int NT = 256;
+
+struct Geo {
+  int N, H, W, C;
+  int nseg, seg;      // each image row is cut into nseg segments of seg pixels (work units)
+  int cgs, ppb;       // 8-channel groups per pixel, pixels per block iteration
+};
+
+__host__ __device__ inline int64_t pix_off(int n, int h, int w, int H, int W, int halo, int C) {
+  return (((int64_t)n * (H + 2) + h + 1) * (W + 2 * halo) + w + halo) * C;
+}
+
+static Geo make_geo(int N, int H, int W, int C) {
+  Geo g;
+  g.N = N; g.H = H; g.W = W; g.C = C;
+  g.cgs = C / 8;
+  g.ppb = NT / g.cgs;
+  if (g.ppb < 1) g.ppb = 1;
+  int nseg = 1;
+  while ((int64_t)N * H * nseg < 4 * MAX_BLOCKS && (W / (nseg * 2)) >= 4 * g.ppb) nseg *= 2;
+  g.nseg = nseg;
+  g.seg = (W + nseg - 1) / nseg;
+  return g;
+}
+
+__device__ __forceinline__ void unpack8(const uint4& v, float (&f)[8]) {
+  const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    f[2 * i] = __uint_as_float(w[i] << 16);
+    f[2 * i + 1] = __uint_as_float(w[i] & 0xffff0000u);
+  }
+}
+__device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
+  uint32_t w[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    __nv_bfloat162 p = __floats2bfloat162_rn(f[2 * i], f[2 * i + 1]);
+    w[i] = *reinterpret_cast<uint32_t*>(&p);
+  }
+  return make_uint4(w[0], w[1], w[2], w[3]);
+}
+
+// Block-level sum of 16 per-thread values over the threads that share a channel group; one partial row
+// [2][C] per block: row[which*C + channel].
+__device__ __forceinline__ void block_reduce_store(const float (&s)[8], const float (&q)[8], const Geo& G,
+                                                   float* __restrict__ partial_row) {
+  __shared__ float red[NT * 16];
+  const int t = threadIdx.x;
+  const int cg = t % G.cgs, pl = t / G.cgs;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    red[(pl * G.cgs + cg) * 16 + i] = s[i];
+    red[(pl * G.cgs + cg) * 16 + 8 + i] = q[i];
+  }
+  __syncthreads();
+  const int nval = G.cgs * 16;  // = 2C
+  for (int v = t; v < nval; v += blockDim.x) {
+    float a = 0.f;
+    for (int p = 0; p < G.ppb; ++p) a += red[p * nval + v];
+    const int cgi = v / 16, i = v % 16;
+    partial_row[(i / 8) * G.C + cgi * 8 + (i % 8)] = a;
+  }
+}
+
+// ---- forward statistics: partial[block][2][C] = (sum z, sum z^2) ---------------------------------
+__global__ void __launch_bounds__(NT) stats_kernel(const __nv_bfloat16* __restrict__ z, Geo G, int halo,
+                                                   float* __restrict__ partial) {
+  const int t = threadIdx.x, cg = t % G.cgs, pl = t / G.cgs;
+  float s[8], q[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) s[i] = q[i] = 0.f;
+  const int nunits = G.N * G.H * G.nseg;
+  for (int u = blockIdx.x; u < nunits; u += gridDim.x) {
+    const int sg = u % G.nseg, row = u / G.nseg, h = row % G.H, n = row / G.H;
+    const int w0 = sg * G.seg, w1 = min(G.W, w0 + G.seg);
+    const __nv_bfloat16* base = z + pix_off(n, h, 0, G.H, G.W, halo, G.C) + cg * 8;
+    for (int w = w0 + pl; w < w1; w += G.ppb) {
+      float f[8];
+      unpack8(__ldg(reinterpret_cast<const uint4*>(base + (int64_t)w * G.C)), f);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) { s[i] += f[i]; q[i] = fmaf(f[i], f[i], q[i]); }
+    }
+  }
+  block_reduce_store(s, q, G, partial + (int64_t)blockIdx.x * 2 * G.C);
+}
+
+// coef layout (fp32, 6 x C): a | b | mean | invstd | batch var (biased) | spare
+__global__ void fwd_finalize_kernel(const float* __restrict__ partial, int nblocks, int C, double count,
+                                    const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
+                                    float momentum, float* __restrict__ moving_mean,
+                                    float* __restrict__ moving_var, float* __restrict__ coef) {
+  for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < C; c += gridDim.x * blockDim.x) {
+    double s = 0.0, q = 0.0;
+    for (int b = 0; b < nblocks; ++b) {
+      s += (double)partial[(int64_t)b * 2 * C + c];
+      q += (double)partial[(int64_t)b * 2 * C + C + c];
+    }
+    const double mean = s / count;
+    double var = q / count - mean * mean;
+    if (var < 0.0) var = 0.0;
+    const float invstd = (float)(1.0 / sqrt(var + (double)eps));
+    const float g = gamma ? gamma[c] : 1.f, be = beta ? beta[c] : 0.f;
+    const float a = g * invstd;
+    coef[c] = a;
+    coef[C + c] = be - (float)mean * a;
+    coef[2 * C + c] = (float)mean;
+    coef[3 * C + c] = invstd;
+    coef[4 * C + c] = (float)var;
+    coef[5 * C + c] = (float)s;
+    // MXNet BatchNorm aux update: moving = moving*momentum + batch*(1-momentum), biased batch variance
+    if (moving_mean) moving_mean[c] = moving_mean[c] * momentum + (float)mean * (1.f - momentum);
+    if (moving_var) moving_var[c] = moving_var[c] * momentum + (float)var * (1.f - momentum);
+  }
+}
+
+// ---- forward apply: y = relu?(z*a + b + rb) + ra --------------------------------------------------
+__global__ void __launch_bounds__(NT) fwd_apply_kernel(const __nv_bfloat16* __restrict__ z,
+                                                       const float* __restrict__ coef,
+                                                       const __nv_bfloat16* __restrict__ rb,
+                                                       const __nv_bfloat16* __restrict__ ra,
+                                                       __nv_bfloat16* __restrict__ y, Geo G, int relu) {
+  const int t = threadIdx.x, cg = t % G.cgs, pl = t / G.cgs;
+  float a[8], b[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) { a[i] = coef[cg * 8 + i]; b[i] = coef[G.C + cg * 8 + i]; }
+  const int nunits = G.N * G.H * G.nseg;
+  for (int u = blockIdx.x; u < nunits; u += gridDim.x) {
+    const int sg = u % G.nseg, row = u / G.nseg, h = row % G.H, n = row / G.H;
+    const int w0 = sg * G.seg, w1 = min(G.W, w0 + G.seg);
+    const int64_t base = pix_off(n, h, 0, G.H, G.W, 1, G.C) + cg * 8;
+    for (int w = w0 + pl; w < w1; w += G.ppb) {
+      const int64_t o = base + (int64_t)w * G.C;
+      float f[8], r[8];
+      unpack8(__ldg(reinterpret_cast<const uint4*>(z + o)), f);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) f[i] = fmaf(f[i], a[i], b[i]);
+      if (rb) {
+        unpack8(__ldg(reinterpret_cast<const uint4*>(rb + o)), r);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) f[i] += r[i];
+      }
+      if (relu) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) f[i] = fmaxf(f[i], 0.f);
+      }
+      if (ra) {
+        unpack8(__ldg(reinterpret_cast<const uint4*>(ra + o)), r);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) f[i] += r[i];
+      }
+      *reinterpret_cast<uint4*>(y + o) = pack8(f);
+    }
+  }
+}
+
+// ---- backward ------------------------------------------------------------------------------------
+// mask_mode: 0 no relu (g = dy), 1 mask = (y > 0) read from `ym`, 2 mask = (z*a + b > 0) recomputed
+__device__ __forceinline__ void masked_grad(float (&g)[8], const float (&zf)[8], const __nv_bfloat16* ym,
+                                            int64_t o, int mask_mode, const float (&a)[8], const float (&b)[8]) {
+  if (mask_mode == 1) {
+    float yf[8];
+    unpack8(__ldg(reinterpret_cast<const uint4*>(ym + o)), yf);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) g[i] = yf[i] > 0.f ? g[i] : 0.f;
+  } else if (mask_mode == 2) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) g[i] = fmaf(zf[i], a[i], b[i]) > 0.f ? g[i] : 0.f;
+  }
+}
+
+__global__ void __launch_bounds__(NT) bwd_reduce_kernel(const __nv_bfloat16* __restrict__ dy,
+                                                        const __nv_bfloat16* __restrict__ ym,
+                                                        const __nv_bfloat16* __restrict__ z,
+                                                        const float* __restrict__ coef, Geo G, int mask_mode,
+                                                        float* __restrict__ partial) {
+  const int t = threadIdx.x, cg = t % G.cgs, pl = t / G.cgs;
+  float a[8], b[8], mean[8], s[8], q[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    a[i] = coef[cg * 8 + i];
+    b[i] = coef[G.C + cg * 8 + i];
+    mean[i] = coef[2 * G.C + cg * 8 + i];
+    s[i] = q[i] = 0.f;
+  }
+  const int nunits = G.N * G.H * G.nseg;
+  for (int u = blockIdx.x; u < nunits; u += gridDim.x) {
+    const int sg = u % G.nseg, row = u / G.nseg, h = row % G.H, n = row / G.H;
+    const int w0 = sg * G.seg, w1 = min(G.W, w0 + G.seg);
+    const int64_t base = pix_off(n, h, 0, G.H, G.W, 1, G.C) + cg * 8;
+    for (int w = w0 + pl; w < w1; w += G.ppb) {
+      const int64_t o = base + (int64_t)w * G.C;
+      float g[8], zf[8];
+      unpack8(__ldg(reinterpret_cast<const uint4*>(dy + o)), g);
+      unpack8(__ldg(reinterpret_cast<const uint4*>(z + o)), zf);
+      masked_grad(g, zf, ym, o, mask_mode, a, b);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) { s[i] += g[i]; q[i] = fmaf(g[i], zf[i] - mean[i], q[i]); }
+    }
+  }
+  block_reduce_store(s, q, G, partial + (int64_t)blockIdx.x * 2 * G.C);
+}
+
+// coef2 (fp32, 2 x C): c1 = S1/M | c2 = invstd^2 * S2/M ; also dgamma = invstd*S2, dbeta = S1
+__global__ void bwd_finalize_kernel(const float* __restrict__ partial, int nblocks, int C, double count,
+                                    const float* __restrict__ coef, float* __restrict__ coef2,
+                                    float* __restrict__ dgamma, float* __restrict__ dbeta) {
+  for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < C; c += gridDim.x * blockDim.x) {
+    double s = 0.0, q = 0.0;
+    for (int b = 0; b < nblocks; ++b) {
+      s += (double)partial[(int64_t)b * 2 * C + c];
+      q += (double)partial[(int64_t)b * 2 * C + C + c];
+    }
+    const double invstd = (double)coef[3 * C + c];
+    coef2[c] = (float)(s / count);
+    coef2[C + c] = (float)(invstd * invstd * q / count);
+    if (dgamma) dgamma[c] = (float)(invstd * q);
+    if (dbeta) dbeta[c] = (float)s;
+  }
+}
+
+__global__ void __launch_bounds__(NT) bwd_apply_kernel(const __nv_bfloat16* __restrict__ dy,
+                                                       const __nv_bfloat16* __restrict__ ym,
+                                                       const __nv_bfloat16* __restrict__ z,
+                                                       const float* __restrict__ coef,
+                                                       const float* __restrict__ coef2, Geo G, int mask_mode,
+                                                       __nv_bfloat16* __restrict__ dz, int dz_halo,
+                                                       __nv_bfloat16* __restrict__ g_out) {
+  const int t = threadIdx.x, cg = t % G.cgs, pl = t / G.cgs;
+  float a[8], b[8], mean[8], c1[8], c2[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    a[i] = coef[cg * 8 + i];
+    b[i] = coef[G.C + cg * 8 + i];
+    mean[i] = coef[2 * G.C + cg * 8 + i];
+    c1[i] = coef2[cg * 8 + i];
+    c2[i] = coef2[G.C + cg * 8 + i];
+  }
+  const int nunits = G.N * G.H * G.nseg;
+  for (int u = blockIdx.x; u < nunits; u += gridDim.x) {
+    const int sg = u % G.nseg, row = u / G.nseg, h = row % G.H, n = row / G.H;
+    const int w0 = sg * G.seg, w1 = min(G.W, w0 + G.seg);
+    const int64_t base = pix_off(n, h, 0, G.H, G.W, 1, G.C) + cg * 8;
+    const int64_t obase = pix_off(n, h, 0, G.H, G.W, dz_halo, G.C) + cg * 8;
+    for (int w = w0 + pl; w < w1; w += G.ppb) {
+      const int64_t o = base + (int64_t)w * G.C;
+      float g[8], zf[8], d[8];
+      unpack8(__ldg(reinterpret_cast<const uint4*>(dy + o)), g);
+      unpack8(__ldg(reinterpret_cast<const uint4*>(z + o)), zf);
+      masked_grad(g, zf, ym, o, mask_mode, a, b);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) d[i] = a[i] * (g[i] - c1[i] - (zf[i] - mean[i]) * c2[i]);
+      *reinterpret_cast<uint4*>(dz + obase + (int64_t)w * G.C) = pack8(d);
+      if (g_out) *reinterpret_cast<uint4*>(g_out + o) = pack8(g);
+    }
+  }
+}
+
+// ---- y = x0 + x1 (gradient accumulation where a tensor has two consumers) -------------------------
+__global__ void __launch_bounds__(NT) add_kernel(const __nv_bfloat16* __restrict__ x0,
+                                                 const __nv_bfloat16* __restrict__ x1,
+                                                 __nv_bfloat16* __restrict__ y, Geo G) {
+  const int t = threadIdx.x, cg = t % G.cgs, pl = t / G.cgs;
+  const int nunits = G.N * G.H * G.nseg;
+  for (int u = blockIdx.x; u < nunits; u += gridDim.x) {
+    const int sg = u % G.nseg, row = u / G.nseg, h = row % G.H, n = row / G.H;
+    const int w0 = sg * G.seg, w1 = min(G.W, w0 + G.seg);
+    const int64_t base = pix_off(n, h, 0, G.H, G.W, 1, G.C) + cg * 8;
+    for (int w = w0 + pl; w < w1; w += G.ppb) {
+      const int64_t o = base + (int64_t)w * G.C;
+      float f[8], r[8];
+      unpack8(__ldg(reinterpret_cast<const uint4*>(x0 + o)), f);
+      unpack8(__ldg(reinterpret_cast<const uint4*>(x1 + o)), r);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) f[i] += r[i];
+      *reinterpret_cast<uint4*>(y + o) = pack8(f);
+    }
+  }
+}
+
+static int check_shape(const char* what, int N, int H, int W, int C) {
+  RD_REQUIRE(N > 0 && H > 0 && W > 0, "%s: bad shape", what);
+  RD_REQUIRE(C >= 8 && C % 8 == 0 && C <= 1024, "%s: C must be a multiple of 8, <= 1024 (got %d)", what, C);
+  return 0;
+}
+
+static int grid_for(const Geo& g) {
+  const int64_t units = (int64_t)g.N * g.H * g.nseg;
+  return (int)(units < MAX_BLOCKS ? units : MAX_BLOCKS);
+}
+
+}  // namespace bn
+
+extern "C" {
+
+size_t rd_bn_workspace_bytes(int C) { return (size_t)bn::MAX_BLOCKS * 2 * (size_t)(C > 0 ? C : 0) * sizeof(float); }
+
+int rd_bn_train_stats_nhwc_bf16(const void* z_pad, int N, int H, int W, int C, const float* gamma, const float* beta,
+                                float eps, float momentum, float* moving_mean, float* moving_var, float* coef,
+                                void* workspace, size_t workspace_bytes, rd_stream_t stream) {
+  if (bn::check_shape("rd_bn_train_stats", N, H, W, C)) return 1;
+  RD_REQUIRE(z_pad && coef && workspace, "rd_bn_train_stats: null pointer");
+  RD_REQUIRE(workspace_bytes >= rd_bn_workspace_bytes(C), "rd_bn_train_stats: workspace too small");
+  if (rd_check_device()) return 1;
+  const bn::Geo g = bn::make_geo(N, H, W, C);
+  const int grid = bn::grid_for(g);
+  cudaStream_t s = rd::as_stream(stream);
+  bn::stats_kernel<<<grid, g.ppb * g.cgs, 0, s>>>(static_cast<const __nv_bfloat16*>(z_pad), g, 1,
+                                                   static_cast<float*>(workspace));
+  bn::fwd_finalize_kernel<<<(C + 127) / 128, 128, 0, s>>>(static_cast<const float*>(workspace), grid, C,
+                                                          (double)N * H * W, gamma, beta, eps, momentum, moving_mean,
+                                                          moving_var, coef);
+  rd::count_launch(2);
+  return rd::check_launch("rd_bn_train_stats");
+}
+
+int rd_bn_act_fwd_nhwc_bf16(const void* z_pad, const float* coef, const void* res_before, const void* res_after,
+                            void* y_pad, int N, int H, int W, int C, int relu, rd_stream_t stream) {
+  if (bn::check_shape("rd_bn_act_fwd", N, H, W, C)) return 1;
+  RD_REQUIRE(z_pad && coef && y_pad, "rd_bn_act_fwd: null pointer");
+  if (rd_check_device()) return 1;
+  const bn::Geo g = bn::make_geo(N, H, W, C);
+  const int64_t units = (int64_t)g.N * g.H * g.nseg;
+  const int grid = (int)(units < 8 * 148 ? units : 8 * 148);
+  bn::fwd_apply_kernel<<<grid, g.ppb * g.cgs, 0, rd::as_stream(stream)>>>(
+      static_cast<const __nv_bfloat16*>(z_pad), coef, static_cast<const __nv_bfloat16*>(res_before),
+      static_cast<const __nv_bfloat16*>(res_after), static_cast<__nv_bfloat16*>(y_pad), g, relu ? 1 : 0);
+  rd::count_launch();
+  return rd::check_launch("rd_bn_act_fwd");
+}
+
+int rd_bn_act_bwd_nhwc_bf16(const void* dy_pad, const void* y_mask_pad, const void* z_pad, const float* coef,
+                            int mask_mode, void* dz_pad, int dz_halo_w, void* g_out_pad, float* dgamma,
+                            float* dbeta, int N, int H, int W, int C, void* workspace, size_t workspace_bytes,
+                            rd_stream_t stream) {
+  if (bn::check_shape("rd_bn_act_bwd", N, H, W, C)) return 1;
+  RD_REQUIRE(dy_pad && z_pad && coef && dz_pad && workspace, "rd_bn_act_bwd: null pointer");
+  RD_REQUIRE(mask_mode >= 0 && mask_mode <= 2, "rd_bn_act_bwd: mask_mode must be 0, 1 or 2");
+  RD_REQUIRE(mask_mode != 1 || y_mask_pad, "rd_bn_act_bwd: mask_mode 1 needs the forward output");
+  RD_REQUIRE(dz_halo_w >= 1 && dz_halo_w <= 8, "rd_bn_act_bwd: dz_halo_w must be in [1,8]");
+  RD_REQUIRE(workspace_bytes >= rd_bn_workspace_bytes(C) + 2 * (size_t)C * sizeof(float),
+             "rd_bn_act_bwd: workspace too small");
+  if (rd_check_device()) return 1;
+  const bn::Geo g = bn::make_geo(N, H, W, C);
+  const int grid = bn::grid_for(g);
+  cudaStream_t s = rd::as_stream(stream);
+  float* partial = static_cast<float*>(workspace);
+  float* coef2 = partial + (size_t)bn::MAX_BLOCKS * 2 * C;
+  const __nv_bfloat16* dy = static_cast<const __nv_bfloat16*>(dy_pad);
+  const __nv_bfloat16* ym = static_cast<const __nv_bfloat16*>(y_mask_pad);
+  const __nv_bfloat16* z = static_cast<const __nv_bfloat16*>(z_pad);
+  bn::bwd_reduce_kernel<<<grid, g.ppb * g.cgs, 0, s>>>(dy, ym, z, coef, g, mask_mode, partial);
+  bn::bwd_finalize_kernel<<<(C + 127) / 128, 128, 0, s>>>(partial, grid, C, (double)N * H * W, coef, coef2, dgamma,
+                                                          dbeta);
+  const int64_t units = (int64_t)g.N * g.H * g.nseg;
+  const int grid2 = (int)(units < 8 * 148 ? units : 8 * 148);
+  bn::bwd_apply_kernel<<<grid2, g.ppb * g.cgs, 0, s>>>(dy, ym, z, coef, coef2, g, mask_mode,
+                                                       static_cast<__nv_bfloat16*>(dz_pad), dz_halo_w,
+                                                       static_cast<__nv_bfloat16*>(g_out_pad));
+  rd::count_launch(3);
+  return rd::check_launch("rd_bn_act_bwd");
+}
+
+int rd_channel_sums_nhwc_bf16(const void* x_pad, int N, int H, int W, int C, float* sums, void* workspace,
+                              size_t workspace_bytes, rd_stream_t stream) {
+  if (bn::check_shape("rd_channel_sums", N, H, W, C)) return 1;
+  RD_REQUIRE(x_pad && sums && workspace, "rd_channel_sums: null pointer");
+  RD_REQUIRE(workspace_bytes >= rd_bn_workspace_bytes(C) + 6 * (size_t)C * sizeof(float),
+             "rd_channel_sums: workspace too small");
+  if (rd_check_device()) return 1;
+  const bn::Geo g = bn::make_geo(N, H, W, C);
+  const int grid = bn::grid_for(g);
+  cudaStream_t s = rd::as_stream(stream);
+  float* partial = static_cast<float*>(workspace);
+  float* coef = partial + (size_t)bn::MAX_BLOCKS * 2 * C;
+  bn::stats_kernel<<<grid, g.ppb * g.cgs, 0, s>>>(static_cast<const __nv_bfloat16*>(x_pad), g, 1, partial);
+  bn::fwd_finalize_kernel<<<(C + 127) / 128, 128, 0, s>>>(partial, grid, C, (double)N * H * W, nullptr, nullptr, 1e-5f,
+                                                          0.f, nullptr, nullptr, coef);
+  RD_CUDA(cudaMemcpyAsync(sums, coef + 5 * (size_t)C, (size_t)C * sizeof(float), cudaMemcpyDeviceToDevice, s));
+  rd::count_launch(2);
+  return rd::check_launch("rd_channel_sums");
+}
+
+int rd_add_nhwc_bf16(const void* x0_pad, const void* x1_pad, void* y_pad, int N, int H, int W, int C,
+                     rd_stream_t stream) {
+  if (bn::check_shape("rd_add_nhwc_bf16", N, H, W, C)) return 1;
+  RD_REQUIRE(x0_pad && x1_pad && y_pad, "rd_add_nhwc_bf16: null pointer");
+  if (rd_check_device()) return 1;
+  const bn::Geo g = bn::make_geo(N, H, W, C);
+  const int64_t units = (int64_t)g.N * g.H * g.nseg;
+  const int grid = (int)(units < 8 * 148 ? units : 8 * 148);
+  bn::add_kernel<<<grid, g.ppb * g.cgs, 0, rd::as_stream(stream)>>>(static_cast<const __nv_bfloat16*>(x0_pad),
+                                                                    static_cast<const __nv_bfloat16*>(x1_pad),
+                                                                    static_cast<__nv_bfloat16*>(y_pad), g);
+  rd::count_launch();
+  return rd::check_launch("rd_add_nhwc_bf16");
+}
+
+}  // extern "C"

@@ -411,7 +411,8 @@ conv_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CU
 }
 
 // mode: 0 = conv ksize x ksize (pad ksize/2), W-stride stride_w in {1,2}; 1 = deconv (3,8)/(1,4)/(1,2);
-//       2 = deconv (3,4)/(1,2)/(1,1)
+//       2 = deconv (3,4)/(1,2)/(1,1); 3 = deconv (3,3)/(1,2)/(1,1) with output width 2*W (the data gradient
+//       of a 3x3 W-stride-2 convolution)
 static int run(int mode, const void* x_pad, const void* w_packed, const float* scale, const float* shift,
                const void* residual_pad, void* y_pad, int N, int H, int W_in, int Cin, int Cout, int ksize,
                int stride_w, int relu, int res_after_relu, cudaStream_t stream) {
@@ -463,7 +464,7 @@ static int run(int mode, const void* x_pad, const void* w_packed, const float* s
     }
   } else {
     // out[oh, ow] += x[ih, iw] w[ky, kx]  with  oh = ih - 1 + ky,  ow = iw*S - pad + kx
-    const int S = mode == 1 ? 4 : 2, KW = mode == 1 ? 8 : 4, pad = mode == 1 ? 2 : 1;
+    const int S = mode == 1 ? 4 : 2, KW = mode == 1 ? 8 : (mode == 2 ? 4 : 3), pad = mode == 1 ? 2 : 1;
     RD_REQUIRE(S * Cout <= 512, "rd_deconv: S*Cout accumulators exceed TMEM");
     W_out = W_in * S;
     P.W_out_tiles = W_in;
@@ -626,8 +627,9 @@ int rd_conv2d_nhwc_bf16(const void* x_pad, const void* w_packed, const float* sc
 int rd_deconv2d_nhwc_bf16(const void* x_pad, const void* w_packed, const float* scale, const float* shift,
                           const void* residual_pad, void* y_pad, int N, int H, int W, int Cin, int Cout, int kw,
                           int relu, rd_stream_t stream) {
-  RD_REQUIRE(kw == 8 || kw == 4, "rd_deconv2d_nhwc_bf16: supported kernels are (3,8)/(1,4)/(1,2) and (3,4)/(1,2)/(1,1)");
-  return conv::run(kw == 8 ? 1 : 2, x_pad, w_packed, scale, shift, residual_pad, y_pad, N, H, W, Cin, Cout, 3, 1, relu, 1,
+  RD_REQUIRE(kw == 8 || kw == 4 || kw == 3,
+             "rd_deconv2d_nhwc_bf16: supported kernels are (3,8)/(1,4)/(1,2), (3,4)/(1,2)/(1,1) and (3,3)/(1,2)/(1,1)");
+  return conv::run(kw == 8 ? 1 : (kw == 4 ? 2 : 3), x_pad, w_packed, scale, shift, residual_pad, y_pad, N, H, W, Cin, Cout, 3, 1, relu, 1,
                    rd::as_stream(stream));
 }
 

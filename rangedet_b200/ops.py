@@ -436,16 +436,159 @@ def deconv2d_nhwc(x_pad, w_packed, scale=None, shift=None, relu=False, residual_
     (Cin,Cout,3,8) -> stride (1,4) pad (1,2), or (Cin,Cout,3,4) -> stride (1,2) pad (1,1)."""
     N, Hp, Wp, Cin = x_pad.shape
     taps = w_packed.shape[0]
-    if taps not in (24, 12):
-        raise ValueError("deconv2d_nhwc supports (3,8) and (3,4) kernels")
+    if taps not in (24, 12, 9):
+        raise ValueError("deconv2d_nhwc supports (3,8)/(1,4), (3,4)/(1,2) and (3,3)/(1,2) kernels")
     kw = taps // 3
     H, W = Hp - 2, Wp - 2
     x_pad, w_packed, sc, sh, residual_pad, out = _conv_common(x_pad, w_packed, scale, shift, residual_pad, out,
-                                                              W * (kw // 2), "deconv2d_nhwc")
+                                                              W * (4 if kw == 8 else 2), "deconv2d_nhwc")
     with torch.cuda.device(x_pad.device):
         st = _lib.lib().rd_deconv2d_nhwc_bf16(_p(x_pad), _p(w_packed), _p(sc) if sc is not None else None,
                                               _p(sh) if sh is not None else None,
                                               _p(residual_pad) if residual_pad is not None else None, _p(out),
                                               N, H, W, Cin, w_packed.shape[1], kw, int(bool(relu)), _stream())
     _lib.check(st, "deconv2d_nhwc")
+    return out
+
+
+# ------------------------------------------------------------------------------------------------
+# Training path: weight gradient, training-mode BatchNorm + ReLU + residual (forward / backward)
+# ------------------------------------------------------------------------------------------------
+_WS = {}
+
+
+def _workspace(nbytes, device, tag="ws"):
+    """Grow-only scratch buffer per (device, tag); the C-ABI never allocates."""
+    key = (str(device), tag)
+    t = _WS.get(key)
+    if t is None or t.numel() < nbytes:
+        t = torch.empty(max(int(nbytes), 1 << 20), device=device, dtype=torch.uint8)
+        _WS[key] = t
+    return t
+
+
+def _chk_nhwc(t, name):
+    if t.dtype != torch.bfloat16 or not t.is_cuda or t.dim() != 4 or not t.is_contiguous():
+        raise TypeError("%s must be a contiguous CUDA bf16 haloed NHWC tensor" % name)
+
+
+def conv2d_wgrad(a_pad, b_pad, ksize, stride_w=1):
+    """G[tap][a][b] = sum_pixels A[p][a] * B[p + tap][b] -> fp32 (ksize*ksize, CA, CB).
+    a_pad (N,H+2,W+2,CA) and b_pad (N,H+2,W*stride_w+2,CB): haloed NHWC bf16.  With A = grad of the conv
+    output and B = the conv input this is the gradient of the packed forward weight [tap][Cout][Cin]."""
+    _chk_nhwc(a_pad, "a_pad")
+    _chk_nhwc(b_pad, "b_pad")
+    N, Hp, Wp, CA = a_pad.shape
+    H, W = Hp - 2, Wp - 2
+    CB = b_pad.shape[3]
+    if tuple(b_pad.shape[:3]) != (N, Hp, W * stride_w + 2):
+        raise ValueError("conv2d_wgrad: b_pad shape %s does not match a_pad %s at W-stride %d"
+                         % (tuple(b_pad.shape), tuple(a_pad.shape), stride_w))
+    L = _lib.lib()
+    nb = L.rd_conv2d_wgrad_workspace_bytes(N, H, W, CA, CB, ksize, stride_w)
+    if nb == 0:
+        raise RuntimeError("rangedet_b200.conv2d_wgrad: %s" % _lib.last_error())
+    ws = _workspace(nb, a_pad.device, "wgrad")
+    g = torch.empty((ksize * ksize, CA, CB), device=a_pad.device, dtype=torch.float32)
+    with torch.cuda.device(a_pad.device):
+        st = L.rd_conv2d_wgrad_nhwc_bf16(_p(a_pad), _p(b_pad), _p(g), N, H, W, CA, CB, ksize, stride_w, _p(ws), nb,
+                                         _stream())
+    _lib.check(st, "conv2d_wgrad")
+    return g
+
+
+BN_EPS = 1e-5 + 1e-10   # mxnext/complicate.py:14
+BN_MOMENTUM = 0.9       # mxnext/complicate.py:32-43
+
+
+def bn_train_stats(z_pad, gamma=None, beta=None, moving_mean=None, moving_var=None, eps=BN_EPS,
+                   momentum=BN_MOMENTUM):
+    """Batch statistics of a haloed NHWC bf16 tensor -> coef (6,C) fp32: a | b | mean | invstd | var | sum;
+    moving_mean / moving_var (fp32, in place) follow MXNet's update."""
+    _chk_nhwc(z_pad, "z_pad")
+    N, Hp, Wp, C = z_pad.shape
+    coef = torch.empty((6, C), device=z_pad.device, dtype=torch.float32)
+    L = _lib.lib()
+    nb = L.rd_bn_workspace_bytes(C)
+    ws = _workspace(nb, z_pad.device, "bn")
+    opt = lambda t: _p(t) if t is not None else None
+    with torch.cuda.device(z_pad.device):
+        st = L.rd_bn_train_stats_nhwc_bf16(_p(z_pad), N, Hp - 2, Wp - 2, C, opt(gamma), opt(beta), eps, momentum,
+                                           opt(moving_mean), opt(moving_var), _p(coef), _p(ws), nb, _stream())
+    _lib.check(st, "bn_train_stats")
+    return coef
+
+
+def bn_act_fwd(z_pad, coef, relu=True, res_before=None, res_after=None, out=None):
+    """y = relu?(z*a + b + res_before) + res_after over the interior of haloed NHWC bf16 tensors."""
+    _chk_nhwc(z_pad, "z_pad")
+    N, Hp, Wp, C = z_pad.shape
+    for r in (res_before, res_after):
+        if r is not None:
+            _chk_nhwc(r, "residual")
+            if r.shape != z_pad.shape:
+                raise ValueError("bn_act_fwd: residual shape %s != %s" % (tuple(r.shape), tuple(z_pad.shape)))
+    if out is None:
+        out = torch.zeros_like(z_pad)
+    opt = lambda t: _p(t) if t is not None else None
+    with torch.cuda.device(z_pad.device):
+        st = _lib.lib().rd_bn_act_fwd_nhwc_bf16(_p(z_pad), _p(coef), opt(res_before), opt(res_after), _p(out), N, Hp - 2,
+                                                Wp - 2, C, int(bool(relu)), _stream())
+    _lib.check(st, "bn_act_fwd")
+    return out
+
+
+def bn_act_bwd(dy_pad, z_pad, coef, mask_mode, y_mask=None, dz_halo_w=1, dz_out=None, want_g=False, g_out=None):
+    """Backward of bn_act_fwd w.r.t. z, gamma, beta (and the masked gradient g that flows into res_before).
+    Returns (dz, dgamma, dbeta, g or None).  dz has a W halo of dz_halo_w pixels."""
+    _chk_nhwc(dy_pad, "dy_pad")
+    _chk_nhwc(z_pad, "z_pad")
+    N, Hp, Wp, C = z_pad.shape
+    H, W = Hp - 2, Wp - 2
+    if dy_pad.shape != z_pad.shape:
+        raise ValueError("bn_act_bwd: dy shape %s != z shape %s" % (tuple(dy_pad.shape), tuple(z_pad.shape)))
+    if dz_out is None:
+        dz_out = torch.zeros((N, Hp, W + 2 * dz_halo_w, C), device=z_pad.device, dtype=torch.bfloat16)
+    if want_g and g_out is None:
+        g_out = torch.zeros_like(z_pad)
+    dgamma = torch.empty(C, device=z_pad.device, dtype=torch.float32)
+    dbeta = torch.empty(C, device=z_pad.device, dtype=torch.float32)
+    L = _lib.lib()
+    nb = L.rd_bn_workspace_bytes(C) + 8 * C * 4
+    ws = _workspace(nb, z_pad.device, "bn")
+    opt = lambda t: _p(t) if t is not None else None
+    with torch.cuda.device(z_pad.device):
+        st = L.rd_bn_act_bwd_nhwc_bf16(_p(dy_pad), opt(y_mask), _p(z_pad), _p(coef), int(mask_mode), _p(dz_out),
+                                       int(dz_halo_w), opt(g_out), _p(dgamma), _p(dbeta), N, H, W, C, _p(ws), nb,
+                                       _stream())
+    _lib.check(st, "bn_act_bwd")
+    return dz_out, dgamma, dbeta, g_out
+
+
+def channel_sums(x_pad):
+    """sums[c] = sum over interior pixels (fp32)."""
+    _chk_nhwc(x_pad, "x_pad")
+    N, Hp, Wp, C = x_pad.shape
+    out = torch.empty(C, device=x_pad.device, dtype=torch.float32)
+    L = _lib.lib()
+    nb = L.rd_bn_workspace_bytes(C) + 8 * C * 4
+    ws = _workspace(nb, x_pad.device, "bn")
+    with torch.cuda.device(x_pad.device):
+        st = L.rd_channel_sums_nhwc_bf16(_p(x_pad), N, Hp - 2, Wp - 2, C, _p(out), _p(ws), nb, _stream())
+    _lib.check(st, "channel_sums")
+    return out
+
+
+def add_nhwc(x0_pad, x1_pad, out=None):
+    """y = x0 + x1 over the interior (haloed NHWC bf16)."""
+    _chk_nhwc(x0_pad, "x0_pad")
+    _chk_nhwc(x1_pad, "x1_pad")
+    if x0_pad.shape != x1_pad.shape:
+        raise ValueError("add_nhwc: shapes differ")
+    N, Hp, Wp, C = x0_pad.shape
+    if out is None:
+        out = torch.zeros_like(x0_pad)
+    with torch.cuda.device(x0_pad.device):
+        st = _lib.lib().rd_add_nhwc_bf16(_p(x0_pad), _p(x1_pad), _p(out), N, Hp - 2, Wp - 2, C, _stream())
+    _lib.check(st, "add_nhwc")
     return out
