@@ -158,6 +158,12 @@ int rd_conv2d_nhwc_bf16(const void* x_pad, const void* w_packed, const float* sc
 int rd_deconv2d_nhwc_bf16(const void* x_pad, const void* w_packed, const float* scale, const float* shift,
                           const void* residual_pad, void* y_pad, int N, int H, int W, int Cin, int Cout,
                           int kw, int relu, rd_stream_t stream);
+/* rd_conv2d without residual, writing channels [y_coff, y_coff+Cout) of a haloed NHWC tensor that has
+ * y_ctotal channels (wide outputs, e.g. the 576-channel data gradient of the Meta-Kernel unit's 1x1
+ * aggregation conv, are produced as several 64/128-channel slices). */
+int rd_conv2d_nhwc_bf16_slice(const void* x_pad, const void* w_packed, const float* scale, const float* shift,
+                              void* y_pad, int N, int H, int W, int Cin, int Cout, int ksize, int stride_w,
+                              int relu, int y_ctotal, int y_coff, rd_stream_t stream);
 
 /* ---- Training path of the convolution family ---------------------------------------------------
  * What the reference gets from MXNet autograd + cuDNN for every conv / BatchNorm / ReLU / add of the

@@ -39,6 +39,7 @@ SIGNATURES = {
     "rd_get_sorted_foreground_workspace_bytes": (_sz, [_i, _i]),
     "rd_get_sorted_foreground": (_i, [_vp] * 4 + [_i] * 3 + [_vp] * 4 + [_sz, _vp]),
     "rd_conv2d_nhwc_bf16": (_i, [_vp] * 6 + [_i] * 8 + [_vp]),
+    "rd_conv2d_nhwc_bf16_slice": (_i, [_vp] * 5 + [_i] * 10 + [_vp]),
     "rd_deconv2d_nhwc_bf16": (_i, [_vp] * 6 + [_i] * 7 + [_vp]),
     "rd_conv2d_wgrad_workspace_bytes": (_sz, [_i] * 7),
     "rd_conv2d_wgrad_nhwc_bf16": (_i, [_vp] * 3 + [_i] * 7 + [_vp, _sz, _vp]),

@@ -415,8 +415,13 @@ conv_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CU
 //       of a 3x3 W-stride-2 convolution)
 static int run(int mode, const void* x_pad, const void* w_packed, const float* scale, const float* shift,
                const void* residual_pad, void* y_pad, int N, int H, int W_in, int Cin, int Cout, int ksize,
-               int stride_w, int relu, int res_after_relu, cudaStream_t stream) {
+               int stride_w, int relu, int res_after_relu, cudaStream_t stream, int y_ctotal = 0, int y_coff = 0) {
   RD_REQUIRE(x_pad && w_packed && y_pad, "rd_conv: null pointer");
+  // channel-slice output: write channels [y_coff, y_coff + Cout) of a y tensor with y_ctotal channels
+  if (y_ctotal == 0) y_ctotal = Cout;
+  RD_REQUIRE(y_ctotal >= Cout && y_coff >= 0 && y_coff + Cout <= y_ctotal && y_ctotal % 8 == 0 && y_coff % 8 == 0,
+             "rd_conv: bad output channel slice (%d + %d of %d)", y_coff, Cout, y_ctotal);
+  RD_REQUIRE(y_ctotal == Cout || (mode == 0 && !residual_pad), "rd_conv: a channel-slice output needs a plain conv without residual");
   RD_REQUIRE(Cin >= 64 && Cin % 64 == 0 && Cin <= 1024, "rd_conv: Cin must be a multiple of 64 (got %d); pad the channels", Cin);
   RD_REQUIRE(Cout == 64 || Cout == 128, "rd_conv: Cout must be 64 or 128 (got %d); pad the channels", Cout);
   RD_REQUIRE(N > 0 && H > 0 && W_in > 0, "rd_conv: bad shape");
@@ -564,10 +569,10 @@ static int run(int mode, const void* x_pad, const void* w_packed, const float* s
     const uint32_t b[3] = {(uint32_t)KC, (uint32_t)Cout, 1u};
     if (tma::make_map(&tm_w, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, w_packed, 3, d, s, b, CU_TENSOR_MAP_SWIZZLE_128B)) return 1;
   }
-  char* y_int = static_cast<char*>(y_pad) + (Wp_out + 1) * Cout * 2;  // interior origin of the haloed output
+  char* y_int = static_cast<char*>(y_pad) + ((Wp_out + 1) * y_ctotal + y_coff) * 2;  // interior origin of the haloed output
   {  // interior view (C, W_out, H, N): stores are clipped at W_out, never touch the halo
     const uint64_t d[4] = {(uint64_t)Cout, (uint64_t)W_out, (uint64_t)H, (uint64_t)N};
-    const uint64_t s[3] = {(uint64_t)Cout * 2, Wp_out * Cout * 2, Hp * Wp_out * Cout * 2};
+    const uint64_t s[3] = {(uint64_t)y_ctotal * 2, Wp_out * y_ctotal * 2, Hp * Wp_out * y_ctotal * 2};
     const uint32_t b[4] = {(uint32_t)KC, (uint32_t)TM, 1u, 1u};
     if (tma::make_map(&tm_y, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, y_int, 4, d, s, b, CU_TENSOR_MAP_SWIZZLE_128B)) return 1;
   }
@@ -622,6 +627,13 @@ int rd_conv2d_nhwc_bf16(const void* x_pad, const void* w_packed, const float* sc
                         int stride_w, int relu, rd_stream_t stream) {
   return conv::run(0, x_pad, w_packed, scale, shift, residual_pad, y_pad, N, H, W, Cin, Cout, ksize, stride_w, relu, 0,
                    rd::as_stream(stream));
+}
+
+int rd_conv2d_nhwc_bf16_slice(const void* x_pad, const void* w_packed, const float* scale, const float* shift,
+                              void* y_pad, int N, int H, int W, int Cin, int Cout, int ksize, int stride_w, int relu,
+                              int y_ctotal, int y_coff, rd_stream_t stream) {
+  return conv::run(0, x_pad, w_packed, scale, shift, nullptr, y_pad, N, H, W, Cin, Cout, ksize, stride_w, relu, 0,
+                   rd::as_stream(stream), y_ctotal, y_coff);
 }
 
 int rd_deconv2d_nhwc_bf16(const void* x_pad, const void* w_packed, const float* scale, const float* shift,

@@ -431,6 +431,23 @@ def conv2d_nhwc(x_pad, w_packed, scale=None, shift=None, relu=False, residual_pa
     return out
 
 
+def conv2d_nhwc_slice(x_pad, w_packed, out, c_off, relu=False, stride_w=1):
+    """conv(x) written into channels [c_off, c_off + Cout) of the haloed NHWC bf16 tensor `out`."""
+    N, Hp, Wp, Cin = x_pad.shape
+    taps, Cout, Cin2 = w_packed.shape
+    if taps not in (1, 9) or Cin2 != Cin or x_pad.dtype != torch.bfloat16 or out.dtype != torch.bfloat16:
+        raise ValueError("conv2d_nhwc_slice: bad operands")
+    H, W = Hp - 2, Wp - 2
+    if tuple(out.shape[:3]) != (N, Hp, W // stride_w + 2) or not out.is_contiguous():
+        raise ValueError("conv2d_nhwc_slice: output shape %s does not match" % (tuple(out.shape),))
+    with torch.cuda.device(x_pad.device):
+        st = _lib.lib().rd_conv2d_nhwc_bf16_slice(_p(x_pad.contiguous()), _p(w_packed.contiguous()), None, None, _p(out), N, H,
+                                                  W, Cin, Cout, 3 if taps == 9 else 1, int(stride_w), int(bool(relu)),
+                                                  out.shape[3], int(c_off), _stream())
+    _lib.check(st, "conv2d_nhwc_slice")
+    return out
+
+
 def deconv2d_nhwc(x_pad, w_packed, scale=None, shift=None, relu=False, residual_pad=None, out=None):
     """y = relu?(deconv(x) * scale + shift) + residual for the two agg_stage shapes: weight packed from
     (Cin,Cout,3,8) -> stride (1,4) pad (1,2), or (Cin,Cout,3,4) -> stride (1,2) pad (1,1)."""

@@ -3,11 +3,10 @@ Reports frames/s and achieved TFLOP/s (1.114 TFLOP / frame forward, SURVEY 8 a3/
 import json, os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
-from oracle import dla_ref   # parameter generator only (names / shapes of the reference graph)
-from rangedet_b200 import dla, synth, _lib
+from rangedet_b200 import dla, synth, _lib, model_params
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 8
 H, W = 64, 2656
-P = dla_ref.make_params(seed=0, device="cuda")
+P = model_params.make_params(seed=0, device="cuda")
 data = torch.randn(B, 8, H, W, device="cuda")
 coord = torch.from_numpy(synth.range_image_coords(B, seed=0)).cuda()
 bb, head = dla.DLABackbone(P), dla.RangeRpnHead(P)

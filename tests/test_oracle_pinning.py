@@ -160,3 +160,39 @@ def test_sorted_foreground_restatement_small_case():
     # masked-out and negative scores rank below: a fifth pick is the masked point (score 0), then -0.5
     s5, d5, _ = sorted_fg_ref.get_sorted_foreground(score, delta, pc, mask, 6)
     assert d5[0, 4:, 0].tolist() == [32.0, 16.0] and s5[0, 4] == 0.0
+
+
+def test_train_oracle_runs_and_names_every_parameter():
+    """oracle/dla_train_ref.py (CPU, tiny): every trainable parameter of the reference's graph gets a
+    gradient, and a central finite difference of the loss (float64, no bf16 emulation) matches the
+    autograd directional derivative (3e-2: the loss is piecewise smooth -- ReLU kinks)."""
+    import torch
+    from oracle import dla_ref, dla_train_ref
+    from rangedet_b200 import synth
+    torch.manual_seed(0)
+    B, H, W = 2, 4, 64
+    P = {k: v.double() for k, v in dla_ref.make_params(seed=0).items()}
+    data = torch.randn(B, 8, H, W).double()
+    coord = torch.from_numpy(synth.range_image_coords(B, seed=0, h=H, w=W - 4, w_pad=W)).double()
+    d_cls = [torch.randn(B, 1, H, W >> l).double() for l in range(3)]
+    d_reg = [torch.randn(B, 8, H, W >> l).double() for l in range(3)]
+    ref = dla_train_ref.TrainRef(P, bf16=False)
+    _, _, grads = ref.forward_backward(data, coord, d_cls, d_reg)
+    trainable = [k for k in P if not k.endswith(("_moving_mean", "_moving_var"))]
+    assert sorted(grads) == sorted(trainable)
+
+    def loss(Pq):
+        r = dla_train_ref.TrainRef(Pq, bf16=False)
+        with torch.no_grad():
+            c, g = r.forward(data, coord)
+        return float(sum((a * b).sum() for a, b in zip(c, d_cls)) + sum((a * b).sum() for a, b in zip(g, d_reg)))
+
+    for name in ("rpn_reg_conv_2_lvl_0_weight", "agg2_deconv_weight"):
+        d = torch.randn_like(P[name])
+        eps = 1e-6
+        Pp, Pm = dict(P), dict(P)
+        Pp[name] = P[name] + eps * d
+        Pm[name] = P[name] - eps * d
+        fd = (loss(Pp) - loss(Pm)) / (2 * eps)
+        an = float((grads[name] * d).sum())
+        assert abs(fd - an) <= 3e-2 * max(abs(fd), abs(an)), (name, fd, an)
