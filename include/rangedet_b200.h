@@ -215,6 +215,16 @@ int rd_channel_sums_nhwc_bf16(const void* x_pad, int N, int H, int W, int C, flo
 int rd_add_nhwc_bf16(const void* x0_pad, const void* x1_pad, void* y_pad, int N, int H, int W, int C,
                      rd_stream_t stream);
 
+/* Layout conversions across the Meta-Kernel op boundary (the reference is NCHW throughout; channel
+ * index of the (B,9C,H,W) Meta-Kernel tensors is c*9+k, meta_kernel.py:232-239):
+ *   src_pad / dst_pad : zero-haloed NHWC bf16 [N][H+2][W+2][C_src or C_dst], interior touched only
+ *   dst / src         : NCHW fp32 [N][C][H][W]
+ *   chmap 0: same channel order; chmap 1: NHWC channel k*(C/9)+c  <->  NCHW channel c*9+k (tap-major). */
+int rd_nhwc_bf16_to_nchw_f32(const void* src_pad, float* dst, int N, int H, int W, int C_src, int C, int chmap,
+                             rd_stream_t stream);
+int rd_nchw_f32_to_nhwc_bf16(const float* src, void* dst_pad, int N, int H, int W, int C, int C_dst, int chmap,
+                             rd_stream_t stream);
+
 /* ---- tcgen05 self-test -------------------------------------------------------------------
  * D(128 x n) = A(128 x k) . B(n x k)^T with bf16 operands staged in shared memory in the
  * canonical no-swizzle K-major core-matrix layout, tcgen05.mma into TMEM, tcgen05.ld back.

@@ -49,6 +49,8 @@ SIGNATURES = {
     "rd_bn_act_bwd_nhwc_bf16": (_i, [_vp] * 4 + [_i, _vp, _i, _vp, _vp, _vp] + [_i] * 4 + [_vp, _sz, _vp]),
     "rd_channel_sums_nhwc_bf16": (_i, [_vp] + [_i] * 4 + [_vp, _vp, _sz, _vp]),
     "rd_add_nhwc_bf16": (_i, [_vp] * 3 + [_i] * 4 + [_vp]),
+    "rd_nhwc_bf16_to_nchw_f32": (_i, [_vp, _vp] + [_i] * 6 + [_vp]),
+    "rd_nchw_f32_to_nhwc_bf16": (_i, [_vp, _vp] + [_i] * 6 + [_vp]),
     "rd_tc_probe_gemm": (_i, [_vp, _vp, _vp, _i, _i, _i, _vp]),
     "rd_tma_probe": (_i, [_vp, _vp, _vp] + [_i] * 7 + [_vp]),
 }

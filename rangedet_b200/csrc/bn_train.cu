@@ -21,7 +21,7 @@
 
 namespace bn {
 
-constexpr int MAX_BLOCKS = 296;  // 2 per SM: partial rows of the two-stage reductions
+constexpr int MAX_BLOCKS = 1184;  // 8 per SM: partial columns of the two-stage reductions
 constexpr int NT = 256;
 
 struct Geo {
@@ -65,10 +65,10 @@ __device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
   return make_uint4(w[0], w[1], w[2], w[3]);
 }
 
-// Block-level sum of 16 per-thread values over the threads that share a channel group; one partial row
-// [2][C] per block: row[which*C + channel].
+// Block-level sum of 16 per-thread values over the threads that share a channel group; one partial COLUMN
+// per block: partial[(which*C + channel) * MAX_BLOCKS + block] (so the finalize warps read contiguously).
 __device__ __forceinline__ void block_reduce_store(const float (&s)[8], const float (&q)[8], const Geo& G,
-                                                   float* __restrict__ partial_row) {
+                                                   float* __restrict__ partial) {
   __shared__ float red[NT * 16];
   const int t = threadIdx.x;
   const int cg = t % G.cgs, pl = t / G.cgs;
@@ -83,7 +83,7 @@ __device__ __forceinline__ void block_reduce_store(const float (&s)[8], const fl
     float a = 0.f;
     for (int p = 0; p < G.ppb; ++p) a += red[p * nval + v];
     const int cgi = v / 16, i = v % 16;
-    partial_row[(i / 8) * G.C + cgi * 8 + (i % 8)] = a;
+    partial[(int64_t)((i / 8) * G.C + cgi * 8 + (i % 8)) * MAX_BLOCKS + blockIdx.x] = a;
   }
 }
 
@@ -106,20 +106,39 @@ __global__ void __launch_bounds__(NT) stats_kernel(const __nv_bfloat16* __restri
       for (int i = 0; i < 8; ++i) { s[i] += f[i]; q[i] = fmaf(f[i], f[i], q[i]); }
     }
   }
-  block_reduce_store(s, q, G, partial + (int64_t)blockIdx.x * 2 * G.C);
+  block_reduce_store(s, q, G, partial);
+}
+
+// One warp per channel: lanes stride over the per-block partials, fp64 combination, shuffle reduction.
+__device__ __forceinline__ void channel_totals(const float* __restrict__ partial, int nblocks, int C, int c, double& s,
+                                               double& q) {
+  const int lane = threadIdx.x & 31;
+  s = 0.0;
+  q = 0.0;
+  const float* ps = partial + (int64_t)c * MAX_BLOCKS;
+  const float* pq = partial + (int64_t)(C + c) * MAX_BLOCKS;
+  for (int b = lane; b < nblocks; b += 32) {
+    s += (double)ps[b];
+    q += (double)pq[b];
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    s += __shfl_xor_sync(0xffffffffu, s, o);
+    q += __shfl_xor_sync(0xffffffffu, q, o);
+  }
 }
 
 // coef layout (fp32, 6 x C): a | b | mean | invstd | batch var (biased) | spare
-__global__ void fwd_finalize_kernel(const float* __restrict__ partial, int nblocks, int C, double count,
-                                    const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
-                                    float momentum, float* __restrict__ moving_mean,
-                                    float* __restrict__ moving_var, float* __restrict__ coef) {
-  for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < C; c += gridDim.x * blockDim.x) {
-    double s = 0.0, q = 0.0;
-    for (int b = 0; b < nblocks; ++b) {
-      s += (double)partial[(int64_t)b * 2 * C + c];
-      q += (double)partial[(int64_t)b * 2 * C + C + c];
-    }
+__global__ void __launch_bounds__(256) fwd_finalize_kernel(const float* __restrict__ partial, int nblocks, int C,
+                                                           double count, const float* __restrict__ gamma,
+                                                           const float* __restrict__ beta, float eps, float momentum,
+                                                           float* __restrict__ moving_mean,
+                                                           float* __restrict__ moving_var, float* __restrict__ coef) {
+  const int c = blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (c >= C) return;
+  double s, q;
+  channel_totals(partial, nblocks, C, c, s, q);
+  if ((threadIdx.x & 31) == 0) {
     const double mean = s / count;
     double var = q / count - mean * mean;
     if (var < 0.0) var = 0.0;
@@ -222,19 +241,19 @@ __global__ void __launch_bounds__(NT) bwd_reduce_kernel(const __nv_bfloat16* __r
       for (int i = 0; i < 8; ++i) { s[i] += g[i]; q[i] = fmaf(g[i], zf[i] - mean[i], q[i]); }
     }
   }
-  block_reduce_store(s, q, G, partial + (int64_t)blockIdx.x * 2 * G.C);
+  block_reduce_store(s, q, G, partial);
 }
 
 // coef2 (fp32, 2 x C): c1 = S1/M | c2 = invstd^2 * S2/M ; also dgamma = invstd*S2, dbeta = S1
-__global__ void bwd_finalize_kernel(const float* __restrict__ partial, int nblocks, int C, double count,
-                                    const float* __restrict__ coef, float* __restrict__ coef2,
-                                    float* __restrict__ dgamma, float* __restrict__ dbeta) {
-  for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < C; c += gridDim.x * blockDim.x) {
-    double s = 0.0, q = 0.0;
-    for (int b = 0; b < nblocks; ++b) {
-      s += (double)partial[(int64_t)b * 2 * C + c];
-      q += (double)partial[(int64_t)b * 2 * C + C + c];
-    }
+__global__ void __launch_bounds__(256) bwd_finalize_kernel(const float* __restrict__ partial, int nblocks, int C,
+                                                           double count, const float* __restrict__ coef,
+                                                           float* __restrict__ coef2, float* __restrict__ dgamma,
+                                                           float* __restrict__ dbeta) {
+  const int c = blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (c >= C) return;
+  double s, q;
+  channel_totals(partial, nblocks, C, c, s, q);
+  if ((threadIdx.x & 31) == 0) {
     const double invstd = (double)coef[3 * C + c];
     coef2[c] = (float)(s / count);
     coef2[C + c] = (float)(invstd * invstd * q / count);
@@ -331,7 +350,7 @@ int rd_bn_train_stats_nhwc_bf16(const void* z_pad, int N, int H, int W, int C, c
   cudaStream_t s = rd::as_stream(stream);
   bn::stats_kernel<<<grid, g.ppb * g.cgs, 0, s>>>(static_cast<const __nv_bfloat16*>(z_pad), g, 1,
                                                    static_cast<float*>(workspace));
-  bn::fwd_finalize_kernel<<<(C + 127) / 128, 128, 0, s>>>(static_cast<const float*>(workspace), grid, C,
+  bn::fwd_finalize_kernel<<<(C + 7) / 8, 256, 0, s>>>(static_cast<const float*>(workspace), grid, C,
                                                           (double)N * H * W, gamma, beta, eps, momentum, moving_mean,
                                                           moving_var, coef);
   rd::count_launch(2);
@@ -374,7 +393,7 @@ int rd_bn_act_bwd_nhwc_bf16(const void* dy_pad, const void* y_mask_pad, const vo
   const __nv_bfloat16* ym = static_cast<const __nv_bfloat16*>(y_mask_pad);
   const __nv_bfloat16* z = static_cast<const __nv_bfloat16*>(z_pad);
   bn::bwd_reduce_kernel<<<grid, g.ppb * g.cgs, 0, s>>>(dy, ym, z, coef, g, mask_mode, partial);
-  bn::bwd_finalize_kernel<<<(C + 127) / 128, 128, 0, s>>>(partial, grid, C, (double)N * H * W, coef, coef2, dgamma,
+  bn::bwd_finalize_kernel<<<(C + 7) / 8, 256, 0, s>>>(partial, grid, C, (double)N * H * W, coef, coef2, dgamma,
                                                           dbeta);
   const int64_t units = (int64_t)g.N * g.H * g.nseg;
   const int grid2 = (int)(units < 8 * 148 ? units : 8 * 148);
@@ -398,7 +417,7 @@ int rd_channel_sums_nhwc_bf16(const void* x_pad, int N, int H, int W, int C, flo
   float* partial = static_cast<float*>(workspace);
   float* coef = partial + (size_t)bn::MAX_BLOCKS * 2 * C;
   bn::stats_kernel<<<grid, g.ppb * g.cgs, 0, s>>>(static_cast<const __nv_bfloat16*>(x_pad), g, 1, partial);
-  bn::fwd_finalize_kernel<<<(C + 127) / 128, 128, 0, s>>>(partial, grid, C, (double)N * H * W, nullptr, nullptr, 1e-5f,
+  bn::fwd_finalize_kernel<<<(C + 7) / 8, 256, 0, s>>>(partial, grid, C, (double)N * H * W, nullptr, nullptr, 1e-5f,
                                                           0.f, nullptr, nullptr, coef);
   RD_CUDA(cudaMemcpyAsync(sums, coef + 5 * (size_t)C, (size_t)C * sizeof(float), cudaMemcpyDeviceToDevice, s));
   rd::count_launch(2);

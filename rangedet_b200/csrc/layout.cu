@@ -1,0 +1,124 @@
+// Layout conversions at the op boundaries of the Meta-Kernel inside the NHWC-bf16 pipeline (sm_100a).
+//
+// The reference keeps every tensor NCHW (MXNet), so the Meta-Kernel op boundary is (B,C,H,W) fp32 /
+// (B,9C,H,W) with channel index c*9+k (/root/reference rangedet/symbol/backbone/meta_kernel.py:232-239);
+// the convolution pipeline here is zero-haloed NHWC bf16.  These two kernels move a tensor across that
+// boundary in one HBM pass each, through a shared-memory tile so that both sides are accessed with
+// full 128-byte lines (a strided permute copy ran at 0.25 TB/s and was 12 % of the training step).
+//   chmap 0: dst channel = src channel
+//   chmap 1: tap-major <-> reference order: NHWC channel k*(C/9)+c  <->  NCHW channel c*9+k
+#include <cuda_bf16.h>
+
+#include "../../include/rangedet_b200.h"
+#include "rd_common.cuh"
+
+namespace lay {
+
+constexpr int TP = 32;  // pixels per tile
+constexpr int TC = 64;  // channels per tile
+
+__device__ __forceinline__ int map_channel(int c_nhwc, int C, int chmap) {
+  if (chmap == 0) return c_nhwc;
+  const int cc = C / 9;
+  return (c_nhwc % cc) * 9 + c_nhwc / cc;
+}
+
+// src: haloed NHWC bf16 [N][H+2][W+2][Cs]; dst: NCHW fp32 [N][C][H][W]; channels [0, C) converted.
+__global__ void __launch_bounds__(256) nhwc_to_nchw_kernel(const __nv_bfloat16* __restrict__ src, float* __restrict__ dst,
+                                                          int N, int H, int W, int Cs, int C, int chmap) {
+  __shared__ float tile[TC][TP + 1];
+  const int wt = blockIdx.x, h = blockIdx.y % H, n = blockIdx.y / H;
+  const int w0 = wt * TP;
+  const int64_t srow = (((int64_t)n * (H + 2) + h + 1) * (W + 2) + 1) * Cs;
+  for (int c0 = 0; c0 < C; c0 += TC) {
+    // load: thread -> (pixel, channel pair): 32 px x 32 pairs = 1024 pairs, 4 per thread
+    for (int e = threadIdx.x; e < TP * (TC / 2); e += 256) {
+      const int p = e / (TC / 2), cp = e % (TC / 2);
+      float a = 0.f, b = 0.f;
+      if (w0 + p < W && c0 + 2 * cp < C) {
+        const __nv_bfloat162 v = *reinterpret_cast<const __nv_bfloat162*>(src + srow + (int64_t)(w0 + p) * Cs + c0 + 2 * cp);
+        a = __bfloat162float(v.x);
+        b = __bfloat162float(v.y);
+      }
+      tile[2 * cp][p] = a;
+      tile[2 * cp + 1][p] = b;
+    }
+    __syncthreads();
+    for (int e = threadIdx.x; e < TC * TP; e += 256) {
+      const int c = e / TP, p = e % TP;
+      if (w0 + p < W && c0 + c < C) {
+        const int cd = map_channel(c0 + c, C, chmap);
+        dst[(((int64_t)n * C + cd) * H + h) * W + w0 + p] = tile[c][p];
+      }
+    }
+    __syncthreads();
+  }
+}
+
+// src: NCHW fp32 [N][C][H][W]; dst: haloed NHWC bf16 [N][H+2][W+2][Cd] (interior, channels [0, C) written)
+__global__ void __launch_bounds__(256) nchw_to_nhwc_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst,
+                                                          int N, int H, int W, int C, int Cd, int chmap) {
+  __shared__ float tile[TC][TP + 1];
+  const int wt = blockIdx.x, h = blockIdx.y % H, n = blockIdx.y / H;
+  const int w0 = wt * TP;
+  const int64_t drow = (((int64_t)n * (H + 2) + h + 1) * (W + 2) + 1) * Cd;
+  for (int c0 = 0; c0 < C; c0 += TC) {
+    for (int e = threadIdx.x; e < TC * TP; e += 256) {
+      const int c = e / TP, p = e % TP;
+      float v = 0.f;
+      if (w0 + p < W && c0 + c < C) {
+        const int cs = map_channel(c0 + c, C, chmap);
+        v = src[(((int64_t)n * C + cs) * H + h) * W + w0 + p];
+      }
+      tile[c][p] = v;
+    }
+    __syncthreads();
+    for (int e = threadIdx.x; e < TP * (TC / 2); e += 256) {
+      const int p = e / (TC / 2), cp = e % (TC / 2);
+      if (w0 + p < W && c0 + 2 * cp < C) {
+        const float a = tile[2 * cp][p];
+        if (c0 + 2 * cp + 1 < C) {
+          *reinterpret_cast<__nv_bfloat162*>(dst + drow + (int64_t)(w0 + p) * Cd + c0 + 2 * cp) =
+              __floats2bfloat162_rn(a, tile[2 * cp + 1][p]);
+        } else {
+          dst[drow + (int64_t)(w0 + p) * Cd + c0 + 2 * cp] = __float2bfloat16_rn(a);
+        }
+      }
+    }
+    __syncthreads();
+  }
+}
+
+}  // namespace lay
+
+extern "C" {
+
+int rd_nhwc_bf16_to_nchw_f32(const void* src_pad, float* dst, int N, int H, int W, int C_src, int C, int chmap,
+                             rd_stream_t stream) {
+  RD_REQUIRE(src_pad && dst, "rd_nhwc_bf16_to_nchw_f32: null pointer");
+  RD_REQUIRE(N > 0 && H > 0 && W > 0 && C > 0 && C <= C_src && C_src % 2 == 0, "rd_nhwc_bf16_to_nchw_f32: bad shape");
+  RD_REQUIRE(chmap == 0 || (chmap == 1 && C % 9 == 0), "rd_nhwc_bf16_to_nchw_f32: chmap 1 needs C %% 9 == 0");
+  RD_REQUIRE((int64_t)N * H <= 65535, "rd_nhwc_bf16_to_nchw_f32: N*H too large");
+  if (rd_check_device()) return 1;
+  dim3 grid((W + lay::TP - 1) / lay::TP, N * H);
+  lay::nhwc_to_nchw_kernel<<<grid, 256, 0, rd::as_stream(stream)>>>(static_cast<const __nv_bfloat16*>(src_pad), dst, N, H, W,
+                                                                    C_src, C, chmap);
+  rd::count_launch();
+  return rd::check_launch("rd_nhwc_bf16_to_nchw_f32");
+}
+
+int rd_nchw_f32_to_nhwc_bf16(const float* src, void* dst_pad, int N, int H, int W, int C, int C_dst, int chmap,
+                             rd_stream_t stream) {
+  RD_REQUIRE(src && dst_pad, "rd_nchw_f32_to_nhwc_bf16: null pointer");
+  RD_REQUIRE(N > 0 && H > 0 && W > 0 && C > 0 && C <= C_dst && C_dst % 2 == 0, "rd_nchw_f32_to_nhwc_bf16: bad shape");
+  RD_REQUIRE(chmap == 0 || (chmap == 1 && C % 9 == 0), "rd_nchw_f32_to_nhwc_bf16: chmap 1 needs C %% 9 == 0");
+  RD_REQUIRE((int64_t)N * H <= 65535, "rd_nchw_f32_to_nhwc_bf16: N*H too large");
+  if (rd_check_device()) return 1;
+  dim3 grid((W + lay::TP - 1) / lay::TP, N * H);
+  lay::nchw_to_nhwc_kernel<<<grid, 256, 0, rd::as_stream(stream)>>>(src, static_cast<__nv_bfloat16*>(dst_pad), N, H, W, C,
+                                                                    C_dst, chmap);
+  rd::count_launch();
+  return rd::check_launch("rd_nchw_f32_to_nhwc_bf16");
+}
+
+}  // extern "C"

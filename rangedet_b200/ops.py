@@ -609,3 +609,30 @@ def add_nhwc(x0_pad, x1_pad, out=None):
         st = _lib.lib().rd_add_nhwc_bf16(_p(x0_pad), _p(x1_pad), _p(out), N, Hp - 2, Wp - 2, C, _stream())
     _lib.check(st, "add_nhwc")
     return out
+
+
+def nhwc_to_nchw(src_pad, channels=None, tap_major=False, out=None):
+    """haloed NHWC bf16 -> (N,C,H,W) fp32 (first `channels` channels); tap_major: NHWC k*(C/9)+c -> NCHW c*9+k."""
+    _chk_nhwc(src_pad, "src_pad")
+    N, Hp, Wp, Cs = src_pad.shape
+    C = channels or Cs
+    if out is None:
+        out = torch.empty((N, C, Hp - 2, Wp - 2), device=src_pad.device, dtype=torch.float32)
+    with torch.cuda.device(src_pad.device):
+        st = _lib.lib().rd_nhwc_bf16_to_nchw_f32(_p(src_pad), _p(out), N, Hp - 2, Wp - 2, Cs, C, int(bool(tap_major)), _stream())
+    _lib.check(st, "nhwc_to_nchw")
+    return out
+
+
+def nchw_to_nhwc(src, out, tap_major=False):
+    """(N,C,H,W) fp32 -> interior of the haloed NHWC bf16 tensor `out` (N,H+2,W+2,Cd), channels [0,C)."""
+    _chk_nhwc(out, "out")
+    if src.dtype != torch.float32 or not src.is_cuda or not src.is_contiguous():
+        raise TypeError("nchw_to_nhwc: src must be a contiguous CUDA float32 tensor")
+    N, C, H, W = src.shape
+    if tuple(out.shape[:3]) != (N, H + 2, W + 2) or out.shape[3] < C:
+        raise ValueError("nchw_to_nhwc: output shape %s does not match %s" % (tuple(out.shape), tuple(src.shape)))
+    with torch.cuda.device(src.device):
+        st = _lib.lib().rd_nchw_f32_to_nhwc_bf16(_p(src), _p(out), N, H, W, C, out.shape[3], int(bool(tap_major)), _stream())
+    _lib.check(st, "nchw_to_nhwc")
+    return out

@@ -242,11 +242,10 @@ class TrainGraph(object):
         bias = torch.zeros(64, device=self.device)
         bias[:co] = P[wname + "_bias"]
         zp = ops.conv2d_nhwc(x, self._w(wname, "fwd", ci_p, 64), None, bias, relu=False, out=self._buf("z", x.shape[:3] + (64,)))
-        out = ops.from_nhwc_padded(zp, co)
+        out = ops.nhwc_to_nchw(zp, co)
 
         def bwd(d_out):
-            dz = self._buf("dz", zp.shape)
-            dz[:, 1:-1, 1:-1, :co] = d_out.permute(0, 2, 3, 1).to(torch.bfloat16)
+            dz = ops.nchw_to_nhwc(d_out.contiguous(), self._buf("dz", zp.shape))
             self._pg(wname + "_bias", ops.channel_sums(dz)[:co])
             G = ops.conv2d_wgrad(dz, x, 1, 1)
             self._pg(wname + "_weight", G[0, :co, :P[wname + "_weight"].shape[1]].reshape(P[wname + "_weight"].shape).contiguous())
@@ -268,7 +267,7 @@ class TrainGraph(object):
         C = 64
         B, Hp, Wp, _ = x.shape
         H, W = Hp - 2, Wp - 2
-        feat = ops.from_nhwc_padded(x)  # (B,64,H,W) fp32: the op boundary of the Meta-Kernel
+        feat = ops.nhwc_to_nchw(x)  # (B,64,H,W) fp32: the op boundary of the Meta-Kernel
         mlp = (P[name + "_2656_mlp0_weight"].reshape(32, 3), P[name + "_2656_mlp0_bias"],
                P[name + "_2656_mlp1_weight"].reshape(-1, 32), P[name + "_2656_mlp1_bias"])
         one, zero = torch.ones(9 * C, device=self.device), torch.zeros(9 * C, device=self.device)
@@ -290,7 +289,7 @@ class TrainGraph(object):
             self._pg(bn + "_gamma", untm(dgamma))
             self._pg(bn + "_beta", untm(dbeta))
             # back to the reference op boundary: grad_out (B, 576 = c*9+k, H, W) fp32
-            go = dm[:, 1:-1, 1:-1, :].reshape(B, H, W, 9, C).permute(0, 4, 3, 1, 2).reshape(B, 9 * C, H, W).float().contiguous()
+            go = ops.nhwc_to_nchw(dm, tap_major=True)
             gd, gw0, gb0, gw1, gb1 = ops.meta_kernel_backward(go, feat, coord, *mlp)
             if self.debug is not None:
                 self.debug.update(meta_da=da, meta_dm=dm, meta_go=go, meta_gd=gd, meta_m=m, meta_a=a)
@@ -298,9 +297,7 @@ class TrainGraph(object):
             self._pg(name + "_2656_mlp0_bias", gb0)
             self._pg(name + "_2656_mlp1_weight", gw1.reshape(P[name + "_2656_mlp1_weight"].shape))
             self._pg(name + "_2656_mlp1_bias", gb1)
-            dx = self._buf("dx", x.shape)
-            dx[:, 1:-1, 1:-1, :] = gd.permute(0, 2, 3, 1).to(torch.bfloat16)
-            self._acc(x, dx)
+            self._acc(x, ops.nchw_to_nhwc(gd, self._buf("dx", x.shape)))
 
         self.tape.append(bwd)
         return a
@@ -326,8 +323,7 @@ class TrainGraph(object):
     def forward(self, data, coord):
         self.begin()
         c = data.shape[1]
-        x = self._buf("data", (data.shape[0], data.shape[2] + 2, data.shape[3] + 2, 64))
-        x[:, 1:-1, 1:-1, :c] = data.permute(0, 2, 3, 1).to(torch.bfloat16)
+        x = ops.nchw_to_nhwc(data.contiguous(), self._buf("data", (data.shape[0], data.shape[2] + 2, data.shape[3] + 2, 64)))
         self.nograd.add(id(x))
         res1 = self.res_stage(x, coord, "res1", 1)
         res2a = self.res_stage(res1, None, "res2a", 2)
@@ -390,3 +386,84 @@ def sgd_momentum_step(params, grads, momenta, lr, momentum=0.9, wd=1e-4, clip_gr
     torch._foreach_mul_(ms, momentum)
     torch._foreach_add_(ms, gs, alpha=-lr)
     torch._foreach_add_(ws, ms)
+
+
+class GraphedTrainStep(object):
+    """Forward, backward and the SGD update captured ONCE in CUDA graphs and replayed: a training step is
+    ~900 launches of 10-500 us kernels, launching them one by one from Python is host-bound.
+
+        step = GraphedTrainStep(params, batch, H, W, lr=...)
+        cls, reg = step.forward(data, coord)          # graph 1
+        ... loss on cls / reg -> d_cls, d_reg ...
+        step.backward_update(d_cls, d_reg)            # graph 2 (+ data-parallel all-reduce) + graph 3
+
+    All activations / gradients live in the TrainGraph buffer pool, so replays touch static addresses; the
+    bf16 operand copies of the weights are re-packed inside graph 1 from the fp32 masters that graph 3
+    updates in place.  With `world_size > 1` the parameter gradients are averaged across ranks between
+    backward and update by one flat NCCL all-reduce (the reference: hvd.DistributedOptimizer,
+    tools/train.py:364-368)."""
+
+    def __init__(self, params, batch, H, W, lr, momentum=0.9, wd=1e-4, clip_gradient=None, device="cuda", use_meta=True,
+                 allreduce=None):
+        self.tg = TrainGraph(params, device, use_meta)
+        self.P = params
+        self.allreduce = allreduce
+        self.hyper = dict(lr=lr, momentum=momentum, wd=wd, clip_gradient=clip_gradient)
+        self.data = torch.zeros((batch, 8, H, W), device=device)
+        self.coord = torch.zeros((batch, 3, H, W), device=device)
+        self.d_cls = [torch.zeros((batch, 1, H, W >> l), device=device) for l in range(3)]
+        self.d_reg = [torch.zeros((batch, 8, H, W >> l), device=device) for l in range(3)]
+        self.mom = {}
+        names = sorted(k for k in params if not k.endswith(("_moving_mean", "_moving_var")))
+        self.names = names
+        sizes = [params[k].numel() for k in names]
+        self.flat = torch.zeros(sum(sizes), device=device)
+        self.gviews, o = {}, 0
+        for k, n in zip(names, sizes):
+            self.gviews[k] = self.flat[o:o + n].view(params[k].shape)
+            o += n
+        # warm-up outside the capture (buffer pool, workspaces, function attributes); lr 0 leaves the weights alone
+        s = torch.cuda.Stream()
+        s.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(s):
+            for _ in range(2):
+                self._fwd()
+                self._bwd()
+                self._update(lr=0.0)
+        torch.cuda.current_stream().wait_stream(s)
+        torch.cuda.synchronize()
+        self.pool = torch.cuda.graph_pool_handle()
+        self.g_fwd, self.g_bwd, self.g_upd = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.g_fwd, pool=self.pool):
+            self._fwd()
+        with torch.cuda.graph(self.g_bwd, pool=self.pool):
+            self._bwd()
+        with torch.cuda.graph(self.g_upd, pool=self.pool):
+            self._update(lr=lr)
+
+    def _fwd(self):
+        self.tg.refresh()
+        self.out = self.tg.forward(self.data, self.coord)
+
+    def _bwd(self):
+        grads = self.tg.backward(self.d_cls, self.d_reg)
+        torch._foreach_copy_([self.gviews[k] for k in self.names], [grads[k].reshape(self.P[k].shape) for k in self.names])
+
+    def _update(self, lr):
+        h = self.hyper
+        sgd_momentum_step(self.P, self.gviews, self.mom, lr=lr, momentum=h["momentum"], wd=h["wd"],
+                          clip_gradient=h["clip_gradient"])
+
+    def forward(self, data, coord):
+        self.data.copy_(data, non_blocking=True)
+        self.coord.copy_(coord, non_blocking=True)
+        self.g_fwd.replay()
+        return self.out
+
+    def backward_update(self, d_cls, d_reg):
+        for dst, src in zip(self.d_cls + self.d_reg, list(d_cls) + list(d_reg)):
+            dst.copy_(src, non_blocking=True)
+        self.g_bwd.replay()
+        if self.allreduce is not None:
+            self.allreduce(self.flat)
+        self.g_upd.replay()

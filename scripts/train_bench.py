@@ -28,6 +28,7 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--no-meta", action="store_true")
+    ap.add_argument("--eager", action="store_true", help="launch every kernel from Python instead of replaying CUDA graphs")
     a = ap.parse_args()
     H, W = 64, 2656
     out = []
@@ -45,7 +46,24 @@ def main():
         t_f = t_b = t_u = 0.0
         l0 = _lib.launch_count()
         wall0 = None
+        step = None if a.eager else train.GraphedTrainStep(P, B, H, W, lr=1e-4, clip_gradient=35.0, use_meta=not a.no_meta)
         for it in range(a.warmup + a.steps):
+            if step is not None:
+                if it == a.warmup:
+                    torch.cuda.synchronize()
+                    l0 = _lib.launch_count()
+                    wall0 = time.perf_counter()
+                ev[0].record()
+                step.forward(data, coord)
+                ev[1].record()
+                step.backward_update(d_cls, d_reg)
+                ev[2].record()
+                ev[3].record()
+                if it >= a.warmup:
+                    torch.cuda.synchronize()
+                    t_f += ev[0].elapsed_time(ev[1])
+                    t_b += ev[1].elapsed_time(ev[2])
+                continue
             if it == a.warmup:
                 torch.cuda.synchronize()
                 l0 = _lib.launch_count()
@@ -73,8 +91,9 @@ def main():
                     "algorithmic_TFLOPs": 3 * FLOP_FWD_PER_FRAME * B / step_ms / 1e9,
                     "launches_per_step": (_lib.launch_count() - l0) / n,
                     "mem_GB": torch.cuda.max_memory_allocated() / 1e9, "params_finite": finite,
-                    "meta_unit": not a.no_meta})
-        del tg, P, mom
+                    "meta_unit": not a.no_meta,
+                    "mode": "eager launches" if a.eager else "CUDA graph replay (forward | backward | update)"})
+        del tg, P, mom, step
         torch.cuda.empty_cache()
     print(json.dumps({"workload": "train step fwd+bwd+SGD, DLA backbone + Meta-Kernel unit + RPN head, 64x2656, bf16 operands / "
                                   "fp32 accumulate, training-mode BN, synthetic data, linear loss on the head outputs",

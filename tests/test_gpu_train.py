@@ -349,8 +349,16 @@ def test_train_layer_vs_autograd(ops, case):
 def test_train_meta_unit_front_vs_autograd(ops):
     """Meta-Kernel -> BN(576) -> ReLU (dla_backbone.py:79-94), training mode: forward, gradient w.r.t. the
     input features and the MLP / BN parameters.  (The 1x1 aggregation conv + BN behind it is an ordinary
-    conv_bn layer: case conv1x1 of the wgrad tests and the slice test below.)"""
-    from oracle import dla_train_ref
+    conv_bn layer: case conv1x1 of the wgrad tests and the slice test below.)
+
+    The tensor-core Meta-Kernel is accurate to ~5e-6 of the largest output (split-bf16 products), i.e. ~5e-4
+    of a typical element; after the per-channel normalisation ~0.1 % of the 576-channel ReLU masks then differ
+    from the fp32 restatement, and a gradient that is a random-signed sum moves by sqrt(0.1 %) = 3 %
+    (measured, with the error concentrated in the masks).  To test the LOGIC of the backward tightly, the
+    reference is evaluated at our forward values (its own Meta-Kernel output replaced by ours, gradients still
+    flowing through its own graph); the unforced comparison only guards against gross errors (0.25: the
+    32-element bias gradients moved by 13 % in that run)."""
+    from oracle import dla_train_ref, meta_kernel_ref
     from rangedet_b200 import synth, train
     P = _layer_params()
     n = "res1_unit2"
@@ -359,25 +367,35 @@ def test_train_meta_unit_front_vs_autograd(ops):
     coord = torch.from_numpy(synth.range_image_coords(B_L, seed=0, h=H_L, w=W_L - 4, w_pad=W_L)).cuda()
     tg = train.TrainGraph({k: v.clone() for k, v in P.items()})
     tg.begin()
+    tg.debug = {}
     xp = ops.to_nhwc_padded(x)
     a = tg.meta_kernel_front(xp, coord, n)  # haloed NHWC bf16, tap-major channels k*64+c
-    ref = dla_train_ref.TrainRef(P, bf16=True)
-    xr = x.clone().requires_grad_(True)
-    ar = _ref_meta_unit(coord)(ref, xr)      # (B, c*9+k, H, W)
     to_ref = lambda t: t[:, 1:-1, 1:-1, :].reshape(B_L, H_L, W_L, 9, 64).permute(0, 4, 3, 1, 2).reshape(B_L, 576, H_L, W_L).float()
-    assert _maxrel(to_ref(a), ar.detach()) < 1e-2
-    da = _bf(torch.randn(ar.shape, device="cuda", generator=g))
+    da = _bf(torch.randn((B_L, 576, H_L, W_L), device="cuda", generator=g))
     da_p = torch.zeros_like(a)
     da_p[:, 1:-1, 1:-1, :] = da.reshape(B_L, 64, 9, H_L, W_L).permute(0, 3, 4, 2, 1).reshape(B_L, H_L, W_L, 576).to(torch.bfloat16)
     tg.seed_grad(a, da_p)
     tg.run_tape()
-    ar.backward(da)
-    # the tcgen05 Meta-Kernel carries ~2^-16 relative error, so a few more of the 576-channel ReLU masks differ
-    got = ops.from_nhwc_padded(tg.grad_of(xp))
-    assert _rms_rel(got, xr.grad) < 2e-2 and _maxrel(got, xr.grad) < 2e-1
-    for k in ("point_wise_mlp_bn1_gamma", "point_wise_mlp_bn1_beta", "_2656_mlp0_weight", "_2656_mlp0_bias", "_2656_mlp1_weight",
-              "_2656_mlp1_bias"):
-        assert _rms_rel(tg.pgrads[n + k], ref.P[n + k].grad) < 2e-2 and _maxrel(tg.pgrads[n + k], ref.P[n + k].grad) < 1e-1, k
+    m_ours = to_ref(tg.debug["meta_m"])
+    names = ("point_wise_mlp_bn1_gamma", "point_wise_mlp_bn1_beta", "_2656_mlp0_weight", "_2656_mlp0_bias", "_2656_mlp1_weight",
+             "_2656_mlp1_bias")
+    for forced, tol in ((True, 1e-2), (False, 0.25)):
+        ref = dla_train_ref.TrainRef(P, bf16=True)
+        xr = x.clone().requires_grad_(True)
+        m = ref.r(meta_kernel_ref.meta_baseline_bias(xr, coord, ref.P[n + "_2656_mlp0_weight"].reshape(32, 3),
+                                                     ref.P[n + "_2656_mlp0_bias"], ref.P[n + "_2656_mlp1_weight"].reshape(-1, 32),
+                                                     ref.P[n + "_2656_mlp1_bias"]))
+        assert _maxrel(m_ours, m) < 1e-2
+        if forced:
+            m = m + (m_ours - m).detach()
+        ar = ref.r(ref.bn(m, n + "point_wise_mlp_bn1").relu())
+        assert _maxrel(to_ref(a), ar) < 1e-2
+        ar.backward(da)
+        got = ops.from_nhwc_padded(tg.grad_of(xp))
+        assert _rms_rel(got, xr.grad) < tol, (forced, _rms_rel(got, xr.grad))
+        for k in names:
+            e = _rms_rel(tg.pgrads[n + k], ref.P[n + k].grad)
+            assert e < tol, (forced, k, e)
 
 
 def test_wide_dgrad_slices(ops):
@@ -417,3 +435,21 @@ def test_train_head_out_vs_autograd(ops):
     assert _maxrel(ops.from_nhwc_padded(tg.grad_of(xp)), xr.grad) < 1e-2
     assert _maxrel(tg.pgrads["rpn_reg_delta_lvl_0_weight"], ref.P["rpn_reg_delta_lvl_0_weight"].grad) < 1e-2
     assert _maxrel(tg.pgrads["rpn_reg_delta_lvl_0_bias"], ref.P["rpn_reg_delta_lvl_0_bias"].grad) < 1e-3
+
+
+@pytest.mark.parametrize("C,Cp,tap", [(64, 64, False), (8, 64, False), (576, 576, True), (1, 64, False)])
+def test_layout_conversions(ops, C, Cp, tap):
+    """NCHW fp32 <-> haloed NHWC bf16 (with the tap-major channel permutation of the Meta-Kernel unit): exact."""
+    N, H, W = 2, 3, 77
+    g = torch.Generator(device="cuda").manual_seed(C)
+    x = _bf(torch.randn((N, C, H, W), device="cuda", generator=g))
+    out = torch.zeros((N, H + 2, W + 2, Cp), device="cuda", dtype=torch.bfloat16)
+    ops.nchw_to_nhwc(x, out, tap_major=tap)
+    want = x.permute(0, 2, 3, 1)
+    if tap:
+        want = x.reshape(N, C // 9, 9, H, W).permute(0, 3, 4, 2, 1).reshape(N, H, W, C)
+    assert torch.equal(out[:, 1:-1, 1:-1, :C].float(), want)
+    assert float(out[:, 0].float().abs().max()) == 0 and float(out[:, :, -1].float().abs().max()) == 0
+    assert float(out[..., C:].float().abs().max()) == 0 if Cp > C else True
+    back = ops.nhwc_to_nchw(out, C, tap_major=tap)
+    assert torch.equal(back, x)
