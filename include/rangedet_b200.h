@@ -96,6 +96,30 @@ int rd_rotated_iou(const float* boxes1, const float* boxes2, float* ious, int64_
 int rd_batch_rotated_iou_max(const float* proposal, const float* gt, float* out, int B, int64_t N,
                              int G, int iou_type, rd_stream_t stream);
 
+/* ---- RPN loss head (training) ----------------------------------------------------------------
+ * Replaces, per pyramid level, RangeRpnHead.get_iou_target + get_vfl_loss + get_normalize_reg_loss
+ * (rangedet/symbol/head/builder.py:155-197, :350-422; rangedet/symbol/head/loss.py:4-30): ~45 MXNet ops
+ * incl. Decode3DBbox and the Python CustomOp 'batch_rotated_iou' -> one reduction + one fused kernel.
+ *   cls_logit (B,1,H,Wl) = (B,N)   reg_delta (B,8,H,Wl) = (B,8,N) planar, as the head produces them
+ *   pc (B,N,3)   gt (B,G,8) corners [or (B,G,7) for iou_type 1]   mask (B,N)
+ *   reg_target / reg_weight / reg_norm_weight (B,8,N)
+ * Outputs (any may be NULL to skip):
+ *   iou_target (B,N)  = max_g sanitise(IoU(decode(reg_delta, pc), gt_g))      (stop_gradient in the graph)
+ *   cls_loss (B,N)    = VFL(cls_logit, iou_target; alpha, gamma) * mask / (sum(mask)+1)
+ *   reg_loss (B,8,N)  = smooth_l1(reg_delta - reg_target; scalar) * weight * norm_weight /
+ *                       (sum(norm_weight)+1) * reg_loss_weight
+ *   d_cls (B,N), d_reg (B,8,N) = gradients of cls_grad_scale*sum(cls_loss) + reg_grad_scale*sum(reg_loss)
+ *                       w.r.t. cls_logit / reg_delta, i.e. what MakeLoss(grad_scale=...) back-propagates
+ *                       (cls: scale_loss_shift*cls_loss_weight, reg: scale_loss_shift; builder.py:374-378,417-421).
+ * iou_type: 0 = 'bev', 1 = '3d'.  workspace: rd_rpn_loss_workspace_bytes(), 8-byte aligned. */
+size_t rd_rpn_loss_workspace_bytes(void);
+int rd_rpn_loss(const float* cls_logit, const float* reg_delta, const float* pc, const float* gt,
+                const float* mask, const float* reg_target, const float* reg_weight,
+                const float* reg_norm_weight, int B, int64_t N, int G, int iou_type, float alpha, float gamma,
+                float smooth_l1_scalar, float cls_grad_scale, float reg_loss_weight, float reg_grad_scale,
+                float* iou_target, float* cls_loss, float* reg_loss, float* d_cls, float* d_reg,
+                void* workspace, size_t workspace_bytes, rd_stream_t stream);
+
 /* ---- weighted NMS ------------------------------------------------------------------------
  * Replaces processing_cxx.wnms_4c: point4_wnms_4c / trtplus::wnms_4c,
  * operator_cxx/src_cxx/nms.h:781-794, :452-577.
@@ -224,6 +248,21 @@ int rd_nhwc_bf16_to_nchw_f32(const void* src_pad, float* dst, int N, int H, int 
                              rd_stream_t stream);
 int rd_nchw_f32_to_nhwc_bf16(const float* src, void* dst_pad, int N, int H, int W, int C, int C_dst, int chmap,
                              rd_stream_t stream);
+
+/* ---- Parameter plumbing of the training step --------------------------------------------------
+ * One launch over flat buffers instead of one per parameter tensor (optim.cu).
+ * rd_gather_f32_to_bf16: dst[i] = bf16(idx[i] >= 0 ? src[idx[i]] : 0) -- re-packs every bf16 conv operand
+ *   (forward / data-gradient / deconv layouts) from the flat fp32 master parameters.
+ * rd_gather_f32:         dst[i] = idx[i] >= 0 ? src[idx[i]] : 0      -- collects every parameter gradient from
+ *   the kernels' native output layouts into the flat buffer that is all-reduced (tools/train.py:364-368).
+ * rd_sgd_mom_update: MXNet sgd_mom_update with fp32 masters (tools/train.py:306-319, 359-361):
+ *   g = clip(rescale*grad, +-clip) + wd[i]*w;  mom = momentum*mom - lr*g;  w += mom
+ *   hyper = DEVICE pointer to {lr, momentum, rescale_grad, clip_gradient (<= 0: off)}; wd[i] is per element
+ *   (0 for *_bias / *_beta like Optimizer.set_wd_mult). */
+int rd_gather_f32_to_bf16(const float* src, const int* idx, void* dst, int64_t n, rd_stream_t stream);
+int rd_gather_f32(const float* src, const int* idx, float* dst, int64_t n, rd_stream_t stream);
+int rd_sgd_mom_update(float* weight, const float* grad, float* mom, const float* wd, const float* hyper,
+                      int64_t n, rd_stream_t stream);
 
 /* ---- tcgen05 self-test -------------------------------------------------------------------
  * D(128 x n) = A(128 x k) . B(n x k)^T with bf16 operands staged in shared memory in the

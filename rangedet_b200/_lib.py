@@ -32,6 +32,8 @@ SIGNATURES = {
     "rd_decode_3d_bbox": (_i, [_vp, _vp, _vp, _i64, _i, _vp]),
     "rd_rotated_iou": (_i, [_vp, _vp, _vp, _i64, _i64, _i, _vp]),
     "rd_batch_rotated_iou_max": (_i, [_vp, _vp, _vp, _i, _i64, _i, _i, _vp]),
+    "rd_rpn_loss_workspace_bytes": (_sz, []),
+    "rd_rpn_loss": (_i, [_vp] * 8 + [_i, _i64, _i, _i] + [_f] * 6 + [_vp] * 5 + [_vp, _sz, _vp]),
     "rd_wnms_4c_workspace_bytes": (_sz, [_i]),
     "rd_wnms_4c": (_i, [_vp, _i, _f, _f, _i, _i, _vp, _vp, ctypes.POINTER(_i), _vp, _sz, _vp]),
     "rd_nms3d_workspace_bytes": (_sz, [_i, _i]),
@@ -51,6 +53,9 @@ SIGNATURES = {
     "rd_add_nhwc_bf16": (_i, [_vp] * 3 + [_i] * 4 + [_vp]),
     "rd_nhwc_bf16_to_nchw_f32": (_i, [_vp, _vp] + [_i] * 6 + [_vp]),
     "rd_nchw_f32_to_nhwc_bf16": (_i, [_vp, _vp] + [_i] * 6 + [_vp]),
+    "rd_gather_f32_to_bf16": (_i, [_vp, _vp, _vp, _i64, _vp]),
+    "rd_gather_f32": (_i, [_vp, _vp, _vp, _i64, _vp]),
+    "rd_sgd_mom_update": (_i, [_vp] * 5 + [_i64, _vp]),
     "rd_tc_probe_gemm": (_i, [_vp, _vp, _vp, _i, _i, _i, _vp]),
     "rd_tma_probe": (_i, [_vp, _vp, _vp] + [_i] * 7 + [_vp]),
 }

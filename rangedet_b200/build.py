@@ -26,6 +26,7 @@ PER_FILE = {
     "decode_iou.cu": ["-fmad=false"],
     "wnms.cu": ["-fmad=false"],
     "nms3d.cu": ["-fmad=false"],
+    "rpn_loss.cu": ["-fmad=false"],
 }
 
 

@@ -11,6 +11,7 @@ device memory and streams.  No function here has a CPU path.
   mx.nd.contrib.RotatedIOU      (rotated_iou.cc:12-60)       rotated_iou
   Custom op 'batch_rotated_iou' (batch_rotated_iou.py)       batch_rotated_iou
   processing_cxx.wnms_4c        (pybinding.cpp:8)            rangedet_b200.processing_cxx.wnms_4c
+  RangeRpnHead.get_fpn_loss, one level (builder.py:300-422)  rpn_loss
 """
 import ctypes
 
@@ -271,6 +272,54 @@ def batch_rotated_iou(proposal, gt_bbox, iou_type="bev"):
     return out
 
 
+def rpn_loss(cls_logit, reg_delta, pc, gt_bbox, mask, reg_target, reg_weight, reg_norm_weight, iou_type="bev",
+             alpha=1.0, gamma=2.0, smooth_l1_scalar=3.0, scale_loss_shift=128.0, cls_loss_weight=10.0,
+             reg_loss_weight=8.0, want_loss=True, out=None):
+    """One pyramid level of RangeRpnHead.get_fpn_loss (rangedet/symbol/head/builder.py:300-348): get_iou_target
+    (:155-197, Decode3DBbox + 'batch_rotated_iou', stop_gradient) -> get_vfl_loss (:350-379, loss.py:4-30) and
+    get_normalize_reg_loss (:381-422), fused.  Hyper-parameters default to config/rangedet/
+    rangedet_veh_wo_aug_4_18e.py:36,122-129.
+
+    cls_logit (B,1,H,W)  reg_delta (B,8,H,W)  pc (B,H*W,3)  gt_bbox (B,G,8|7)  mask (B,1,H,W)
+    reg_target / reg_weight / reg_norm_weight (B,8,H,W)
+    -> dict(iou_target (B,1,H,W), cls_loss (B,1,H,W), reg_loss (B,8,H,W), d_cls, d_reg): the loss tensors are
+    the graph outputs `rpn_cls_loss_s*` / `rpn_reg_loss_s*`; d_cls / d_reg are the gradients MakeLoss
+    (grad_scale = scale_loss_shift * cls_loss_weight resp. scale_loss_shift) sends into the head outputs.
+    `out`: optional dict of preallocated outputs (static addresses for CUDA-graph capture)."""
+    if iou_type not in ("bev", "3d"):
+        raise ValueError("Unknown iou type!")
+    x = _chk(cls_logit, "cls_logit", 4)
+    d = _chk(reg_delta, "reg_delta", 4)
+    B, _, H, W = d.shape
+    N = H * W
+    if tuple(x.shape) != (B, 1, H, W) or d.shape[1] != 8:
+        raise ValueError("cls_logit must be (B,1,H,W) and reg_delta (B,8,H,W)")
+    pc = _chk(pc, "pc", 3, 3)
+    gt = _chk(gt_bbox, "gt_bbox", 3, 8 if iou_type == "bev" else 7)
+    m = _chk(mask, "mask")
+    rt, rw, rn = _chk(reg_target, "reg_target", 4), _chk(reg_weight, "reg_weight", 4), _chk(reg_norm_weight, "reg_norm_weight", 4)
+    if tuple(pc.shape[:2]) != (B, N) or gt.shape[0] != B or m.numel() != B * N or any(tuple(t.shape) != (B, 8, H, W) for t in (rt, rw, rn)):
+        raise ValueError("rpn_loss: inconsistent shapes")
+    dev = d.device
+    o = dict(out) if out is not None else {}
+    for k, shp in (("iou_target", (B, 1, H, W)), ("cls_loss", (B, 1, H, W)), ("reg_loss", (B, 8, H, W)),
+                   ("d_cls", (B, 1, H, W)), ("d_reg", (B, 8, H, W))):
+        if k not in o:
+            o[k] = torch.empty(shp, device=dev) if (want_loss or k in ("d_cls", "d_reg")) else None
+    L = _lib.lib()
+    ws = _workspace(int(L.rd_rpn_loss_workspace_bytes()), dev, "rpn_loss")
+    nul = ctypes.c_void_p(0)
+    pp = lambda t: nul if t is None else _p(t)
+    with torch.cuda.device(dev):
+        st = L.rd_rpn_loss(_p(x), _p(d), _p(pc), _p(gt), _p(m), _p(rt), _p(rw), _p(rn), B, N, gt.shape[1],
+                           0 if iou_type == "bev" else 1, float(alpha), float(gamma), float(smooth_l1_scalar),
+                           float(scale_loss_shift * cls_loss_weight), float(reg_loss_weight), float(scale_loss_shift),
+                           pp(o["iou_target"]), pp(o["cls_loss"]), pp(o["reg_loss"]), pp(o["d_cls"]), pp(o["d_reg"]),
+                           _p(ws), ctypes.c_size_t(ws.numel()), _stream())
+    _lib.check(st, "rpn_loss")
+    return o
+
+
 def wnms_4c_device(dets, thresh, thresh_vote, is_3d=False, hash_scale=100):
     """Device-resident weighted NMS: dets (N,12) CUDA float32 -> (out_dets (K,12), keep_inds (K) int32)."""
     d = _chk(dets, "dets", 2, 12)
@@ -375,21 +424,22 @@ def from_nhwc_padded(y_pad, channels=None):
     return y.permute(0, 3, 1, 2).float().contiguous()
 
 
-def pack_conv_weight(w_oihw, cin=None, cout=None):
-    """(Cout,Cin,kh,kw) -> bf16 [kh*kw][Cout'][Cin'] (zero padded), the layout rd_conv2d_nhwc_bf16 expects."""
+def pack_conv_weight(w_oihw, cin=None, cout=None, dtype=torch.bfloat16):
+    """(Cout,Cin,kh,kw) -> bf16 [kh*kw][Cout'][Cin'] (zero padded), the layout rd_conv2d_nhwc_bf16 expects.
+    (`dtype` other than bf16: used to push element INDICES through the same permutation, see train.py.)"""
     co, ci, kh, kw = w_oihw.shape
     cin, cout = cin or ci, cout or co
-    out = torch.zeros((kh * kw, cout, cin), device=w_oihw.device, dtype=torch.bfloat16)
-    out[:, :co, :ci] = w_oihw.permute(2, 3, 0, 1).reshape(kh * kw, co, ci).to(torch.bfloat16)
+    out = torch.zeros((kh * kw, cout, cin), device=w_oihw.device, dtype=dtype)
+    out[:, :co, :ci] = w_oihw.permute(2, 3, 0, 1).reshape(kh * kw, co, ci).to(dtype)
     return out
 
 
-def pack_deconv_weight(w_iohw, cin=None, cout=None):
+def pack_deconv_weight(w_iohw, cin=None, cout=None, dtype=torch.bfloat16):
     """MXNet/torch transposed-conv weight (Cin,Cout,kh,kw) -> bf16 [kh*kw][Cout'][Cin'] (zero padded)."""
     ci, co, kh, kw = w_iohw.shape
     cin, cout = cin or ci, cout or co
-    out = torch.zeros((kh * kw, cout, cin), device=w_iohw.device, dtype=torch.bfloat16)
-    out[:, :co, :ci] = w_iohw.permute(2, 3, 1, 0).reshape(kh * kw, co, ci).to(torch.bfloat16)
+    out = torch.zeros((kh * kw, cout, cin), device=w_iohw.device, dtype=dtype)
+    out[:, :co, :ci] = w_iohw.permute(2, 3, 1, 0).reshape(kh * kw, co, ci).to(dtype)
     return out
 
 
@@ -489,7 +539,7 @@ def _chk_nhwc(t, name):
         raise TypeError("%s must be a contiguous CUDA bf16 haloed NHWC tensor" % name)
 
 
-def conv2d_wgrad(a_pad, b_pad, ksize, stride_w=1):
+def conv2d_wgrad(a_pad, b_pad, ksize, stride_w=1, out=None):
     """G[tap][a][b] = sum_pixels A[p][a] * B[p + tap][b] -> fp32 (ksize*ksize, CA, CB).
     a_pad (N,H+2,W+2,CA) and b_pad (N,H+2,W*stride_w+2,CB): haloed NHWC bf16.  With A = grad of the conv
     output and B = the conv input this is the gradient of the packed forward weight [tap][Cout][Cin]."""
@@ -506,7 +556,10 @@ def conv2d_wgrad(a_pad, b_pad, ksize, stride_w=1):
     if nb == 0:
         raise RuntimeError("rangedet_b200.conv2d_wgrad: %s" % _lib.last_error())
     ws = _workspace(nb, a_pad.device, "wgrad")
-    g = torch.empty((ksize * ksize, CA, CB), device=a_pad.device, dtype=torch.float32)
+    g = out if out is not None else torch.empty((ksize * ksize, CA, CB), device=a_pad.device, dtype=torch.float32)
+    if g.dtype != torch.float32 or g.numel() != ksize * ksize * CA * CB or not g.is_contiguous():
+        raise ValueError("conv2d_wgrad: out must be a contiguous float32 tensor of %d elements" % (ksize * ksize * CA * CB))
+    g = g.view(ksize * ksize, CA, CB)
     with torch.cuda.device(a_pad.device):
         st = L.rd_conv2d_wgrad_nhwc_bf16(_p(a_pad), _p(b_pad), _p(g), N, H, W, CA, CB, ksize, stride_w, _p(ws), nb,
                                          _stream())
@@ -555,7 +608,8 @@ def bn_act_fwd(z_pad, coef, relu=True, res_before=None, res_after=None, out=None
     return out
 
 
-def bn_act_bwd(dy_pad, z_pad, coef, mask_mode, y_mask=None, dz_halo_w=1, dz_out=None, want_g=False, g_out=None):
+def bn_act_bwd(dy_pad, z_pad, coef, mask_mode, y_mask=None, dz_halo_w=1, dz_out=None, want_g=False, g_out=None,
+               dgb_out=None):
     """Backward of bn_act_fwd w.r.t. z, gamma, beta (and the masked gradient g that flows into res_before).
     Returns (dz, dgamma, dbeta, g or None).  dz has a W halo of dz_halo_w pixels."""
     _chk_nhwc(dy_pad, "dy_pad")
@@ -568,8 +622,9 @@ def bn_act_bwd(dy_pad, z_pad, coef, mask_mode, y_mask=None, dz_halo_w=1, dz_out=
         dz_out = torch.zeros((N, Hp, W + 2 * dz_halo_w, C), device=z_pad.device, dtype=torch.bfloat16)
     if want_g and g_out is None:
         g_out = torch.zeros_like(z_pad)
-    dgamma = torch.empty(C, device=z_pad.device, dtype=torch.float32)
-    dbeta = torch.empty(C, device=z_pad.device, dtype=torch.float32)
+    if dgb_out is None:
+        dgb_out = torch.empty((2, C), device=z_pad.device, dtype=torch.float32)
+    dgamma, dbeta = dgb_out.view(2, C)[0], dgb_out.view(2, C)[1]
     L = _lib.lib()
     nb = L.rd_bn_workspace_bytes(C) + 8 * C * 4
     ws = _workspace(nb, z_pad.device, "bn")
@@ -582,11 +637,12 @@ def bn_act_bwd(dy_pad, z_pad, coef, mask_mode, y_mask=None, dz_halo_w=1, dz_out=
     return dz_out, dgamma, dbeta, g_out
 
 
-def channel_sums(x_pad):
+def channel_sums(x_pad, out=None):
     """sums[c] = sum over interior pixels (fp32)."""
     _chk_nhwc(x_pad, "x_pad")
     N, Hp, Wp, C = x_pad.shape
-    out = torch.empty(C, device=x_pad.device, dtype=torch.float32)
+    if out is None:
+        out = torch.empty(C, device=x_pad.device, dtype=torch.float32)
     L = _lib.lib()
     nb = L.rd_bn_workspace_bytes(C) + 8 * C * 4
     ws = _workspace(nb, x_pad.device, "bn")
@@ -636,3 +692,40 @@ def nchw_to_nhwc(src, out, tap_major=False):
         st = _lib.lib().rd_nchw_f32_to_nhwc_bf16(_p(src), _p(out), N, H, W, C, out.shape[3], int(bool(tap_major)), _stream())
     _lib.check(st, "nchw_to_nhwc")
     return out
+
+
+# ------------------------------------------------------------------------------------------------
+# Parameter plumbing: flat gathers and the SGD update (optim.cu)
+# ------------------------------------------------------------------------------------------------
+def gather_to_bf16(src, idx, out):
+    """out[i] = bf16(src[idx[i]]) (0 where idx[i] < 0); src fp32 flat, idx int32, out bf16, all CUDA."""
+    if src.dtype != torch.float32 or idx.dtype != torch.int32 or out.dtype != torch.bfloat16 or idx.numel() != out.numel():
+        raise TypeError("gather_to_bf16: src float32, idx int32 and out bfloat16 of equal length expected")
+    with torch.cuda.device(src.device):
+        st = _lib.lib().rd_gather_f32_to_bf16(_p(src), _p(idx), _p(out), idx.numel(), _stream())
+    _lib.check(st, "gather_to_bf16")
+    return out
+
+
+def gather_f32(src, idx, out):
+    """out[i] = src[idx[i]] (0 where idx[i] < 0); fp32 -> fp32."""
+    if src.dtype != torch.float32 or idx.dtype != torch.int32 or out.dtype != torch.float32 or idx.numel() != out.numel():
+        raise TypeError("gather_f32: src / out float32 and idx int32 of equal length expected")
+    with torch.cuda.device(src.device):
+        st = _lib.lib().rd_gather_f32(_p(src), _p(idx), _p(out), idx.numel(), _stream())
+    _lib.check(st, "gather_f32")
+    return out
+
+
+def sgd_mom_update(weight, grad, mom, wd, hyper):
+    """MXNet sgd_mom_update on flat fp32 buffers, in place (weight, mom).  hyper: CUDA float32 tensor
+    [lr, momentum, rescale_grad, clip_gradient]; wd: per-element weight decay."""
+    n = weight.numel()
+    for t in (weight, grad, mom, wd):
+        if t.dtype != torch.float32 or not t.is_cuda or not t.is_contiguous() or t.numel() != n:
+            raise TypeError("sgd_mom_update: flat contiguous CUDA float32 buffers of equal length expected")
+    if hyper.dtype != torch.float32 or hyper.numel() < 4 or not hyper.is_cuda:
+        raise TypeError("sgd_mom_update: hyper must be a CUDA float32 tensor [lr, momentum, rescale, clip]")
+    with torch.cuda.device(weight.device):
+        st = _lib.lib().rd_sgd_mom_update(_p(weight), _p(grad), _p(mom), _p(wd), _p(hyper), n, _stream())
+    _lib.check(st, "sgd_mom_update")

@@ -132,3 +132,75 @@ def decode_inputs(batch, n, seed=4):
     az = rng.uniform(-np.pi, np.pi, (batch, n))
     pc = np.stack([r * np.cos(az), r * np.sin(az), rng.uniform(-2, 3, (batch, n))], -1).astype(np.float32)
     return delta, pc
+
+
+def encode_box8(b7, px, py):
+    """Inverse of the non-bin decode (operator_cxx/contrib/decode_3d_bbox-inl.h:186-235): regression target
+    [dx, dy, log w, log l, cos, sin, z0, log h] of box b7 = [cx,cy,cz,l,w,h,yaw] seen from point (px,py)."""
+    cx, cy, cz, l, w, h, yaw = [np.asarray(b7[..., i], np.float64) for i in range(7)]
+    az = np.arctan2(py, px)
+    ox, oy = cx - px, cy - py
+    rx = ox * np.cos(az) + oy * np.sin(az)
+    ry = -ox * np.sin(az) + oy * np.cos(az)
+    cols = [np.sign(rx) * np.sqrt(np.abs(rx)), np.sign(ry) * np.sqrt(np.abs(ry)), np.log(w), np.log(l),
+            np.cos(yaw - az), np.sin(yaw - az), cz - h / 2, np.log(h)]
+    out = np.stack(np.broadcast_arrays(*cols), -1)
+    return out.astype(np.float32)
+
+
+def rpn_targets(batch, seed=5, n_vehicles=30, strides=(1, 2, 4), h=H_RANGE, w=W_RANGE, w_pad=W_PADDED, n_gt=200,
+                missing=0.10):
+    """Synthetic roidb record(s) with the post-transform shapes and names of the training graph's inputs
+    (config/rangedet/rangedet_veh_wo_aug_4_18e.py:367-378, rangedet/core/input.py:452-506,561-624):
+    ~n_vehicles vehicles per frame whose points are assigned to them.
+      rpn_reg_target_s{s}, rpn_reg_weight_s{s}, reg_normalize_weight_s{s}  (B,8,h,w_pad/s)
+      range_image_mask_s{s} (B,1,h,w_pad/s)   pc_vehicle_frame_s{s} (B,h*w_pad/s,3)
+      gt_bbox_veh_for_iou_pred (B,200,8), padded per input.py:264-265."""
+    rng = np.random.default_rng(seed)
+    incl = np.linspace(-0.31, 0.04, h, dtype=np.float64)[:, None]
+    azim = np.linspace(np.pi, -np.pi, w, dtype=np.float64)[None, :]
+    xyz = np.zeros((batch, 3, h, w_pad), np.float32)
+    tgt = np.zeros((batch, 8, h, w_pad), np.float32)
+    wgt = np.zeros((batch, 8, h, w_pad), np.float32)
+    nrm = np.zeros((batch, 8, h, w_pad), np.float32)
+    msk = np.zeros((batch, 1, h, w_pad), np.float32)
+    gt = np.zeros((batch, n_gt, 8), np.float32)
+    gt[:, :, 3:7] = np.float32(1e-3)
+    for b in range(batch):
+        r = rng.uniform(2.0, 75.0, size=(h, w))
+        x = r * np.cos(incl) * np.cos(azim)
+        y = r * np.cos(incl) * np.sin(azim)
+        z = r * np.sin(incl)
+        valid = rng.uniform(size=(h, w)) >= missing
+        b7 = boxes7(n_vehicles, seed * 1000 + b)
+        rc = rng.uniform(8.0, 60.0, n_vehicles)
+        ac = rng.uniform(-np.pi, np.pi, n_vehicles)
+        b7[:, 0], b7[:, 1] = rc * np.cos(ac), rc * np.sin(ac)
+        gt[b, :n_vehicles] = boxes7_to_corners10(b7)[:, :8]
+        for v in range(n_vehicles):
+            half = max(2, int(np.arctan2(2.0, rc[v]) / (2 * np.pi) * w))
+            c0 = int((np.pi - ac[v]) / (2 * np.pi) * (w - 1))
+            cols = np.arange(max(c0 - half, 0), min(c0 + half + 1, w))
+            nrow = min(6, h)
+            r0 = int(rng.integers(min(8, h - nrow), max(h - 8 - nrow, min(8, h - nrow)) + 1))
+            rows = np.arange(r0, r0 + nrow)
+            hh, ww = np.meshgrid(rows, cols, indexing="ij")
+            # points on the vehicle: within ~1 m of its centre
+            x[hh, ww] = b7[v, 0] + rng.uniform(-1, 1, hh.shape)
+            y[hh, ww] = b7[v, 1] + rng.uniform(-1, 1, hh.shape)
+            z[hh, ww] = b7[v, 2] + rng.uniform(-0.5, 0.5, hh.shape)
+            valid[hh, ww] = True
+            tgt[b][:, hh, ww] = np.moveaxis(encode_box8(b7[v], x[hh, ww], y[hh, ww]), -1, 0)
+            wgt[b][:, hh, ww] = 1.0
+            nrm[b][:, hh, ww] = 1.0 / hh.size
+        p = np.stack([x, y, z], 0) * valid[None]
+        xyz[b, :, :, :w] = p.astype(np.float32)
+        msk[b, 0, :, :w] = valid
+    out = {"gt_bbox_veh_for_iou_pred": gt}
+    for s in strides:
+        out["rpn_reg_target_s%d" % s] = np.ascontiguousarray(tgt[..., ::s])
+        out["rpn_reg_weight_s%d" % s] = np.ascontiguousarray(wgt[..., ::s])
+        out["reg_normalize_weight_s%d" % s] = np.ascontiguousarray(nrm[..., ::s])
+        out["range_image_mask_s%d" % s] = np.ascontiguousarray(msk[..., ::s])
+        out["pc_vehicle_frame_s%d" % s] = np.ascontiguousarray(xyz[..., ::s].reshape(batch, 3, -1).transpose(0, 2, 1))
+    return out

@@ -38,6 +38,52 @@ def _cout_pad(c):
     return 64 if c <= 64 else 128
 
 
+def pack_operand(w, kind, ci_p, co_p, S=1, dtype=torch.bfloat16):
+    """bf16 operand copy of a conv / deconv weight in the layout one of the kernels consumes.  A pure index
+    permutation + zero padding, so it is also applied to tensors of element INDICES (dtype float64) to build the
+    gather map of TrainGraph.enable_flat()."""
+    if kind == "fwd":          # conv, cross-correlation: [tap][co][ci]
+        return ops.pack_conv_weight(w, ci_p, co_p, dtype)
+    if kind == "fwd_tapmajor":  # 1x1 aggregation conv over tap-major Meta-Kernel channels
+        return ops.pack_conv_weight(ops.tap_major_weight(w, w.shape[1] // 9), ci_p, co_p, dtype)
+    if kind == "dgrad":        # stride 1: flipped taps, transposed channels: [tap][ci][co]
+        return ops.pack_conv_weight(w.flip(2, 3).transpose(0, 1), co_p, ci_p, dtype)
+    if kind == "dgrad_tapmajor":
+        return ops.pack_conv_weight(ops.tap_major_weight(w, w.shape[1] // 9).transpose(0, 1), co_p, ci_p, dtype)
+    if kind == "dgrad_s2":     # W-stride 2: transposed conv (3,3)/(1,2), taps not flipped; 1x1 -> centre tap
+        if w.shape[2] == 1:
+            w3 = torch.zeros((w.shape[0], w.shape[1], 3, 3), device=w.device, dtype=w.dtype)
+            w3[:, :, 1, 1] = w[:, :, 0, 0]
+            w = w3
+        return ops.pack_deconv_weight(w, co_p, ci_p, dtype)  # (Cin_t = co, Cout_t = ci)
+    if kind == "deconv_fwd":
+        return ops.pack_deconv_weight(w, ci_p, co_p, dtype)
+    if kind == "deconv_dgrad":  # 3x3 stride-1 conv over the phase-grouped dz: [tap][ci][(ph,co)]
+        ci, co, _, KW = w.shape
+        pad = KW // 4
+        g = torch.zeros((3, 3, ci_p, S, co_p), device=w.device, dtype=w.dtype)
+        for tx in range(3):
+            for ph in range(S):
+                kx = ph + pad - (1 - tx) * S
+                if 0 <= kx < KW:
+                    g[:, tx, :ci, ph, :co] = w[:, :, :, kx].permute(2, 0, 1)
+        return g.reshape(9, ci_p, S * co_p).to(dtype).contiguous()
+    raise KeyError(kind)
+
+
+def _index_like(t, base):
+    """float64 tensor shaped like t holding base+1, base+2, ... (0 stays free to mean 'zero padding')."""
+    return (torch.arange(t.numel(), device=t.device, dtype=torch.float64) + (base + 1)).reshape(t.shape)
+
+
+def _to_map(ix):
+    return (ix.reshape(-1).to(torch.int64) - 1).to(torch.int32)
+
+
+def _align(n, a=64):
+    return (n + a - 1) // a * a
+
+
 class _Pool:
     """Named activation / gradient buffers reused across steps.  Kernels only ever write the interior, so
     a haloed buffer zero-initialised once keeps a valid zero halo."""
@@ -68,47 +114,110 @@ class TrainGraph(object):
         self.nograd = set()
         self._n = 0
         self.debug = None  # set to a dict to capture intermediates (diagnostics)
+        # flat mode (enable_flat): one gather launch packs every operand, one collects every gradient
+        self.packed32 = {}
+        self.pack_rec, self.pack32_rec = {}, {}
+        self.flat_pack = False
+        self.flat_grads = False
+        self.arena = None          # fp32 scratch all parameter-gradient kernels write into (flat mode)
+        self.g_sizes, self._gn = [], 0
+        self.pg_rec = {}
 
     # ---- parameter packing (bf16 operand copies; call refresh() after an optimiser step) -------------
     def refresh(self):
+        if self.flat_pack:
+            ops.gather_to_bf16(self.flatP, self.pmap, self.packed_flat)
+            if self.pmap32.numel():
+                ops.gather_f32(self.flatP, self.pmap32, self.packed32_flat)
+            return
         self.packed = {}
+        self.packed32 = {}
+
+    def enable_flat(self, flatP, offsets, flat_g, run_step):
+        """Switch to flat mode.  `flatP`: flat fp32 buffer holding every trainable parameter, `offsets[name]` its
+        element offset (self.P[name] must already be views of it); `flat_g`: flat gradient buffer with the same
+        layout; `run_step()`: runs one eager forward + backward.  Must follow at least one eager step (so every
+        operand key and gradient source is recorded).  Afterwards
+          refresh()   = ONE gather launch re-packing all bf16 operands (+ one for the small fp32 ones),
+          backward()  = ... + ONE gather launch collecting all parameter gradients into flat_g."""
+        dev = flatP.device
+        self.flatP, self.flat_g, self.offsets = flatP, flat_g, offsets
+        # -- operands: push element indices through the same packing functions
+        keys = sorted(self.pack_rec)
+        sizes = [_align(self.packed[k].numel(), 128) for k in keys]
+        self.packed_flat = torch.zeros(sum(sizes), device=dev, dtype=torch.bfloat16)
+        self.pmap = torch.full((sum(sizes),), -1, device=dev, dtype=torch.int32)
+        o, views = 0, {}
+        for k, n in zip(keys, sizes):
+            w = self.P[k[0] + "_weight"]
+            ix = pack_operand(_index_like(w, offsets[k[0] + "_weight"]), k[1], *self.pack_rec[k], dtype=torch.float64)
+            assert ix.shape == self.packed[k].shape
+            self.pmap[o:o + ix.numel()] = _to_map(ix)
+            views[k] = self.packed_flat[o:o + ix.numel()].view(ix.shape)
+            o += n
+        keys32 = sorted(self.pack32_rec)
+        ix32 = []
+        for k in keys32:
+            names, fn = self.pack32_rec[k]
+            ix32.append(fn(*[_index_like(self.P[n], offsets[n]) for n in names]))
+        sizes32 = [_align(t.numel(), 64) for t in ix32]
+        self.packed32_flat = torch.zeros(sum(sizes32), device=dev, dtype=torch.float32)
+        self.pmap32 = torch.full((sum(sizes32),), -1, device=dev, dtype=torch.int32)
+        o, views32 = 0, {}
+        for k, ix, n in zip(keys32, ix32, sizes32):
+            self.pmap32[o:o + ix.numel()] = _to_map(ix)
+            views32[k] = self.packed32_flat[o:o + ix.numel()].view(ix.shape)
+            o += n
+        self.packed, self.packed32 = views, views32
+        self.flat_pack = True
+        # -- gradients: every producing kernel writes into one arena; record where each gradient element lives
+        self.g_offsets, o = [], 0
+        for n in self.g_sizes:
+            self.g_offsets.append(o)
+            o += _align(n, 64)
+        self.arena = torch.zeros(max(o, 64), device=dev, dtype=torch.float32)
+        self.arena_sizes = list(self.g_sizes)
+        run_step()   # eager, arena-backed: pg_rec now refers to arena views
+        gmap = torch.full((flat_g.numel(),), -1, device=dev, dtype=torch.int32)
+        seen = set()
+        for name, (src, fn) in self.pg_rec.items():
+            if name not in offsets:
+                continue
+            base = (src.data_ptr() - self.arena.data_ptr()) // 4
+            assert 0 <= base and base + src.numel() <= self.arena.numel(), name
+            ix = _index_like(src, base)
+            ix = fn(ix) if fn is not None else ix
+            n = self.P[name].numel()
+            assert ix.numel() == n, (name, tuple(ix.shape), tuple(self.P[name].shape))
+            gmap[offsets[name]:offsets[name] + n] = _to_map(ix)
+            seen.add(name)
+        # parameters the graph does not use (e.g. the Meta-Kernel MLP when use_meta=False) keep gmap = -1: zero gradient
+        self.no_grad_params = sorted(n for n in offsets if n not in seen)
+        self.gmap = gmap
+        self.flat_grads = True
 
     def _w(self, name, kind, ci_p, co_p, S=1):
         key = (name, kind)
         t = self.packed.get(key)
         if t is not None:
             return t
-        w = self.P[name + "_weight"]
-        if kind == "fwd":          # conv, cross-correlation: [tap][co][ci]
-            t = ops.pack_conv_weight(w, ci_p, co_p)
-        elif kind == "fwd_tapmajor":  # 1x1 aggregation conv over tap-major Meta-Kernel channels
-            t = ops.pack_conv_weight(ops.tap_major_weight(w, w.shape[1] // 9), ci_p, co_p)
-        elif kind == "dgrad":      # stride 1: flipped taps, transposed channels: [tap][ci][co]
-            t = ops.pack_conv_weight(w.flip(2, 3).transpose(0, 1), co_p, ci_p)
-        elif kind == "dgrad_tapmajor":
-            t = ops.pack_conv_weight(ops.tap_major_weight(w, w.shape[1] // 9).transpose(0, 1), co_p, ci_p)
-        elif kind == "dgrad_s2":   # W-stride 2: transposed conv (3,3)/(1,2), taps not flipped; 1x1 -> centre tap
-            if w.shape[2] == 1:
-                w3 = torch.zeros((w.shape[0], w.shape[1], 3, 3), device=w.device, dtype=w.dtype)
-                w3[:, :, 1, 1] = w[:, :, 0, 0]
-                w = w3
-            t = ops.pack_deconv_weight(w, co_p, ci_p)  # (Cin_t = co, Cout_t = ci)
-        elif kind == "deconv_fwd":
-            t = ops.pack_deconv_weight(w, ci_p, co_p)
-        elif kind == "deconv_dgrad":  # 3x3 stride-1 conv over the phase-grouped dz: [tap][ci][(ph,co)]
-            ci, co, _, KW = w.shape
-            pad = KW // 4
-            g = torch.zeros((3, 3, ci_p, S, co_p), device=w.device, dtype=torch.float32)
-            for tx in range(3):
-                for ph in range(S):
-                    kx = ph + pad - (1 - tx) * S
-                    if 0 <= kx < KW:
-                        g[:, tx, :ci, ph, :co] = w[:, :, :, kx].permute(2, 0, 1)
-            t = g.reshape(9, ci_p, S * co_p).to(torch.bfloat16).contiguous()
-        else:
-            raise KeyError(kind)
+        if self.flat_pack:
+            raise KeyError("operand %s was not recorded before enable_flat()" % (key,))
+        self.pack_rec[key] = (ci_p, co_p, S)
+        t = pack_operand(self.P[name + "_weight"], kind, ci_p, co_p, S)
         self.packed[key] = t
         return t
+
+    def _p32(self, key, names, fn):
+        """Small fp32 operand derived from parameters by a pure index permutation / zero padding `fn`
+        (padded head bias, tap-major BN(576) vectors).  Flat mode: a view of the buffer refresh() gathers."""
+        t = self.packed32.get(key)
+        if t is not None:
+            return t
+        if self.flat_pack:
+            raise KeyError("operand %s was not recorded before enable_flat()" % (key,))
+        self.pack32_rec[key] = (names, fn)
+        return fn(*[self.P[n] for n in names])
 
     # ---- tape helpers ---------------------------------------------------------------------------------
     def _buf(self, tag, shape):
@@ -125,6 +234,24 @@ class TrainGraph(object):
     def begin(self):
         """Start a new step: empty tape, no gradients."""
         self.tape, self.grads, self.pgrads, self.nograd, self._n = [], {}, {}, set(), 0
+        self._gn = 0
+        if self.arena is None:
+            self.g_sizes = []
+
+    def _gbuf(self, shape):
+        """fp32 output buffer of a parameter-gradient kernel: fresh memory (eager mode) or the next slot of the
+        gradient arena (flat mode; slots are handed out in the fixed order of the tape)."""
+        n = 1
+        for d in shape:
+            n *= int(d)
+        if self.arena is None:
+            self.g_sizes.append(n)
+            return torch.empty(tuple(shape), device=self.device, dtype=torch.float32)
+        i = self._gn
+        self._gn += 1
+        assert self.arena_sizes[i] == n, "gradient arena slot %d: %d elements expected, %d requested" % (i, self.arena_sizes[i], n)
+        o = self.g_offsets[i]
+        return self.arena[o:o + n].view(tuple(shape))
 
     def seed_grad(self, t, g):
         """Set the gradient of activation t (haloed NHWC bf16) before run_tape()."""
@@ -138,8 +265,21 @@ class TrainGraph(object):
             fn()
         self.tape = []
 
-    def _pg(self, name, g):
-        self.pgrads[name] = g if name not in self.pgrads else self.pgrads[name] + g
+    def _pg(self, name, src, fn=None, copy=False):
+        """Gradient of parameter `name` = fn(src): `src` is what a kernel wrote (into a _gbuf() buffer, or anywhere
+        with copy=True), `fn` a pure view / permutation into the parameter's layout.  Eager mode materialises
+        fn(src) in the dictionary backward() returns; flat mode leaves it to the single gather launch."""
+        if copy:
+            slot = self._gbuf(src.shape)
+            slot.copy_(src)
+            src = slot
+        assert name not in self.pgrads, "parameter %s has two gradient sources" % name
+        self.pg_rec[name] = (src, fn)
+        if not self.flat_grads:
+            g = fn(src) if fn is not None else src
+            self.pgrads[name] = g.contiguous()
+        else:
+            self.pgrads[name] = None
 
     # ---- layers -----------------------------------------------------------------------------------------
     def conv_bn(self, x, wname, bnname, stride_w=1, relu=True, res_before=None, kinds=("fwd", "dgrad")):
@@ -157,20 +297,21 @@ class TrainGraph(object):
 
         def bwd():
             dy = self.grads.pop(id(y))
+            dgb = self._gbuf((2, co_p))
             dz, dgamma, dbeta, g = ops.bn_act_bwd(dy, z, coef, 1 if relu else 0, y_mask=y, dz_out=self._buf("dz", z.shape),
                                                   want_g=res_before is not None and relu,
-                                                  g_out=self._buf("g", z.shape) if (res_before is not None and relu) else None)
+                                                  g_out=self._buf("g", z.shape) if (res_before is not None and relu) else None,
+                                                  dgb_out=dgb)
             if res_before is not None:
                 self._acc(res_before, g if relu else dy)
-            self._pg(bnname + "_gamma", dgamma[:co])
-            self._pg(bnname + "_beta", dbeta[:co])
-            G = ops.conv2d_wgrad(dz, x, k, stride_w)  # [tap][co_p][ci_p]
+            self._pg(bnname + "_gamma", dgb, lambda t: t[0, :co])
+            self._pg(bnname + "_beta", dgb, lambda t: t[1, :co])
+            G = ops.conv2d_wgrad(dz, x, k, stride_w, out=self._gbuf((k * k, co_p, ci_p)))  # [tap][co_p][ci_p]
             if kinds[0] == "fwd_tapmajor":
                 C = ci // 9
-                gw = G[0, :co, :ci].reshape(co, 9, C).transpose(1, 2).reshape(co, ci, 1, 1)
+                self._pg(wname + "_weight", G, lambda t: t[0, :co, :ci].reshape(co, 9, C).transpose(1, 2).reshape(co, ci, 1, 1))
             else:
-                gw = G[:, :co, :ci].reshape(k, k, co, ci).permute(2, 3, 0, 1)
-            self._pg(wname + "_weight", gw.contiguous())
+                self._pg(wname + "_weight", G, lambda t: t[:, :co, :ci].reshape(k, k, co, ci).permute(2, 3, 0, 1))
             if id(x) in self.nograd:
                 return
             old = self.grads.pop(id(x), None)
@@ -215,19 +356,25 @@ class TrainGraph(object):
 
         def bwd():
             dy = self.grads.pop(id(y))
+            dgb = self._gbuf((2, co_p))
             dzg, dgamma, dbeta, _ = ops.bn_act_bwd(dy, z, coef, 2, dz_halo_w=S,
-                                                   dz_out=self._buf("dzg", (N, Hp, W_in * S + 2 * S, co_p)))
+                                                   dz_out=self._buf("dzg", (N, Hp, W_in * S + 2 * S, co_p)), dgb_out=dgb)
             self._acc(const, dy)
-            self._pg(bnname + "_gamma", dgamma[:co])
-            self._pg(bnname + "_beta", dbeta[:co])
+            self._pg(bnname + "_gamma", dgb, lambda t: t[0, :co])
+            self._pg(bnname + "_beta", dgb, lambda t: t[1, :co])
             dzg = dzg.view(N, Hp, W_in + 2, S * co_p)  # phase-grouped: pixel group j holds output pixels j*S .. j*S+S-1
-            G = ops.conv2d_wgrad(up, dzg, 3, 1).reshape(3, 3, ci_p, S, co_p)  # [ty][tx][ci][ph][co]
-            gw = torch.zeros_like(w)
+            G = ops.conv2d_wgrad(up, dzg, 3, 1, out=self._gbuf((9, ci_p, S * co_p)))  # [ty][tx][ci][ph][co]
             pad = KW // 4
-            for kx in range(KW):
-                tx, ph = divmod(kx - pad + S, S)
-                gw[:, :, :, kx] = G[:, tx, :ci, ph, :co].permute(1, 2, 0)
-            self._pg(wname + "_weight", gw)
+
+            def gw_of(t):
+                t = t.reshape(3, 3, ci_p, S, co_p)
+                cols = []
+                for kx in range(KW):
+                    tx, ph = divmod(kx - pad + S, S)
+                    cols.append(t[:, tx, :ci, ph, :co].permute(1, 2, 0))     # (ci, co, 3)
+                return torch.stack(cols, 3)                                     # (ci, co, 3, KW)
+
+            self._pg(wname + "_weight", G, gw_of)
             old = self.grads.pop(id(up), None)
             self.grads[id(up)] = ops.conv2d_nhwc(dzg, self._w(wname, "deconv_dgrad", ci_p, co_p, S), relu=False,
                                                  residual_pad=old, out=self._buf("dx", up.shape))
@@ -239,16 +386,21 @@ class TrainGraph(object):
         """1x1 conv + bias, no norm (builder.py:247-262) -> fp32 NCHW."""
         P = self.P
         ci_p = x.shape[3]
-        bias = torch.zeros(64, device=self.device)
-        bias[:co] = P[wname + "_bias"]
+        def pad64(b):
+            t = torch.zeros(64, device=b.device, dtype=b.dtype)
+            t[:co] = b
+            return t
+
+        bias = self._p32((wname, "bias64"), [wname + "_bias"], pad64)
         zp = ops.conv2d_nhwc(x, self._w(wname, "fwd", ci_p, 64), None, bias, relu=False, out=self._buf("z", x.shape[:3] + (64,)))
         out = ops.nhwc_to_nchw(zp, co)
 
         def bwd(d_out):
             dz = ops.nchw_to_nhwc(d_out.contiguous(), self._buf("dz", zp.shape))
-            self._pg(wname + "_bias", ops.channel_sums(dz)[:co])
-            G = ops.conv2d_wgrad(dz, x, 1, 1)
-            self._pg(wname + "_weight", G[0, :co, :P[wname + "_weight"].shape[1]].reshape(P[wname + "_weight"].shape).contiguous())
+            self._pg(wname + "_bias", ops.channel_sums(dz, out=self._gbuf((dz.shape[3],))), lambda t: t[:co])
+            G = ops.conv2d_wgrad(dz, x, 1, 1, out=self._gbuf((1, 64, ci_p)))
+            wshape = tuple(P[wname + "_weight"].shape)
+            self._pg(wname + "_weight", G, lambda t: t[0, :co, :wshape[1]].reshape(wshape))
             old = self.grads.pop(id(x), None)
             self.grads[id(x)] = ops.conv2d_nhwc(dz, self._w(wname, "dgrad", ci_p, 64), relu=False, residual_pad=old,
                                                 out=self._buf("dx", x.shape))
@@ -276,7 +428,7 @@ class TrainGraph(object):
         bn = name + "point_wise_mlp_bn1"
         tm = lambda v: v.reshape(C, 9).t().reshape(-1).contiguous()      # reference order c*9+k -> tap-major
         untm = lambda v: v.reshape(9, C).t().reshape(-1).contiguous()
-        gamma_t, beta_t = tm(P[bn + "_gamma"]), tm(P[bn + "_beta"])
+        gamma_t, beta_t = self._p32((bn, "gamma_tm"), [bn + "_gamma"], tm), self._p32((bn, "beta_tm"), [bn + "_beta"], tm)
         mm_t, mv_t = tm(P[bn + "_moving_mean"]), tm(P[bn + "_moving_var"])
         coef = ops.bn_train_stats(m, gamma_t, beta_t, mm_t, mv_t)
         P[bn + "_moving_mean"].copy_(untm(mm_t))
@@ -285,18 +437,19 @@ class TrainGraph(object):
 
         def bwd():
             da = self.grads.pop(id(a))
-            dm, dgamma, dbeta, _ = ops.bn_act_bwd(da, m, coef, 1, y_mask=a, dz_out=self._buf("dmeta", m.shape))
-            self._pg(bn + "_gamma", untm(dgamma))
-            self._pg(bn + "_beta", untm(dbeta))
+            dgb = self._gbuf((2, 9 * C))
+            dm, dgamma, dbeta, _ = ops.bn_act_bwd(da, m, coef, 1, y_mask=a, dz_out=self._buf("dmeta", m.shape), dgb_out=dgb)
+            self._pg(bn + "_gamma", dgb, lambda t: untm(t[0]))
+            self._pg(bn + "_beta", dgb, lambda t: untm(t[1]))
             # back to the reference op boundary: grad_out (B, 576 = c*9+k, H, W) fp32
             go = ops.nhwc_to_nchw(dm, tap_major=True)
             gd, gw0, gb0, gw1, gb1 = ops.meta_kernel_backward(go, feat, coord, *mlp)
             if self.debug is not None:
                 self.debug.update(meta_da=da, meta_dm=dm, meta_go=go, meta_gd=gd, meta_m=m, meta_a=a)
-            self._pg(name + "_2656_mlp0_weight", gw0.reshape(P[name + "_2656_mlp0_weight"].shape))
-            self._pg(name + "_2656_mlp0_bias", gb0)
-            self._pg(name + "_2656_mlp1_weight", gw1.reshape(P[name + "_2656_mlp1_weight"].shape))
-            self._pg(name + "_2656_mlp1_bias", gb1)
+            self._pg(name + "_2656_mlp0_weight", gw0, lambda t: t.reshape(32, 3, 1, 1), copy=True)
+            self._pg(name + "_2656_mlp0_bias", gb0, copy=True)
+            self._pg(name + "_2656_mlp1_weight", gw1, lambda t: t.reshape(-1, 32, 1, 1), copy=True)
+            self._pg(name + "_2656_mlp1_bias", gb1, copy=True)
             self._acc(x, ops.nchw_to_nhwc(gd, self._buf("dx", x.shape)))
 
         self.tape.append(bwd)
@@ -366,72 +519,125 @@ class TrainGraph(object):
         for kind, lvl, b, _ in self.head_bwd:
             b(d_cls[lvl] if kind == "cls" else d_reg[lvl])
         self.run_tape()
+        if self.flat_grads:   # one launch: every parameter gradient -> the flat (all-reduce) buffer
+            ops.gather_f32(self.arena, self.gmap, self.flat_g)
         return self.pgrads
 
 
+STRIDES = (1, 2, 4)
+LOSS_HYPER = dict(iou_type="bev", alpha=1.0, gamma=2.0, smooth_l1_scalar=3.0, scale_loss_shift=128.0,
+                  cls_loss_weight=10.0, reg_loss_weight=8.0)   # config/rangedet/rangedet_veh_wo_aug_4_18e.py:36,122-129
+
+
+def rpn_loss_levels(cls_logit, bbox_delta, targets, out=None, hyper=LOSS_HYPER):
+    """RangeRpnHead.get_fpn_loss (builder.py:268-348) on the head outputs: per level one fused launch pair
+    (ops.rpn_loss).  `targets`: dict of CUDA tensors with the graph-input names of builder.py:20-37.
+    Returns [per-level dict(iou_target, cls_loss, reg_loss, d_cls, d_reg)]."""
+    res = []
+    for lvl, s in enumerate(STRIDES):
+        res.append(ops.rpn_loss(cls_logit[lvl], bbox_delta[lvl], targets["pc_vehicle_frame_s%d" % s],
+                                targets["gt_bbox_veh_for_iou_pred"], targets["range_image_mask_s%d" % s],
+                                targets["rpn_reg_target_s%d" % s], targets["rpn_reg_weight_s%d" % s],
+                                targets["reg_normalize_weight_s%d" % s], out=None if out is None else out[lvl], **hyper))
+    return res
+
+
+def wd_mult(name):
+    """MXNet Optimizer.set_wd_mult: weight decay only on *_weight and *_gamma."""
+    return 1.0 if name.endswith(("_weight", "_gamma")) else 0.0
+
+
 def sgd_momentum_step(params, grads, momenta, lr, momentum=0.9, wd=1e-4, clip_gradient=None, rescale_grad=1.0):
-    """MXNet SGD (tools/train.py:312-319): g = clip(rescale*g) + wd*w; m = momentum*m - lr*g; w += m.
-    Fused multi-tensor update through torch._foreach (plumbing: 9.1 M parameters, 0.1 % of the step)."""
-    names = [n for n in grads if n in params]
-    ws = [params[n] for n in names]
-    gs = [grads[n].to(params[n].dtype).reshape(params[n].shape) * rescale_grad for n in names]
-    if clip_gradient is not None:
-        gs = [g.clamp_(-clip_gradient, clip_gradient) for g in gs]
-    ms = []
-    for n in names:
+    """MXNet SGD (tools/train.py:312-319), per-tensor torch restatement used by the eager path and as the
+    check of rd_sgd_mom_update: g = clip(rescale*g) + wd*wd_mult*w; m = momentum*m - lr*g; w += m."""
+    for n in grads:
+        if n not in params:
+            continue
+        g = grads[n].to(params[n].dtype).reshape(params[n].shape) * rescale_grad
+        if clip_gradient is not None:
+            g = g.clamp(-clip_gradient, clip_gradient)
+        g = g + wd * wd_mult(n) * params[n]
         if n not in momenta:
             momenta[n] = torch.zeros_like(params[n])
-        ms.append(momenta[n])
-    torch._foreach_add_(gs, ws, alpha=wd)
-    torch._foreach_mul_(ms, momentum)
-    torch._foreach_add_(ms, gs, alpha=-lr)
-    torch._foreach_add_(ws, ms)
+        momenta[n].mul_(momentum).add_(g, alpha=-lr)
+        params[n].add_(momenta[n])
 
 
 class GraphedTrainStep(object):
-    """Forward, backward and the SGD update captured ONCE in CUDA graphs and replayed: a training step is
-    ~900 launches of 10-500 us kernels, launching them one by one from Python is host-bound.
+    """The training iteration captured ONCE in CUDA graphs and replayed: forward | loss + backward | update.
 
         step = GraphedTrainStep(params, batch, H, W, lr=...)
-        cls, reg = step.forward(data, coord)          # graph 1
-        ... loss on cls / reg -> d_cls, d_reg ...
-        step.backward_update(d_cls, d_reg)            # graph 2 (+ data-parallel all-reduce) + graph 3
+        step.set_targets(targets)                      # synthetic roidb record (names of builder.py:20-37)
+        step.train_step(data, coord)                   # forward, RPN loss, backward, all-reduce, SGD
+      or, with an external loss:
+        cls, reg = step.forward(data, coord); step.backward_update(d_cls, d_reg)
 
-    All activations / gradients live in the TrainGraph buffer pool, so replays touch static addresses; the
-    bf16 operand copies of the weights are re-packed inside graph 1 from the fp32 masters that graph 3
-    updates in place.  With `world_size > 1` the parameter gradients are averaged across ranks between
-    backward and update by one flat NCCL all-reduce (the reference: hvd.DistributedOptimizer,
-    tools/train.py:364-368)."""
+    The step is ~950 launches of 10-500 us kernels; launching them one by one from Python is host-bound, and the
+    per-parameter plumbing (operand packing, gradient extraction, optimiser) used to be ~2 800 more.  Here the
+    trainable parameters live in ONE flat fp32 buffer (`params[name]` become views of it), TrainGraph runs in flat
+    mode (one gather launch packs all bf16 operands, one collects all gradients) and the MXNet SGD-momentum
+    update is one launch (rd_sgd_mom_update) whose learning rate is read from device memory (set_lr).  With
+    `allreduce` given, the flat gradient buffer is averaged across ranks between backward and update by one NCCL
+    all-reduce (the reference: hvd.DistributedOptimizer, tools/train.py:364-368)."""
 
-    def __init__(self, params, batch, H, W, lr, momentum=0.9, wd=1e-4, clip_gradient=None, device="cuda", use_meta=True,
-                 allreduce=None):
-        self.tg = TrainGraph(params, device, use_meta)
+    def __init__(self, params, batch, H, W, lr, momentum=0.9, wd=1e-5, clip_gradient=35.0, rescale_grad=1.0 / 128.0,
+                 device="cuda", use_meta=True, allreduce=None, with_loss=True):
         self.P = params
         self.allreduce = allreduce
-        self.hyper = dict(lr=lr, momentum=momentum, wd=wd, clip_gradient=clip_gradient)
-        self.data = torch.zeros((batch, 8, H, W), device=device)
-        self.coord = torch.zeros((batch, 3, H, W), device=device)
-        self.d_cls = [torch.zeros((batch, 1, H, W >> l), device=device) for l in range(3)]
-        self.d_reg = [torch.zeros((batch, 8, H, W >> l), device=device) for l in range(3)]
-        self.mom = {}
+        self.with_loss = with_loss
         names = sorted(k for k in params if not k.endswith(("_moving_mean", "_moving_var")))
         self.names = names
         sizes = [params[k].numel() for k in names]
-        self.flat = torch.zeros(sum(sizes), device=device)
-        self.gviews, o = {}, 0
+        total = sum(sizes)
+        self.flatP = torch.empty(total, device=device)
+        self.flat = torch.zeros(total, device=device)       # gradients (all-reduced)
+        self.flat_m = torch.zeros(total, device=device)     # momentum
+        self.flat_wd = torch.empty(total, device=device)
+        self.offsets, o = {}, 0
         for k, n in zip(names, sizes):
-            self.gviews[k] = self.flat[o:o + n].view(params[k].shape)
+            self.offsets[k] = o
+            self.flatP[o:o + n].copy_(params[k].reshape(-1))
+            params[k] = self.flatP[o:o + n].view(params[k].shape)   # masters now live in the flat buffer
+            self.flat_wd[o:o + n] = wd * wd_mult(k)
             o += n
-        # warm-up outside the capture (buffer pool, workspaces, function attributes); lr 0 leaves the weights alone
+        self.gviews = {k: self.flat[self.offsets[k]:self.offsets[k] + n].view(params[k].shape) for k, n in zip(names, sizes)}
+        self.hyper = torch.tensor([lr, momentum, rescale_grad, clip_gradient if clip_gradient else 0.0], device=device)
+        self.tg = TrainGraph(params, device, use_meta)
+        self.data = torch.zeros((batch, 8, H, W), device=device)
+        self.coord = torch.zeros((batch, 3, H, W), device=device)
+        self.d_cls = [torch.zeros((batch, 1, H, W // s), device=device) for s in STRIDES]
+        self.d_reg = [torch.zeros((batch, 8, H, W // s), device=device) for s in STRIDES]
+        self.targets, self.loss_out = None, None
+        if with_loss:
+            z = lambda *shape: torch.zeros(shape, device=device)
+            self.targets = {"gt_bbox_veh_for_iou_pred": z(batch, 200, 8)}
+            self.targets["gt_bbox_veh_for_iou_pred"][:, :, 3:7] = 1e-3     # all-padding GT (input.py:264-265)
+            self.loss_out = []
+            for s, dc, dr in zip(STRIDES, self.d_cls, self.d_reg):
+                self.targets["rpn_reg_target_s%d" % s] = z(batch, 8, H, W // s)
+                self.targets["rpn_reg_weight_s%d" % s] = z(batch, 8, H, W // s)
+                self.targets["reg_normalize_weight_s%d" % s] = z(batch, 8, H, W // s)
+                self.targets["range_image_mask_s%d" % s] = z(batch, 1, H, W // s)
+                self.targets["pc_vehicle_frame_s%d" % s] = z(batch, H * W // s, 3)
+                self.loss_out.append(dict(iou_target=z(batch, 1, H, W // s), cls_loss=z(batch, 1, H, W // s),
+                                          reg_loss=z(batch, 8, H, W // s), d_cls=dc, d_reg=dr))
+        # eager passes outside the capture: (1) sizes every buffer / records every operand and gradient source,
+        # (2) inside enable_flat: builds the gather maps, (3) flat mode warm-up.  lr = 0 leaves the weights alone.
+        lr_saved = self.hyper.clone()
+        self.hyper[0] = 0.0
         s = torch.cuda.Stream()
         s.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(s):
-            for _ in range(2):
-                self._fwd()
-                self._bwd()
-                self._update(lr=0.0)
+            self._fwd()
+            self._bwd()
+            self.tg.enable_flat(self.flatP, self.offsets, self.flat, lambda: (self._fwd(), self._bwd()))
+            self._fwd()
+            self._bwd()
+            self._update()
         torch.cuda.current_stream().wait_stream(s)
         torch.cuda.synchronize()
+        self.hyper.copy_(lr_saved)
+        self.flat_m.zero_()
         self.pool = torch.cuda.graph_pool_handle()
         self.g_fwd, self.g_bwd, self.g_upd = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
         with torch.cuda.graph(self.g_fwd, pool=self.pool):
@@ -439,20 +645,34 @@ class GraphedTrainStep(object):
         with torch.cuda.graph(self.g_bwd, pool=self.pool):
             self._bwd()
         with torch.cuda.graph(self.g_upd, pool=self.pool):
-            self._update(lr=lr)
+            self._update()
 
     def _fwd(self):
         self.tg.refresh()
         self.out = self.tg.forward(self.data, self.coord)
 
     def _bwd(self):
+        if self.with_loss:
+            rpn_loss_levels(self.out[0], self.out[1], self.targets, out=self.loss_out)
         grads = self.tg.backward(self.d_cls, self.d_reg)
-        torch._foreach_copy_([self.gviews[k] for k in self.names], [grads[k].reshape(self.P[k].shape) for k in self.names])
+        if not self.tg.flat_grads:
+            ks = [k for k in self.names if k in grads]
+            torch._foreach_copy_([self.gviews[k] for k in ks], [grads[k].reshape(self.P[k].shape) for k in ks])
 
-    def _update(self, lr):
-        h = self.hyper
-        sgd_momentum_step(self.P, self.gviews, self.mom, lr=lr, momentum=h["momentum"], wd=h["wd"],
-                          clip_gradient=h["clip_gradient"])
+    def _update(self):
+        ops.sgd_mom_update(self.flatP, self.flat, self.flat_m, self.flat_wd, self.hyper)
+
+    def set_lr(self, lr):
+        """Learning-rate schedule: the captured update reads lr from device memory."""
+        self.hyper[0:1].fill_(float(lr))
+
+    def set_targets(self, targets):
+        """Copy one synthetic-roidb / loader record (numpy or torch, names of builder.py:20-37) into the static
+        buffers the captured loss kernels read."""
+        for k, dst in self.targets.items():
+            src = targets[k]
+            src = torch.from_numpy(src) if not isinstance(src, torch.Tensor) else src
+            dst.copy_(src.reshape(dst.shape), non_blocking=True)
 
     def forward(self, data, coord):
         self.data.copy_(data, non_blocking=True)
@@ -460,10 +680,17 @@ class GraphedTrainStep(object):
         self.g_fwd.replay()
         return self.out
 
-    def backward_update(self, d_cls, d_reg):
-        for dst, src in zip(self.d_cls + self.d_reg, list(d_cls) + list(d_reg)):
-            dst.copy_(src, non_blocking=True)
+    def backward_update(self, d_cls=None, d_reg=None):
+        if not self.with_loss:
+            for dst, src in zip(self.d_cls + self.d_reg, list(d_cls) + list(d_reg)):
+                dst.copy_(src, non_blocking=True)
         self.g_bwd.replay()
         if self.allreduce is not None:
             self.allreduce(self.flat)
         self.g_upd.replay()
+
+    def train_step(self, data, coord):
+        """One iteration of tools/train.py's fit loop on the device: forward, loss, backward, all-reduce, SGD."""
+        self.forward(data, coord)
+        self.backward_update()
+        return self.loss_out

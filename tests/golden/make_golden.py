@@ -22,7 +22,19 @@ from rangedet_b200 import synth  # noqa: E402
 OUT = os.path.dirname(os.path.abspath(__file__))
 
 
+def loss_vectors():
+    """RPN loss head (torch fp32 restatement, oracle/loss_ref.py; parity unpinned at the MXNet boundary)."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import test_rpn_loss as T
+    items = {}
+    for it in ("bev", "3d"):
+        r = T.ref_level(T.loss_case(seed=0, iou_type=it), it)
+        items.update({it + "_" + k: v.numpy() for k, v in r.items()})
+    np.savez_compressed(os.path.join(OUT, "rpn_loss.npz"), **items)
+
+
 def main():
+    loss_vectors()
     ref = oracle.reference()
     assert ref is not None, "needs /root/reference"
     # decode (8-dim and bin)
