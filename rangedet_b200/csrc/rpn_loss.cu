@@ -112,6 +112,7 @@ rpn_loss_kernel(const LossParams p) {
   __shared__ Box2 sg[IOU_3D ? 1 : LOSS_GCHUNK];
   __shared__ float sg7[IOU_3D ? LOSS_GCHUNK * 7 : 1];
   __shared__ float s_norm[2];
+  __shared__ unsigned char s_dup[LOSS_GCHUNK];   // GT row bit-identical to the previous row (the fixed-length padding)
   const int b = blockIdx.y;
   const int64_t n = (int64_t)blockIdx.x * LOSS_THREADS + threadIdx.x;
   const int64_t N = p.N;
@@ -152,6 +153,20 @@ rpn_loss_kernel(const LossParams p) {
   for (int g0 = 0; g0 < G; g0 += LOSS_GCHUNK) {
     const int ng = min(LOSS_GCHUNK, G - g0);
     __syncthreads();
+    // The reference pads GT to 200 rows with one constant box (rangedet/core/input.py:264-265).  max() over a
+    // set does not change when bit-identical duplicates are dropped, so a row equal to its predecessor is skipped:
+    // pixels without a return (pc = 0) decode to boxes around the origin that would otherwise be clipped against
+    // every one of the ~170 padding rows.
+    constexpr int GD = IOU_3D ? 7 : 8;
+    for (int g = threadIdx.x; g < ng; g += LOSS_THREADS) {
+      const float* r1 = p.gt + ((int64_t)b * G + g0 + g) * GD;
+      bool dup = g0 + g > 0;
+      if (dup) {
+#pragma unroll
+        for (int k = 0; k < GD; ++k) dup = dup && __float_as_uint(__ldg(r1 + k)) == __float_as_uint(__ldg(r1 + k - GD));
+      }
+      s_dup[g] = dup ? 1 : 0;
+    }
     if (!IOU_3D) {
       for (int g = threadIdx.x; g < ng; g += LOSS_THREADS) {
         float w[8];
@@ -171,6 +186,7 @@ rpn_loss_kernel(const LossParams p) {
     __syncthreads();
     if (active) {
       for (int g = 0; g < ng; ++g) {
+        if (s_dup[g]) continue;   // uniform across the CTA
         float u;
         if (!IOU_3D) {
           u = sanitise_iou(iou_quads(me, sg[g]));

@@ -87,10 +87,20 @@ def main():
                 t_u += ev[2].elapsed_time(ev[3])
         torch.cuda.synchronize()
         wall = (time.perf_counter() - wall0) / a.steps * 1e3
+        loss_ms = None
+        if step is not None and not a.no_loss:   # the loss head alone (3 levels, 6 launches), same buffers
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            train.rpn_loss_levels(step.out[0], step.out[1], step.targets, out=step.loss_out)
+            e0.record()
+            for _ in range(5):
+                train.rpn_loss_levels(step.out[0], step.out[1], step.targets, out=step.loss_out)
+            e1.record()
+            torch.cuda.synchronize()
+            loss_ms = e0.elapsed_time(e1) / 5
         n = a.steps
         step_ms = (t_f + t_b + t_u) / n
         finite = all(bool(torch.isfinite(v).all()) for v in P.values())
-        out.append({"batch": B, "fwd_ms": t_f / n, "bwd_ms": t_b / n, "update_ms": t_u / n, "step_ms": step_ms,
+        out.append({"batch": B, "fwd_ms": t_f / n, "bwd_ms": t_b / n, "update_ms": t_u / n, "loss_ms": loss_ms, "step_ms": step_ms,
                     "wall_ms_per_step": wall, "frames_per_s": B / step_ms * 1e3,
                     "algorithmic_TFLOPs": 3 * FLOP_FWD_PER_FRAME * B / step_ms / 1e9,
                     "launches_per_step": (_lib.launch_count() - l0) / n,
