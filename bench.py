@@ -159,6 +159,66 @@ def run_reference(args, rank, world):
     print(json.dumps(line), flush=True)
 
 
+TRAIN_B = 2   # per-GPU batch of the shipped config (config/rangedet/rangedet_veh_wo_aug_4_18e.py:32)
+
+
+def train_step_leg(args, rank, world, dev):
+    """BASELINE.json configs[4]: the whole training iteration -- DLA backbone + Meta-Kernel unit
+    + RPN head forward, fused RPN loss (IoU target + VFL + smooth-L1), backward, NCCL all-reduce of the flat
+    9.1 M-parameter gradient, MXNet SGD-momentum update -- on a synthetic roidb record, B=2 frames per GPU,
+    CUDA-graph replay.  Reported beside the headline (not the headline: that is configs[1])."""
+    import torch
+    import torch.distributed as dist
+
+    from rangedet_b200 import synth, train
+    from rangedet_b200.model_params import make_params, num_parameters
+
+    B = TRAIN_B
+    P = make_params(seed=0, device=dev)
+    nparam = num_parameters(P)
+
+    def allreduce(flat):
+        dist.all_reduce(flat, op=dist.ReduceOp.SUM)
+        flat.div_(world)
+
+    step = train.GraphedTrainStep(P, B, H, W_PAD, lr=0.01 / 8 * world * B * 5, device=dev,
+                                  allreduce=allreduce if world > 1 else None)
+    step.set_targets(synth.rpn_targets(B, seed=500 + rank))
+    g = torch.Generator(device=dev).manual_seed(600 + rank)
+    data = torch.randn((B, 8, H, W_PAD), device=dev, generator=g)
+    coord = torch.from_numpy(synth.range_image_coords(B, seed=700 + rank)).to(dev)
+    for _ in range(3):
+        step.train_step(data, coord)
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    n = max(5, min(args.steps, 20))
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(n):
+        step.train_step(data, coord)
+    e1.record()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    if world > 1:
+        t = torch.tensor([ms], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    loss = step.loss_out
+    res = {"workload": "rangedet_veh_wo_aug_4_18e train step on synthetic roidb: backbone + Meta-Kernel unit + head fwd, "
+                       "RPN loss, bwd, all-reduce, SGD; B=%d/GPU, 64x2656, bf16 operands / fp32 accumulate, training-mode BN" % B,
+           "value": B * world * n / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms / n, "steps": n, "batch_per_gpu": B,
+           "parameters": int(nparam), "allreduce_bytes": int(step.flat.numel() * 4) if world > 1 else 0,
+           "algorithmic_TFLOPs": 3 * 1.114e12 * B / (ms / n * 1e-3) / 1e12,
+           "cls_loss": float(sum(o["cls_loss"].sum() for o in loss)), "reg_loss": float(sum(o["reg_loss"].sum() for o in loss)),
+           "params_finite": bool(torch.isfinite(step.flatP).all())}
+    del step, P
+    torch.cuda.empty_cache()
+    return res
+
+
 def run_ours(args, rank, local_rank, world):
     import numpy as np
     import torch
@@ -334,6 +394,13 @@ def run_ours(args, rank, local_rank, world):
                "sample": "1 frame (B=1 of the B=4 batch) fwd+bwd, best of 2, torch fp32 CPU port of meta_kernel.py:166-240 "
                          "(reference CPU path = MXNet, not installable: no network)"}
 
+    train_leg = None
+    if not args.no_train_step:
+        try:
+            train_leg = train_step_leg(args, rank, world, dev)
+        except Exception as ex:  # report, never fake
+            train_leg = {"value": None, "unit": UNIT, "error": repr(ex)[:300]}
+
     if rank == 0:
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
@@ -344,6 +411,7 @@ def run_ours(args, rank, local_rank, world):
                        "mk_impl": {0: "default (TMA+tcgen05 warp-specialised)", 1: "cuda-core fp32", 2: "tcgen05", 3: "TMA+tcgen05 warp-specialised"}[impl],
                        "l2": "inputs larger than L2 (3.5 GB touched per step vs 126 MB L2)"},
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "clocks": clocks, "gpu_launches": int(launches),
+            "train_step": train_leg,
         }
         print(json.dumps(line), flush=True)
     if world > 1:
@@ -358,6 +426,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--mk-impl", type=int, default=0, choices=[0, 1, 2, 3])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-train-step", action="store_true", help="skip the whole-model training-step leg (cfg-5)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))

@@ -298,7 +298,10 @@ class TrainGraph(object):
         def bwd():
             dy = self.grads.pop(id(y))
             dgb = self._gbuf((2, co_p))
-            dz, dgamma, dbeta, g = ops.bn_act_bwd(dy, z, coef, 1 if relu else 0, y_mask=y, dz_out=self._buf("dz", z.shape),
+            # ReLU mask: without a residual the pre-activation is z*a+b, recomputed from the z the kernels read
+            # anyway (mask_mode 2) -- saves one full read of y in each of the two backward passes
+            mm = 0 if not relu else (2 if res_before is None else 1)
+            dz, dgamma, dbeta, g = ops.bn_act_bwd(dy, z, coef, mm, y_mask=y if mm == 1 else None, dz_out=self._buf("dz", z.shape),
                                                   want_g=res_before is not None and relu,
                                                   g_out=self._buf("g", z.shape) if (res_before is not None and relu) else None,
                                                   dgb_out=dgb)
@@ -438,7 +441,7 @@ class TrainGraph(object):
         def bwd():
             da = self.grads.pop(id(a))
             dgb = self._gbuf((2, 9 * C))
-            dm, dgamma, dbeta, _ = ops.bn_act_bwd(da, m, coef, 1, y_mask=a, dz_out=self._buf("dmeta", m.shape), dgb_out=dgb)
+            dm, dgamma, dbeta, _ = ops.bn_act_bwd(da, m, coef, 2, dz_out=self._buf("dmeta", m.shape), dgb_out=dgb)
             self._pg(bn + "_gamma", dgb, lambda t: untm(t[0]))
             self._pg(bn + "_beta", dgb, lambda t: untm(t[1]))
             # back to the reference op boundary: grad_out (B, 576 = c*9+k, H, W) fp32
