@@ -99,7 +99,20 @@ __global__ void __launch_bounds__(NT) stats_kernel(const __nv_bfloat16* __restri
     const int sg = u % G.nseg, row = u / G.nseg, h = row % G.H, n = row / G.H;
     const int w0 = sg * G.seg, w1 = min(G.W, w0 + G.seg);
     const __nv_bfloat16* base = z + pix_off(n, h, 0, G.H, G.W, halo, G.C) + cg * 8;
-    for (int w = w0 + pl; w < w1; w += G.ppb) {
+    int w = w0 + pl;
+    for (; w + 3 * G.ppb < w1; w += 4 * G.ppb) {   // four independent 16-byte loads in flight per thread
+      uint4 v[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) v[j] = __ldg(reinterpret_cast<const uint4*>(base + (int64_t)(w + j * G.ppb) * G.C));
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        float f[8];
+        unpack8(v[j], f);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) { s[i] += f[i]; q[i] = fmaf(f[i], f[i], q[i]); }
+      }
+    }
+    for (; w < w1; w += G.ppb) {
       float f[8];
       unpack8(__ldg(reinterpret_cast<const uint4*>(base + (int64_t)w * G.C)), f);
 #pragma unroll
@@ -158,7 +171,7 @@ __global__ void __launch_bounds__(256) fwd_finalize_kernel(const float* __restri
 }
 
 // ---- forward apply: y = relu?(z*a + b + rb) + ra --------------------------------------------------
-__global__ void __launch_bounds__(NT) fwd_apply_kernel(const __nv_bfloat16* __restrict__ z,
+__global__ void __launch_bounds__(NT, 4) fwd_apply_kernel(const __nv_bfloat16* __restrict__ z,
                                                        const float* __restrict__ coef,
                                                        const __nv_bfloat16* __restrict__ rb,
                                                        const __nv_bfloat16* __restrict__ ra,
@@ -172,7 +185,43 @@ __global__ void __launch_bounds__(NT) fwd_apply_kernel(const __nv_bfloat16* __re
     const int sg = u % G.nseg, row = u / G.nseg, h = row % G.H, n = row / G.H;
     const int w0 = sg * G.seg, w1 = min(G.W, w0 + G.seg);
     const int64_t base = pix_off(n, h, 0, G.H, G.W, 1, G.C) + cg * 8;
-    for (int w = w0 + pl; w < w1; w += G.ppb) {
+    int w = w0 + pl;
+    for (; w + G.ppb < w1; w += 2 * G.ppb) {   // two pixels per trip: all loads issued before the first use
+      const int64_t o0 = base + (int64_t)w * G.C, o1 = o0 + (int64_t)G.ppb * G.C;
+      const uint4 z0 = __ldg(reinterpret_cast<const uint4*>(z + o0)), z1 = __ldg(reinterpret_cast<const uint4*>(z + o1));
+      uint4 rb0 = make_uint4(0, 0, 0, 0), rb1 = rb0, ra0 = rb0, ra1 = rb0;
+      if (rb) {
+        rb0 = __ldg(reinterpret_cast<const uint4*>(rb + o0));
+        rb1 = __ldg(reinterpret_cast<const uint4*>(rb + o1));
+      }
+      if (ra) {
+        ra0 = __ldg(reinterpret_cast<const uint4*>(ra + o0));
+        ra1 = __ldg(reinterpret_cast<const uint4*>(ra + o1));
+      }
+#pragma unroll
+      for (int j = 0; j < 2; ++j) {
+        float f[8], r[8];
+        unpack8(j ? z1 : z0, f);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) f[i] = fmaf(f[i], a[i], b[i]);
+        if (rb) {
+          unpack8(j ? rb1 : rb0, r);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) f[i] += r[i];
+        }
+        if (relu) {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) f[i] = fmaxf(f[i], 0.f);
+        }
+        if (ra) {
+          unpack8(j ? ra1 : ra0, r);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) f[i] += r[i];
+        }
+        *reinterpret_cast<uint4*>(y + (j ? o1 : o0)) = pack8(f);
+      }
+    }
+    for (; w < w1; w += G.ppb) {
       const int64_t o = base + (int64_t)w * G.C;
       float f[8], r[8];
       unpack8(__ldg(reinterpret_cast<const uint4*>(z + o)), f);
@@ -212,7 +261,20 @@ __device__ __forceinline__ void masked_grad(float (&g)[8], const float (&zf)[8],
   }
 }
 
-__global__ void __launch_bounds__(NT) bwd_reduce_kernel(const __nv_bfloat16* __restrict__ dy,
+__device__ __forceinline__ void masked_grad_v(float (&g)[8], const float (&zf)[8], const uint4& ymv, int mask_mode,
+                                              const float (&a)[8], const float (&b)[8]) {
+  if (mask_mode == 1) {
+    float yf[8];
+    unpack8(ymv, yf);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) g[i] = yf[i] > 0.f ? g[i] : 0.f;
+  } else if (mask_mode == 2) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) g[i] = fmaf(zf[i], a[i], b[i]) > 0.f ? g[i] : 0.f;
+  }
+}
+
+__global__ void __launch_bounds__(NT, 3) bwd_reduce_kernel(const __nv_bfloat16* __restrict__ dy,
                                                         const __nv_bfloat16* __restrict__ ym,
                                                         const __nv_bfloat16* __restrict__ z,
                                                         const float* __restrict__ coef, Geo G, int mask_mode,
@@ -231,7 +293,27 @@ __global__ void __launch_bounds__(NT) bwd_reduce_kernel(const __nv_bfloat16* __r
     const int sg = u % G.nseg, row = u / G.nseg, h = row % G.H, n = row / G.H;
     const int w0 = sg * G.seg, w1 = min(G.W, w0 + G.seg);
     const int64_t base = pix_off(n, h, 0, G.H, G.W, 1, G.C) + cg * 8;
-    for (int w = w0 + pl; w < w1; w += G.ppb) {
+    int w = w0 + pl;
+    for (; w + G.ppb < w1; w += 2 * G.ppb) {   // two pixels per trip: all loads issued before the first use
+      const int64_t o0 = base + (int64_t)w * G.C, o1 = o0 + (int64_t)G.ppb * G.C;
+      const uint4 vd0 = __ldg(reinterpret_cast<const uint4*>(dy + o0)), vz0 = __ldg(reinterpret_cast<const uint4*>(z + o0));
+      const uint4 vd1 = __ldg(reinterpret_cast<const uint4*>(dy + o1)), vz1 = __ldg(reinterpret_cast<const uint4*>(z + o1));
+      uint4 vm0 = make_uint4(0, 0, 0, 0), vm1 = vm0;
+      if (mask_mode == 1) {
+        vm0 = __ldg(reinterpret_cast<const uint4*>(ym + o0));
+        vm1 = __ldg(reinterpret_cast<const uint4*>(ym + o1));
+      }
+#pragma unroll
+      for (int j = 0; j < 2; ++j) {
+        float g[8], zf[8];
+        unpack8(j ? vd1 : vd0, g);
+        unpack8(j ? vz1 : vz0, zf);
+        masked_grad_v(g, zf, j ? vm1 : vm0, mask_mode, a, b);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) { s[i] += g[i]; q[i] = fmaf(g[i], zf[i] - mean[i], q[i]); }
+      }
+    }
+    for (; w < w1; w += G.ppb) {
       const int64_t o = base + (int64_t)w * G.C;
       float g[8], zf[8];
       unpack8(__ldg(reinterpret_cast<const uint4*>(dy + o)), g);
@@ -262,7 +344,7 @@ __global__ void __launch_bounds__(256) bwd_finalize_kernel(const float* __restri
   }
 }
 
-__global__ void __launch_bounds__(NT) bwd_apply_kernel(const __nv_bfloat16* __restrict__ dy,
+__global__ void __launch_bounds__(NT, 3) bwd_apply_kernel(const __nv_bfloat16* __restrict__ dy,
                                                        const __nv_bfloat16* __restrict__ ym,
                                                        const __nv_bfloat16* __restrict__ z,
                                                        const float* __restrict__ coef,
@@ -285,7 +367,30 @@ __global__ void __launch_bounds__(NT) bwd_apply_kernel(const __nv_bfloat16* __re
     const int w0 = sg * G.seg, w1 = min(G.W, w0 + G.seg);
     const int64_t base = pix_off(n, h, 0, G.H, G.W, 1, G.C) + cg * 8;
     const int64_t obase = pix_off(n, h, 0, G.H, G.W, dz_halo, G.C) + cg * 8;
-    for (int w = w0 + pl; w < w1; w += G.ppb) {
+    int w = w0 + pl;
+    for (; w + G.ppb < w1; w += 2 * G.ppb) {   // two pixels per trip: all loads issued before the first use
+      const int64_t o0 = base + (int64_t)w * G.C, o1 = o0 + (int64_t)G.ppb * G.C;
+      const uint4 vd0 = __ldg(reinterpret_cast<const uint4*>(dy + o0)), vz0 = __ldg(reinterpret_cast<const uint4*>(z + o0));
+      const uint4 vd1 = __ldg(reinterpret_cast<const uint4*>(dy + o1)), vz1 = __ldg(reinterpret_cast<const uint4*>(z + o1));
+      uint4 vm0 = make_uint4(0, 0, 0, 0), vm1 = vm0;
+      if (mask_mode == 1) {
+        vm0 = __ldg(reinterpret_cast<const uint4*>(ym + o0));
+        vm1 = __ldg(reinterpret_cast<const uint4*>(ym + o1));
+      }
+#pragma unroll
+      for (int j = 0; j < 2; ++j) {
+        float g[8], zf[8], d[8];
+        unpack8(j ? vd1 : vd0, g);
+        unpack8(j ? vz1 : vz0, zf);
+        masked_grad_v(g, zf, j ? vm1 : vm0, mask_mode, a, b);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) d[i] = a[i] * (g[i] - c1[i] - (zf[i] - mean[i]) * c2[i]);
+        const int wj = w + j * G.ppb;
+        *reinterpret_cast<uint4*>(dz + obase + (int64_t)wj * G.C) = pack8(d);
+        if (g_out) *reinterpret_cast<uint4*>(g_out + (j ? o1 : o0)) = pack8(g);
+      }
+    }
+    for (; w < w1; w += G.ppb) {
       const int64_t o = base + (int64_t)w * G.C;
       float g[8], zf[8], d[8];
       unpack8(__ldg(reinterpret_cast<const uint4*>(dy + o)), g);
