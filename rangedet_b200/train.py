@@ -122,6 +122,10 @@ class TrainGraph(object):
         self.arena = None          # fp32 scratch all parameter-gradient kernels write into (flat mode)
         self.g_sizes, self._gn = [], 0
         self.pg_rec = {}
+        # optional second stream for the weight-gradient kernels: dW of a layer only feeds the optimiser, so it can
+        # overlap the HBM-bound BatchNorm backward / data gradient of the layers below it (fork-join, capturable)
+        self.side = None
+        self._side_used = False
 
     # ---- parameter packing (bf16 operand copies; call refresh() after an optimiser step) -------------
     def refresh(self):
@@ -265,6 +269,22 @@ class TrainGraph(object):
             fn()
         self.tape = []
 
+    def _wgrad(self, a_pad, b_pad, ksize, stride_w, out):
+        if self.side is None:
+            return ops.conv2d_wgrad(a_pad, b_pad, ksize, stride_w, out=out)
+        ev = torch.cuda.Event()
+        ev.record()
+        self.side.wait_event(ev)
+        with torch.cuda.stream(self.side):
+            G = ops.conv2d_wgrad(a_pad, b_pad, ksize, stride_w, out=out)
+        self._side_used = True
+        return G
+
+    def _join_side(self):
+        if self.side is not None and self._side_used:
+            torch.cuda.current_stream().wait_stream(self.side)
+            self._side_used = False
+
     def _pg(self, name, src, fn=None, copy=False):
         """Gradient of parameter `name` = fn(src): `src` is what a kernel wrote (into a _gbuf() buffer, or anywhere
         with copy=True), `fn` a pure view / permutation into the parameter's layout.  Eager mode materialises
@@ -309,7 +329,7 @@ class TrainGraph(object):
                 self._acc(res_before, g if relu else dy)
             self._pg(bnname + "_gamma", dgb, lambda t: t[0, :co])
             self._pg(bnname + "_beta", dgb, lambda t: t[1, :co])
-            G = ops.conv2d_wgrad(dz, x, k, stride_w, out=self._gbuf((k * k, co_p, ci_p)))  # [tap][co_p][ci_p]
+            G = self._wgrad(dz, x, k, stride_w, self._gbuf((k * k, co_p, ci_p)))  # [tap][co_p][ci_p]
             if kinds[0] == "fwd_tapmajor":
                 C = ci // 9
                 self._pg(wname + "_weight", G, lambda t: t[0, :co, :ci].reshape(co, 9, C).transpose(1, 2).reshape(co, ci, 1, 1))
@@ -366,7 +386,7 @@ class TrainGraph(object):
             self._pg(bnname + "_gamma", dgb, lambda t: t[0, :co])
             self._pg(bnname + "_beta", dgb, lambda t: t[1, :co])
             dzg = dzg.view(N, Hp, W_in + 2, S * co_p)  # phase-grouped: pixel group j holds output pixels j*S .. j*S+S-1
-            G = ops.conv2d_wgrad(up, dzg, 3, 1, out=self._gbuf((9, ci_p, S * co_p)))  # [ty][tx][ci][ph][co]
+            G = self._wgrad(up, dzg, 3, 1, self._gbuf((9, ci_p, S * co_p)))  # [ty][tx][ci][ph][co]
             pad = KW // 4
 
             def gw_of(t):
@@ -401,7 +421,7 @@ class TrainGraph(object):
         def bwd(d_out):
             dz = ops.nchw_to_nhwc(d_out.contiguous(), self._buf("dz", zp.shape))
             self._pg(wname + "_bias", ops.channel_sums(dz, out=self._gbuf((dz.shape[3],))), lambda t: t[:co])
-            G = ops.conv2d_wgrad(dz, x, 1, 1, out=self._gbuf((1, 64, ci_p)))
+            G = self._wgrad(dz, x, 1, 1, self._gbuf((1, 64, ci_p)))
             wshape = tuple(P[wname + "_weight"].shape)
             self._pg(wname + "_weight", G, lambda t: t[0, :co, :wshape[1]].reshape(wshape))
             old = self.grads.pop(id(x), None)
@@ -522,6 +542,7 @@ class TrainGraph(object):
         for kind, lvl, b, _ in self.head_bwd:
             b(d_cls[lvl] if kind == "cls" else d_reg[lvl])
         self.run_tape()
+        self._join_side()
         if self.flat_grads:   # one launch: every parameter gradient -> the flat (all-reduce) buffer
             ops.gather_f32(self.arena, self.gmap, self.flat_g)
         return self.pgrads
@@ -584,7 +605,7 @@ class GraphedTrainStep(object):
     all-reduce (the reference: hvd.DistributedOptimizer, tools/train.py:364-368)."""
 
     def __init__(self, params, batch, H, W, lr, momentum=0.9, wd=1e-5, clip_gradient=35.0, rescale_grad=1.0 / 128.0,
-                 device="cuda", use_meta=True, allreduce=None, with_loss=True):
+                 device="cuda", use_meta=True, allreduce=None, with_loss=True, overlap_wgrad=True):
         self.P = params
         self.allreduce = allreduce
         self.with_loss = with_loss
@@ -606,6 +627,8 @@ class GraphedTrainStep(object):
         self.gviews = {k: self.flat[self.offsets[k]:self.offsets[k] + n].view(params[k].shape) for k, n in zip(names, sizes)}
         self.hyper = torch.tensor([lr, momentum, rescale_grad, clip_gradient if clip_gradient else 0.0], device=device)
         self.tg = TrainGraph(params, device, use_meta)
+        if overlap_wgrad:
+            self.tg.side = torch.cuda.Stream(device=device)
         self.data = torch.zeros((batch, 8, H, W), device=device)
         self.coord = torch.zeros((batch, 3, H, W), device=device)
         self.d_cls = [torch.zeros((batch, 1, H, W // s), device=device) for s in STRIDES]

@@ -29,6 +29,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--no-meta", action="store_true")
     ap.add_argument("--eager", action="store_true", help="launch every kernel from Python instead of replaying CUDA graphs")
+    ap.add_argument("--no-overlap", action="store_true", help="weight gradients on the main stream (no second stream)")
     ap.add_argument("--no-loss", action="store_true", help="linear loss (random head-output gradients) instead of the RPN loss")
     a = ap.parse_args()
     H, W = 64, 2656
@@ -48,7 +49,7 @@ def main():
         l0 = _lib.launch_count()
         wall0 = None
         step = None if a.eager else train.GraphedTrainStep(P, B, H, W, lr=1e-4, clip_gradient=35.0, use_meta=not a.no_meta,
-                                                           with_loss=not a.no_loss)
+                                                           with_loss=not a.no_loss, overlap_wgrad=not a.no_overlap)
         if step is not None and not a.no_loss:
             step.set_targets(synth.rpn_targets(B, seed=5))
         for it in range(a.warmup + a.steps):
@@ -105,7 +106,7 @@ def main():
                     "algorithmic_TFLOPs": 3 * FLOP_FWD_PER_FRAME * B / step_ms / 1e9,
                     "launches_per_step": (_lib.launch_count() - l0) / n,
                     "mem_GB": torch.cuda.max_memory_allocated() / 1e9, "params_finite": finite,
-                    "meta_unit": not a.no_meta, "loss": "linear" if (a.no_loss or a.eager) else "RPN loss (IoU target + VFL + smooth-L1)",
+                    "meta_unit": not a.no_meta, "overlap_wgrad": not a.no_overlap, "loss": "linear" if (a.no_loss or a.eager) else "RPN loss (IoU target + VFL + smooth-L1)",
                     "mode": "eager launches" if a.eager else "CUDA graph replay (forward | loss + backward | update)"})
         del tg, P, mom, step
         torch.cuda.empty_cache()
