@@ -30,6 +30,7 @@ using namespace rd_iou;
 
 constexpr int LOSS_THREADS = 128;
 constexpr int LOSS_GCHUNK = 256;
+constexpr int LOSS_QCAP = 2048;   // queue of (pixel, GT) pairs per CTA and GT chunk
 constexpr int SUM_BLOCKS = 296;   // 2 x 148 SMs
 constexpr int SUM_THREADS = 256;
 
@@ -113,6 +114,10 @@ rpn_loss_kernel(const LossParams p) {
   __shared__ float sg7[IOU_3D ? LOSS_GCHUNK * 7 : 1];
   __shared__ float s_norm[2];
   __shared__ unsigned char s_dup[LOSS_GCHUNK];   // GT row bit-identical to the previous row (the fixed-length padding)
+  __shared__ Box2 s_me[IOU_3D ? 1 : LOSS_THREADS];      // decoded boxes of this CTA's pixels (phase 2 reads any of them)
+  __shared__ unsigned short s_q[IOU_3D ? 1 : LOSS_QCAP];   // queued (pixel << 8 | gt) pairs that need clipping
+  __shared__ unsigned int s_best[LOSS_THREADS];
+  __shared__ int s_qn;
   const int b = blockIdx.y;
   const int64_t n = (int64_t)blockIdx.x * LOSS_THREADS + threadIdx.x;
   const int64_t N = p.N;
@@ -135,6 +140,7 @@ rpn_loss_kernel(const LossParams p) {
     decode_box(d, __ldg(q), __ldg(q + 1), v);
     if (!IOU_3D) {
       load_box8(v, me);
+      s_me[threadIdx.x] = me;
     } else {  // to_box_type_7 (batch_rotated_iou.py:51-68) + yaw negation (:35-36)
       float b7[7];
       b7[0] = (((v[0] + v[2]) + v[4]) + v[6]) / 4.0f;
@@ -149,6 +155,8 @@ rpn_loss_kernel(const LossParams p) {
     }
   }
   float best = -INFINITY;
+  s_best[threadIdx.x] = 0u;   // every sanitised IoU is >= +0 and at least GT row 0 is evaluated
+  if (threadIdx.x == 0) s_qn = 0;
   const int G = p.G;
   for (int g0 = 0; g0 < G; g0 += LOSS_GCHUNK) {
     const int ng = min(LOSS_GCHUNK, G - g0);
@@ -184,22 +192,51 @@ rpn_loss_kernel(const LossParams p) {
       }
     }
     __syncthreads();
-    if (active) {
+    if (!IOU_3D) {
+      // Two phases, so that the expensive part (polygon clipping, divergent: only a few percent of the (pixel, GT)
+      // pairs survive the exact early-outs of iou_quads) is spread over the whole CTA instead of stalling the warp
+      // of whichever pixel needs it:  (1) every pixel runs the early-outs inline and queues its surviving pairs,
+      // (2) all threads clip queued pairs, one per thread, and fold the result into the pixel's maximum with an
+      // atomicMax on the bit pattern (IoUs are non-negative floats: bit order == value order; max is
+      // order-independent, so this stays deterministic).  A full queue falls back to clipping in place.
+      if (active) {
+        for (int g = 0; g < ng; ++g) {
+          if (s_dup[g]) continue;   // uniform across the CTA
+          const Box2& t = sg[g];
+          if (me.area < R_EPS || t.area < R_EPS) continue;             // iou_quads would return +0
+          if (me.convex && t.convex && aabb_disjoint(me, t)) continue;   // likewise
+          const int pos = atomicAdd(&s_qn, 1);
+          if (pos < LOSS_QCAP) {
+            s_q[pos] = (unsigned short)((threadIdx.x << 8) | g);
+          } else {
+            float u = sanitise_iou(iou_quads(me, t));
+            u = u > 0.f ? u : 0.f;
+            atomicMax(&s_best[threadIdx.x], __float_as_uint(u));
+          }
+        }
+      }
+      __syncthreads();
+      const int nq = min(s_qn, LOSS_QCAP);
+      for (int i = threadIdx.x; i < nq; i += LOSS_THREADS) {
+        const int e = s_q[i], px = e >> 8, g = e & 255;
+        float u = sanitise_iou(iou_quads(s_me[px], sg[g]));
+        u = u > 0.f ? u : 0.f;   // also folds -0.0 into +0.0 (its bit pattern would win the unsigned max)
+        atomicMax(&s_best[px], __float_as_uint(u));
+      }
+      __syncthreads();
+      if (threadIdx.x == 0) s_qn = 0;
+    } else if (active) {
       for (int g = 0; g < ng; ++g) {
         if (s_dup[g]) continue;   // uniform across the CTA
-        float u;
-        if (!IOU_3D) {
-          u = sanitise_iou(iou_quads(me, sg[g]));
-        } else {
-          Rect rg;
-          float gz, gh;
-          load_rect7(sg7 + g * 7, rg, &gz, &gh);
-          u = sanitise_iou(iou_rect7(mr, mz, mh, rg, gz, gh));
-        }
+        Rect rg;
+        float gz, gh;
+        load_rect7(sg7 + g * 7, rg, &gz, &gh);
+        const float u = sanitise_iou(iou_rect7(mr, mz, mh, rg, gz, gh));
         best = u > best ? u : best;
       }
     }
   }
+  if (!IOU_3D) best = __uint_as_float(s_best[threadIdx.x]);
   if (!active) return;
   const float t = best;  // IoU target in [0,1]
   const int64_t i1 = (int64_t)b * N + n;
