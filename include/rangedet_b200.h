@@ -120,6 +120,33 @@ int rd_rpn_loss(const float* cls_logit, const float* reg_delta, const float* pc,
                 float* iou_target, float* cls_loss, float* reg_loss, float* d_cls, float* d_reg,
                 void* workspace, size_t workspace_bytes, rd_stream_t stream);
 
+/* ---- Training-target assignment (data-loader side of the training graph) -------------------------
+ * Replace processing_cxx.assign3D_v2 / get_point_num (operator_cxx/src_cxx/assigner.h:11-87, :89-109; called from
+ * rangedet/core/input.py:311-320, :433) and GenerateTarget.get_rpn_reg_target (+ normalisation / dimension
+ * weights, input.py:345-372, 430-506, num_classes == 1).  One frame per call, like the reference.
+ *   pc (N,3) vehicle-frame points   bbox (M,24) = 8 corners xyz   bbox_center (M,3)   bbox_radius (M)
+ *   mask (N), is_in_nlz (N): point skipped if mask < 0.5 or nlz > 0; the six extent floats and max_dist as in
+ *   the reference (distances are SQUARED distances there, and so here).
+ *   result (N) int32: index of the first containing box, -1 if none.  */
+int rd_assign3d_v2(const float* pc, const float* bbox, const float* bbox_center, const float* bbox_radius,
+                   const float* mask, const float* is_in_nlz, float max_x, float min_x, float max_y, float min_y,
+                   float max_z, float min_z, float max_dist, int64_t n_points, int n_boxes, int* result,
+                   rd_stream_t stream);
+/* bbox_inds_each_pt (N) FLOAT indices as the reference passes them (input.py:433-435) -> out (N) float: number
+ * of points sharing the point's box, -1 where the index is negative (MAX_BOX_NUM = 500, assigner.h:94; indices
+ * >= 500 are out of bounds in the reference and yield -1 here).  The workspace holds the 500 int32 counts
+ * afterwards (input of rd_rpn_reg_target). */
+size_t rd_get_point_num_workspace_bytes(void);
+int rd_get_point_num(const float* bbox_inds_each_pt, int64_t n_points, float* out, void* workspace,
+                     size_t workspace_bytes, rd_stream_t stream);
+/* gt_box7 (M,7) [x,y,z,l,w,h,yaw] ("gt_bbox_csa"), bbox_ind (N) from rd_assign3d_v2, point_hist = the counts
+ * left in rd_get_point_num's workspace, reg_dim_weight (8) -> reg_target (N,8) =
+ * [dx,dy (signed sqrt, azimuth frame), log w, log l, cos, sin (yaw - azimuth), bottom z, log h],
+ * reg_normalize_weight (N,8) = 1 / points-in-box, reg_weight (N,8) = reg_dim_weight inside boxes; 0 elsewhere. */
+int rd_rpn_reg_target(const float* pc, const float* gt_box7, const int* bbox_ind, const int* point_hist,
+                      const float* reg_dim_weight, int64_t n_points, int n_boxes, float* reg_target,
+                      float* reg_normalize_weight, float* reg_weight, rd_stream_t stream);
+
 /* ---- weighted NMS ------------------------------------------------------------------------
  * Replaces processing_cxx.wnms_4c: point4_wnms_4c / trtplus::wnms_4c,
  * operator_cxx/src_cxx/nms.h:781-794, :452-577.

@@ -112,6 +112,22 @@ class _OracleOps(_Ops):
         return out
 
 
+    def assign3d_v2(self, pc, bbox, center, radius, mask, nlz, max_x, min_x, max_y, min_y, max_z, min_z, max_dist):
+        pc, bbox, center = _c32(pc).reshape(-1, 3), _c32(bbox).reshape(-1, 24), _c32(center).reshape(-1, 3)
+        radius, mask, nlz = _c32(radius).reshape(-1), _c32(mask).reshape(-1), _c32(nlz).reshape(-1)
+        out = np.empty((pc.shape[0],), np.int32)
+        cf = ctypes.c_float
+        self.lib.orc_assign3d_v2(_fp(pc), _fp(bbox), _fp(center), _fp(radius), _fp(mask), _fp(nlz), cf(max_x), cf(min_x),
+                                 cf(max_y), cf(min_y), cf(max_z), cf(min_z), cf(max_dist), ctypes.c_long(pc.shape[0]),
+                                 int(bbox.shape[0]), _ip(out))
+        return out
+
+    def get_point_num(self, inds):
+        inds = _c32(inds).reshape(-1)
+        out = np.empty_like(inds)
+        self.lib.orc_get_point_num(_fp(inds), ctypes.c_long(inds.shape[0]), _fp(out))
+        return out
+
     def nms3d(self, boxes, iou_thres, max_keep, normal_iou=False):
         boxes = _c32(boxes)
         B, N, _ = boxes.shape

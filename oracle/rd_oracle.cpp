@@ -682,4 +682,68 @@ void orc_nms3d(const float* boxes, int B, int N, float thr, int max_keep, int no
   }
 }
 
+// ---- training-target assignment ---------------------------------------------------------------------------
+// assign3D_v2, operator_cxx/src_cxx/assigner.h:11-87 (Eigen + pybind11; Eigen is not available here, so this is a
+// restatement -- "parity unpinned" for this piece).  Distances are SQUARED norms compared with radius / max_dist
+// as given (:46-50); the squared norm is accumulated in index order like Eigen's scalar loop over a dynamic row.
+void orc_assign3d_v2(const float* pc, const float* bbox, const float* center, const float* radius, const float* mask,
+                     const float* nlz, float max_x, float min_x, float max_y, float min_y, float max_z, float min_z,
+                     float max_dist, long N, int M, int* result) {
+  std::vector<float> dist(M > 0 ? M : 1);
+  for (long i = 0; i < N; ++i) {
+    result[i] = -1;
+    if (mask[i] < 0.5f || nlz[i] > 0.f) continue;
+    const float px = pc[i * 3], py = pc[i * 3 + 1], pz = pc[i * 3 + 2];
+    if (px < min_x || px > max_x) continue;
+    if (py < min_y || py > max_y) continue;
+    if (pz < min_z || pz > max_z) continue;
+    float min_d = INFINITY;
+    for (int j = 0; j < M; ++j) {
+      const float d0 = center[j * 3] - px, d1 = center[j * 3 + 1] - py, d2 = center[j * 3 + 2] - pz;
+      float acc = d0 * d0;
+      acc = acc + d1 * d1;
+      acc = acc + d2 * d2;
+      dist[j] = acc;
+      if (acc < min_d) min_d = acc;
+    }
+    if (min_d > max_dist) continue;
+    for (int j = 0; j < M; ++j) {
+      const float* q = bbox + (long)j * 24;
+      const float ax = q[0], ay = q[1], az = q[2], bx = q[3], by = q[4], cx = q[6], cy = q[7], dx = q[9], dy = q[10],
+                  ez = q[14];
+      if (dist[j] > radius[j]) continue;
+      if (pz <= az || pz >= ez) continue;
+      if (px < ax && px < bx && px < cx && px < dx) continue;
+      if (py < ay && py < by && py < cy && py < dy) continue;
+      if (px > ax && px > bx && px > cx && px > dx) continue;
+      if (py > ay && py > by && py > cy && py > dy) continue;
+      const float bpx = px - bx, bpy = py - by;
+      if ((ax - bx) * bpx + (ay - by) * bpy <= 0.f) continue;
+      if ((cx - bx) * bpx + (cy - by) * bpy <= 0.f) continue;
+      const float dpx = px - dx, dpy = py - dy;
+      if ((ax - dx) * dpx + (ay - dy) * dpy <= 0.f) continue;
+      if ((cx - dx) * dpx + (cy - dy) * dpy <= 0.f) continue;
+      result[i] = j;
+      break;
+    }
+  }
+}
+
+// get_point_num, assigner.h:89-109: float indices in, float counts out, -1 where the index is negative.
+void orc_get_point_num(const float* inds, long N, float* out) {
+  const int MAX_BOX_NUM = 500;
+  std::vector<float> cnt(MAX_BOX_NUM, 0.f);
+  for (long i = 0; i < N; ++i) {
+    if (inds[i] < 0) continue;
+    const int k = (int)inds[i];
+    if (k < MAX_BOX_NUM) cnt[k] += 1;
+  }
+  for (long i = 0; i < N; ++i) {
+    out[i] = -1.f;
+    if (inds[i] < 0) continue;
+    const int k = (int)inds[i];
+    if (k < MAX_BOX_NUM) out[i] = cnt[k];
+  }
+}
+
 }  // extern "C"

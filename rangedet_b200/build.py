@@ -27,6 +27,7 @@ PER_FILE = {
     "wnms.cu": ["-fmad=false"],
     "nms3d.cu": ["-fmad=false"],
     "rpn_loss.cu": ["-fmad=false"],
+    "assign.cu": ["-fmad=false"],
 }
 
 

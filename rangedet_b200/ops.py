@@ -12,6 +12,8 @@ device memory and streams.  No function here has a CPU path.
   Custom op 'batch_rotated_iou' (batch_rotated_iou.py)       batch_rotated_iou
   processing_cxx.wnms_4c        (pybinding.cpp:8)            rangedet_b200.processing_cxx.wnms_4c
   RangeRpnHead.get_fpn_loss, one level (builder.py:300-422)  rpn_loss
+  processing_cxx.assign3D_v2 / get_point_num (assigner.h)    rangedet_b200.processing_cxx.* / *_device
+  GenerateTarget.get_rpn_reg_target (input.py:452-506)       rpn_reg_target
 """
 import ctypes
 
@@ -318,6 +320,60 @@ def rpn_loss(cls_logit, reg_delta, pc, gt_bbox, mask, reg_target, reg_weight, re
                            _p(ws), ctypes.c_size_t(ws.numel()), _stream())
     _lib.check(st, "rpn_loss")
     return o
+
+
+def assign3d_v2_device(pc, bbox, bbox_center, bbox_radius, mask, is_in_nlz, max_x, min_x, max_y, min_y, max_z, min_z,
+                       max_dist):
+    """Device-resident assign3D_v2 (operator_cxx/src_cxx/assigner.h:11-87): pc (N,3), bbox (M,24), bbox_center (M,3),
+    bbox_radius (M[,1]), mask (N[,1]), is_in_nlz (N[,1]) CUDA float32 -> (N,) int32 box index, -1 = none."""
+    pc = _chk(pc, "pc", 2, 3)
+    N = pc.shape[0]
+    bbox = _chk(bbox.reshape(-1, 24), "bbox", 2, 24)
+    M = bbox.shape[0]
+    ctr = _chk(bbox_center.reshape(-1, 3), "bbox_center", 2, 3)
+    rad = _chk(bbox_radius.reshape(-1), "bbox_radius", 1)
+    mask = _chk(mask.reshape(-1), "mask", 1)
+    nlz = _chk(is_in_nlz.reshape(-1), "is_in_nlz", 1)
+    if ctr.shape[0] != M or rad.shape[0] != M or mask.shape[0] != N or nlz.shape[0] != N:
+        raise ValueError("assign3D_v2: inconsistent shapes")
+    out = torch.empty((N,), device=pc.device, dtype=torch.int32)
+    with torch.cuda.device(pc.device):
+        st = _lib.lib().rd_assign3d_v2(_p(pc), _p(bbox), _p(ctr), _p(rad), _p(mask), _p(nlz), float(max_x), float(min_x),
+                                       float(max_y), float(min_y), float(max_z), float(min_z), float(max_dist), N, M,
+                                       _p(out), _stream())
+    _lib.check(st, "assign3D_v2")
+    return out
+
+
+def get_point_num_device(bbox_inds_each_pt, return_hist=False):
+    """Device-resident get_point_num (assigner.h:89-109): (N,) float32 box index per point -> (N,) float32 number of
+    points in that box (-1 where the index is negative).  return_hist: also the (500,) int32 per-box counts."""
+    inds = _chk(bbox_inds_each_pt.reshape(-1), "bbox_inds_each_pt", 1)
+    out = torch.empty_like(inds)
+    L = _lib.lib()
+    hist = torch.zeros(int(L.rd_get_point_num_workspace_bytes()) // 4, device=inds.device, dtype=torch.int32)
+    with torch.cuda.device(inds.device):
+        st = L.rd_get_point_num(_p(inds), inds.numel(), _p(out), _p(hist), ctypes.c_size_t(hist.numel() * 4), _stream())
+    _lib.check(st, "get_point_num")
+    return (out, hist) if return_hist else out
+
+
+def rpn_reg_target(pc, gt_box7, bbox_ind, point_hist, reg_dim_weight):
+    """GenerateTarget for one frame, num_classes == 1 (rangedet/core/input.py:345-372, 430-506): pc (N,3), gt_box7 (M,7)
+    [x,y,z,l,w,h,yaw], bbox_ind (N) int32, point_hist (500) int32, reg_dim_weight (8) ->
+    (rpn_reg_target, reg_normalize_weight, rpn_reg_weight), each (N,8) float32."""
+    pc = _chk(pc, "pc", 2, 3)
+    N = pc.shape[0]
+    g7 = _chk(gt_box7.reshape(-1, 7), "gt_box7", 2, 7)
+    dw = _chk(reg_dim_weight.reshape(-1), "reg_dim_weight", 1)
+    if bbox_ind.dtype != torch.int32 or point_hist.dtype != torch.int32 or bbox_ind.numel() != N or dw.numel() != 8:
+        raise ValueError("rpn_reg_target: bbox_ind (N) / point_hist must be int32 and reg_dim_weight have 8 entries")
+    outs = [torch.empty((N, 8), device=pc.device) for _ in range(3)]
+    with torch.cuda.device(pc.device):
+        st = _lib.lib().rd_rpn_reg_target(_p(pc), _p(g7), _p(bbox_ind.contiguous()), _p(point_hist.contiguous()), _p(dw), N,
+                                          g7.shape[0], _p(outs[0]), _p(outs[1]), _p(outs[2]), _stream())
+    _lib.check(st, "rpn_reg_target")
+    return tuple(outs)
 
 
 def wnms_4c_device(dets, thresh, thresh_vote, is_3d=False, hash_scale=100):

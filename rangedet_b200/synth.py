@@ -204,3 +204,46 @@ def rpn_targets(batch, seed=5, n_vehicles=30, strides=(1, 2, 4), h=H_RANGE, w=W_
         out["range_image_mask_s%d" % s] = np.ascontiguousarray(msk[..., ::s])
         out["pc_vehicle_frame_s%d" % s] = np.ascontiguousarray(xyz[..., ::s].reshape(batch, 3, -1).transpose(0, 2, 1))
     return out
+
+
+def boxes7_to_corners24(b7):
+    """[cx,cy,cz,l,w,h,yaw] -> (M,24): 8 corners xyz, bottom face A,B,C,D then top face E,F,G,H (the layout
+    operator_cxx/src_cxx/assigner.h:31-35 reads: A,B,C,D footprint, A.z bottom, E.z top)."""
+    c10 = boxes7_to_corners10(b7)
+    m = c10.shape[0]
+    out = np.empty((m, 8, 3), np.float32)
+    for k in range(4):
+        out[:, k, 0] = out[:, k + 4, 0] = c10[:, 2 * k]
+        out[:, k, 1] = out[:, k + 4, 1] = c10[:, 2 * k + 1]
+        out[:, k, 2] = c10[:, 8]
+        out[:, k + 4, 2] = c10[:, 9]
+    return out.reshape(m, 24)
+
+
+def assign_frame(n_vehicles=30, seed=0, h=H_RANGE, w=W_RANGE, missing=0.10):
+    """One synthetic frame for the target-assignment path: points (h*w,3) in the vehicle frame of which a few
+    hundred fall inside each of n_vehicles boxes (plus near misses around them), the validity mask, the boxes as
+    7-dof and as 8 corners."""
+    rng = np.random.default_rng(seed)
+    incl = np.linspace(-0.31, 0.04, h, dtype=np.float64)[:, None]
+    azim = np.linspace(np.pi, -np.pi, w, dtype=np.float64)[None, :]
+    r = rng.uniform(2.0, 75.0, size=(h, w))
+    x = r * np.cos(incl) * np.cos(azim)
+    y = r * np.cos(incl) * np.sin(azim)
+    z = r * np.sin(incl)
+    b7 = boxes7(n_vehicles, seed + 31)
+    rc, ac = rng.uniform(8.0, 60.0, n_vehicles), rng.uniform(-np.pi, np.pi, n_vehicles)
+    b7[:, 0], b7[:, 1], b7[:, 2] = rc * np.cos(ac), rc * np.sin(ac), rng.uniform(0.5, 1.5, n_vehicles)
+    for v in range(n_vehicles):
+        half = max(2, int(np.arctan2(3.0, rc[v]) / (2 * np.pi) * w))
+        c0 = int((np.pi - ac[v]) / (2 * np.pi) * (w - 1))
+        cols = np.arange(max(c0 - half, 0), min(c0 + half + 1, w))
+        r0 = int(rng.integers(0, max(h - 8, 1)))
+        hh, ww = np.meshgrid(np.arange(r0, min(r0 + 8, h)), cols, indexing="ij")
+        # scattered around the box: inside, on the faces' outside, above / below
+        x[hh, ww] = b7[v, 0] + rng.uniform(-3.5, 3.5, hh.shape)
+        y[hh, ww] = b7[v, 1] + rng.uniform(-3.5, 3.5, hh.shape)
+        z[hh, ww] = b7[v, 2] + rng.uniform(-1.5, 1.5, hh.shape)
+    mask = (rng.uniform(size=(h, w)) >= missing).astype(np.float32)
+    pc = np.stack([x, y, z], -1).astype(np.float32) * mask[..., None]
+    return pc.reshape(-1, 3), mask.reshape(-1), b7.astype(np.float32), boxes7_to_corners24(b7)

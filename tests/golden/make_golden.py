@@ -33,8 +33,18 @@ def loss_vectors():
     np.savez_compressed(os.path.join(OUT, "rpn_loss.npz"), **items)
 
 
+def assign_vectors():
+    """Target assignment (restatement of assigner.h / input.py; parity unpinned: Eigen absent)."""
+    from oracle import target_ref
+    pc, mask, b7, c24 = synth.assign_frame(n_vehicles=12, seed=2, h=16, w=400)
+    ind = target_ref.bbox3d_ind(pc, c24, mask)
+    np.savez_compressed(os.path.join(OUT, "assign.npz"), ind=ind, norm_w=target_ref.normalization_weight(ind),
+                        target=target_ref.rpn_reg_target(pc, b7, ind))
+
+
 def main():
     loss_vectors()
+    assign_vectors()
     ref = oracle.reference()
     assert ref is not None, "needs /root/reference"
     # decode (8-dim and bin)
