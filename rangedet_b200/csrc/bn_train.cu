@@ -15,6 +15,7 @@
 //              reduce  S1 = sum g, S2 = sum g*(z - mean)
 //              dz = a * (g - S1/M - (z - mean) * invstd^2 * S2/M),  dgamma = invstd*S2,  dbeta = S1
 #include <cuda_bf16.h>
+#include <stdlib.h>
 
 #include "../../include/rangedet_b200.h"
 #include "rd_common.cuh"
@@ -426,6 +427,8 @@ __global__ void __launch_bounds__(NT) add_kernel(const __nv_bfloat16* __restrict
   }
 }
 
+#include "bn_stream.cuh"
+
 static int check_shape(const char* what, int N, int H, int W, int C) {
   RD_REQUIRE(N > 0 && H > 0 && W > 0, "%s: bad shape", what);
   RD_REQUIRE(C >= 8 && C % 8 == 0 && C <= 1024, "%s: C must be a multiple of 8, <= 1024 (got %d)", what, C);
@@ -451,10 +454,18 @@ int rd_bn_train_stats_nhwc_bf16(const void* z_pad, int N, int H, int W, int C, c
   RD_REQUIRE(workspace_bytes >= rd_bn_workspace_bytes(C), "rd_bn_train_stats: workspace too small");
   if (rd_check_device()) return 1;
   const bn::Geo g = bn::make_geo(N, H, W, C);
-  const int grid = bn::grid_for(g);
+  int grid = bn::grid_for(g);
   cudaStream_t s = rd::as_stream(stream);
-  bn::stats_kernel<<<grid, g.ppb * g.cgs, 0, s>>>(static_cast<const __nv_bfloat16*>(z_pad), g, 1,
-                                                   static_cast<float*>(workspace));
+  if (bn::stream_enabled()) {
+    const bn::SGeo sg = bn::make_sgeo(N, H, W, C, 1);
+    const size_t smem = bn::sgeo_smem(sg, 1);
+    if (bn::stream_prepare(bn::s_stats_kernel, smem)) return 1;
+    grid = bn::stream_grid(sg);
+    bn::s_stats_kernel<<<grid, bn::SNT, smem, s>>>(static_cast<const __nv_bfloat16*>(z_pad), sg, static_cast<float*>(workspace));
+  } else {
+    bn::stats_kernel<<<grid, g.ppb * g.cgs, 0, s>>>(static_cast<const __nv_bfloat16*>(z_pad), g, 1,
+                                                     static_cast<float*>(workspace));
+  }
   bn::fwd_finalize_kernel<<<(C + 7) / 8, 256, 0, s>>>(static_cast<const float*>(workspace), grid, C,
                                                           (double)N * H * W, gamma, beta, eps, momentum, moving_mean,
                                                           moving_var, coef);
@@ -470,9 +481,19 @@ int rd_bn_act_fwd_nhwc_bf16(const void* z_pad, const float* coef, const void* re
   const bn::Geo g = bn::make_geo(N, H, W, C);
   const int64_t units = (int64_t)g.N * g.H * g.nseg;
   const int grid = (int)(units < 8 * 148 ? units : 8 * 148);
-  bn::fwd_apply_kernel<<<grid, g.ppb * g.cgs, 0, rd::as_stream(stream)>>>(
-      static_cast<const __nv_bfloat16*>(z_pad), coef, static_cast<const __nv_bfloat16*>(res_before),
-      static_cast<const __nv_bfloat16*>(res_after), static_cast<__nv_bfloat16*>(y_pad), g, relu ? 1 : 0);
+  if (bn::stream_enabled()) {
+    const int nt = 1 + (res_before ? 1 : 0) + (res_after ? 1 : 0);
+    const bn::SGeo sg = bn::make_sgeo(N, H, W, C, nt);
+    const size_t smem = bn::sgeo_smem(sg, nt);
+    if (bn::stream_prepare(bn::s_fwd_apply_kernel, smem)) return 1;
+    bn::s_fwd_apply_kernel<<<bn::stream_grid(sg), bn::SNT, smem, rd::as_stream(stream)>>>(
+        static_cast<const __nv_bfloat16*>(z_pad), coef, static_cast<const __nv_bfloat16*>(res_before),
+        static_cast<const __nv_bfloat16*>(res_after), static_cast<__nv_bfloat16*>(y_pad), sg, relu ? 1 : 0);
+  } else {
+    bn::fwd_apply_kernel<<<grid, g.ppb * g.cgs, 0, rd::as_stream(stream)>>>(
+        static_cast<const __nv_bfloat16*>(z_pad), coef, static_cast<const __nv_bfloat16*>(res_before),
+        static_cast<const __nv_bfloat16*>(res_after), static_cast<__nv_bfloat16*>(y_pad), g, relu ? 1 : 0);
+  }
   rd::count_launch();
   return rd::check_launch("rd_bn_act_fwd");
 }
@@ -497,14 +518,28 @@ int rd_bn_act_bwd_nhwc_bf16(const void* dy_pad, const void* y_mask_pad, const vo
   const __nv_bfloat16* dy = static_cast<const __nv_bfloat16*>(dy_pad);
   const __nv_bfloat16* ym = static_cast<const __nv_bfloat16*>(y_mask_pad);
   const __nv_bfloat16* z = static_cast<const __nv_bfloat16*>(z_pad);
-  bn::bwd_reduce_kernel<<<grid, g.ppb * g.cgs, 0, s>>>(dy, ym, z, coef, g, mask_mode, partial);
-  bn::bwd_finalize_kernel<<<(C + 7) / 8, 256, 0, s>>>(partial, grid, C, (double)N * H * W, coef, coef2, dgamma,
-                                                          dbeta);
-  const int64_t units = (int64_t)g.N * g.H * g.nseg;
-  const int grid2 = (int)(units < 8 * 148 ? units : 8 * 148);
-  bn::bwd_apply_kernel<<<grid2, g.ppb * g.cgs, 0, s>>>(dy, ym, z, coef, coef2, g, mask_mode,
-                                                       static_cast<__nv_bfloat16*>(dz_pad), dz_halo_w,
-                                                       static_cast<__nv_bfloat16*>(g_out_pad));
+  if (bn::stream_enabled()) {
+    const int nt = mask_mode == 1 ? 3 : 2;
+    const bn::SGeo sg = bn::make_sgeo(N, H, W, C, nt);
+    const size_t smem = bn::sgeo_smem(sg, nt);
+    if (bn::stream_prepare(bn::s_bwd_reduce_kernel, smem) || bn::stream_prepare(bn::s_bwd_apply_kernel, smem)) return 1;
+    const int sgrid = bn::stream_grid(sg);
+    bn::s_bwd_reduce_kernel<<<sgrid, bn::SNT, smem, s>>>(dy, ym, z, coef, sg, mask_mode, partial);
+    bn::bwd_finalize_kernel<<<(C + 7) / 8, 256, 0, s>>>(partial, sgrid, C, (double)N * H * W, coef, coef2, dgamma,
+                                                            dbeta);
+    bn::s_bwd_apply_kernel<<<sgrid, bn::SNT, smem, s>>>(dy, ym, z, coef, coef2, sg, mask_mode,
+                                                        static_cast<__nv_bfloat16*>(dz_pad), dz_halo_w,
+                                                        static_cast<__nv_bfloat16*>(g_out_pad));
+  } else {
+    bn::bwd_reduce_kernel<<<grid, g.ppb * g.cgs, 0, s>>>(dy, ym, z, coef, g, mask_mode, partial);
+    bn::bwd_finalize_kernel<<<(C + 7) / 8, 256, 0, s>>>(partial, grid, C, (double)N * H * W, coef, coef2, dgamma,
+                                                            dbeta);
+    const int64_t units = (int64_t)g.N * g.H * g.nseg;
+    const int grid2 = (int)(units < 8 * 148 ? units : 8 * 148);
+    bn::bwd_apply_kernel<<<grid2, g.ppb * g.cgs, 0, s>>>(dy, ym, z, coef, coef2, g, mask_mode,
+                                                         static_cast<__nv_bfloat16*>(dz_pad), dz_halo_w,
+                                                         static_cast<__nv_bfloat16*>(g_out_pad));
+  }
   rd::count_launch(3);
   return rd::check_launch("rd_bn_act_bwd");
 }
