@@ -3,8 +3,8 @@
 // The register-staged kernels in bn_train.cu keep at most 4-6 16-byte loads per thread in flight
 // (24-48 KB per SM): ncu shows them at 33 % (stats), 50 % (bwd_reduce) and 56 % (bwd_apply) of the DRAM peak with
 // the warps parked on the long scoreboard.  Here one elected thread streams contiguous row segments
-// (UP pixels x C channels, 16-24 KB per tensor) into a 3-stage shared-memory ring with cp.async.bulk + mbarrier
-// complete_tx: up to ~150 KB per SM in flight at no register cost; 512 threads consume each stage with
+// (UP pixels x C channels, 22-48 KB per tensor) into a 3-stage shared-memory ring with cp.async.bulk + mbarrier
+// complete_tx: up to ~190 KB per SM in flight at no register cost; 512 threads consume each stage with
 // conflict-free 16-byte shared loads and write results with 16-byte global stores.  One persistent CTA per SM.
 #pragma once
 
@@ -24,7 +24,17 @@ static SGeo make_sgeo(int N, int H, int W, int C, int ntensors) {
   g.N = N; g.H = H; g.W = W; g.C = C;
   g.cgs = C / 8;
   g.ppb = SNT / g.cgs;
-  const int target = ntensors <= 2 ? 24576 : 16384;
+  // measured (scripts/bn_bench.py, 4x64x2656x128): 12 KB units 3.0 TB/s, 16 KB 4.6, 24 KB 5.5, 32 KB 5.9 TB/s for the
+  // backward pair -- the ring must hold ~100-190 KB per SM to cover the HBM latency-bandwidth product
+  int target = ntensors == 1 ? 49152 : (ntensors == 2 ? 32768 : 21840);
+  {
+    static int env_ub = -1;   // RD_BN_UB=<bytes>: tuning override of the per-tensor unit size (2 tensors; 3 use 2/3 of it)
+    if (env_ub < 0) {
+      const char* e = getenv("RD_BN_UB");
+      env_ub = e ? atoi(e) : 0;
+    }
+    if (env_ub >= 2048 && env_ub <= 32768) target = ntensors == 1 ? env_ub * 3 / 2 : (ntensors == 2 ? env_ub : env_ub * 2 / 3);
+  }
   int up = target / (2 * C) / g.ppb * g.ppb;
   if (up < g.ppb) up = g.ppb;
   g.up = up;
