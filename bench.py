@@ -176,12 +176,11 @@ def train_step_leg(args, rank, world, dev, B=TRAIN_B):
     P = make_params(seed=0, device=dev)
     nparam = num_parameters(P)
 
-    def allreduce(flat):
+    def allreduce(flat):   # sum; the 1/world of the average is folded into the optimiser's rescale_grad
         dist.all_reduce(flat, op=dist.ReduceOp.SUM)
-        flat.div_(world)
 
     step = train.GraphedTrainStep(P, B, H, W_PAD, lr=0.01 / 8 * world * B * 5, device=dev,
-                                  allreduce=allreduce if world > 1 else None)
+                                  allreduce=allreduce if world > 1 else None, world_size=world)
     step.set_targets(synth.rpn_targets(B, seed=500 + rank))
     g = torch.Generator(device=dev).manual_seed(600 + rank)
     data = torch.randn((B, 8, H, W_PAD), device=dev, generator=g)

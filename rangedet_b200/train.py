@@ -601,11 +601,12 @@ class GraphedTrainStep(object):
     trainable parameters live in ONE flat fp32 buffer (`params[name]` become views of it), TrainGraph runs in flat
     mode (one gather launch packs all bf16 operands, one collects all gradients) and the MXNet SGD-momentum
     update is one launch (rd_sgd_mom_update) whose learning rate is read from device memory (set_lr).  With
-    `allreduce` given, the flat gradient buffer is averaged across ranks between backward and update by one NCCL
-    all-reduce (the reference: hvd.DistributedOptimizer, tools/train.py:364-368)."""
+    `allreduce` given, the flat gradient buffer is summed across ranks between backward and update by one NCCL
+    all-reduce and averaged through rescale_grad / world_size (the reference: hvd.DistributedOptimizer,
+    tools/train.py:364-368)."""
 
     def __init__(self, params, batch, H, W, lr, momentum=0.9, wd=1e-5, clip_gradient=35.0, rescale_grad=1.0 / 128.0,
-                 device="cuda", use_meta=True, allreduce=None, with_loss=True, overlap_wgrad=True):
+                 device="cuda", use_meta=True, allreduce=None, world_size=1, with_loss=True, overlap_wgrad=True):
         self.P = params
         self.allreduce = allreduce
         self.with_loss = with_loss
@@ -625,7 +626,9 @@ class GraphedTrainStep(object):
             self.flat_wd[o:o + n] = wd * wd_mult(k)
             o += n
         self.gviews = {k: self.flat[self.offsets[k]:self.offsets[k] + n].view(params[k].shape) for k, n in zip(names, sizes)}
-        self.hyper = torch.tensor([lr, momentum, rescale_grad, clip_gradient if clip_gradient else 0.0], device=device)
+        # `allreduce(flat)` SUMS the flat gradient over ranks; the 1/world_size of the average rides rescale_grad
+        self.hyper = torch.tensor([lr, momentum, rescale_grad / world_size, clip_gradient if clip_gradient else 0.0],
+                                  device=device)
         self.tg = TrainGraph(params, device, use_meta)
         if overlap_wgrad:
             self.tg.side = torch.cuda.Stream(device=device)
