@@ -176,8 +176,12 @@ def train_step_leg(args, rank, world, dev, B=TRAIN_B):
     P = make_params(seed=0, device=dev)
     nparam = num_parameters(P)
 
+    ar_ev = [torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)]
+
     def allreduce(flat):   # sum; the 1/world of the average is folded into the optimiser's rescale_grad
+        ar_ev[0].record()
         dist.all_reduce(flat, op=dist.ReduceOp.SUM)
+        ar_ev[1].record()
 
     step = train.GraphedTrainStep(P, B, H, W_PAD, lr=0.01 / 8 * world * B * 5, device=dev,
                                   allreduce=allreduce if world > 1 else None, world_size=world)
@@ -209,6 +213,7 @@ def train_step_leg(args, rank, world, dev, B=TRAIN_B):
                        "RPN loss, bwd, all-reduce, SGD; B=%d/GPU, 64x2656, bf16 operands / fp32 accumulate, training-mode BN" % B,
            "value": B * world * n / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms / n, "steps": n, "batch_per_gpu": B,
            "parameters": int(nparam), "allreduce_bytes": int(step.flat.numel() * 4) if world > 1 else 0,
+           "allreduce_ms": ar_ev[0].elapsed_time(ar_ev[1]) if world > 1 else 0.0,
            "algorithmic_TFLOPs": 3 * 1.114e12 * B / (ms / n * 1e-3) / 1e12,
            "cls_loss": float(sum(o["cls_loss"].sum() for o in loss)), "reg_loss": float(sum(o["reg_loss"].sum() for o in loss)),
            "params_finite": bool(torch.isfinite(step.flatP).all())}
@@ -228,6 +233,9 @@ def run_ours(args, rank, local_rank, world):
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
+        # rank 0 prints ONE JSON line on stdout: keep NCCL's version banner (NCCL_DEBUG=VERSION) out of it
+        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+            os.environ["NCCL_DEBUG"] = "WARN"
         dist.init_process_group("nccl", device_id=dev)
     impl = args.mk_impl
     B = B_PER_GPU
