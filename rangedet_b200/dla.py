@@ -200,7 +200,7 @@ class GraphedForward(object):
             self.out = self.head.get_fpn_output(self.backbone.get_rpn_feature(self.data, self.coord))
         torch.cuda.synchronize()
         self.graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(self.graph):
+        with torch.cuda.graph(self.graph, capture_error_mode="thread_local"):
             self.out = self.head.get_fpn_output(self.backbone.get_rpn_feature(self.data, self.coord))
 
     def __call__(self, data, coord):

@@ -669,11 +669,14 @@ class GraphedTrainStep(object):
         self.flat_m.zero_()
         self.pool = torch.cuda.graph_pool_handle()
         self.g_fwd, self.g_bwd, self.g_upd = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
-        with torch.cuda.graph(self.g_fwd, pool=self.pool):
+        # thread_local: another thread's CUDA calls (the NCCL watchdog of a data-parallel job polls events) must not
+        # invalidate the capture
+        mode = dict(capture_error_mode="thread_local")
+        with torch.cuda.graph(self.g_fwd, pool=self.pool, **mode):
             self._fwd()
-        with torch.cuda.graph(self.g_bwd, pool=self.pool):
+        with torch.cuda.graph(self.g_bwd, pool=self.pool, **mode):
             self._bwd()
-        with torch.cuda.graph(self.g_upd, pool=self.pool):
+        with torch.cuda.graph(self.g_upd, pool=self.pool, **mode):
             self._update()
 
     def _fwd(self):
