@@ -553,14 +553,14 @@ LOSS_HYPER = dict(iou_type="bev", alpha=1.0, gamma=2.0, smooth_l1_scalar=3.0, sc
                   cls_loss_weight=10.0, reg_loss_weight=8.0)   # config/rangedet/rangedet_veh_wo_aug_4_18e.py:36,122-129
 
 
-def rpn_loss_levels(cls_logit, bbox_delta, targets, out=None, hyper=LOSS_HYPER):
+def rpn_loss_levels(cls_logit, bbox_delta, targets, out=None, hyper=LOSS_HYPER, gt_name="gt_bbox_veh_for_iou_pred"):
     """RangeRpnHead.get_fpn_loss (builder.py:268-348) on the head outputs: per level one fused launch pair
     (ops.rpn_loss).  `targets`: dict of CUDA tensors with the graph-input names of builder.py:20-37.
     Returns [per-level dict(iou_target, cls_loss, reg_loss, d_cls, d_reg)]."""
     res = []
     for lvl, s in enumerate(STRIDES):
         res.append(ops.rpn_loss(cls_logit[lvl], bbox_delta[lvl], targets["pc_vehicle_frame_s%d" % s],
-                                targets["gt_bbox_veh_for_iou_pred"], targets["range_image_mask_s%d" % s],
+                                targets[gt_name], targets["range_image_mask_s%d" % s],
                                 targets["rpn_reg_target_s%d" % s], targets["rpn_reg_weight_s%d" % s],
                                 targets["reg_normalize_weight_s%d" % s], out=None if out is None else out[lvl], **hyper))
     return res
@@ -606,10 +606,13 @@ class GraphedTrainStep(object):
     tools/train.py:364-368)."""
 
     def __init__(self, params, batch, H, W, lr, momentum=0.9, wd=1e-5, clip_gradient=35.0, rescale_grad=1.0 / 128.0,
-                 device="cuda", use_meta=True, allreduce=None, world_size=1, with_loss=True, overlap_wgrad=True):
+                 device="cuda", use_meta=True, allreduce=None, world_size=1, with_loss=True, overlap_wgrad=True,
+                 loss_hyper=None, gt_name="gt_bbox_veh_for_iou_pred"):
         self.P = params
         self.allreduce = allreduce
         self.with_loss = with_loss
+        self.loss_hyper = dict(LOSS_HYPER if loss_hyper is None else loss_hyper)
+        self.gt_name = gt_name
         names = sorted(k for k in params if not k.endswith(("_moving_mean", "_moving_var")))
         self.names = names
         sizes = [params[k].numel() for k in names]
@@ -639,8 +642,11 @@ class GraphedTrainStep(object):
         self.targets, self.loss_out = None, None
         if with_loss:
             z = lambda *shape: torch.zeros(shape, device=device)
-            self.targets = {"gt_bbox_veh_for_iou_pred": z(batch, 200, 8)}
-            self.targets["gt_bbox_veh_for_iou_pred"][:, :, 3:7] = 1e-3     # all-padding GT (input.py:264-265)
+            self.targets = {gt_name: z(batch, 200, 8 if self.loss_hyper["iou_type"] == "bev" else 7)}
+            if self.loss_hyper["iou_type"] == "bev":
+                self.targets[gt_name][:, :, 3:7] = 1e-3     # all-padding GT (input.py:264-265)
+            else:
+                self.targets[gt_name][:, :, 3:6] = 1e-3
             self.loss_out = []
             for s, dc, dr in zip(STRIDES, self.d_cls, self.d_reg):
                 self.targets["rpn_reg_target_s%d" % s] = z(batch, 8, H, W // s)
@@ -685,7 +691,7 @@ class GraphedTrainStep(object):
 
     def _bwd(self):
         if self.with_loss:
-            rpn_loss_levels(self.out[0], self.out[1], self.targets, out=self.loss_out)
+            rpn_loss_levels(self.out[0], self.out[1], self.targets, out=self.loss_out, hyper=self.loss_hyper, gt_name=self.gt_name)
         grads = self.tg.backward(self.d_cls, self.d_reg)
         if not self.tg.flat_grads:
             ks = [k for k in self.names if k in grads]
