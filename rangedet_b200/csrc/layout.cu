@@ -24,31 +24,51 @@ __device__ __forceinline__ int map_channel(int c_nhwc, int C, int chmap) {
 }
 
 // src: haloed NHWC bf16 [N][H+2][W+2][Cs]; dst: NCHW fp32 [N][C][H][W]; channels [0, C) converted.
+// Tile = 64 pixels x 64 channels: 16-byte loads (8 channels of one pixel; a warp covers 4 pixels x 128 B),
+// transposed through shared memory, 16-byte stores (4 pixels of one channel; 16 lanes cover 256 contiguous bytes).
+constexpr int TP2 = 64;
 __global__ void __launch_bounds__(256) nhwc_to_nchw_kernel(const __nv_bfloat16* __restrict__ src, float* __restrict__ dst,
                                                           int N, int H, int W, int Cs, int C, int chmap) {
-  __shared__ float tile[TC][TP + 1];
+  __shared__ float tile[TC][TP2 + 1];
   const int wt = blockIdx.x, h = blockIdx.y % H, n = blockIdx.y / H;
-  const int w0 = wt * TP;
+  const int w0 = wt * TP2;
   const int64_t srow = (((int64_t)n * (H + 2) + h + 1) * (W + 2) + 1) * Cs;
+  const bool vec_ld = (Cs % 8) == 0;                 // 16-byte aligned pixel rows
+  const bool vec_st = (W % 4) == 0;                  // 16-byte aligned channel rows
   for (int c0 = 0; c0 < C; c0 += TC) {
-    // load: thread -> (pixel, channel pair): 32 px x 32 pairs = 1024 pairs, 4 per thread
-    for (int e = threadIdx.x; e < TP * (TC / 2); e += 256) {
-      const int p = e / (TC / 2), cp = e % (TC / 2);
-      float a = 0.f, b = 0.f;
-      if (w0 + p < W && c0 + 2 * cp < C) {
-        const __nv_bfloat162 v = *reinterpret_cast<const __nv_bfloat162*>(src + srow + (int64_t)(w0 + p) * Cs + c0 + 2 * cp);
-        a = __bfloat162float(v.x);
-        b = __bfloat162float(v.y);
+    for (int e = threadIdx.x; e < TP2 * (TC / 8); e += 256) {
+      const int p = e / (TC / 8), ch = (e % (TC / 8)) * 8;
+      float f[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) f[i] = 0.f;
+      if (w0 + p < W && c0 + ch < C) {
+        const __nv_bfloat16* q = src + srow + (int64_t)(w0 + p) * Cs + c0 + ch;
+        if (vec_ld && c0 + ch + 8 <= Cs) {
+          const uint4 v = __ldg(reinterpret_cast<const uint4*>(q));
+          const uint32_t w4[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            f[2 * i] = __uint_as_float(w4[i] << 16);
+            f[2 * i + 1] = __uint_as_float(w4[i] & 0xffff0000u);
+          }
+        } else {
+          for (int i = 0; i < 8 && c0 + ch + i < Cs; ++i) f[i] = __bfloat162float(q[i]);
+        }
       }
-      tile[2 * cp][p] = a;
-      tile[2 * cp + 1][p] = b;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) tile[ch + i][p] = f[i];
     }
     __syncthreads();
-    for (int e = threadIdx.x; e < TC * TP; e += 256) {
-      const int c = e / TP, p = e % TP;
-      if (w0 + p < W && c0 + c < C) {
+    for (int e = threadIdx.x; e < TC * (TP2 / 4); e += 256) {
+      const int c = e / (TP2 / 4), p = (e % (TP2 / 4)) * 4;
+      if (c0 + c < C && w0 + p < W) {
         const int cd = map_channel(c0 + c, C, chmap);
-        dst[(((int64_t)n * C + cd) * H + h) * W + w0 + p] = tile[c][p];
+        float* o = dst + (((int64_t)n * C + cd) * H + h) * W + w0 + p;
+        if (vec_st && w0 + p + 4 <= W) {
+          *reinterpret_cast<float4*>(o) = make_float4(tile[c][p], tile[c][p + 1], tile[c][p + 2], tile[c][p + 3]);
+        } else {
+          for (int i = 0; i < 4 && w0 + p + i < W; ++i) o[i] = tile[c][p + i];
+        }
       }
     }
     __syncthreads();
@@ -100,7 +120,7 @@ int rd_nhwc_bf16_to_nchw_f32(const void* src_pad, float* dst, int N, int H, int 
   RD_REQUIRE(chmap == 0 || (chmap == 1 && C % 9 == 0), "rd_nhwc_bf16_to_nchw_f32: chmap 1 needs C %% 9 == 0");
   RD_REQUIRE((int64_t)N * H <= 65535, "rd_nhwc_bf16_to_nchw_f32: N*H too large");
   if (rd_check_device()) return 1;
-  dim3 grid((W + lay::TP - 1) / lay::TP, N * H);
+  dim3 grid((W + lay::TP2 - 1) / lay::TP2, N * H);
   lay::nhwc_to_nchw_kernel<<<grid, 256, 0, rd::as_stream(stream)>>>(static_cast<const __nv_bfloat16*>(src_pad), dst, N, H, W,
                                                                     C_src, C, chmap);
   rd::count_launch();
