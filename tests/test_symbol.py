@@ -158,3 +158,38 @@ def test_train_and_test_symbols_run_on_the_device():
     s = score[0].cpu().numpy()
     assert np.all(s[:-1] >= s[1:]) and 0.0 <= s.min() and s.max() <= 1.0
     assert bool(torch.isfinite(score).all())   # (boxes of a random-init head may overflow exp(): no finiteness claim)
+
+
+def test_contrib_operator_names_dispatch_and_validate():
+    """Operator surface by name (rangedet_b200/contrib.py): unknown CustomOp names fail like MXNet's registry, string
+    kwargs are accepted, and without a device the call fails loudly instead of falling back."""
+    from rangedet_b200 import contrib
+    with pytest.raises(ValueError, match="not registered"):
+        contrib.Custom(op_type="roi_align")
+    assert contrib._as_bool("True") and not contrib._as_bool("0") and contrib._as_bool(1)
+    if not torch.cuda.is_available():
+        with pytest.raises(RuntimeError):
+            contrib.Decode3DBbox(torch.zeros(1, 4, 8), torch.zeros(1, 4, 3), is_bin="False")
+        with pytest.raises(RuntimeError):
+            contrib.Custom(op_type="get_sorted_foreground", cls_score=torch.zeros(1, 8), bbox_delta=torch.zeros(1, 8, 8),
+                           pc=torch.zeros(1, 8, 3), mask=torch.zeros(1, 8), num_fgs="4")
+
+
+@pytest.mark.gpu
+def test_contrib_operators_match_ops():
+    from rangedet_b200 import contrib, ops
+    d, pc = synth.decode_inputs(2, 500, seed=1)
+    d, pc = torch.from_numpy(d).cuda(), torch.from_numpy(pc).cuda()
+    dec = contrib.Decode3DBbox(d, pc, is_bin=False)
+    assert torch.equal(dec, ops.decode_3d_bbox(d, pc))
+    gt = torch.from_numpy(synth.gt_boxes8(2)).cuda()
+    iou = contrib.Custom(proposal=dec, gt_bbox=gt, op_type="batch_rotated_iou", iou_type="bev")
+    assert torch.equal(iou, ops.batch_rotated_iou(dec, gt, "bev"))
+    m = contrib.RotatedIOU(dec[0, :50, :8].contiguous(), gt[0, :20].contiguous())
+    assert m.shape == (50, 20) and float(m.max()) <= 1.0
+    score = torch.rand(2, 500, device="cuda")
+    s, fd, fp = contrib.Custom(cls_score=score, bbox_delta=d, pc=pc, mask=torch.ones(2, 500, device="cuda"),
+                               op_type="get_sorted_foreground", num_fgs="100")
+    assert s.shape == (2, 100) and fd.shape == (2, 100, 8) and fp.shape == (2, 100, 3)
+    keep, boxes = contrib.NMS3D(contrib.Decode3DBbox(fd, fp), 0.2, 30)
+    assert keep.shape == (2, 30) and boxes.shape == (2, 30, 10) and keep.dtype == torch.int32
