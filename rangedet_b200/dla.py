@@ -12,8 +12,8 @@ runs the fused TMA/tcgen05 Meta-Kernel.  Activations stay in HBM as zero-haloed 
 The Meta-Kernel unit (meta_kernel_conv) runs as: NHWC bf16 -> NCHW fp32 conversion of the 64-channel
 input (torch, the op boundary of the Meta-Kernel) -> ONE fused kernel (Meta-Kernel + BN(576) + ReLU,
 NHWC bf16 out) -> tcgen05 1x1 aggregation conv.  `fuse_meta=False` keeps the reference op boundary
-((B,576,H,W) fp32) with torch glue, for comparison.  Training-mode BatchNorm (batch statistics) and the backward
-convolutions are next-round work.
+((B,576,H,W) fp32) with torch glue, for comparison.  The training graph (batch statistics, backward kernels, loss,
+optimiser) is rangedet_b200/train.py.
 """
 import torch
 
