@@ -84,6 +84,13 @@ class _Ops:
                        ctypes.c_long(b2.shape[0]), b1.shape[1])
         return out
 
+    def nms3d_iou(self, box_a, box_b, normal_iou=False):
+        """IoU of two 10-dim boxes as NMS3D evaluates it (nms_3d.cu:342-378)."""
+        f = getattr(self.lib, self.prefix + "_nms3d_iou")
+        f.restype = ctypes.c_float
+        box_a, box_b = _c32(box_a), _c32(box_b)
+        return float(f(_fp(box_a), _fp(box_b), int(bool(normal_iou))))
+
     def single_overlap(self, box1, box2, is3d=False):
         box1, box2 = _c32(box1), _c32(box2)
         return float(self._ovl(_fp(box1), _fp(box2), int(is3d)))

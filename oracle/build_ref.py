@@ -6,12 +6,15 @@ What it does (only when /root/reference is present, i.e. in the build container;
 the GPU box just uses the prebuilt oracle/_ref/librd_ref.so that travels with
 the snapshot):
 
-  * derives three headers into oracle/_ref/ (git-ignored, never committed) from
+  * derives four headers into oracle/_ref/ (git-ignored, never committed) from
     the reference sources where they lie:
       - operator_cxx/contrib/decode_3d_bbox-inl.h : the part between
         ``const float EPS`` and ``template <typename xpu>`` (the two functor
         structs; the MXNet FCompute driver needs an MXNet source tree)
       - operator_cxx/contrib/rotated_iou-inl.h    : same cut
+      - operator_cxx/contrib/nms_3d.cu            : the __device__ geometry helpers
+        between ``const float EPS`` and the first ``__global__`` kernel, compiled
+        for the host with ``#define __device__`` (pins the IoU of NMS3D)
       - operator_cxx/src_cxx/nms.h                : line 1 (``#include
         "overlap.h"``, which drags Eigen) replaced by overlap.h's own non-Eigen
         preamble so ``atan2(float,float)`` resolves exactly as in the original TU
@@ -68,6 +71,10 @@ def build(force=False):
     with open(os.path.join(OUT, "riou_extract.h"), "w") as f:
         f.write(_cut(os.path.join(contrib, "rotated_iou-inl.h"),
                      "const float EPS", "template <typename xpu>"))
+    # nms_3d.cu: the __device__ helper functions (Point ... iou_bev, iou_normal, lines 29-378) are plain C++ once
+    # __device__ is defined away; the kernels / MXNet driver below them need nvcc + an MXNet tree and are not taken
+    with open(os.path.join(OUT, "nms3d_extract.h"), "w") as f:
+        f.write(_cut(os.path.join(contrib, "nms_3d.cu"), "const float EPS", "__global__ void nms_kernel_3d"))
     with open(os.path.join(REF, "operator_cxx", "src_cxx", "nms.h"), "r",
               encoding="utf-8", errors="replace") as f:
         nms = f.readlines()

@@ -656,6 +656,10 @@ int orc_wnms_4c(const float* dets, int n, float thresh, float thresh_vote, int i
   return K;
 }
 
+float orc_nms3d_iou(const float* box_a, const float* box_b, int normal_iou) {
+  return normal_iou ? n3::iou_normal(box_a, box_b) : n3::iou_bev3d(box_a, box_b);
+}
+
 // NMS3DForward<gpu> nms_3d.cu:470-534 + nms_kernel_3d :380-434 + prepare_output_kernel_3d :436-468.
 // boxes (B,N,10) sorted by score; keep_idx (B,max_keep) filled -1; boxes_out (B,max_keep,10) filled 0.
 void orc_nms3d(const float* boxes, int B, int N, float thr, int max_keep, int normal_iou, int* keep_idx,

@@ -29,6 +29,16 @@ namespace ref_riou {
 #undef MACRO_MAX
 #undef MACRO_MIN
 
+// nms_3d.cu device helpers compiled for the host (operator_cxx/contrib/nms_3d.cu:29-378)
+#define __device__
+namespace ref_nms3d {
+// CUDA's device-side min / max overloads for float are fminf / fmaxf (cuda math API); the host has no unqualified ones
+inline float min(float a, float b) { return fminf(a, b); }
+inline float max(float a, float b) { return fmaxf(a, b); }
+#include "nms3d_extract.h"
+}
+#undef __device__
+
 #include "nms_extract.h"
 
 extern "C" {
@@ -59,6 +69,11 @@ void ref_rotated_iou(const float* b1, const float* b2, float* out, long n1, long
     for (long i = 0; i < total; ++i)
       ref_riou::RotateIoUKernelGPU::Map<float>((int)i, (int)n1, (int)n2, b1, b2, out, box_type);
   }
+}
+
+// iou_bev (volumetric, :342-368) / iou_normal (:370-378) of two 10-dim boxes, as nms_kernel_3d calls them (:420-426)
+float ref_nms3d_iou(const float* box_a, const float* box_b, int normal_iou) {
+  return normal_iou ? ref_nms3d::iou_normal(box_a, box_b) : ref_nms3d::iou_bev(box_a, box_b);
 }
 
 float ref_single_overlap(const float* box1, const float* box2, int is3d) {

@@ -42,9 +42,19 @@ def assign_vectors():
                         target=target_ref.rpn_reg_target(pc, b7, ind))
 
 
+def nms3d_iou_vectors(ref):
+    """IoU as NMS3D evaluates it, from the reference's nms_3d.cu device helpers compiled for the host."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import test_oracle_pinning as T
+    b, pairs = T._nms3d_pairs()
+    iou = np.array([[ref.nms3d_iou(b[i], b[j], nrm) for nrm in (0, 1)] for i, j in pairs], np.float32)
+    np.savez_compressed(os.path.join(OUT, "nms3d_iou.npz"), iou=iou)
+
+
 def main():
     loss_vectors()
     assign_vectors()
+    nms3d_iou_vectors(oracle.reference())
     ref = oracle.reference()
     assert ref is not None, "needs /root/reference"
     # decode (8-dim and bin)
