@@ -8,10 +8,11 @@ Parity status
   * post-process ops (decode / rotated IoU / wNMS): restatement in rd_oracle.cpp, PINNED
     against the reference's own C++ compiled from source (oracle/_ref/librd_ref.so, built
     by build_ref.py) and against tests/golden/*.npz generated from it.
-  * Meta-Kernel / convs: the arithmetic lives in MXNet (mxnet==2.0.0 per the reference's
-    requirements.txt:2), absent from /root/reference and not installable here ->
-    "parity unpinned" at the MXNet boundary; meta_kernel_ref.py restates
-    rangedet/symbol/backbone/meta_kernel.py:166-240 op-for-op in torch fp32.
+  * Meta-Kernel / convs / loss head: the arithmetic lives in MXNet (mxnet==2.0.0 per the reference's
+    requirements.txt:2), absent from /root/reference and not installable here -> operator-level
+    parity unpinned; meta_kernel_ref.py / dla_ref.py / dla_train_ref.py / loss_ref.py restate the graphs
+    op-for-op in torch fp32 and are checked against the reference's OWN graph code executed eagerly
+    (mx_eager.py stand-in for the MXNet symbol operators; ref_graph.py, ref_py.py; tests/test_reference_graph.py).
 """
 import ctypes
 import os

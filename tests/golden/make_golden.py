@@ -51,7 +51,19 @@ def nms3d_iou_vectors(ref):
     np.savez_compressed(os.path.join(OUT, "nms3d_iou.npz"), iou=iou)
 
 
+def ref_py_vectors():
+    """Outputs of the reference's own Python CustomOps run through oracle/ref_py.py (needs /root/reference)."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import test_oracle_pinning as T
+    from oracle import ref_py
+    prop, gt8, g7, score, d, pc, mask = T._ref_py_case()
+    fs, fd, fp = ref_py.get_sorted_foreground(score, d, pc, mask, 200)
+    np.savez_compressed(os.path.join(OUT, "ref_py_ops.npz"), bev=ref_py.batch_rotated_iou(prop, gt8, "bev"),
+                        iou3d=ref_py.batch_rotated_iou(prop, g7.copy(), "3d"), fg_score=fs, fg_delta=fd, fg_pc=fp)
+
+
 def main():
+    ref_py_vectors()
     loss_vectors()
     assign_vectors()
     nms3d_iou_vectors(oracle.reference())

@@ -218,3 +218,44 @@ def test_nms3d_iou_matches_reference_device_functions(orc, ref):
         pytest.skip("reference sources / prebuilt oracle/_ref not present")
     live = np.array([[ref.nms3d_iou(b[i], b[j], nrm) for nrm in (0, 1)] for i, j in pairs], np.float32)
     assert np.array_equal(got, live, equal_nan=True)
+
+
+def _ref_py_case():
+    """Inputs for the reference's Python CustomOps: clustered proposals, GT = every 12th proposal jittered (+ padding)."""
+    prop = np.stack([synth.boxes7_to_corners10(synth.boxes7(600, seed=11 + b, clustered=True)) for b in range(2)])
+    gt8 = synth.gt_boxes8(2, 50, 200, seed=3)
+    g7 = np.zeros((2, 200, 7), np.float32)
+    g7[:, :, 3:6] = 1e-3
+    for b in range(2):
+        gt8[b, :50] = prop[b, ::12, :8] + np.float32(0.07)
+        bb = synth.boxes7(600, seed=11 + b, clustered=True)[::12].copy()
+        bb[:, :2] += 0.07
+        g7[b, :50] = bb
+    d, pc = synth.decode_inputs(2, 600, seed=4)
+    rng = np.random.default_rng(0)
+    score = rng.standard_normal((2, 600)).astype(np.float32)
+    mask = (rng.uniform(size=(2, 600)) > 0.3).astype(np.float32)
+    return prop, gt8, g7, score, d, pc, mask
+
+
+def test_restatements_match_the_reference_python_customops(orc):
+    """operator_py/batch_rotated_iou.py and get_sorted_foreground.py, executed UNMODIFIED over a minimal stand-in for
+    the MXNet array calls they make (oracle/ref_py.py; RotatedIOU = the reference's compiled functor): golden outputs
+    committed from that run, plus the live run where /root/reference exists.  'bev' and the foreground selection are
+    bit-exact; '3d' goes through numpy's mean / **0.5 / arctan2 in to_box_type_7 (:51-68) -> 1e-3 (observed 8e-5)."""
+    from oracle import ref_py, sorted_fg_ref
+    prop, gt8, g7, score, d, pc, mask = _ref_py_case()
+    g = golden("ref_py_ops.npz")
+    bev = orc.batch_rotated_iou_max(prop, gt8, "bev")
+    i3d = orc.batch_rotated_iou_max(prop, g7.copy(), "3d")
+    fg = sorted_fg_ref.get_sorted_foreground(score, d, pc, mask, 200)
+    assert np.array_equal(bev, g["bev"]) and (bev > 0.3).mean() > 0.3
+    assert np.abs(i3d - g["iou3d"]).max() <= 1e-3 and (i3d > 0).mean() > 0.3
+    for a, k in zip(fg, ("fg_score", "fg_delta", "fg_pc")):
+        assert np.array_equal(a, g[k]), k
+    if not ref_py.available():
+        pytest.skip("/root/reference not present: golden vectors only")
+    assert np.array_equal(ref_py.batch_rotated_iou(prop, gt8, "bev"), bev)
+    assert np.abs(ref_py.batch_rotated_iou(prop, g7.copy(), "3d") - i3d).max() <= 1e-3
+    for a, b in zip(ref_py.get_sorted_foreground(score, d, pc, mask, 200), fg):
+        assert np.array_equal(a, b)
