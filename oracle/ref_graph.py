@@ -118,3 +118,25 @@ def backbone_head(P, data, coord, training=True, targets=None, iou_type="bev"):
                 cls_loss=[l.t.detach() for l in losses[:3]], reg_loss=[l.t.detach() for l in losses[3:]],
                 d_cls=[c.t.grad for c in cls], d_reg=[r.t.grad for r in reg],
                 grads={k: v.grad for k, v in Pg.items() if v.grad is not None}, used=used, moving={k: v.detach() for k, v in Pg.items() if "_moving_" in k})
+
+
+def fpn_prediction(cls_logit, bbox_delta, pc_list, mask_list, pre_n, post_n=200, nms_thr=0.2):
+    """RangeRpnHead.get_fpn_prediction of the reference (builder.py:424-534, wnms branch) on GIVEN head outputs
+    (get_fpn_output is replaced by a function returning them): -> (fg_cls_score (B,K), decoded_bbox (B,K,10))."""
+    B, _, H, W = cls_logit[0].shape
+    with mx_eager.reference_modules() as imp:
+        norm = imp("mxnext.complicate").normalizer_factory(type="localbn", ndev=1)
+        _, pR = _configs(B, H, W, norm)
+
+        class all_proposal:
+            rpn_pre_nms_top_n = {"veh": pre_n}
+            rpn_post_nms_top_n = {"veh": post_n}
+            nms_thr = {"veh": 0.2}
+        pR.all_proposal = all_proposal
+        hb = imp("rangedet.symbol.head.builder")
+        head = hb.RangeRpnHead(pR)
+        head.get_fpn_output = lambda feats: ([S(c) for c in cls_logit], [S(d) for d in bbox_delta])
+        with mx_eager.bound({}, training=False):
+            out = head.get_fpn_prediction([None] * 3, [S(torch.as_tensor(p)) for p in pc_list],
+                                          [S(torch.as_tensor(m)) for m in mask_list])
+    return out[0].t.detach(), out[1].t.detach()

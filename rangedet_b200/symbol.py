@@ -190,9 +190,14 @@ class _TestExecutor(object):
     def __call__(self, record):
         """record: dict of CUDA tensors named like list_inputs().  Returns the reference's output list
         [rec_id, fg_cls_score (B,K), proposal (B,K,10) or (B,post_n,10), keep_inds, gt_bbox_imu, gt_class]."""
-        s_ = self.sym.det.fpn_strides
         cls_logit, bbox_delta = self.fwd(record["input_data"], record["coord_s1"])
-        B = self.B
+        fg_score, prop, keep = self.predict(cls_logit, bbox_delta, record)
+        return [record.get("rec_id"), fg_score, prop, keep, record.get("gt_bbox_imu"), record.get("gt_class")]
+
+    def predict(self, cls_logit, bbox_delta, record):
+        """get_fpn_prediction (builder.py:424-534) on the head outputs: per-level (B,1,H,W_l) / (B,8,H,W_l) lists."""
+        s_ = self.sym.det.fpn_strides
+        B = cls_logit[0].shape[0]
         # sep_level_type(concat_all_level_per_class=True), builder.py:99-153
         cls = torch.cat([c.reshape(B, -1) for c in cls_logit], 1)
         delta = torch.cat([d.reshape(B, 8, -1).transpose(1, 2) for d in bbox_delta], 1).contiguous()
@@ -202,7 +207,6 @@ class _TestExecutor(object):
         fg_score, fg_delta, fg_pc = ops.get_sorted_foreground(score, delta, pc, mask, self.pre_n)
         decoded = ops.decode_3d_bbox(fg_delta, fg_pc, is_bin=False)
         if self.wnms:
-            prop, keep = decoded, torch.zeros((1,), device=decoded.device)
-        else:
-            keep, prop = ops.nms3d(decoded, self.nms_thr, self.post_n)
-        return [record.get("rec_id"), fg_score, prop, keep, record.get("gt_bbox_imu"), record.get("gt_class")]
+            return fg_score, decoded, torch.zeros((1,), device=decoded.device)
+        keep, prop = ops.nms3d(decoded, self.nms_thr, self.post_n)
+        return fg_score, prop, keep

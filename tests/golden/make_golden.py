@@ -62,7 +62,19 @@ def ref_py_vectors():
                         iou3d=ref_py.batch_rotated_iou(prop, g7.copy(), "3d"), fg_score=fs, fg_delta=fd, fg_pc=fp)
 
 
+def prediction_vectors():
+    """get_fpn_prediction of the reference executed eagerly (oracle/mx_eager.py) on fixed head outputs."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import test_symbol as T
+    from oracle import ref_graph
+    cls, reg, rec = T._prediction_case()
+    sc, box = ref_graph.fpn_prediction(cls, reg, [rec["pc_vehicle_frame_s%d" % s] for s in (1, 2, 4)],
+                                       [rec["range_image_mask_s%d" % s].reshape(2, -1) for s in (1, 2, 4)], 300)
+    np.savez_compressed(os.path.join(OUT, "fpn_prediction.npz"), score=sc.numpy(), boxes=box.numpy())
+
+
 def main():
+    prediction_vectors()
     ref_py_vectors()
     loss_vectors()
     assign_vectors()

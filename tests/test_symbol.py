@@ -193,3 +193,52 @@ def test_contrib_operators_match_ops():
     assert s.shape == (2, 100) and fd.shape == (2, 100, 8) and fp.shape == (2, 100, 3)
     keep, boxes = contrib.NMS3D(contrib.Decode3DBbox(fd, fp), 0.2, 30)
     assert keep.shape == (2, 30) and boxes.shape == (2, 30, 10) and keep.dtype == torch.int32
+
+
+def _prediction_case():
+    B, H, W = 2, 64, 32
+    g = torch.Generator().manual_seed(0)
+    cls = [torch.randn(B, 1, H, W // s, generator=g) for s in (1, 2, 4)]
+    T = synth.rpn_targets(B, seed=3, n_vehicles=6, h=H, w=W - 2, w_pad=W)
+    reg = [torch.from_numpy(T["rpn_reg_target_s%d" % s]) + 0.2 * torch.randn(B, 8, H, W // s, generator=g) for s in (1, 2, 4)]
+    return cls, reg, T
+
+
+def test_prediction_golden_is_the_reference_graph_output():
+    """tests/golden/fpn_prediction.npz = RangeRpnHead.get_fpn_prediction of the reference (builder.py:424-534) executed
+    through oracle/mx_eager.py on the head outputs of _prediction_case(); re-derived live where /root/reference exists."""
+    from conftest import golden
+    from oracle import mx_eager, ref_graph
+    g = golden("fpn_prediction.npz")
+    assert g["score"].shape == (2, 300) and g["boxes"].shape == (2, 300, 10)
+    assert np.all(g["score"][:, :-1] >= g["score"][:, 1:])
+    if not mx_eager.available():
+        pytest.skip("/root/reference not present")
+    cls, reg, T = _prediction_case()
+    sc, box = ref_graph.fpn_prediction(cls, reg, [T["pc_vehicle_frame_s%d" % s] for s in (1, 2, 4)],
+                                       [T["range_image_mask_s%d" % s].reshape(2, -1) for s in (1, 2, 4)], 300)
+    assert np.array_equal(sc.numpy(), g["score"]) and np.array_equal(box.numpy(), g["boxes"])
+
+
+@pytest.mark.gpu
+def test_test_executor_prediction_matches_reference_graph():
+    """Our inference executor's post-forward part (level concat order, sigmoid, get_sorted_foreground, decode) on the
+    same head outputs: scores 1e-6 (sigmoid ulp), selected points identical, boxes 1e-5."""
+    from conftest import golden
+    cls, reg, T = _prediction_case()
+    _, pR, _ = shipped_config(False, (64, 32))
+
+    class R(pR):
+        class all_proposal:
+            rpn_pre_nms_top_n = {'veh': 300}
+            rpn_post_nms_top_n = {'veh': 200}
+            nms_thr = {'veh': 0.2}
+    ex = symbol._TestExecutor.__new__(symbol._TestExecutor)          # the post-forward part needs no parameters
+    ex.sym = symbol.RangeRCNN(R).get_test_symbol(symbol.DLABackbone(shipped_config(False, (64, 32))[0]), symbol.RangeRpnHead(R))
+    ex.pre_n, ex.post_n, ex.nms_thr, ex.wnms = 300, 200, 0.2, True
+    record = {k: torch.from_numpy(v).cuda() for k, v in T.items()}
+    score, boxes, keep = ex.predict([c.cuda() for c in cls], [r.cuda() for r in reg], record)
+    g = golden("fpn_prediction.npz")
+    assert np.abs(score.cpu().numpy() - g["score"]).max() <= 1e-6
+    assert np.allclose(boxes.cpu().numpy(), g["boxes"], rtol=1e-5, atol=1e-4)
+    assert keep.shape == (1,)
