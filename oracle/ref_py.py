@@ -128,3 +128,56 @@ def get_sorted_foreground(cls_score, bbox_delta, pc, mask, num_fgs):
         outs = [A(np.zeros((B, num_fgs), np.float32)), A(np.zeros((B, num_fgs, 8), np.float32)), A(np.zeros((B, num_fgs, 3), np.float32))]
         op.forward(False, ["write"] * 3, [A(np.array(x, np.float32)) for x in (cls_score, bbox_delta, pc, mask)], outs, [])
         return tuple(np.asarray(o) for o in outs)
+
+
+# ---- the reference's numpy data-loader transforms (rangedet/core/input.py) ---------------------------------------
+@contextlib.contextmanager
+def _loader_modules():
+    """rangedet.core.input imports `processing_cxx` (pybind11 + Eigen: not buildable here -> the C++ restatement in
+    rd_oracle.cpp stands in, so the index assignment itself stays unpinned) and utils.detection_input (needs
+    mx.io.DataIter as a base class only)."""
+    from . import oracle
+    assert os.path.isfile(os.path.join(REF, "rangedet", "core", "input.py")), "needs /root/reference"
+    orc = oracle()
+    pcx = types.ModuleType("processing_cxx")
+    pcx.assign3D_v2 = lambda pc, bbox, ctr, rad, mask, nlz, *f: orc.assign3d_v2(pc, bbox, ctr, rad, mask, nlz, *f).reshape(-1, 1)
+    pcx.get_point_num = lambda inds: orc.get_point_num(inds).reshape(-1, 1)
+    mx = types.ModuleType("mxnet")
+    mx.io = types.SimpleNamespace(DataIter=object, DataBatch=object, DataDesc=object)
+    stubs = {"processing_cxx": pcx, "mxnet": mx}
+    pk = ("rangedet", "utils")
+    saved = {k: sys.modules.get(k) for k in stubs}
+    for k in list(sys.modules):
+        if k.split(".")[0] in pk:
+            saved[k] = sys.modules.pop(k)
+    sys.modules.update(stubs)
+    sys.path.insert(0, REF)
+    try:
+        import importlib
+        yield importlib.import_module("rangedet.core.input")
+    finally:
+        sys.path.remove(REF)
+        for k in list(sys.modules):
+            if k.split(".")[0] in pk or k in stubs:
+                sys.modules.pop(k, None)
+        for k, v in saved.items():
+            if v is not None:
+                sys.modules[k] = v
+
+
+def loader_targets(pc_hw3, mask_hw1, gt_corners_m83, gt_box7, reg_weight):
+    """Bbox3dAssigner.apply + GenerateTarget.apply of the reference (input.py:276-372) on one 64x2650 frame ->
+    (bbox3d_ind (H*W,), rpn_reg_target, reg_normalize_weight, rpn_reg_weight each (H,W,8))."""
+    H, W = pc_hw3.shape[:2]
+    with _loader_modules() as inp:
+        class GP:
+            feat_size = (H, W)
+            num_classes = 1
+            label_set = [1]
+        GP.reg_weight = list(reg_weight)
+        rec = {"pc_vehicle_frame": np.array(pc_hw3, np.float32), "gt_bbox_imu": np.array(gt_corners_m83, np.float32),
+               "range_image_mask": np.array(mask_hw1), "gt_bbox_csa": np.array(gt_box7, np.float32),
+               "gt_class": np.ones((len(gt_box7),), np.int32)}
+        inp.Bbox3dAssigner(GP).apply(rec)
+        inp.GenerateTarget(GP).apply(rec)
+        return (rec["bbox3d_ind_of_each_pt"].reshape(-1), rec["rpn_reg_target"], rec["reg_normalize_weight"], rec["rpn_reg_weight"])

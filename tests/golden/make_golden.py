@@ -73,7 +73,21 @@ def prediction_vectors():
     np.savez_compressed(os.path.join(OUT, "fpn_prediction.npz"), score=sc.numpy(), boxes=box.numpy())
 
 
+def loader_vectors():
+    """Bbox3dAssigner + GenerateTarget of the reference (rangedet/core/input.py) run through oracle/ref_py.py."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import test_assign as T
+    from oracle import ref_py
+    pc, mask, b7, c24 = T._loader_case()
+    ind, tgt, nw, rw = ref_py.loader_targets(pc.reshape(64, 2650, 3), mask.reshape(64, 2650, 1), c24.reshape(-1, 8, 3), b7,
+                                             T.REG_W_SHIPPED)
+    sel = ind >= 0
+    np.savez_compressed(os.path.join(OUT, "loader_targets.npz"), ind=ind.astype(np.int32), target_fg=tgt.reshape(-1, 8)[sel],
+                        norm_fg=nw.reshape(-1, 8)[sel][:, 0], weight_fg=rw.reshape(-1, 8)[sel])
+
+
 def main():
+    loader_vectors()
     prediction_vectors()
     ref_py_vectors()
     loss_vectors()

@@ -121,3 +121,37 @@ def test_processing_cxx_assign_mirrors_and_edges():
     assert processing_cxx.get_point_num(np.zeros((0, 1), np.float32)).shape == (0, 1)
     with pytest.raises(ValueError):
         processing_cxx.assign3D_v2(pc[:, :2], c24, center, radius, mask, nlz, *ext, max_dist)
+
+
+REG_W_SHIPPED = [3, 1, 1, 1, 1, 1, 1, 1]    # config/rangedet/rangedet_veh_wo_aug_4_18e.py:219
+
+
+def _loader_case():
+    pc, mask, b7, c24 = synth.assign_frame(n_vehicles=30, seed=0)     # one full 64x2650 frame
+    return pc, mask, b7, c24
+
+
+def test_target_restatement_matches_the_reference_loader_code():
+    """rangedet/core/input.py Bbox3dAssigner.apply + GenerateTarget.apply, imported UNMODIFIED (oracle/ref_py.py;
+    processing_cxx = the C++ restatement, so the index assignment itself stays unpinned, but its ARGUMENTS -- radius,
+    centres, GT extent, max_dist, input.py:296-322 -- and all of the numpy target arithmetic are the reference's):
+    committed golden from that run, plus the live run where /root/reference exists.  Bit-exact."""
+    from oracle import ref_py, target_ref
+    pc, mask, b7, c24 = _loader_case()
+    ind = target_ref.bbox3d_ind(pc, c24, mask)
+    sel = ind >= 0
+    tgt = target_ref.rpn_reg_target(pc, b7, ind)
+    nw = target_ref.normalization_weight(ind)
+    rw = target_ref.rpn_reg_weight(ind, REG_W_SHIPPED)
+    g = golden("loader_targets.npz")
+    assert np.array_equal(ind, g["ind"]) and sel.sum() > 1000
+    assert np.array_equal(tgt[sel], g["target_fg"]) and not tgt[~sel].any()
+    assert np.array_equal(nw[sel], g["norm_fg"]) and np.array_equal(rw[sel], g["weight_fg"])
+    if not ref_py.available():
+        pytest.skip("/root/reference not present: golden vectors only")
+    r_ind, r_tgt, r_nw, r_rw = ref_py.loader_targets(pc.reshape(64, 2650, 3), mask.reshape(64, 2650, 1), c24.reshape(-1, 8, 3),
+                                                     b7, REG_W_SHIPPED)
+    assert np.array_equal(r_ind, ind)
+    assert np.array_equal(r_tgt.reshape(-1, 8), tgt)
+    assert np.array_equal(r_nw.reshape(-1, 8), np.tile(nw[:, None], (1, 8)))
+    assert np.array_equal(r_rw.reshape(-1, 8), rw)
