@@ -181,3 +181,17 @@ def loader_targets(pc_hw3, mask_hw1, gt_corners_m83, gt_box7, reg_weight):
         inp.Bbox3dAssigner(GP).apply(rec)
         inp.GenerateTarget(GP).apply(rec)
         return (rec["bbox3d_ind_of_each_pt"].reshape(-1), rec["rpn_reg_target"], rec["reg_normalize_weight"], rec["rpn_reg_weight"])
+
+
+def test_py_functions():
+    """The two numpy helpers of tools/test.py (bbox3d_12dim_to_8dim :43-53, bbox3d_10dim_to_11dim :56-81), their
+    source taken verbatim from the file with `ast` (the module itself cannot be imported: it dlopens contrib_cxx.so and
+    imports MXNet on line 1) and executed with numpy."""
+    import ast
+    path = os.path.join(REF, "tools", "test.py")
+    tree = ast.parse(open(path).read())
+    ns = {"np": np}
+    for node in tree.body:
+        if isinstance(node, ast.FunctionDef) and node.name in ("bbox3d_12dim_to_8dim", "bbox3d_10dim_to_11dim"):
+            exec(compile(ast.Module([node], []), path, "exec"), ns)
+    return ns["bbox3d_10dim_to_11dim"], ns["bbox3d_12dim_to_8dim"]
