@@ -92,6 +92,15 @@ class _Ops:
         box_a, box_b = _c32(box_a), _c32(box_b)
         return float(f(_fp(box_a), _fp(box_b), int(bool(normal_iou))))
 
+    def nms3d_kernels(self, boxes, iou_thres, max_keep, normal_iou=False):
+        """(reference library only) NMS3D through the reference's own kernels emulated on the host."""
+        boxes = _c32(boxes)
+        B, N, _ = boxes.shape
+        keep = np.empty((B, max_keep), np.int32)
+        out = np.empty((B, max_keep, 10), np.float32)
+        self.lib.ref_nms3d_kernels(_fp(boxes), B, N, ctypes.c_float(iou_thres), int(max_keep), int(bool(normal_iou)), _ip(keep), _fp(out))
+        return keep, out
+
     def single_overlap(self, box1, box2, is3d=False):
         box1, box2 = _c32(box1), _c32(box2)
         return float(self._ovl(_fp(box1), _fp(box2), int(is3d)))

@@ -75,6 +75,9 @@ def build(force=False):
     # __device__ is defined away; the kernels / MXNet driver below them need nvcc + an MXNet tree and are not taken
     with open(os.path.join(OUT, "nms3d_extract.h"), "w") as f:
         f.write(_cut(os.path.join(contrib, "nms_3d.cu"), "const float EPS", "__global__ void nms_kernel_3d"))
+        # ... and the two kernels themselves (nms_kernel_3d, prepare_output_kernel_3d, :380-468): ref_shim.cpp runs them
+        # on the host by defining blockIdx / threadIdx / __shared__ / __syncthreads (block emulation, see there)
+        f.write(_cut(os.path.join(contrib, "nms_3d.cu"), "__global__ void nms_kernel_3d", "template <>"))
     with open(os.path.join(REF, "operator_cxx", "src_cxx", "nms.h"), "r",
               encoding="utf-8", errors="replace") as f:
         nms = f.readlines()

@@ -49,6 +49,13 @@ def nms3d_iou_vectors(ref):
     b, pairs = T._nms3d_pairs()
     iou = np.array([[ref.nms3d_iou(b[i], b[j], nrm) for nrm in (0, 1)] for i, j in pairs], np.float32)
     np.savez_compressed(os.path.join(OUT, "nms3d_iou.npz"), iou=iou)
+    # whole op through the reference's kernels emulated on the host
+    b = T._nms3d_case()
+    items = {}
+    for tag, thr, mk, nrm in (("bev", 0.1, 300, False), ("normal", 0.3, 100, True)):
+        k, bx = ref.nms3d_kernels(b, thr, mk, nrm)
+        items[tag + "_keep"], items[tag + "_boxes"] = k, bx
+    np.savez_compressed(os.path.join(OUT, "nms3d_keep.npz"), **items)
 
 
 def ref_py_vectors():
