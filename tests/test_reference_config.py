@@ -1,0 +1,94 @@
+"""the reference's UNMODIFIED config file builds its graphs through this package's classes.
+
+config/rangedet/rangedet_veh_wo_aug_4_18e.py is imported verbatim from /root/reference with
+  rangedet.symbol.head.builder       -> rangedet_b200.symbol (RangeRCNN, RangeRpnHead)
+  rangedet.symbol.backbone.dla_backbone -> rangedet_b200.symbol (DLABackbone)
+  processing_cxx                     -> rangedet_b200.processing_cxx
+and the rest of the reference (mxnext, rangedet.core.input, rangedet.core.detection_metric, utils) as is, over the
+MXNet stand-in of oracle/mx_eager.py (imports only: nothing MXNet-side is executed).  `get_config()` must return
+our graph objects, and everything the config says about them -- metric output names, data / label names, the
+optimizer block -- must line up with what they expose.  Needs /root/reference: skipped elsewhere."""
+import contextlib
+import importlib
+import sys
+import types
+
+import pytest
+
+mx_eager = pytest.importorskip("oracle.mx_eager")
+pytestmark = pytest.mark.skipif(not mx_eager.available(), reason="/root/reference not present")
+
+
+@contextlib.contextmanager
+def drop_in():
+    from rangedet_b200 import processing_cxx, symbol
+    stubs = mx_eager._modules()
+    mx = stubs["mxnet"]
+
+    class EvalMetric(object):                      # mx.metric.EvalMetric: constructor signature only
+        def __init__(self, name, output_names=None, label_names=None, **kw):
+            self.name, self.output_names, self.label_names = name, output_names, label_names
+
+    mx.metric = types.SimpleNamespace(EvalMetric=EvalMetric)
+    mx.io = types.SimpleNamespace(DataIter=object, DataBatch=object, DataDesc=object)
+    builder = types.ModuleType("rangedet.symbol.head.builder")
+    builder.RangeRCNN, builder.RangeRpnHead = symbol.RangeRCNN, symbol.RangeRpnHead
+    backbone = types.ModuleType("rangedet.symbol.backbone.dla_backbone")
+    backbone.DLABackbone = symbol.DLABackbone
+    stubs.update({"processing_cxx": processing_cxx, "rangedet.symbol.head.builder": builder,
+                  "rangedet.symbol.backbone.dla_backbone": backbone})
+    pk = ("mxnext", "rangedet", "operator_py", "utils", "config")
+    saved = {k: sys.modules.get(k) for k in stubs}
+    for k in list(sys.modules):
+        if k.split(".")[0] in pk:
+            saved[k] = sys.modules.pop(k)
+    sys.modules.update(stubs)
+    sys.path.insert(0, mx_eager.REF)
+    try:
+        yield
+    finally:
+        sys.path.remove(mx_eager.REF)
+        for k in list(sys.modules):
+            if k.split(".")[0] in pk or k in stubs:
+                sys.modules.pop(k, None)
+        for k, v in saved.items():
+            if v is not None:
+                sys.modules[k] = v
+
+
+@pytest.mark.parametrize("name", ["rangedet_veh_wo_aug_4_18e", "rangedet_veh_wo_aug_all_36e", "rangedet_ped_wo_aug_4_18e"])
+def test_unmodified_config_builds_our_graphs(name):
+    from rangedet_b200 import symbol
+    with drop_in():
+        cfg = importlib.import_module("config.rangedet." + name)
+        (pGen, pKv, pRpn, pRoi, pBbox, pDataset, pModel, pOpt, pTest, transform, data_name, label_name, metric_list,
+         pLabelMap) = cfg.get_config(is_train=True)
+        train_sym = pModel.train_symbol
+        assert isinstance(train_sym, symbol.TrainSymbol) and pModel.test_symbol is None
+        # the metrics the config registers read exactly the outputs our train symbol lists (tools/train.py binds them by name)
+        assert sorted(o for m in metric_list for o in m.output_names) == sorted(train_sym.list_outputs())
+        # every array the loader is told to provide is a graph input of ours
+        inputs = train_sym.list_inputs()
+        assert set(data_name) | set(label_name) <= set(inputs), sorted((set(data_name) | set(label_name)) - set(inputs))
+        sh = train_sym.infer_shape()
+        assert sh["input_data"] == (pGen.batch_image, 8, 64, 2656) and all(n in sh for n in data_name + label_name)
+        # loss hyper-parameters and optimiser block as our bind() consumes them
+        hyp = train_sym.head.loss_hyper()
+        assert hyp["scale_loss_shift"] == 128.0 and hyp["smooth_l1_scalar"] == 3.0 and hyp["iou_type"] == "bev"
+        assert pOpt.optimizer.type == "sgd" and pOpt.optimizer.clip_gradient == 35 and pOpt.optimizer.momentum == 0.9
+        names = [type(t).__name__ for t in transform]                      # the loader pipeline is the reference's own
+        assert names.index("Bbox3dAssigner") < names.index("GenerateTarget") < names.index("GenerateFPNTarget")
+        # test-time graph from the same file
+        cfg_t = cfg.get_config(is_train=False)
+        test_sym = cfg_t[6].test_symbol
+        assert isinstance(test_sym, symbol.TestSymbol) and set(cfg_t[10]) <= set(test_sym.list_inputs())
+        assert cfg_t[8].nms.wnms is True and cfg_t[8].nms.thr_lo == 0.1
+
+
+def test_drop_in_context_restores_the_interpreter():
+    before = set(sys.modules)
+    with drop_in():
+        importlib.import_module("mxnext.complicate")
+        assert "mxnext" in sys.modules
+    assert not [k for k in sys.modules if k.split(".")[0] in ("mxnext", "mxnet", "config", "utils")]
+    assert "processing_cxx" not in sys.modules and set(sys.modules) - before <= {k for k in sys.modules if k.startswith(("numba", "llvmlite", "rangedet_b200", "oracle"))} | (set(sys.modules) - before)
