@@ -92,3 +92,57 @@ def test_drop_in_context_restores_the_interpreter():
         assert "mxnext" in sys.modules
     assert not [k for k in sys.modules if k.split(".")[0] in ("mxnext", "mxnet", "config", "utils")]
     assert "processing_cxx" not in sys.modules and set(sys.modules) - before <= {k for k in sys.modules if k.startswith(("numba", "llvmlite", "rangedet_b200", "oracle"))} | (set(sys.modules) - before)
+
+
+def _raw_record(tmp_path, seed=0):
+    """A synthetic raw roidb record + the npz LoadRecord reads (rangedet/core/input.py:24-42)."""
+    import numpy as np
+    from rangedet_b200 import synth
+    pc, mask, b7, c24 = synth.assign_frame(n_vehicles=20, seed=seed)
+    H, W = 64, 2650
+    rng = np.random.default_rng(seed)
+    pc = pc.reshape(H, W, 3)
+    rim = np.zeros((H, W, 4), np.float32)
+    rng_val = np.linalg.norm(pc, axis=2)
+    valid = mask.reshape(H, W) > 0
+    rim[..., 0] = np.where(valid, rng_val, -1.0)
+    rim[..., 1] = rng.uniform(0, 1, (H, W)) * valid
+    rim[..., 2] = rng.uniform(0, 1, (H, W)) * valid
+    rim[..., 3] = -1.0
+    url = str(tmp_path / "frame.npz")
+    np.savez(url, pc_vehicle_frame=pc, range_image=rim, inclination=np.linspace(-0.31, 0.04, H).astype(np.float32),
+             azimuth=np.linspace(np.pi, -np.pi, W).astype(np.float32))
+    M = b7.shape[0]
+    return {"pc_url": url, "gt_class": np.ones((M,), np.int64), "gt_bbox_yaw": b7[:, 6].copy(), "gt_bbox_csa": b7.copy(),
+            "gt_bbox_imu": c24.reshape(M, 8, 3).copy(), "meta_data": np.zeros((M, 4)), "points_in_box": np.full((M,), 10.0),
+            "rec_id": np.array([0])}
+
+
+def test_reference_loader_pipeline_output_fits_our_graph_inputs(tmp_path):
+    """The config's own transform list (LoadRecord ... TransAndReshape, rangedet/core/input.py) executed on a synthetic
+    raw frame: the record it produces must match, name by name and shape by shape, what TrainSymbol.infer_shape()
+    declares and GraphedTrainStep.set_targets() copies.  (processing_cxx = the CPU restatement here: the product
+    module has no CPU path.)"""
+    import numpy as np
+    from oracle import oracle
+    orc = oracle()
+    with drop_in():
+        pcx = types.ModuleType("processing_cxx")
+        pcx.assign3D_v2 = lambda pc, bbox, ctr, rad, mask, nlz, *f: orc.assign3d_v2(pc, bbox, ctr, rad, mask, nlz, *f).reshape(-1, 1)
+        pcx.get_point_num = lambda inds: orc.get_point_num(inds).reshape(-1, 1)
+        sys.modules["processing_cxx"] = pcx
+        cfg = importlib.import_module("config.rangedet.rangedet_veh_wo_aug_4_18e")
+        out = cfg.get_config(is_train=True)
+        pModel, transform, data_name, label_name = out[6], out[9], out[10], out[11]
+        rec = _raw_record(tmp_path)
+        for t in transform:
+            t.apply(rec)
+        sh = pModel.train_symbol.infer_shape(batch_image=1)
+        for n in data_name + label_name:
+            assert n in rec, n
+            assert tuple(rec[n].shape) == tuple(sh[n][1:]), (n, rec[n].shape, sh[n])
+            assert np.asarray(rec[n]).dtype in (np.float32, np.float64), (n, rec[n].dtype)
+        # content sanity of the record the kernels will see
+        assert rec["gt_bbox_veh_for_iou_pred"].shape == (200, 8) and np.allclose(rec["gt_bbox_veh_for_iou_pred"][-1], [0, 0, 0, 1e-3, 1e-3, 1e-3, 1e-3, 0])
+        assert (rec["rpn_reg_weight_s1"] > 0).any() and not rec["rpn_reg_target_s1"][:, :, 2650:].any()
+        assert set(np.unique(rec["range_image_mask_s1"])) <= {0.0, 1.0}
