@@ -62,3 +62,57 @@ def test_gloo_world2_gradient_allreduce_matches_global_batch():
     mp.spawn(_worker, args=(world, _free_port(), ret), nprocs=world, join=True)
     assert ret["err"] < 1e-5
     assert ret["shapes"] == [(32, 3), (32,), (64, 32), (64,)]
+
+
+def _train_worker(rank, world, port, ret):
+    """Whole-model data-parallel step on CPU: per-rank frames + LOCAL BatchNorm statistics (config:56), ONE flat
+    SUM all-reduce of every parameter gradient, MXNet SGD with rescale_grad / world -- the exchange contract of
+    rangedet_b200.train.GraphedTrainStep (tools/train.py:306-319, 359-368), with the torch restatement standing in
+    for the kernels."""
+    from oracle import dla_ref, dla_train_ref
+    from rangedet_b200 import train
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    torch.set_num_threads(2)
+    H, W = 8, 32
+    P = dla_ref.make_params(seed=0, device="cpu")
+    g = torch.Generator().manual_seed(5)
+    data = torch.randn(world, 8, H, W, generator=g)
+    coord = torch.from_numpy(synth.range_image_coords(world, seed=0, h=H, w=W - 2, w_pad=W))
+    d_cls = [torch.randn(world, 1, H, W // s, generator=g) for s in (1, 2, 4)]
+    d_reg = [torch.randn(world, 8, H, W // s, generator=g) for s in (1, 2, 4)]
+    names = sorted(k for k in P if not k.endswith(("_moving_mean", "_moving_var")))
+
+    def local_grads(r):
+        tr = dla_train_ref.TrainRef(P, bf16=False)
+        _, _, grads = tr.forward_backward(data[r:r + 1], coord[r:r + 1], [d[r:r + 1] for d in d_cls], [d[r:r + 1] for d in d_reg])
+        return torch.cat([grads[k].reshape(-1) for k in names])
+
+    flat = local_grads(rank)
+    dist.all_reduce(flat, op=dist.ReduceOp.SUM)                      # what GraphedTrainStep.allreduce must do
+    Pw = {k: P[k].clone() for k in names}
+    grads = {k: v for k, v in zip(names, rd_dist.unflatten_like(flat, [P[k] for k in names]))}
+    train.sgd_momentum_step(Pw, grads, {}, lr=0.05, momentum=0.9, wd=1e-5, clip_gradient=35.0, rescale_grad=1.0 / 128 / world)
+    after = torch.cat([Pw[k].reshape(-1) for k in names])
+    both = [torch.zeros_like(after) for _ in range(world)]
+    dist.all_gather(both, after)
+    if rank == 0:
+        ret["ranks_agree"] = bool(torch.equal(both[0], both[1]))
+        mean = sum(local_grads(r) for r in range(world)) / world     # single-process emulation of the same update
+        Ps = {k: P[k].clone() for k in names}
+        gs = {k: v for k, v in zip(names, rd_dist.unflatten_like(mean, [P[k] for k in names]))}
+        train.sgd_momentum_step(Ps, gs, {}, lr=0.05, momentum=0.9, wd=1e-5, clip_gradient=35.0, rescale_grad=1.0 / 128)
+        want = torch.cat([Ps[k].reshape(-1) for k in names])
+        ret["err"] = float((after - want).abs().max())
+        ret["moved"] = float((after - torch.cat([P[k].reshape(-1) for k in names])).abs().max())
+        ret["n"] = int(after.numel())
+    dist.destroy_process_group()
+
+
+def test_gloo_world2_whole_model_exchange_and_update():
+    world = 2
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    mp.spawn(_train_worker, args=(world, _free_port(), ret), nprocs=world, join=True)
+    assert ret["ranks_agree"] and ret["n"] > 9_000_000
+    assert ret["err"] < 1e-6 and ret["moved"] > 1e-4
