@@ -1,0 +1,143 @@
+"""Host logic of the training graph on a box WITHOUT a GPU: rangedet_b200.train.TrainGraph runs with `train.ops`
+replaced by tests/fake_ops.py (a plain-torch emulation of the kernel API with the same layouts), and is compared with
+the torch-autograd restatement oracle/dla_train_ref.py.  This checks the tape -- data-gradient weight layouts, W-stride-2
+layers as transposed convolutions, phase-grouped deconvolution gradients, the tap-major Meta-Kernel unit, residual
+gradient accumulation -- and the flat-mode gather maps; the kernels themselves are covered by the -m gpu tests."""
+import numpy as np
+import pytest
+import torch
+
+import fake_ops
+from rangedet_b200 import synth, train
+
+
+@pytest.fixture()
+def cpu_train(monkeypatch):
+    monkeypatch.setattr(train, "ops", fake_ops)
+    return train
+
+
+def _case(use_meta, B=1, H=4, W=32, seed=0):
+    from oracle import dla_ref
+    P = dla_ref.make_params(seed=seed, device="cpu")
+    g = torch.Generator().manual_seed(9)
+    P["res1_unit2_conv1_weight"] = torch.randn((64, 64, 3, 3), generator=g) * 0.06
+    for k, v in (("gamma", 1.0), ("beta", 0.0), ("moving_mean", 0.0), ("moving_var", 1.0)):
+        P["res1_unit2_bn1_" + k] = torch.full((64,), v)
+    data = torch.randn(B, 8, H, W, generator=g)
+    coord = torch.from_numpy(synth.range_image_coords(B, seed=0, h=H, w=W - 2, w_pad=W))
+    d_cls = [torch.randn(B, 1, H, W // s, generator=g) * 1e-2 for s in (1, 2, 4)]
+    d_reg = [torch.randn(B, 8, H, W // s, generator=g) * 1e-2 for s in (1, 2, 4)]
+    return P, data, coord, d_cls, d_reg
+
+
+def _rms(a, b):
+    a, b = a.double().reshape(-1), b.double().reshape(-1)
+    return float(((a - b) ** 2).mean().sqrt() / max(float((b ** 2).mean().sqrt()), 1e-30))
+
+
+@pytest.fixture()
+def exact_train(monkeypatch):
+    """float64 activations and operands everywhere: no storage rounding, so the tape must agree with autograd to
+    fp32-level precision (the parameter-gradient buffers stay float32)."""
+    monkeypatch.setattr(train, "ops", fake_ops)
+    fake_ops.set_exact(True)
+    pack = train.pack_operand
+    monkeypatch.setattr(train, "pack_operand", lambda w, kind, ci_p, co_p, S=1, dtype=None: pack(w, kind, ci_p, co_p, S, torch.float64))
+
+    def get(self, key, shape):
+        t = self.bufs.get(key)
+        if t is None or tuple(t.shape) != tuple(shape):
+            t = self.bufs[key] = torch.zeros(tuple(shape), dtype=torch.float64)
+        return t
+    monkeypatch.setattr(train._Pool, "get", get)
+    yield train
+    fake_ops.set_exact(False)
+
+
+@pytest.mark.parametrize("use_meta", [False, True], ids=["nometa", "meta"])
+def test_train_graph_tape_equals_autograd_without_rounding(exact_train, use_meta):
+    """Every activation, every data gradient and all 279 parameter gradients of the tape against torch autograd on the
+    restatement, in float64: a wrong weight layout, tap order, phase grouping or residual routing gives O(1) errors;
+    what remains is fp32 rounding of the gradient buffers."""
+    from oracle import dla_train_ref
+    P, data, coord, d_cls, d_reg = _case(use_meta, B=2, H=8, W=64)
+    P = {k: v.double() for k, v in P.items()}
+    data, coord = data.double(), coord.double()
+    d_cls, d_reg = [d.double() for d in d_cls], [d.double() for d in d_reg]
+    tg = exact_train.TrainGraph({k: v.clone() for k, v in P.items()}, device="cpu", use_meta=use_meta)
+    cls, reg = tg.forward(data, coord)
+    grads = tg.backward(d_cls, d_reg)
+    rc, rr, rg = dla_train_ref.TrainRef(P, bf16=False, use_meta=use_meta).forward_backward(data, coord, d_cls, d_reg)
+    for a, b in zip(cls + reg, rc + rr):
+        assert _rms(a, b) < 1e-9
+    used = [k for k in rg if float(rg[k].abs().max()) > 0]
+    assert set(used) <= set(grads) and len(used) > 250
+    errs = {k: _rms(grads[k].reshape(rg[k].shape), rg[k]) for k in used}
+    assert max(errs.values()) < 1e-5, sorted(errs.items(), key=lambda kv: -kv[1])[:5]
+    k = "res2_unit1_bn1_moving_var"          # moving statistics follow MXNet's update
+    assert not torch.equal(tg.P[k], P[k])
+
+
+@pytest.mark.parametrize("use_meta", [False, True], ids=["nometa", "meta"])
+def test_train_graph_tape_with_bf16_storage_stays_within_the_noise_floor(cpu_train, use_meta):
+    """Kernel-like storage (bf16 activations / gradients): at random initialisation the 40-layer BN + ReLU graph is
+    chaotic on small images, so the bound is the restatement's own sensitivity to 2e-3 rounding-level jitter."""
+    from oracle import dla_train_ref
+    P, data, coord, d_cls, d_reg = _case(use_meta, B=2, H=8, W=64)
+    tg = cpu_train.TrainGraph({k: v.clone() for k, v in P.items()}, device="cpu", use_meta=use_meta)
+    cls, reg = tg.forward(data, coord)
+    grads = tg.backward(d_cls, d_reg)
+    rc, rr, rg = dla_train_ref.TrainRef(P, bf16=True, use_meta=use_meta).forward_backward(data, coord, d_cls, d_reg)
+    jc, jr, jg = dla_train_ref.TrainRef(P, bf16=True, use_meta=use_meta, jitter=2e-3).forward_backward(data, coord, d_cls, d_reg)
+    assert max(_rms(a, b) for a, b in zip(cls + reg, rc + rr)) < max(_rms(a, b) for a, b in zip(jc + jr, rc + rr))
+    used = [k for k in rg if float(rg[k].abs().max()) > 0]
+    e = np.median([_rms(grads[k].reshape(rg[k].shape), rg[k]) for k in used])
+    floor = np.median([_rms(jg[k], rg[k]) for k in used])
+    assert e < floor, (e, floor)
+
+
+def test_flat_mode_gathers_reproduce_the_per_tensor_path(cpu_train):
+    P, data, coord, d_cls, d_reg = _case(True)
+    names = sorted(k for k in P if not k.endswith(("_moving_mean", "_moving_var")))
+    # eager reference
+    tg0 = cpu_train.TrainGraph({k: v.clone() for k, v in P.items()}, device="cpu")
+    tg0.forward(data, coord)
+    g0 = {k: v.clone() for k, v in tg0.backward(d_cls, d_reg).items()}
+    packed0 = {k: v.clone() for k, v in tg0.packed.items()}
+    # flat parameters / gradients like GraphedTrainStep builds them
+    Pf = {k: v.clone() for k, v in P.items()}
+    sizes = [Pf[k].numel() for k in names]
+    flatP, flat_g = torch.empty(sum(sizes)), torch.zeros(sum(sizes))
+    offsets, o = {}, 0
+    for k, n in zip(names, sizes):
+        offsets[k] = o
+        flatP[o:o + n] = Pf[k].reshape(-1)
+        Pf[k] = flatP[o:o + n].view(Pf[k].shape)
+        o += n
+    tg = cpu_train.TrainGraph(Pf, device="cpu")
+
+    def run_step():
+        tg.refresh()
+        tg.forward(data, coord)
+        tg.backward(d_cls, d_reg)
+
+    run_step()
+    tg.enable_flat(flatP, offsets, flat_g, run_step)
+    assert tg.no_grad_params == sorted(k for k in names if k.startswith("res1_unit2_conv1") or k.startswith("res1_unit2_bn1"))
+    run_step()                                                 # flat mode: one gather in, one gather out
+    for key, want in packed0.items():                          # every bf16 operand re-packed by the gather
+        assert torch.equal(tg.packed[key], want), key
+    for k in names:
+        want = g0[k].reshape(-1) if k in g0 else torch.zeros(Pf[k].numel())
+        assert torch.equal(flat_g[offsets[k]:offsets[k] + Pf[k].numel()], want), k
+    # the optimiser restatement on the flat buffers == per-tensor MXNet SGD
+    wd = torch.cat([torch.full((Pf[k].numel(),), 1e-5 * train.wd_mult(k)) for k in names])
+    mom = torch.zeros_like(flatP)
+    before = {k: Pf[k].clone() for k in names}
+    fake_ops.sgd_mom_update(flatP, flat_g, mom, wd, torch.tensor([0.05, 0.9, 1 / 128, 35.0]))
+    Ps, ms = {k: before[k].clone() for k in names}, {}
+    train.sgd_momentum_step(Ps, {k: g0.get(k, torch.zeros_like(before[k])) for k in names}, ms, lr=0.05, wd=1e-5,
+                            clip_gradient=35.0, rescale_grad=1 / 128)
+    for k in names:
+        assert torch.allclose(Pf[k], Ps[k], rtol=1e-6, atol=1e-7), k
