@@ -607,7 +607,7 @@ class GraphedTrainStep(object):
 
     def __init__(self, params, batch, H, W, lr, momentum=0.9, wd=1e-5, clip_gradient=35.0, rescale_grad=1.0 / 128.0,
                  device="cuda", use_meta=True, allreduce=None, world_size=1, with_loss=True, overlap_wgrad=True,
-                 loss_hyper=None, gt_name="gt_bbox_veh_for_iou_pred"):
+                 loss_hyper=None, gt_name="gt_bbox_veh_for_iou_pred", capture=True):
         self.P = params
         self.allreduce = allreduce
         self.with_loss = with_loss
@@ -633,7 +633,8 @@ class GraphedTrainStep(object):
         self.hyper = torch.tensor([lr, momentum, rescale_grad / world_size, clip_gradient if clip_gradient else 0.0],
                                   device=device)
         self.tg = TrainGraph(params, device, use_meta)
-        if overlap_wgrad:
+        self.capture = capture    # False: same buffers and flat plumbing, kernels launched eagerly (debugging)
+        if overlap_wgrad and capture:
             self.tg.side = torch.cuda.Stream(device=device)
         self.data = torch.zeros((batch, 8, H, W), device=device)
         self.coord = torch.zeros((batch, 3, H, W), device=device)
@@ -660,15 +661,24 @@ class GraphedTrainStep(object):
         # (2) inside enable_flat: builds the gather maps, (3) flat mode warm-up.  lr = 0 leaves the weights alone.
         lr_saved = self.hyper.clone()
         self.hyper[0] = 0.0
-        s = torch.cuda.Stream()
-        s.wait_stream(torch.cuda.current_stream())
-        with torch.cuda.stream(s):
+
+        def warm():
             self._fwd()
             self._bwd()
             self.tg.enable_flat(self.flatP, self.offsets, self.flat, lambda: (self._fwd(), self._bwd()))
             self._fwd()
             self._bwd()
             self._update()
+
+        if not capture:
+            warm()
+            self.hyper.copy_(lr_saved)
+            self.flat_m.zero_()
+            return
+        s = torch.cuda.Stream()
+        s.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(s):
+            warm()
         torch.cuda.current_stream().wait_stream(s)
         torch.cuda.synchronize()
         self.hyper.copy_(lr_saved)
@@ -715,17 +725,26 @@ class GraphedTrainStep(object):
     def forward(self, data, coord):
         self.data.copy_(data, non_blocking=True)
         self.coord.copy_(coord, non_blocking=True)
-        self.g_fwd.replay()
+        if self.capture:
+            self.g_fwd.replay()
+        else:
+            self._fwd()
         return self.out
 
     def backward_update(self, d_cls=None, d_reg=None):
         if not self.with_loss:
             for dst, src in zip(self.d_cls + self.d_reg, list(d_cls) + list(d_reg)):
                 dst.copy_(src, non_blocking=True)
-        self.g_bwd.replay()
+        if self.capture:
+            self.g_bwd.replay()
+        else:
+            self._bwd()
         if self.allreduce is not None:
             self.allreduce(self.flat)
-        self.g_upd.replay()
+        if self.capture:
+            self.g_upd.replay()
+        else:
+            self._update()
 
     def train_step(self, data, coord):
         """One iteration of tools/train.py's fit loop on the device: forward, loss, backward, all-reduce, SGD."""

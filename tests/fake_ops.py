@@ -226,3 +226,20 @@ def sgd_mom_update(weight, grad, mom, wd, hyper):
     g = g + wd * weight
     mom.mul_(momentum).add_(g, alpha=-lr)
     weight.add_(mom)
+
+
+def rpn_loss(cls_logit, reg_delta, pc, gt_bbox, mask, reg_target, reg_weight, reg_norm_weight, iou_type="bev", alpha=1.0,
+             gamma=2.0, smooth_l1_scalar=3.0, scale_loss_shift=128.0, cls_loss_weight=10.0, reg_loss_weight=8.0,
+             want_loss=True, out=None):
+    """The fused loss head through its torch restatement (oracle/loss_ref.py), writing into the caller's buffers."""
+    from oracle import loss_ref
+    r = loss_ref.rpn_loss_level(cls_logit.float(), reg_delta.float(), pc.numpy(), gt_bbox.numpy(), mask.float(), reg_target.float(),
+                                reg_weight.float(), reg_norm_weight.float(), iou_type=iou_type, alpha=alpha, gamma=gamma,
+                                smooth_l1_scalar=smooth_l1_scalar, scale_loss_shift=scale_loss_shift,
+                                cls_loss_weight=cls_loss_weight, reg_loss_weight=reg_loss_weight)
+    if out is None:
+        return r
+    for k, v in r.items():
+        if out.get(k) is not None:
+            out[k].copy_(v.reshape(out[k].shape))
+    return out

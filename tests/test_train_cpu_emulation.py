@@ -141,3 +141,34 @@ def test_flat_mode_gathers_reproduce_the_per_tensor_path(cpu_train):
                             clip_gradient=35.0, rescale_grad=1 / 128)
     for k in names:
         assert torch.allclose(Pf[k], Ps[k], rtol=1e-6, atol=1e-7), k
+
+
+def test_whole_training_iteration_on_cpu(cpu_train):
+    """GraphedTrainStep(capture=False): same flat buffers, gather maps, loss hand-off and optimiser call as the captured
+    step, launched eagerly -- forward, fused-loss restatement, backward, SGD on the emulated kernels."""
+    from oracle import dla_ref
+    B, H, W = 1, 8, 64
+    P = dla_ref.make_params(seed=0, device="cpu")
+    step = cpu_train.GraphedTrainStep(P, B, H, W, lr=0.05, device="cpu", capture=False, overlap_wgrad=False)
+    T = synth.rpn_targets(B, seed=7, n_vehicles=6, h=H, w=W - 6, w_pad=W)
+    step.set_targets(T)
+    g = torch.Generator().manual_seed(4)
+    data = torch.randn(B, 8, H, W, generator=g)
+    xyz = torch.from_numpy(T["pc_vehicle_frame_s1"]).reshape(B, H, W, 3).permute(0, 3, 1, 2).contiguous()
+    coord = xyz / torch.tensor([25.0, 25.0, 2.0]).view(1, 3, 1, 1)
+    before = step.flatP.clone()
+    hist = []
+    for it in range(5):
+        out = step.train_step(data, coord)
+        hist.append(sum(float(o["reg_loss"].sum()) for o in out))
+        assert np.isfinite(hist[-1]) and bool(torch.isfinite(step.flatP).all())
+        if it == 0:
+            dead = [k for k in step.names if float(step.gviews[k].abs().max()) == 0.0 and k not in step.tg.no_grad_params]
+            assert not dead, dead[:5]
+    assert min(hist[2:]) < hist[0], hist                    # the regression loss goes down
+    assert float((step.flatP - before).abs().max()) > 1e-4
+    assert all(P[k].data_ptr() >= step.flatP.data_ptr() for k in step.names)   # masters live in the flat buffer
+    step.set_lr(0.0)
+    w = step.flatP.clone()
+    step.train_step(data, coord)
+    assert torch.equal(step.flatP, w + step.flat_m)          # lr = 0: pure momentum step
