@@ -10,7 +10,8 @@ bf16-rounded operands and rounds its bf16 outputs once, like the kernels.  The p
 import torch
 import torch.nn.functional as F
 
-from rangedet_b200.ops import (BN_EPS, BN_MOMENTUM, pack_conv_weight, pack_deconv_weight, tap_major_weight)  # noqa: F401  (pure torch)
+from rangedet_b200.ops import (BN_EPS, BN_MOMENTUM, IMPL_DEFAULT, from_nhwc_padded, pack_conv_weight, pack_deconv_weight,  # noqa: F401
+                               tap_major_weight, to_nhwc_padded)  # (pure torch helpers of the real module)
 
 bf16 = torch.bfloat16
 COMPUTE = torch.float32      # arithmetic type of the emulated kernels

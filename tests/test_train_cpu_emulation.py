@@ -172,3 +172,28 @@ def test_whole_training_iteration_on_cpu(cpu_train):
     w = step.flatP.clone()
     step.train_step(data, coord)
     assert torch.equal(step.flatP, w + step.flat_m)          # lr = 0: pure momentum step
+
+
+def test_inference_graph_host_logic_on_cpu(monkeypatch):
+    """rangedet_b200.dla (folded moving statistics, fused Meta-Kernel unit with tap-major aggregation weights, deconv
+    skip connections, head) over the emulated kernels vs the restatement oracle/dla_ref.py with the same bf16 storage."""
+    from oracle import dla_ref
+    from rangedet_b200 import dla
+    monkeypatch.setattr(dla, "ops", fake_ops)
+    P = dla_ref.make_params(seed=0, device="cpu")
+    g = torch.Generator().manual_seed(2)
+    for k in P:                                    # non-trivial statistics so that the folding matters
+        if k.endswith("_moving_mean"):
+            P[k] = 0.1 * torch.randn(P[k].shape, generator=g)
+        elif k.endswith("_moving_var"):
+            P[k] = 1 + 0.3 * torch.rand(P[k].shape, generator=g)
+        elif k.endswith("_gamma"):
+            P[k] = 1 + 0.2 * torch.randn(P[k].shape, generator=g)
+    B, H, W = 1, 8, 64
+    data = torch.randn(B, 8, H, W, generator=g)
+    coord = torch.from_numpy(synth.range_image_coords(B, seed=0, h=H, w=W - 2, w_pad=W))
+    cls, reg = dla.RangeRpnHead(P, "cpu").get_fpn_output(dla.DLABackbone(P, "cpu").get_rpn_feature(data, coord))
+    ref = dla_ref.Ref(P, bf16=True)
+    rc, rr = ref.head(ref.backbone(data, coord))
+    for a, b in zip(cls + reg, rc + rr):
+        assert a.shape == b.shape and _rms(a, b) < 3e-2, _rms(a, b)
