@@ -149,7 +149,8 @@ class TrainGraph(object):
         # -- operands: push element indices through the same packing functions
         keys = sorted(self.pack_rec)
         sizes = [_align(self.packed[k].numel(), 128) for k in keys]
-        self.packed_flat = torch.zeros(sum(sizes), device=dev, dtype=torch.bfloat16)
+        op_dtype = self.packed[keys[0]].dtype if keys else torch.bfloat16     # bf16 (the kernels' operand type)
+        self.packed_flat = torch.zeros(sum(sizes), device=dev, dtype=op_dtype)
         self.pmap = torch.full((sum(sizes),), -1, device=dev, dtype=torch.int32)
         o, views = 0, {}
         for k, n in zip(keys, sizes):
