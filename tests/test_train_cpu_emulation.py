@@ -197,3 +197,64 @@ def test_inference_graph_host_logic_on_cpu(monkeypatch):
     rc, rr = ref.head(ref.backbone(data, coord))
     for a, b in zip(cls + reg, rc + rr):
         assert a.shape == b.shape and _rms(a, b) < 3e-2, _rms(a, b)
+
+
+def test_inference_executor_equals_reference_graph_without_rounding(monkeypatch):
+    """Forward (rangedet_b200.dla, folded moving statistics) + symbol._TestExecutor.predict over the emulated kernels
+    in float64, against the reference's OWN inference graph executed eagerly (DLABackbone + get_fpn_output +
+    get_fpn_prediction through oracle/mx_eager.py).  Skipped where /root/reference is absent."""
+    from oracle import dla_ref, mx_eager, ref_graph
+    if not mx_eager.available():
+        pytest.skip("/root/reference not present")
+    from rangedet_b200 import dla, symbol
+    from test_symbol import shipped_config
+    fake_ops.set_exact(True)
+    try:
+        monkeypatch.setattr(dla, "ops", fake_ops)
+        monkeypatch.setattr(symbol, "ops", fake_ops)
+        pk_c, pk_d = fake_ops.pack_conv_weight, fake_ops.pack_deconv_weight
+        monkeypatch.setattr(fake_ops, "pack_conv_weight", lambda w, cin=None, cout=None, dtype=None: pk_c(w, cin, cout, torch.float64))
+        monkeypatch.setattr(fake_ops, "pack_deconv_weight", lambda w, cin=None, cout=None, dtype=None: pk_d(w, cin, cout, torch.float64))
+
+        def get(self, key, shape, device):
+            t = self.bufs.get(key)
+            if t is None or tuple(t.shape) != tuple(shape):
+                t = self.bufs[key] = torch.zeros(tuple(shape), dtype=torch.float64)
+            return t
+        monkeypatch.setattr(dla._BufferPool, "get", get)
+
+        def to_pad(x, channels=None):
+            N, C, H, W = x.shape
+            out = torch.zeros((N, H + 2, W + 2, channels or C), dtype=torch.float64)
+            out[:, 1:H + 1, 1:W + 1, :C] = x.permute(0, 2, 3, 1)
+            return out
+        monkeypatch.setattr(fake_ops, "to_nhwc_padded", to_pad)
+        monkeypatch.setattr(fake_ops, "from_nhwc_padded",
+                            lambda y, channels=None: (y[:, 1:-1, 1:-1, :channels] if channels else y[:, 1:-1, 1:-1]).permute(0, 3, 1, 2).contiguous())
+        B, H, W = 1, 16, 64
+        P = dla_ref.make_params(seed=0, device="cpu")
+        g = torch.Generator().manual_seed(3)
+        data = torch.randn(B, 8, H, W, generator=g)
+        T = synth.rpn_targets(B, seed=3, n_vehicles=5, h=H, w=W - 2, w_pad=W)
+        xyz = torch.from_numpy(T["pc_vehicle_frame_s1"]).reshape(B, H, W, 3).permute(0, 3, 1, 2).contiguous()
+        coord = xyz / torch.tensor([25.0, 25.0, 2.0]).view(1, 3, 1, 1)
+        P.update(ref_graph.backbone_head(P, data, coord, training=True, bn_momentum=0.0)["moving"])   # "trained" statistics
+        P64 = {k: v.double() for k, v in P.items()}
+        pB, pR, _ = shipped_config(False, (H, W))
+        ex = symbol._TestExecutor.__new__(symbol._TestExecutor)
+        ex.sym = symbol.RangeRCNN(pR).get_test_symbol(symbol.DLABackbone(pB), symbol.RangeRpnHead(pR))
+        ex.pre_n, ex.post_n, ex.nms_thr, ex.wnms = 300, 200, 0.2, True
+        cls, reg = dla.RangeRpnHead(P64, "cpu").get_fpn_output(dla.DLABackbone(P64, "cpu").get_rpn_feature(data.double(), coord.double()))
+        record = {k: torch.from_numpy(v) for k, v in T.items()}
+        score, boxes, _ = ex.predict(cls, reg, record)
+        r = ref_graph.backbone_head(P64, data.double(), coord.double(), training=False)
+        for a, b in zip(cls + reg, r["cls"] + r["reg"]):
+            assert _rms(a, b) < 1e-5            # folded scale / shift are fp32 in dla._Layer
+        sc_r, box_r = ref_graph.fpn_prediction([c.float() for c in r["cls"]], [d.float() for d in r["reg"]],
+                                               [T["pc_vehicle_frame_s%d" % s] for s in (1, 2, 4)],
+                                               [T["range_image_mask_s%d" % s].reshape(B, -1) for s in (1, 2, 4)], 300)
+        assert float((score - sc_r).abs().max()) < 1e-5
+        d = torch.cdist(boxes[0].double(), box_r[0].double(), p=float("inf")).min(1).values     # near-ties may swap ranks
+        assert float(d.max()) < 1e-2 and int(((boxes - box_r).abs().amax(-1) > 1e-2).sum()) < 15
+    finally:
+        fake_ops.set_exact(False)
