@@ -195,6 +195,9 @@ def train_step_leg(args, rank, world, dev, B=TRAIN_B):
         dist.barrier()
     torch.cuda.synchronize()
     n = max(5, min(args.steps, 20))
+    sampler = ClockSampler(dev.index if dev.index is not None else 0) if rank == 0 else None   # this region is long enough
+    if sampler is not None:                                                                     # for ~10 nvidia-smi samples
+        sampler.start()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(n):
@@ -209,7 +212,8 @@ def train_step_leg(args, rank, world, dev, B=TRAIN_B):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms = float(t.item())
     loss = step.loss_out
-    res = {"workload": "rangedet_veh_wo_aug_4_18e train step on synthetic roidb: backbone + Meta-Kernel unit + head fwd, "
+    clocks = sampler.finish() if sampler is not None else None
+    res = {"clocks": clocks, "workload": "rangedet_veh_wo_aug_4_18e train step on synthetic roidb: backbone + Meta-Kernel unit + head fwd, "
                        "RPN loss, bwd, all-reduce, SGD; B=%d/GPU, 64x2656, bf16 operands / fp32 accumulate, training-mode BN" % B,
            "value": B * world * n / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms / n, "steps": n, "batch_per_gpu": B,
            "parameters": int(nparam), "allreduce_bytes": int(step.flat.numel() * 4) if world > 1 else 0,
