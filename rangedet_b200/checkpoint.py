@@ -53,13 +53,15 @@ def nd_load(path):
         if stype != 0:
             raise ValueError("%s: sparse storage type %d is not supported" % (path, stype))
         ndim = rd("I") if m == V2_MAGIC else rd("i")
+        # NDArray::Save writes the shape and returns when is_none(): an unknown shape is ndim 0 in the legacy (v2)
+        # convention and ndim -1 under np_shape (v3, where ndim 0 is a genuine scalar holding one element)
+        if (m == V2_MAGIC and ndim == 0) or (m == V3_MAGIC and ndim == -1):
+            arrays.append(np.zeros((0,), np.float32))
+            continue
         if ndim < 0 or ndim > 32:
             raise ValueError("%s: bad ndim %d" % (path, ndim))
         shape = tuple(struct.unpack_from("<%dq" % ndim, buf, off)) if ndim else ()
         off += 8 * ndim
-        if ndim == 0 and m == V2_MAGIC:   # v2: ndim 0 marks an empty array, nothing else follows
-            arrays.append(np.zeros((0,), np.float32))
-            continue
         rd("ii")   # context (dev_type, dev_id): ignored, the caller chooses the device
         flag = rd("i")
         if flag not in DTYPES:

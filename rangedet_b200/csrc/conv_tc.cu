@@ -581,12 +581,8 @@ static int run(int mode, const void* x_pad, const void* w_packed, const float* s
   int dev = 0, sms = 0;
   RD_CUDA(cudaGetDevice(&dev));
   RD_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-  static size_t smem_set = 0;
-  if (smem > smem_set) {
-    RD_CUDA(cudaFuncSetAttribute(conv_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    RD_CUDA(cudaFuncSetAttribute(conv_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    smem_set = smem;
-  }
+  RD_CUDA(rd::smem_optin(conv_kernel<false>, smem));
+  RD_CUDA(rd::smem_optin(conv_kernel<true>, smem));
   const int nsuper = (P.ntiles + P.npipes - 1) / P.npipes;
   const int grid = nsuper < sms ? nsuper : sms;
   static const bool prof = [] { const char* e = getenv("RD_CONV_PROF"); return e && e[0] == '1'; }();

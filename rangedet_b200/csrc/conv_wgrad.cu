@@ -284,11 +284,7 @@ int rd_conv2d_wgrad_nhwc_bf16(const void* a_pad, const void* b_pad, float* g, in
   }
   const size_t smem = (size_t)P.nstages * P.stage_bytes + sizeof(wg::Misc) + 1024;
   RD_REQUIRE(smem <= 227 * 1024, "rd_conv2d_wgrad: shared memory layout exceeds 227 KB (%zu)", smem);
-  static size_t smem_set = 0;
-  if (smem > smem_set) {
-    RD_CUDA(cudaFuncSetAttribute(wg::wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    smem_set = smem;
-  }
+  RD_CUDA(rd::smem_optin(wg::wgrad_kernel, smem));
   float* partial = static_cast<float*>(workspace);
   wg::wgrad_kernel<<<P.njobs * P.nsplit, wg::NTHREADS, smem, s>>>(tm_a, tm_b, partial, P);
   const int n4 = P.ntaps * CA * CB / 4;

@@ -503,15 +503,11 @@ inline int launch(int mode, const float* tap_src, void* dst, const float* coord,
     RD_CUDA(cudaMemsetAsync(buf, 0, 1024 * 16 * sizeof(long long), stream));
     d_prof = buf;
   }
-  static bool attr = false;
-  if (!attr) {
-    RD_CUDA(cudaFuncSetAttribute(meta_ws_kernel<0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    RD_CUDA(cudaFuncSetAttribute(meta_ws_kernel<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    RD_CUDA(cudaFuncSetAttribute(meta_ws_kernel<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    RD_CUDA(cudaFuncSetAttribute(meta_ws_kernel<0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    RD_CUDA(cudaFuncSetAttribute(meta_ws_kernel<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr = true;
-  }
+  RD_CUDA(rd::smem_optin(meta_ws_kernel<0, false>, smem));
+  RD_CUDA(rd::smem_optin(meta_ws_kernel<1, false>, smem));
+  RD_CUDA(rd::smem_optin(meta_ws_kernel<2, false>, smem));
+  RD_CUDA(rd::smem_optin(meta_ws_kernel<0, true>, smem));
+  RD_CUDA(rd::smem_optin(meta_ws_kernel<1, true>, smem));
 #define RD_MKWS_LAUNCH(M, PR, SC, SH, RELU)                                                                              \
   meta_ws_kernel<M, PR><<<(unsigned)grid, NTHREADS, smem, stream>>>(tm_in, tm_out, coord, w0, b0, w1, b1, SC, SH, RELU, B, H, \
                                                                     W, tiles_w, (int)ntiles, d_prof)

@@ -453,12 +453,8 @@ int rd_meta_kernel_bwd_params_ws(const float* grad_out, const float* data, const
   RD_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
   const size_t smem = sizeof(Smem) + 1024;
   const int64_t grid = ntiles < sms ? ntiles : sms;
-  static bool attr = false;
-  if (!attr) {
-    RD_CUDA(cudaFuncSetAttribute(meta_ws_params_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    RD_CUDA(cudaFuncSetAttribute(meta_ws_params_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr = true;
-  }
+  RD_CUDA(rd::smem_optin(meta_ws_params_kernel<false>, smem));
+  RD_CUDA(rd::smem_optin(meta_ws_params_kernel<true>, smem));
   static const bool want_prof = [] { const char* e = getenv("RD_MK_PROF"); return e && e[0] == '1'; }();
   long long* d_prof = nullptr;
   if (want_prof) {

@@ -241,11 +241,7 @@ int rd_nms3d(const float* boxes, int B, int N, float iou_thres, int max_keep, in
   float4* aabb = static_cast<float4*>(workspace);
   const int64_t total = (int64_t)B * N;
   n3::prep_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(boxes, total, aabb);
-  static size_t smem_set = 0;
-  if (bitmap_bytes > smem_set) {
-    RD_CUDA(cudaFuncSetAttribute(n3::nms3d_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bitmap_bytes));
-    smem_set = bitmap_bytes;
-  }
+  RD_CUDA(rd::smem_optin(n3::nms3d_kernel, bitmap_bytes));   // per (kernel, device), see rd_common.cuh
   n3::nms3d_kernel<<<B, n3::NT, bitmap_bytes, st>>>(boxes, aabb, N, iou_thres, max_keep, normal_iou ? 1 : 0, keep_idx,
                                                     boxes_out);
   rd::count_launch(2);

@@ -578,13 +578,19 @@ def deconv2d_nhwc(x_pad, w_packed, scale=None, shift=None, relu=False, residual_
 # Training path: weight gradient, training-mode BatchNorm + ReLU + residual (forward / backward)
 # ------------------------------------------------------------------------------------------------
 _WS = {}
+_WS_RETIRED = []   # outgrown buffers stay allocated: a captured CUDA graph may have their address baked in
 
 
 def _workspace(nbytes, device, tag="ws"):
-    """Grow-only scratch buffer per (device, tag); the C-ABI never allocates."""
+    """Grow-only scratch buffer per (device, tag); the C-ABI never allocates.  A buffer that is outgrown is
+    retired, not freed: graphs captured while it was current (train.GraphedTrainStep, dla.GraphedForward) keep
+    replaying through its address, so returning it to the caching allocator would let them scribble over
+    someone else's memory."""
     key = (str(device), tag)
     t = _WS.get(key)
     if t is None or t.numel() < nbytes:
+        if t is not None:
+            _WS_RETIRED.append(t)
         t = torch.empty(max(int(nbytes), 1 << 20), device=device, dtype=torch.uint8)
         _WS[key] = t
     return t

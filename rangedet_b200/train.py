@@ -662,6 +662,13 @@ class GraphedTrainStep(object):
         # (2) inside enable_flat: builds the gather maps, (3) flat mode warm-up.  lr = 0 leaves the weights alone.
         lr_saved = self.hyper.clone()
         self.hyper[0] = 0.0
+        # the warm-up passes run on all-zero inputs: keep them out of the BatchNorm moving statistics (a checkpoint's
+        # values must survive bind(); MXNet's executor has no such passes)
+        aux_saved = {k: v.clone() for k, v in params.items() if k.endswith(("_moving_mean", "_moving_var"))}
+
+        def restore_aux():
+            for k, v in aux_saved.items():
+                params[k].copy_(v)
 
         def warm():
             self._fwd()
@@ -675,6 +682,7 @@ class GraphedTrainStep(object):
             warm()
             self.hyper.copy_(lr_saved)
             self.flat_m.zero_()
+            restore_aux()
             return
         s = torch.cuda.Stream()
         s.wait_stream(torch.cuda.current_stream())
@@ -695,6 +703,7 @@ class GraphedTrainStep(object):
             self._bwd()
         with torch.cuda.graph(self.g_upd, pool=self.pool, **mode):
             self._update()
+        restore_aux()   # capture executes nothing: this undoes the eager warm-up passes
 
     def _fwd(self):
         self.tg.refresh()

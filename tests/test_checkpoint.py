@@ -57,3 +57,26 @@ def test_model_round_trip(tmp_path):
     assert sorted(Q) == sorted(P)
     for k in P:
         assert np.array_equal(Q[k].numpy(), P[k].numpy()), k
+
+
+def test_v3_none_and_scalar_arrays(tmp_path):
+    """np_shape (v3) files: NDArray::Save writes the shape and returns for a none array, which v3 marks with
+    ndim -1; ndim 0 is a real scalar there (one element follows).  In v2 ndim 0 is the none marker."""
+    s = np.array(2.5, np.float32)
+    v = np.array([7, 8], np.int64)
+    raw = struct.pack("<QQQ", 0x112, 0, 4)
+    raw += struct.pack("<Iii", 0xF993FACA, 0, -1)                                                     # v3 none
+    raw += struct.pack("<Iii", 0xF993FACA, 0, 0) + struct.pack("<iii", 1, 0, 0) + s.tobytes()         # v3 scalar
+    raw += struct.pack("<IiI", 0xF993FAC9, 0, 0)                                                      # v2 none
+    raw += struct.pack("<Iii1q", 0xF993FACA, 0, 1, 2) + struct.pack("<iii", 1, 0, 6) + v.tobytes()    # v3 int64 vector
+    raw += struct.pack("<Q", 0)
+    p = tmp_path / "n.params"
+    p.write_bytes(raw)
+    out = ck.nd_load(str(p))
+    assert len(out) == 4 and out[0].size == 0 and out[2].size == 0
+    assert out[1].shape == () and float(out[1]) == 2.5
+    assert np.array_equal(out[3], v)
+    bad = struct.pack("<QQQ", 0x112, 0, 1) + struct.pack("<Iii", 0xF993FACA, 0, -2)
+    (tmp_path / "bad.params").write_bytes(bad)
+    with pytest.raises(ValueError):
+        ck.nd_load(str(tmp_path / "bad.params"))
