@@ -33,6 +33,17 @@ def _need(cond, what):
         raise NotImplementedError("rangedet_b200.symbol: unsupported configuration: " + what)
 
 
+def _check_normalizer(norm, what):
+    """The layer kernels implement per-GPU BatchNorm with batch statistics (config:56 normalizer_factory(type="local"),
+    mxnext/complicate.py:26-44): eps 1e-5 + 1e-10, momentum 0.9.  A declarative spec from rangedet_b200.shim is
+    checked; a foreign callable (a real mxnext closure) cannot be inspected and is taken as the shipped local BN."""
+    from .shim.mxnext_complicate import Normalizer
+    if isinstance(norm, Normalizer):
+        _need(norm.type in ("local", "localbn"), "%s type %r (only per-GPU 'local' BatchNorm)" % (what, norm.type))
+        _need(abs(norm.eps - ops.BN_EPS) < 1e-12 and abs(norm.mom - ops.BN_MOMENTUM) < 1e-12,
+              "%s eps / momentum %r / %r (kernels: %r / %r)" % (what, norm.eps, norm.mom, ops.BN_EPS, ops.BN_MOMENTUM))
+
+
 class DLABackbone(object):
     """dla_backbone.py:164-175.  Validates BackboneParam against the stage layout the kernels implement."""
 
@@ -49,6 +60,7 @@ class DLABackbone(object):
             _need(u.get("meta_func_param") == "meta_baseline_bias", "%s.meta_func_param %r" % (name, u.get("meta_func_param")))
             _need(u.get("data_channels") == 64 and u.get("coord_channels") == 3 and list(u.get("channel_list")) == [32, 64]
                   and u.get("kernel_size", 3) == 3 and u.get("stride", 1) == 1, "%s: %r" % (name, u))
+        _check_normalizer(getattr(p, "normalizer", None), "BackboneParam.normalizer")
         self.use_meta = bool(units)
         self.batch_image = int(p.batch_image)
         self.range_image_shape_hw = tuple(p.range_image_shape_hw)
@@ -80,6 +92,7 @@ class RangeRpnHead(object):
               "RpnParam.head must be 4 x 128-channel cls and reg convs")
         _need(not getattr(p.loss, "l1", False), "RpnParam.loss.l1 (plain L1 regression loss)")
         _need(p.loss.iou_type in ("bev", "3d"), "RpnParam.loss.iou_type %r" % (p.loss.iou_type,))
+        _check_normalizer(getattr(p, "normalizer", None), "RpnParam.normalizer")     # builder.py:212-213
 
     def loss_hyper(self):
         """Arguments of the fused loss head (builder.py:350-422, loss.py:4-30)."""

@@ -4,56 +4,29 @@ config/rangedet/rangedet_veh_wo_aug_4_18e.py is imported verbatim from /root/ref
   rangedet.symbol.head.builder       -> rangedet_b200.symbol (RangeRCNN, RangeRpnHead)
   rangedet.symbol.backbone.dla_backbone -> rangedet_b200.symbol (DLABackbone)
   processing_cxx                     -> rangedet_b200.processing_cxx
-and the rest of the reference (mxnext, rangedet.core.input, rangedet.core.detection_metric, utils) as is, over the
-MXNet stand-in of oracle/mx_eager.py (imports only: nothing MXNet-side is executed).  `get_config()` must return
+by the shim this package SHIPS (rangedet_b200/shim: install() / drop_in()), and the rest of the reference
+(rangedet.core.input, rangedet.core.detection_metric, utils) as is.  MXNet is absent here, so the shim also supplies the
+three host-side base classes those files subclass (shim/mxnet_host.py); nothing under oracle/ is imported.  `get_config()` must return
 our graph objects, and everything the config says about them -- metric output names, data / label names, the
 optimizer block -- must line up with what they expose.  Needs /root/reference: skipped elsewhere."""
 import contextlib
 import importlib
+import os
 import sys
 import types
 
 import pytest
 
-mx_eager = pytest.importorskip("oracle.mx_eager")
-pytestmark = pytest.mark.skipif(not mx_eager.available(), reason="/root/reference not present")
+REF = "/root/reference"
+pytestmark = pytest.mark.skipif(not os.path.isdir(os.path.join(REF, "config")), reason="/root/reference not present")
 
 
 @contextlib.contextmanager
-def drop_in():
-    from rangedet_b200 import processing_cxx, symbol
-    stubs = mx_eager._modules()
-    mx = stubs["mxnet"]
-
-    class EvalMetric(object):                      # mx.metric.EvalMetric: constructor signature only
-        def __init__(self, name, output_names=None, label_names=None, **kw):
-            self.name, self.output_names, self.label_names = name, output_names, label_names
-
-    mx.metric = types.SimpleNamespace(EvalMetric=EvalMetric)
-    mx.io = types.SimpleNamespace(DataIter=object, DataBatch=object, DataDesc=object)
-    builder = types.ModuleType("rangedet.symbol.head.builder")
-    builder.RangeRCNN, builder.RangeRpnHead = symbol.RangeRCNN, symbol.RangeRpnHead
-    backbone = types.ModuleType("rangedet.symbol.backbone.dla_backbone")
-    backbone.DLABackbone = symbol.DLABackbone
-    stubs.update({"processing_cxx": processing_cxx, "rangedet.symbol.head.builder": builder,
-                  "rangedet.symbol.backbone.dla_backbone": backbone})
-    pk = ("mxnext", "rangedet", "operator_py", "utils", "config")
-    saved = {k: sys.modules.get(k) for k in stubs}
-    for k in list(sys.modules):
-        if k.split(".")[0] in pk:
-            saved[k] = sys.modules.pop(k)
-    sys.modules.update(stubs)
-    sys.path.insert(0, mx_eager.REF)
-    try:
+def drop_in(processing_cxx=None):
+    """The SHIPPED shim (rangedet_b200/shim): no test-side patching, nothing from oracle/."""
+    from rangedet_b200 import shim
+    with shim.drop_in(REF, processing_cxx=processing_cxx):
         yield
-    finally:
-        sys.path.remove(mx_eager.REF)
-        for k in list(sys.modules):
-            if k.split(".")[0] in pk or k in stubs:
-                sys.modules.pop(k, None)
-        for k, v in saved.items():
-            if v is not None:
-                sys.modules[k] = v
 
 
 @pytest.mark.parametrize("name", ["rangedet_veh_wo_aug_4_18e", "rangedet_veh_wo_aug_all_36e", "rangedet_ped_wo_aug_4_18e"])
@@ -91,7 +64,40 @@ def test_drop_in_context_restores_the_interpreter():
         importlib.import_module("mxnext.complicate")
         assert "mxnext" in sys.modules
     assert not [k for k in sys.modules if k.split(".")[0] in ("mxnext", "mxnet", "config", "utils")]
-    assert "processing_cxx" not in sys.modules and set(sys.modules) - before <= {k for k in sys.modules if k.startswith(("numba", "llvmlite", "rangedet_b200", "oracle"))} | (set(sys.modules) - before)
+    assert "processing_cxx" not in sys.modules
+
+
+def test_shim_is_product_code_and_needs_no_oracle():
+    """The drop-in lives in the package and resolves every module path the config imports without oracle/."""
+    import subprocess
+    code = ("import sys, importlib; import rangedet_b200.shim as shim; shim.install(%r); "
+            "cfg = importlib.import_module('config.rangedet.rangedet_veh_wo_aug_4_18e'); out = cfg.get_config(True); "
+            "from rangedet_b200 import symbol; assert isinstance(out[6].train_symbol, symbol.TrainSymbol); "
+            "assert not [m for m in sys.modules if m == 'oracle' or m.startswith('oracle.')], 'oracle imported'; "
+            "import rangedet.symbol.backbone.meta_kernel as mk; from rangedet_b200.meta_kernel import MetaKernel; "
+            "assert mk.MetaKernel is MetaKernel; print('ok')" % REF)
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, cwd=os.path.dirname(os.path.dirname(__file__)))
+    assert r.returncode == 0 and r.stdout.strip().endswith("ok"), r.stderr[-2000:]
+
+
+def test_shim_refuses_a_normalizer_the_kernels_do_not_implement():
+    from rangedet_b200 import symbol
+    from rangedet_b200.shim.mxnext_complicate import normalizer_factory
+    with drop_in():
+        cfg = importlib.import_module("config.rangedet.rangedet_veh_wo_aug_4_18e")
+        pBackbone_cls = None
+        out = cfg.get_config(is_train=True)
+        backbone = out[6].train_symbol.backbone
+        p = backbone.p
+        assert p.normalizer.type == "localbn"
+
+        class P2(p):
+            normalizer = normalizer_factory(type="syncbn", ndev=8)
+
+        with pytest.raises(NotImplementedError):
+            symbol.DLABackbone(P2)
+    with pytest.raises(KeyError):
+        normalizer_factory(type="nonsense")
 
 
 def _raw_record(tmp_path, seed=0):
@@ -126,11 +132,10 @@ def test_reference_loader_pipeline_output_fits_our_graph_inputs(tmp_path):
     import numpy as np
     from oracle import oracle
     orc = oracle()
-    with drop_in():
-        pcx = types.ModuleType("processing_cxx")
-        pcx.assign3D_v2 = lambda pc, bbox, ctr, rad, mask, nlz, *f: orc.assign3d_v2(pc, bbox, ctr, rad, mask, nlz, *f).reshape(-1, 1)
-        pcx.get_point_num = lambda inds: orc.get_point_num(inds).reshape(-1, 1)
-        sys.modules["processing_cxx"] = pcx
+    pcx = types.ModuleType("processing_cxx")
+    pcx.assign3D_v2 = lambda pc, bbox, ctr, rad, mask, nlz, *f: orc.assign3d_v2(pc, bbox, ctr, rad, mask, nlz, *f).reshape(-1, 1)
+    pcx.get_point_num = lambda inds: orc.get_point_num(inds).reshape(-1, 1)
+    with drop_in(processing_cxx=pcx):
         cfg = importlib.import_module("config.rangedet.rangedet_veh_wo_aug_4_18e")
         out = cfg.get_config(is_train=True)
         pModel, transform, data_name, label_name = out[6], out[9], out[10], out[11]
