@@ -720,6 +720,17 @@ class GraphedTrainStep(object):
     def _update(self):
         ops.sgd_mom_update(self.flatP, self.flat, self.flat_m, self.flat_wd, self.hyper)
 
+    def broadcast_parameters(self, src=0):
+        """tools/train.py:219-229: all ranks start from rank `src`'s arg + aux parameters (one flat broadcast of the
+        master buffer + one of the moving statistics).  Call after construction, before the first step."""
+        from . import dist as rd_dist
+        rd_dist.broadcast_params_(self.P, src=src, flat=self.flatP)
+
+    def average_aux(self):
+        """utils/detection_module.py:1164-1170: epoch-end average of the BatchNorm moving statistics over ranks."""
+        from . import dist as rd_dist
+        rd_dist.average_aux_(self.P)
+
     def set_lr(self, lr):
         """Learning-rate schedule: the captured update reads lr from device memory."""
         self.hyper[0:1].fill_(float(lr))

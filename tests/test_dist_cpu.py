@@ -116,3 +116,59 @@ def test_gloo_world2_whole_model_exchange_and_update():
     mp.spawn(_train_worker, args=(world, _free_port(), ret), nprocs=world, join=True)
     assert ret["ranks_agree"] and ret["n"] > 9_000_000
     assert ret["err"] < 1e-6 and ret["moved"] > 1e-4
+
+
+def _sync_worker(rank, world, port, ret):
+    """Start-up broadcast (tools/train.py:219-229) and epoch-end aux average (utils/detection_module.py:1164-1170)."""
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    g = torch.Generator().manual_seed(100 + rank)          # every rank initialises DIFFERENTLY
+    mk = lambda *s: torch.randn(*s, generator=g)
+    P = {"a_weight": mk(4, 3, 3, 3), "a_bn_gamma": mk(4), "a_bn_beta": mk(4), "a_bn_moving_mean": mk(4), "a_bn_moving_var": mk(4).abs(),
+         "b_weight": mk(2, 4, 1, 1), "b_bias": mk(2)}
+    mine = {k: v.clone() for k, v in P.items()}
+    # (1) generic path: every tensor staged through one flat buffer
+    rd_dist.broadcast_params_(P, src=0)
+    gathered = {}
+    for k in sorted(P):
+        both = [torch.zeros_like(P[k]) for _ in range(world)]
+        dist.all_gather(both, P[k])
+        gathered[k] = both
+    # (2) flat-master path: trainable parameters are views of one buffer (GraphedTrainStep layout)
+    names = sorted(k for k in mine if not k.endswith(("_moving_mean", "_moving_var")))
+    flat = torch.cat([mine[k].reshape(-1) for k in names])
+    Q, o = {}, 0
+    for k in names:
+        n = mine[k].numel()
+        Q[k] = flat[o:o + n].view(mine[k].shape)
+        o += n
+    for k in mine:
+        if k not in Q:
+            Q[k] = mine[k].clone()
+    rd_dist.broadcast_params_(Q, src=0, flat=flat)
+    same_as_generic = all(torch.equal(Q[k], P[k]) for k in P)
+    # (3) aux average: moving statistics drift apart per rank, then are averaged; trainable parameters untouched
+    P["a_bn_moving_mean"] += rank + 1.0
+    P["a_bn_moving_var"] *= rank + 2.0
+    before = {k: v.clone() for k, v in P.items()}
+    both_mm = [torch.zeros(4) for _ in range(world)]
+    dist.all_gather(both_mm, P["a_bn_moving_mean"])
+    rd_dist.average_aux_(P)
+    if rank == 0:
+        ret["bcast_equal"] = all(torch.equal(v[0], v[1]) for v in gathered.values())
+        ret["bcast_is_rank0"] = all(torch.equal(gathered[k][0], mine[k]) for k in mine)
+        ret["flat_path_same"] = same_as_generic
+        ret["aux_avg_err"] = float((P["a_bn_moving_mean"] - (both_mm[0] + both_mm[1]) / 2).abs().max())
+        ret["args_untouched"] = all(torch.equal(P[k], before[k]) for k in names)
+    else:
+        ret["rank1_changed"] = not torch.equal(gathered["a_weight"][1], mine["a_weight"])
+    dist.destroy_process_group()
+
+
+def test_gloo_world2_startup_broadcast_and_aux_average():
+    world = 2
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    mp.spawn(_sync_worker, args=(world, _free_port(), ret), nprocs=world, join=True)
+    assert ret["bcast_equal"] and ret["bcast_is_rank0"] and ret["rank1_changed"] and ret["flat_path_same"]
+    assert ret["aux_avg_err"] < 1e-6 and ret["args_untouched"]
