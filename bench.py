@@ -1,21 +1,24 @@
 #!/usr/bin/env python
-"""bench.py -- RangeDet hot-path benchmark (BASELINE.json configs[1]).
+"""bench.py -- RangeDet hot-path benchmark.  Headline: BASELINE.json configs[4], the config the
+metric "range-image frames/s (fwd+bwd, 64x2650)" is quoted on.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--mk-impl 0|1|2]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--dtype f16|bf16] [--batch B]
 
-A "step" is one pass of the Meta-Kernel hot path over one batch of synthetic range images:
-forward + backward (grad w.r.t. features and the four MLP parameters) of
-MetaKernel.meta_baseline_bias at B=4 frames per GPU, C=64, 64x2650 padded to 2656, fp32
-(SURVEY.md 8d cfg-2).  N>1 (launched by torchrun, one rank per GPU): frames are sharded across ranks
-(weak scaling, no data-path collective); the only exchange is the data-parallel all-reduce of the
-MLP parameter gradients over NCCL, as in the reference's Horovod loop (tools/train.py:364-368).
+A "step" is one training iteration of rangedet_veh_wo_aug_4_18e on a synthetic roidb record: DLA backbone + Meta-Kernel
+unit + RPN head forward, fused RPN loss (decode -> rotated IoU target -> VFL + smooth-L1), backward, NCCL all-reduce of
+the flat 9.1 M-parameter gradient (N > 1), MXNet SGD-momentum update; B = 2 frames per GPU (config:32), 64x2650 padded to
+2656, storage dtype f16 as the reference ships (config:35) or bf16, fp32 accumulation and statistics.  N > 1 (torchrun,
+one rank per GPU): frames shard across ranks (weak scaling), the only exchange is the gradient all-reduce.
 
-Printed JSON line: see the task contract.  `value` = whole-job frames/s with inputs resident in
-HBM; `e2e` = same metric through the C-ABI with HOST (pinned) buffers, H2D/D2H copies timed;
-`roofline` = dominant kernel vs measured HBM peak; `cpu_baseline` = the CPU oracle port (torch
-fp32 restatement; the reference's own CPU path is MXNet, not installable here) on a bounded sample.
+JSON line (rank 0): `value` = whole-job frames/s, inputs resident in HBM; `e2e` = the same step through the reference-
+facing graph API (symbol.TrainSymbol.bind -> train.HostFedTrainStep) fed a HOST loader record per step, H2D copies and the
+loss read-back inside the timed region; `roofline` = the dominant kernel family (tcgen05 implicit-GEMM convolutions)
+timed in situ with CUDA events vs the measured bf16/f16 tensor peak, with the per-family table; `cpu_baseline` = the
+torch-fp32 CPU restatement of the same step on one frame.  Extra keys (N = 1): `meta_kernel` (cfg-2, the "Meta-Kernel HBM
+GB/s" half of the metric), `postprocess` (cfg-3: batch rotated IoU + weighted NMS on 100 k boxes, compiled reference
+beside it), `forward_b8` (cfg-4), `train_step_b4`.
 
---impl reference: times that CPU restatement on all host cores (rank 0 only).
+--impl reference: the CPU restatement alone, all host cores, one frame per step (rank 0 only).
 """
 import argparse
 import json
@@ -30,21 +33,25 @@ sys.path.insert(0, ROOT)
 
 METRIC = "range-image frames/s (fwd+bwd, 64x2650)"
 UNIT = "frames/s"
-B_PER_GPU, C, H, W, W_PAD = 4, 64, 64, 2650, 2656
-WORKLOAD = "meta_kernel_fwd_bwd cfg-2: B=4/GPU, C=64, 64x2650 (padded 2656), fp32, NCHW"
-# algorithmic HBM bytes per pixel at the op boundary (DESIGN.md "Meta-Kernel")
-BYTES_FWD = 64 * 4 + 3 * 4 + 576 * 4          # 2572
-BYTES_BWD_DATA = 576 * 4 + 3 * 4 + 64 * 4      # grad_out + coord -> grad_data            2572
-BYTES_BWD_PARAM = 576 * 4 + 64 * 4 + 3 * 4     # grad_out + data + coord -> (tiny) grads   2572
-PIXELS_PER_FRAME = H * W_PAD                   # counted on the padded grid the kernels process
+H, W, W_PAD = 64, 2650, 2656
+TRAIN_B = 2                       # per-GPU batch of the shipped config (config/rangedet/rangedet_veh_wo_aug_4_18e.py:32)
+FLOP_FWD_PER_FRAME = 1.114e12     # SURVEY.md 8(a3/a4): backbone 480 + head 634 GFLOP forward per frame
+FLOP_STEP_PER_FRAME = 3 * FLOP_FWD_PER_FRAME
 
 
-def measured_peak_gbs():
+def workload(B, dtype):
+    return ("cfg-5 rangedet_veh_wo_aug_4_18e train step on synthetic roidb: backbone + Meta-Kernel unit + head fwd, RPN loss, "
+            "bwd, all-reduce, SGD; B=%d/GPU, 64x2650 (padded 2656), %s storage / fp32 accumulate, training-mode BN" % (B, dtype))
+
+
+def peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     try:
-        return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        d = json.load(open(p))
+        return dict(hbm=float(d["hbm_gbs"]), tensor_burst=float(d["bf16_tflops"]), tensor=float(d["bf16_tflops_sustained"]),
+                    source="measured (MEASURED_PEAKS.json)")
     except Exception:
-        return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+        return dict(hbm=6650.0, tensor_burst=1650.0, tensor=1450.0, source="fallback (B200_PROFILING.md)")
 
 
 class ClockSampler(threading.Thread):
@@ -95,143 +102,419 @@ class ClockSampler(threading.Thread):
         return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm)}
 
 
-class CpuPort(object):
-    """The CPU port (oracle/meta_kernel_ref.py) on `frames` frames of the bench workload; inputs are
-    generated once, only forward+backward is timed.  The thread count is calibrated (all cores is not
-    always the fastest on a two-socket host): one pass each at all / half / quarter of the cores."""
+# =====================================================================================================
+# CPU arm: the torch-fp32 restatement of the same training step (oracle/: the one place bench.py may execute it)
+# =====================================================================================================
+class CpuTrainStep(object):
+    """One frame of the cfg-5 step on host cores: oracle/dla_train_ref.py (fp32, training-mode BN) forward -> oracle/
+    loss_ref.py per level (IoU target through the C restatement of Decode3DBbox + RotatedIOU, split over a thread pool)
+    -> autograd backward -> MXNet SGD restatement.  The reference's own CPU path is MXNet (not installable: no network)."""
 
-    def __init__(self, frames):
+    def __init__(self, frames=1):
+        import numpy as np
         import torch
+        from oracle import dla_ref
         from rangedet_b200 import synth
-        self.torch, self.frames = torch, frames
-        self.t = [torch.from_numpy(x) for x in (synth.feature_map(frames, C, seed=1), synth.range_image_coords(frames, seed=0))]
-        self.ps = [torch.from_numpy(p) for p in synth.meta_mlp_params(seed=2)]
-        self.go = torch.randn(frames, 9 * C, H, W_PAD)
+        self.torch, self.np, self.frames = torch, np, frames
+        self.P = dla_ref.make_params(seed=0, device="cpu")
+        self.T = synth.rpn_targets(frames, seed=500)
+        g = torch.Generator().manual_seed(600)
+        self.data = torch.randn((frames, 8, H, W_PAD), generator=g)
+        self.coord = torch.from_numpy(synth.range_image_coords(frames, seed=700))
+        self.mom = {}
+        self.threads = os.cpu_count() or 1
+
+    def iou_target(self, reg, pc, gt):
+        import concurrent.futures as cf
+        import oracle
+        np, orc = self.np, oracle.oracle()
+        B, _, h, w = reg.shape
+        delta = np.ascontiguousarray(reg.detach().numpy().reshape(B, 8, -1).transpose(0, 2, 1))
+        n = delta.shape[1]
+        nchunk = max(1, min(self.threads, 64))
+        edges = [n * i // nchunk for i in range(nchunk + 1)]
+
+        def part(i):   # ctypes releases the GIL: the C loops run in parallel
+            lo, hi = edges[i], edges[i + 1]
+            dec = orc.decode_3d_bbox(delta[:, lo:hi], np.ascontiguousarray(pc[:, lo:hi]))
+            return orc.batch_rotated_iou_max(dec, gt, "bev")
+
+        with cf.ThreadPoolExecutor(nchunk) as ex:
+            parts = list(ex.map(part, range(nchunk)))
+        return self.torch.from_numpy(np.concatenate(parts, 1)).reshape(B, 1, h, w)
 
     def once(self):
-        from oracle import meta_kernel_ref
+        from oracle import dla_train_ref, loss_ref
+        from rangedet_b200 import train
+        torch, T = self.torch, self.T
         t0 = time.perf_counter()
-        meta_kernel_ref.meta_baseline_bias_fwd_bwd(self.t[0], self.t[1], *self.ps, self.go)
+        ref = dla_train_ref.TrainRef(self.P, bf16=False)
+        cls, reg = ref.forward(self.data, self.coord)
+        d_cls, d_reg = [], []
+        for lvl, s in enumerate((1, 2, 4)):
+            tt = lambda k: torch.from_numpy(T["%s_s%d" % (k, s)])
+            iou = self.iou_target(reg[lvl], T["pc_vehicle_frame_s%d" % s], T["gt_bbox_veh_for_iou_pred"])
+            r = loss_ref.rpn_loss_level(cls[lvl], reg[lvl], None, None, tt("range_image_mask"), tt("rpn_reg_target"),
+                                        tt("rpn_reg_weight"), tt("reg_normalize_weight"), iou_target_override=iou)
+            d_cls.append(r["d_cls"])
+            d_reg.append(r["d_reg"])
+        torch.autograd.backward(cls + reg, d_cls + d_reg)
+        grads = {k: v.grad for k, v in ref.P.items() if v.requires_grad and v.grad is not None}
+        train.sgd_momentum_step(self.P, grads, self.mom, lr=0.0125, momentum=0.9, wd=1e-5, clip_gradient=35.0, rescale_grad=1 / 128.0)
         return time.perf_counter() - t0
 
     def calibrate_threads(self):
+        """all cores is not always the fastest on a two-socket host: one pass each at all / half of the cores"""
         cores = os.cpu_count() or 1
-        self.torch.set_num_threads(cores)
-        self.once()  # first call pays allocator start-up
         best = None
-        for th in sorted({cores, max(1, cores // 2), max(1, cores // 4)}, reverse=True):
+        for th in sorted({cores, max(1, cores // 2)}, reverse=True):
             self.torch.set_num_threads(th)
+            self.threads = th
             dt = self.once()
             if best is None or dt < best[0]:
                 best = (dt, th)
         self.torch.set_num_threads(best[1])
-        return best[1]
+        self.threads = best[1]
+        return best
 
 
-def cpu_oracle_fwd_bwd(frames, reps):
-    """-> (frames/s, threads): best of `reps` passes at the calibrated thread count."""
-    port = CpuPort(frames)
-    th = port.calibrate_threads()
-    best = min(port.once() for _ in range(reps))
-    return frames / best, th
+CPU_SAMPLE = ("each step = 1 frame of the B=2 batch: fwd + RPN loss + bwd + SGD, torch fp32 CPU restatement of dla_backbone.py:17-161 / "
+              "builder.py:198-422 + C restatement of Decode3DBbox/RotatedIOU (reference CPU path = MXNet, not installable: no network)")
 
 
 def run_reference(args, rank, world):
     if rank != 0:
         return
-    port = CpuPort(1)
-    th = port.calibrate_threads()  # untimed (includes the warm-up pass)
-    for _ in range(min(args.warmup, 1)):
-        port.once()
-    dt = sum(port.once() for _ in range(args.steps))
-    val = args.steps * 1.0 / dt
-    sample = "each step = 1 frame (of the B=4 batch) fwd+bwd, torch fp32 CPU restatement of meta_kernel.py:166-240"
-    line = {
-        "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus,
-        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "note": "reference CPU path is MXNet (not installable here, no network); "
-                   "timed: op-for-op torch CPU port, thread count calibrated over {all, 1/2, 1/4} of the host cores"},
-        "cpu_baseline": {"value": val, "unit": UNIT, "cores": th, "kind": "port", "sample": sample},
-        "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-        "gpu_launches": 0,
-    }
+    port = CpuTrainStep(1)
+    _, th = port.calibrate_threads()      # untimed: doubles as the warm-up passes
+    steps = max(1, min(args.steps, 8))    # bounded: ~5-15 s of CPU work per step
+    dt = sum(port.once() for _ in range(steps))
+    val = steps / dt
+    line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
+            "warmup": 2, "ms_per_step": 1e3 * dt / steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": workload(TRAIN_B, "f32 (CPU)"),
+                       "note": "CPU port of the step, thread count calibrated over {all, 1/2} of the host cores; steps capped at 8"},
+            "cpu_baseline": {"value": val, "unit": UNIT, "cores": th, "kind": "port", "sample": CPU_SAMPLE},
+            "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
     print(json.dumps(line), flush=True)
 
 
-TRAIN_B = 2   # per-GPU batch of the shipped config (config/rangedet/rangedet_veh_wo_aug_4_18e.py:32)
-
-
-def train_step_leg(args, rank, world, dev, B=TRAIN_B):
-    """BASELINE.json configs[4]: the whole training iteration -- DLA backbone + Meta-Kernel unit
-    + RPN head forward, fused RPN loss (IoU target + VFL + smooth-L1), backward, NCCL all-reduce of the flat
-    9.1 M-parameter gradient, MXNet SGD-momentum update -- on a synthetic roidb record, B=2 frames per GPU,
-    CUDA-graph replay.  Reported beside the headline (not the headline: that is configs[1])."""
+# =====================================================================================================
+# GPU arm
+# =====================================================================================================
+def _barrier(world):
     import torch
     import torch.distributed as dist
-
-    from rangedet_b200 import synth, train
-    from rangedet_b200.model_params import make_params, num_parameters
-
-    P = make_params(seed=0, device=dev)
-    nparam = num_parameters(P)
-
-    ar_ev = [torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)]
-
-    def allreduce(flat):   # sum; the 1/world of the average is folded into the optimiser's rescale_grad
-        ar_ev[0].record()
-        dist.all_reduce(flat, op=dist.ReduceOp.SUM)
-        ar_ev[1].record()
-
-    step = train.GraphedTrainStep(P, B, H, W_PAD, lr=0.01 / 8 * world * B * 5, device=dev,
-                                  allreduce=allreduce if world > 1 else None, world_size=world)
-    step.set_targets(synth.rpn_targets(B, seed=500 + rank))
-    g = torch.Generator(device=dev).manual_seed(600 + rank)
-    data = torch.randn((B, 8, H, W_PAD), device=dev, generator=g)
-    coord = torch.from_numpy(synth.range_image_coords(B, seed=700 + rank)).to(dev)
-    for _ in range(3):
-        step.train_step(data, coord)
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
-    n = max(5, min(args.steps, 20))
-    sampler = ClockSampler(dev.index if dev.index is not None else 0) if rank == 0 else None   # this region is long enough
-    if sampler is not None:                                                                     # for ~10 nvidia-smi samples
-        sampler.start()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(n):
-        step.train_step(data, coord)
-    e1.record()
-    if world > 1:
-        dist.barrier()
-    torch.cuda.synchronize()
-    ms = e0.elapsed_time(e1)
+
+
+def _max_over_ranks(ms, world, dev):
+    import torch
+    import torch.distributed as dist
     if world > 1:
         t = torch.tensor([ms], device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms = float(t.item())
-    loss = step.loss_out
+    return ms
+
+
+def make_step(B, dev, world, dtype, capture=True, ar_ev=None):
+    """symbol.TrainSymbol.bind() on the shipped config values -> train.GraphedTrainStep (the reference-facing API)."""
+    import torch
+    import torch.distributed as dist
+    from rangedet_b200 import symbol, synth
+    from rangedet_b200.model_params import make_params
+    pB, pR, opt = synth.shipped_config(is_train=True)
+    pB.batch_image = pR.batch_image = B
+    sym = symbol.RangeRCNN(pR).get_train_symbol(symbol.DLABackbone(pB), symbol.RangeRpnHead(pR))
+
+    def allreduce(flat):   # SUM; the 1/world of the average is folded into the optimiser's rescale_grad
+        if ar_ev is not None:
+            ar_ev[0].record()
+        dist.all_reduce(flat, op=dist.ReduceOp.SUM)
+        if ar_ev is not None:
+            ar_ev[1].record()
+
+    P = make_params(seed=0, device=dev)
+    kw = dict(act_dtype=dtype) if dtype is not None else {}
+    step = sym.bind(P, batch_image=B, optimizer=opt, world_size=world, allreduce=allreduce if world > 1 else None, device=dev,
+                    lr=0.01 / 8 * world * B * 5, capture=capture, **kw)
+    if world > 1:
+        step.broadcast_parameters(src=0)      # tools/train.py:219-229
+    return step, sym
+
+
+def train_leg(args, rank, world, dev, B, dtype, steps, warmup, with_clocks):
+    import numpy as np
+    import torch
+    from rangedet_b200 import _lib, synth
+    ar_ev = [torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)]
+    step, sym = make_step(B, dev, world, dtype, ar_ev=ar_ev)
+    step.set_targets(synth.rpn_targets(B, seed=500 + rank))
+    g = torch.Generator(device=dev).manual_seed(600 + rank)
+    data = torch.randn((B, 8, H, W_PAD), device=dev, generator=g)
+    coord = torch.from_numpy(synth.range_image_coords(B, seed=700 + rank)).to(dev)
+    for _ in range(max(warmup, 3)):
+        step.train_step(data, coord)
+    _barrier(world)
+    sampler = ClockSampler(dev.index or 0) if (rank == 0 and with_clocks) else None
+    if sampler is not None:
+        sampler.start()
+        time.sleep(0.15)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    _barrier(world)
+    e0.record()
+    for _ in range(steps):
+        step.train_step(data, coord)
+    e1.record()
+    _barrier(world)
+    ms = _max_over_ranks(e0.elapsed_time(e1), world, dev)
     clocks = sampler.finish() if sampler is not None else None
-    res = {"clocks": clocks, "workload": "rangedet_veh_wo_aug_4_18e train step on synthetic roidb: backbone + Meta-Kernel unit + head fwd, "
-                       "RPN loss, bwd, all-reduce, SGD; B=%d/GPU, 64x2656, bf16 operands / fp32 accumulate, training-mode BN" % B,
-           "value": B * world * n / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms / n, "steps": n, "batch_per_gpu": B,
-           "parameters": int(nparam), "allreduce_bytes": int(step.flat.numel() * 4) if world > 1 else 0,
+    loss = step.loss_out
+    per_step = sum(step.launches.values()) if step.launches else None
+    res = {"value": B * world * steps / (ms * 1e-3), "ms_per_step": ms / steps, "steps": steps, "batch_per_gpu": B,
+           "parameters": int(step.flatP.numel()), "allreduce_bytes": int(step.flat.numel() * 4) if world > 1 else 0,
            "allreduce_ms": ar_ev[0].elapsed_time(ar_ev[1]) if world > 1 else 0.0,
-           "algorithmic_TFLOPs": 3 * 1.114e12 * B / (ms / n * 1e-3) / 1e12,
+           "algorithmic_TFLOPs_per_gpu": FLOP_STEP_PER_FRAME * B / (ms / steps * 1e-3) / 1e12,
+           "launches_per_step": per_step, "launches_by_graph": step.launches,
            "cls_loss": float(sum(o["cls_loss"].sum() for o in loss)), "reg_loss": float(sum(o["reg_loss"].sum() for o in loss)),
-           "params_finite": bool(torch.isfinite(step.flatP).all())}
-    del step, P
+           "params_finite": bool(torch.isfinite(step.flatP).all()), "clocks": clocks}
+    return res, step, sym, (data, coord)
+
+
+def e2e_leg(step, rank, world, dev, B, steps):
+    """The step as a host-side caller drives it: a pinned HOST loader record per iteration (input_data, coord_s1 and the 16
+    target / mask / point / GT arrays of builder.py:20-37), uploaded inside the timed region, the six loss sums read back."""
+    import numpy as np
+    import torch
+    from rangedet_b200 import synth, train
+    fed = train.HostFedTrainStep(step, slots=2)
+    recs = []
+    for i in range(2):   # two distinct records alternate (a real loader never repeats a buffer back to back)
+        T = synth.rpn_targets(B, seed=800 + 2 * rank + i)
+        T["input_data"] = np.random.default_rng(900 + 2 * rank + i).standard_normal((B, 8, H, W_PAD)).astype(np.float32)
+        T["coord_s1"] = synth.range_image_coords(B, seed=950 + 2 * rank + i)
+        recs.append({k: torch.from_numpy(np.ascontiguousarray(v, dtype=np.float32)).pin_memory() for k, v in T.items()})
+    fed.feed(recs[0])
+    for i in range(3):                     # warm-up (pinned staging, copy stream)
+        fed.feed(recs[(i + 1) % 2])
+        fed.step()
+    fed.losses()
+    _barrier(world)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(steps):
+        fed.feed(recs[i % 2])              # record i+1 uploads while record i computes
+        fed.step()
+    vals = fed.losses()                    # waits for the last step's read-back
+    e1.record()
+    _barrier(world)
+    ms = _max_over_ranks(e0.elapsed_time(e1), world, dev)
+    fed.step()                             # drain the record still in flight
+    fed.losses()
+    return {"value": B * world * steps / (ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": int(fed.h2d_bytes),
+            "d2h_bytes_per_step": int(fed.d2h_bytes), "steps": steps, "ms_per_step": ms / steps,
+            "loss_values": [float(v) for v in vals],
+            "note": "symbol.TrainSymbol.bind() -> train.HostFedTrainStep: pinned host loader record (input_data, coord_s1, targets, "
+                    "masks, points, GT) -> device on a copy stream (record i+1 overlaps step i), captured fwd/loss/bwd/all-reduce/"
+                    "SGD, six loss sums -> pinned host"}
+
+
+def roofline_leg(dev, B, dtype, pk):
+    """Per-family in-situ timing of ONE eager step (same buffers / kernels as the captured step), CUDA events on the launching
+    stream around every C-ABI call, no host sync in between (rangedet_b200/profiling.py)."""
+    import torch
+    from rangedet_b200 import profiling, synth
+    step, _ = make_step(B, dev, 1, dtype, capture=False)
+    step.set_targets(synth.rpn_targets(B, seed=500))
+    g = torch.Generator(device=dev).manual_seed(600)
+    data = torch.randn((B, 8, H, W_PAD), device=dev, generator=g)
+    coord = torch.from_numpy(synth.range_image_coords(B, seed=700)).to(dev)
+    for _ in range(2):
+        step.train_step(data, coord)
+    torch.cuda.synchronize()
+    with profiling.OpTimer() as t:
+        step.train_step(data, coord)
+    rows = t.rows()
+    fams = profiling.OpTimer.families(rows)
+    total_ms = sum(f["ms"] for f in fams)
+    table = {}
+    for f in fams:
+        e = {"bound": f["bound"], "calls": f["n"], "ms": round(f["ms"], 3), "share": round(f["ms"] / total_ms, 4)}
+        if f["bound"] == "tensor":
+            e.update(TFLOPs=round(f["TFLOPs"], 1), frac=round(f["TFLOPs"] / pk["tensor"], 4))
+        elif f["bound"] == "hbm":
+            e.update(GBps=round(f["GBps"], 1), frac=round(f["GBps"] / pk["hbm"], 4))
+        table[f["family"]] = e
+    conv = next(f for f in fams if f["family"] == "conv")
+    top = [{"op": r["op"], "shape": r["key"], "calls": r["n"], "ms": round(r["ms"], 3),
+            "TFLOPs": round(r["flops"] / (r["ms"] * 1e-3) / 1e12, 1) if r["flops"] else None,
+            "GBps": round(r["bytes"] / (r["ms"] * 1e-3) / 1e9, 1)} for r in rows[:14]]
+    traffic = None
+    try:   # DRAM bytes per launch of the dominant conv shape from the committed `ncu --set full` capture (profiles/)
+        tr = json.load(open(os.path.join(ROOT, "profiles", "r02_dram_traffic.json")))
+        if tr.get("batch") == B:
+            traffic = tr.get("conv_128_128_2656_bytes_per_launch")
+    except (OSError, ValueError):
+        pass
+    del step
     torch.cuda.empty_cache()
+    return {"bound": "tensor", "kernel": "conv::conv_kernel family (tcgen05 implicit-GEMM fprop + dgrad + transposed conv), %d launches/step"
+            % conv["n"], "achieved": conv["TFLOPs"], "peak": pk["tensor"], "unit": "TFLOP/s", "frac": conv["TFLOPs"] / pk["tensor"],
+            "traffic": traffic, "traffic_unit": "bytes per launch of conv 3x3 128->128 @2656 (ncu dram read+write)",
+            "algorithmic_flops": conv["flops"], "ms": conv["ms"], "peak_source": pk["source"] + ": bf16_tflops_sustained "
+            "(kernel timed inside a long step; f16 and bf16 share the tcgen05 kind::f16 rate)",
+            "how": "one eager step, CUDA events around every C-ABI call on the launching stream, no host sync between calls",
+            "step_ms_sum_of_kernels": round(total_ms, 3), "families": table, "top_calls": top}
+
+
+def meta_kernel_leg(dev, pk, steps):
+    """BASELINE.json configs[1] (cfg-2): Meta-Kernel fwd+bwd at the reference op boundary (fp32 NCHW), B=4, C=64, 64x2656."""
+    import ctypes
+    import torch
+    from rangedet_b200 import _lib, ops, synth
+    B, C = 4, 64
+    data = torch.from_numpy(synth.feature_map(B, C, seed=100)).to(dev)
+    coord = torch.from_numpy(synth.range_image_coords(B, seed=200)).to(dev)
+    w0, b0, w1, b1 = [torch.from_numpy(p).to(dev) for p in synth.meta_mlp_params(seed=2)]
+    gen = torch.Generator(device=dev).manual_seed(300)
+    grad_out = torch.randn((B, 9 * C, H, W_PAD), device=dev, generator=gen)
+
+    def step():
+        ops.meta_kernel_forward(data, coord, w0, b0, w1, b1)
+        ops.meta_kernel_backward(grad_out, data, coord, w0, b0, w1, b1)
+
+    def timed(fn, reps):
+        fn()
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(reps):
+            fn()
+        b.record()
+        torch.cuda.synchronize()
+        return a.elapsed_time(b) / reps
+
+    for _ in range(3):
+        step()
+    ms = timed(step, steps)
+    L, P, S = _lib.lib(), ops._p, ops._stream
+    out = torch.empty((B, 9 * C, H, W_PAD), device=dev)
+    gd = torch.empty_like(data)
+    gws = [torch.empty(96, device=dev), torch.empty(32, device=dev), torch.empty(C * 32, device=dev), torch.empty(C, device=dev)]
+    ws = torch.empty(int(L.rd_meta_kernel_bwd_workspace_bytes(B, C, H, W_PAD)) // 4 + 1, device=dev)
+    px = B * H * W_PAD
+    bpp = 64 * 4 + 12 + 576 * 4          # 2572 B/px per kernel at the op boundary (SURVEY 8d)
+    ks = {
+        "meta_fwd": lambda: _lib.check(L.rd_meta_kernel_fwd(P(data), P(coord), P(w0), P(b0), P(w1), P(b1), P(out), B, C, H, W_PAD, 0, S()), "fwd"),
+        "meta_bwd_data": lambda: _lib.check(L.rd_meta_kernel_bwd_data(P(grad_out), P(coord), P(w0), P(b0), P(w1), P(b1), P(gd), B, C, H,
+                                                                      W_PAD, 0, S()), "bwd_data"),
+        "meta_bwd_params": lambda: _lib.check(L.rd_meta_kernel_bwd_params(P(grad_out), P(data), P(coord), P(w0), P(b0), P(w1), P(b1),
+                                                                          P(gws[0]), P(gws[1]), P(gws[2]), P(gws[3]), P(ws),
+                                                                          ctypes.c_size_t(ws.numel() * 4), B, C, H, W_PAD, 0, S()), "bwd_params"),
+    }
+    kernels = {}
+    for name, fn in ks.items():
+        kms = timed(fn, max(3, min(steps, 10)))
+        kernels[name] = {"ms": round(kms, 4), "GBps": round(px * bpp / (kms * 1e-3) / 1e9, 1), "frac": round(px * bpp / (kms * 1e-3) / 1e9 / pk["hbm"], 4)}
+    step_bytes = px * (2572 + 2828)      # fwd + fused-backward algorithmic bytes (SURVEY 8d: 5400 B/px)
+    return {"workload": "cfg-2 meta_kernel fwd+bwd: B=4, C=64, 64x2650 (padded 2656), fp32 NCHW op boundary (meta_kernel.py:166-240)",
+            "frames_per_s": B / (ms * 1e-3), "ms_per_step": ms, "step_algorithmic_GBps": step_bytes / (ms * 1e-3) / 1e9,
+            "step_frac_of_hbm_peak": step_bytes / (ms * 1e-3) / 1e9 / pk["hbm"], "hbm_peak_GBps": pk["hbm"], "kernels": kernels,
+            "algorithmic_bytes_per_kernel": px * bpp}
+
+
+def postprocess_leg(dev, want_cpu):
+    """BASELINE.json configs[2] (cfg-3): batch_rotated_iou (100 000 x 200) and weighted NMS (100 000 clustered 7-DoF boxes),
+    device-resident and through the host-facing processing_cxx call; the compiled reference (oracle/_ref, 1 thread, as the
+    reference runs it) timed beside them on a bounded sample."""
+    import numpy as np
+    import torch
+    from rangedet_b200 import ops, processing_cxx, synth
+    N, G = 100000, 200
+    res = {"workload": "cfg-3: batch_rotated_iou %dx%d + wnms_4c(thresh 0.1, vote 0.5, bev, hash 100) on %d clustered boxes" % (N, G, N)}
+
+    def timed(fn, reps):
+        fn()
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(reps):
+            r = fn()
+        b.record()
+        torch.cuda.synchronize()
+        return a.elapsed_time(b) / reps, r
+
+    c10 = synth.boxes7_to_corners10(synth.boxes7(N, seed=0, clustered=True)).astype(np.float32)[None]
+    gt = synth.gt_boxes8(1)
+    prop, gtd = torch.from_numpy(c10).to(dev), torch.from_numpy(gt).to(dev)
+    ms, iou = timed(lambda: ops.batch_rotated_iou(prop, gtd, "bev"), 10)
+    res["batch_rotated_iou"] = {"ms": ms, "pairs_per_s": N * G / (ms * 1e-3), "pairs": N * G}
+    dets_h = synth.wnms_dets(N, seed=0, clustered=True)
+    dets = torch.from_numpy(dets_h).to(dev)
+    ms, (out, keep) = timed(lambda: ops.wnms_4c_device(dets, 0.1, 0.5, False, 100), 3)
+    res["wnms_4c"] = {"ms": ms, "boxes_per_s": N / (ms * 1e-3), "kept": int(keep.numel()), "boxes": N}
+    t0 = time.perf_counter()
+    o, k = processing_cxx.wnms_4c(dets_h, 0.1, 0.5, False, 100)     # numpy in, Python lists out (pybinding.cpp:8)
+    dt = time.perf_counter() - t0
+    res["wnms_4c_host_call"] = {"ms": dt * 1e3, "boxes_per_s": N / dt, "note": "processing_cxx.wnms_4c: H2D, kernels, D2H, list conversion"}
+    if want_cpu:
+        try:
+            import oracle
+            ref = oracle.reference() or oracle.oracle()
+            kind = "reference" if oracle.reference() is not None else "port"
+            ns = 20000     # bounded sample (the reference is O(N*K): 76 s at 100 k)
+            d_s = synth.wnms_dets(ns, seed=0, clustered=True)
+            t0 = time.perf_counter()
+            _, rk = ref.wnms_4c(d_s, 0.1, 0.5, False, 100)
+            dt = time.perf_counter() - t0
+            og, kg = ops.wnms_4c_device(torch.from_numpy(d_s).to(dev), 0.1, 0.5, False, 100)
+            res["wnms_4c_cpu"] = {"kind": kind, "cores": 1, "boxes": ns, "ms": dt * 1e3, "boxes_per_s": ns / dt,
+                                  "keep_indices_bit_exact_vs_gpu": bool(np.array_equal(np.asarray(rk), kg.cpu().numpy()))}
+            n1 = 4000
+            b1 = np.ascontiguousarray(c10[0, :n1, :8])
+            t0 = time.perf_counter()
+            ri = ref.rotated_iou(b1, np.ascontiguousarray(gt[0]))
+            dt = time.perf_counter() - t0
+            gi = ops.rotated_iou(torch.from_numpy(b1).to(dev), gtd[0].contiguous()).cpu().numpy()
+            res["rotated_iou_cpu"] = {"kind": kind, "cores": 1, "pairs": n1 * G, "ms": dt * 1e3, "pairs_per_s": n1 * G / dt,
+                                      "max_abs_diff_vs_gpu": float(np.abs(ri - gi).max())}
+        except Exception as ex:  # report, never fake
+            res["cpu_error"] = repr(ex)[:300]
     return res
 
 
+def forward_leg(dev, B=8, reps=10):
+    """BASELINE.json configs[3] (cfg-4): full backbone + Meta-Kernel + head forward, bf16, batch 8, CUDA-graph replay."""
+    import torch
+    from rangedet_b200 import dla, synth
+    from rangedet_b200.model_params import make_params
+    fwd = dla.GraphedForward(make_params(seed=0, device=dev), B, H, W_PAD, dev)
+    g = torch.Generator(device=dev).manual_seed(1)
+    data = torch.randn((B, 8, H, W_PAD), device=dev, generator=g)
+    coord = torch.from_numpy(synth.range_image_coords(B, seed=0)).to(dev)
+    for _ in range(3):
+        fwd(data, coord)
+    torch.cuda.synchronize()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(reps):
+        fwd(data, coord)
+    b.record()
+    torch.cuda.synchronize()
+    ms = a.elapsed_time(b) / reps
+    del fwd
+    torch.cuda.empty_cache()
+    return {"workload": "cfg-4: DLA backbone + Meta-Kernel + head forward (inference form, folded BN), bf16, B=8, 64x2656",
+            "ms": ms, "frames_per_s": B / (ms * 1e-3), "algorithmic_TFLOPs": FLOP_FWD_PER_FRAME * B / (ms * 1e-3) / 1e12}
+
+
 def run_ours(args, rank, local_rank, world):
-    import numpy as np
     import torch
     import torch.distributed as dist
-
-    from rangedet_b200 import _lib, ops, synth
 
     assert torch.cuda.is_available(), "bench.py (impl ours) needs a CUDA device: there is no CPU fallback"
     torch.cuda.set_device(local_rank)
@@ -241,190 +524,51 @@ def run_ours(args, rank, local_rank, world):
         if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
             os.environ["NCCL_DEBUG"] = "WARN"
         dist.init_process_group("nccl", device_id=dev)
-    impl = args.mk_impl
-    B = B_PER_GPU
-    # synthetic inputs, resident in HBM (different frames per rank)
-    data = torch.from_numpy(synth.feature_map(B, C, seed=100 + rank)).to(dev)
-    coord = torch.from_numpy(synth.range_image_coords(B, seed=200 + rank)).to(dev)
-    w0, b0, w1, b1 = [torch.from_numpy(p).to(dev) for p in synth.meta_mlp_params(seed=2)]
-    gen = torch.Generator(device=dev).manual_seed(300 + rank)
-    grad_out = torch.randn((B, 9 * C, H, W_PAD), device=dev, generator=gen)
-    flat_grads = torch.empty(32 * 3 + 32 + C * 32 + C, device=dev)
+    pk = peaks()
+    B = args.batch
+    dtype = {"f16": torch.float16, "bf16": torch.bfloat16}[args.dtype]
+    warm = max(args.warmup, 3)
+    head, step, sym, (data, coord) = train_leg(args, rank, world, dev, B, dtype, args.steps, warm, True)
 
-    def step():
-        out = ops.meta_kernel_forward(data, coord, w0, b0, w1, b1, impl=impl)
-        gd, gw0, gb0, gw1, gb1 = ops.meta_kernel_backward(grad_out, data, coord, w0, b0, w1, b1, impl=impl)
-        if world > 1:  # data-parallel exchange: average the MLP parameter gradients
-            torch.cat([gw0.reshape(-1), gb0, gw1.reshape(-1), gb1], out=flat_grads)
-            dist.all_reduce(flat_grads, op=dist.ReduceOp.SUM)
-            flat_grads.div_(world)
-        return out, gd
-
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    for _ in range(max(args.warmup, 3)):
-        step()
-    barrier()
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
-        sampler.start()
-        time.sleep(0.15)
-    launches0 = _lib.launch_count()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    barrier()
-    e0.record()
-    for _ in range(args.steps):
-        step()
-    e1.record()
-    barrier()
-    ms = e0.elapsed_time(e1)
-    launches = _lib.launch_count() - launches0
-    clocks = sampler.finish() if rank == 0 else None
-    if world > 1:
-        t = torch.tensor([ms], device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms = float(t.item())
-    value = B * world * args.steps / (ms * 1e-3)
-
-    # ---- per-kernel timing (CUDA events on the launching stream) for the roofline ----------
-    L = _lib.lib()
-    out = torch.empty((B, 9 * C, H, W_PAD), device=dev)
-    gd = torch.empty_like(data)
-    gws = [torch.empty(32 * 3, device=dev), torch.empty(32, device=dev), torch.empty(C * 32, device=dev),
-           torch.empty(C, device=dev)]
-    ws = torch.empty(int(L.rd_meta_kernel_bwd_workspace_bytes(B, C, H, W_PAD)) // 4 + 1, device=dev)
-    P, S = ops._p, ops._stream
-    import ctypes
-
-    def k_fwd():
-        _lib.check(L.rd_meta_kernel_fwd(P(data), P(coord), P(w0), P(b0), P(w1), P(b1), P(out), B, C, H, W_PAD, impl, S()), "fwd")
-
-    def k_bwd_data():
-        _lib.check(L.rd_meta_kernel_bwd_data(P(grad_out), P(coord), P(w0), P(b0), P(w1), P(b1), P(gd), B, C, H, W_PAD,
-                                             impl, S()), "bwd_data")
-
-    def k_bwd_param():
-        _lib.check(L.rd_meta_kernel_bwd_params(P(grad_out), P(data), P(coord), P(w0), P(b0), P(w1), P(b1), P(gws[0]),
-                                               P(gws[1]), P(gws[2]), P(gws[3]), P(ws), ctypes.c_size_t(ws.numel() * 4),
-                                               B, C, H, W_PAD, impl, S()), "bwd_params")
-
-    kernels = {}
-    px = B * PIXELS_PER_FRAME
-    for name, fn, bpp in [("meta_fwd", k_fwd, BYTES_FWD), ("meta_bwd_data", k_bwd_data, BYTES_BWD_DATA),
-                          ("meta_bwd_params", k_bwd_param, BYTES_BWD_PARAM)]:
-        reps = max(3, min(args.steps, 10))
-        fn()
-        torch.cuda.synchronize()
-        a, b_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        a.record()
-        for _ in range(reps):
-            fn()
-        b_.record()
-        torch.cuda.synchronize()
-        kms = a.elapsed_time(b_) / reps
-        kernels[name] = {"ms": kms, "algorithmic_bytes": px * bpp, "GBps": px * bpp / (kms * 1e-3) / 1e9}
-    peak, peak_src = measured_peak_gbs()
-    dom = max(kernels, key=lambda k: kernels[k]["ms"])
-    # DRAM bytes per launch of that kernel from the committed `ncu --set full` capture of this workload
-    # (profiles/r01_dram_traffic.json, written by scripts/ncu_summary.py); null for any other shape.
-    traffic = None
-    try:
-        tr = json.load(open(os.path.join(ROOT, "profiles", "r01_dram_traffic.json")))
-        if tr.get("workload") == [B, C, H, W_PAD]:
-            pat = {"meta_fwd": "meta_ws_kernel<0,", "meta_bwd_data": "meta_ws_kernel<1,",
-                   "meta_bwd_params": "meta_ws_params_kernel"}[dom]
-            for name, v in tr["kernels"].items():
-                if pat in name.replace(" ", ""):
-                    traffic = int(v["dram_read_bytes"] + v["dram_write_bytes"])
-    except (OSError, KeyError, ValueError):
-        traffic = None
-    roofline = {"bound": "hbm", "kernel": dom, "achieved": kernels[dom]["GBps"], "peak": peak, "unit": "GB/s",
-                "frac": kernels[dom]["GBps"] / peak, "traffic": traffic, "traffic_unit": "bytes per launch (ncu dram read+write)",
-                "algorithmic_bytes": int(kernels[dom]["algorithmic_bytes"]), "peak_source": peak_src,
-                "kernels": {k: {"ms": round(v["ms"], 4), "GBps": round(v["GBps"], 1), "frac": round(v["GBps"] / peak, 4)}
-                            for k, v in kernels.items()},
-                "step_algorithmic_GBps": px * (BYTES_FWD + 576 * 4 + 64 * 4 + 12 + 256) / (ms / args.steps * 1e-3) / 1e9}
-    del out, gd, ws
-
-    # ---- e2e: host (pinned) buffers through the public API, copies inside the timed region --
-    e2e = None
-    try:
-        h_data, h_coord = data.cpu().pin_memory(), coord.cpu().pin_memory()
-        h_go = torch.empty((B, 9 * C, H, W_PAD), pin_memory=True)
-        h_go.copy_(grad_out)
-        h_out = torch.empty((B, 9 * C, H, W_PAD), pin_memory=True)
-        h_gd = torch.empty((B, C, H, W_PAD), pin_memory=True)
-        h_gp = torch.empty(flat_grads.numel(), pin_memory=True)
-        h2d = (h_data.numel() + h_coord.numel() + h_go.numel()) * 4
-        d2h = (h_out.numel() + h_gd.numel() + h_gp.numel()) * 4
-
-        pipe = ops.MetaKernelHostPipeline(C, H, W_PAD, dev, impl=impl)
-
-        def e2e_step():
-            # the public host-buffer call: per-frame upload / fwd+bwd / download pipeline on three streams
-            pipe(h_data, h_coord, h_go, w0, b0, w1, b1, h_out, h_gd, h_gp)
-            if world > 1:  # data-parallel exchange of the (already summed) parameter gradients
-                pipe.wait()
-                flat_grads.copy_(pipe.gp_sum)
-                dist.all_reduce(flat_grads, op=dist.ReduceOp.SUM)
-                flat_grads.div_(world)
-                h_gp.copy_(flat_grads, non_blocking=True)
-
-        e2e_steps = max(2, min(args.steps, 8))
-        e2e_step()
-        pipe.wait()
-        barrier()
-        a, b_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        a.record()
-        for _ in range(e2e_steps):
-            e2e_step()
-        pipe.wait()
-        b_.record()
-        barrier()
-        ems = a.elapsed_time(b_)
-        if world > 1:
-            t = torch.tensor([ems], device=dev)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            ems = float(t.item())
-        e2e = {"value": B * world * e2e_steps / (ems * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d,
-               "d2h_bytes_per_step": d2h, "steps": e2e_steps,
-               "note": "ops.MetaKernelHostPipeline: pinned host data/coord/grad_out -> device, fwd+bwd per frame, out/grad_data/param "
-                       "grads -> pinned host; uploads of frame i+1 overlap downloads of frame i (PCIe full duplex)"}
-    except Exception as ex:  # report, never fake
-        e2e = {"value": None, "unit": UNIT, "error": repr(ex)[:200]}
-
-    # ---- CPU baseline (rank 0, N == 1 only): the oracle port on a bounded sample -------------
-    cpu = None
-    if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        v, th = cpu_oracle_fwd_bwd(1, 2)
-        cpu = {"value": v, "unit": UNIT, "cores": th, "kind": "port",
-               "sample": "1 frame (B=1 of the B=4 batch) fwd+bwd, best of 2, torch fp32 CPU port of meta_kernel.py:166-240 "
-                         "(reference CPU path = MXNet, not installable: no network)"}
-
-    train_leg = train_leg4 = None
-    if not args.no_train_step:
+    def guarded(fn, *a):
         try:
-            train_leg = train_step_leg(args, rank, world, dev)            # shipped per-GPU batch (config:32)
-            train_leg4 = train_step_leg(args, rank, world, dev, B=4)      # "also report B=4"
-        except Exception as ex:  # report, never fake
-            err = {"value": None, "unit": UNIT, "error": repr(ex)[:300]}
-            train_leg, train_leg4 = train_leg or err, train_leg4 or (err if train_leg else None)
+            return fn(*a)
+        except Exception as ex:   # report, never fake
+            return {"value": None, "error": repr(ex)[:300]}
 
+    e2e = guarded(e2e_leg, step, rank, world, dev, B, max(3, min(args.steps, 20)))
+    del step
+    torch.cuda.empty_cache()
+    extra = {}
+    if world == 1:
+        extra["roofline"] = guarded(roofline_leg, dev, B, dtype, pk)
+        if not args.quick:
+            extra["meta_kernel"] = guarded(meta_kernel_leg, dev, pk, max(5, min(args.steps, 20)))
+            extra["postprocess"] = guarded(postprocess_leg, dev, not args.no_cpu_baseline)
+            extra["forward_b8"] = guarded(forward_leg, dev)
+            b4 = guarded(lambda: train_leg(args, rank, world, dev, 4, dtype, max(5, min(args.steps, 10)), 3, False)[0])
+            extra["train_step_b4"] = b4
+            torch.cuda.empty_cache()
+            if not args.no_cpu_baseline:
+                def cpu():
+                    port = CpuTrainStep(1)
+                    dt, th = port.calibrate_threads()
+                    return {"value": 1.0 / dt, "unit": UNIT, "cores": th, "kind": "port", "sample": CPU_SAMPLE + "; best of 2 passes"}
+                extra["cpu_baseline"] = guarded(cpu)
     if rank == 0:
-        line = {
-            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
-            "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "batch_per_gpu": B, "global_batch": B * world,
-                       "parallelism": "dp%d (frames sharded; NCCL all-reduce of MLP param grads)" % world,
-                       "mk_impl": {0: "default (TMA+tcgen05 warp-specialised)", 1: "cuda-core fp32", 2: "tcgen05", 3: "TMA+tcgen05 warp-specialised"}[impl],
-                       "l2": "inputs larger than L2 (3.5 GB touched per step vs 126 MB L2)"},
-            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "clocks": clocks, "gpu_launches": int(launches),
-            "train_step": train_leg, "train_step_b4": train_leg4,
-        }
+        line = {"metric": METRIC, "value": head["value"], "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": warm,
+                "ms_per_step": head["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": args.dtype, "data": "synthetic",
+                "config": {"workload": workload(B, args.dtype), "batch_per_gpu": B, "global_batch": B * world,
+                           "parallelism": "dp%d (frames sharded; one flat NCCL all-reduce of the %.1f M-parameter gradient)" % (world, head["parameters"] / 1e6),
+                           "l2": "inputs larger than L2 (each step streams >10 GB of activations vs 126 MB L2)",
+                           "execution": "three CUDA graphs per step (forward | loss + backward | update), all-reduce between the last two"},
+                "roofline": extra.get("roofline"), "cpu_baseline": extra.get("cpu_baseline"), "e2e": e2e, "clocks": head.pop("clocks"),
+                "gpu_launches": int(head["launches_per_step"] * args.steps) if head["launches_per_step"] else None,
+                "train_step": head}
+        for k in ("meta_kernel", "postprocess", "forward_b8", "train_step_b4"):
+            if k in extra:
+                line[k] = extra[k]
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
@@ -436,16 +580,15 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--mk-impl", type=int, default=0, choices=[0, 1, 2, 3])
+    ap.add_argument("--dtype", default="f16", choices=["f16", "bf16"], help="activation / operand storage (reference: fp16, config:35)")
+    ap.add_argument("--batch", type=int, default=TRAIN_B, help="frames per GPU (shipped config: 2)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--no-train-step", action="store_true", help="skip the whole-model training-step leg (cfg-5)")
+    ap.add_argument("--quick", action="store_true", help="headline + e2e + roofline only (skip the cfg-2/3/4 legs)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     if args.impl == "reference":
-        if args.steps > 30:
-            args.steps = 30  # keep the CPU arm within minutes
         run_reference(args, rank, world)
         return
     if world == 1 and args.gpus > 1:

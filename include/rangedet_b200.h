@@ -291,6 +291,50 @@ int rd_gather_f32(const float* src, const int* idx, float* dst, int64_t n, rd_st
 int rd_sgd_mom_update(float* weight, const float* grad, float* mom, const float* wd, const float* hyper,
                       int64_t n, rd_stream_t stream);
 
+/* ---- fp16-storage twins ------------------------------------------------------------------------
+ * The reference trains this graph with fp16 storage and loss scale 128 (config/rangedet/
+ * rangedet_veh_wo_aug_4_18e.py:35-36; casts at rangedet/symbol/backbone/dla_backbone.py:136-137 and
+ * meta_kernel.py:193-196, un-scaled by rescale_grad at tools/train.py:359-361).  Every entry point above whose
+ * name carries `bf16` has a twin with identical arguments and semantics in which the stored activations /
+ * operands (x_pad, w_packed, residual_pad, y_pad, z_pad, dy_pad, ... ) are IEEE fp16 instead of bf16: same
+ * kernels compiled from the same source with the other storage type (csrc/act_type.cuh), same tcgen05
+ * kind::f16 MMA with fp32 accumulation, fp32 statistics / parameter gradients. */
+int rd_meta_kernel_fwd_nhwc_f16(const float* data, const float* coord, const float* w0, const float* b0,
+                                const float* w1, const float* b1, const float* scale, const float* shift,
+                                int relu, void* y_pad, int B, int C, int H, int W, rd_stream_t stream);
+int rd_conv2d_nhwc_f16(const void* x_pad, const void* w_packed, const float* scale, const float* shift,
+                       const void* residual_pad, void* y_pad, int N, int H, int W, int Cin, int Cout,
+                       int ksize, int stride_w, int relu, rd_stream_t stream);
+int rd_deconv2d_nhwc_f16(const void* x_pad, const void* w_packed, const float* scale, const float* shift,
+                         const void* residual_pad, void* y_pad, int N, int H, int W, int Cin, int Cout,
+                         int kw, int relu, rd_stream_t stream);
+int rd_conv2d_nhwc_f16_slice(const void* x_pad, const void* w_packed, const float* scale, const float* shift,
+                             void* y_pad, int N, int H, int W, int Cin, int Cout, int ksize, int stride_w,
+                             int relu, int y_ctotal, int y_coff, rd_stream_t stream);
+int rd_conv2d_wgrad_nhwc_f16(const void* a_pad, const void* b_pad, float* g, int N, int H, int W, int CA,
+                             int CB, int ksize, int stride_w, void* workspace, size_t workspace_bytes,
+                             rd_stream_t stream);
+int rd_bn_train_stats_nhwc_f16(const void* z_pad, int N, int H, int W, int C, const float* gamma,
+                               const float* beta, float eps, float momentum, float* moving_mean,
+                               float* moving_var, float* coef, void* workspace, size_t workspace_bytes,
+                               rd_stream_t stream);
+int rd_bn_act_fwd_nhwc_f16(const void* z_pad, const float* coef, const void* res_before,
+                           const void* res_after, void* y_pad, int N, int H, int W, int C, int relu,
+                           rd_stream_t stream);
+int rd_bn_act_bwd_nhwc_f16(const void* dy_pad, const void* y_mask_pad, const void* z_pad, const float* coef,
+                           int mask_mode, void* dz_pad, int dz_halo_w, void* g_out_pad, float* dgamma,
+                           float* dbeta, int N, int H, int W, int C, void* workspace,
+                           size_t workspace_bytes, rd_stream_t stream);
+int rd_channel_sums_nhwc_f16(const void* x_pad, int N, int H, int W, int C, float* sums, void* workspace,
+                             size_t workspace_bytes, rd_stream_t stream);
+int rd_add_nhwc_f16(const void* x0_pad, const void* x1_pad, void* y_pad, int N, int H, int W, int C,
+                    rd_stream_t stream);
+int rd_nhwc_f16_to_nchw_f32(const void* src_pad, float* dst, int N, int H, int W, int C_src, int C, int chmap,
+                            rd_stream_t stream);
+int rd_nchw_f32_to_nhwc_f16(const float* src, void* dst_pad, int N, int H, int W, int C, int C_dst, int chmap,
+                            rd_stream_t stream);
+int rd_gather_f32_to_f16(const float* src, const int* idx, void* dst, int64_t n, rd_stream_t stream);
+
 /* ---- tcgen05 self-test -------------------------------------------------------------------
  * D(128 x n) = A(128 x k) . B(n x k)^T with bf16 operands staged in shared memory in the
  * canonical no-swizzle K-major core-matrix layout, tcgen05.mma into TMEM, tcgen05.ld back.

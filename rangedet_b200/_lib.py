@@ -60,6 +60,20 @@ SIGNATURES = {
     "rd_gather_f32_to_bf16": (_i, [_vp, _vp, _vp, _i64, _vp]),
     "rd_gather_f32": (_i, [_vp, _vp, _vp, _i64, _vp]),
     "rd_sgd_mom_update": (_i, [_vp] * 5 + [_i64, _vp]),
+    # fp16-storage twins of every *bf16* entry point (same arguments)
+    "rd_meta_kernel_fwd_nhwc_f16": (_i, [_vp] * 8 + [_i, _vp] + [_i] * 4 + [_vp]),
+    "rd_conv2d_nhwc_f16": (_i, [_vp] * 6 + [_i] * 8 + [_vp]),
+    "rd_conv2d_nhwc_f16_slice": (_i, [_vp] * 5 + [_i] * 10 + [_vp]),
+    "rd_deconv2d_nhwc_f16": (_i, [_vp] * 6 + [_i] * 7 + [_vp]),
+    "rd_conv2d_wgrad_nhwc_f16": (_i, [_vp] * 3 + [_i] * 7 + [_vp, _sz, _vp]),
+    "rd_bn_train_stats_nhwc_f16": (_i, [_vp] + [_i] * 4 + [_vp, _vp, _f, _f, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "rd_bn_act_fwd_nhwc_f16": (_i, [_vp] * 5 + [_i] * 5 + [_vp]),
+    "rd_bn_act_bwd_nhwc_f16": (_i, [_vp] * 4 + [_i, _vp, _i, _vp, _vp, _vp] + [_i] * 4 + [_vp, _sz, _vp]),
+    "rd_channel_sums_nhwc_f16": (_i, [_vp] + [_i] * 4 + [_vp, _vp, _sz, _vp]),
+    "rd_add_nhwc_f16": (_i, [_vp] * 3 + [_i] * 4 + [_vp]),
+    "rd_nhwc_f16_to_nchw_f32": (_i, [_vp, _vp] + [_i] * 6 + [_vp]),
+    "rd_nchw_f32_to_nhwc_f16": (_i, [_vp, _vp] + [_i] * 6 + [_vp]),
+    "rd_gather_f32_to_f16": (_i, [_vp, _vp, _vp, _i64, _vp]),
     "rd_tc_probe_gemm": (_i, [_vp, _vp, _vp, _i, _i, _i, _vp]),
     "rd_tma_probe": (_i, [_vp, _vp, _vp] + [_i] * 7 + [_vp]),
 }
@@ -79,6 +93,17 @@ def lib():
             fn.argtypes = args
         _lib = L
     return _lib
+
+
+def act_fn(name_bf16, dtype):
+    """The entry point for the storage type of the tensors at hand: `name_bf16` (a name containing 'bf16') for
+    torch.bfloat16, its fp16 twin for torch.float16."""
+    import torch
+    if dtype == torch.bfloat16:
+        return getattr(lib(), name_bf16)
+    if dtype == torch.float16:
+        return getattr(lib(), name_bf16.replace("bf16", "f16"))
+    raise TypeError("rangedet_b200: activations must be stored as bfloat16 or float16, got %s" % (dtype,))
 
 
 def last_error():

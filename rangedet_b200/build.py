@@ -31,8 +31,23 @@ PER_FILE = {
 }
 
 
+# Sources that touch stored activations are compiled twice: as is (bf16 storage) and with -DRD_ACT_F16 (fp16 storage,
+# the reference's training format) -- see csrc/act_type.cuh.
+DUAL_STORAGE = ("bn_train.cu", "conv_tc.cu", "conv_wgrad.cu", "layout.cu", "optim.cu")
+
+
 def sources():
     return sorted(f for f in os.listdir(CSRC) if f.endswith(".cu"))
+
+
+def compile_units():
+    """(source file, object name, extra flags)"""
+    units = []
+    for src in sources():
+        units.append((src, src[:-3] + ".o", []))
+        if src in DUAL_STORAGE:
+            units.append((src, src[:-3] + "_f16.o", ["-DRD_ACT_F16=1"]))
+    return units
 
 
 def _newer(target, deps):
@@ -50,17 +65,21 @@ def build(force=False, verbose=False):
     headers.append(os.path.abspath(__file__))
     objs = []
     rebuilt = False
-    for src in sources():
+    procs = []
+    for src, obj, extra in compile_units():
         s = os.path.join(CSRC, src)
-        o = os.path.join(OBJDIR, src[:-3] + ".o")
+        o = os.path.join(OBJDIR, obj)
         objs.append(o)
         if not force and _newer(o, [s] + headers):
             continue
-        cmd = [NVCC] + COMMON + PER_FILE.get(src, []) + (["-Xptxas", "-v"] if verbose else []) + ["-c", s, "-o", o]
+        cmd = [NVCC] + COMMON + PER_FILE.get(src, []) + extra + (["-Xptxas", "-v"] if verbose else []) + ["-c", s, "-o", o]
         if verbose:
             print(" ".join(cmd), flush=True)
-        subprocess.check_call(cmd)
+        procs.append((cmd, subprocess.Popen(cmd)))     # independent translation units: compile them concurrently
         rebuilt = True
+    for cmd, pr in procs:
+        if pr.wait() != 0:
+            raise subprocess.CalledProcessError(pr.returncode, cmd)
     if rebuilt or not os.path.isfile(LIB):
         cmd = [NVCC, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", LIB] + objs
         if verbose:

@@ -104,7 +104,7 @@ __device__ __forceinline__ SUnit s_unit(const SGeo& G, int u) {
 struct SRing {
   unsigned char* buf;
   uint64_t* full;
-  const __nv_bfloat16* src[3];
+  const act_t* src[3];
   int nt;
   int my_units;
 
@@ -161,7 +161,7 @@ __device__ __forceinline__ void s_block_reduce_store(const float (&s)[8], const 
 }
 
 // ---- forward statistics ------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(SNT, 1) s_stats_kernel(const __nv_bfloat16* __restrict__ z, SGeo G,
+__global__ void __launch_bounds__(SNT, 1) s_stats_kernel(const act_t* __restrict__ z, SGeo G,
                                                          float* __restrict__ partial) {
   extern __shared__ unsigned char dsm[];
   __shared__ uint64_t bars[STAGES];
@@ -193,11 +193,11 @@ __global__ void __launch_bounds__(SNT, 1) s_stats_kernel(const __nv_bfloat16* __
 }
 
 // ---- forward apply: y = relu?(z*a + b + rb) + ra --------------------------------------------------------------
-__global__ void __launch_bounds__(SNT, 1) s_fwd_apply_kernel(const __nv_bfloat16* __restrict__ z,
+__global__ void __launch_bounds__(SNT, 1) s_fwd_apply_kernel(const act_t* __restrict__ z,
                                                              const float* __restrict__ coef,
-                                                             const __nv_bfloat16* __restrict__ rb,
-                                                             const __nv_bfloat16* __restrict__ ra,
-                                                             __nv_bfloat16* __restrict__ y, SGeo G, int relu) {
+                                                             const act_t* __restrict__ rb,
+                                                             const act_t* __restrict__ ra,
+                                                             act_t* __restrict__ y, SGeo G, int relu) {
   extern __shared__ unsigned char dsm[];
   __shared__ uint64_t bars[STAGES];
   SRing R;
@@ -251,9 +251,9 @@ __global__ void __launch_bounds__(SNT, 1) s_fwd_apply_kernel(const __nv_bfloat16
 }
 
 // ---- backward reduce ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(SNT, 1) s_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ dy,
-                                                              const __nv_bfloat16* __restrict__ ym,
-                                                              const __nv_bfloat16* __restrict__ z,
+__global__ void __launch_bounds__(SNT, 1) s_bwd_reduce_kernel(const act_t* __restrict__ dy,
+                                                              const act_t* __restrict__ ym,
+                                                              const act_t* __restrict__ z,
                                                               const float* __restrict__ coef, SGeo G, int mask_mode,
                                                               float* __restrict__ partial) {
   extern __shared__ unsigned char dsm[];
@@ -296,13 +296,13 @@ __global__ void __launch_bounds__(SNT, 1) s_bwd_reduce_kernel(const __nv_bfloat1
 }
 
 // ---- backward apply ----------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(SNT, 1) s_bwd_apply_kernel(const __nv_bfloat16* __restrict__ dy,
-                                                             const __nv_bfloat16* __restrict__ ym,
-                                                             const __nv_bfloat16* __restrict__ z,
+__global__ void __launch_bounds__(SNT, 1) s_bwd_apply_kernel(const act_t* __restrict__ dy,
+                                                             const act_t* __restrict__ ym,
+                                                             const act_t* __restrict__ z,
                                                              const float* __restrict__ coef,
                                                              const float* __restrict__ coef2, SGeo G, int mask_mode,
-                                                             __nv_bfloat16* __restrict__ dz, int dz_halo,
-                                                             __nv_bfloat16* __restrict__ g_out) {
+                                                             act_t* __restrict__ dz, int dz_halo,
+                                                             act_t* __restrict__ g_out) {
   extern __shared__ unsigned char dsm[];
   __shared__ uint64_t bars[STAGES];
   SRing R;

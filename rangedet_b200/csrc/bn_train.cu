@@ -14,13 +14,13 @@
 //   backward:  g = dy * [pre-activation > 0]          (mask from y, or recomputed from z when res_after)
 //              reduce  S1 = sum g, S2 = sum g*(z - mean)
 //              dz = a * (g - S1/M - (z - mean) * invstd^2 * S2/M),  dgamma = invstd*S2,  dbeta = S1
-#include <cuda_bf16.h>
 #include <stdlib.h>
 
 #include "../../include/rangedet_b200.h"
+#include "act_type.cuh"
 #include "rd_common.cuh"
 
-namespace bn {
+namespace RD_ACT_NS(bn) {
 
 constexpr int MAX_BLOCKS = 1184;  // 8 per SM: partial columns of the two-stage reductions
 constexpr int NT = 256;
@@ -52,16 +52,14 @@ __device__ __forceinline__ void unpack8(const uint4& v, float (&f)[8]) {
   const uint32_t w[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
-    f[2 * i] = __uint_as_float(w[i] << 16);
-    f[2 * i + 1] = __uint_as_float(w[i] & 0xffff0000u);
+    act::unpack2(w[i], f[2 * i], f[2 * i + 1]);
   }
 }
 __device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
   uint32_t w[4];
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
-    __nv_bfloat162 p = __floats2bfloat162_rn(f[2 * i], f[2 * i + 1]);
-    w[i] = *reinterpret_cast<uint32_t*>(&p);
+    w[i] = act::pack2(f[2 * i], f[2 * i + 1]);
   }
   return make_uint4(w[0], w[1], w[2], w[3]);
 }
@@ -89,7 +87,7 @@ __device__ __forceinline__ void block_reduce_store(const float (&s)[8], const fl
 }
 
 // ---- forward statistics: partial[block][2][C] = (sum z, sum z^2) ---------------------------------
-__global__ void __launch_bounds__(NT) stats_kernel(const __nv_bfloat16* __restrict__ z, Geo G, int halo,
+__global__ void __launch_bounds__(NT) stats_kernel(const act_t* __restrict__ z, Geo G, int halo,
                                                    float* __restrict__ partial) {
   const int t = threadIdx.x, cg = t % G.cgs, pl = t / G.cgs;
   float s[8], q[8];
@@ -99,7 +97,7 @@ __global__ void __launch_bounds__(NT) stats_kernel(const __nv_bfloat16* __restri
   for (int u = blockIdx.x; u < nunits; u += gridDim.x) {
     const int sg = u % G.nseg, row = u / G.nseg, h = row % G.H, n = row / G.H;
     const int w0 = sg * G.seg, w1 = min(G.W, w0 + G.seg);
-    const __nv_bfloat16* base = z + pix_off(n, h, 0, G.H, G.W, halo, G.C) + cg * 8;
+    const act_t* base = z + pix_off(n, h, 0, G.H, G.W, halo, G.C) + cg * 8;
     int w = w0 + pl;
     for (; w + 3 * G.ppb < w1; w += 4 * G.ppb) {   // four independent 16-byte loads in flight per thread
       uint4 v[4];
@@ -172,11 +170,11 @@ __global__ void __launch_bounds__(256) fwd_finalize_kernel(const float* __restri
 }
 
 // ---- forward apply: y = relu?(z*a + b + rb) + ra --------------------------------------------------
-__global__ void __launch_bounds__(NT, 4) fwd_apply_kernel(const __nv_bfloat16* __restrict__ z,
+__global__ void __launch_bounds__(NT, 4) fwd_apply_kernel(const act_t* __restrict__ z,
                                                        const float* __restrict__ coef,
-                                                       const __nv_bfloat16* __restrict__ rb,
-                                                       const __nv_bfloat16* __restrict__ ra,
-                                                       __nv_bfloat16* __restrict__ y, Geo G, int relu) {
+                                                       const act_t* __restrict__ rb,
+                                                       const act_t* __restrict__ ra,
+                                                       act_t* __restrict__ y, Geo G, int relu) {
   const int t = threadIdx.x, cg = t % G.cgs, pl = t / G.cgs;
   float a[8], b[8];
 #pragma unroll
@@ -249,7 +247,7 @@ __global__ void __launch_bounds__(NT, 4) fwd_apply_kernel(const __nv_bfloat16* _
 
 // ---- backward ------------------------------------------------------------------------------------
 // mask_mode: 0 no relu (g = dy), 1 mask = (y > 0) read from `ym`, 2 mask = (z*a + b > 0) recomputed
-__device__ __forceinline__ void masked_grad(float (&g)[8], const float (&zf)[8], const __nv_bfloat16* ym,
+__device__ __forceinline__ void masked_grad(float (&g)[8], const float (&zf)[8], const act_t* ym,
                                             int64_t o, int mask_mode, const float (&a)[8], const float (&b)[8]) {
   if (mask_mode == 1) {
     float yf[8];
@@ -275,9 +273,9 @@ __device__ __forceinline__ void masked_grad_v(float (&g)[8], const float (&zf)[8
   }
 }
 
-__global__ void __launch_bounds__(NT, 3) bwd_reduce_kernel(const __nv_bfloat16* __restrict__ dy,
-                                                        const __nv_bfloat16* __restrict__ ym,
-                                                        const __nv_bfloat16* __restrict__ z,
+__global__ void __launch_bounds__(NT, 3) bwd_reduce_kernel(const act_t* __restrict__ dy,
+                                                        const act_t* __restrict__ ym,
+                                                        const act_t* __restrict__ z,
                                                         const float* __restrict__ coef, Geo G, int mask_mode,
                                                         float* __restrict__ partial) {
   const int t = threadIdx.x, cg = t % G.cgs, pl = t / G.cgs;
@@ -345,13 +343,13 @@ __global__ void __launch_bounds__(256) bwd_finalize_kernel(const float* __restri
   }
 }
 
-__global__ void __launch_bounds__(NT, 3) bwd_apply_kernel(const __nv_bfloat16* __restrict__ dy,
-                                                       const __nv_bfloat16* __restrict__ ym,
-                                                       const __nv_bfloat16* __restrict__ z,
+__global__ void __launch_bounds__(NT, 3) bwd_apply_kernel(const act_t* __restrict__ dy,
+                                                       const act_t* __restrict__ ym,
+                                                       const act_t* __restrict__ z,
                                                        const float* __restrict__ coef,
                                                        const float* __restrict__ coef2, Geo G, int mask_mode,
-                                                       __nv_bfloat16* __restrict__ dz, int dz_halo,
-                                                       __nv_bfloat16* __restrict__ g_out) {
+                                                       act_t* __restrict__ dz, int dz_halo,
+                                                       act_t* __restrict__ g_out) {
   const int t = threadIdx.x, cg = t % G.cgs, pl = t / G.cgs;
   float a[8], b[8], mean[8], c1[8], c2[8];
 #pragma unroll
@@ -406,9 +404,9 @@ __global__ void __launch_bounds__(NT, 3) bwd_apply_kernel(const __nv_bfloat16* _
 }
 
 // ---- y = x0 + x1 (gradient accumulation where a tensor has two consumers) -------------------------
-__global__ void __launch_bounds__(NT) add_kernel(const __nv_bfloat16* __restrict__ x0,
-                                                 const __nv_bfloat16* __restrict__ x1,
-                                                 __nv_bfloat16* __restrict__ y, Geo G) {
+__global__ void __launch_bounds__(NT) add_kernel(const act_t* __restrict__ x0,
+                                                 const act_t* __restrict__ x1,
+                                                 act_t* __restrict__ y, Geo G) {
   const int t = threadIdx.x, cg = t % G.cgs, pl = t / G.cgs;
   const int nunits = G.N * G.H * G.nseg;
   for (int u = blockIdx.x; u < nunits; u += gridDim.x) {
@@ -440,13 +438,16 @@ static int grid_for(const Geo& g) {
   return (int)(units < MAX_BLOCKS ? units : MAX_BLOCKS);
 }
 
-}  // namespace bn
+}  // namespace bn_<storage type>
+namespace bn = RD_ACT_NS(bn);
 
 extern "C" {
 
+#ifndef RD_ACT_F16   // storage-type independent: defined once, by the bf16 pass
 size_t rd_bn_workspace_bytes(int C) { return (size_t)bn::MAX_BLOCKS * 2 * (size_t)(C > 0 ? C : 0) * sizeof(float); }
+#endif
 
-int rd_bn_train_stats_nhwc_bf16(const void* z_pad, int N, int H, int W, int C, const float* gamma, const float* beta,
+int RD_ACT_FN(rd_bn_train_stats_nhwc_, )(const void* z_pad, int N, int H, int W, int C, const float* gamma, const float* beta,
                                 float eps, float momentum, float* moving_mean, float* moving_var, float* coef,
                                 void* workspace, size_t workspace_bytes, rd_stream_t stream) {
   if (bn::check_shape("rd_bn_train_stats", N, H, W, C)) return 1;
@@ -461,9 +462,9 @@ int rd_bn_train_stats_nhwc_bf16(const void* z_pad, int N, int H, int W, int C, c
     const size_t smem = bn::sgeo_smem(sg, 1);
     if (bn::stream_prepare(bn::s_stats_kernel, smem)) return 1;
     grid = bn::stream_grid(sg);
-    bn::s_stats_kernel<<<grid, bn::SNT, smem, s>>>(static_cast<const __nv_bfloat16*>(z_pad), sg, static_cast<float*>(workspace));
+    bn::s_stats_kernel<<<grid, bn::SNT, smem, s>>>(static_cast<const act_t*>(z_pad), sg, static_cast<float*>(workspace));
   } else {
-    bn::stats_kernel<<<grid, g.ppb * g.cgs, 0, s>>>(static_cast<const __nv_bfloat16*>(z_pad), g, 1,
+    bn::stats_kernel<<<grid, g.ppb * g.cgs, 0, s>>>(static_cast<const act_t*>(z_pad), g, 1,
                                                      static_cast<float*>(workspace));
   }
   bn::fwd_finalize_kernel<<<(C + 7) / 8, 256, 0, s>>>(static_cast<const float*>(workspace), grid, C,
@@ -473,7 +474,7 @@ int rd_bn_train_stats_nhwc_bf16(const void* z_pad, int N, int H, int W, int C, c
   return rd::check_launch("rd_bn_train_stats");
 }
 
-int rd_bn_act_fwd_nhwc_bf16(const void* z_pad, const float* coef, const void* res_before, const void* res_after,
+int RD_ACT_FN(rd_bn_act_fwd_nhwc_, )(const void* z_pad, const float* coef, const void* res_before, const void* res_after,
                             void* y_pad, int N, int H, int W, int C, int relu, rd_stream_t stream) {
   if (bn::check_shape("rd_bn_act_fwd", N, H, W, C)) return 1;
   RD_REQUIRE(z_pad && coef && y_pad, "rd_bn_act_fwd: null pointer");
@@ -487,18 +488,18 @@ int rd_bn_act_fwd_nhwc_bf16(const void* z_pad, const float* coef, const void* re
     const size_t smem = bn::sgeo_smem(sg, nt);
     if (bn::stream_prepare(bn::s_fwd_apply_kernel, smem)) return 1;
     bn::s_fwd_apply_kernel<<<bn::stream_grid(sg), bn::SNT, smem, rd::as_stream(stream)>>>(
-        static_cast<const __nv_bfloat16*>(z_pad), coef, static_cast<const __nv_bfloat16*>(res_before),
-        static_cast<const __nv_bfloat16*>(res_after), static_cast<__nv_bfloat16*>(y_pad), sg, relu ? 1 : 0);
+        static_cast<const act_t*>(z_pad), coef, static_cast<const act_t*>(res_before),
+        static_cast<const act_t*>(res_after), static_cast<act_t*>(y_pad), sg, relu ? 1 : 0);
   } else {
     bn::fwd_apply_kernel<<<grid, g.ppb * g.cgs, 0, rd::as_stream(stream)>>>(
-        static_cast<const __nv_bfloat16*>(z_pad), coef, static_cast<const __nv_bfloat16*>(res_before),
-        static_cast<const __nv_bfloat16*>(res_after), static_cast<__nv_bfloat16*>(y_pad), g, relu ? 1 : 0);
+        static_cast<const act_t*>(z_pad), coef, static_cast<const act_t*>(res_before),
+        static_cast<const act_t*>(res_after), static_cast<act_t*>(y_pad), g, relu ? 1 : 0);
   }
   rd::count_launch();
   return rd::check_launch("rd_bn_act_fwd");
 }
 
-int rd_bn_act_bwd_nhwc_bf16(const void* dy_pad, const void* y_mask_pad, const void* z_pad, const float* coef,
+int RD_ACT_FN(rd_bn_act_bwd_nhwc_, )(const void* dy_pad, const void* y_mask_pad, const void* z_pad, const float* coef,
                             int mask_mode, void* dz_pad, int dz_halo_w, void* g_out_pad, float* dgamma,
                             float* dbeta, int N, int H, int W, int C, void* workspace, size_t workspace_bytes,
                             rd_stream_t stream) {
@@ -515,9 +516,9 @@ int rd_bn_act_bwd_nhwc_bf16(const void* dy_pad, const void* y_mask_pad, const vo
   cudaStream_t s = rd::as_stream(stream);
   float* partial = static_cast<float*>(workspace);
   float* coef2 = partial + (size_t)bn::MAX_BLOCKS * 2 * C;
-  const __nv_bfloat16* dy = static_cast<const __nv_bfloat16*>(dy_pad);
-  const __nv_bfloat16* ym = static_cast<const __nv_bfloat16*>(y_mask_pad);
-  const __nv_bfloat16* z = static_cast<const __nv_bfloat16*>(z_pad);
+  const act_t* dy = static_cast<const act_t*>(dy_pad);
+  const act_t* ym = static_cast<const act_t*>(y_mask_pad);
+  const act_t* z = static_cast<const act_t*>(z_pad);
   if (bn::stream_enabled()) {
     const int nt = mask_mode == 1 ? 3 : 2;
     const bn::SGeo sg = bn::make_sgeo(N, H, W, C, nt);
@@ -528,8 +529,8 @@ int rd_bn_act_bwd_nhwc_bf16(const void* dy_pad, const void* y_mask_pad, const vo
     bn::bwd_finalize_kernel<<<(C + 7) / 8, 256, 0, s>>>(partial, sgrid, C, (double)N * H * W, coef, coef2, dgamma,
                                                             dbeta);
     bn::s_bwd_apply_kernel<<<sgrid, bn::SNT, smem, s>>>(dy, ym, z, coef, coef2, sg, mask_mode,
-                                                        static_cast<__nv_bfloat16*>(dz_pad), dz_halo_w,
-                                                        static_cast<__nv_bfloat16*>(g_out_pad));
+                                                        static_cast<act_t*>(dz_pad), dz_halo_w,
+                                                        static_cast<act_t*>(g_out_pad));
   } else {
     bn::bwd_reduce_kernel<<<grid, g.ppb * g.cgs, 0, s>>>(dy, ym, z, coef, g, mask_mode, partial);
     bn::bwd_finalize_kernel<<<(C + 7) / 8, 256, 0, s>>>(partial, grid, C, (double)N * H * W, coef, coef2, dgamma,
@@ -537,14 +538,14 @@ int rd_bn_act_bwd_nhwc_bf16(const void* dy_pad, const void* y_mask_pad, const vo
     const int64_t units = (int64_t)g.N * g.H * g.nseg;
     const int grid2 = (int)(units < 8 * 148 ? units : 8 * 148);
     bn::bwd_apply_kernel<<<grid2, g.ppb * g.cgs, 0, s>>>(dy, ym, z, coef, coef2, g, mask_mode,
-                                                         static_cast<__nv_bfloat16*>(dz_pad), dz_halo_w,
-                                                         static_cast<__nv_bfloat16*>(g_out_pad));
+                                                         static_cast<act_t*>(dz_pad), dz_halo_w,
+                                                         static_cast<act_t*>(g_out_pad));
   }
   rd::count_launch(3);
   return rd::check_launch("rd_bn_act_bwd");
 }
 
-int rd_channel_sums_nhwc_bf16(const void* x_pad, int N, int H, int W, int C, float* sums, void* workspace,
+int RD_ACT_FN(rd_channel_sums_nhwc_, )(const void* x_pad, int N, int H, int W, int C, float* sums, void* workspace,
                               size_t workspace_bytes, rd_stream_t stream) {
   if (bn::check_shape("rd_channel_sums", N, H, W, C)) return 1;
   RD_REQUIRE(x_pad && sums && workspace, "rd_channel_sums: null pointer");
@@ -556,7 +557,7 @@ int rd_channel_sums_nhwc_bf16(const void* x_pad, int N, int H, int W, int C, flo
   cudaStream_t s = rd::as_stream(stream);
   float* partial = static_cast<float*>(workspace);
   float* coef = partial + (size_t)bn::MAX_BLOCKS * 2 * C;
-  bn::stats_kernel<<<grid, g.ppb * g.cgs, 0, s>>>(static_cast<const __nv_bfloat16*>(x_pad), g, 1, partial);
+  bn::stats_kernel<<<grid, g.ppb * g.cgs, 0, s>>>(static_cast<const act_t*>(x_pad), g, 1, partial);
   bn::fwd_finalize_kernel<<<(C + 7) / 8, 256, 0, s>>>(partial, grid, C, (double)N * H * W, nullptr, nullptr, 1e-5f,
                                                           0.f, nullptr, nullptr, coef);
   RD_CUDA(cudaMemcpyAsync(sums, coef + 5 * (size_t)C, (size_t)C * sizeof(float), cudaMemcpyDeviceToDevice, s));
@@ -564,19 +565,19 @@ int rd_channel_sums_nhwc_bf16(const void* x_pad, int N, int H, int W, int C, flo
   return rd::check_launch("rd_channel_sums");
 }
 
-int rd_add_nhwc_bf16(const void* x0_pad, const void* x1_pad, void* y_pad, int N, int H, int W, int C,
+int RD_ACT_FN(rd_add_nhwc_, )(const void* x0_pad, const void* x1_pad, void* y_pad, int N, int H, int W, int C,
                      rd_stream_t stream) {
-  if (bn::check_shape("rd_add_nhwc_bf16", N, H, W, C)) return 1;
-  RD_REQUIRE(x0_pad && x1_pad && y_pad, "rd_add_nhwc_bf16: null pointer");
+  if (bn::check_shape(RD_ACT_FN_STR(rd_add_nhwc_, ) "", N, H, W, C)) return 1;
+  RD_REQUIRE(x0_pad && x1_pad && y_pad, RD_ACT_FN_STR(rd_add_nhwc_, ) ": null pointer");
   if (rd_check_device()) return 1;
   const bn::Geo g = bn::make_geo(N, H, W, C);
   const int64_t units = (int64_t)g.N * g.H * g.nseg;
   const int grid = (int)(units < 8 * 148 ? units : 8 * 148);
-  bn::add_kernel<<<grid, g.ppb * g.cgs, 0, rd::as_stream(stream)>>>(static_cast<const __nv_bfloat16*>(x0_pad),
-                                                                    static_cast<const __nv_bfloat16*>(x1_pad),
-                                                                    static_cast<__nv_bfloat16*>(y_pad), g);
+  bn::add_kernel<<<grid, g.ppb * g.cgs, 0, rd::as_stream(stream)>>>(static_cast<const act_t*>(x0_pad),
+                                                                    static_cast<const act_t*>(x1_pad),
+                                                                    static_cast<act_t*>(y_pad), g);
   rd::count_launch();
-  return rd::check_launch("rd_add_nhwc_bf16");
+  return rd::check_launch(RD_ACT_FN_STR(rd_add_nhwc_, ) "");
 }
 
 }  // extern "C"

@@ -22,16 +22,16 @@
 //   warps 2-5 epilogue: tcgen05.ld -> x scale + shift (+ residual) -> ReLU -> bf16 ->
 //       conv: 128B-swizzled staging tile -> TMA store into the interior view of the haloed output
 //       deconv: each thread owns S consecutive output pixels -> direct 16-byte stores
-#include <cuda_bf16.h>
 #include <stdlib.h>
 #include <string.h>
 
 #include "../../include/rangedet_b200.h"
+#include "act_type.cuh"
 #include "rd_common.cuh"
 #include "tc_common.cuh"
 #include "tma_common.cuh"
 
-namespace conv {
+namespace RD_ACT_NS(conv) {
 
 constexpr int TM = 128;               // GEMM rows per tile
 constexpr int KC = 64;                // channels per TMA box / swizzle atom
@@ -102,8 +102,8 @@ template <bool PROF>
 __global__ void __launch_bounds__(NTHREADS, 1)
 conv_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_w,
             const __grid_constant__ CUtensorMap tm_y, const float* __restrict__ scale,
-            const float* __restrict__ shift, const __nv_bfloat16* __restrict__ residual,
-            __nv_bfloat16* __restrict__ y_interior, const __grid_constant__ Params P) {
+            const float* __restrict__ shift, const act_t* __restrict__ residual,
+            act_t* __restrict__ y_interior, const __grid_constant__ Params P) {
   extern __shared__ unsigned char smem_raw[];
   unsigned char* base = smem_raw + ((1024u - (tc::smem_u32(smem_raw) & 1023u)) & 1023u);
   const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
@@ -238,7 +238,7 @@ conv_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CU
     // descriptors that differ only in their start-address field, four back-to-back MMAs per use.
     const int p = warp == 1 ? 0 : 1;
     if (p < npipes) {
-      const uint32_t idesc = tc::make_idesc_bf16(TM, P.Cout);
+      const uint32_t idesc = tc::make_idesc_f16kind(TM, P.Cout, RD_ACT_MMA_FMT);
       const uint64_t desc_hi = tc::make_smem_desc(0, 0, 1024, tc::LAYOUT_SW128);  // everything but the address
       const uint32_t ringA_lo = tc::smem_u32(base + P.a_off[p]) >> 4, ringB_lo = tc::smem_u32(ringB) >> 4;
       const uint32_t slot_lo = (uint32_t)P.slot_bytes >> 4, btile_lo = (uint32_t)b_tile >> 4;
@@ -361,14 +361,12 @@ conv_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CU
                 float ra = 0.f, rb = 0.f;
                 if (P.has_residual && in_img) {
                   const uint32_t w = reinterpret_cast<const uint32_t*>(&rv[j])[e];
-                  const __nv_bfloat162 r2 = *reinterpret_cast<const __nv_bfloat162*>(&w);
-                  ra = __bfloat162float(r2.x);
-                  rb = __bfloat162float(r2.y);
+                  act::unpack2(w, ra, rb);
                 }
                 if (!P.res_after_relu) { a += ra; b += rb; }
                 if (P.relu) { a = fmaxf(a, 0.f); b = fmaxf(b, 0.f); }
                 if (P.res_after_relu) { a += ra; b += rb; }
-                pk[e] = tc::pack_bf16x2(a, b);
+                pk[e] = act::pack2(a, b);
               }
               if (P.deconv_s) {
                 if (in_img) *reinterpret_cast<uint4*>(y_interior + ooff + c0 + j * 8) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
@@ -561,23 +559,23 @@ static int run(int mode, const void* x_pad, const void* w_packed, const float* s
     const uint64_t s[3] = {(uint64_t)Cin * 2, Wp_in * Cin * 2, Hp * Wp_in * Cin * 2};
     const uint32_t b[4] = {(uint32_t)KC, (uint32_t)box_px, 1u, 1u};
     const uint32_t es[4] = {1u, (uint32_t)P.in_stride_w, 1u, 1u};
-    if (tma::make_map_es(&tm_x, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, x_pad, 4, d, s, b, es, CU_TENSOR_MAP_SWIZZLE_128B)) return 1;
+    if (tma::make_map_es(&tm_x, RD_ACT_TMA_TYPE, x_pad, 4, d, s, b, es, CU_TENSOR_MAP_SWIZZLE_128B)) return 1;
   }
   {  // packed weights (Cin, Cout, taps)
     const uint64_t d[3] = {(uint64_t)Cin, (uint64_t)Cout, (uint64_t)P.ntaps};
     const uint64_t s[2] = {(uint64_t)Cin * 2, (uint64_t)Cin * Cout * 2};
     const uint32_t b[3] = {(uint32_t)KC, (uint32_t)Cout, 1u};
-    if (tma::make_map(&tm_w, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, w_packed, 3, d, s, b, CU_TENSOR_MAP_SWIZZLE_128B)) return 1;
+    if (tma::make_map(&tm_w, RD_ACT_TMA_TYPE, w_packed, 3, d, s, b, CU_TENSOR_MAP_SWIZZLE_128B)) return 1;
   }
   char* y_int = static_cast<char*>(y_pad) + ((Wp_out + 1) * y_ctotal + y_coff) * 2;  // interior origin of the haloed output
   {  // interior view (C, W_out, H, N): stores are clipped at W_out, never touch the halo
     const uint64_t d[4] = {(uint64_t)Cout, (uint64_t)W_out, (uint64_t)H, (uint64_t)N};
     const uint64_t s[3] = {(uint64_t)y_ctotal * 2, Wp_out * y_ctotal * 2, Hp * Wp_out * y_ctotal * 2};
     const uint32_t b[4] = {(uint32_t)KC, (uint32_t)TM, 1u, 1u};
-    if (tma::make_map(&tm_y, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, y_int, 4, d, s, b, CU_TENSOR_MAP_SWIZZLE_128B)) return 1;
+    if (tma::make_map(&tm_y, RD_ACT_TMA_TYPE, y_int, 4, d, s, b, CU_TENSOR_MAP_SWIZZLE_128B)) return 1;
   }
-  const __nv_bfloat16* res = nullptr;
-  if (residual_pad) res = static_cast<const __nv_bfloat16*>(residual_pad) + (Wp_out + 1) * Cout;
+  const act_t* res = nullptr;
+  if (residual_pad) res = static_cast<const act_t*>(residual_pad) + (Wp_out + 1) * Cout;
   int dev = 0, sms = 0;
   RD_CUDA(cudaGetDevice(&dev));
   RD_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
@@ -592,7 +590,7 @@ static int run(int mode, const void* x_pad, const void* w_packed, const float* s
     RD_CUDA(cudaMemsetAsync(d_prof, 0, 1024 * 16 * sizeof(long long), stream));
     P.prof = d_prof;
     conv_kernel<true><<<grid, NTHREADS, smem, stream>>>(tm_x, tm_w, tm_y, scale, shift, res,
-                                                        reinterpret_cast<__nv_bfloat16*>(y_int), P);
+                                                        reinterpret_cast<act_t*>(y_int), P);
     RD_CUDA(cudaStreamSynchronize(stream));
     static long long h[1024 * 16];
     RD_CUDA(cudaMemcpy(h, d_prof, sizeof(long long) * 16 * grid, cudaMemcpyDeviceToHost));
@@ -608,31 +606,32 @@ static int run(int mode, const void* x_pad, const void* w_packed, const float* s
             m[5] / tiles, m[7] / tiles, m[6] / tiles, m[8] / tiles, m[9] / tiles, m[10] / tiles, m[11] / tiles);
   } else {
     conv_kernel<false><<<grid, NTHREADS, smem, stream>>>(tm_x, tm_w, tm_y, scale, shift, res,
-                                                         reinterpret_cast<__nv_bfloat16*>(y_int), P);
+                                                         reinterpret_cast<act_t*>(y_int), P);
   }
   rd::count_launch();
   return rd::check_launch("rd_conv");
 }
 
-}  // namespace conv
+}  // namespace conv_<storage type>
+namespace conv = RD_ACT_NS(conv);
 
 extern "C" {
 
-int rd_conv2d_nhwc_bf16(const void* x_pad, const void* w_packed, const float* scale, const float* shift,
+int RD_ACT_FN(rd_conv2d_nhwc_, )(const void* x_pad, const void* w_packed, const float* scale, const float* shift,
                         const void* residual_pad, void* y_pad, int N, int H, int W, int Cin, int Cout, int ksize,
                         int stride_w, int relu, rd_stream_t stream) {
   return conv::run(0, x_pad, w_packed, scale, shift, residual_pad, y_pad, N, H, W, Cin, Cout, ksize, stride_w, relu, 0,
                    rd::as_stream(stream));
 }
 
-int rd_conv2d_nhwc_bf16_slice(const void* x_pad, const void* w_packed, const float* scale, const float* shift,
+int RD_ACT_FN(rd_conv2d_nhwc_, _slice)(const void* x_pad, const void* w_packed, const float* scale, const float* shift,
                               void* y_pad, int N, int H, int W, int Cin, int Cout, int ksize, int stride_w, int relu,
                               int y_ctotal, int y_coff, rd_stream_t stream) {
   return conv::run(0, x_pad, w_packed, scale, shift, nullptr, y_pad, N, H, W, Cin, Cout, ksize, stride_w, relu, 0,
                    rd::as_stream(stream), y_ctotal, y_coff);
 }
 
-int rd_deconv2d_nhwc_bf16(const void* x_pad, const void* w_packed, const float* scale, const float* shift,
+int RD_ACT_FN(rd_deconv2d_nhwc_, )(const void* x_pad, const void* w_packed, const float* scale, const float* shift,
                           const void* residual_pad, void* y_pad, int N, int H, int W, int Cin, int Cout, int kw,
                           int relu, rd_stream_t stream) {
   RD_REQUIRE(kw == 8 || kw == 4 || kw == 3,

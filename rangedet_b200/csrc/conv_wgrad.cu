@@ -24,16 +24,16 @@
 //   warp 0 TMA producer | warp 1 MMA issuer | warps 2-5 final TMEM -> workspace
 // RD_WGRAD_NOSWZ=1 selects the no-swizzle canonical layout instead (8-channel TMA boxes; the layout
 // tests/test_gpu_parity.py::test_tc_probe validates) -- a diagnostic cross-check of the SW128 path.
-#include <cuda_bf16.h>
 #include <stdlib.h>
 #include <string.h>
 
 #include "../../include/rangedet_b200.h"
+#include "act_type.cuh"
 #include "rd_common.cuh"
 #include "tc_common.cuh"
 #include "tma_common.cuh"
 
-namespace wg {
+namespace RD_ACT_NS(wg) {
 
 constexpr int TM = 128;        // pixels per K tile
 constexpr int NTHREADS = 192;
@@ -112,7 +112,7 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ C
     __syncwarp();
   } else if (warp == 1) {
     // ===== MMA issuer: converged warp, one elected lane issues =====
-    const uint32_t idesc = tc::make_idesc_bf16(128, P.CBJ, 1, 1);  // both operands MN-major
+    const uint32_t idesc = tc::make_idesc_f16kind(128, P.CBJ, RD_ACT_MMA_FMT, 1, 1);  // both operands MN-major
     // MN-major descriptors.  SW128: LBO = stride between 64-channel atoms, SBO = 1024 (8 pixel rows);
     // no swizzle: LBO = 128 (8 pixels x 16 B), SBO = stride between 8-channel chunks.
     const uint64_t a_hi = P.swz ? tc::make_smem_desc(0, (uint32_t)P.a_unit_bytes, 1024, tc::LAYOUT_SW128)
@@ -248,17 +248,20 @@ static int make_plan(Plan& P, int N, int H, int W, int CA, int CB, int ksize, in
   return 0;
 }
 
-}  // namespace wg
+}  // namespace wg_<storage type>
+namespace wg = RD_ACT_NS(wg);
 
 extern "C" {
 
+#ifndef RD_ACT_F16   // storage-type independent: defined once, by the bf16 pass
 size_t rd_conv2d_wgrad_workspace_bytes(int N, int H, int W, int CA, int CB, int ksize, int stride_w) {
   wg::Plan P;
   if (wg::make_plan(P, N, H, W, CA, CB, ksize, stride_w)) return 0;
   return (size_t)P.nsplit * P.ntaps * CA * CB * sizeof(float);
 }
+#endif
 
-int rd_conv2d_wgrad_nhwc_bf16(const void* a_pad, const void* b_pad, float* g, int N, int H, int W, int CA, int CB,
+int RD_ACT_FN(rd_conv2d_wgrad_nhwc_, )(const void* a_pad, const void* b_pad, float* g, int N, int H, int W, int CA, int CB,
                               int ksize, int stride_w, void* workspace, size_t workspace_bytes, rd_stream_t stream) {
   wg::Plan P;
   if (wg::make_plan(P, N, H, W, CA, CB, ksize, stride_w)) return 1;
@@ -273,14 +276,14 @@ int rd_conv2d_wgrad_nhwc_bf16(const void* a_pad, const void* b_pad, float* g, in
     const uint64_t d[4] = {(uint64_t)CA, Wa, Hp, (uint64_t)N};
     const uint64_t st[3] = {(uint64_t)CA * 2, Wa * CA * 2, Hp * Wa * CA * 2};
     const uint32_t b[4] = {(uint32_t)P.ch_unit, (uint32_t)wg::TM, 1u, 1u};
-    if (tma::make_map(&tm_a, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, a_pad, 4, d, st, b, sw)) return 1;
+    if (tma::make_map(&tm_a, RD_ACT_TMA_TYPE, a_pad, 4, d, st, b, sw)) return 1;
   }
   {
     const uint64_t d[4] = {(uint64_t)CB, Wb, Hp, (uint64_t)N};
     const uint64_t st[3] = {(uint64_t)CB * 2, Wb * CB * 2, Hp * Wb * CB * 2};
     const uint32_t b[4] = {(uint32_t)P.ch_unit, (uint32_t)P.b_box_px, 1u, 1u};
     const uint32_t es[4] = {1u, (uint32_t)stride_w, 1u, 1u};
-    if (tma::make_map_es(&tm_b, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, b_pad, 4, d, st, b, es, sw)) return 1;
+    if (tma::make_map_es(&tm_b, RD_ACT_TMA_TYPE, b_pad, 4, d, st, b, es, sw)) return 1;
   }
   const size_t smem = (size_t)P.nstages * P.stage_bytes + sizeof(wg::Misc) + 1024;
   RD_REQUIRE(smem <= 227 * 1024, "rd_conv2d_wgrad: shared memory layout exceeds 227 KB (%zu)", smem);

@@ -7,12 +7,11 @@
 // full 128-byte lines (a strided permute copy ran at 0.25 TB/s and was 12 % of the training step).
 //   chmap 0: dst channel = src channel
 //   chmap 1: tap-major <-> reference order: NHWC channel k*(C/9)+c  <->  NCHW channel c*9+k
-#include <cuda_bf16.h>
-
 #include "../../include/rangedet_b200.h"
+#include "act_type.cuh"
 #include "rd_common.cuh"
 
-namespace lay {
+namespace RD_ACT_NS(lay) {
 
 constexpr int TP = 32;  // pixels per tile
 constexpr int TC = 64;  // channels per tile
@@ -27,7 +26,7 @@ __device__ __forceinline__ int map_channel(int c_nhwc, int C, int chmap) {
 // Tile = 64 pixels x 64 channels: 16-byte loads (8 channels of one pixel; a warp covers 4 pixels x 128 B),
 // transposed through shared memory, 16-byte stores (4 pixels of one channel; 16 lanes cover 256 contiguous bytes).
 constexpr int TP2 = 64;
-__global__ void __launch_bounds__(256) nhwc_to_nchw_kernel(const __nv_bfloat16* __restrict__ src, float* __restrict__ dst,
+__global__ void __launch_bounds__(256) nhwc_to_nchw_kernel(const act_t* __restrict__ src, float* __restrict__ dst,
                                                           int N, int H, int W, int Cs, int C, int chmap) {
   __shared__ float tile[TC][TP2 + 1];
   const int wt = blockIdx.x, h = blockIdx.y % H, n = blockIdx.y / H;
@@ -42,17 +41,16 @@ __global__ void __launch_bounds__(256) nhwc_to_nchw_kernel(const __nv_bfloat16* 
 #pragma unroll
       for (int i = 0; i < 8; ++i) f[i] = 0.f;
       if (w0 + p < W && c0 + ch < C) {
-        const __nv_bfloat16* q = src + srow + (int64_t)(w0 + p) * Cs + c0 + ch;
+        const act_t* q = src + srow + (int64_t)(w0 + p) * Cs + c0 + ch;
         if (vec_ld && c0 + ch + 8 <= Cs) {
           const uint4 v = __ldg(reinterpret_cast<const uint4*>(q));
           const uint32_t w4[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
-            f[2 * i] = __uint_as_float(w4[i] << 16);
-            f[2 * i + 1] = __uint_as_float(w4[i] & 0xffff0000u);
+            act::unpack2(w4[i], f[2 * i], f[2 * i + 1]);
           }
         } else {
-          for (int i = 0; i < 8 && c0 + ch + i < Cs; ++i) f[i] = __bfloat162float(q[i]);
+          for (int i = 0; i < 8 && c0 + ch + i < Cs; ++i) f[i] = act::to_float(q[i]);
         }
       }
 #pragma unroll
@@ -76,7 +74,7 @@ __global__ void __launch_bounds__(256) nhwc_to_nchw_kernel(const __nv_bfloat16* 
 }
 
 // src: NCHW fp32 [N][C][H][W]; dst: haloed NHWC bf16 [N][H+2][W+2][Cd] (interior, channels [0, C) written)
-__global__ void __launch_bounds__(256) nchw_to_nhwc_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst,
+__global__ void __launch_bounds__(256) nchw_to_nhwc_kernel(const float* __restrict__ src, act_t* __restrict__ dst,
                                                           int N, int H, int W, int C, int Cd, int chmap) {
   __shared__ float tile[TC][TP + 1];
   const int wt = blockIdx.x, h = blockIdx.y % H, n = blockIdx.y / H;
@@ -98,10 +96,9 @@ __global__ void __launch_bounds__(256) nchw_to_nhwc_kernel(const float* __restri
       if (w0 + p < W && c0 + 2 * cp < C) {
         const float a = tile[2 * cp][p];
         if (c0 + 2 * cp + 1 < C) {
-          *reinterpret_cast<__nv_bfloat162*>(dst + drow + (int64_t)(w0 + p) * Cd + c0 + 2 * cp) =
-              __floats2bfloat162_rn(a, tile[2 * cp + 1][p]);
+          *reinterpret_cast<uint32_t*>(dst + drow + (int64_t)(w0 + p) * Cd + c0 + 2 * cp) = act::pack2(a, tile[2 * cp + 1][p]);
         } else {
-          dst[drow + (int64_t)(w0 + p) * Cd + c0 + 2 * cp] = __float2bfloat16_rn(a);
+          dst[drow + (int64_t)(w0 + p) * Cd + c0 + 2 * cp] = act::from_float(a);
         }
       }
     }
@@ -109,36 +106,37 @@ __global__ void __launch_bounds__(256) nchw_to_nhwc_kernel(const float* __restri
   }
 }
 
-}  // namespace lay
+}  // namespace lay_<storage type>
+namespace lay = RD_ACT_NS(lay);
 
 extern "C" {
 
-int rd_nhwc_bf16_to_nchw_f32(const void* src_pad, float* dst, int N, int H, int W, int C_src, int C, int chmap,
+int RD_ACT_FN(rd_nhwc_, _to_nchw_f32)(const void* src_pad, float* dst, int N, int H, int W, int C_src, int C, int chmap,
                              rd_stream_t stream) {
-  RD_REQUIRE(src_pad && dst, "rd_nhwc_bf16_to_nchw_f32: null pointer");
-  RD_REQUIRE(N > 0 && H > 0 && W > 0 && C > 0 && C <= C_src && C_src % 2 == 0, "rd_nhwc_bf16_to_nchw_f32: bad shape");
-  RD_REQUIRE(chmap == 0 || (chmap == 1 && C % 9 == 0), "rd_nhwc_bf16_to_nchw_f32: chmap 1 needs C %% 9 == 0");
-  RD_REQUIRE((int64_t)N * H <= 65535, "rd_nhwc_bf16_to_nchw_f32: N*H too large");
+  RD_REQUIRE(src_pad && dst, RD_ACT_FN_STR(rd_nhwc_, _to_nchw_f32) ": null pointer");
+  RD_REQUIRE(N > 0 && H > 0 && W > 0 && C > 0 && C <= C_src && C_src % 2 == 0, RD_ACT_FN_STR(rd_nhwc_, _to_nchw_f32) ": bad shape");
+  RD_REQUIRE(chmap == 0 || (chmap == 1 && C % 9 == 0), RD_ACT_FN_STR(rd_nhwc_, _to_nchw_f32) ": chmap 1 needs C %% 9 == 0");
+  RD_REQUIRE((int64_t)N * H <= 65535, RD_ACT_FN_STR(rd_nhwc_, _to_nchw_f32) ": N*H too large");
   if (rd_check_device()) return 1;
   dim3 grid((W + lay::TP2 - 1) / lay::TP2, N * H);
-  lay::nhwc_to_nchw_kernel<<<grid, 256, 0, rd::as_stream(stream)>>>(static_cast<const __nv_bfloat16*>(src_pad), dst, N, H, W,
+  lay::nhwc_to_nchw_kernel<<<grid, 256, 0, rd::as_stream(stream)>>>(static_cast<const act_t*>(src_pad), dst, N, H, W,
                                                                     C_src, C, chmap);
   rd::count_launch();
-  return rd::check_launch("rd_nhwc_bf16_to_nchw_f32");
+  return rd::check_launch(RD_ACT_FN_STR(rd_nhwc_, _to_nchw_f32) "");
 }
 
-int rd_nchw_f32_to_nhwc_bf16(const float* src, void* dst_pad, int N, int H, int W, int C, int C_dst, int chmap,
+int RD_ACT_FN(rd_nchw_f32_to_nhwc_, )(const float* src, void* dst_pad, int N, int H, int W, int C, int C_dst, int chmap,
                              rd_stream_t stream) {
-  RD_REQUIRE(src && dst_pad, "rd_nchw_f32_to_nhwc_bf16: null pointer");
-  RD_REQUIRE(N > 0 && H > 0 && W > 0 && C > 0 && C <= C_dst && C_dst % 2 == 0, "rd_nchw_f32_to_nhwc_bf16: bad shape");
-  RD_REQUIRE(chmap == 0 || (chmap == 1 && C % 9 == 0), "rd_nchw_f32_to_nhwc_bf16: chmap 1 needs C %% 9 == 0");
-  RD_REQUIRE((int64_t)N * H <= 65535, "rd_nchw_f32_to_nhwc_bf16: N*H too large");
+  RD_REQUIRE(src && dst_pad, RD_ACT_FN_STR(rd_nchw_f32_to_nhwc_, ) ": null pointer");
+  RD_REQUIRE(N > 0 && H > 0 && W > 0 && C > 0 && C <= C_dst && C_dst % 2 == 0, RD_ACT_FN_STR(rd_nchw_f32_to_nhwc_, ) ": bad shape");
+  RD_REQUIRE(chmap == 0 || (chmap == 1 && C % 9 == 0), RD_ACT_FN_STR(rd_nchw_f32_to_nhwc_, ) ": chmap 1 needs C %% 9 == 0");
+  RD_REQUIRE((int64_t)N * H <= 65535, RD_ACT_FN_STR(rd_nchw_f32_to_nhwc_, ) ": N*H too large");
   if (rd_check_device()) return 1;
   dim3 grid((W + lay::TP - 1) / lay::TP, N * H);
-  lay::nchw_to_nhwc_kernel<<<grid, 256, 0, rd::as_stream(stream)>>>(src, static_cast<__nv_bfloat16*>(dst_pad), N, H, W, C,
+  lay::nchw_to_nhwc_kernel<<<grid, 256, 0, rd::as_stream(stream)>>>(src, static_cast<act_t*>(dst_pad), N, H, W, C,
                                                                     C_dst, chmap);
   rd::count_launch();
-  return rd::check_launch("rd_nchw_f32_to_nhwc_bf16");
+  return rd::check_launch(RD_ACT_FN_STR(rd_nchw_f32_to_nhwc_, ) "");
 }
 
 }  // extern "C"

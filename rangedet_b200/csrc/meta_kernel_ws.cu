@@ -346,8 +346,8 @@ meta_ws_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant_
                 const int c = half * 32 + j * 8 + 2 * e;
                 float a = fmaf(d[j * 8 + 2 * e] * v[j * 8 + 2 * e], __ldg(esc + c), __ldg(esh + c));
                 float bb = fmaf(d[j * 8 + 2 * e + 1] * v[j * 8 + 2 * e + 1], __ldg(esc + c + 1), __ldg(esh + c + 1));
-                if (ep_relu) { a = fmaxf(a, 0.f); bb = fmaxf(bb, 0.f); }
-                pk[e] = tc::pack_bf16x2(a, bb);
+                if (ep_relu & 1) { a = fmaxf(a, 0.f); bb = fmaxf(bb, 0.f); }
+                pk[e] = (ep_relu & 2) ? tc::pack_f16x2(a, bb) : tc::pack_bf16x2(a, bb);   // bit 1: fp16 storage
               }
               const int chunk = half * 4 + j;
               *reinterpret_cast<uint4*>(ot + px * 128 + ((chunk ^ (px & 7)) << 4)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
@@ -558,5 +558,15 @@ extern "C" int rd_meta_kernel_fwd_nhwc_bf16(const float* data, const float* coor
   RD_REQUIRE(data && coord && w0 && b0 && w1 && b1 && scale && shift && y_pad, "rd_meta_kernel_fwd_nhwc_bf16: null pointer");
   RD_REQUIRE(B > 0 && H > 0 && W > 0, "rd_meta_kernel_fwd_nhwc_bf16: bad shape");
   if (rd_check_device()) return 1;
-  return mkws::launch(2, data, y_pad, coord, w0, b0, w1, b1, scale, shift, relu, B, C, H, W, rd::as_stream(stream));
+  return mkws::launch(2, data, y_pad, coord, w0, b0, w1, b1, scale, shift, relu ? 1 : 0, B, C, H, W, rd::as_stream(stream));
+}
+
+// Same kernel, output stored as fp16 (the reference's training storage type, config:35): bit 1 of the epilogue flag.
+extern "C" int rd_meta_kernel_fwd_nhwc_f16(const float* data, const float* coord, const float* w0, const float* b0,
+                                           const float* w1, const float* b1, const float* scale, const float* shift,
+                                           int relu, void* y_pad, int B, int C, int H, int W, rd_stream_t stream) {
+  RD_REQUIRE(data && coord && w0 && b0 && w1 && b1 && scale && shift && y_pad, "rd_meta_kernel_fwd_nhwc_f16: null pointer");
+  RD_REQUIRE(B > 0 && H > 0 && W > 0, "rd_meta_kernel_fwd_nhwc_f16: bad shape");
+  if (rd_check_device()) return 1;
+  return mkws::launch(2, data, y_pad, coord, w0, b0, w1, b1, scale, shift, (relu ? 1 : 0) | 2, B, C, H, W, rd::as_stream(stream));
 }

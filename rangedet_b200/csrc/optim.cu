@@ -13,9 +13,8 @@
 //                           rescale / clip are read from DEVICE memory so a captured CUDA graph follows the
 //                           learning-rate schedule.
 // All three are HBM-bound streaming kernels (index maps are int32, read once).
-#include <cuda_bf16.h>
-
 #include "../../include/rangedet_b200.h"
+#include "act_type.cuh"
 #include "rd_common.cuh"
 
 namespace {
@@ -23,7 +22,7 @@ namespace {
 constexpr int OPT_THREADS = 256;
 
 __global__ void __launch_bounds__(OPT_THREADS)
-gather_bf16_kernel(const float* __restrict__ src, const int* __restrict__ idx, __nv_bfloat16* __restrict__ dst,
+gather_act_kernel(const float* __restrict__ src, const int* __restrict__ idx, act_t* __restrict__ dst,
                    int64_t n) {
   const int64_t stride = (int64_t)gridDim.x * OPT_THREADS * 2;
   for (int64_t i = ((int64_t)blockIdx.x * OPT_THREADS + threadIdx.x) * 2; i < n; i += stride) {
@@ -32,9 +31,9 @@ gather_bf16_kernel(const float* __restrict__ src, const int* __restrict__ idx, _
     const float v0 = i0 >= 0 ? __ldg(src + i0) : 0.f;
     const float v1 = i1 >= 0 ? __ldg(src + i1) : 0.f;
     if (i + 1 < n) {
-      *reinterpret_cast<__nv_bfloat162*>(dst + i) = __floats2bfloat162_rn(v0, v1);   // n even or tail handled below
+      *reinterpret_cast<uint32_t*>(dst + i) = act::pack2(v0, v1);   // n even or tail handled below
     } else {
-      dst[i] = __float2bfloat16_rn(v0);
+      dst[i] = act::from_float(v0);
     }
   }
 }
@@ -74,17 +73,18 @@ inline unsigned grid_for(int64_t n, int per_thread) {
 
 extern "C" {
 
-int rd_gather_f32_to_bf16(const float* src, const int* idx, void* dst, int64_t n, rd_stream_t stream) {
-  RD_REQUIRE(n >= 0, "rd_gather_f32_to_bf16: negative n");
+int RD_ACT_FN(rd_gather_f32_to_, )(const float* src, const int* idx, void* dst, int64_t n, rd_stream_t stream) {
+  RD_REQUIRE(n >= 0, RD_ACT_FN_STR(rd_gather_f32_to_, ) ": negative n");
   if (n == 0) return 0;
-  RD_REQUIRE(src && idx && dst, "rd_gather_f32_to_bf16: null pointer");
-  RD_REQUIRE((reinterpret_cast<uintptr_t>(dst) & 3) == 0, "rd_gather_f32_to_bf16: dst must be 4-byte aligned");
+  RD_REQUIRE(src && idx && dst, RD_ACT_FN_STR(rd_gather_f32_to_, ) ": null pointer");
+  RD_REQUIRE((reinterpret_cast<uintptr_t>(dst) & 3) == 0, RD_ACT_FN_STR(rd_gather_f32_to_, ) ": dst must be 4-byte aligned");
   if (rd_check_device()) return 1;
-  gather_bf16_kernel<<<grid_for(n, 2), OPT_THREADS, 0, rd::as_stream(stream)>>>(src, idx, static_cast<__nv_bfloat16*>(dst), n);
+  gather_act_kernel<<<grid_for(n, 2), OPT_THREADS, 0, rd::as_stream(stream)>>>(src, idx, static_cast<act_t*>(dst), n);
   rd::count_launch();
-  return rd::check_launch("rd_gather_f32_to_bf16");
+  return rd::check_launch(RD_ACT_FN_STR(rd_gather_f32_to_, ) "");
 }
 
+#ifndef RD_ACT_F16   // storage-type independent entry points: compiled once, in the bf16 pass
 int rd_gather_f32(const float* src, const int* idx, float* dst, int64_t n, rd_stream_t stream) {
   RD_REQUIRE(n >= 0, "rd_gather_f32: negative n");
   if (n == 0) return 0;
@@ -105,5 +105,6 @@ int rd_sgd_mom_update(float* weight, const float* grad, float* mom, const float*
   rd::count_launch();
   return rd::check_launch("rd_sgd_mom_update");
 }
+#endif  // RD_ACT_F16
 
 }  // extern "C"

@@ -2,6 +2,7 @@
 // Bit layouts follow the PTX ISA "tcgen05 matrix / instruction descriptors".
 #pragma once
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <stdint.h>
 
 namespace tc {
@@ -35,10 +36,15 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr, uint32_t 
 // ---- instruction descriptor (32 bit), kind::f16, fp32 accumulate ------------------------------
 // [4,6) D format (1 = f32) | [7,10) A format (0 f16, 1 bf16) | [10,13) B format | [13] negA | [14] negB
 // | [15] A major (0 = K) | [16] B major (0 = K) | [17,23) N >> 3 | [24,29) M >> 4
+// fmt: operand format of BOTH A and B (0 = f16, 1 = bf16)
+__host__ __device__ constexpr uint32_t make_idesc_f16kind(int M, int N, uint32_t fmt, int a_mn_major = 0,
+                                                          int b_mn_major = 0) {
+  return (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)a_mn_major << 15) |
+         ((uint32_t)b_mn_major << 16) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
 __host__ __device__ constexpr uint32_t make_idesc_bf16(int M, int N, int a_mn_major = 0,
                                                        int b_mn_major = 0) {
-  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)a_mn_major << 15) |
-         ((uint32_t)b_mn_major << 16) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+  return make_idesc_f16kind(M, N, 1u, a_mn_major, b_mn_major);
 }
 
 // ---- TMEM allocation (one warp, .sync.aligned) -------------------------------------------------
@@ -175,6 +181,10 @@ __device__ __forceinline__ void tmem_ld_x8(uint32_t taddr, float (&v)[8]) {
 // two floats -> packed bf16x2 (a in the low half = lower address)
 __device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
   __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&v);
+}
+__device__ __forceinline__ uint32_t pack_f16x2(float a, float b) {
+  __half2 v = __floats2half2_rn(a, b);
   return *reinterpret_cast<uint32_t*>(&v);
 }
 // split x = hi + lo (+ O(2^-17 |x|)) with hi, lo representable in bf16

@@ -31,7 +31,7 @@ def _pad64(c):
 class _Layer:
     """One conv / deconv with folded BN: packed bf16 weight + fp32 scale/shift (padded to 64/128 channels)."""
 
-    def __init__(self, P, wname, bnname=None, bias=None, deconv=False, device="cuda"):
+    def __init__(self, P, wname, bnname=None, bias=None, deconv=False, device="cuda", dtype=torch.bfloat16):
         w = P[wname + "_weight"].to(device)
         if deconv:
             ci, co = w.shape[0], w.shape[1]
@@ -39,7 +39,7 @@ class _Layer:
             co, ci = w.shape[0], w.shape[1]
         self.cin, self.cout = ci, co
         self.cin_p, self.cout_p = _pad64(ci), (64 if co <= 64 else 128)
-        self.w = (ops.pack_deconv_weight if deconv else ops.pack_conv_weight)(w, self.cin_p, self.cout_p)
+        self.w = (ops.pack_deconv_weight if deconv else ops.pack_conv_weight)(w, self.cin_p, self.cout_p, dtype)
         scale = torch.ones(self.cout_p, device=device)
         shift = torch.zeros(self.cout_p, device=device)
         if bnname is not None:
@@ -56,13 +56,13 @@ class _BufferPool:
     """Output activations are reused across forward calls: the kernels only ever write the interior,
     so a haloed buffer zero-initialised once keeps a valid zero halo forever."""
 
-    def __init__(self):
-        self.bufs = {}
+    def __init__(self, dtype=torch.bfloat16):
+        self.bufs, self.dtype = {}, dtype
 
     def get(self, key, shape, device):
         t = self.bufs.get(key)
         if t is None or tuple(t.shape) != tuple(shape):
-            t = torch.zeros(shape, device=device, dtype=torch.bfloat16)
+            t = torch.zeros(shape, device=device, dtype=self.dtype)
             self.bufs[key] = t
         return t
 
@@ -70,15 +70,16 @@ class _BufferPool:
 class DLABackbone(object):
     """DLABackbone(pBackbone).get_rpn_feature(data) of the reference, over torch tensors."""
 
-    def __init__(self, params, device="cuda", meta_impl=ops.IMPL_DEFAULT, fuse_meta=True):
+    def __init__(self, params, device="cuda", meta_impl=ops.IMPL_DEFAULT, fuse_meta=True, act_dtype=torch.bfloat16):
         self.P, self.device, self.meta_impl, self.fuse_meta = params, device, meta_impl, fuse_meta
+        self.act_dtype = act_dtype      # storage of activations / operands: bf16 (cfg-4) or fp16 (config:35)
         self.L = {}
-        self.pool = _BufferPool()
+        self.pool = _BufferPool(act_dtype)
 
     def layer(self, wname, bnname=None, deconv=False):
         key = wname
         if key not in self.L:
-            self.L[key] = _Layer(self.P, wname, bnname, deconv=deconv, device=self.device)
+            self.L[key] = _Layer(self.P, wname, bnname, deconv=deconv, device=self.device, dtype=self.act_dtype)
         return self.L[key]
 
     def conv_bn(self, x, wname, bnname, stride_w=1, relu=True, residual=None):
@@ -105,12 +106,12 @@ class DLABackbone(object):
             if wname + "#tapmajor" not in self.L:
                 Pt = {wname + "_weight": ops.tap_major_weight(P[wname + "_weight"].to(dev), C)}
                 Pt.update({k: v for k, v in P.items() if k.startswith(name + "aggregation_bn1")})
-                self.L[wname + "#tapmajor"] = _Layer(Pt, wname, name + "aggregation_bn1", device=dev)
+                self.L[wname + "#tapmajor"] = _Layer(Pt, wname, name + "aggregation_bn1", device=dev, dtype=self.act_dtype)
             l = self.L[wname + "#tapmajor"]
             return ops.conv2d_nhwc(m, l.w, l.scale, l.shift, relu=True, out=self.pool.get(wname, (B, H + 2, W + 2, l.cout_p), dev))
         m = ops.meta_kernel_forward(feat, coord, *args, impl=self.meta_impl)
         m = torch.relu_(m.mul_(s[None, :, None, None]).add_(b[None, :, None, None]))
-        return self.conv_bn(ops.to_nhwc_padded(m), wname, name + "aggregation_bn1")
+        return self.conv_bn(ops.to_nhwc_padded(m, dtype=self.act_dtype), wname, name + "aggregation_bn1")
 
     def basicblock(self, x, coord, name, stride_w, proj):  # dla_backbone.py:17-56
         if name in META_UNITS:
@@ -135,7 +136,7 @@ class DLABackbone(object):
     def get_rpn_feature(self, data, coord):
         """data (B,8,H,W) fp32, coord (B,3,H,W) fp32 -> [agg3+data (72 of 128 ch), agg2a (64), agg2 (128)]
         as haloed NHWC bf16 (backbone_factory :129-161, fpn_strides (1,2,4), add_data_sc)."""
-        x = ops.to_nhwc_padded(data, 64)
+        x = ops.to_nhwc_padded(data, 64, dtype=self.act_dtype)
         res1 = self.res_stage(x, coord, "res1", 1)
         res2a = self.res_stage(res1, None, "res2a", 2)
         res2 = self.res_stage(res2a, None, "res2", 2)
@@ -155,10 +156,10 @@ class DLABackbone(object):
 class RangeRpnHead(object):
     """get_fpn_output (builder.py:198-266): per level, un-shared cls / reg towers + 1x1 heads."""
 
-    def __init__(self, params, device="cuda"):
-        self.P, self.device = params, device
+    def __init__(self, params, device="cuda", act_dtype=torch.bfloat16):
+        self.P, self.device, self.act_dtype = params, device, act_dtype
         self.L = {}
-        self.pool = _BufferPool()
+        self.pool = _BufferPool(act_dtype)
 
     def _conv(self, x, l, name, relu):
         N, Hp, Wp, _ = x.shape
@@ -166,7 +167,7 @@ class RangeRpnHead(object):
 
     def _l(self, wname, bnname=None, bias=None):
         if wname not in self.L:
-            self.L[wname] = _Layer(self.P, wname, bnname, bias=bias, device=self.device)
+            self.L[wname] = _Layer(self.P, wname, bnname, bias=bias, device=self.device, dtype=self.act_dtype)
         return self.L[wname]
 
     def get_fpn_output(self, feats):
@@ -192,8 +193,8 @@ class GraphedForward(object):
     kernel launches of 0.05-0.5 ms: launching them from Python is host-bound).  Inputs are copied into
     static buffers; outputs are the static tensors of the captured run."""
 
-    def __init__(self, params, batch, H, W, device="cuda"):
-        self.backbone, self.head = DLABackbone(params, device), RangeRpnHead(params, device)
+    def __init__(self, params, batch, H, W, device="cuda", act_dtype=torch.bfloat16):
+        self.backbone, self.head = DLABackbone(params, device, act_dtype=act_dtype), RangeRpnHead(params, device, act_dtype)
         self.data = torch.zeros((batch, 8, H, W), device=device)
         self.coord = torch.zeros((batch, 3, H, W), device=device)
         for _ in range(2):  # warm-up: builds layers, buffers, function attributes outside the capture

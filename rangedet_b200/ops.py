@@ -67,10 +67,11 @@ def meta_kernel_forward(data, coord, w0, b0, w1, b1, impl=IMPL_DEFAULT):
     return out
 
 
-def meta_kernel_forward_nhwc(data, coord, w0, b0, w1, b1, scale, shift, relu=True, out=None):
+def meta_kernel_forward_nhwc(data, coord, w0, b0, w1, b1, scale, shift, relu=True, out=None, dtype=torch.bfloat16):
     """Meta-Kernel forward fused with the following per-channel scale/shift (+ReLU), written as haloed NHWC
-    bf16 (B,H+2,W+2,9C) with tap-major channels k*C+c; `scale`/`shift` are given in the REFERENCE order
-    (c*9+k, i.e. the BatchNorm(576) parameters of dla_backbone.py:93) and permuted here."""
+    bf16 / fp16 (B,H+2,W+2,9C) with tap-major channels k*C+c (storage type = that of `out`, else `dtype`);
+    `scale`/`shift` are given in the REFERENCE order (c*9+k, i.e. the BatchNorm(576) parameters of
+    dla_backbone.py:93) and permuted here."""
     data = _chk(data, "data", 4)
     coord = _chk(coord, "coord", 4)
     B, C, H, W = data.shape
@@ -80,9 +81,9 @@ def meta_kernel_forward_nhwc(data, coord, w0, b0, w1, b1, scale, shift, relu=Tru
     sc = scale.float().reshape(C, 9).t().contiguous().reshape(-1)   # (c*9+k) -> (k*C+c)
     sh = shift.float().reshape(C, 9).t().contiguous().reshape(-1)
     if out is None:
-        out = torch.zeros((B, H + 2, W + 2, 9 * C), device=data.device, dtype=torch.bfloat16)
+        out = torch.zeros((B, H + 2, W + 2, 9 * C), device=data.device, dtype=dtype)
     with torch.cuda.device(data.device):
-        st = _lib.lib().rd_meta_kernel_fwd_nhwc_bf16(_p(data), _p(coord), _p(w0), _p(b0), _p(w1), _p(b1), _p(sc), _p(sh),
+        st = _lib.act_fn("rd_meta_kernel_fwd_nhwc_bf16", out.dtype)(_p(data), _p(coord), _p(w0), _p(b0), _p(w1), _p(b1), _p(sc), _p(sh),
                                                      int(bool(relu)), _p(out), B, C, H, W, _stream())
     _lib.check(st, "meta_kernel_forward_nhwc")
     return out
@@ -465,12 +466,15 @@ def tma_probe(src, box_w, c0, c1, c2):
 # ------------------------------------------------------------------------------------------------
 # Convolutions (NHWC bf16, zero-haloed activations)
 # ------------------------------------------------------------------------------------------------
-def to_nhwc_padded(x_nchw, channels=None):
-    """(N,C,H,W) float -> haloed NHWC bf16 (N,H+2,W+2,C') with zero halo (and zero channel padding)."""
+ACT_DTYPES = (torch.bfloat16, torch.float16)   # storage types of activations / operands (csrc/act_type.cuh)
+
+
+def to_nhwc_padded(x_nchw, channels=None, dtype=torch.bfloat16):
+    """(N,C,H,W) float -> haloed NHWC bf16 / fp16 (N,H+2,W+2,C') with zero halo (and zero channel padding)."""
     N, C, H, W = x_nchw.shape
     Cp = channels or C
-    out = torch.zeros((N, H + 2, W + 2, Cp), device=x_nchw.device, dtype=torch.bfloat16)
-    out[:, 1:H + 1, 1:W + 1, :C] = x_nchw.permute(0, 2, 3, 1).to(torch.bfloat16)
+    out = torch.zeros((N, H + 2, W + 2, Cp), device=x_nchw.device, dtype=dtype)
+    out[:, 1:H + 1, 1:W + 1, :C] = x_nchw.permute(0, 2, 3, 1).to(dtype)
     return out
 
 
@@ -500,21 +504,21 @@ def pack_deconv_weight(w_iohw, cin=None, cout=None, dtype=torch.bfloat16):
 
 
 def _conv_common(x_pad, w_packed, scale, shift, residual_pad, out, w_out, what):
-    if x_pad.dtype != torch.bfloat16 or w_packed.dtype != torch.bfloat16 or not x_pad.is_cuda:
-        raise TypeError("%s expects CUDA bf16 tensors" % what)
+    if x_pad.dtype not in ACT_DTYPES or w_packed.dtype != x_pad.dtype or not x_pad.is_cuda:
+        raise TypeError("%s expects CUDA bf16 (or fp16) tensors of one storage type" % what)
     x_pad, w_packed = x_pad.contiguous(), w_packed.contiguous()
     N, Hp, Wp, Cin = x_pad.shape
     taps, Cout, Cin2 = w_packed.shape
     if Cin2 != Cin:
         raise ValueError("weight shape %s does not match input channels %d" % (tuple(w_packed.shape), Cin))
     if out is None:
-        out = torch.zeros((N, Hp, w_out + 2, Cout), device=x_pad.device, dtype=torch.bfloat16)
+        out = torch.zeros((N, Hp, w_out + 2, Cout), device=x_pad.device, dtype=x_pad.dtype)
     sc = scale.float().contiguous() if scale is not None else None
     sh = shift.float().contiguous() if shift is not None else None
     if residual_pad is not None:
         residual_pad = residual_pad.contiguous()
-        if tuple(residual_pad.shape) != (N, Hp, w_out + 2, Cout) or residual_pad.dtype != torch.bfloat16:
-            raise ValueError("residual must be haloed NHWC bf16 at output resolution with Cout channels")
+        if tuple(residual_pad.shape) != (N, Hp, w_out + 2, Cout) or residual_pad.dtype != x_pad.dtype:
+            raise ValueError("residual must be haloed NHWC (storage type of x) at output resolution with Cout channels")
     return x_pad, w_packed, sc, sh, residual_pad, out
 
 
@@ -528,7 +532,7 @@ def conv2d_nhwc(x_pad, w_packed, scale=None, shift=None, relu=False, residual_pa
     x_pad, w_packed, sc, sh, residual_pad, out = _conv_common(x_pad, w_packed, scale, shift, residual_pad, out,
                                                               W // stride_w, "conv2d_nhwc")
     with torch.cuda.device(x_pad.device):
-        st = _lib.lib().rd_conv2d_nhwc_bf16(_p(x_pad), _p(w_packed), _p(sc) if sc is not None else None,
+        st = _lib.act_fn("rd_conv2d_nhwc_bf16", x_pad.dtype)(_p(x_pad), _p(w_packed), _p(sc) if sc is not None else None,
                                             _p(sh) if sh is not None else None,
                                             _p(residual_pad) if residual_pad is not None else None, _p(out),
                                             N, H, W, Cin, w_packed.shape[1], 3 if taps == 9 else 1, int(stride_w),
@@ -541,13 +545,13 @@ def conv2d_nhwc_slice(x_pad, w_packed, out, c_off, relu=False, stride_w=1):
     """conv(x) written into channels [c_off, c_off + Cout) of the haloed NHWC bf16 tensor `out`."""
     N, Hp, Wp, Cin = x_pad.shape
     taps, Cout, Cin2 = w_packed.shape
-    if taps not in (1, 9) or Cin2 != Cin or x_pad.dtype != torch.bfloat16 or out.dtype != torch.bfloat16:
+    if taps not in (1, 9) or Cin2 != Cin or x_pad.dtype not in ACT_DTYPES or out.dtype != x_pad.dtype or w_packed.dtype != x_pad.dtype:
         raise ValueError("conv2d_nhwc_slice: bad operands")
     H, W = Hp - 2, Wp - 2
     if tuple(out.shape[:3]) != (N, Hp, W // stride_w + 2) or not out.is_contiguous():
         raise ValueError("conv2d_nhwc_slice: output shape %s does not match" % (tuple(out.shape),))
     with torch.cuda.device(x_pad.device):
-        st = _lib.lib().rd_conv2d_nhwc_bf16_slice(_p(x_pad.contiguous()), _p(w_packed.contiguous()), None, None, _p(out), N, H,
+        st = _lib.act_fn("rd_conv2d_nhwc_bf16_slice", x_pad.dtype)(_p(x_pad.contiguous()), _p(w_packed.contiguous()), None, None, _p(out), N, H,
                                                   W, Cin, Cout, 3 if taps == 9 else 1, int(stride_w), int(bool(relu)),
                                                   out.shape[3], int(c_off), _stream())
     _lib.check(st, "conv2d_nhwc_slice")
@@ -566,7 +570,7 @@ def deconv2d_nhwc(x_pad, w_packed, scale=None, shift=None, relu=False, residual_
     x_pad, w_packed, sc, sh, residual_pad, out = _conv_common(x_pad, w_packed, scale, shift, residual_pad, out,
                                                               W * (4 if kw == 8 else 2), "deconv2d_nhwc")
     with torch.cuda.device(x_pad.device):
-        st = _lib.lib().rd_deconv2d_nhwc_bf16(_p(x_pad), _p(w_packed), _p(sc) if sc is not None else None,
+        st = _lib.act_fn("rd_deconv2d_nhwc_bf16", x_pad.dtype)(_p(x_pad), _p(w_packed), _p(sc) if sc is not None else None,
                                               _p(sh) if sh is not None else None,
                                               _p(residual_pad) if residual_pad is not None else None, _p(out),
                                               N, H, W, Cin, w_packed.shape[1], kw, int(bool(relu)), _stream())
@@ -596,9 +600,11 @@ def _workspace(nbytes, device, tag="ws"):
     return t
 
 
-def _chk_nhwc(t, name):
-    if t.dtype != torch.bfloat16 or not t.is_cuda or t.dim() != 4 or not t.is_contiguous():
-        raise TypeError("%s must be a contiguous CUDA bf16 haloed NHWC tensor" % name)
+def _chk_nhwc(t, name, like=None):
+    if t.dtype not in ACT_DTYPES or not t.is_cuda or t.dim() != 4 or not t.is_contiguous():
+        raise TypeError("%s must be a contiguous CUDA bf16 / fp16 haloed NHWC tensor" % name)
+    if like is not None and t.dtype != like.dtype:
+        raise TypeError("%s is stored as %s but its companion tensor as %s" % (name, t.dtype, like.dtype))
 
 
 def conv2d_wgrad(a_pad, b_pad, ksize, stride_w=1, out=None):
@@ -606,7 +612,7 @@ def conv2d_wgrad(a_pad, b_pad, ksize, stride_w=1, out=None):
     a_pad (N,H+2,W+2,CA) and b_pad (N,H+2,W*stride_w+2,CB): haloed NHWC bf16.  With A = grad of the conv
     output and B = the conv input this is the gradient of the packed forward weight [tap][Cout][Cin]."""
     _chk_nhwc(a_pad, "a_pad")
-    _chk_nhwc(b_pad, "b_pad")
+    _chk_nhwc(b_pad, "b_pad", a_pad)
     N, Hp, Wp, CA = a_pad.shape
     H, W = Hp - 2, Wp - 2
     CB = b_pad.shape[3]
@@ -623,7 +629,7 @@ def conv2d_wgrad(a_pad, b_pad, ksize, stride_w=1, out=None):
         raise ValueError("conv2d_wgrad: out must be a contiguous float32 tensor of %d elements" % (ksize * ksize * CA * CB))
     g = g.view(ksize * ksize, CA, CB)
     with torch.cuda.device(a_pad.device):
-        st = L.rd_conv2d_wgrad_nhwc_bf16(_p(a_pad), _p(b_pad), _p(g), N, H, W, CA, CB, ksize, stride_w, _p(ws), nb,
+        st = _lib.act_fn("rd_conv2d_wgrad_nhwc_bf16", a_pad.dtype)(_p(a_pad), _p(b_pad), _p(g), N, H, W, CA, CB, ksize, stride_w, _p(ws), nb,
                                          _stream())
     _lib.check(st, "conv2d_wgrad")
     return g
@@ -645,7 +651,7 @@ def bn_train_stats(z_pad, gamma=None, beta=None, moving_mean=None, moving_var=No
     ws = _workspace(nb, z_pad.device, "bn")
     opt = lambda t: _p(t) if t is not None else None
     with torch.cuda.device(z_pad.device):
-        st = L.rd_bn_train_stats_nhwc_bf16(_p(z_pad), N, Hp - 2, Wp - 2, C, opt(gamma), opt(beta), eps, momentum,
+        st = _lib.act_fn("rd_bn_train_stats_nhwc_bf16", z_pad.dtype)(_p(z_pad), N, Hp - 2, Wp - 2, C, opt(gamma), opt(beta), eps, momentum,
                                            opt(moving_mean), opt(moving_var), _p(coef), _p(ws), nb, _stream())
     _lib.check(st, "bn_train_stats")
     return coef
@@ -657,14 +663,14 @@ def bn_act_fwd(z_pad, coef, relu=True, res_before=None, res_after=None, out=None
     N, Hp, Wp, C = z_pad.shape
     for r in (res_before, res_after):
         if r is not None:
-            _chk_nhwc(r, "residual")
+            _chk_nhwc(r, "residual", z_pad)
             if r.shape != z_pad.shape:
                 raise ValueError("bn_act_fwd: residual shape %s != %s" % (tuple(r.shape), tuple(z_pad.shape)))
     if out is None:
         out = torch.zeros_like(z_pad)
     opt = lambda t: _p(t) if t is not None else None
     with torch.cuda.device(z_pad.device):
-        st = _lib.lib().rd_bn_act_fwd_nhwc_bf16(_p(z_pad), _p(coef), opt(res_before), opt(res_after), _p(out), N, Hp - 2,
+        st = _lib.act_fn("rd_bn_act_fwd_nhwc_bf16", z_pad.dtype)(_p(z_pad), _p(coef), opt(res_before), opt(res_after), _p(out), N, Hp - 2,
                                                 Wp - 2, C, int(bool(relu)), _stream())
     _lib.check(st, "bn_act_fwd")
     return out
@@ -675,13 +681,13 @@ def bn_act_bwd(dy_pad, z_pad, coef, mask_mode, y_mask=None, dz_halo_w=1, dz_out=
     """Backward of bn_act_fwd w.r.t. z, gamma, beta (and the masked gradient g that flows into res_before).
     Returns (dz, dgamma, dbeta, g or None).  dz has a W halo of dz_halo_w pixels."""
     _chk_nhwc(dy_pad, "dy_pad")
-    _chk_nhwc(z_pad, "z_pad")
+    _chk_nhwc(z_pad, "z_pad", dy_pad)
     N, Hp, Wp, C = z_pad.shape
     H, W = Hp - 2, Wp - 2
     if dy_pad.shape != z_pad.shape:
         raise ValueError("bn_act_bwd: dy shape %s != z shape %s" % (tuple(dy_pad.shape), tuple(z_pad.shape)))
     if dz_out is None:
-        dz_out = torch.zeros((N, Hp, W + 2 * dz_halo_w, C), device=z_pad.device, dtype=torch.bfloat16)
+        dz_out = torch.zeros((N, Hp, W + 2 * dz_halo_w, C), device=z_pad.device, dtype=z_pad.dtype)
     if want_g and g_out is None:
         g_out = torch.zeros_like(z_pad)
     if dgb_out is None:
@@ -692,7 +698,7 @@ def bn_act_bwd(dy_pad, z_pad, coef, mask_mode, y_mask=None, dz_halo_w=1, dz_out=
     ws = _workspace(nb, z_pad.device, "bn")
     opt = lambda t: _p(t) if t is not None else None
     with torch.cuda.device(z_pad.device):
-        st = L.rd_bn_act_bwd_nhwc_bf16(_p(dy_pad), opt(y_mask), _p(z_pad), _p(coef), int(mask_mode), _p(dz_out),
+        st = _lib.act_fn("rd_bn_act_bwd_nhwc_bf16", z_pad.dtype)(_p(dy_pad), opt(y_mask), _p(z_pad), _p(coef), int(mask_mode), _p(dz_out),
                                        int(dz_halo_w), opt(g_out), _p(dgamma), _p(dbeta), N, H, W, C, _p(ws), nb,
                                        _stream())
     _lib.check(st, "bn_act_bwd")
@@ -709,7 +715,7 @@ def channel_sums(x_pad, out=None):
     nb = L.rd_bn_workspace_bytes(C) + 8 * C * 4
     ws = _workspace(nb, x_pad.device, "bn")
     with torch.cuda.device(x_pad.device):
-        st = L.rd_channel_sums_nhwc_bf16(_p(x_pad), N, Hp - 2, Wp - 2, C, _p(out), _p(ws), nb, _stream())
+        st = _lib.act_fn("rd_channel_sums_nhwc_bf16", x_pad.dtype)(_p(x_pad), N, Hp - 2, Wp - 2, C, _p(out), _p(ws), nb, _stream())
     _lib.check(st, "channel_sums")
     return out
 
@@ -717,14 +723,14 @@ def channel_sums(x_pad, out=None):
 def add_nhwc(x0_pad, x1_pad, out=None):
     """y = x0 + x1 over the interior (haloed NHWC bf16)."""
     _chk_nhwc(x0_pad, "x0_pad")
-    _chk_nhwc(x1_pad, "x1_pad")
+    _chk_nhwc(x1_pad, "x1_pad", x0_pad)
     if x0_pad.shape != x1_pad.shape:
         raise ValueError("add_nhwc: shapes differ")
     N, Hp, Wp, C = x0_pad.shape
     if out is None:
         out = torch.zeros_like(x0_pad)
     with torch.cuda.device(x0_pad.device):
-        st = _lib.lib().rd_add_nhwc_bf16(_p(x0_pad), _p(x1_pad), _p(out), N, Hp - 2, Wp - 2, C, _stream())
+        st = _lib.act_fn("rd_add_nhwc_bf16", x0_pad.dtype)(_p(x0_pad), _p(x1_pad), _p(out), N, Hp - 2, Wp - 2, C, _stream())
     _lib.check(st, "add_nhwc")
     return out
 
@@ -737,7 +743,7 @@ def nhwc_to_nchw(src_pad, channels=None, tap_major=False, out=None):
     if out is None:
         out = torch.empty((N, C, Hp - 2, Wp - 2), device=src_pad.device, dtype=torch.float32)
     with torch.cuda.device(src_pad.device):
-        st = _lib.lib().rd_nhwc_bf16_to_nchw_f32(_p(src_pad), _p(out), N, Hp - 2, Wp - 2, Cs, C, int(bool(tap_major)), _stream())
+        st = _lib.act_fn("rd_nhwc_bf16_to_nchw_f32", src_pad.dtype)(_p(src_pad), _p(out), N, Hp - 2, Wp - 2, Cs, C, int(bool(tap_major)), _stream())
     _lib.check(st, "nhwc_to_nchw")
     return out
 
@@ -751,7 +757,7 @@ def nchw_to_nhwc(src, out, tap_major=False):
     if tuple(out.shape[:3]) != (N, H + 2, W + 2) or out.shape[3] < C:
         raise ValueError("nchw_to_nhwc: output shape %s does not match %s" % (tuple(out.shape), tuple(src.shape)))
     with torch.cuda.device(src.device):
-        st = _lib.lib().rd_nchw_f32_to_nhwc_bf16(_p(src), _p(out), N, H, W, C, out.shape[3], int(bool(tap_major)), _stream())
+        st = _lib.act_fn("rd_nchw_f32_to_nhwc_bf16", out.dtype)(_p(src), _p(out), N, H, W, C, out.shape[3], int(bool(tap_major)), _stream())
     _lib.check(st, "nchw_to_nhwc")
     return out
 
@@ -760,11 +766,11 @@ def nchw_to_nhwc(src, out, tap_major=False):
 # Parameter plumbing: flat gathers and the SGD update (optim.cu)
 # ------------------------------------------------------------------------------------------------
 def gather_to_bf16(src, idx, out):
-    """out[i] = bf16(src[idx[i]]) (0 where idx[i] < 0); src fp32 flat, idx int32, out bf16, all CUDA."""
-    if src.dtype != torch.float32 or idx.dtype != torch.int32 or out.dtype != torch.bfloat16 or idx.numel() != out.numel():
-        raise TypeError("gather_to_bf16: src float32, idx int32 and out bfloat16 of equal length expected")
+    """out[i] = bf16 / fp16 (src[idx[i]]) (0 where idx[i] < 0); src fp32 flat, idx int32, out bf16 or fp16, all CUDA."""
+    if src.dtype != torch.float32 or idx.dtype != torch.int32 or out.dtype not in ACT_DTYPES or idx.numel() != out.numel():
+        raise TypeError("gather_to_bf16: src float32, idx int32 and out bfloat16 / float16 of equal length expected")
     with torch.cuda.device(src.device):
-        st = _lib.lib().rd_gather_f32_to_bf16(_p(src), _p(idx), _p(out), idx.numel(), _stream())
+        st = _lib.act_fn("rd_gather_f32_to_bf16", out.dtype)(_p(src), _p(idx), _p(out), idx.numel(), _stream())
     _lib.check(st, "gather_to_bf16")
     return out
 

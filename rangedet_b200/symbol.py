@@ -155,10 +155,14 @@ class TrainSymbol(_Symbol):
             sh["gt_bbox_%s_for_iou_pred" % c] = (B, 200, 8 if self.head.p.loss.iou_type == "bev" else 7)
         return sh
 
-    def bind(self, params, batch_image=None, optimizer=None, world_size=1, allreduce=None, device="cuda", lr=None):
+    def bind(self, params, batch_image=None, optimizer=None, world_size=1, allreduce=None, device="cuda", lr=None,
+             act_dtype=None, capture=True):
         """-> train.GraphedTrainStep on `params` (reference names).  `optimizer`: OptimizeParam.optimizer
         (type 'sgd', lr, momentum, wd, clip_gradient; tools/train.py:306-319).  rescale_grad = 1/scale_loss_shift with
-        fp16 (tools/train.py:359-361); the all-reduce average is 1/world_size on top."""
+        fp16 (tools/train.py:359-361); the all-reduce average is 1/world_size on top.  `act_dtype`: storage type of
+        activations / operands; default = what the config asks for: torch.float16 when RpnParam.fp16 (config:35; the
+        reference casts the graph to fp16, dla_backbone.py:136-137), else torch.bfloat16 (the reference would run
+        fp32 there, which the tensor-core kernels do not store)."""
         B = batch_image or self.head.batch_size
         H, W = self.backbone.range_image_shape_hw
         o = optimizer
@@ -169,7 +173,8 @@ class TrainSymbol(_Symbol):
             clip_gradient=getattr(o, "clip_gradient", None) if o is not None else 35.0,
             rescale_grad=1.0 / self.head.scale_loss_shift, device=device, use_meta=self.backbone.use_meta,
             allreduce=allreduce, world_size=world_size, loss_hyper=self.head.loss_hyper(),
-            gt_name="gt_bbox_%s_for_iou_pred" % self.det.class_names[0])
+            gt_name="gt_bbox_%s_for_iou_pred" % self.det.class_names[0], capture=capture,
+            act_dtype=act_dtype if act_dtype is not None else (torch.float16 if self.head.fp16 else torch.bfloat16))
         return step
 
 

@@ -247,3 +247,68 @@ def assign_frame(n_vehicles=30, seed=0, h=H_RANGE, w=W_RANGE, missing=0.10):
     mask = (rng.uniform(size=(h, w)) >= missing).astype(np.float32)
     pc = np.stack([x, y, z], -1).astype(np.float32) * mask[..., None]
     return pc.reshape(-1, 3), mask.reshape(-1), b7.astype(np.float32), boxes7_to_corners24(b7)
+
+
+def shipped_config(is_train=True, hw=(H_RANGE, W_PADDED), fp16=True):
+    """The VALUES of config/rangedet/rangedet_veh_wo_aug_4_18e.py:31-141,177-184 as parameter classes, for a box
+    without the reference checkout (bench.py on the GPU box); with a checkout, rangedet_b200.shim.load_config()
+    reads the file itself.  -> (BackboneParam, RpnParam, OptimizeParam.optimizer)"""
+    class General:
+        batch_image = 2 if is_train else 1           # :32
+        scale_loss_shift = 128                       # :36
+        class_names = ('veh',)                       # :41
+        num_classes = 1
+
+    General.fp16 = fp16                              # :35 (True as shipped)
+
+    class BackboneParam:                             # :89-108
+        fp16 = General.fp16
+        normalizer = None                            # the file passes normalizer_factory(type="localbn") (:56)
+        fpn_strides = (1, 2, 4)
+        batch_image = General.batch_image
+        range_image_shape_hw = hw
+        meta_kernel_units = {'res1_unit2': dict(stride=1, meta_func_param='meta_baseline_bias', data_channels=64,
+                                                coord_channels=3, channel_list=[32, 64], kernel_size=3)}
+        num_block = {'res1': 2, 'res2a': 3, 'res2': 3, 'res3a': 5, 'res3': 5, 'agg1': 2, 'agg2': 2, 'agg2a': 1, 'agg3': 2}
+        num_filter = {'res1': 64, 'res2a': 64, 'res2': 128, 'res3a': 128, 'res3': 128, 'agg1': 64, 'agg2': 128,
+                      'agg2a': 64, 'agg3': 64}
+        add_data_sc = True
+
+    class RpnParam:                                  # :110-141
+        fp16 = General.fp16
+        normalizer = None
+        batch_image = General.batch_image
+        scale_loss_shift = General.scale_loss_shift
+        class_names = General.class_names
+        num_classes = General.num_classes
+        fpn_strides = (1, 2, 4)
+        num_reg_delta = 8
+        wnms = True
+
+        class loss:
+            alpha = 1
+            gamma = 2
+            reg_loss_weight = 8.0
+            cls_loss_weight = 10.0
+            iou_type = 'bev'
+            smooth_l1_scalar = 3
+
+        class head:
+            cls_conv_layers = 4
+            cls_conv_channel = 128
+            reg_conv_layers = 4
+            reg_conv_channel = 128
+
+        class all_proposal:
+            rpn_pre_nms_top_n = {'veh': 50000, 'ped': 5000, 'cyc': 5000}
+            rpn_post_nms_top_n = {'veh': 200, 'ped': 200, 'cyc': 100}
+            nms_thr = {'veh': 0.2, 'ped': 0.2, 'cyc': 0.2}
+
+    class optimizer:                                 # :178-184
+        type = "sgd"
+        lr = 0.01 / 8 * 1 * General.batch_image * 5
+        momentum = 0.9
+        wd = 0.00001
+        clip_gradient = 35
+
+    return BackboneParam, RpnParam, optimizer

@@ -88,13 +88,13 @@ class _Pool:
     """Named activation / gradient buffers reused across steps.  Kernels only ever write the interior, so
     a haloed buffer zero-initialised once keeps a valid zero halo."""
 
-    def __init__(self, device):
-        self.device, self.bufs = device, {}
+    def __init__(self, device, dtype=torch.bfloat16):
+        self.device, self.dtype, self.bufs = device, dtype, {}
 
     def get(self, key, shape):
         t = self.bufs.get(key)
         if t is None or tuple(t.shape) != tuple(shape):
-            t = torch.zeros(tuple(shape), device=self.device, dtype=torch.bfloat16)
+            t = torch.zeros(tuple(shape), device=self.device, dtype=self.dtype)
             self.bufs[key] = t
         return t
 
@@ -102,11 +102,17 @@ class _Pool:
 class TrainGraph(object):
     """forward(data, coord) -> (cls_logit[3], bbox_delta[3]) fp32 NCHW; backward(d_cls, d_reg) -> {name: grad}."""
 
-    def __init__(self, params, device="cuda", use_meta=True):
+    def __init__(self, params, device="cuda", use_meta=True, act_dtype=torch.bfloat16):
+        """act_dtype: storage type of activations, activation gradients and weight operands -- torch.float16 (what the
+        reference trains in, config:35, with loss scale 128) or torch.bfloat16; accumulation, statistics, parameter
+        gradients and master parameters are fp32 either way."""
+        if act_dtype not in ops.ACT_DTYPES:
+            raise TypeError("act_dtype must be torch.bfloat16 or torch.float16, got %r" % (act_dtype,))
         self.P = params  # fp32 master parameters (reference names), updated in place by the optimiser
         self.device = device
         self.use_meta = use_meta
-        self.pool = _Pool(device)
+        self.act_dtype = act_dtype
+        self.pool = _Pool(device, act_dtype)
         self.packed = {}
         self.tape = []
         self.grads = {}
@@ -149,7 +155,7 @@ class TrainGraph(object):
         # -- operands: push element indices through the same packing functions
         keys = sorted(self.pack_rec)
         sizes = [_align(self.packed[k].numel(), 128) for k in keys]
-        op_dtype = self.packed[keys[0]].dtype if keys else torch.bfloat16     # bf16 (the kernels' operand type)
+        op_dtype = self.packed[keys[0]].dtype if keys else self.act_dtype     # the kernels' operand type (act_dtype)
         self.packed_flat = torch.zeros(sum(sizes), device=dev, dtype=op_dtype)
         self.pmap = torch.full((sum(sizes),), -1, device=dev, dtype=torch.int32)
         o, views = 0, {}
@@ -209,7 +215,7 @@ class TrainGraph(object):
         if self.flat_pack:
             raise KeyError("operand %s was not recorded before enable_flat()" % (key,))
         self.pack_rec[key] = (ci_p, co_p, S)
-        t = pack_operand(self.P[name + "_weight"], kind, ci_p, co_p, S)
+        t = pack_operand(self.P[name + "_weight"], kind, ci_p, co_p, S, dtype=self.act_dtype)
         self.packed[key] = t
         return t
 
@@ -608,7 +614,7 @@ class GraphedTrainStep(object):
 
     def __init__(self, params, batch, H, W, lr, momentum=0.9, wd=1e-5, clip_gradient=35.0, rescale_grad=1.0 / 128.0,
                  device="cuda", use_meta=True, allreduce=None, world_size=1, with_loss=True, overlap_wgrad=True,
-                 loss_hyper=None, gt_name="gt_bbox_veh_for_iou_pred", capture=True):
+                 loss_hyper=None, gt_name="gt_bbox_veh_for_iou_pred", capture=True, act_dtype=torch.bfloat16):
         self.P = params
         self.allreduce = allreduce
         self.with_loss = with_loss
@@ -633,7 +639,8 @@ class GraphedTrainStep(object):
         # `allreduce(flat)` SUMS the flat gradient over ranks; the 1/world_size of the average rides rescale_grad
         self.hyper = torch.tensor([lr, momentum, rescale_grad / world_size, clip_gradient if clip_gradient else 0.0],
                                   device=device)
-        self.tg = TrainGraph(params, device, use_meta)
+        self.tg = TrainGraph(params, device, use_meta, act_dtype)
+        self.act_dtype = act_dtype
         self.capture = capture    # False: same buffers and flat plumbing, kernels launched eagerly (debugging)
         if overlap_wgrad and capture:
             self.tg.side = torch.cuda.Stream(device=device)
@@ -642,6 +649,7 @@ class GraphedTrainStep(object):
         self.d_cls = [torch.zeros((batch, 1, H, W // s), device=device) for s in STRIDES]
         self.d_reg = [torch.zeros((batch, 8, H, W // s), device=device) for s in STRIDES]
         self.targets, self.loss_out = None, None
+        self.launches = None   # kernels per graph replay (captured mode)
         if with_loss:
             z = lambda *shape: torch.zeros(shape, device=device)
             self.targets = {gt_name: z(batch, 200, 8 if self.loss_hyper["iou_type"] == "bev" else 7)}
@@ -697,12 +705,18 @@ class GraphedTrainStep(object):
         # thread_local: another thread's CUDA calls (the NCCL watchdog of a data-parallel job polls events) must not
         # invalidate the capture
         mode = dict(capture_error_mode="thread_local")
+        # kernels per replay: the C-ABI counts every launch it issues (rd_launch_count), also under capture
+        from . import _lib
+        c0 = _lib.launch_count()
         with torch.cuda.graph(self.g_fwd, pool=self.pool, **mode):
             self._fwd()
+        c1 = _lib.launch_count()
         with torch.cuda.graph(self.g_bwd, pool=self.pool, **mode):
             self._bwd()
+        c2 = _lib.launch_count()
         with torch.cuda.graph(self.g_upd, pool=self.pool, **mode):
             self._update()
+        self.launches = dict(fwd=c1 - c0, bwd=c2 - c1, upd=_lib.launch_count() - c2)
         restore_aux()   # capture executes nothing: this undoes the eager warm-up passes
 
     def _fwd(self):
@@ -772,3 +786,74 @@ class GraphedTrainStep(object):
         self.forward(data, coord)
         self.backward_update()
         return self.loss_out
+
+
+class HostFedTrainStep(object):
+    """The body of tools/train.py's fit loop as the caller sees it: one HOST loader record in, loss values out.
+
+        fed = HostFedTrainStep(step)                  # step: GraphedTrainStep (e.g. from TrainSymbol.bind())
+        fed.feed(record)                              # pinned host tensors named like builder.py:20-37 + input_data, coord_s1
+        losses = fed.step()                           # forward, loss, backward, all-reduce, SGD on that record
+        fed.feed(next_record); ...                    # upload of record i+1 overlaps the kernels of record i
+        values = fed.losses()                         # waits; (6,) numpy: [cls_s1, cls_s2, cls_s4, reg_s1, reg_s2, reg_s4] sums
+
+    The reference's loader hands MXNet a DataBatch of host arrays per iteration (utils/detection_input.py:160-177) and its
+    metrics read the six loss outputs back (ScalarLoss, rangedet/core/detection_metric.py:200-211).  Here the record is
+    uploaded on a copy stream into one of `slots` staging sets (PCIe: ~41 MB per frame), the captured graphs read their
+    static buffers (filled device-to-device from the staging set), and the six per-level loss sums come back through
+    one pinned 24-byte buffer.  Nothing synchronises the host except `losses()`."""
+
+    def __init__(self, step, slots=2):
+        if not step.with_loss:
+            raise ValueError("HostFedTrainStep needs a GraphedTrainStep built with the fused loss (with_loss=True)")
+        self.step_, self.slots, self.n_fed, self.n_run = step, slots, 0, 0
+        dev = step.data.device
+        self.names = ["input_data", "coord_s1"] + sorted(step.targets)
+        self.static = dict(step.targets, input_data=step.data, coord_s1=step.coord)
+        self.staging = [{k: torch.empty_like(self.static[k]) for k in self.names} for _ in range(slots)]
+        self.copy_stream = torch.cuda.Stream(device=dev)
+        self.ready = [torch.cuda.Event() for _ in range(slots)]       # record i is on the device
+        self.consumed = [torch.cuda.Event() for _ in range(slots)]    # its staging set has been read
+        self.loss_dev = torch.zeros(6, device=dev)
+        self.loss_host = torch.zeros(6).pin_memory()
+        self.loss_done = torch.cuda.Event()
+        self.h2d_bytes = sum(self.static[k].numel() * self.static[k].element_size() for k in self.names)
+        self.d2h_bytes = self.loss_host.numel() * 4
+
+    def feed(self, record):
+        if self.n_fed - self.n_run >= self.slots:
+            raise RuntimeError("HostFedTrainStep: %d records already in flight" % self.slots)
+        s = self.n_fed % self.slots
+        self.n_fed += 1
+        with torch.cuda.stream(self.copy_stream):
+            self.copy_stream.wait_event(self.consumed[s])
+            for k in self.names:
+                src = record[k]
+                src = torch.from_numpy(src) if not isinstance(src, torch.Tensor) else src
+                self.staging[s][k].copy_(src.reshape(self.staging[s][k].shape), non_blocking=True)
+            self.ready[s].record(self.copy_stream)
+
+    def step(self):
+        if self.n_run >= self.n_fed:
+            raise RuntimeError("HostFedTrainStep.step() without a fed record")
+        s = self.n_run % self.slots
+        self.n_run += 1
+        st, cur = self.step_, torch.cuda.current_stream()
+        cur.wait_event(self.ready[s])
+        stg = self.staging[s]
+        torch._foreach_copy_([self.static[k] for k in self.names], [stg[k] for k in self.names])
+        self.consumed[s].record(cur)
+        if st.capture:
+            st.g_fwd.replay()
+        else:
+            st._fwd()
+        st.backward_update()
+        lo = st.loss_out
+        torch.stack([l["cls_loss"].sum() for l in lo] + [l["reg_loss"].sum() for l in lo], out=self.loss_dev)
+        self.loss_host.copy_(self.loss_dev, non_blocking=True)
+        self.loss_done.record(cur)
+        return self.loss_host
+
+    def losses(self):
+        self.loss_done.synchronize()
+        return self.loss_host.numpy().copy()

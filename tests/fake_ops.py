@@ -10,8 +10,8 @@ bf16-rounded operands and rounds its bf16 outputs once, like the kernels.  The p
 import torch
 import torch.nn.functional as F
 
-from rangedet_b200.ops import (BN_EPS, BN_MOMENTUM, IMPL_DEFAULT, from_nhwc_padded, pack_conv_weight, pack_deconv_weight,  # noqa: F401
-                               tap_major_weight, to_nhwc_padded)  # (pure torch helpers of the real module)
+from rangedet_b200.ops import (ACT_DTYPES, BN_EPS, BN_MOMENTUM, IMPL_DEFAULT, from_nhwc_padded, pack_conv_weight,  # noqa: F401
+                               pack_deconv_weight, tap_major_weight, to_nhwc_padded)  # (pure torch helpers of the real module)
 
 bf16 = torch.bfloat16
 COMPUTE = torch.float32      # arithmetic type of the emulated kernels
@@ -191,7 +191,7 @@ def nchw_to_nhwc(src, out, tap_major=False):
     return _store(out, x.to(COMPUTE))
 
 
-def meta_kernel_forward_nhwc(data, coord, w0, b0, w1, b1, scale, shift, relu=True, out=None):
+def meta_kernel_forward_nhwc(data, coord, w0, b0, w1, b1, scale, shift, relu=True, out=None, dtype=None):
     from oracle import meta_kernel_ref
     m = meta_kernel_ref.meta_baseline_bias(data, coord, w0.reshape(32, 3), b0, w1.reshape(-1, 32), b1)   # (B, c*9+k, H, W)
     m = m * scale.to(COMPUTE).view(1, -1, 1, 1) + shift.to(COMPUTE).view(1, -1, 1, 1)

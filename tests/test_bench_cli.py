@@ -24,7 +24,8 @@ def test_reference_arm_prints_one_json_line():
     assert d["metric"] == "range-image frames/s (fwd+bwd, 64x2650)" and d["value"] > 0
     assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
     assert d["e2e"] == {"value": d["value"], "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
-    assert d["config"]["workload"].startswith("meta_kernel_fwd_bwd cfg-2") and d["gpu_launches"] == 0
+    assert d["config"]["workload"].startswith("cfg-5 rangedet_veh_wo_aug_4_18e train step") and d["gpu_launches"] == 0
+    assert "1 frame" in d["cpu_baseline"]["sample"]
 
 
 def test_default_arm_needs_a_gpu():
@@ -32,5 +33,5 @@ def test_default_arm_needs_a_gpu():
     if torch.cuda.is_available():
         import pytest
         pytest.skip("a CUDA device is present")
-    p = _run("--steps", "1", "--warmup", "1", "--no-cpu-baseline", "--no-train-step", timeout=300)
+    p = _run("--steps", "1", "--warmup", "1", "--no-cpu-baseline", "--quick", timeout=300)
     assert p.returncode != 0 and "no CPU fallback" in (p.stderr + p.stdout)

@@ -223,7 +223,7 @@ def test_inference_executor_equals_reference_graph_without_rounding(monkeypatch)
             return t
         monkeypatch.setattr(dla._BufferPool, "get", get)
 
-        def to_pad(x, channels=None):
+        def to_pad(x, channels=None, dtype=None):
             N, C, H, W = x.shape
             out = torch.zeros((N, H + 2, W + 2, channels or C), dtype=torch.float64)
             out[:, 1:H + 1, 1:W + 1, :C] = x.permute(0, 2, 3, 1)
