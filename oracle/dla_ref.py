@@ -95,11 +95,13 @@ def bn_fold(P, name):
 
 
 class Ref:
-    def __init__(self, P, bf16=True):
-        self.P, self.bf16 = P, bf16
+    def __init__(self, P, bf16=True, store=None):
+        self.P = P
+        self.store = store if store is not None else (torch.bfloat16 if bf16 else None)
+        self.bf16 = self.store is not None
 
-    def r(self, x):  # storage format of the B200 pipeline
-        return x.bfloat16().float() if self.bf16 else x
+    def r(self, x):  # storage format of the B200 pipeline (bf16, or fp16 as the reference trains: config:35)
+        return x.to(self.store).to(x.dtype) if self.bf16 else x
 
     def conv_bn(self, x, wname, bnname, stride=(1, 1), relu=True, residual=None, res_after_relu=False):
         w = self.r(self.P[wname + "_weight"])

@@ -10,7 +10,7 @@ absent here); this file follows the graph builders op for op, name for name, in 
   mxnext/complicate.py:14,32-43                     BatchNorm: batch statistics (use_global_stats False),
                                                      biased variance, eps 1e-5+1e-10, momentum 0.9
 
-`bf16=True` rounds values to bf16 wherever the B200 pipeline stores them in that format (conv outputs z,
+`bf16=True` (or `store=torch.float16`) rounds values to the storage type wherever the B200 pipeline stores them (conv outputs z,
 activations y, activation gradients, weight operands), with a straight-through gradient that is itself
 rounded -- so the comparison isolates kernel errors from the storage format.  Gradients come from
 torch.autograd.
@@ -24,14 +24,17 @@ from .dla_ref import META_UNITS, NUM_BLOCK
 EPS = 1e-5 + 1e-10
 
 
-class _RoundBF16(torch.autograd.Function):
+class _Round(torch.autograd.Function):
+    """Round to the storage type in both directions (straight-through: the gradient is what the kernels store)."""
+
     @staticmethod
-    def forward(ctx, x):
-        return x.bfloat16().float()
+    def forward(ctx, x, dtype):
+        ctx.dtype = dtype
+        return x.to(dtype).to(x.dtype)
 
     @staticmethod
     def backward(ctx, g):
-        return g.bfloat16().float()
+        return g.to(ctx.dtype).to(g.dtype), None
 
 
 class TrainRef:
@@ -41,8 +44,12 @@ class TrainRef:
     fp32 bits disagree on a few masks per layer and hence visibly in deep gradients; the difference
     between the jittered and the plain reference measures that sensitivity (the tests' noise floor)."""
 
-    def __init__(self, P, bf16=True, use_meta=True, jitter=0.0, seed=1234):
+    def __init__(self, P, bf16=True, use_meta=True, jitter=0.0, seed=1234, store=None):
+        """store: storage type to emulate (torch.bfloat16 / torch.float16 -- the reference itself trains in fp16,
+        config:35); default bf16 when `bf16` is set, none (plain fp32 graph) otherwise."""
         self.P = {k: v.detach().clone().requires_grad_(not k.endswith(("_moving_mean", "_moving_var"))) for k, v in P.items()}
+        self.store = store if store is not None else (torch.bfloat16 if bf16 else None)
+        bf16 = self.store is not None
         self.bf16, self.use_meta, self.jitter = bf16, use_meta, jitter
         self.gen = None
         if jitter:
@@ -54,7 +61,7 @@ class TrainRef:
             return x
         if self.jitter:
             x = x * (1.0 + self.jitter * scale * torch.randn(x.shape, device=x.device, generator=self.gen))
-        return _RoundBF16.apply(x)
+        return _Round.apply(x, self.store)
 
     def bn(self, z, name):
         return F.batch_norm(z, None, None, self.P[name + "_gamma"], self.P[name + "_beta"], training=True, eps=EPS)
@@ -121,8 +128,8 @@ class TrainRef:
     def forward_backward(self, data, coord, d_cls, d_reg):
         """-> (cls, reg, {name: grad}) for the linear loss sum(cls*d_cls) + sum(reg*d_reg)."""
         cls, reg = self.forward(data, coord)
-        loss = sum((c * g.bfloat16().float() if self.bf16 else c * g).sum() for c, g in zip(cls, d_cls)) + \
-            sum((r * g.bfloat16().float() if self.bf16 else r * g).sum() for r, g in zip(reg, d_reg))
+        rnd = (lambda g: g.to(self.store).to(g.dtype)) if self.bf16 else (lambda g: g)
+        loss = sum((c * rnd(g)).sum() for c, g in zip(cls, d_cls)) + sum((r * rnd(g)).sum() for r, g in zip(reg, d_reg))
         loss.backward()
         grads = {k: v.grad for k, v in self.P.items() if v.requires_grad and v.grad is not None}
         return [c.detach() for c in cls], [r.detach() for r in reg], grads

@@ -182,69 +182,9 @@ def test_channel_sums_and_add(ops):
     assert float(s[:, 0].float().abs().max()) == 0
 
 
-def _train_graph_case(ops, use_meta, B=2, H=4, W=160, seed=0):
-    import json
-    from oracle import dla_ref, dla_train_ref
-    from rangedet_b200 import synth, train
-    P = dla_ref.make_params(seed=seed, device="cuda")
-    g = torch.Generator(device="cuda").manual_seed(seed + 1)
-    if not use_meta:  # the unit as a plain basic block (meta_kernel_units = {} in the config)
-        P["res1_unit2_conv1_weight"] = torch.randn((64, 64, 3, 3), device="cuda", generator=g) * (2.0 / 576) ** 0.5
-        P["res1_unit2_bn1_gamma"] = torch.ones(64, device="cuda")
-        P["res1_unit2_bn1_beta"] = torch.zeros(64, device="cuda")
-        P["res1_unit2_bn1_moving_mean"] = torch.zeros(64, device="cuda")
-        P["res1_unit2_bn1_moving_var"] = torch.ones(64, device="cuda")
-        P = {k: v for k, v in P.items() if "mlp" not in k and "aggregation" not in k}
-    data = torch.randn((B, 8, H, W), device="cuda", generator=g)
-    coord = torch.from_numpy(synth.range_image_coords(B, seed=seed, h=H, w=W - 4, w_pad=W)).cuda()
-    Ws = [W, W // 2, W // 4]
-    d_cls = [torch.randn((B, 1, H, w), device="cuda", generator=g) for w in Ws]
-    d_reg = [torch.randn((B, 8, H, w), device="cuda", generator=g) for w in Ws]
-
-    cls_r, reg_r, grads_r = dla_train_ref.TrainRef(P, bf16=True, use_meta=use_meta).forward_backward(data, coord, d_cls, d_reg)
-    # the oracle's own sensitivity to rounding-level perturbations (2e-6 relative before each bf16 rounding)
-    cls_j, reg_j, grads_j = dla_train_ref.TrainRef(P, bf16=True, use_meta=use_meta, jitter=2e-6).forward_backward(
-        data, coord, d_cls, d_reg)
-
-    Pg = {k: v.clone() for k, v in P.items()}
-    tg = train.TrainGraph(Pg, use_meta=use_meta)
-    cls, reg = tg.forward(data, coord)
-    grads = tg.backward(d_cls, d_reg)
-    torch.cuda.synchronize()
-
-    rows = {}
-    for l in range(3):
-        rows["out_cls_%d" % l] = (cls[l], cls_r[l], cls_j[l])
-        rows["out_reg_%d" % l] = (reg[l], reg_r[l], reg_j[l])
-    missing = [k for k in grads_r if k not in grads]
-    for k, v in grads_r.items():
-        if k in grads:
-            assert grads[k].shape == v.shape, (k, grads[k].shape, v.shape)
-            rows[k] = (grads[k], v, grads_j[k])
-    errs = {k: {"rms": _rms_rel(a, b), "floor": _rms_rel(c, b), "cos": _cos(a, b), "cos_floor": _cos(c, b)}
-            for k, (a, b, c) in rows.items()}
-    os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
-    with open(os.path.join(ROOT, "gpurun_out", "train_graph_errs_meta%d.json" % int(use_meta)), "w") as f:
-        json.dump(dict(sorted(errs.items(), key=lambda kv: -kv[1]["rms"])), f, indent=1)
-    # moving statistics follow MXNet's update
-    k = "res2_unit1_bn1_moving_var"
-    assert not torch.equal(Pg[k], P[k])
-    return errs, missing
-
-
-@pytest.mark.parametrize("use_meta", [False, True], ids=["nometa", "meta"])
-def test_train_graph_fwd_bwd_vs_torch_autograd(ops, use_meta):
-    """Whole backbone (+ Meta-Kernel unit) + head, training-mode BN: forward outputs and EVERY parameter
-    gradient against torch autograd on the bf16-storage-emulating restatement (oracle/dla_train_ref.py).
-    Single layers agree to 3e-3 (scripts/dbg_train_layers.py); through ~40 layers the gradient of a ReLU
-    network is discontinuous at every pre-activation that sits within rounding noise of zero, so the bound
-    is relative to the oracle's own sensitivity: rms error <= 3 x (error of the oracle under 2e-6 relative
-    jitter) + 2e-2, and the direction must agree (cosine >= 0.8 wherever the jittered oracle's is >= 0.9)."""
-    errs, missing = _train_graph_case(ops, use_meta)
-    assert not missing, missing
-    bad = {k: e for k, e in errs.items()
-           if not np.isfinite(e["rms"]) or e["rms"] > 3 * e["floor"] + 2e-2 or (e["cos_floor"] >= 0.9 and e["cos"] < 0.8)}
-    assert not bad, sorted(bad.items(), key=lambda kv: -kv[1]["rms"])[:6]
+# The whole graph at size (B=2, 64x2656, every layer teacher-forced with the oracle's tensors, then end to end) lives in
+# tests/test_gpu_parity_full.py; it replaces the former whole-graph test on a 4x160 toy whose bound was relative to the
+# oracle's own jitter response and therefore could not fail.
 
 
 # ---------------------------------------------------------------------------------------------
@@ -316,8 +256,9 @@ LAYER_CASES = {
 }
 
 
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16], ids=["bf16", "f16"])
 @pytest.mark.parametrize("case", sorted(LAYER_CASES))
-def test_train_layer_vs_autograd(ops, case):
+def test_train_layer_vs_autograd(ops, case, dtype):
     """Bounds: forward 1e-2 of the largest value; gradients 1e-2 rms-relative and 1e-1 of the largest value
     (observed 2-5e-3: one bf16 rounding of y / dz / dx; isolated elements differ more where a ReLU
     pre-activation sits within fp32 summation-order noise of zero and the two masks disagree)."""
@@ -327,16 +268,16 @@ def test_train_layer_vs_autograd(ops, case):
     P = _layer_params()
     g = torch.Generator(device="cuda").manual_seed(1)
     xs = [_bf(torch.randn((B_L, c, H_L, w), device="cuda", generator=g)) for c, w in shapes]
-    tg = train.TrainGraph({k: v.clone() for k, v in P.items()})
+    tg = train.TrainGraph({k: v.clone() for k, v in P.items()}, act_dtype=dtype)
     tg.begin()
-    xps = [ops.to_nhwc_padded(x, 128 if x.shape[1] == 72 else ((x.shape[1] + 63) // 64) * 64) for x in xs]
+    xps = [ops.to_nhwc_padded(x, 128 if x.shape[1] == 72 else ((x.shape[1] + 63) // 64) * 64, dtype=dtype) for x in xs]
     y = build_g(tg, *xps)
-    ref = dla_train_ref.TrainRef(P, bf16=True)
+    ref = dla_train_ref.TrainRef(P, store=dtype)
     xr = [x.clone().requires_grad_(True) for x in xs]
     yr = build_r(ref, *xr)
-    assert _maxrel(ops.from_nhwc_padded(y, yr.shape[1]), yr.detach()) < 1e-2
+    assert _maxrel(ops.from_nhwc_padded(y, yr.shape[1]), yr.detach()) < (1e-2 if dtype == torch.bfloat16 else 2e-3)
     dy = _bf(torch.randn(yr.shape, device="cuda", generator=g))
-    tg.seed_grad(y, ops.to_nhwc_padded(dy, y.shape[3]))
+    tg.seed_grad(y, ops.to_nhwc_padded(dy, y.shape[3], dtype=dtype))
     tg.run_tape()
     yr.backward(dy)
     for xp, x in zip(xps, xr):
@@ -453,3 +394,118 @@ def test_layout_conversions(ops, C, Cp, tap):
     assert float(out[..., C:].float().abs().max()) == 0 if Cp > C else True
     back = ops.nhwc_to_nchw(out, C, tap_major=tap)
     assert torch.equal(back, x)
+
+
+# ---------------------------------------------------------------------------------------------
+# fp16 storage (the reference's training type, config:35): the same kernels compiled with the other storage type.
+# Operands rounded to fp16, torch fp32 reference on the same rounded operands; outputs carry one fp16 rounding
+# (2^-11 relative) on top of fp32 summation-order noise.
+# ---------------------------------------------------------------------------------------------
+def _hf(x):
+    return x.to(torch.float16).float()
+
+
+F16 = torch.float16
+
+
+@pytest.mark.parametrize("shape", [(2, 64, 64, 5, 300, 3, 1), (2, 128, 128, 4, 200, 3, 1), (2, 128, 64, 3, 150, 3, 2),
+                                   (1, 64, 128, 4, 140, 1, 2), (1, 64, 576, 3, 300, 1, 1)])
+def test_f16_wgrad_vs_torch(ops, shape):
+    N, CA, CB, H, W, ks, s = shape
+    g = torch.Generator(device="cuda").manual_seed(hash(shape) % 1000)
+    A = _hf(torch.randn((N, CA, H, W), device="cuda", generator=g))
+    B = _hf(torch.randn((N, CB, H, W * s), device="cuda", generator=g))
+    got = ops.conv2d_wgrad(ops.to_nhwc_padded(A, dtype=F16), ops.to_nhwc_padded(B, dtype=F16), ks, s)
+    assert _maxrel(got, _wgrad_ref(A, B, ks, s)) < 1e-4
+    with pytest.raises(TypeError):   # mixed storage types are refused, not reinterpreted
+        ops.conv2d_wgrad(ops.to_nhwc_padded(A, dtype=F16), ops.to_nhwc_padded(B), ks, s)
+
+
+@pytest.mark.parametrize("case", [(2, 64, 64, 5, 300, 3, 1, True), (1, 128, 128, 4, 260, 3, 1, True), (2, 128, 128, 3, 150, 3, 2, False),
+                                  (1, 64, 128, 4, 140, 1, 2, False), (1, 576, 64, 3, 200, 1, 1, False), (1, 128, 64, 2, 131, 3, 1, False)])
+def test_f16_conv_fwd_vs_torch(ops, case):
+    """y = relu(conv(x)*scale + shift + residual) with fp16 operands / output (conv_tc.cu compiled with RD_ACT_F16)."""
+    N, Ci, Co, H, W, ks, s, res = case
+    g = torch.Generator(device="cuda").manual_seed(13)
+    x = _hf(torch.randn((N, Ci, H, W), device="cuda", generator=g))
+    w = _hf(torch.randn((Co, Ci, ks, ks), device="cuda", generator=g) * (2.0 / (Ci * ks * ks)) ** 0.5)
+    scale = torch.rand(Co, device="cuda", generator=g) + 0.5
+    shift = torch.randn(Co, device="cuda", generator=g) * 0.2
+    r = _hf(torch.randn((N, Co, H, W // s), device="cuda", generator=g)) if res else None
+    want = F.conv2d(x, w, stride=(1, s), padding=ks // 2) * scale[None, :, None, None] + shift[None, :, None, None]
+    want = torch.relu(want + r if res else want)
+    got = ops.conv2d_nhwc(ops.to_nhwc_padded(x, dtype=F16), ops.pack_conv_weight(w, dtype=F16), scale, shift, relu=True,
+                          residual_pad=ops.to_nhwc_padded(r, dtype=F16) if res else None, stride_w=s)
+    assert got.dtype == F16
+    assert float((ops.from_nhwc_padded(got) - want).abs().max()) <= 2 ** -10 * float(want.abs().max()) + 1e-3
+    assert float(got[:, 0].float().abs().max()) == 0 and float(got[:, :, 0].float().abs().max()) == 0     # halo untouched
+
+
+@pytest.mark.parametrize("kw,S,pad", [(8, 4, 2), (4, 2, 1)])
+def test_f16_deconv_fwd_vs_torch(ops, kw, S, pad):
+    g = torch.Generator(device="cuda").manual_seed(17)
+    x = _hf(torch.randn((2, 128, 3, 83), device="cuda", generator=g))
+    w = _hf(torch.randn((128, 64, 3, kw), device="cuda", generator=g) * 0.05)
+    c = _hf(torch.randn((2, 64, 3, 83 * S), device="cuda", generator=g))
+    want = torch.relu(F.conv_transpose2d(x, w, stride=(1, S), padding=(1, pad))) + c
+    got = ops.deconv2d_nhwc(ops.to_nhwc_padded(x, dtype=F16), ops.pack_deconv_weight(w, dtype=F16), relu=True,
+                            residual_pad=ops.to_nhwc_padded(c, dtype=F16))
+    assert float((ops.from_nhwc_padded(got) - want).abs().max()) <= 2 ** -10 * float(want.abs().max()) + 1e-3
+
+
+@pytest.mark.parametrize("mode", ["plain", "res_before", "res_after"])
+def test_f16_bn_act_fwd_bwd_vs_torch(ops, mode):
+    N, C, H, W = 2, 128, 6, 333
+    g = torch.Generator(device="cuda").manual_seed(19)
+    z = _hf(torch.randn((N, C, H, W), device="cuda", generator=g) * 2 + 0.5)
+    rb = _hf(torch.randn((N, C, H, W), device="cuda", generator=g)) if mode == "res_before" else None
+    ra = _hf(torch.randn((N, C, H, W), device="cuda", generator=g)) if mode == "res_after" else None
+    dy = _hf(torch.randn((N, C, H, W), device="cuda", generator=g))
+    gamma = torch.rand(C, device="cuda", generator=g) + 0.5
+    beta = torch.randn(C, device="cuda", generator=g) * 0.3
+    pad = lambda t: ops.to_nhwc_padded(t, dtype=F16)
+    zp = pad(z)
+    coef = ops.bn_train_stats(zp, gamma, beta, torch.zeros(C, device="cuda"), torch.ones(C, device="cuda"))
+    y = ops.bn_act_fwd(zp, coef, relu=True, res_before=None if rb is None else pad(rb), res_after=None if ra is None else pad(ra))
+    zr = z.clone().requires_grad_(True)
+    gr, br = gamma.clone().requires_grad_(True), beta.clone().requires_grad_(True)
+    rbr = rb.clone().requires_grad_(True) if rb is not None else None
+    mean, var = zr.mean((0, 2, 3), keepdim=True), zr.var((0, 2, 3), unbiased=False, keepdim=True)
+    u = (zr - mean) / torch.sqrt(var + ops.BN_EPS) * gr[None, :, None, None] + br[None, :, None, None]
+    yr = torch.relu(u + rbr if rbr is not None else u)
+    yr = yr + ra if ra is not None else yr
+    yr.backward(dy)
+    assert y.dtype == F16 and _maxrel(coef[2], mean.flatten()) < 1e-5 and _maxrel(coef[4], var.flatten()) < 1e-4
+    assert float((ops.from_nhwc_padded(y) - yr).abs().max()) <= 2 ** -11 * float(yr.abs().max()) + 1e-6
+    mask_mode = 2 if ra is not None else 1
+    dz, dgamma, dbeta, gout = ops.bn_act_bwd(pad(dy), zp, coef, mask_mode, y_mask=y, want_g=rb is not None)
+    assert _maxrel(dgamma, gr.grad) < 1e-3 and _maxrel(dbeta, br.grad) < 1e-3
+    assert _maxrel(ops.from_nhwc_padded(dz), zr.grad) < 2e-3
+    if rb is not None:
+        assert _maxrel(ops.from_nhwc_padded(gout), rbr.grad) < 2e-3
+
+
+def test_f16_layout_gather_and_meta_nhwc(ops):
+    """Layout conversions (exact), the operand gather (one rounding) and the Meta-Kernel's fused NHWC epilogue in fp16."""
+    from oracle import meta_kernel_ref
+    from rangedet_b200 import synth
+    g = torch.Generator(device="cuda").manual_seed(23)
+    x = _hf(torch.randn((2, 576, 3, 77), device="cuda", generator=g))
+    out = torch.zeros((2, 5, 79, 576), device="cuda", dtype=F16)
+    ops.nchw_to_nhwc(x, out, tap_major=True)
+    assert torch.equal(ops.nhwc_to_nchw(out, 576, tap_major=True), x)
+    src = torch.randn(1000, device="cuda", generator=g)
+    idx = torch.randint(-1, 1000, (513,), device="cuda", generator=g, dtype=torch.int32)
+    dst = torch.empty(513, device="cuda", dtype=F16)
+    ops.gather_to_bf16(src, idx, dst)
+    want = torch.where(idx >= 0, src[idx.clamp(min=0).long()], torch.zeros((), device="cuda")).to(F16)
+    assert torch.equal(dst, want)
+    B, C, H, W = 1, 64, 4, 256
+    data = torch.from_numpy(synth.feature_map(B, C, seed=1, h=H, w=W - 4, w_pad=W)).cuda()
+    coord = torch.from_numpy(synth.range_image_coords(B, seed=0, h=H, w=W - 4, w_pad=W)).cuda()
+    w0, b0, w1, b1 = [torch.from_numpy(p).cuda() for p in synth.meta_mlp_params(seed=2)]
+    sc, sh = torch.rand(576, device="cuda", generator=g) + 0.5, torch.randn(576, device="cuda", generator=g) * 0.1
+    m = ops.meta_kernel_forward_nhwc(data, coord, w0, b0, w1, b1, sc, sh, relu=True, dtype=F16)
+    ref = torch.relu(meta_kernel_ref.meta_baseline_bias(data, coord, w0, b0, w1, b1) * sc[None, :, None, None] + sh[None, :, None, None])
+    got = m[:, 1:-1, 1:-1, :].reshape(B, H, W, 9, C).permute(0, 4, 3, 1, 2).reshape(B, 576, H, W).float()
+    assert m.dtype == F16 and float((got - ref).abs().max()) <= 2 ** -10 * float(ref.abs().max()) + 1e-3
