@@ -32,7 +32,7 @@ H, W = 64, 2656
 # one storage rounding: bf16 2^-9 = 2.0e-3, fp16 2^-12 = 2.4e-4 relative per element (round to nearest); a normwise forward
 # error additionally sees the largest element's ulp; gradients add the ReLU-mask elements that sit within rounding of 0
 FWD_TOL = {torch.bfloat16: 1e-2, torch.float16: 2e-3}
-GRAD_TOL = {torch.bfloat16: 1e-2, torch.float16: 3e-3}
+GRAD_TOL = {torch.bfloat16: 1.5e-2, torch.float16: 5e-3}
 DTYPES = [torch.float16, torch.bfloat16]
 IDS = ["f16", "bf16"]
 
@@ -65,9 +65,11 @@ class RecordingRef(object):
                 self.records = []
 
             def conv_bn(self, x, wname, bnname, stride=(1, 1), relu=True, residual=None):
-                y = super().conv_bn(x, wname, bnname, stride=stride, relu=relu, residual=residual)
+                base = super().conv_bn
+                y = base(x, wname, bnname, stride=stride, relu=relu, residual=residual)
                 self.records.append(dict(kind="conv_bn", name=wname, bn=bnname, x=x, res=residual, y=y, stride_w=stride[1], relu=relu,
-                                         params=[wname + "_weight", bnname + "_gamma", bnname + "_beta"]))
+                                         params=[wname + "_weight", bnname + "_gamma", bnname + "_beta"],
+                                         redo=lambda x_, r_: base(x_, wname, bnname, stride=stride, relu=relu, residual=r_)))
                 return y
 
             def basicblock(self, x, coord, name, stride, proj):
@@ -78,7 +80,13 @@ class RecordingRef(object):
                                                            P[name + "_2656_mlp1_bias"])
                     m = self.r(m)
                     a = self.r(self.bn(m, name + "point_wise_mlp_bn1").relu())
-                    self.records.append(dict(kind="meta_front", name=name, x=x, coord=coord, y=a, m=m,
+
+                    def redo(x_, r_):
+                        m_ = meta_kernel_ref.meta_baseline_bias(x_, coord, P[name + "_2656_mlp0_weight"].reshape(32, 3),
+                                                                P[name + "_2656_mlp0_bias"], P[name + "_2656_mlp1_weight"].reshape(-1, 32),
+                                                                P[name + "_2656_mlp1_bias"])
+                        return self.r(self.bn(self.r(m_), name + "point_wise_mlp_bn1").relu())
+                    self.records.append(dict(kind="meta_front", name=name, x=x, coord=coord, y=a, m=m, redo=redo,
                                              params=[name + "point_wise_mlp_bn1_gamma", name + "point_wise_mlp_bn1_beta",
                                                      name + "_2656_mlp0_weight", name + "_2656_mlp0_bias",
                                                      name + "_2656_mlp1_weight", name + "_2656_mlp1_bias"]))
@@ -88,10 +96,12 @@ class RecordingRef(object):
                 return super().basicblock(x, coord, name, stride, proj)
 
             def agg_stage(self, name, const, up, sw, pad):
-                w = self.r(self.P[name + "_deconv_weight"])
-                z = self.r(F.conv_transpose2d(up, w, stride=(1, sw), padding=(1, pad)))
-                y = self.r(self.bn(z, name + "_deconv_bn").relu() + const)
-                self.records.append(dict(kind="deconv_bn", name=name, x=up, res=const, y=y,
+                def layer(up_, const_):
+                    w = self.r(self.P[name + "_deconv_weight"])
+                    z = self.r(F.conv_transpose2d(up_, w, stride=(1, sw), padding=(1, pad)))
+                    return self.r(self.bn(z, name + "_deconv_bn").relu() + const_)
+                y = layer(up, const)
+                self.records.append(dict(kind="deconv_bn", name=name, x=up, res=const, y=y, redo=layer,
                                          params=[name + "_deconv_weight", name + "_deconv_bn_gamma", name + "_deconv_bn_beta"]))
                 return self.res_stage(y, None, name + "_res", (1, 1))
 
@@ -103,7 +113,8 @@ class RecordingRef(object):
                     for br, out, co in (("cls", cls, 1), ("reg", reg, 8)):
                         n = "rpn_%s_%s_lvl_%d" % (br, "logit" if br == "cls" else "delta", lvl)
                         self.records.append(dict(kind="head_out", name=n, x=last["rpn_%s_conv_3_lvl_%d" % (br, lvl)], y=out[lvl], co=co,
-                                                 params=[n + "_weight", n + "_bias"]))
+                                                 params=[n + "_weight", n + "_bias"],
+                                                 redo=lambda x_, r_, n=n: F.conv2d(x_, self.r(self.P[n + "_weight"]), self.P[n + "_bias"])))
                 return cls, reg
 
         return _Rec(P, store)
@@ -144,18 +155,29 @@ def test_cfg5_every_layer_teacher_forced_at_full_size(ops, dtype):
     rnd = lambda t: t.to(dtype).float()
     loss = sum((c * rnd(g)).sum() for c, g in zip(cls_r, d_cls)) + sum((r * rnd(g)).sum() for r, g in zip(reg_r, d_reg))
     ys = [r["y"] for r in ref.records]
-    dys = torch.autograd.grad(loss, ys, retain_graph=True)
+    dys = torch.autograd.grad(loss, ys)       # the whole-graph backward is only needed for these; the graph is freed here
+    for r in ref.records:                     # keep values only
+        for k in ("x", "res", "y", "m"):
+            if r.get(k) is not None:
+                r[k + "_grad"] = r[k].requires_grad
+                r[k] = r[k].detach()
+    del loss, cls_r, reg_r, ys
     tg = train.TrainGraph({k: v.clone() for k, v in P.items()}, act_dtype=dtype)
     pad = lambda t, c=None: ops.to_nhwc_padded(t.detach(), c or _chan_pad(t.shape[1]), dtype=dtype)
     unpad = lambda t, c: ops.from_nhwc_padded(t, c)
     report, worst = {}, {"fwd": 0.0, "grad": 0.0}
     for rec, dy in zip(ref.records, dys):
         kind, name = rec["kind"], rec["name"]
-        wrt = [rec["x"]] + ([rec["res"]] if rec.get("res") is not None else []) + [ref.P[n] for n in rec["params"]]
-        if rec["x"] is data or not rec["x"].requires_grad:      # the network input carries no gradient
-            wrt = wrt[1:]
-        want = torch.autograd.grad(rec["y"], wrt, grad_outputs=dy, retain_graph=True, allow_unused=True)
+        # the layer ALONE on detached copies of the oracle's own input tensors: gradients that are local to it
+        # (the residual / skip input is upstream of the main input in the full graph: it must not see that path)
+        x_l = rec["x"].clone().requires_grad_(rec["x_grad"])
+        r_l = rec["res"].clone().requires_grad_(True) if rec.get("res") is not None else None
+        y_l = rec["redo"](x_l, r_l)
+        wrt = ([x_l] if rec["x_grad"] else []) + ([r_l] if r_l is not None else []) + [ref.P[n] for n in rec["params"]]
+        want = torch.autograd.grad(y_l, wrt, grad_outputs=dy, allow_unused=True)
         want = dict(zip([id(t) for t in wrt], want))
+        assert _maxrel(y_l, rec["y"]) < 2e-3, name       # the isolated recomputation IS the recorded layer (<= 1 storage ulp)
+        x_key, r_key = id(x_l), (id(r_l) if r_l is not None else None)
         tg.begin()
         tapmajor = kind == "conv_bn" and name.endswith("aggregation_conv1")
         x_in = rec["x"].detach()
@@ -166,7 +188,7 @@ def test_cfg5_every_layer_teacher_forced_at_full_size(ops, dtype):
         resp = pad(rec["res"]) if rec.get("res") is not None else None
         e = {}
         if kind == "conv_bn":
-            if not rec["x"].requires_grad:
+            if not rec["x_grad"]:
                 tg.nograd.add(id(xp))
             y = tg.conv_bn(xp, name, rec["bn"], stride_w=rec["stride_w"], relu=rec["relu"], res_before=resp,
                            kinds=("fwd_tapmajor", "dgrad_tapmajor") if tapmajor else ("fwd", "dgrad"))
@@ -194,16 +216,16 @@ def test_cfg5_every_layer_teacher_forced_at_full_size(ops, dtype):
         else:
             tg.run_tape()
         tg._join_side()
-        if id(rec["x"]) in want and want[id(rec["x"])] is not None:
+        if x_key in want and want[x_key] is not None:
             gx = tg.grad_of(xp)
             got = unpad(gx, rec["x"].shape[1])
-            w_ = want[id(rec["x"])]
+            w_ = want[x_key]
             if tapmajor:
                 Bc, C9, Hc, Wc = w_.shape
                 w_ = w_.reshape(Bc, C9 // 9, 9, Hc, Wc).transpose(1, 2).reshape(Bc, C9, Hc, Wc)
             e["dx"] = _rms_rel(got, w_)
         if resp is not None:
-            e["dres"] = _rms_rel(unpad(tg.grad_of(resp), rec["res"].shape[1]), want[id(rec["res"])])
+            e["dres"] = _rms_rel(unpad(tg.grad_of(resp), rec["res"].shape[1]), want[r_key])
         for n in rec["params"]:
             g_ref = want.get(id(ref.P[n]))
             if g_ref is None:
@@ -212,7 +234,7 @@ def test_cfg5_every_layer_teacher_forced_at_full_size(ops, dtype):
         report["%s:%s" % (kind, name)] = e
         worst["fwd"] = max(worst["fwd"], e["fwd"])
         worst["grad"] = max([worst["grad"]] + [v for k, v in e.items() if k != "fwd"])
-        del want
+        del want, y_l, x_l, r_l
     torch.cuda.synchronize()
     os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
     tag = "f16" if dtype == torch.float16 else "bf16"
@@ -222,11 +244,11 @@ def test_cfg5_every_layer_teacher_forced_at_full_size(ops, dtype):
     assert len(report) >= 90, len(report)
     bad = {k: e for k, e in report.items()
            if e["fwd"] > FWD_TOL[dtype] or any(v > GRAD_TOL[dtype] for kk, v in e.items() if kk != "fwd") or any(v != v for v in e.values())}
-    # the Meta-Kernel unit's front carries its own (looser) bound: see the comment in the dedicated test below
+    # the Meta-Kernel unit's front (tcgen05 split-bf16 MLP + BN(576) masks) carries twice the gradient bound
     bad = {k: e for k, e in bad.items() if not k.startswith("meta_front")}
     assert not bad, sorted(bad.items(), key=lambda kv: -max(kv[1].values()))[:8]
     mf = next(v for k, v in report.items() if k.startswith("meta_front"))
-    assert mf["fwd"] <= 1e-2 and all(v <= 0.25 for v in mf.values()), mf
+    assert mf["fwd"] <= FWD_TOL[dtype] and all(v <= 2 * GRAD_TOL[dtype] for v in mf.values()), mf
 
 
 @pytest.mark.parametrize("dtype", DTYPES, ids=IDS)
