@@ -336,6 +336,10 @@ def roofline_leg(dev, B, dtype, pk):
     for _ in range(2):
         step.train_step(data, coord)
     torch.cuda.synchronize()
+    # keep the launch queue ahead of the device: an eager step is host-bound (~1000 launches + 2000 event records), and a
+    # kernel that finds the GPU idle shows its launch latency inside its event bracket.  Behind a 40 ms spin kernel the
+    # host enqueues (most of) the step before the first kernel runs, so the kernels execute back to back as in a replay.
+    torch.cuda._sleep(int(0.04 * 1.9e9))
     with profiling.OpTimer() as t:
         step.train_step(data, coord)
     rows = t.rows()

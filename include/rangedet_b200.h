@@ -266,6 +266,20 @@ int rd_channel_sums_nhwc_bf16(const void* x_pad, int N, int H, int W, int C, flo
 int rd_add_nhwc_bf16(const void* x0_pad, const void* x1_pad, void* y_pad, int N, int H, int W, int C,
                      rd_stream_t stream);
 
+/* Training forward with the batch statistics fused into the convolution epilogue: y = conv(x) (raw, no scale / shift /
+ * ReLU / residual) as rd_conv2d_nhwc_*, and the per-channel sums of the STORED values (sum z, sum z^2) accumulated by
+ * the epilogue warps straight from the staged output tile -- the separate full read of z by rd_bn_train_stats goes away
+ * (mxnext/complicate.py:32-43: mx.sym.BatchNorm with batch statistics, following every conv of dla_backbone.py:17-56
+ * and builder.py:198-246).  stats_partial: rd_bn_workspace_bytes(Cout) bytes; *stats_slots receives the number of
+ * partial slots written.  rd_bn_train_finalize turns them into `coef` and updates the moving statistics exactly like
+ * the second half of rd_bn_train_stats. */
+int rd_conv2d_nhwc_bf16_stats(const void* x_pad, const void* w_packed, void* y_pad, int N, int H, int W, int Cin,
+                              int Cout, int ksize, int stride_w, float* stats_partial, size_t stats_bytes,
+                              int* stats_slots, rd_stream_t stream);
+int rd_bn_train_finalize(const float* partial, int nslots, int N, int H, int W, int C, const float* gamma,
+                         const float* beta, float eps, float momentum, float* moving_mean, float* moving_var,
+                         float* coef, rd_stream_t stream);
+
 /* Layout conversions across the Meta-Kernel op boundary (the reference is NCHW throughout; channel
  * index of the (B,9C,H,W) Meta-Kernel tensors is c*9+k, meta_kernel.py:232-239):
  *   src_pad / dst_pad : zero-haloed NHWC bf16 [N][H+2][W+2][C_src or C_dst], interior touched only
@@ -311,6 +325,9 @@ int rd_deconv2d_nhwc_f16(const void* x_pad, const void* w_packed, const float* s
 int rd_conv2d_nhwc_f16_slice(const void* x_pad, const void* w_packed, const float* scale, const float* shift,
                              void* y_pad, int N, int H, int W, int Cin, int Cout, int ksize, int stride_w,
                              int relu, int y_ctotal, int y_coff, rd_stream_t stream);
+int rd_conv2d_nhwc_f16_stats(const void* x_pad, const void* w_packed, void* y_pad, int N, int H, int W, int Cin,
+                             int Cout, int ksize, int stride_w, float* stats_partial, size_t stats_bytes,
+                             int* stats_slots, rd_stream_t stream);
 int rd_conv2d_wgrad_nhwc_f16(const void* a_pad, const void* b_pad, float* g, int N, int H, int W, int CA,
                              int CB, int ksize, int stride_w, void* workspace, size_t workspace_bytes,
                              rd_stream_t stream);

@@ -46,6 +46,8 @@ SIGNATURES = {
     "rd_get_sorted_foreground": (_i, [_vp] * 4 + [_i] * 3 + [_vp] * 4 + [_sz, _vp]),
     "rd_conv2d_nhwc_bf16": (_i, [_vp] * 6 + [_i] * 8 + [_vp]),
     "rd_conv2d_nhwc_bf16_slice": (_i, [_vp] * 5 + [_i] * 10 + [_vp]),
+    "rd_conv2d_nhwc_bf16_stats": (_i, [_vp] * 3 + [_i] * 7 + [_vp, _sz, ctypes.POINTER(_i), _vp]),
+    "rd_bn_train_finalize": (_i, [_vp] + [_i] * 5 + [_vp, _vp, _f, _f, _vp, _vp, _vp, _vp]),
     "rd_deconv2d_nhwc_bf16": (_i, [_vp] * 6 + [_i] * 7 + [_vp]),
     "rd_conv2d_wgrad_workspace_bytes": (_sz, [_i] * 7),
     "rd_conv2d_wgrad_nhwc_bf16": (_i, [_vp] * 3 + [_i] * 7 + [_vp, _sz, _vp]),
@@ -64,6 +66,7 @@ SIGNATURES = {
     "rd_meta_kernel_fwd_nhwc_f16": (_i, [_vp] * 8 + [_i, _vp] + [_i] * 4 + [_vp]),
     "rd_conv2d_nhwc_f16": (_i, [_vp] * 6 + [_i] * 8 + [_vp]),
     "rd_conv2d_nhwc_f16_slice": (_i, [_vp] * 5 + [_i] * 10 + [_vp]),
+    "rd_conv2d_nhwc_f16_stats": (_i, [_vp] * 3 + [_i] * 7 + [_vp, _sz, ctypes.POINTER(_i), _vp]),
     "rd_deconv2d_nhwc_f16": (_i, [_vp] * 6 + [_i] * 7 + [_vp]),
     "rd_conv2d_wgrad_nhwc_f16": (_i, [_vp] * 3 + [_i] * 7 + [_vp, _sz, _vp]),
     "rd_bn_train_stats_nhwc_f16": (_i, [_vp] + [_i] * 4 + [_vp, _vp, _f, _f, _vp, _vp, _vp, _vp, _sz, _vp]),

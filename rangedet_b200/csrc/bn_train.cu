@@ -474,6 +474,22 @@ int RD_ACT_FN(rd_bn_train_stats_nhwc_, )(const void* z_pad, int N, int H, int W,
   return rd::check_launch("rd_bn_train_stats");
 }
 
+#ifndef RD_ACT_F16   // storage-type independent: defined once, by the bf16 pass
+// Second half of rd_bn_train_stats on partial sums produced elsewhere (the fused epilogue of rd_conv2d_nhwc_*_stats):
+// partial[(which*C + c) * 1184 + slot], slot < nslots.
+int rd_bn_train_finalize(const float* partial, int nslots, int N, int H, int W, int C, const float* gamma, const float* beta,
+                         float eps, float momentum, float* moving_mean, float* moving_var, float* coef, rd_stream_t stream) {
+  if (bn::check_shape("rd_bn_train_finalize", N, H, W, C)) return 1;
+  RD_REQUIRE(partial && coef, "rd_bn_train_finalize: null pointer");
+  RD_REQUIRE(nslots > 0 && nslots <= bn::MAX_BLOCKS, "rd_bn_train_finalize: nslots %d out of range", nslots);
+  if (rd_check_device()) return 1;
+  bn::fwd_finalize_kernel<<<(C + 7) / 8, 256, 0, rd::as_stream(stream)>>>(partial, nslots, C, (double)N * H * W, gamma, beta, eps,
+                                                                         momentum, moving_mean, moving_var, coef);
+  rd::count_launch();
+  return rd::check_launch("rd_bn_train_finalize");
+}
+#endif
+
 int RD_ACT_FN(rd_bn_act_fwd_nhwc_, )(const void* z_pad, const float* coef, const void* res_before, const void* res_after,
                             void* y_pad, int N, int H, int W, int C, int relu, rd_stream_t stream) {
   if (bn::check_shape("rd_bn_act_fwd", N, H, W, C)) return 1;

@@ -40,6 +40,7 @@ constexpr int NTHREADS = 384;
 constexpr int BAR_EPI = 1;
 constexpr int MAX_LOADS = 9, MAX_USES = 4;
 constexpr uint32_t USE_NEWLOAD = 1, USE_LASTOFLOAD = 2, USE_FIRST = 4;  // flags of a per-use record
+constexpr int STATS_STRIDE = 1184;    // = bn::MAX_BLOCKS: slots per channel row of the batch-statistics partials
 
 struct Load {
   int8_t dy, dx;            // offsets in the haloed input frame (already >= 0)
@@ -103,7 +104,7 @@ __global__ void __launch_bounds__(NTHREADS, 1)
 conv_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_w,
             const __grid_constant__ CUtensorMap tm_y, const float* __restrict__ scale,
             const float* __restrict__ shift, const act_t* __restrict__ residual,
-            act_t* __restrict__ y_interior, const __grid_constant__ Params P) {
+            act_t* __restrict__ y_interior, float* __restrict__ stats, const __grid_constant__ Params P) {
   extern __shared__ unsigned char smem_raw[];
   unsigned char* base = smem_raw + ((1024u - (tc::smem_u32(smem_raw) & 1023u)) & 1023u);
   const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
@@ -314,6 +315,16 @@ conv_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CU
       const bool leader = ((warp == 2 || warp == 8) && lane == 0);
       const int bar_id = BAR_EPI + p;
       unsigned char* sO = base + P.o_off[p];
+      // Fused batch statistics (training-mode BatchNorm, mxnext/complicate.py:32-43): after the tile is staged, the 128
+      // epilogue threads re-map to (channel pair, row group) and add the column sums of the STORED values (sum z,
+      // sum z^2) into four registers that live across all tiles of this CTA; one partial per (CTA, pipe, row group)
+      // at the end.  Saves the separate full read of z by rd_bn_train_stats.
+      const int e128 = q4 * 32 + lane;
+      const int ncp = P.Cout >> 1;                 // channel pairs: 64 or 32
+      const int st_cp = e128 & (ncp - 1), st_rg = e128 / ncp, st_rows = ncp;   // rows per group = 128 / (128 / ncp)
+      const uint32_t st_col = (uint32_t)(((2 * st_cp) / KC) * SLOT + (((2 * st_cp) % 8) * 2));
+      const uint32_t st_chunk = (uint32_t)(((2 * st_cp) % KC) / 8);
+      float st_s0 = 0.f, st_s1 = 0.f, st_q0 = 0.f, st_q1 = 0.f;
       uint32_t it = 0;
       for (int st = blockIdx.x; st < nsuper; st += gridDim.x, ++it) {
         const int tile = st * npipes + p;
@@ -392,7 +403,31 @@ conv_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CU
             for (int hf = 0; hf < nh; ++hf) tma::store_4d(&tm_y, sO + hf * SLOT, hf * KC, w0, h, n);
             tma::store_commit();
           }
+          if (stats != nullptr && real) {
+            const int nvalid = min(TM, P.W_out_tiles - w0);
+            const int r1 = min((st_rg + 1) * st_rows, nvalid);
+#pragma unroll 4
+            for (int r = st_rg * st_rows; r < r1; ++r) {
+              const uint32_t wv = *reinterpret_cast<const uint32_t*>(sO + st_col + r * 128 + ((st_chunk ^ (uint32_t)(r & 7)) << 4));
+              float f0, f1;
+              act::unpack2(wv, f0, f1);
+              st_s0 += f0;
+              st_s1 += f1;
+              st_q0 = fmaf(f0, f0, st_q0);
+              st_q1 = fmaf(f1, f1, st_q1);
+            }
+          }
         }
+      }
+      if (stats != nullptr && !P.deconv_s) {
+        // partial[(which * Cout + channel) * STATS_STRIDE + slot], the layout bn::fwd_finalize_kernel reads
+        const int nrg = TM / st_rows;
+        const int slot = ((int)blockIdx.x * npipes + p) * nrg + st_rg;
+        const int c = 2 * st_cp;
+        stats[(int64_t)c * STATS_STRIDE + slot] = st_s0;
+        stats[(int64_t)(c + 1) * STATS_STRIDE + slot] = st_s1;
+        stats[(int64_t)(P.Cout + c) * STATS_STRIDE + slot] = st_q0;
+        stats[(int64_t)(P.Cout + c + 1) * STATS_STRIDE + slot] = st_q1;
       }
       if (!P.deconv_s && leader) tma::store_wait_all<0>();
       if (PROF && leader && p == 0) {
@@ -413,7 +448,8 @@ conv_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CU
 //       of a 3x3 W-stride-2 convolution)
 static int run(int mode, const void* x_pad, const void* w_packed, const float* scale, const float* shift,
                const void* residual_pad, void* y_pad, int N, int H, int W_in, int Cin, int Cout, int ksize,
-               int stride_w, int relu, int res_after_relu, cudaStream_t stream, int y_ctotal = 0, int y_coff = 0) {
+               int stride_w, int relu, int res_after_relu, cudaStream_t stream, int y_ctotal = 0, int y_coff = 0,
+               float* stats = nullptr, int* stats_slots = nullptr) {
   RD_REQUIRE(x_pad && w_packed && y_pad, "rd_conv: null pointer");
   // channel-slice output: write channels [y_coff, y_coff + Cout) of a y tensor with y_ctotal channels
   if (y_ctotal == 0) y_ctotal = Cout;
@@ -583,6 +619,12 @@ static int run(int mode, const void* x_pad, const void* w_packed, const float* s
   RD_CUDA(rd::smem_optin(conv_kernel<true>, smem));
   const int nsuper = (P.ntiles + P.npipes - 1) / P.npipes;
   const int grid = nsuper < sms ? nsuper : sms;
+  if (stats) {
+    RD_REQUIRE(mode == 0 && y_ctotal == Cout, "rd_conv2d stats: only the plain convolution epilogue accumulates batch statistics");
+    const int slots = grid * P.npipes * (TM / (Cout / 2));
+    RD_REQUIRE(slots <= STATS_STRIDE, "rd_conv2d stats: %d partial slots exceed %d", slots, STATS_STRIDE);
+    if (stats_slots) *stats_slots = slots;
+  }
   static const bool prof = [] { const char* e = getenv("RD_CONV_PROF"); return e && e[0] == '1'; }();
   if (prof) {  // diagnostic: per-role cycle counters, synchronous, printed to stderr
     static long long* d_prof = nullptr;
@@ -590,7 +632,7 @@ static int run(int mode, const void* x_pad, const void* w_packed, const float* s
     RD_CUDA(cudaMemsetAsync(d_prof, 0, 1024 * 16 * sizeof(long long), stream));
     P.prof = d_prof;
     conv_kernel<true><<<grid, NTHREADS, smem, stream>>>(tm_x, tm_w, tm_y, scale, shift, res,
-                                                        reinterpret_cast<act_t*>(y_int), P);
+                                                        reinterpret_cast<act_t*>(y_int), stats, P);
     RD_CUDA(cudaStreamSynchronize(stream));
     static long long h[1024 * 16];
     RD_CUDA(cudaMemcpy(h, d_prof, sizeof(long long) * 16 * grid, cudaMemcpyDeviceToHost));
@@ -606,7 +648,7 @@ static int run(int mode, const void* x_pad, const void* w_packed, const float* s
             m[5] / tiles, m[7] / tiles, m[6] / tiles, m[8] / tiles, m[9] / tiles, m[10] / tiles, m[11] / tiles);
   } else {
     conv_kernel<false><<<grid, NTHREADS, smem, stream>>>(tm_x, tm_w, tm_y, scale, shift, res,
-                                                         reinterpret_cast<act_t*>(y_int), P);
+                                                         reinterpret_cast<act_t*>(y_int), stats, P);
   }
   rd::count_launch();
   return rd::check_launch("rd_conv");
@@ -622,6 +664,16 @@ int RD_ACT_FN(rd_conv2d_nhwc_, )(const void* x_pad, const void* w_packed, const 
                         int stride_w, int relu, rd_stream_t stream) {
   return conv::run(0, x_pad, w_packed, scale, shift, residual_pad, y_pad, N, H, W, Cin, Cout, ksize, stride_w, relu, 0,
                    rd::as_stream(stream));
+}
+
+int RD_ACT_FN(rd_conv2d_nhwc_, _stats)(const void* x_pad, const void* w_packed, void* y_pad, int N, int H, int W, int Cin, int Cout,
+                                       int ksize, int stride_w, float* stats_partial, size_t stats_bytes, int* stats_slots,
+                                       rd_stream_t stream) {
+  RD_REQUIRE(stats_partial && stats_slots, "rd_conv2d_nhwc_stats: null statistics buffer");
+  RD_REQUIRE(stats_bytes >= (size_t)conv::STATS_STRIDE * 2 * (size_t)Cout * sizeof(float),
+             "rd_conv2d_nhwc_stats: statistics workspace too small (rd_bn_workspace_bytes(Cout))");
+  return conv::run(0, x_pad, w_packed, nullptr, nullptr, nullptr, y_pad, N, H, W, Cin, Cout, ksize, stride_w, 0, 0,
+                   rd::as_stream(stream), 0, 0, stats_partial, stats_slots);
 }
 
 int RD_ACT_FN(rd_conv2d_nhwc_, _slice)(const void* x_pad, const void* w_packed, const float* scale, const float* shift,

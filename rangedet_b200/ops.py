@@ -467,6 +467,8 @@ def tma_probe(src, box_w, c0, c1, c2):
 # Convolutions (NHWC bf16, zero-haloed activations)
 # ------------------------------------------------------------------------------------------------
 ACT_DTYPES = (torch.bfloat16, torch.float16)   # storage types of activations / operands (csrc/act_type.cuh)
+BN_EPS = 1e-5 + 1e-10   # mxnext/complicate.py:14
+BN_MOMENTUM = 0.9       # mxnext/complicate.py:32-43
 
 
 def to_nhwc_padded(x_nchw, channels=None, dtype=torch.bfloat16):
@@ -539,6 +541,47 @@ def conv2d_nhwc(x_pad, w_packed, scale=None, shift=None, relu=False, residual_pa
                                             int(bool(relu)), _stream())
     _lib.check(st, "conv2d_nhwc")
     return out
+
+
+def conv2d_nhwc_stats(x_pad, w_packed, out=None, stride_w=1, ws=None):
+    """Training forward of a conv that is followed by BatchNorm: z = conv(x) (raw) AND the partial per-channel sums of
+    the stored z (sum, sum of squares), accumulated by the conv epilogue.  Returns (z, partial, nslots) for
+    bn_train_finalize.  `ws`: statistics workspace (a private one per layer call is required when several such convs
+    are in flight before their finalize; default: a fresh buffer)."""
+    N, Hp, Wp, Cin = x_pad.shape
+    taps = w_packed.shape[0]
+    if taps not in (1, 9):
+        raise ValueError("conv2d_nhwc_stats supports 1x1 and 3x3 kernels")
+    H, W = Hp - 2, Wp - 2
+    x_pad, w_packed, _, _, _, out = _conv_common(x_pad, w_packed, None, None, None, out, W // stride_w, "conv2d_nhwc_stats")
+    L = _lib.lib()
+    Cout = w_packed.shape[1]
+    nb = int(L.rd_bn_workspace_bytes(Cout))
+    if ws is None:
+        ws = torch.empty(nb // 4, device=x_pad.device, dtype=torch.float32)
+    if ws.dtype != torch.float32 or ws.numel() * 4 < nb:
+        raise ValueError("conv2d_nhwc_stats: statistics workspace needs %d bytes of float32" % nb)
+    slots = ctypes.c_int(0)
+    with torch.cuda.device(x_pad.device):
+        st = _lib.act_fn("rd_conv2d_nhwc_bf16_stats", x_pad.dtype)(_p(x_pad), _p(w_packed), _p(out), N, H, W, Cin, Cout,
+                                                                   3 if taps == 9 else 1, int(stride_w), _p(ws),
+                                                                   ctypes.c_size_t(ws.numel() * 4), ctypes.byref(slots), _stream())
+    _lib.check(st, "conv2d_nhwc_stats")
+    return out, ws, slots.value
+
+
+def bn_train_finalize(partial, nslots, N, H, W, C, gamma=None, beta=None, moving_mean=None, moving_var=None, eps=None,
+                      momentum=None, coef=None):
+    """Partial sums (conv2d_nhwc_stats) -> coef (6,C) fp32 as bn_train_stats returns; moving statistics updated in place."""
+    if coef is None:
+        coef = torch.empty((6, C), device=partial.device, dtype=torch.float32)
+    opt = lambda t: _p(t) if t is not None else None
+    with torch.cuda.device(partial.device):
+        st = _lib.lib().rd_bn_train_finalize(_p(partial), int(nslots), N, H, W, C, opt(gamma), opt(beta),
+                                             BN_EPS if eps is None else eps, BN_MOMENTUM if momentum is None else momentum,
+                                             opt(moving_mean), opt(moving_var), _p(coef), _stream())
+    _lib.check(st, "bn_train_finalize")
+    return coef
 
 
 def conv2d_nhwc_slice(x_pad, w_packed, out, c_off, relu=False, stride_w=1):
@@ -633,10 +676,6 @@ def conv2d_wgrad(a_pad, b_pad, ksize, stride_w=1, out=None):
                                          _stream())
     _lib.check(st, "conv2d_wgrad")
     return g
-
-
-BN_EPS = 1e-5 + 1e-10   # mxnext/complicate.py:14
-BN_MOMENTUM = 0.9       # mxnext/complicate.py:32-43
 
 
 def bn_train_stats(z_pad, gamma=None, beta=None, moving_mean=None, moving_var=None, eps=BN_EPS,

@@ -34,6 +34,15 @@ def _conv(x, w, *a, **k):
             2.0 * N * H * (W // s) * Ci * Co * taps, by)
 
 
+def _conv_stats(x, w, out=None, stride_w=1, ws=None):
+    key, fl, by = _conv(x, w, stride_w=stride_w)
+    return key + " +stats", fl, by
+
+
+def _finalize(partial, nslots, N, H, W, C, *a, **k):
+    return ("C%d" % C, 0.0, 4.0 * nslots * 2 * C)
+
+
 def _slice(x, w, out, c_off, **k):
     N, H, W, Ci = _nhwc(x)
     taps, Co, _ = w.shape
@@ -121,7 +130,8 @@ def _sgd(weight, *a):
 # op name -> (family, metadata function); family "tensor" rows are judged against the bf16 tensor peak, "hbm" rows
 # against the measured copy bandwidth
 OPS = OrderedDict([
-    ("conv2d_nhwc", ("conv", _conv)), ("conv2d_nhwc_slice", ("conv", _slice)), ("deconv2d_nhwc", ("conv", _deconv)),
+    ("conv2d_nhwc", ("conv", _conv)), ("conv2d_nhwc_stats", ("conv", _conv_stats)), ("bn_train_finalize", ("bn", _finalize)),
+    ("conv2d_nhwc_slice", ("conv", _slice)), ("deconv2d_nhwc", ("conv", _deconv)),
     ("conv2d_wgrad", ("wgrad", _wgrad)),
     ("bn_train_stats", ("bn", _stats)), ("bn_act_fwd", ("bn", _bn_fwd)), ("bn_act_bwd", ("bn", _bn_bwd)),
     ("channel_sums", ("bn", _sums)), ("add_nhwc", ("bn", _add)),

@@ -112,6 +112,8 @@ class TrainGraph(object):
         self.device = device
         self.use_meta = use_meta
         self.act_dtype = act_dtype
+        self.fuse_stats = True     # BatchNorm batch statistics in the conv epilogue (False: separate rd_bn_train_stats pass)
+        self._stats_bufs = {}
         self.pool = _Pool(device, act_dtype)
         self.packed = {}
         self.tape = []
@@ -231,6 +233,15 @@ class TrainGraph(object):
         return fn(*[self.P[n] for n in names])
 
     # ---- tape helpers ---------------------------------------------------------------------------------
+    def _stats_ws(self, C):
+        """Per-call fp32 workspace of the fused statistics (reused across steps in tape order, like the activations)."""
+        self._n += 1
+        key = "stats#%d" % self._n
+        t = self._stats_bufs.get(key)
+        if t is None or t.numel() < 1184 * 2 * C:
+            t = self._stats_bufs[key] = torch.zeros(1184 * 2 * C, device=self.device, dtype=torch.float32)
+        return t
+
     def _buf(self, tag, shape):
         self._n += 1
         return self.pool.get("%s#%d" % (tag, self._n), shape)
@@ -316,10 +327,17 @@ class TrainGraph(object):
         ci_p, co_p = x.shape[3], _cout_pad(co)
         N, Hp, Wp, _ = x.shape
         W_out = (Wp - 2) // stride_w
-        z = ops.conv2d_nhwc(x, self._w(wname, kinds[0], ci_p, co_p), relu=False, stride_w=stride_w,
-                            out=self._buf("z", (N, Hp, W_out + 2, co_p)))
-        coef = ops.bn_train_stats(z, P[bnname + "_gamma"], P[bnname + "_beta"], P[bnname + "_moving_mean"],
-                                  P[bnname + "_moving_var"])
+        if self.fuse_stats:
+            # batch statistics ride the conv epilogue (one full read of z less per layer); each layer owns its partials
+            z, part, nslots = ops.conv2d_nhwc_stats(x, self._w(wname, kinds[0], ci_p, co_p), stride_w=stride_w,
+                                                    out=self._buf("z", (N, Hp, W_out + 2, co_p)), ws=self._stats_ws(co_p))
+            coef = ops.bn_train_finalize(part, nslots, N, Hp - 2, W_out, co_p, P[bnname + "_gamma"], P[bnname + "_beta"],
+                                         P[bnname + "_moving_mean"], P[bnname + "_moving_var"])
+        else:
+            z = ops.conv2d_nhwc(x, self._w(wname, kinds[0], ci_p, co_p), relu=False, stride_w=stride_w,
+                                out=self._buf("z", (N, Hp, W_out + 2, co_p)))
+            coef = ops.bn_train_stats(z, P[bnname + "_gamma"], P[bnname + "_beta"], P[bnname + "_moving_mean"],
+                                      P[bnname + "_moving_var"])
         y = ops.bn_act_fwd(z, coef, relu=relu, res_before=res_before, out=self._buf("y", z.shape))
 
         def bwd():

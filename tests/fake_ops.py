@@ -63,6 +63,17 @@ def conv2d_nhwc(x_pad, w_packed, scale=None, shift=None, relu=False, residual_pa
     return _store(out, _epilogue(y, scale, shift, relu, residual_pad))
 
 
+def conv2d_nhwc_stats(x_pad, w_packed, out=None, stride_w=1, ws=None):
+    """Emulation of the fused conv + batch-statistics call: the 'partials' handed to bn_train_finalize are z itself."""
+    z = conv2d_nhwc(x_pad, w_packed, relu=False, out=out, stride_w=stride_w)
+    return z, z, -1
+
+
+def bn_train_finalize(partial, nslots, N, H, W, C, gamma=None, beta=None, moving_mean=None, moving_var=None, eps=None,
+                      momentum=None, coef=None):
+    return bn_train_stats(partial, gamma, beta, moving_mean, moving_var)
+
+
 def conv2d_nhwc_slice(x_pad, w_packed, out, c_off, relu=False, stride_w=1):
     w, k = _unpack_conv(w_packed)
     y = F.conv2d(_nchw(x_pad), w, stride=(1, stride_w), padding=k // 2)

@@ -509,3 +509,34 @@ def test_f16_layout_gather_and_meta_nhwc(ops):
     ref = torch.relu(meta_kernel_ref.meta_baseline_bias(data, coord, w0, b0, w1, b1) * sc[None, :, None, None] + sh[None, :, None, None])
     got = m[:, 1:-1, 1:-1, :].reshape(B, H, W, 9, C).permute(0, 4, 3, 1, 2).reshape(B, 576, H, W).float()
     assert m.dtype == F16 and float((got - ref).abs().max()) <= 2 ** -10 * float(ref.abs().max()) + 1e-3
+
+
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16], ids=["bf16", "f16"])
+@pytest.mark.parametrize("shape", [(2, 64, 64, 5, 300, 3, 1), (1, 128, 128, 7, 131, 3, 1), (2, 128, 128, 3, 150, 3, 2),
+                                   (1, 64, 128, 4, 140, 1, 2), (1, 576, 64, 3, 200, 1, 1), (2, 64, 64, 64, 2656, 3, 1),
+                                   (1, 128, 128, 1, 64, 3, 1)])
+def test_conv_epilogue_batch_statistics(ops, shape, dtype):
+    """rd_conv2d_nhwc_*_stats: same z, bit for bit, as the plain conv, and the fused partial sums finalize to the
+    coefficients the separate statistics pass computes from that z (fp32 summation order differs: 1e-5)."""
+    N, Ci, Co, H, W, ks, s = shape
+    g = torch.Generator(device="cuda").manual_seed(29)
+    x = torch.randn((N, Ci, H, W), device="cuda", generator=g) + 0.3
+    w = torch.randn((Co, Ci, ks, ks), device="cuda", generator=g) * (2.0 / (Ci * ks * ks)) ** 0.5
+    xp, wp = ops.to_nhwc_padded(x, dtype=dtype), ops.pack_conv_weight(w, dtype=dtype)
+    gamma, beta = torch.rand(Co, device="cuda", generator=g) + 0.5, torch.randn(Co, device="cuda", generator=g)
+    z0 = ops.conv2d_nhwc(xp, wp, relu=False, stride_w=s)
+    mm0, mv0 = torch.zeros(Co, device="cuda"), torch.ones(Co, device="cuda")
+    coef0 = ops.bn_train_stats(z0, gamma, beta, mm0, mv0)
+    z1, part, nslots = ops.conv2d_nhwc_stats(xp, wp, stride_w=s)
+    mm1, mv1 = torch.zeros(Co, device="cuda"), torch.ones(Co, device="cuda")
+    coef1 = ops.bn_train_finalize(part, nslots, N, H, W // s, Co, gamma, beta, mm1, mv1)
+    torch.cuda.synchronize()
+    assert torch.equal(z0, z1) and 0 < nslots <= 1184
+    for row, name in enumerate(("a", "b", "mean", "invstd", "var", "sum")):
+        ref = coef0[row]
+        assert float((coef1[row] - ref).abs().max()) <= 2e-5 * float(ref.abs().max()) + 1e-6, (name, shape)
+    assert torch.allclose(mm1, mm0, rtol=1e-5, atol=1e-7) and torch.allclose(mv1, mv0, rtol=1e-5, atol=1e-7)
+    # and against the definition, in float64, on the stored values
+    zf = ops.from_nhwc_padded(z1).double()
+    assert float((coef1[2].double() - zf.mean((0, 2, 3))).abs().max()) < 1e-5 * max(1.0, float(zf.abs().max()))
+    assert float((coef1[4].double() - zf.var((0, 2, 3), unbiased=False)).abs().max()) < 1e-4 * float(zf.var())
