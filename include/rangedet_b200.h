@@ -352,6 +352,12 @@ int rd_nchw_f32_to_nhwc_f16(const float* src, void* dst_pad, int N, int H, int W
                             rd_stream_t stream);
 int rd_gather_f32_to_f16(const float* src, const int* idx, void* dst, int64_t n, rd_stream_t stream);
 
+/* ---- Launch mode ------------------------------------------------------------------------------------
+ * The conv / wgrad / BatchNorm kernels are launched with programmatic dependent launch (each kernel's prologue and
+ * launch latency overlap the tail of its predecessor; csrc/rd_common.cuh).  rd_set_pdl(0) switches to plain stream
+ * order (diagnostics, A/B timing); returns the previous setting.  Default: on, unless the environment has RD_PDL=0. */
+int rd_set_pdl(int on);
+
 /* ---- tcgen05 self-test -------------------------------------------------------------------
  * D(128 x n) = A(128 x k) . B(n x k)^T with bf16 operands staged in shared memory in the
  * canonical no-swizzle K-major core-matrix layout, tcgen05.mma into TMEM, tcgen05.ld back.

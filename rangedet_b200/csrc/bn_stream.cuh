@@ -113,10 +113,12 @@ struct SRing {
     full = bars;
     my_units = (int)blockIdx.x < G.nunits ? (G.nunits - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
     if (threadIdx.x == 0) {
+      rd::pdl_trigger();
       for (int s = 0; s < STAGES; ++s) s_mbar_init(&full[s], 1);
       asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
+    rd::pdl_wait();   // programmatic dependent launch: the predecessor's tensors are complete from here on
     if (threadIdx.x == 0)
       for (int k = 0; k < STAGES && k < my_units; ++k) issue(G, k);
   }

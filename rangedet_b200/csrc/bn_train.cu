@@ -146,6 +146,8 @@ __global__ void __launch_bounds__(256) fwd_finalize_kernel(const float* __restri
                                                            const float* __restrict__ beta, float eps, float momentum,
                                                            float* __restrict__ moving_mean,
                                                            float* __restrict__ moving_var, float* __restrict__ coef) {
+  if (threadIdx.x == 0) rd::pdl_trigger();
+  rd::pdl_wait();
   const int c = blockIdx.x * 8 + (threadIdx.x >> 5);
   if (c >= C) return;
   double s, q;
@@ -330,6 +332,8 @@ __global__ void __launch_bounds__(256) bwd_finalize_kernel(const float* __restri
                                                            double count, const float* __restrict__ coef,
                                                            float* __restrict__ coef2, float* __restrict__ dgamma,
                                                            float* __restrict__ dbeta) {
+  if (threadIdx.x == 0) rd::pdl_trigger();
+  rd::pdl_wait();
   const int c = blockIdx.x * 8 + (threadIdx.x >> 5);
   if (c >= C) return;
   double s, q;
@@ -440,6 +444,9 @@ static int grid_for(const Geo& g) {
 
 }  // namespace bn_<storage type>
 namespace bn = RD_ACT_NS(bn);
+// the per-channel finalize kernels ((C + 7) / 8 blocks of 8 warps), launched with the PDL attribute
+#define RD_CUDA_LAUNCH_FINALIZE(kernel, stream_, ...) \
+  RD_CUDA(rd::launch(kernel, dim3((C + 7) / 8), dim3(256), 0, stream_, __VA_ARGS__))
 
 extern "C" {
 
@@ -462,12 +469,13 @@ int RD_ACT_FN(rd_bn_train_stats_nhwc_, )(const void* z_pad, int N, int H, int W,
     const size_t smem = bn::sgeo_smem(sg, 1);
     if (bn::stream_prepare(bn::s_stats_kernel, smem)) return 1;
     grid = bn::stream_grid(sg);
-    bn::s_stats_kernel<<<grid, bn::SNT, smem, s>>>(static_cast<const act_t*>(z_pad), sg, static_cast<float*>(workspace));
+    RD_CUDA(rd::launch(bn::s_stats_kernel, dim3(grid), dim3(bn::SNT), smem, s, static_cast<const act_t*>(z_pad), sg,
+                       static_cast<float*>(workspace)));
   } else {
     bn::stats_kernel<<<grid, g.ppb * g.cgs, 0, s>>>(static_cast<const act_t*>(z_pad), g, 1,
                                                      static_cast<float*>(workspace));
   }
-  bn::fwd_finalize_kernel<<<(C + 7) / 8, 256, 0, s>>>(static_cast<const float*>(workspace), grid, C,
+  RD_CUDA_LAUNCH_FINALIZE(bn::fwd_finalize_kernel, s, static_cast<const float*>(workspace), grid, C,
                                                           (double)N * H * W, gamma, beta, eps, momentum, moving_mean,
                                                           moving_var, coef);
   rd::count_launch(2);
@@ -483,7 +491,7 @@ int rd_bn_train_finalize(const float* partial, int nslots, int N, int H, int W, 
   RD_REQUIRE(partial && coef, "rd_bn_train_finalize: null pointer");
   RD_REQUIRE(nslots > 0 && nslots <= bn::MAX_BLOCKS, "rd_bn_train_finalize: nslots %d out of range", nslots);
   if (rd_check_device()) return 1;
-  bn::fwd_finalize_kernel<<<(C + 7) / 8, 256, 0, rd::as_stream(stream)>>>(partial, nslots, C, (double)N * H * W, gamma, beta, eps,
+  RD_CUDA_LAUNCH_FINALIZE(bn::fwd_finalize_kernel, rd::as_stream(stream), partial, nslots, C, (double)N * H * W, gamma, beta, eps,
                                                                          momentum, moving_mean, moving_var, coef);
   rd::count_launch();
   return rd::check_launch("rd_bn_train_finalize");
@@ -503,9 +511,9 @@ int RD_ACT_FN(rd_bn_act_fwd_nhwc_, )(const void* z_pad, const float* coef, const
     const bn::SGeo sg = bn::make_sgeo(N, H, W, C, nt);
     const size_t smem = bn::sgeo_smem(sg, nt);
     if (bn::stream_prepare(bn::s_fwd_apply_kernel, smem)) return 1;
-    bn::s_fwd_apply_kernel<<<bn::stream_grid(sg), bn::SNT, smem, rd::as_stream(stream)>>>(
-        static_cast<const act_t*>(z_pad), coef, static_cast<const act_t*>(res_before),
-        static_cast<const act_t*>(res_after), static_cast<act_t*>(y_pad), sg, relu ? 1 : 0);
+    RD_CUDA(rd::launch(bn::s_fwd_apply_kernel, dim3(bn::stream_grid(sg)), dim3(bn::SNT), smem, rd::as_stream(stream),
+                       static_cast<const act_t*>(z_pad), coef, static_cast<const act_t*>(res_before),
+                       static_cast<const act_t*>(res_after), static_cast<act_t*>(y_pad), sg, relu ? 1 : 0));
   } else {
     bn::fwd_apply_kernel<<<grid, g.ppb * g.cgs, 0, rd::as_stream(stream)>>>(
         static_cast<const act_t*>(z_pad), coef, static_cast<const act_t*>(res_before),
@@ -541,15 +549,14 @@ int RD_ACT_FN(rd_bn_act_bwd_nhwc_, )(const void* dy_pad, const void* y_mask_pad,
     const size_t smem = bn::sgeo_smem(sg, nt);
     if (bn::stream_prepare(bn::s_bwd_reduce_kernel, smem) || bn::stream_prepare(bn::s_bwd_apply_kernel, smem)) return 1;
     const int sgrid = bn::stream_grid(sg);
-    bn::s_bwd_reduce_kernel<<<sgrid, bn::SNT, smem, s>>>(dy, ym, z, coef, sg, mask_mode, partial);
-    bn::bwd_finalize_kernel<<<(C + 7) / 8, 256, 0, s>>>(partial, sgrid, C, (double)N * H * W, coef, coef2, dgamma,
+    RD_CUDA(rd::launch(bn::s_bwd_reduce_kernel, dim3(sgrid), dim3(bn::SNT), smem, s, dy, ym, z, coef, sg, mask_mode, partial));
+    RD_CUDA_LAUNCH_FINALIZE(bn::bwd_finalize_kernel, s, partial, sgrid, C, (double)N * H * W, coef, coef2, dgamma,
                                                             dbeta);
-    bn::s_bwd_apply_kernel<<<sgrid, bn::SNT, smem, s>>>(dy, ym, z, coef, coef2, sg, mask_mode,
-                                                        static_cast<act_t*>(dz_pad), dz_halo_w,
-                                                        static_cast<act_t*>(g_out_pad));
+    RD_CUDA(rd::launch(bn::s_bwd_apply_kernel, dim3(sgrid), dim3(bn::SNT), smem, s, dy, ym, z, coef, (const float*)coef2, sg,
+                       mask_mode, static_cast<act_t*>(dz_pad), dz_halo_w, static_cast<act_t*>(g_out_pad)));
   } else {
     bn::bwd_reduce_kernel<<<grid, g.ppb * g.cgs, 0, s>>>(dy, ym, z, coef, g, mask_mode, partial);
-    bn::bwd_finalize_kernel<<<(C + 7) / 8, 256, 0, s>>>(partial, grid, C, (double)N * H * W, coef, coef2, dgamma,
+    RD_CUDA_LAUNCH_FINALIZE(bn::bwd_finalize_kernel, s, partial, grid, C, (double)N * H * W, coef, coef2, dgamma,
                                                             dbeta);
     const int64_t units = (int64_t)g.N * g.H * g.nseg;
     const int grid2 = (int)(units < 8 * 148 ? units : 8 * 148);
@@ -574,7 +581,7 @@ int RD_ACT_FN(rd_channel_sums_nhwc_, )(const void* x_pad, int N, int H, int W, i
   float* partial = static_cast<float*>(workspace);
   float* coef = partial + (size_t)bn::MAX_BLOCKS * 2 * C;
   bn::stats_kernel<<<grid, g.ppb * g.cgs, 0, s>>>(static_cast<const act_t*>(x_pad), g, 1, partial);
-  bn::fwd_finalize_kernel<<<(C + 7) / 8, 256, 0, s>>>(partial, grid, C, (double)N * H * W, nullptr, nullptr, 1e-5f,
+  RD_CUDA_LAUNCH_FINALIZE(bn::fwd_finalize_kernel, s, partial, grid, C, (double)N * H * W, nullptr, nullptr, 1e-5f,
                                                           0.f, nullptr, nullptr, coef);
   RD_CUDA(cudaMemcpyAsync(sums, coef + 5 * (size_t)C, (size_t)C * sizeof(float), cudaMemcpyDeviceToDevice, s));
   rd::count_launch(2);

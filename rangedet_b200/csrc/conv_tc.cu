@@ -108,6 +108,7 @@ conv_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CU
   extern __shared__ unsigned char smem_raw[];
   unsigned char* base = smem_raw + ((1024u - (tc::smem_u32(smem_raw) & 1023u)) & 1023u);
   const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+  if (t == 0) rd::pdl_trigger();   // the next kernel may take SMs as this grid's CTAs leave them
   auto tick = [&]() -> long long { return PROF ? clock64() : 0ll; };
   long long pc1 = 0, pc2 = 0, pc3 = 0;
   const long long t_begin = tick();
@@ -164,6 +165,7 @@ conv_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CU
     tc::tmem_alloc(&M.tmem_slot, 512);
     tc::tmem_relinquish();
   }
+  rd::pdl_wait();   // everything above touched only shared memory / TMEM / kernel parameters
   for (int c = t; c < P.Cout; c += NTHREADS) {
     M.scale[c] = scale ? __ldg(scale + c) : 1.f;
     M.shift[c] = shift ? __ldg(shift + c) : 0.f;
@@ -631,8 +633,8 @@ static int run(int mode, const void* x_pad, const void* w_packed, const float* s
     if (!d_prof) RD_CUDA(cudaMalloc(&d_prof, 1024 * 16 * sizeof(long long)));
     RD_CUDA(cudaMemsetAsync(d_prof, 0, 1024 * 16 * sizeof(long long), stream));
     P.prof = d_prof;
-    conv_kernel<true><<<grid, NTHREADS, smem, stream>>>(tm_x, tm_w, tm_y, scale, shift, res,
-                                                        reinterpret_cast<act_t*>(y_int), stats, P);
+    RD_CUDA(rd::launch(conv_kernel<true>, dim3(grid), dim3(NTHREADS), smem, stream, tm_x, tm_w, tm_y, scale, shift, res,
+                       reinterpret_cast<act_t*>(y_int), stats, P));
     RD_CUDA(cudaStreamSynchronize(stream));
     static long long h[1024 * 16];
     RD_CUDA(cudaMemcpy(h, d_prof, sizeof(long long) * 16 * grid, cudaMemcpyDeviceToHost));
@@ -647,8 +649,8 @@ static int run(int mode, const void* x_pad, const void* w_packed, const float* s
             P.Cin, P.Cout, P.npipes, P.nsa, P.nsb, P.b_resident, tiles, m[0] / tiles, m[1] / tiles, m[2] / tiles, m[4] / tiles,
             m[5] / tiles, m[7] / tiles, m[6] / tiles, m[8] / tiles, m[9] / tiles, m[10] / tiles, m[11] / tiles);
   } else {
-    conv_kernel<false><<<grid, NTHREADS, smem, stream>>>(tm_x, tm_w, tm_y, scale, shift, res,
-                                                         reinterpret_cast<act_t*>(y_int), stats, P);
+    RD_CUDA(rd::launch(conv_kernel<false>, dim3(grid), dim3(NTHREADS), smem, stream, tm_x, tm_w, tm_y, scale, shift, res,
+                       reinterpret_cast<act_t*>(y_int), stats, P));
   }
   rd::count_launch();
   return rd::check_launch("rd_conv");

@@ -70,6 +70,7 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ C
   unsigned char* base = smem_raw + ((1024u - (tc::smem_u32(smem_raw) & 1023u)) & 1023u);
   Misc& M = *reinterpret_cast<Misc*>(base + P.nstages * P.stage_bytes);
   const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+  if (t == 0) rd::pdl_trigger();
   const int job_id = blockIdx.x / P.nsplit, split = blockIdx.x % P.nsplit;
   const Job J = P.jobs[job_id];
   const int t_begin = (int)((int64_t)P.ntiles * split / P.nsplit);
@@ -90,6 +91,7 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ C
   __syncthreads();
   tc::tc_fence_after();
   const uint32_t tmem_base = M.tmem_slot;
+  rd::pdl_wait();   // prologue done: only now are the predecessors' tensors (and the partial buffer) touched
 
   if (warp == 0) {
     // ===== TMA producer =====
@@ -178,6 +180,8 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ C
 
 // out[i] = sum over splits of partial[s][i], fixed order
 __global__ void reduce_kernel(const float4* __restrict__ partial, float4* __restrict__ out, int n4, int nsplit) {
+  if (threadIdx.x == 0) rd::pdl_trigger();
+  rd::pdl_wait();
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += gridDim.x * blockDim.x) {
     float4 a = partial[i];
     for (int s = 1; s < nsplit; ++s) {
@@ -289,10 +293,10 @@ int RD_ACT_FN(rd_conv2d_wgrad_nhwc_, )(const void* a_pad, const void* b_pad, flo
   RD_REQUIRE(smem <= 227 * 1024, "rd_conv2d_wgrad: shared memory layout exceeds 227 KB (%zu)", smem);
   RD_CUDA(rd::smem_optin(wg::wgrad_kernel, smem));
   float* partial = static_cast<float*>(workspace);
-  wg::wgrad_kernel<<<P.njobs * P.nsplit, wg::NTHREADS, smem, s>>>(tm_a, tm_b, partial, P);
+  RD_CUDA(rd::launch(wg::wgrad_kernel, dim3(P.njobs * P.nsplit), dim3(wg::NTHREADS), smem, s, tm_a, tm_b, partial, P));
   const int n4 = P.ntaps * CA * CB / 4;
-  wg::reduce_kernel<<<(n4 + 255) / 256 < 592 ? (n4 + 255) / 256 : 592, 256, 0, s>>>(
-      reinterpret_cast<const float4*>(partial), reinterpret_cast<float4*>(g), n4, P.nsplit);
+  RD_CUDA(rd::launch(wg::reduce_kernel, dim3((n4 + 255) / 256 < 592 ? (n4 + 255) / 256 : 592), dim3(256), 0, s,
+                     reinterpret_cast<const float4*>(partial), reinterpret_cast<float4*>(g), n4, (int)P.nsplit));
   rd::count_launch(2);
   return rd::check_launch("rd_conv2d_wgrad");
 }

@@ -1,5 +1,6 @@
 // Library-level entry points of librangedet_b200.so (see include/rangedet_b200.h).
 #include <stdarg.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "../../include/rangedet_b200.h"
@@ -19,6 +20,16 @@ void set_error(const char* fmt, ...) {
 
 void count_launch(int n) { g_launches += (uint64_t)n; }
 
+static int g_pdl = -1;   // -1: not decided yet (RD_PDL environment variable, default on)
+
+bool pdl_enabled() {
+  if (g_pdl < 0) {
+    const char* e = getenv("RD_PDL");
+    g_pdl = (e && e[0] == '0') ? 0 : 1;
+  }
+  return g_pdl != 0;
+}
+
 int check_launch(const char* what) {
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) {
@@ -37,6 +48,12 @@ int rd_version(void) { return 1; }
 const char* rd_last_error(void) { return rd::g_err; }
 
 uint64_t rd_launch_count(void) { return rd::g_launches; }
+
+int rd_set_pdl(int on) {
+  const int prev = rd::pdl_enabled() ? 1 : 0;
+  rd::g_pdl = on ? 1 : 0;
+  return prev;
+}
 
 int rd_check_device(void) {
   // Result cached per device: cudaGetDeviceProperties costs ~1 ms and this guards every launch.

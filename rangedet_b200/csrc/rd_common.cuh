@@ -12,6 +12,7 @@ namespace rd {
 
 void set_error(const char* fmt, ...);
 void count_launch(int n = 1);
+bool pdl_enabled();   // programmatic dependent launch on (default) unless RD_PDL=0
 
 // Returns 0 if ok; records the message otherwise.
 int check_launch(const char* what);
@@ -36,6 +37,34 @@ inline cudaError_t smem_optin(F* fn, size_t bytes) {
   if (e == cudaSuccess) g = bytes;
   return e;
 }
+
+// ---- Programmatic dependent launch (PDL) ---------------------------------------------------------------------
+// The training step is ~950 dependent kernels of 5-100 us.  Launched with the programmatic-stream-serialization
+// attribute, kernel N+1 may start as soon as every CTA of kernel N has called pdl_trigger() (or exited): its CTAs take
+// the SMs that kernel N's CTAs leave, run their prologue (barrier init, TMEM allocation, descriptor prefetch) and
+// then block in pdl_wait() until kernel N has completed and flushed -- launch latency and prologue hide behind the
+// tail of the predecessor.  Rules every kernel launched through rd::launch follows: pdl_trigger() first thing,
+// pdl_wait() by ALL threads before the first access to global memory that another kernel writes or reads.
+// (A kernel completes only after its own wait returned, so completion of N implies completion of N-1: transitive.)
+#ifdef __CUDACC__
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);
+}
+#endif
 
 }  // namespace rd
 

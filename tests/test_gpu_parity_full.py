@@ -302,14 +302,76 @@ def test_cfg5_train_step_end_to_end_at_full_size(ops, dtype):
     os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
     with open(os.path.join(ROOT, "gpurun_out", "parity_e2e_%s.json" % tag), "w") as f:
         json.dump(res, f, indent=1)
-    tol_head = {torch.float16: 2e-2, torch.bfloat16: 1.5e-1}[dtype]
-    tol_loss = {torch.float16: 2e-3, torch.bfloat16: 2e-2}[dtype]
-    cos_min = {torch.float16: 0.99, torch.bfloat16: 0.9}[dtype]
+    # Observed (profiles/r02_parity_*.json): f16 head outputs 1.4-2.9e-2 rms, loss sums 1e-4-3e-4, gradient cosines min 0.91 /
+    # median 0.97; bf16 9-18e-2, 1e-3, 0.48 / 0.81.  Two correct implementations of a ~40-layer random-init ReLU network
+    # that differ by one storage rounding per layer disagree on a fraction of the ReLU masks, hence this much in deep
+    # gradients; the TIGHT checks are the teacher-forced test above (every layer within one rounding) and the derivative
+    # test below (our backward is the derivative of our forward).  A composition error -- a mis-routed skip, a missing
+    # gradient accumulation, a stale buffer -- drives the affected cosines to ~0 and the loss sums off by O(1).
+    tol_head = {torch.float16: 5e-2, torch.bfloat16: 2.5e-1}[dtype]
+    tol_loss = {torch.float16: 1e-3, torch.bfloat16: 5e-3}[dtype]
+    cos_min, cos_med = {torch.float16: (0.85, 0.95), torch.bfloat16: (0.35, 0.7)}[dtype]
     assert max(res["head"].values()) < tol_head, res["head"]
     for a, b in zip(losses_g, losses_r):
         assert abs(a - b) <= tol_loss * abs(b) + 1e-6, (losses_g, losses_r)
+    cs = sorted(v["cos"] for v in res["grads"].values())
     low = {k: v for k, v in res["grads"].items() if not (v["cos"] >= cos_min)}
     assert len(res["grads"]) >= 270 and not low, sorted(low.items(), key=lambda kv: kv[1]["cos"])[:8]
+    assert cs[len(cs) // 2] >= cos_med, cs[len(cs) // 2]
+
+
+def test_cfg5_backward_is_the_derivative_of_the_forward(ops):
+    """Self-consistency of the composed step at B=2, 64x2656 (fp16 storage), independent of any other implementation and of
+    the ReLU-mask chaos between implementations: for the linear loss L(theta) = sum <out_l(theta), c_l> the flat gradient g
+    returned by the backward graph must satisfy  L(theta + D) - L(theta - D) = 2 <g, D>  for small random D.  One direction
+    per parameter group (head towers, residual stages, aggregation stages, Meta-Kernel unit, BatchNorm affine), so a wrong
+    gradient route in any of them shows up in its own number."""
+    from oracle import dla_ref
+    from rangedet_b200 import train
+    B, dtype = 2, torch.float16
+    P = dla_ref.make_params(seed=0, device="cuda")
+    data, coord, d_cls, d_reg = _inputs(B)
+    step = train.GraphedTrainStep({k: v.clone() for k, v in P.items()}, B, H, W, lr=0.0, capture=False, act_dtype=dtype, with_loss=False)
+    cot = [d.to(dtype).float() for d in d_cls + d_reg]       # the kernels store the incoming gradient in fp16
+
+    def L():
+        cls, reg = step.forward(data, coord)
+        return float(sum((o.double() * c.double()).sum() for o, c in zip(list(cls) + list(reg), cot)))
+
+    L0 = L()
+    for dst, src in zip(step.d_cls + step.d_reg, d_cls + d_reg):
+        dst.copy_(src)
+    step._bwd()
+    torch.cuda.synchronize()
+    g = step.flat.clone().double()
+    theta0 = step.flatP.clone()
+    groups = {"head": lambda k: k.startswith("rpn_") and k.endswith("_weight"),
+              "res_stages": lambda k: k.startswith("res") and k.endswith("_weight") and "mlp" not in k,
+              "agg_stages": lambda k: k.startswith("agg") and k.endswith("_weight"),
+              "meta_unit": lambda k: "mlp" in k or "aggregation" in k or "point_wise" in k,
+              "bn_affine": lambda k: k.endswith(("_gamma", "_beta")) and "point_wise" not in k}
+    gen = torch.Generator(device="cuda").manual_seed(77)
+    res = {"L0": L0}
+    for name, sel in groups.items():
+        D = torch.zeros_like(theta0)
+        for k in step.names:
+            if sel(k):
+                o, n = step.offsets[k], step.P[k].numel()
+                scale = float(theta0[o:o + n].abs().mean()) + 1e-3
+                D[o:o + n] = torch.randn(n, device="cuda", generator=gen) * (2e-2 * scale)
+        assert float(D.abs().max()) > 0, name
+        step.flatP.copy_(theta0 + D)
+        Lp = L()
+        step.flatP.copy_(theta0 - D)
+        Lm = L()
+        step.flatP.copy_(theta0)
+        fd, an = Lp - Lm, 2.0 * float((g * D.double()).sum())
+        res[name] = {"finite_difference": fd, "gradient_dot_direction": an, "rel": abs(fd - an) / max(abs(an), abs(fd), 1e-30)}
+    os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+    with open(os.path.join(ROOT, "gpurun_out", "parity_derivative_f16.json"), "w") as f:
+        json.dump(res, f, indent=1)
+    bad = {k: v for k, v in res.items() if k != "L0" and not (v["rel"] < 0.15)}
+    assert not bad, res
 
 
 def test_cfg4_forward_b8_at_full_size(ops):
