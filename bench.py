@@ -221,7 +221,7 @@ def _max_over_ranks(ms, world, dev):
     return ms
 
 
-def make_step(B, dev, world, dtype, capture=True, ar_ev=None):
+def make_step(B, dev, world, dtype, capture=True):
     """symbol.TrainSymbol.bind() on the shipped config values -> train.GraphedTrainStep (the reference-facing API)."""
     import torch
     import torch.distributed as dist
@@ -231,12 +231,8 @@ def make_step(B, dev, world, dtype, capture=True, ar_ev=None):
     pB.batch_image = pR.batch_image = B
     sym = symbol.RangeRCNN(pR).get_train_symbol(symbol.DLABackbone(pB), symbol.RangeRpnHead(pR))
 
-    def allreduce(flat):   # SUM; the 1/world of the average is folded into the optimiser's rescale_grad
-        if ar_ev is not None:
-            ar_ev[0].record()
-        dist.all_reduce(flat, op=dist.ReduceOp.SUM)
-        if ar_ev is not None:
-            ar_ev[1].record()
+    def allreduce(flat):   # SUM of one bucket (head | backbone), asynchronous: the head's exchange overlaps the backbone's
+        return dist.all_reduce(flat, op=dist.ReduceOp.SUM, async_op=True)   # backward; 1/world rides rescale_grad
 
     P = make_params(seed=0, device=dev)
     kw = dict(act_dtype=dtype) if dtype is not None else {}
@@ -251,8 +247,7 @@ def train_leg(args, rank, world, dev, B, dtype, steps, warmup, with_clocks):
     import numpy as np
     import torch
     from rangedet_b200 import _lib, synth
-    ar_ev = [torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)]
-    step, sym = make_step(B, dev, world, dtype, ar_ev=ar_ev)
+    step, sym = make_step(B, dev, world, dtype)
     step.set_targets(synth.rpn_targets(B, seed=500 + rank))
     g = torch.Generator(device=dev).manual_seed(600 + rank)
     data = torch.randn((B, 8, H, W_PAD), device=dev, generator=g)
@@ -277,7 +272,8 @@ def train_leg(args, rank, world, dev, B, dtype, steps, warmup, with_clocks):
     per_step = sum(step.launches.values()) if step.launches else None
     res = {"value": B * world * steps / (ms * 1e-3), "ms_per_step": ms / steps, "steps": steps, "batch_per_gpu": B,
            "parameters": int(step.flatP.numel()), "allreduce_bytes": int(step.flat.numel() * 4) if world > 1 else 0,
-           "allreduce_ms": ar_ev[0].elapsed_time(ar_ev[1]) if world > 1 else 0.0,
+           "allreduce": "two buckets (head %.1f MB overlapping the backbone backward, backbone %.1f MB)" % (
+               (step.flat.numel() - step.head_lo) * 4 / 1e6, step.head_lo * 4 / 1e6) if step.split_bwd else "none",
            "algorithmic_TFLOPs_per_gpu": FLOP_STEP_PER_FRAME * B / (ms / steps * 1e-3) / 1e12,
            "launches_per_step": per_step, "launches_by_graph": step.launches,
            "cls_loss": float(sum(o["cls_loss"].sum() for o in loss)), "reg_loss": float(sum(o["reg_loss"].sum() for o in loss)),

@@ -544,6 +544,7 @@ class TrainGraph(object):
             self._acc(agg3, dcat[..., c:c + 64].contiguous())
 
         self.tape.append(cat_bwd)
+        self.head_tape_start = len(self.tape)     # tape entries from here on belong to the RPN head towers
         self.head_bwd = []
         cls_logit, bbox_delta = [], []
         for lvl, f in enumerate([cat, agg2a, agg2]):
@@ -570,6 +571,35 @@ class TrainGraph(object):
         self._join_side()
         if self.flat_grads:   # one launch: every parameter gradient -> the flat (all-reduce) buffer
             ops.gather_f32(self.arena, self.gmap, self.flat_g)
+        return self.pgrads
+
+    def head_split(self):
+        """Element offset in the flat buffers where the RPN head's parameters start: names are sorted, so the head
+        (`rpn_*`, ~60 % of the parameters) is the trailing contiguous block.  Flat mode only."""
+        names = sorted(self.offsets)
+        first = next(i for i, n in enumerate(names) if n.startswith("rpn_"))
+        assert all(n.startswith("rpn_") for n in names[first:]) and not any(n.startswith("rpn_") for n in names[:first])
+        return self.offsets[names[first]]
+
+    def backward_head(self, d_cls, d_reg):
+        """First half of backward(): the head towers only (the END of the tape), their parameter gradients gathered into
+        flat_g[head_split():] -- so that their all-reduce can overlap backward_body() (flat mode)."""
+        for kind, lvl, b, _ in self.head_bwd:
+            b(d_cls[lvl] if kind == "cls" else d_reg[lvl])
+        body, head = self.tape[:self.head_tape_start], self.tape[self.head_tape_start:]
+        for fn in reversed(head):
+            fn()
+        self.tape = body
+        self._join_side()
+        lo = self.head_split()
+        ops.gather_f32(self.arena, self.gmap[lo:], self.flat_g[lo:])
+
+    def backward_body(self):
+        """Second half: backbone + aggregation stages, gradients into flat_g[:head_split()]."""
+        self.run_tape()
+        self._join_side()
+        lo = self.head_split()
+        ops.gather_f32(self.arena, self.gmap[:lo], self.flat_g[:lo])
         return self.pgrads
 
 
@@ -626,13 +656,16 @@ class GraphedTrainStep(object):
     trainable parameters live in ONE flat fp32 buffer (`params[name]` become views of it), TrainGraph runs in flat
     mode (one gather launch packs all bf16 operands, one collects all gradients) and the MXNet SGD-momentum
     update is one launch (rd_sgd_mom_update) whose learning rate is read from device memory (set_lr).  With
-    `allreduce` given, the flat gradient buffer is summed across ranks between backward and update by one NCCL
-    all-reduce and averaged through rescale_grad / world_size (the reference: hvd.DistributedOptimizer,
-    tools/train.py:364-368)."""
+    `allreduce` given, the flat gradient buffer is summed across ranks between backward and update and averaged through
+    rescale_grad / world_size (the reference: hvd.DistributedOptimizer, tools/train.py:364-368).  `allreduce(view)` must
+    SUM the given contiguous view of the flat buffer over ranks; it may return a handle with `.wait()` (e.g.
+    dist.all_reduce(..., async_op=True)): with world_size > 1 the captured backward is then split head | backbone and the
+    head's exchange overlaps the backbone's backward kernels (two bucket all-reduces per step)."""
 
     def __init__(self, params, batch, H, W, lr, momentum=0.9, wd=1e-5, clip_gradient=35.0, rescale_grad=1.0 / 128.0,
                  device="cuda", use_meta=True, allreduce=None, world_size=1, with_loss=True, overlap_wgrad=True,
-                 loss_hyper=None, gt_name="gt_bbox_veh_for_iou_pred", capture=True, act_dtype=torch.bfloat16):
+                 loss_hyper=None, gt_name="gt_bbox_veh_for_iou_pred", capture=True, act_dtype=torch.bfloat16,
+                 overlap_allreduce=True):
         self.P = params
         self.allreduce = allreduce
         self.with_loss = with_loss
@@ -668,6 +701,7 @@ class GraphedTrainStep(object):
         self.d_reg = [torch.zeros((batch, 8, H, W // s), device=device) for s in STRIDES]
         self.targets, self.loss_out = None, None
         self.launches = None   # kernels per graph replay (captured mode)
+        self.split_bwd = False
         if with_loss:
             z = lambda *shape: torch.zeros(shape, device=device)
             self.targets = {gt_name: z(batch, 200, 8 if self.loss_hyper["iou_type"] == "bev" else 7)}
@@ -729,8 +763,19 @@ class GraphedTrainStep(object):
         with torch.cuda.graph(self.g_fwd, pool=self.pool, **mode):
             self._fwd()
         c1 = _lib.launch_count()
-        with torch.cuda.graph(self.g_bwd, pool=self.pool, **mode):
-            self._bwd()
+        # With a gradient exchange the backward is captured in two graphs -- head towers | backbone -- so that the
+        # all-reduce of the head's gradients (~60 % of the parameters) runs while the backbone's backward computes
+        self.split_bwd = self.allreduce is not None and world_size > 1 and overlap_allreduce
+        if self.split_bwd:
+            self.g_bwd_head, self.g_bwd_body = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self.g_bwd_head, pool=self.pool, **mode):
+                self._bwd_head()
+            with torch.cuda.graph(self.g_bwd_body, pool=self.pool, **mode):
+                self.tg.backward_body()
+            self.head_lo = self.tg.head_split()
+        else:
+            with torch.cuda.graph(self.g_bwd, pool=self.pool, **mode):
+                self._bwd()
         c2 = _lib.launch_count()
         with torch.cuda.graph(self.g_upd, pool=self.pool, **mode):
             self._update()
@@ -748,6 +793,11 @@ class GraphedTrainStep(object):
         if not self.tg.flat_grads:
             ks = [k for k in self.names if k in grads]
             torch._foreach_copy_([self.gviews[k] for k in ks], [grads[k].reshape(self.P[k].shape) for k in ks])
+
+    def _bwd_head(self):
+        if self.with_loss:
+            rpn_loss_levels(self.out[0], self.out[1], self.targets, out=self.loss_out, hyper=self.loss_hyper, gt_name=self.gt_name)
+        self.tg.backward_head(self.d_cls, self.d_reg)
 
     def _update(self):
         ops.sgd_mom_update(self.flatP, self.flat, self.flat_m, self.flat_wd, self.hyper)
@@ -788,12 +838,25 @@ class GraphedTrainStep(object):
         if not self.with_loss:
             for dst, src in zip(self.d_cls + self.d_reg, list(d_cls) + list(d_reg)):
                 dst.copy_(src, non_blocking=True)
+        if self.split_bwd:
+            # head backward | all-reduce(head gradients) overlapping the backbone backward | all-reduce(backbone gradients)
+            self.g_bwd_head.replay()
+            h1 = self.allreduce(self.flat[self.head_lo:])
+            self.g_bwd_body.replay()
+            h2 = self.allreduce(self.flat[:self.head_lo])
+            for h in (h1, h2):      # an asynchronous exchange returns a handle: the update must wait for it
+                if h is not None and hasattr(h, "wait"):
+                    h.wait()
+            self.g_upd.replay()
+            return
         if self.capture:
             self.g_bwd.replay()
         else:
             self._bwd()
         if self.allreduce is not None:
-            self.allreduce(self.flat)
+            h = self.allreduce(self.flat)
+            if h is not None and hasattr(h, "wait"):
+                h.wait()
         if self.capture:
             self.g_upd.replay()
         else:

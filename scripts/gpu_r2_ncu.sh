@@ -1,0 +1,11 @@
+#!/bin/bash
+# round 2 ncu captures: launch list of two replayed cfg-5 steps + `--set full` of the dominant kernels (B=2, fp16)
+mkdir -p gpurun_out
+timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none --profile-from-start off --csv \
+  --log-file gpurun_out/r02_train_step_launches.csv python scripts/ncu_targets.py step > gpurun_out/ncu_step.log 2>&1; echo "ncu launch list rc=$?"
+tail -2 gpurun_out/ncu_step.log
+timeout 900 ncu --set full --clock-control none --import-source on --profile-from-start off -o gpurun_out/r02_kernels -f \
+  python scripts/ncu_targets.py kernels > gpurun_out/ncu_kernels.log 2>&1; echo "ncu full rc=$?"
+python scripts/ncu_summary.py gpurun_out/r02_kernels.ncu-rep gpurun_out/r02_kernels_ncu_full.csv gpurun_out/r02_kernels_traffic.json
+python scripts/launch_summary.py gpurun_out/r02_train_step_launches.csv > gpurun_out/r02_train_step_launch_summary.txt 2>&1; head -40 gpurun_out/r02_train_step_launch_summary.txt
+ls -la gpurun_out/*.ncu-rep

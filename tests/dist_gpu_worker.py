@@ -34,8 +34,16 @@ def main():
         dist.all_gather(out, t.contiguous())
         return out
 
-    def allreduce(flat):
-        dist.all_reduce(flat, op=dist.ReduceOp.SUM)
+    def allreduce(flat):       # asynchronous: the step overlaps the head bucket with the backbone's backward
+        return dist.all_reduce(flat, op=dist.ReduceOp.SUM, async_op=True)
+
+    def local_backward():
+        """loss + backward of the frames already in the static buffers, no exchange"""
+        if step.split_bwd:
+            step.g_bwd_head.replay()
+            step.g_bwd_body.replay()
+        else:
+            step.g_bwd.replay()
 
     P = make_params(seed=10 + rank, device=dev)               # every rank initialises differently
     for k in P:                                               # ... including the moving statistics
@@ -63,7 +71,7 @@ def main():
         T, data, xyz = frames(r)
         step.set_targets(T)
         step.forward(data, xyz)
-        step.g_bwd.replay()
+        local_backward()
         torch.cuda.synchronize()
         return step.flat.clone()
 
@@ -82,12 +90,16 @@ def main():
     T, data, xyz = frames(rank)
     step.set_targets(T)
     step.forward(data, xyz)
-    step.g_bwd.replay()
-    step.allreduce(step.flat)
+    res["split_backward"] = bool(step.split_bwd)
+    hyper = step.hyper.clone()
+    step.hyper[0] = 0.0                      # lr 0: the exchange as train_step runs it (two overlapped buckets), weights untouched
+    step.backward_update()
     torch.cuda.synchronize()
     res["allreduce_bitexact_sum"] = bool(torch.equal(step.flat, want_sum))
     res["grad_nonzero"] = bool(float(want_sum.abs().max()) > 0)
-    step.g_upd.replay()
+    step.hyper.copy_(hyper)
+    step.flat_m.zero_()
+    step.g_upd.replay()                      # the real update on the exchanged gradients
     torch.cuda.synchronize()
     upd = gather(step.flatP)
     res["params_equal_after_update"] = all(torch.equal(upd[0], u) for u in upd)

@@ -27,7 +27,7 @@ def test_torchrun_nccl_exchange_bitexact(world):
     with open(os.path.join(ROOT, "gpurun_out", "dist_parity_n%d.json" % world), "w") as f:
         json.dump(res, f, indent=1)
     for k in ("init_differs", "bcast_args_equal", "bcast_aux_equal", "single_rank_recompute_bitexact", "allreduce_bitexact_sum",
-              "grad_nonzero", "params_equal_after_update", "params_moved", "aux_drifted", "aux_equal_after_average",
+              "grad_nonzero", "split_backward", "params_equal_after_update", "params_moved", "aux_drifted", "aux_equal_after_average",
               "lockstep_second_step"):
         assert res[k] is True, (k, res)
     assert res["aux_average_err"] < 1e-6, res

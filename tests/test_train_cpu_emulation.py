@@ -126,6 +126,18 @@ def test_flat_mode_gathers_reproduce_the_per_tensor_path(cpu_train):
     tg.enable_flat(flatP, offsets, flat_g, run_step)
     assert tg.no_grad_params == sorted(k for k in names if k.startswith("res1_unit2_conv1") or k.startswith("res1_unit2_bn1"))
     run_step()                                                 # flat mode: one gather in, one gather out
+    # split backward (head towers | backbone): the same flat gradient, bucket by bucket -- what the overlapped
+    # all-reduce of GraphedTrainStep exchanges (rpn_* parameters are the trailing contiguous block)
+    whole = flat_g.clone()
+    lo = tg.head_split()
+    assert 0 < lo < flat_g.numel() and all((k.startswith("rpn_")) == (offsets[k] >= lo) for k in names)
+    tg.refresh()
+    tg.forward(data, coord)
+    flat_g.zero_()
+    tg.backward_head(d_cls, d_reg)
+    assert torch.equal(flat_g[lo:], whole[lo:]) and not flat_g[:lo].any()
+    tg.backward_body()
+    assert torch.equal(flat_g, whole)
     for key, want in packed0.items():                          # every bf16 operand re-packed by the gather
         assert torch.equal(tg.packed[key], want), key
     for k in names:
