@@ -12,7 +12,7 @@
 //
 // HBM traffic at the op boundary (fp32): fwd 2572 B/pixel, bwd 2828 B/pixel algorithmic
 // (SURVEY.md 8d); this implementation reads grad_out twice in bwd (5132 B/pixel).
-// The tcgen05 variant (impl 2) lives in meta_kernel_tc.cu.
+// The TMA + tcgen05 warp-specialised variant (impl 3, the default for C == 64) lives in meta_kernel_ws*.cu.
 #include "../../include/rangedet_b200.h"
 #include "rd_common.cuh"
 
@@ -488,10 +488,6 @@ int rd_meta_kernel_bwd_data_ws(const float* grad_out, const float* coord, const 
 int rd_meta_kernel_bwd_params_ws(const float* grad_out, const float* data, const float* coord, const float* w0,
                                  const float* b0, const float* w1, float* partial, int* nparts, int B, int C, int H,
                                  int W, cudaStream_t stream);
-// implemented in meta_kernel_tc.cu (impl 2)
-int rd_meta_kernel_fwd_tc(const float* data, const float* coord, const float* w0, const float* b0,
-                          const float* w1, const float* b1, float* out, int B, int C, int H, int W,
-                          cudaStream_t stream);
 
 extern "C" {
 
@@ -508,7 +504,7 @@ int rd_meta_kernel_fwd(const float* data, const float* coord, const float* w0, c
   if (impl == 0)  // default: TMA/tcgen05 kernel when its preconditions hold, generic fp32 kernel otherwise
     impl = (C == 64 && W % 4 == 0 && ((reinterpret_cast<uintptr_t>(data) | reinterpret_cast<uintptr_t>(out)) & 15) == 0) ? 3 : 1;
   if (impl == 3) return rd_meta_kernel_fwd_ws(data, coord, w0, b0, w1, b1, out, B, C, H, W, rd::as_stream(stream));
-  if (impl == 2) return rd_meta_kernel_fwd_tc(data, coord, w0, b0, w1, b1, out, B, C, H, W, rd::as_stream(stream));
+  RD_REQUIRE(impl != 2, "rd_meta_kernel_fwd: impl 2 (first tcgen05 version) was removed; use 0 (default), 1 (fp32) or 3 (TMA + tcgen05)");
   const int tiles_w = (W + mk::F_TW - 1) / mk::F_TW;
   const int64_t ntiles = (int64_t)B * H * tiles_w;
   RD_REQUIRE(ntiles <= 0x7fffffffLL, "rd_meta_kernel_fwd: too many tiles");

@@ -21,7 +21,7 @@ import torch
 
 from . import _lib
 
-IMPL_DEFAULT, IMPL_FP32, IMPL_TCGEN05, IMPL_TMA_WS = 0, 1, 2, 3
+IMPL_DEFAULT, IMPL_FP32, IMPL_TMA_WS = 0, 1, 3   # (2, the first tcgen05 version, was removed: superseded by 3)
 
 
 def _stream():

@@ -8,8 +8,9 @@ kernel (rangedet_b200.processing_cxx.wnms_4c, bit-exact keep indices) and the tw
 expressions (float32, like the reference's arrays).
 """
 import numpy as np
+import torch
 
-from . import processing_cxx
+from . import ops, processing_cxx
 
 
 def bbox3d_10dim_to_11dim(bbox3d_10dim):   # tools/test.py:56-81
@@ -51,3 +52,26 @@ def frame_detections(cls_score, bbox_4pts, keep_inds=None, min_score=0.5, wnms=T
     if bbox_score.shape[0] == 0:
         return np.zeros((0, 8), np.float32)
     return bbox3d_12dim_to_8dim(bbox_score).astype(np.float32)
+
+
+def frame_detections_device(cls_score, bbox_4pts, min_score=0.5, thr_lo=0.1, thr_hi=0.5, is_3d_iou=False, hash_scale=100):
+    """Device-resident twin of frame_detections (wnms branch): CUDA tensors in -- cls_score (K,), bbox_4pts (K,10), e.g.
+    one frame of symbol._TestExecutor's output -- (D,8) CUDA tensor out.  The boxes never leave the device between the
+    inference graph and the weighted NMS (the reference copies them to the host, tools/test.py:178-218, because its
+    wnms_4c is a CPU routine); what crosses PCIe is two counts (foreground boxes, kept boxes).  Same arithmetic as the
+    host path in float32; `atan2` is torch's CUDA implementation instead of numpy's, so yaw may differ in the last bit."""
+    if not (cls_score.is_cuda and bbox_4pts.is_cuda):
+        raise RuntimeError("frame_detections_device needs CUDA tensors (use frame_detections for host arrays)")
+    fg = cls_score > min_score                                                         # tools/test.py:200
+    s, b = cls_score[fg].float(), bbox_4pts[fg].float()
+    if b.shape[0] == 0:
+        return torch.zeros((0, 8), device=b.device)
+    yaw = torch.atan2(b[:, 1] - b[:, 3], b[:, 0] - b[:, 2])                             # :56-81
+    dets = torch.cat([b[:, :8], yaw[:, None], b[:, 8:9], b[:, 9:10] - b[:, 8:9], s[:, None]], 1).contiguous()
+    d, _ = ops.wnms_4c_device(dets, thr_lo, thr_hi, bool(is_3d_iou), int(hash_scale))   # :209-217
+    if d.shape[0] == 0:
+        return torch.zeros((0, 8), device=b.device)
+    cx, cy = d[:, [0, 2, 4, 6]].mean(1), d[:, [1, 3, 5, 7]].mean(1)                     # :43-53
+    length = torch.sqrt((d[:, 2] - d[:, 0]) ** 2 + (d[:, 3] - d[:, 1]) ** 2)
+    width = torch.sqrt((d[:, 2] - d[:, 4]) ** 2 + (d[:, 3] - d[:, 5]) ** 2)
+    return torch.stack([cx, cy, d[:, 9] + d[:, 10] / 2, length, width, d[:, 10], d[:, 8], d[:, 11]], 1)

@@ -212,6 +212,16 @@ class _TestExecutor(object):
         fg_score, prop, keep = self.predict(cls_logit, bbox_delta, record)
         return [record.get("rec_id"), fg_score, prop, keep, record.get("gt_bbox_imu"), record.get("gt_class")]
 
+    def detections(self, record, min_score=0.5, thr_lo=0.1, thr_hi=0.5, is_3d_iou=False, hash_scale=100):
+        """Forward + get_fpn_prediction + the per-frame loop body of tools/test.py:178-225 with everything resident on
+        the device (wnms configs): -> list over frames of (D,8) CUDA tensors [cx,cy,cz,l,w,h,heading,score].
+        Arguments as pTest.min_det_score / pTest.nms.{thr_lo,thr_hi,is_3d_iou} (config:204-215)."""
+        from . import postprocess
+        _need(self.wnms, "detections() is the weighted-NMS path (RpnParam.wnms)")
+        _, fg_score, boxes, _, _, _ = self(record)
+        return [postprocess.frame_detections_device(fg_score[b], boxes[b], min_score, thr_lo, thr_hi, is_3d_iou, hash_scale)
+                for b in range(fg_score.shape[0])]
+
     def predict(self, cls_logit, bbox_delta, record):
         """get_fpn_prediction (builder.py:424-534) on the head outputs: per-level (B,1,H,W_l) / (B,8,H,W_l) lists."""
         s_ = self.sym.det.fpn_strides

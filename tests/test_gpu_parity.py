@@ -223,7 +223,7 @@ def _mk_inputs(B, C, H, W, wpad, seed):
     return data, coord, params
 
 
-@pytest.mark.parametrize("impl", [1, 2, 3])
+@pytest.mark.parametrize("impl", [1, 3])
 def test_meta_kernel_fwd_golden(ops, impl):
     g = golden("meta_kernel.npz")
     got = ops.meta_kernel_forward(cu(g["data"]), cu(g["coord"]), cu(g["w0"]), cu(g["b0"]), cu(g["w1"]), cu(g["b1"]),
@@ -233,7 +233,7 @@ def test_meta_kernel_fwd_golden(ops, impl):
     assert err < (1e-5 if impl == 1 else 2e-4), err
 
 
-@pytest.mark.parametrize("impl", [1, 2, 3])
+@pytest.mark.parametrize("impl", [1, 3])
 @pytest.mark.parametrize("shape", [(2, 64, 16, 300, 304), (1, 64, 3, 129, 132), (1, 64, 64, 2650, 2656)])
 def test_meta_kernel_fwd_vs_oracle(ops, impl, shape):
     from oracle import meta_kernel_ref
@@ -343,7 +343,7 @@ def test_meta_kernel_autograd_and_properties(ops):
     data, coord, (w0, b0, w1, b1) = _mk_inputs(B, C, H, W, wpad, seed=40)
     args = [cu(x) for x in (coord, w0, b0, w1, b1)]
     d = cu(data)
-    for impl in (1, 2, 3):
+    for impl in (1, 3):
         o1 = ops.meta_kernel_forward(d, *args, impl=impl)
         o2 = ops.meta_kernel_forward(d * 2, *args, impl=impl)
         assert torch.equal(o2, o1 * 2)

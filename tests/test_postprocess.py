@@ -41,3 +41,18 @@ def test_frame_detections_end_to_end(orc):
     keep[:20] = np.arange(20) * 3
     out2 = postprocess.frame_detections(score, c10[keep.clip(0)], keep_inds=keep, min_score=0.0, wnms=False)
     assert out2.shape == (20, 8) and np.array_equal(out2[:, 7], score[keep[:20]])
+
+
+@pytest.mark.gpu
+def test_frame_detections_device_matches_host_path():
+    """The device-resident twin (no host hop between the executor and the weighted NMS): same boxes kept, same 8-dim
+    detections to float32 rounding (torch's CUDA atan2 vs numpy's for the yaw column)."""
+    import torch
+    c10, score = _dets(5000, 11)
+    host = postprocess.frame_detections(score, c10, min_score=0.4)
+    dev = postprocess.frame_detections_device(torch.from_numpy(score).cuda(), torch.from_numpy(c10).cuda(), min_score=0.4)
+    assert dev.is_cuda and tuple(dev.shape) == host.shape and host.shape[0] > 10
+    assert np.allclose(dev.cpu().numpy(), host, rtol=1e-5, atol=1e-5)
+    assert postprocess.frame_detections_device(torch.from_numpy(score).cuda(), torch.from_numpy(c10).cuda(), min_score=2.0).shape == (0, 8)
+    with pytest.raises(RuntimeError):
+        postprocess.frame_detections_device(torch.from_numpy(score), torch.from_numpy(c10))
