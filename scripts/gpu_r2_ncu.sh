@@ -1,7 +1,8 @@
 #!/bin/bash
-# round 2 ncu captures: launch list of two replayed cfg-5 steps + `--set full` of the dominant kernels (B=2, fp16)
+# round 2 ncu captures (the launch-list pass runs with RD_PDL=0: ncu reports LaunchFailed on programmatic-dependent graph edges;
+# kernel durations are what is wanted there, not the overlap): launch list of two replayed cfg-5 steps + `--set full` of the dominant kernels (B=2, fp16)
 mkdir -p gpurun_out
-timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none --profile-from-start off --csv \
+RD_PDL=0 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none --profile-from-start off --csv \
   --log-file gpurun_out/r02_train_step_launches.csv python scripts/ncu_targets.py step > gpurun_out/ncu_step.log 2>&1; echo "ncu launch list rc=$?"
 tail -2 gpurun_out/ncu_step.log
 timeout 900 ncu --set full --clock-control none --import-source on --profile-from-start off -o gpurun_out/r02_kernels -f \
