@@ -43,7 +43,7 @@ namespace wn {
 constexpr int D = 12;
 constexpr int NCELL_MAX = 1 << 20;
 constexpr int GRID_DIM_MAX = 1024;
-constexpr int NT = 256;         // threads of the greedy CTA
+constexpr int NT = 512;         // threads of the greedy CTA (113 registers per thread)
 constexpr int LCAP = 4 * NT;    // candidate list capacity
 constexpr float AABB_MARGIN = 0.05f;
 constexpr float HALF_PI = 1.5707963f;
@@ -284,7 +284,7 @@ struct Counters {
 struct Layout {
   size_t keys_in, keys_out, idx_in, order, bx, aabb, hashr, cell_id, cell_id_s, rank_in, cell_rank,
       cell_start, cell_end, params, counters, kept_rank, nb_start, nb_list, theta, theta_s, theta_rank,
-      cub_temp, total;
+      aabb_c, hash_c, th_range, cub_temp, total;
   size_t cub_bytes, nb_cap;
 };
 
@@ -304,6 +304,8 @@ __host__ inline Layout make_layout(int n) {
   L.nb_cap = N + 4096;
   L.nb_list = take(L.nb_cap * 4);
   L.theta = take(N * 4); L.theta_s = take(N * 4); L.theta_rank = take(N * 4);
+  L.aabb_c = take(N * 16); L.hash_c = take(N * 8);   // AABB / hash range in CELL order (aligned with cell_rank)
+  L.th_range = take(N * 6 * 4);                      // per box: [first, last) of its three theta segments
   L.cub_bytes = (size_t)(16u << 20) + N * 32;
   L.cub_temp = take(L.cub_bytes);
   L.total = o;
@@ -445,7 +447,51 @@ __device__ bool share_key(short4 a, short4 b) {
   return false;
 }
 
+// Cell-ordered copies of what the candidate test reads, so that the greedy scan issues independent loads
+// (cell_rank[e], aabb_c[e], hash_c[e]) instead of a dependent chain through the rank.
+__global__ void cell_gather_kernel(const int* __restrict__ cell_rank, const float4* __restrict__ aabb,
+                                   const short4* __restrict__ hashr, int n, float4* __restrict__ aabb_c,
+                                   short4* __restrict__ hash_c) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= n) return;
+  const int r = cell_rank[e];
+  aabb_c[e] = aabb[r];
+  hash_c[e] = hashr[r];
+}
+
+// The ranges of the theta-sorted array that hold the boxes parallel to box r (its own direction +- THETA_TOL, with
+// the wrap at 0 / pi/2): six binary searches per box, done here for ALL boxes in parallel instead of by the single
+// greedy CTA for every kept box (34-100 dependent loads on its critical path).  Empty segment: first == last.
+__global__ void theta_range_kernel(const float* __restrict__ theta, const float* __restrict__ theta_s, int n,
+                                   int* __restrict__ th_range) {
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= n) return;
+  const float th = theta[r];
+  for (int seg = 0; seg < 3; ++seg) {
+    float lo, hi;
+    bool on = true;
+    if (seg == 0) { lo = th - THETA_TOL; hi = th + THETA_TOL; }
+    else if (seg == 1) { lo = th - THETA_TOL + HALF_PI; hi = HALF_PI + 1.f; on = th < THETA_TOL; }
+    else { lo = -1.f; hi = th + THETA_TOL - HALF_PI; on = th + THETA_TOL > HALF_PI; }
+    int first = 0, last = 0;
+    if (on) {
+      int a = 0, b = n;  // lower_bound(lo)
+      while (a < b) { const int mid = (a + b) >> 1; if (theta_s[mid] < lo) a = mid + 1; else b = mid; }
+      first = a;
+      b = n;             // upper_bound(hi)
+      while (a < b) { const int mid = (a + b) >> 1; if (theta_s[mid] <= hi) a = mid + 1; else b = mid; }
+      last = a;
+    }
+    th_range[(size_t)r * 6 + 2 * seg] = first;
+    th_range[(size_t)r * 6 + 2 * seg + 1] = last;
+  }
+}
+
+constexpr int NSEG = 12;   // candidate segments of one kept box: 9 grid cells + 3 theta ranges
+
 struct GreedySmem {
+  int seg_start[NSEG];     // first entry of each segment (cell-sorted resp. theta-sorted array)
+  int seg_off[NSEG + 1];   // exclusive prefix of the segment lengths: one flat index space for the gather
   float box_i[D];
   float4 aabb_i;
   short4 hash_i;
@@ -458,8 +504,9 @@ struct GreedySmem {
 __global__ void __launch_bounds__(NT, 1)
 greedy_kernel(const float* __restrict__ bx, const float4* __restrict__ aabb, const short4* __restrict__ hashr,
               const int* __restrict__ cell_rank, const int* __restrict__ cell_start,
-              const int* __restrict__ cell_end, const float* __restrict__ theta,
-              const float* __restrict__ theta_s, const int* __restrict__ theta_rank,
+              const int* __restrict__ cell_end, const float4* __restrict__ aabb_c,
+              const short4* __restrict__ hash_c, const int* __restrict__ th_range,
+              const int* __restrict__ theta_rank,
               const GridParams* gpp, int n, float thresh,
               float thresh_vote, int is3d, int* __restrict__ kept_rank, int* __restrict__ nb_start,
               int* __restrict__ nb_list, int nb_cap, Counters* ctr) {
@@ -507,71 +554,68 @@ greedy_kernel(const float* __restrict__ bx, const float4* __restrict__ aabb, con
     const short4 hi_key = S.hash_i;
     int cx, cy;
     cell_of(gp, ai.x, ai.y, &cx, &cy);
-    for (int dy = -1; dy <= 1; ++dy) {
-      const int yy = cy + dy;
-      if (yy < 0 || yy >= gp.ny) continue;
-      for (int dx = -1; dx <= 1; ++dx) {
-        const int xx = cx + dx;
-        if (xx < 0 || xx >= gp.nx) continue;
-        const int c = yy * gp.nx + xx;
-        const int s = cell_start[c], e_end = cell_end[c];
-        for (int base = s; base < e_end; base += NT) {
-          const int e = base + t;
-          if (e < e_end) {
-            const int rb = cell_rank[e];
-            if (rb > ri && !((bitmap[rb >> 5] >> (rb & 31)) & 1u)) {
-              const float4 ab = aabb[rb];
-              const bool near = !(ai.z < ab.x || ab.z < ai.x || ai.w < ab.y || ab.w < ai.y);
-              if (near && share_key(hi_key, hashr[rb])) {
-                const int pos = atomicAdd(&S.ncand, 1);
-                S.cand[pos] = rb;
-              }
+    // The candidates of box i live in up to 12 segments: the 3x3 grid cells around it (entries in cell order) and the
+    // three precomputed ranges of the theta-sorted array (parallel boxes at any distance).  Their bounds are fetched
+    // by 12 threads at once and laid end to end, so the gather below is ONE flat loop whose loads are independent.
+    if (t < NSEG) {
+      int s0 = 0, len = 0;
+      if (t < 9) {
+        const int yy = cy + t / 3 - 1, xx = cx + t % 3 - 1;
+        if (yy >= 0 && yy < gp.ny && xx >= 0 && xx < gp.nx) {
+          const int c = yy * gp.nx + xx;
+          s0 = cell_start[c];
+          len = cell_end[c] - s0;
+        }
+      } else {
+        s0 = th_range[(size_t)ri * 6 + 2 * (t - 9)];
+        len = th_range[(size_t)ri * 6 + 2 * (t - 9) + 1] - s0;
+      }
+      S.seg_start[t] = s0;
+      S.seg_off[t + 1] = len > 0 ? len : 0;
+    }
+    __syncthreads();
+    if (t == 0) {
+      S.seg_off[0] = 0;
+      for (int q = 0; q < NSEG; ++q) S.seg_off[q + 1] += S.seg_off[q];
+    }
+    __syncthreads();
+    const int total = S.seg_off[NSEG];
+    for (int base = 0; base < total; base += NT) {
+      const int f = base + t;
+      if (f < total) {
+        int q = 0;
+#pragma unroll
+        for (int u = 1; u < NSEG; ++u) q += (f >= S.seg_off[u]) ? 1 : 0;   // segment of flat index f
+        const int e = S.seg_start[q] + (f - S.seg_off[q]);
+        if (q < 9) {   // grid cells: near boxes
+          const int rb = cell_rank[e];
+          const float4 ab = aabb_c[e];
+          const short4 hb = hash_c[e];
+          if (rb > ri && !((bitmap[rb >> 5] >> (rb & 31)) & 1u)) {
+            const bool near = !(ai.z < ab.x || ab.z < ai.x || ai.w < ab.y || ab.w < ai.y);
+            if (near && share_key(hi_key, hb)) {
+              const int pos = atomicAdd(&S.ncand, 1);
+              S.cand[pos] = rb;
             }
           }
-          __syncthreads();
-          if (S.ncand > LCAP - NT) {  // uniform decision
-            evaluate();
-            __syncthreads();
-            if (t == 0) S.ncand = 0;
-            __syncthreads();
+        } else {       // theta ranges: parallel boxes that are NOT near (the near ones came through the grid)
+          const int rb = theta_rank[e];
+          if (rb > ri && !((bitmap[rb >> 5] >> (rb & 31)) & 1u)) {
+            const float4 ab = aabb[rb];
+            const bool near = !(ai.z < ab.x || ab.z < ai.x || ai.w < ab.y || ab.w < ai.y);
+            if (!near && share_key(hi_key, hashr[rb])) {
+              const int pos = atomicAdd(&S.ncand, 1);
+              S.cand[pos] = rb;
+            }
           }
         }
       }
-    }
-    {  // parallel boxes (any distance): ranges of the theta-sorted array around theta_i, with wrap
-      const float th = theta[ri];
-      for (int seg = 0; seg < 3; ++seg) {
-        float lo, hi;
-        if (seg == 0) { lo = th - THETA_TOL; hi = th + THETA_TOL; }
-        else if (seg == 1) { lo = th - THETA_TOL + HALF_PI; hi = HALF_PI + 1.f; if (!(th < THETA_TOL)) continue; }
-        else { lo = -1.f; hi = th + THETA_TOL - HALF_PI; if (!(th + THETA_TOL > HALF_PI)) continue; }
-        int a = 0, b = n;  // lower_bound(lo)
-        while (a < b) { const int mid = (a + b) >> 1; if (theta_s[mid] < lo) a = mid + 1; else b = mid; }
-        const int first = a;
-        a = first; b = n;  // upper_bound(hi)
-        while (a < b) { const int mid = (a + b) >> 1; if (theta_s[mid] <= hi) a = mid + 1; else b = mid; }
-        const int last = a;
-        for (int base = first; base < last; base += NT) {
-          const int e = base + t;
-          if (e < last) {
-            const int rb = theta_rank[e];
-            if (rb > ri && !((bitmap[rb >> 5] >> (rb & 31)) & 1u)) {
-              const float4 ab = aabb[rb];
-              const bool near = !(ai.z < ab.x || ab.z < ai.x || ai.w < ab.y || ab.w < ai.y);
-              if (!near && share_key(hi_key, hashr[rb])) {  // near ones came through the grid
-                const int pos = atomicAdd(&S.ncand, 1);
-                S.cand[pos] = rb;
-              }
-            }
-          }
-          __syncthreads();
-          if (S.ncand > LCAP - NT) {
-            evaluate();
-            __syncthreads();
-            if (t == 0) S.ncand = 0;
-            __syncthreads();
-          }
-        }
+      __syncthreads();
+      if (S.ncand > LCAP - NT) {  // uniform decision
+        evaluate();
+        __syncthreads();
+        if (t == 0) S.ncand = 0;
+        __syncthreads();
       }
     }
     __syncthreads();
@@ -725,6 +769,9 @@ int rd_wnms_4c(const float* dets, int n, float thresh, float thresh_vote, int is
   float* theta = (float*)(ws + L.theta);
   float* theta_s = (float*)(ws + L.theta_s);
   int* theta_rank = (int*)(ws + L.theta_rank);
+  float4* aabb_c = (float4*)(ws + L.aabb_c);
+  short4* hash_c = (short4*)(ws + L.hash_c);
+  int* th_range = (int*)(ws + L.th_range);
   void* cub_temp = ws + L.cub_temp;
 
   const int TB = 256, nb = (n + TB - 1) / TB;
@@ -758,9 +805,11 @@ int rd_wnms_4c(const float* dets, int n, float thresh, float thresh_vote, int is
   RD_CUDA(cudaMemsetAsync(cell_start, 0, (size_t)(NCELL_MAX + 1) * 4, st));
   RD_CUDA(cudaMemsetAsync(cell_end, 0, (size_t)(NCELL_MAX + 1) * 4, st));
   cell_bounds_kernel<<<nb, TB, 0, st>>>(cell_id_s, n, cell_start, cell_end);
-  rd::count_launch();
-  RD_CUDA(cudaFuncSetAttribute(greedy_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bitmap_bytes));
-  greedy_kernel<<<1, NT, bitmap_bytes, st>>>(bx, aabb, hashr, cell_rank, cell_start, cell_end, theta, theta_s,
+  cell_gather_kernel<<<nb, TB, 0, st>>>(cell_rank, aabb, hashr, n, aabb_c, hash_c);
+  theta_range_kernel<<<nb, TB, 0, st>>>(theta, theta_s, n, th_range);
+  rd::count_launch(3);
+  RD_CUDA(rd::smem_optin(greedy_kernel, bitmap_bytes));
+  greedy_kernel<<<1, NT, bitmap_bytes, st>>>(bx, aabb, hashr, cell_rank, cell_start, cell_end, aabb_c, hash_c, th_range,
                                              theta_rank, gp, n, thresh,
                                              thresh_vote, is_3d, kept_rank, nb_start, nb_list, (int)L.nb_cap, ctr);
   rd::count_launch();
