@@ -665,7 +665,7 @@ class GraphedTrainStep(object):
     def __init__(self, params, batch, H, W, lr, momentum=0.9, wd=1e-5, clip_gradient=35.0, rescale_grad=1.0 / 128.0,
                  device="cuda", use_meta=True, allreduce=None, world_size=1, with_loss=True, overlap_wgrad=True,
                  loss_hyper=None, gt_name="gt_bbox_veh_for_iou_pred", capture=True, act_dtype=torch.bfloat16,
-                 overlap_allreduce=True):
+                 overlap_allreduce=True, fuse_stats=True):
         self.P = params
         self.allreduce = allreduce
         self.with_loss = with_loss
@@ -691,6 +691,7 @@ class GraphedTrainStep(object):
         self.hyper = torch.tensor([lr, momentum, rescale_grad / world_size, clip_gradient if clip_gradient else 0.0],
                                   device=device)
         self.tg = TrainGraph(params, device, use_meta, act_dtype)
+        self.tg.fuse_stats = bool(fuse_stats)     # False: separate rd_bn_train_stats pass after every conv (A/B timing)
         self.act_dtype = act_dtype
         self.capture = capture    # False: same buffers and flat plumbing, kernels launched eagerly (debugging)
         if overlap_wgrad and capture:

@@ -1,6 +1,6 @@
 """Targets for the round-2 ncu captures (run under `ncu --profile-from-start off`): only the region between
 cudaProfilerStart / Stop is profiled.
-    python scripts/ncu_targets.py step      # two CUDA-graph replays of the cfg-5 train step (B=2, fp16): launch list
+    python scripts/ncu_targets.py step      # two eager cfg-5 train steps (B=2, fp16): launch list
     python scripts/ncu_targets.py kernels   # the dominant kernels of that step, one shape each, launched alone twice"""
 import os
 import sys
@@ -19,7 +19,9 @@ torch.cuda.set_device(0)
 g = torch.Generator(device=dev).manual_seed(0)
 
 if mode == "step":
-    step = train.GraphedTrainStep(make_params(seed=0, device=dev), B, H, W, lr=0.0125, device=dev, act_dtype=DT)
+    # eager launches (capture=False: same buffers, flat plumbing and kernels as the captured step): ncu reports LaunchFailed
+    # when it replays kernel nodes of the captured graphs one by one
+    step = train.GraphedTrainStep(make_params(seed=0, device=dev), B, H, W, lr=0.0125, device=dev, act_dtype=DT, capture=False)
     step.set_targets(synth.rpn_targets(B, seed=500))
     data = torch.randn((B, 8, H, W), device=dev, generator=g)
     coord = torch.from_numpy(synth.range_image_coords(B, seed=700)).to(dev)

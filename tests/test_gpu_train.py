@@ -283,11 +283,12 @@ def test_train_layer_vs_autograd(ops, case, dtype):
     # blocks are two or three layers deep: a ReLU mask that flips in the first layer moves single elements of the data
     # gradient by O(1) of the largest value, so only the rms bound applies to them
     mx = 1.0 if case.startswith("block_") else 1.5e-1
+    rt = 1.5e-2 if dtype == torch.bfloat16 else 1e-2      # the full-size test's per-layer gradient bounds
     for xp, x in zip(xps, xr):
         got = ops.from_nhwc_padded(tg.grad_of(xp), x.shape[1])
-        assert _rms_rel(got, x.grad) < 1e-2 and _maxrel(got, x.grad) < mx, case
+        assert _rms_rel(got, x.grad) < rt and _maxrel(got, x.grad) < mx, case
     for n in names:
-        assert _rms_rel(tg.pgrads[n], ref.P[n].grad) < 1e-2 and _maxrel(tg.pgrads[n], ref.P[n].grad) < 1.5e-1, (case, n)
+        assert _rms_rel(tg.pgrads[n], ref.P[n].grad) < rt and _maxrel(tg.pgrads[n], ref.P[n].grad) < 1.5e-1, (case, n)
 
 
 def test_train_meta_unit_front_vs_autograd(ops):
