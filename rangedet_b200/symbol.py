@@ -215,7 +215,7 @@ class _TestExecutor(object):
     def detections(self, record, min_score=0.5, thr_lo=0.1, thr_hi=0.5, is_3d_iou=False, hash_scale=100):
         """Forward + get_fpn_prediction + the per-frame loop body of tools/test.py:178-225 with everything resident on
         the device (wnms configs): -> list over frames of (D,8) CUDA tensors [cx,cy,cz,l,w,h,heading,score].
-        Arguments as pTest.min_det_score / pTest.nms.{thr_lo,thr_hi,is_3d_iou} (config:204-215)."""
+        Arguments as pTest.min_score[class] / pTest.nms.{thr_lo,thr_hi,is_3d_iou} (config:200-215)."""
         from . import postprocess
         _need(self.wnms, "detections() is the weighted-NMS path (RpnParam.wnms)")
         _, fg_score, boxes, _, _, _ = self(record)
