@@ -421,17 +421,19 @@ conv_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CU
           }
         }
       }
-      if (stats != nullptr && !P.deconv_s) {
-        // partial[(which * Cout + channel) * STATS_STRIDE + slot], the layout bn::fwd_finalize_kernel reads
-        const int nrg = TM / st_rows;
-        const int slot = ((int)blockIdx.x * npipes + p) * nrg + st_rg;
-        const int c = 2 * st_cp;
-        stats[(int64_t)c * STATS_STRIDE + slot] = st_s0;
-        stats[(int64_t)(c + 1) * STATS_STRIDE + slot] = st_s1;
-        stats[(int64_t)(P.Cout + c) * STATS_STRIDE + slot] = st_q0;
-        stats[(int64_t)(P.Cout + c + 1) * STATS_STRIDE + slot] = st_q1;
-      }
       if (!P.deconv_s && leader) tma::store_wait_all<0>();
+      if (stats != nullptr && !P.deconv_s) {
+        // this pipeline's (row group x channel) partials -> its (now idle) staging tile; the CTA adds the pipelines and
+        // row groups in fixed order after the final barrier and writes ONE slot per channel (the finalize kernel then
+        // walks 148 slots per channel instead of 1184)
+        tma::named_bar_sync(bar_id, 128);   // the leader's TMA stores have finished reading the staging tile
+        float* red = reinterpret_cast<float*>(sO) + st_rg * 2 * P.Cout;
+        const int c = 2 * st_cp;
+        red[c] = st_s0;
+        red[c + 1] = st_s1;
+        red[P.Cout + c] = st_q0;
+        red[P.Cout + c + 1] = st_q1;
+      }
       if (PROF && leader && p == 0) {
         P.prof[blockIdx.x * 16 + 8] = tick() - t_begin;
         P.prof[blockIdx.x * 16 + 9] = pc1;
@@ -443,6 +445,16 @@ conv_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CU
   tc::tc_fence_before();
   __syncthreads();
   if (warp == 1) tc::tmem_dealloc(tmem_base, 512);
+  if (stats != nullptr && !P.deconv_s) {
+    // partial[(which * Cout + channel) * STATS_STRIDE + slot], slot = CTA: the layout bn::fwd_finalize_kernel reads
+    const int nrg = TM / (P.Cout >> 1);
+    for (int v = t; v < 2 * P.Cout; v += NTHREADS) {
+      float a = 0.f;
+      for (int p = 0; p < npipes; ++p)
+        for (int rg = 0; rg < nrg; ++rg) a += reinterpret_cast<const float*>(base + P.o_off[p])[rg * 2 * P.Cout + v];
+      stats[(int64_t)v * STATS_STRIDE + blockIdx.x] = a;
+    }
+  }
 }
 
 // mode: 0 = conv ksize x ksize (pad ksize/2), W-stride stride_w in {1,2}; 1 = deconv (3,8)/(1,4)/(1,2);
@@ -623,7 +635,7 @@ static int run(int mode, const void* x_pad, const void* w_packed, const float* s
   const int grid = nsuper < sms ? nsuper : sms;
   if (stats) {
     RD_REQUIRE(mode == 0 && y_ctotal == Cout, "rd_conv2d stats: only the plain convolution epilogue accumulates batch statistics");
-    const int slots = grid * P.npipes * (TM / (Cout / 2));
+    const int slots = grid;   // one partial per CTA and channel
     RD_REQUIRE(slots <= STATS_STRIDE, "rd_conv2d stats: %d partial slots exceed %d", slots, STATS_STRIDE);
     if (stats_slots) *stats_slots = slots;
   }

@@ -178,17 +178,34 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ C
   if (warp == 1) tc::tmem_dealloc(tmem_base, (uint32_t)P.tmem_cols);
 }
 
-// out[i] = sum over splits of partial[s][i], fixed order
-__global__ void reduce_kernel(const float4* __restrict__ partial, float4* __restrict__ out, int n4, int nsplit) {
+// out[i] = sum over splits of partial[s][i], fixed order.  A warp covers 4 consecutive float4 outputs x 8 split groups
+// (lane = group * 4 + element): every group streams its splits (g, g + 8, ...) with 64-byte contiguous reads, so a thread
+// has nsplit / 8 independent loads in flight instead of walking all ~49 splits on its own (the first version spent
+// 15 us per layer, latency-bound, 1.4 ms per training step); the groups are then combined by a fixed shuffle tree:
+// deterministic.
+__global__ void __launch_bounds__(256) reduce_kernel(const float4* __restrict__ partial, float4* __restrict__ out, int n4, int nsplit) {
   if (threadIdx.x == 0) rd::pdl_trigger();
   rd::pdl_wait();
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += gridDim.x * blockDim.x) {
-    float4 a = partial[i];
-    for (int s = 1; s < nsplit; ++s) {
-      const float4 b = partial[(int64_t)s * n4 + i];
-      a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
+  const int lane = threadIdx.x & 31, el = lane & 3, g = lane >> 2;
+  const int warps_total = (gridDim.x * blockDim.x) >> 5;
+  for (int base = (((int)blockIdx.x * (int)blockDim.x + (int)threadIdx.x) >> 5) * 4; base < n4; base += warps_total * 4) {
+    const int i = base + el;
+    float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (i < n4) {
+#pragma unroll 4
+      for (int s = g; s < nsplit; s += 8) {
+        const float4 b = partial[(int64_t)s * n4 + i];
+        a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
+      }
     }
-    out[i] = a;
+#pragma unroll
+    for (int o = 4; o < 32; o <<= 1) {
+      a.x += __shfl_xor_sync(0xffffffffu, a.x, o);
+      a.y += __shfl_xor_sync(0xffffffffu, a.y, o);
+      a.z += __shfl_xor_sync(0xffffffffu, a.z, o);
+      a.w += __shfl_xor_sync(0xffffffffu, a.w, o);
+    }
+    if (g == 0 && i < n4) out[i] = a;
   }
 }
 
@@ -295,8 +312,13 @@ int RD_ACT_FN(rd_conv2d_wgrad_nhwc_, )(const void* a_pad, const void* b_pad, flo
   float* partial = static_cast<float*>(workspace);
   RD_CUDA(rd::launch(wg::wgrad_kernel, dim3(P.njobs * P.nsplit), dim3(wg::NTHREADS), smem, s, tm_a, tm_b, partial, P));
   const int n4 = P.ntaps * CA * CB / 4;
-  RD_CUDA(rd::launch(wg::reduce_kernel, dim3((n4 + 255) / 256 < 592 ? (n4 + 255) / 256 : 592), dim3(256), 0, s,
-                     reinterpret_cast<const float4*>(partial), reinterpret_cast<float4*>(g), n4, (int)P.nsplit));
+  {
+    const int64_t warps = ((int64_t)n4 + 3) / 4;                 // one warp per 4 outputs
+    int64_t blocks = (warps + 7) / 8;                            // 8 warps per block
+    if (blocks > 148 * 8) blocks = 148 * 8;
+    RD_CUDA(rd::launch(wg::reduce_kernel, dim3((unsigned)blocks), dim3(256), 0, s, reinterpret_cast<const float4*>(partial),
+                       reinterpret_cast<float4*>(g), n4, (int)P.nsplit));
+  }
   rd::count_launch(2);
   return rd::check_launch("rd_conv2d_wgrad");
 }
