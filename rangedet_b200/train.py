@@ -529,6 +529,7 @@ class TrainGraph(object):
         res1 = self.res_stage(x, coord, "res1", 1)
         res2a = self.res_stage(res1, None, "res2a", 2)
         res2 = self.res_stage(res2a, None, "res2", 2)
+        self.mid_tape_start = len(self.tape)      # res3a, res3 and the aggregation stages: bucket 1 of the backward
         res3a = self.res_stage(res2, None, "res3a", 2)
         res3 = self.res_stage(res3a, None, "res3", 2)
         agg2 = self.agg_stage("agg2", res2, res3)
@@ -573,33 +574,53 @@ class TrainGraph(object):
             ops.gather_f32(self.arena, self.gmap, self.flat_g)
         return self.pgrads
 
-    def head_split(self):
-        """Element offset in the flat buffers where the RPN head's parameters start: names are sorted, so the head
-        (`rpn_*`, ~60 % of the parameters) is the trailing contiguous block.  Flat mode only."""
+    # ---- backward in buckets (flat mode): gradient exchange overlapping the rest of the backward ----------------
+    N_BUCKETS = 3
+
+    @staticmethod
+    def bucket_of(name):
+        """Backward runs head -> aggregation stages -> res3 -> res3a -> res2 -> res2a -> res1.  Bucket 0: the RPN head
+        (`rpn_*`, 13.1 MB of gradients); bucket 1: aggregation stages + res3 / res3a (large parameters, early and cheap
+        backward, 18.3 MB); bucket 2: res2 / res2a / res1 incl. the Meta-Kernel unit (5.2 MB, the last kernels of the
+        backward) -- so only the smallest exchange is left exposed after the backward."""
+        if name.startswith("rpn_"):
+            return 0
+        if name.startswith(("agg", "res3_", "res3a_")):
+            return 1
+        return 2
+
+    def bucket_ranges(self):
+        """-> [[(lo, hi), ...] per bucket]: contiguous element ranges of the name-sorted flat buffers."""
         names = sorted(self.offsets)
-        first = next(i for i, n in enumerate(names) if n.startswith("rpn_"))
-        assert all(n.startswith("rpn_") for n in names[first:]) and not any(n.startswith("rpn_") for n in names[:first])
-        return self.offsets[names[first]]
+        out = [[] for _ in range(self.N_BUCKETS)]
+        for n in names:
+            k, lo = self.bucket_of(n), self.offsets[n]
+            hi = lo + self.P[n].numel()
+            if out[k] and out[k][-1][1] == lo:
+                out[k][-1] = (out[k][-1][0], hi)
+            else:
+                out[k].append((lo, hi))
+        return out
 
-    def backward_head(self, d_cls, d_reg):
-        """First half of backward(): the head towers only (the END of the tape), their parameter gradients gathered into
-        flat_g[head_split():] -- so that their all-reduce can overlap backward_body() (flat mode)."""
-        for kind, lvl, b, _ in self.head_bwd:
-            b(d_cls[lvl] if kind == "cls" else d_reg[lvl])
-        body, head = self.tape[:self.head_tape_start], self.tape[self.head_tape_start:]
-        for fn in reversed(head):
+    def backward_bucket(self, k, d_cls=None, d_reg=None):
+        """Bucket k of backward() (call 0, 1, 2 in order): its slice of the tape, then its parameter gradients gathered
+        into their ranges of flat_g.  Flat mode only."""
+        s1, s2 = self.mid_tape_start, self.head_tape_start
+        if k == 0:
+            for kind, lvl, b, _ in self.head_bwd:
+                b(d_cls[lvl] if kind == "cls" else d_reg[lvl])
+            seg = self.tape[s2:]
+        elif k == 1:
+            seg = self.tape[s1:s2]
+        else:
+            seg = self.tape[:s1]
+        for fn in reversed(seg):
             fn()
-        self.tape = body
         self._join_side()
-        lo = self.head_split()
-        ops.gather_f32(self.arena, self.gmap[lo:], self.flat_g[lo:])
-
-    def backward_body(self):
-        """Second half: backbone + aggregation stages, gradients into flat_g[:head_split()]."""
-        self.run_tape()
-        self._join_side()
-        lo = self.head_split()
-        ops.gather_f32(self.arena, self.gmap[:lo], self.flat_g[:lo])
+        for lo, hi in self.bucket_ranges()[k]:
+            ops.gather_f32(self.arena, self.gmap[lo:hi], self.flat_g[lo:hi])
+        if k == self.N_BUCKETS - 1:
+            self.tape = []
         return self.pgrads
 
 
@@ -659,8 +680,9 @@ class GraphedTrainStep(object):
     `allreduce` given, the flat gradient buffer is summed across ranks between backward and update and averaged through
     rescale_grad / world_size (the reference: hvd.DistributedOptimizer, tools/train.py:364-368).  `allreduce(view)` must
     SUM the given contiguous view of the flat buffer over ranks; it may return a handle with `.wait()` (e.g.
-    dist.all_reduce(..., async_op=True)): with world_size > 1 the captured backward is then split head | backbone and the
-    head's exchange overlaps the backbone's backward kernels (two bucket all-reduces per step)."""
+    dist.all_reduce(..., async_op=True)): with world_size > 1 the captured backward is then split into three buckets (head |
+    aggregation stages + res3 / res3a | res2 / res2a / res1, TrainGraph.bucket_of) and each bucket's exchange overlaps the
+    backward kernels of the buckets after it; only the last, smallest one (5 MB) is exposed."""
 
     def __init__(self, params, batch, H, W, lr, momentum=0.9, wd=1e-5, clip_gradient=35.0, rescale_grad=1.0 / 128.0,
                  device="cuda", use_meta=True, allreduce=None, world_size=1, with_loss=True, overlap_wgrad=True,
@@ -764,16 +786,15 @@ class GraphedTrainStep(object):
         with torch.cuda.graph(self.g_fwd, pool=self.pool, **mode):
             self._fwd()
         c1 = _lib.launch_count()
-        # With a gradient exchange the backward is captured in two graphs -- head towers | backbone -- so that the
-        # all-reduce of the head's gradients (~60 % of the parameters) runs while the backbone's backward computes
+        # With a gradient exchange the backward is captured as one graph per bucket, so that a bucket's all-reduce runs
+        # while the next bucket's backward computes
         self.split_bwd = self.allreduce is not None and world_size > 1 and overlap_allreduce
         if self.split_bwd:
-            self.g_bwd_head, self.g_bwd_body = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
-            with torch.cuda.graph(self.g_bwd_head, pool=self.pool, **mode):
-                self._bwd_head()
-            with torch.cuda.graph(self.g_bwd_body, pool=self.pool, **mode):
-                self.tg.backward_body()
-            self.head_lo = self.tg.head_split()
+            self.g_bwd_parts = [torch.cuda.CUDAGraph() for _ in range(TrainGraph.N_BUCKETS)]
+            for k, g in enumerate(self.g_bwd_parts):
+                with torch.cuda.graph(g, pool=self.pool, **mode):
+                    self._bwd_bucket(k)
+            self.bucket_ranges = self.tg.bucket_ranges()
         else:
             with torch.cuda.graph(self.g_bwd, pool=self.pool, **mode):
                 self._bwd()
@@ -795,10 +816,10 @@ class GraphedTrainStep(object):
             ks = [k for k in self.names if k in grads]
             torch._foreach_copy_([self.gviews[k] for k in ks], [grads[k].reshape(self.P[k].shape) for k in ks])
 
-    def _bwd_head(self):
-        if self.with_loss:
+    def _bwd_bucket(self, k):
+        if k == 0 and self.with_loss:
             rpn_loss_levels(self.out[0], self.out[1], self.targets, out=self.loss_out, hyper=self.loss_hyper, gt_name=self.gt_name)
-        self.tg.backward_head(self.d_cls, self.d_reg)
+        self.tg.backward_bucket(k, self.d_cls, self.d_reg)
 
     def _update(self):
         ops.sgd_mom_update(self.flatP, self.flat, self.flat_m, self.flat_wd, self.hyper)
@@ -840,12 +861,14 @@ class GraphedTrainStep(object):
             for dst, src in zip(self.d_cls + self.d_reg, list(d_cls) + list(d_reg)):
                 dst.copy_(src, non_blocking=True)
         if self.split_bwd:
-            # head backward | all-reduce(head gradients) overlapping the backbone backward | all-reduce(backbone gradients)
-            self.g_bwd_head.replay()
-            h1 = self.allreduce(self.flat[self.head_lo:])
-            self.g_bwd_body.replay()
-            h2 = self.allreduce(self.flat[:self.head_lo])
-            for h in (h1, h2):      # an asynchronous exchange returns a handle: the update must wait for it
+            # bucket k's backward graph, then its (asynchronous) exchange, which overlaps the graphs of the buckets after it;
+            # the update waits for all of them
+            handles = []
+            for g, ranges in zip(self.g_bwd_parts, self.bucket_ranges):
+                g.replay()
+                for lo, hi in ranges:
+                    handles.append(self.allreduce(self.flat[lo:hi]))
+            for h in handles:
                 if h is not None and hasattr(h, "wait"):
                     h.wait()
             self.g_upd.replay()

@@ -40,8 +40,8 @@ def main():
     def local_backward():
         """loss + backward of the frames already in the static buffers, no exchange"""
         if step.split_bwd:
-            step.g_bwd_head.replay()
-            step.g_bwd_body.replay()
+            for g in step.g_bwd_parts:
+                g.replay()
         else:
             step.g_bwd.replay()
 

@@ -126,17 +126,22 @@ def test_flat_mode_gathers_reproduce_the_per_tensor_path(cpu_train):
     tg.enable_flat(flatP, offsets, flat_g, run_step)
     assert tg.no_grad_params == sorted(k for k in names if k.startswith("res1_unit2_conv1") or k.startswith("res1_unit2_bn1"))
     run_step()                                                 # flat mode: one gather in, one gather out
-    # split backward (head towers | backbone): the same flat gradient, bucket by bucket -- what the overlapped
-    # all-reduce of GraphedTrainStep exchanges (rpn_* parameters are the trailing contiguous block)
+    # backward in buckets (head | aggregation stages + res3 / res3a | res2 / res2a / res1): the same flat gradient, bucket
+    # by bucket -- what the overlapped all-reduces of GraphedTrainStep exchange
     whole = flat_g.clone()
-    lo = tg.head_split()
-    assert 0 < lo < flat_g.numel() and all((k.startswith("rpn_")) == (offsets[k] >= lo) for k in names)
+    ranges = tg.bucket_ranges()
+    covered = sorted(r for rs in ranges for r in rs)
+    assert covered[0][0] == 0 and covered[-1][1] == flat_g.numel() and all(a[1] == b[0] for a, b in zip(covered, covered[1:]))
+    assert len(ranges[0]) == 1 and len(ranges[1]) == 2 and len(ranges[2]) == 1      # rpn_* | agg*, res3* | res1..res2a
     tg.refresh()
     tg.forward(data, coord)
     flat_g.zero_()
-    tg.backward_head(d_cls, d_reg)
-    assert torch.equal(flat_g[lo:], whole[lo:]) and not flat_g[:lo].any()
-    tg.backward_body()
+    done = torch.zeros(flat_g.numel(), dtype=torch.bool)
+    for k in range(tg.N_BUCKETS):
+        tg.backward_bucket(k, d_cls, d_reg)
+        for lo, hi in ranges[k]:
+            done[lo:hi] = True
+        assert torch.equal(flat_g[done], whole[done]) and not flat_g[~done].any(), k
     assert torch.equal(flat_g, whole)
     for key, want in packed0.items():                          # every bf16 operand re-packed by the gather
         assert torch.equal(tg.packed[key], want), key
