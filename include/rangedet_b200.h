@@ -357,6 +357,10 @@ int rd_gather_f32_to_f16(const float* src, const int* idx, void* dst, int64_t n,
  * launch latency overlap the tail of its predecessor; csrc/rd_common.cuh).  rd_set_pdl(0) switches to plain stream
  * order (diagnostics, A/B timing); returns the previous setting.  Default: on, unless the environment has RD_PDL=0. */
 int rd_set_pdl(int on);
+/* 3x3 / stride-1 convolutions with 128 output channels run in the transposed GEMM orientation of csrc/conv_t.cu
+ * (M = Cout, N = 256 flattened pixels) by default; rd_set_conv_t(0) (or RD_CONV_T=0) keeps them on the M = pixels kernel of
+ * csrc/conv_tc.cu.  Same results (same K order); returns the previous setting. */
+int rd_set_conv_t(int on);
 
 /* ---- tcgen05 self-test -------------------------------------------------------------------
  * D(128 x n) = A(128 x k) . B(n x k)^T with bf16 operands staged in shared memory in the

@@ -24,6 +24,7 @@ SIGNATURES = {
     "rd_check_device": (_i, []),
     "rd_launch_count": (ctypes.c_uint64, []),
     "rd_set_pdl": (_i, [_i]),
+    "rd_set_conv_t": (_i, [_i]),
     "rd_meta_kernel_fwd": (_i, [_vp] * 7 + [_i] * 5 + [_vp]),
     "rd_meta_kernel_fwd_nhwc_bf16": (_i, [_vp] * 8 + [_i, _vp] + [_i] * 4 + [_vp]),
     "rd_meta_kernel_bwd_workspace_bytes": (_sz, [_i] * 4),
@@ -123,6 +124,12 @@ def set_pdl(on):
     """Programmatic dependent launch on / off for every subsequent kernel launch of this process (default on);
     returns the previous setting."""
     return bool(lib().rd_set_pdl(1 if on else 0))
+
+
+def set_conv_t(on):
+    """Transposed-orientation kernel (csrc/conv_t.cu) for 3x3 / stride-1 / Cout-128 convolutions on / off; returns the
+    previous setting."""
+    return bool(lib().rd_set_conv_t(1 if on else 0))
 
 
 def launch_count():

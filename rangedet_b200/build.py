@@ -33,7 +33,7 @@ PER_FILE = {
 
 # Sources that touch stored activations are compiled twice: as is (bf16 storage) and with -DRD_ACT_F16 (fp16 storage,
 # the reference's training format) -- see csrc/act_type.cuh.
-DUAL_STORAGE = ("bn_train.cu", "conv_tc.cu", "conv_wgrad.cu", "layout.cu", "optim.cu")
+DUAL_STORAGE = ("bn_train.cu", "conv_tc.cu", "conv_t.cu", "conv_wgrad.cu", "layout.cu", "optim.cu")
 
 
 def sources():

@@ -1,0 +1,313 @@
+// 3x3 stride-1 convolution with 128 output channels, "transposed" GEMM orientation (sm_100a, tcgen05).
+//
+// Same operation and tensor layouts as the 3x3 / stride-1 case of conv_tc.cu (mx.sym.Convolution of /root/reference
+// mxnext/simple.py:123-158 at the 128-channel call sites: rangedet/symbol/backbone/dla_backbone.py:23-56 for res2 / res3a /
+// res3 / agg2, rangedet/symbol/head/builder.py:198-246 for the 24 head-tower layers = 57 % of the model's FLOPs), but the
+// MMA operands swap roles:
+//
+//     D[Cout = 128 TMEM lanes][256 pixel columns]  +=  W_tap[128 x 64]  .  X_tap[256 px x 64]^T        (M128 N256 K16)
+//
+// Why: with both operands in shared memory an M128 x N x K16 MMA reads (128 + N) * 32 B.  In conv_tc.cu (M = pixels,
+// N = Cout = 128) that is 8 KB per 64 tensor-cycles = 128 B/clk, the whole shared-memory bandwidth of the SM -- before
+// the TMA writes and the epilogue's staging traffic; ncu: tensor pipe 61-64 %.  Here N = 256 pixels: 12 KB per 128
+// cycles = 96 B/clk.  (A cta_group::2 pair would reach the same ratio with two SMs and cluster plumbing.)
+//
+// Tiles run over the FLATTENED haloed pixel grid [N*(H+2)*(W+2)] instead of per image row: a tile is 256 consecutive
+// flat pixels, a tap (dy, dx) is the constant offset (dy-1)*(W+2) + (dx-1), so every width packs tiles densely
+// (W = 664: 666 half-tiles' worth instead of 768; W = 166: 173 instead of 256).  Outputs that fall on halo pixels are
+// forced to zero in the epilogue, which is what the halo holds anyway; the first tile starts at the first interior pixel,
+// so no TMA coordinate is negative.
+//   warp 0    TMA producer: per K-half and dy ONE 258-pixel strip (a 256-pixel box + an 8-pixel box; the three dx taps
+//             are row-shifted views of it), and the 128 x 64 weight tile of every tap, through two rings
+//   warp 1    MMA issuer (converged warp, elected lane): 4 x tcgen05.mma M128 N256 K16 per tap and K-half, fp32
+//             accumulators double-buffered in all 512 TMEM columns
+//   warps 2-5 epilogue: thread = TMEM lane = OUTPUT CHANNEL, columns = pixels; scale / shift / residual / ReLU, halo
+//             mask, storage rounding, transposed 2-byte writes into a [pixel][channel] 128B-swizzled staging tile -> two
+//             TMA stores; the BatchNorm batch statistics of the stored values are plain per-thread sums here.
+#include <stdlib.h>
+#include <string.h>
+
+#include "../../include/rangedet_b200.h"
+#include "act_type.cuh"
+#include "rd_common.cuh"
+#include "tc_common.cuh"
+#include "tma_common.cuh"
+
+namespace RD_ACT_NS(convt) {
+
+constexpr int TN = 256;                       // pixels per tile = MMA N
+constexpr int CO = 128;                       // output channels = MMA M
+constexpr int KC = 64;                        // channels per K-half (one 128B swizzle atom)
+constexpr int STRIP_ROWS = 264;               // 258 pixels used; 256-pixel box + 8-pixel box
+constexpr int STRIP_BYTES = STRIP_ROWS * 128; // 33792
+constexpr int WT_BYTES = CO * 128;            // 16384: one tap, one K-half
+constexpr int HALF_BYTES = TN * 128;          // 32768: staging tile of 64 channels
+constexpr int NSA = 2, NSB = 5;
+constexpr int NTHREADS = 192;
+constexpr int BAR_EPI = 1;
+constexpr int STATS_STRIDE = 1184;            // = bn::MAX_BLOCKS
+constexpr int OFF_W = NSA * STRIP_BYTES;                  // 67584
+constexpr int OFF_O = OFF_W + NSB * WT_BYTES;             // 149504
+constexpr int OFF_MISC = OFF_O + 2 * HALF_BYTES;          // 215040
+
+struct Params {
+  int kh;                 // Cin / 64
+  int Wp, Hp;             // haloed width / height
+  int P_total;            // N * Hp * Wp flat pixels
+  int p_first;            // first interior pixel = Wp + 1
+  int ntiles;
+  int relu, has_res;
+};
+
+struct Misc {
+  uint64_t a_full[NSA], a_empty[NSA], b_full[NSB], b_empty[NSB], t_full[2], t_empty[2], r_full;
+  uint32_t tmem_slot, pad;
+  uint32_t mask[8];       // halo bits of the 256 pixels of the tile in the epilogue
+  float scale[CO], shift[CO];
+};
+
+__global__ void __launch_bounds__(NTHREADS, 1)
+convt_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_x2,
+             const __grid_constant__ CUtensorMap tm_w, const __grid_constant__ CUtensorMap tm_y,
+             const __grid_constant__ CUtensorMap tm_r, const float* __restrict__ scale, const float* __restrict__ shift,
+             float* __restrict__ stats, const __grid_constant__ Params P) {
+  extern __shared__ unsigned char smem_raw[];
+  unsigned char* base = smem_raw + ((1024u - (tc::smem_u32(smem_raw) & 1023u)) & 1023u);
+  const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+  if (t == 0) rd::pdl_trigger();
+  unsigned char* strips = base;
+  unsigned char* wts = base + OFF_W;
+  unsigned char* sO = base + OFF_O;
+  Misc& M = *reinterpret_cast<Misc*>(base + OFF_MISC);
+
+  if (t == 0) {
+    for (int i = 0; i < NSA; ++i) { tc::mbar_init(&M.a_full[i], 1); tc::mbar_init(&M.a_empty[i], 1); }
+    for (int i = 0; i < NSB; ++i) { tc::mbar_init(&M.b_full[i], 1); tc::mbar_init(&M.b_empty[i], 1); }
+    for (int i = 0; i < 2; ++i) { tc::mbar_init(&M.t_full[i], 1); tc::mbar_init(&M.t_empty[i], 4); }
+    tc::mbar_init(&M.r_full, 1);
+    tc::fence_mbar_init();
+    tma::prefetch_map(&tm_x);
+    tma::prefetch_map(&tm_x2);
+    tma::prefetch_map(&tm_w);
+    tma::prefetch_map(&tm_y);
+  }
+  if (warp == 1) {
+    tc::tmem_alloc(&M.tmem_slot, 512);
+    tc::tmem_relinquish();
+  }
+  rd::pdl_wait();   // everything above touched only shared memory / TMEM / kernel parameters
+  for (int c = t; c < CO; c += NTHREADS) {
+    M.scale[c] = scale ? __ldg(scale + c) : 1.f;
+    M.shift[c] = shift ? __ldg(shift + c) : 0.f;
+  }
+  tc::tc_fence_before();
+  __syncthreads();
+  tc::tc_fence_after();
+  const uint32_t tmem_base = M.tmem_slot;
+  const int kh = P.kh;
+
+  if (warp == 0) {
+    // ===== TMA producer =====
+    if (lane == 0) {
+      uint32_t sa = 0, pa = 1, sb = 0, pb = 1;   // ring positions, parity of the `empty` wait
+      for (int tile = blockIdx.x; tile < P.ntiles; tile += gridDim.x) {
+        const int p0 = P.p_first + tile * TN;
+        for (int q = 0; q < kh; ++q)
+          for (int dy = 0; dy < 3; ++dy) {
+            const int ps = p0 + (dy - 1) * P.Wp - 1;   // >= 0: p0 >= Wp + 1
+            tc::mbar_wait(&M.a_empty[sa], pa);
+            tc::mbar_arrive_expect_tx(&M.a_full[sa], (uint32_t)STRIP_BYTES);
+            tma::load_2d(strips + sa * STRIP_BYTES, &tm_x, &M.a_full[sa], q * KC, ps);
+            tma::load_2d(strips + sa * STRIP_BYTES + TN * 128, &tm_x2, &M.a_full[sa], q * KC, ps + TN);
+            if (++sa == NSA) { sa = 0; pa ^= 1; }
+            for (int dx = 0; dx < 3; ++dx) {
+              tc::mbar_wait(&M.b_empty[sb], pb);
+              tc::mbar_arrive_expect_tx(&M.b_full[sb], (uint32_t)WT_BYTES);
+              tma::load_3d(wts + sb * WT_BYTES, &tm_w, &M.b_full[sb], q * KC, 0, dy * 3 + dx);
+              if (++sb == NSB) { sb = 0; pb ^= 1; }
+            }
+          }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    // ===== MMA issuer: converged warp, one elected lane issues =====
+    const uint32_t idesc = tc::make_idesc_f16kind(CO, TN, RD_ACT_MMA_FMT);
+    const uint64_t desc_hi = tc::make_smem_desc(0, 0, 1024, tc::LAYOUT_SW128);  // everything but the address
+    const uint32_t strip_lo = tc::smem_u32(strips) >> 4, wt_lo = tc::smem_u32(wts) >> 4;
+    const bool leader = tc::elect_one();
+    uint32_t sa = 0, pha = 0, sb = 0, phb = 0, it = 0;
+    for (int tile = blockIdx.x; tile < P.ntiles; tile += gridDim.x, ++it) {
+      const uint32_t buf = it & 1;
+      tc::mbar_wait(&M.t_empty[buf], ((it >> 1) & 1) ^ 1);
+      const uint32_t d_tmem = tmem_base + buf * (uint32_t)TN;
+      bool first = true;
+      for (int q = 0; q < kh; ++q)
+        for (int dy = 0; dy < 3; ++dy) {
+          tc::mbar_wait(&M.a_full[sa], pha);
+          const uint32_t x_lo = strip_lo + sa * (uint32_t)(STRIP_BYTES >> 4);
+#pragma unroll 1
+          for (int dx = 0; dx < 3; ++dx) {
+            tc::mbar_wait(&M.b_full[sb], phb);
+            tc::tc_fence_after();
+            if (leader) {
+              // A = weight tile (128 rows), B = strip rows [dx, dx + 256): one pixel = one 128-byte row = 8 address units
+              const uint64_t wd = desc_hi | (uint64_t)((wt_lo + sb * (uint32_t)(WT_BYTES >> 4)) & 0x3FFF);
+              const uint64_t xd = desc_hi | (uint64_t)((x_lo + (uint32_t)dx * 8u) & 0x3FFF);
+              tc::mma_bf16_ss(d_tmem, wd, xd, idesc, first ? 0u : 1u);
+              tc::mma_bf16_ss_acc(d_tmem, wd + 2, xd + 2, idesc);
+              tc::mma_bf16_ss_acc(d_tmem, wd + 4, xd + 4, idesc);
+              tc::mma_bf16_ss_acc(d_tmem, wd + 6, xd + 6, idesc);
+              tc::umma_commit(&M.b_empty[sb]);
+              if (dx == 2) tc::umma_commit(&M.a_empty[sa]);
+            }
+            first = false;
+            __syncwarp();
+            if (++sb == NSB) { sb = 0; phb ^= 1; }
+          }
+          if (++sa == NSA) { sa = 0; pha ^= 1; }
+        }
+      if (leader) tc::umma_commit(&M.t_full[buf]);
+      __syncwarp();
+    }
+  } else {
+    // ===== epilogue: thread = TMEM lane = output channel =====
+    const int q4 = warp & 3;                      // TMEM lane quadrant this warp may read (warps 2..5 -> 2, 3, 0, 1)
+    const int c = q4 * 32 + lane;
+    const int e = (warp - 2) * 32 + lane;         // 0..127: index among the epilogue threads
+    const uint32_t lane_sel = (uint32_t)(q4 * 32) << 16;
+    const bool leader = (warp == 2 && lane == 0);
+    const float sc = M.scale[c], sh = M.shift[c];
+    unsigned char* my_col = sO + (c >> 6) * HALF_BYTES + (c & 7) * 2;   // + px*128 + (((c & 63) >> 3) ^ (px & 7)) << 4
+    const uint32_t my_chunk = (uint32_t)((c & 63) >> 3);
+    float s_sum = 0.f, s_sq = 0.f;
+    uint32_t it = 0;
+    for (int tile = blockIdx.x; tile < P.ntiles; tile += gridDim.x, ++it) {
+      const int p0 = P.p_first + tile * TN;
+      const uint32_t buf = it & 1;
+      if (leader) tma::store_wait_read<0>();      // the previous tile's stores have read the staging tile
+      {  // halo bits of the tile's 256 pixels: warp w covers pixels [32w, 32w+32) and [128+32w, 128+32w+32)
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          const int p = p0 + h * 128 + e;
+          bool halo = true;
+          if (p < P.P_total) {
+            const int col = p % P.Wp, row = (p / P.Wp) % P.Hp;
+            halo = col == 0 || col == P.Wp - 1 || row == 0 || row == P.Hp - 1;
+          }
+          const unsigned bits = __ballot_sync(0xffffffffu, halo);
+          if (lane == 0) M.mask[h * 4 + (warp - 2)] = bits;
+        }
+      }
+      tma::named_bar_sync(BAR_EPI, 128);
+      if (P.has_res) {                            // the other consumer's gradient / residual lands in the staging tile
+        if (leader) {
+          tc::mbar_arrive_expect_tx(&M.r_full, (uint32_t)(2 * HALF_BYTES));
+          tma::load_2d(sO, &tm_r, &M.r_full, 0, p0);
+          tma::load_2d(sO + HALF_BYTES, &tm_r, &M.r_full, KC, p0);
+        }
+        tc::mbar_wait(&M.r_full, it & 1);
+      }
+      tc::mbar_wait(&M.t_full[buf], (it >> 1) & 1);
+      __syncwarp();
+      tc::tc_fence_after();
+      const uint32_t t_acc = tmem_base + lane_sel + buf * (uint32_t)TN;
+#pragma unroll 1
+      for (int ch = 0; ch < 8; ++ch) {
+        float v[32];
+        tc::tmem_ld_x32(t_acc + (uint32_t)(ch * 32), v);
+        const uint32_t mbits = M.mask[ch];
+        unsigned char* rowp = my_col + ch * 32 * 128;
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          act_t* ptr = reinterpret_cast<act_t*>(rowp + j * 128 + ((my_chunk ^ (uint32_t)(j & 7)) << 4));
+          float a = fmaf(v[j], sc, sh);
+          if (P.has_res) a += act::to_float(*ptr);
+          if (P.relu) a = fmaxf(a, 0.f);
+          if ((mbits >> j) & 1u) a = 0.f;         // halo pixel: keep it zero
+          const act_t r = act::from_float(a);
+          *ptr = r;
+          const float f = act::to_float(r);
+          s_sum += f;
+          s_sq = fmaf(f, f, s_sq);
+        }
+      }
+      tc::tc_fence_before();
+      tc::fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) tc::mbar_arrive(&M.t_empty[buf]);
+      tma::named_bar_sync(BAR_EPI, 128);
+      if (leader) {
+        tma::store_2d(&tm_y, sO, 0, p0);
+        tma::store_2d(&tm_y, sO + HALF_BYTES, KC, p0);
+        tma::store_commit();
+      }
+    }
+    if (leader) tma::store_wait_all<0>();
+    if (stats != nullptr) {   // partial[(which * 128 + channel) * STATS_STRIDE + CTA]: the layout bn::fwd_finalize_kernel reads
+      stats[(int64_t)c * STATS_STRIDE + blockIdx.x] = s_sum;
+      stats[(int64_t)(CO + c) * STATS_STRIDE + blockIdx.x] = s_sq;
+    }
+  }
+  tc::tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tc::tmem_dealloc(tmem_base, 512);
+}
+
+}  // namespace convt_<storage type>
+namespace convt = RD_ACT_NS(convt);
+
+// Called by conv_tc.cu's dispatcher (same storage-type pass).  y = relu?(conv3x3(x) * scale + shift + residual), Cout = 128.
+int RD_ACT_FN(rd_convt_run_, )(const void* x_pad, const void* w_packed, const float* scale, const float* shift,
+                               const void* residual_pad, void* y_pad, int N, int H, int W, int Cin, int relu,
+                               cudaStream_t stream, float* stats, int* stats_slots) {
+  using namespace convt;
+  Params P;
+  memset(&P, 0, sizeof(P));
+  P.kh = Cin / KC;
+  P.Wp = W + 2;
+  P.Hp = H + 2;
+  const int64_t total = (int64_t)N * P.Hp * P.Wp;
+  RD_REQUIRE(total < 0x7fffff00LL, "rd_conv(T): tensor too large for 32-bit flat pixel coordinates");
+  P.P_total = (int)total;
+  P.p_first = P.Wp + 1;
+  const int p_last = P.P_total - P.Wp - 2;   // last interior pixel of the last image
+  P.ntiles = (p_last - P.p_first + 1 + TN - 1) / TN;
+  P.relu = relu ? 1 : 0;
+  P.has_res = residual_pad ? 1 : 0;
+  CUtensorMap tm_x, tm_x2, tm_w, tm_y, tm_r;
+  {
+    const uint64_t d[2] = {(uint64_t)Cin, (uint64_t)total};
+    const uint64_t s[1] = {(uint64_t)Cin * 2};
+    const uint32_t b[2] = {(uint32_t)KC, (uint32_t)TN}, b2[2] = {(uint32_t)KC, 8u};
+    if (tma::make_map(&tm_x, RD_ACT_TMA_TYPE, x_pad, 2, d, s, b, CU_TENSOR_MAP_SWIZZLE_128B)) return 1;
+    if (tma::make_map(&tm_x2, RD_ACT_TMA_TYPE, x_pad, 2, d, s, b2, CU_TENSOR_MAP_SWIZZLE_128B)) return 1;
+  }
+  {
+    const uint64_t d[3] = {(uint64_t)Cin, (uint64_t)CO, 9u};
+    const uint64_t s[2] = {(uint64_t)Cin * 2, (uint64_t)Cin * CO * 2};
+    const uint32_t b[3] = {(uint32_t)KC, (uint32_t)CO, 1u};
+    if (tma::make_map(&tm_w, RD_ACT_TMA_TYPE, w_packed, 3, d, s, b, CU_TENSOR_MAP_SWIZZLE_128B)) return 1;
+  }
+  {
+    const uint64_t d[2] = {(uint64_t)CO, (uint64_t)total};
+    const uint64_t s[1] = {(uint64_t)CO * 2};
+    const uint32_t b[2] = {(uint32_t)KC, (uint32_t)TN};
+    if (tma::make_map(&tm_y, RD_ACT_TMA_TYPE, y_pad, 2, d, s, b, CU_TENSOR_MAP_SWIZZLE_128B)) return 1;
+    if (tma::make_map(&tm_r, RD_ACT_TMA_TYPE, residual_pad ? residual_pad : y_pad, 2, d, s, b, CU_TENSOR_MAP_SWIZZLE_128B)) return 1;
+  }
+  int dev = 0, sms = 0;
+  RD_CUDA(cudaGetDevice(&dev));
+  RD_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  const size_t smem = (size_t)OFF_MISC + sizeof(Misc) + 1024;
+  RD_REQUIRE(smem <= 227 * 1024, "rd_conv(T): shared memory layout exceeds 227 KB (%zu)", smem);
+  RD_CUDA(rd::smem_optin(convt_kernel, smem));
+  const int grid = P.ntiles < sms ? P.ntiles : sms;
+  if (stats) {
+    RD_REQUIRE(grid <= STATS_STRIDE, "rd_conv(T) stats: %d partial slots exceed %d", grid, STATS_STRIDE);
+    if (stats_slots) *stats_slots = grid;
+  }
+  RD_CUDA(rd::launch(convt_kernel, dim3(grid), dim3(NTHREADS), smem, stream, tm_x, tm_x2, tm_w, tm_y, tm_r, scale, shift, stats, P));
+  rd::count_launch();
+  return rd::check_launch("rd_conv(T)");
+}

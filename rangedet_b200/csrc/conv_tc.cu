@@ -31,6 +31,11 @@
 #include "tc_common.cuh"
 #include "tma_common.cuh"
 
+// conv_t.cu: 3x3 / stride 1 / Cout = 128 in the transposed GEMM orientation (M = Cout, N = 256 pixels)
+int RD_ACT_FN(rd_convt_run_, )(const void* x_pad, const void* w_packed, const float* scale, const float* shift,
+                               const void* residual_pad, void* y_pad, int N, int H, int W, int Cin, int relu,
+                               cudaStream_t stream, float* stats, int* stats_slots);
+
 namespace RD_ACT_NS(conv) {
 
 constexpr int TM = 128;               // GEMM rows per tile
@@ -474,6 +479,14 @@ static int run(int mode, const void* x_pad, const void* w_packed, const float* s
   RD_REQUIRE(Cout == 64 || Cout == 128, "rd_conv: Cout must be 64 or 128 (got %d); pad the channels", Cout);
   RD_REQUIRE(N > 0 && H > 0 && W_in > 0, "rd_conv: bad shape");
   if (rd_check_device()) return 1;
+  {
+    // 3x3 stride-1 convolutions with 128 output channels (head towers, res2 / res3a / res3 / agg2 and their data
+    // gradients) take the transposed orientation of conv_t.cu: 96 instead of 128 B/clk of shared-memory operand reads per
+    // MMA, tiles over the flattened pixel grid.  RD_CONV_T=0 keeps them here (A/B timing, cross-check).
+    if (rd::conv_t_enabled() && mode == 0 && ksize == 3 && stride_w == 1 && Cout == 128 && y_ctotal == Cout && !res_after_relu)
+      return RD_ACT_FN(rd_convt_run_, )(x_pad, w_packed, scale, shift, residual_pad, y_pad, N, H, W_in, Cin, relu, stream, stats,
+                                        stats_slots);
+  }
   Params P;
   memset(&P, 0, sizeof(P));
   P.N = N; P.H = H; P.Cin = Cin; P.Cout = Cout;

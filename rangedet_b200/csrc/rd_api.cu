@@ -39,6 +39,16 @@ int check_launch(const char* what) {
   return 0;
 }
 
+static int g_conv_t = -1;
+
+bool conv_t_enabled() {
+  if (g_conv_t < 0) {
+    const char* e = getenv("RD_CONV_T");
+    g_conv_t = (e && e[0] == '0') ? 0 : 1;
+  }
+  return g_conv_t != 0;
+}
+
 }  // namespace rd
 
 extern "C" {
@@ -48,6 +58,12 @@ int rd_version(void) { return 1; }
 const char* rd_last_error(void) { return rd::g_err; }
 
 uint64_t rd_launch_count(void) { return rd::g_launches; }
+
+int rd_set_conv_t(int on) {
+  const int prev = rd::conv_t_enabled() ? 1 : 0;
+  rd::g_conv_t = on ? 1 : 0;
+  return prev;
+}
 
 int rd_set_pdl(int on) {
   const int prev = rd::pdl_enabled() ? 1 : 0;

@@ -13,6 +13,7 @@ namespace rd {
 void set_error(const char* fmt, ...);
 void count_launch(int n = 1);
 bool pdl_enabled();   // programmatic dependent launch on (default) unless RD_PDL=0
+bool conv_t_enabled();   // transposed-orientation kernel for 3x3 / stride 1 / Cout 128 convolutions (default) unless RD_CONV_T=0
 
 // Returns 0 if ok; records the message otherwise.
 int check_launch(const char* what);

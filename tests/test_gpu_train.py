@@ -544,3 +544,49 @@ def test_conv_epilogue_batch_statistics(ops, shape, dtype):
     zf = ops.from_nhwc_padded(z1).double()
     assert float((coef1[2].double() - zf.mean((0, 2, 3))).abs().max()) < 1e-5 * max(1.0, float(zf.abs().max()))
     assert float((coef1[4].double() - zf.var((0, 2, 3), unbiased=False)).abs().max()) < 1e-4 * float(zf.var())
+
+
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16], ids=["bf16", "f16"])
+@pytest.mark.parametrize("shape", [(1, 128, 4, 131, False, False), (2, 128, 7, 300, True, True), (1, 64, 3, 64, False, True),
+                                   (2, 256, 5, 166, True, False), (1, 128, 1, 1, False, False), (2, 128, 64, 2656, True, True),
+                                   (3, 128, 2, 257, False, False)])
+def test_conv_transposed_orientation_matches_pixel_major_kernel(ops, shape, dtype):
+    """csrc/conv_t.cu (M = Cout = 128, N = 256 flattened pixels) against csrc/conv_tc.cu (M = 128 pixels of a row) on the same
+    operands: 3x3 stride 1, Cout 128, with scale / shift / ReLU / residual, with the fused batch statistics, at widths
+    that put tile borders everywhere (1, 64, 131, 166, 257, 300, 2656) -- and against torch."""
+    from rangedet_b200 import _lib
+    N, Ci, H, W, res, relu = shape
+    g = torch.Generator(device="cuda").manual_seed(31)
+    rnd = lambda t: t.to(dtype).float()
+    x = rnd(torch.randn((N, Ci, H, W), device="cuda", generator=g))
+    w = rnd(torch.randn((128, Ci, 3, 3), device="cuda", generator=g) * (2.0 / (Ci * 9)) ** 0.5)
+    scale, shift = torch.rand(128, device="cuda", generator=g) + 0.5, torch.randn(128, device="cuda", generator=g) * 0.2
+    r = rnd(torch.randn((N, 128, H, W), device="cuda", generator=g)) if res else None
+    xp, wp = ops.to_nhwc_padded(x, dtype=dtype), ops.pack_conv_weight(w, dtype=dtype)
+    rp = ops.to_nhwc_padded(r, dtype=dtype) if res else None
+    outs, stats = {}, {}
+    for on in (True, False):
+        prev = _lib.set_conv_t(on)
+        try:
+            outs[on] = ops.conv2d_nhwc(xp, wp, scale, shift, relu=relu, residual_pad=rp)
+            z, part, nslots = ops.conv2d_nhwc_stats(xp, wp)
+            stats[on] = (z, ops.bn_train_finalize(part, nslots, N, H, W, 128))
+            torch.cuda.synchronize()
+        finally:
+            _lib.set_conv_t(prev)
+    want = F.conv2d(x, w, padding=1) * scale[None, :, None, None] + shift[None, :, None, None]
+    want = want + r if res else want
+    want = torch.relu(want) if relu else want
+    ulp = 2 ** -7 if dtype == torch.bfloat16 else 2 ** -10
+    for on in (True, False):
+        got = outs[on]
+        assert float((ops.from_nhwc_padded(got) - want).abs().max()) <= ulp * float(want.abs().max()) + 2e-2 * (ulp / 2 ** -7), on
+        assert float(got[:, 0].float().abs().max()) == 0 and float(got[:, -1].float().abs().max()) == 0          # halo rows
+        assert float(got[:, :, 0].float().abs().max()) == 0 and float(got[:, :, -1].float().abs().max()) == 0    # halo columns
+    # same K order in both orientations: identical up to the hardware's in-MMA summation
+    d = (outs[True].float() - outs[False].float()).abs().max()
+    assert float(d) <= ulp * float(want.abs().max()), float(d)
+    assert float((stats[True][0].float() - stats[False][0].float()).abs().max()) <= ulp * float(stats[False][0].float().abs().max())
+    for row in (2, 4):   # mean, var
+        a, b = stats[True][1][row], stats[False][1][row]
+        assert float((a - b).abs().max()) <= 1e-4 * float(b.abs().max()) + 1e-6, row
