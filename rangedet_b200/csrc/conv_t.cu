@@ -66,14 +66,20 @@ struct Misc {
   float scale[CO], shift[CO];
 };
 
+// PROF: diagnostic build (RD_CONVT_PROF=1): clock64() cycles per role into prof[block][8]: 0 MMA total, 1 wait(a_full),
+// 2 wait(b_full), 3 wait(t_empty); 4 epilogue total, 5 wait(t_full), 6 wait(store read) + mask + barrier, 7 body.
+template <bool PROF>
 __global__ void __launch_bounds__(NTHREADS, 1)
 convt_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_x2,
              const __grid_constant__ CUtensorMap tm_w, const __grid_constant__ CUtensorMap tm_y,
              const __grid_constant__ CUtensorMap tm_r, const float* __restrict__ scale, const float* __restrict__ shift,
-             float* __restrict__ stats, const __grid_constant__ Params P) {
+             float* __restrict__ stats, long long* __restrict__ prof, const __grid_constant__ Params P) {
   extern __shared__ unsigned char smem_raw[];
   unsigned char* base = smem_raw + ((1024u - (tc::smem_u32(smem_raw) & 1023u)) & 1023u);
   const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+  auto tick = [&]() -> long long { return PROF ? clock64() : 0ll; };
+  const long long t_begin = tick();
+  long long pc1 = 0, pc2 = 0, pc3 = 0;
   if (t == 0) rd::pdl_trigger();
   unsigned char* strips = base;
   unsigned char* wts = base + OFF_W;
@@ -139,16 +145,16 @@ convt_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ C
     uint32_t sa = 0, pha = 0, sb = 0, phb = 0, it = 0;
     for (int tile = blockIdx.x; tile < P.ntiles; tile += gridDim.x, ++it) {
       const uint32_t buf = it & 1;
-      tc::mbar_wait(&M.t_empty[buf], ((it >> 1) & 1) ^ 1);
+      { const long long a0 = tick(); tc::mbar_wait(&M.t_empty[buf], ((it >> 1) & 1) ^ 1); pc3 += tick() - a0; }
       const uint32_t d_tmem = tmem_base + buf * (uint32_t)TN;
       bool first = true;
       for (int q = 0; q < kh; ++q)
         for (int dy = 0; dy < 3; ++dy) {
-          tc::mbar_wait(&M.a_full[sa], pha);
+          { const long long a0 = tick(); tc::mbar_wait(&M.a_full[sa], pha); pc1 += tick() - a0; }
           const uint32_t x_lo = strip_lo + sa * (uint32_t)(STRIP_BYTES >> 4);
 #pragma unroll 1
           for (int dx = 0; dx < 3; ++dx) {
-            tc::mbar_wait(&M.b_full[sb], phb);
+            { const long long a0 = tick(); tc::mbar_wait(&M.b_full[sb], phb); pc2 += tick() - a0; }
             tc::tc_fence_after();
             if (leader) {
               // A = weight tile (128 rows), B = strip rows [dx, dx + 256): one pixel = one 128-byte row = 8 address units
@@ -170,6 +176,12 @@ convt_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ C
       if (leader) tc::umma_commit(&M.t_full[buf]);
       __syncwarp();
     }
+    if (PROF && lane == 0) {
+      prof[blockIdx.x * 8 + 0] = tick() - t_begin;
+      prof[blockIdx.x * 8 + 1] = pc1;
+      prof[blockIdx.x * 8 + 2] = pc2;
+      prof[blockIdx.x * 8 + 3] = pc3;
+    }
   } else {
     // ===== epilogue: thread = TMEM lane = output channel =====
     const int q4 = warp & 3;                      // TMEM lane quadrant this warp may read (warps 2..5 -> 2, 3, 0, 1)
@@ -185,6 +197,7 @@ convt_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ C
     for (int tile = blockIdx.x; tile < P.ntiles; tile += gridDim.x, ++it) {
       const int p0 = P.p_first + tile * TN;
       const uint32_t buf = it & 1;
+      const long long e0 = tick();
       if (leader) tma::store_wait_read<0>();      // the previous tile's stores have read the staging tile
       {  // halo bits of the tile's 256 pixels: warp w covers pixels [32w, 32w+32) and [128+32w, 128+32w+32)
 #pragma unroll
@@ -208,9 +221,13 @@ convt_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ C
         }
         tc::mbar_wait(&M.r_full, it & 1);
       }
+      const long long e1 = tick();
       tc::mbar_wait(&M.t_full[buf], (it >> 1) & 1);
       __syncwarp();
       tc::tc_fence_after();
+      const long long e2 = tick();
+      pc2 += e1 - e0;
+      pc1 += e2 - e1;
       const uint32_t t_acc = tmem_base + lane_sel + buf * (uint32_t)TN;
 #pragma unroll 1
       for (int ch = 0; ch < 8; ++ch) {
@@ -236,6 +253,7 @@ convt_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ C
       tc::fence_proxy_async_smem();
       __syncwarp();
       if (lane == 0) tc::mbar_arrive(&M.t_empty[buf]);
+      pc3 += tick() - e2;
       tma::named_bar_sync(BAR_EPI, 128);
       if (leader) {
         tma::store_2d(&tm_y, sO, 0, p0);
@@ -244,6 +262,12 @@ convt_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ C
       }
     }
     if (leader) tma::store_wait_all<0>();
+    if (PROF && leader) {
+      prof[blockIdx.x * 8 + 4] = tick() - t_begin;
+      prof[blockIdx.x * 8 + 5] = pc1;
+      prof[blockIdx.x * 8 + 6] = pc2;
+      prof[blockIdx.x * 8 + 7] = pc3;
+    }
     if (stats != nullptr) {   // partial[(which * 128 + channel) * STATS_STRIDE + CTA]: the layout bn::fwd_finalize_kernel reads
       stats[(int64_t)c * STATS_STRIDE + blockIdx.x] = s_sum;
       stats[(int64_t)(CO + c) * STATS_STRIDE + blockIdx.x] = s_sq;
@@ -301,13 +325,34 @@ int RD_ACT_FN(rd_convt_run_, )(const void* x_pad, const void* w_packed, const fl
   RD_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
   const size_t smem = (size_t)OFF_MISC + sizeof(Misc) + 1024;
   RD_REQUIRE(smem <= 227 * 1024, "rd_conv(T): shared memory layout exceeds 227 KB (%zu)", smem);
-  RD_CUDA(rd::smem_optin(convt_kernel, smem));
+  RD_CUDA(rd::smem_optin(convt_kernel<false>, smem));
+  RD_CUDA(rd::smem_optin(convt_kernel<true>, smem));
   const int grid = P.ntiles < sms ? P.ntiles : sms;
   if (stats) {
     RD_REQUIRE(grid <= STATS_STRIDE, "rd_conv(T) stats: %d partial slots exceed %d", grid, STATS_STRIDE);
     if (stats_slots) *stats_slots = grid;
   }
-  RD_CUDA(rd::launch(convt_kernel, dim3(grid), dim3(NTHREADS), smem, stream, tm_x, tm_x2, tm_w, tm_y, tm_r, scale, shift, stats, P));
+  static const bool want_prof = [] { const char* e = getenv("RD_CONVT_PROF"); return e && e[0] == '1'; }();
+  if (want_prof) {   // diagnostic: per-role cycle counters, synchronous, printed to stderr
+    static long long* d_prof = nullptr;
+    if (!d_prof) RD_CUDA(cudaMalloc(&d_prof, 1024 * 8 * sizeof(long long)));
+    RD_CUDA(cudaMemsetAsync(d_prof, 0, 1024 * 8 * sizeof(long long), stream));
+    RD_CUDA(rd::launch(convt_kernel<true>, dim3(grid), dim3(NTHREADS), smem, stream, tm_x, tm_x2, tm_w, tm_y, tm_r, scale, shift, stats,
+                       d_prof, P));
+    RD_CUDA(cudaStreamSynchronize(stream));
+    static long long h[1024 * 8];
+    RD_CUDA(cudaMemcpy(h, d_prof, sizeof(long long) * 8 * grid, cudaMemcpyDeviceToHost));
+    double m[8] = {0};
+    for (int b = 0; b < grid; ++b)
+      for (int k = 0; k < 8; ++k) m[k] += (double)h[b * 8 + k] / grid;
+    const double tiles = (double)P.ntiles / grid;
+    fprintf(stderr, "[rd_conv(T) prof] Cin=%d tiles/cta=%.1f | per tile: mma %.0f (wait a_full %.0f, b_full %.0f, t_empty %.0f) | epi %.0f "
+            "(wait t_full %.0f, store+mask+bar %.0f, body %.0f)\n", Cin, tiles, m[0] / tiles, m[1] / tiles, m[2] / tiles, m[3] / tiles,
+            m[4] / tiles, m[5] / tiles, m[6] / tiles, m[7] / tiles);
+  } else {
+    RD_CUDA(rd::launch(convt_kernel<false>, dim3(grid), dim3(NTHREADS), smem, stream, tm_x, tm_x2, tm_w, tm_y, tm_r, scale, shift, stats,
+                       (long long*)nullptr, P));
+  }
   rd::count_launch();
   return rd::check_launch("rd_conv(T)");
 }
