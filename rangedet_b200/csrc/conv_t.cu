@@ -21,9 +21,10 @@
 //             are row-shifted views of it), and the 128 x 64 weight tile of every tap, through two rings
 //   warp 1    MMA issuer (converged warp, elected lane): 4 x tcgen05.mma M128 N256 K16 per tap and K-half, fp32
 //             accumulators double-buffered in all 512 TMEM columns
-//   warps 2-5 epilogue: thread = TMEM lane = OUTPUT CHANNEL, columns = pixels; scale / shift / residual / ReLU, halo
-//             mask, storage rounding, transposed 2-byte writes into a [pixel][channel] 128B-swizzled staging tile -> two
-//             TMA stores; the BatchNorm batch statistics of the stored values are plain per-thread sums here.
+//   warps 2-9 epilogue (two per TMEM lane quadrant, each 128 of the tile's pixel columns): thread = TMEM lane = OUTPUT
+//             CHANNEL; scale / shift / residual / ReLU, halo mask, storage rounding in pixel pairs, lane pairs swap halves so
+//             that 4-byte words [pixel][c, c+1] go into a [pixel][channel] 128B-swizzled staging tile -> two TMA stores;
+//             the BatchNorm batch statistics of the stored values are plain per-thread sums here.
 #include <stdlib.h>
 #include <string.h>
 
@@ -43,7 +44,7 @@ constexpr int STRIP_BYTES = STRIP_ROWS * 128; // 33792
 constexpr int WT_BYTES = CO * 128;            // 16384: one tap, one K-half
 constexpr int HALF_BYTES = TN * 128;          // 32768: staging tile of 64 channels
 constexpr int NSA = 2, NSB = 5;
-constexpr int NTHREADS = 192;
+constexpr int NTHREADS = 320;                // warp 0 producer, warp 1 MMA, warps 2-9 epilogue
 constexpr int BAR_EPI = 1;
 constexpr int STATS_STRIDE = 1184;            // = bn::MAX_BLOCKS
 constexpr int OFF_W = NSA * STRIP_BYTES;                  // 67584
@@ -89,7 +90,7 @@ convt_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ C
   if (t == 0) {
     for (int i = 0; i < NSA; ++i) { tc::mbar_init(&M.a_full[i], 1); tc::mbar_init(&M.a_empty[i], 1); }
     for (int i = 0; i < NSB; ++i) { tc::mbar_init(&M.b_full[i], 1); tc::mbar_init(&M.b_empty[i], 1); }
-    for (int i = 0; i < 2; ++i) { tc::mbar_init(&M.t_full[i], 1); tc::mbar_init(&M.t_empty[i], 4); }
+    for (int i = 0; i < 2; ++i) { tc::mbar_init(&M.t_full[i], 1); tc::mbar_init(&M.t_empty[i], 8); }
     tc::mbar_init(&M.r_full, 1);
     tc::fence_mbar_init();
     tma::prefetch_map(&tm_x);
@@ -183,14 +184,23 @@ convt_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ C
       prof[blockIdx.x * 8 + 3] = pc3;
     }
   } else {
-    // ===== epilogue: thread = TMEM lane = output channel =====
-    const int q4 = warp & 3;                      // TMEM lane quadrant this warp may read (warps 2..5 -> 2, 3, 0, 1)
+    // ===== epilogue: thread = TMEM lane = output channel; EIGHT warps, two per TMEM lane quadrant =====
+    // (One warp per scheduler cannot hide its own latencies: the first version, four warps writing 2-byte elements, spent
+    //  14.4 k cycles per tile against 9.2 k of MMA time.  Now warps w and w+4 share a quadrant and split the tile's pixel
+    //  columns, values are rounded in pairs, and lane pairs (c, c+1) swap halves so that every store is a 4-byte word
+    //  [pixel][c, c+1] -- 16 lanes cover 64 contiguous bytes of a row, the 128B swizzle keeps the two rows of a warp-wide
+    //  store in different banks.)
+    const int ew = warp - 2;                      // 0..7
+    const int q4 = warp & 3;                      // TMEM lane quadrant this warp may read
+    const int half = ew >> 2;                     // pixels [128*half, 128*half + 128) of the tile
     const int c = q4 * 32 + lane;
-    const int e = (warp - 2) * 32 + lane;         // 0..127: index among the epilogue threads
     const uint32_t lane_sel = (uint32_t)(q4 * 32) << 16;
     const bool leader = (warp == 2 && lane == 0);
     const float sc = M.scale[c], sh = M.shift[c];
-    unsigned char* my_col = sO + (c >> 6) * HALF_BYTES + (c & 7) * 2;   // + px*128 + (((c & 63) >> 3) ^ (px & 7)) << 4
+    const uint32_t odd = (uint32_t)(lane & 1);
+    const uint32_t sel = odd ? 0x3276u : 0x5410u; // odd: (partner.hi, mine.hi) = channels (c-1, c) of pixel j+1; even: (mine.lo, partner.lo)
+    unsigned char* my_row = sO + (c >> 6) * HALF_BYTES + odd * 128 + (c & 6) * 2;   // word (c & ~1) of row j + odd
+    unsigned char* my_col = sO + (c >> 6) * HALF_BYTES + (c & 7) * 2;               // 2-byte element of channel c (residual reads)
     const uint32_t my_chunk = (uint32_t)((c & 63) >> 3);
     float s_sum = 0.f, s_sq = 0.f;
     uint32_t it = 0;
@@ -199,20 +209,17 @@ convt_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ C
       const uint32_t buf = it & 1;
       const long long e0 = tick();
       if (leader) tma::store_wait_read<0>();      // the previous tile's stores have read the staging tile
-      {  // halo bits of the tile's 256 pixels: warp w covers pixels [32w, 32w+32) and [128+32w, 128+32w+32)
-#pragma unroll
-        for (int h = 0; h < 2; ++h) {
-          const int p = p0 + h * 128 + e;
-          bool halo = true;
-          if (p < P.P_total) {
-            const int col = p % P.Wp, row = (p / P.Wp) % P.Hp;
-            halo = col == 0 || col == P.Wp - 1 || row == 0 || row == P.Hp - 1;
-          }
-          const unsigned bits = __ballot_sync(0xffffffffu, halo);
-          if (lane == 0) M.mask[h * 4 + (warp - 2)] = bits;
+      {  // halo bits of the tile's 256 pixels: warp ew covers pixels [32 ew, 32 ew + 32)
+        const int p = p0 + ew * 32 + lane;
+        bool halo = true;
+        if (p < P.P_total) {
+          const int col = p % P.Wp, row = (p / P.Wp) % P.Hp;
+          halo = col == 0 || col == P.Wp - 1 || row == 0 || row == P.Hp - 1;
         }
+        const unsigned bits = __ballot_sync(0xffffffffu, halo);
+        if (lane == 0) M.mask[ew] = bits;
       }
-      tma::named_bar_sync(BAR_EPI, 128);
+      tma::named_bar_sync(BAR_EPI, 256);
       if (P.has_res) {                            // the other consumer's gradient / residual lands in the staging tile
         if (leader) {
           tc::mbar_arrive_expect_tx(&M.r_full, (uint32_t)(2 * HALF_BYTES));
@@ -228,25 +235,32 @@ convt_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ C
       const long long e2 = tick();
       pc2 += e1 - e0;
       pc1 += e2 - e1;
-      const uint32_t t_acc = tmem_base + lane_sel + buf * (uint32_t)TN;
+      const uint32_t t_acc = tmem_base + lane_sel + buf * (uint32_t)TN + (uint32_t)(half * 128);
 #pragma unroll 1
-      for (int ch = 0; ch < 8; ++ch) {
+      for (int ch = 0; ch < 4; ++ch) {
         float v[32];
         tc::tmem_ld_x32(t_acc + (uint32_t)(ch * 32), v);
-        const uint32_t mbits = M.mask[ch];
-        unsigned char* rowp = my_col + ch * 32 * 128;
+        const uint32_t mbits = M.mask[half * 4 + ch];
+        const int px0 = half * 128 + ch * 32;
 #pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          act_t* ptr = reinterpret_cast<act_t*>(rowp + j * 128 + ((my_chunk ^ (uint32_t)(j & 7)) << 4));
-          float a = fmaf(v[j], sc, sh);
-          if (P.has_res) a += act::to_float(*ptr);
-          if (P.relu) a = fmaxf(a, 0.f);
-          if ((mbits >> j) & 1u) a = 0.f;         // halo pixel: keep it zero
-          const act_t r = act::from_float(a);
-          *ptr = r;
-          const float f = act::to_float(r);
-          s_sum += f;
-          s_sq = fmaf(f, f, s_sq);
+        for (int j = 0; j < 32; j += 2) {
+          float a0 = fmaf(v[j], sc, sh), a1 = fmaf(v[j + 1], sc, sh);
+          if (P.has_res) {
+            a0 += act::to_float(*reinterpret_cast<const act_t*>(my_col + (px0 + j) * 128 + ((my_chunk ^ (uint32_t)(j & 7)) << 4)));
+            a1 += act::to_float(*reinterpret_cast<const act_t*>(my_col + (px0 + j + 1) * 128 + ((my_chunk ^ (uint32_t)((j + 1) & 7)) << 4)));
+          }
+          if (P.relu) { a0 = fmaxf(a0, 0.f); a1 = fmaxf(a1, 0.f); }
+          if ((mbits >> j) & 1u) a0 = 0.f;        // halo pixels: keep them zero
+          if ((mbits >> (j + 1)) & 1u) a1 = 0.f;
+          const uint32_t mine = act::pack2(a0, a1);                      // channel c: (pixel j, pixel j + 1)
+          float f0, f1;
+          act::unpack2(mine, f0, f1);
+          s_sum += f0 + f1;
+          s_sq = fmaf(f0, f0, fmaf(f1, f1, s_sq));
+          const uint32_t theirs = __shfl_xor_sync(0xffffffffu, mine, 1);
+          const uint32_t word = __byte_perm(mine, theirs, sel);          // channels (c & ~1, +1) of pixel j + odd
+          // all lanes of a pair have passed their residual reads of both rows before either writes (shuffle above)
+          *reinterpret_cast<uint32_t*>(my_row + (px0 + j) * 128 + (((my_chunk ^ odd) ^ (uint32_t)(j & 7)) << 4)) = word;
         }
       }
       tc::tc_fence_before();
@@ -254,7 +268,7 @@ convt_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ C
       __syncwarp();
       if (lane == 0) tc::mbar_arrive(&M.t_empty[buf]);
       pc3 += tick() - e2;
-      tma::named_bar_sync(BAR_EPI, 128);
+      tma::named_bar_sync(BAR_EPI, 256);
       if (leader) {
         tma::store_2d(&tm_y, sO, 0, p0);
         tma::store_2d(&tm_y, sO + HALF_BYTES, KC, p0);
@@ -268,9 +282,10 @@ convt_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ C
       prof[blockIdx.x * 8 + 6] = pc2;
       prof[blockIdx.x * 8 + 7] = pc3;
     }
-    if (stats != nullptr) {   // partial[(which * 128 + channel) * STATS_STRIDE + CTA]: the layout bn::fwd_finalize_kernel reads
-      stats[(int64_t)c * STATS_STRIDE + blockIdx.x] = s_sum;
-      stats[(int64_t)(CO + c) * STATS_STRIDE + blockIdx.x] = s_sq;
+    if (stats != nullptr) {   // partial[(which * 128 + channel) * STATS_STRIDE + slot], slot = 2 * CTA + pixel half
+      const int slot = (int)blockIdx.x * 2 + half;
+      stats[(int64_t)c * STATS_STRIDE + slot] = s_sum;
+      stats[(int64_t)(CO + c) * STATS_STRIDE + slot] = s_sq;
     }
   }
   tc::tc_fence_before();
@@ -329,8 +344,8 @@ int RD_ACT_FN(rd_convt_run_, )(const void* x_pad, const void* w_packed, const fl
   RD_CUDA(rd::smem_optin(convt_kernel<true>, smem));
   const int grid = P.ntiles < sms ? P.ntiles : sms;
   if (stats) {
-    RD_REQUIRE(grid <= STATS_STRIDE, "rd_conv(T) stats: %d partial slots exceed %d", grid, STATS_STRIDE);
-    if (stats_slots) *stats_slots = grid;
+    RD_REQUIRE(2 * grid <= STATS_STRIDE, "rd_conv(T) stats: %d partial slots exceed %d", 2 * grid, STATS_STRIDE);
+    if (stats_slots) *stats_slots = 2 * grid;
   }
   static const bool want_prof = [] { const char* e = getenv("RD_CONVT_PROF"); return e && e[0] == '1'; }();
   if (want_prof) {   // diagnostic: per-role cycle counters, synchronous, printed to stderr
