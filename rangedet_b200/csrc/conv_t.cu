@@ -43,13 +43,10 @@ constexpr int STRIP_ROWS = 264;               // 258 pixels used; 256-pixel box 
 constexpr int STRIP_BYTES = STRIP_ROWS * 128; // 33792
 constexpr int WT_BYTES = CO * 128;            // 16384: one tap, one K-half
 constexpr int HALF_BYTES = TN * 128;          // 32768: staging tile of 64 channels
-constexpr int NSA = 2, NSB = 5;
+constexpr int MAX_SA = 3, MAX_SB = 5;        // ring depths are chosen on the host (Params::nsa / nsb)
 constexpr int NTHREADS = 320;                // warp 0 producer, warp 1 MMA, warps 2-9 epilogue
 constexpr int BAR_EPI = 1;
 constexpr int STATS_STRIDE = 1184;            // = bn::MAX_BLOCKS
-constexpr int OFF_W = NSA * STRIP_BYTES;                  // 67584
-constexpr int OFF_O = OFF_W + NSB * WT_BYTES;             // 149504
-constexpr int OFF_MISC = OFF_O + 2 * HALF_BYTES;          // 215040
 
 struct Params {
   int kh;                 // Cin / 64
@@ -58,10 +55,12 @@ struct Params {
   int p_first;            // first interior pixel = Wp + 1
   int ntiles;
   int relu, has_res;
+  int nsa, nsb;           // strip / weight ring stages
+  int off_w, off_o, off_misc;
 };
 
 struct Misc {
-  uint64_t a_full[NSA], a_empty[NSA], b_full[NSB], b_empty[NSB], t_full[2], t_empty[2], r_full;
+  uint64_t a_full[MAX_SA], a_empty[MAX_SA], b_full[MAX_SB], b_empty[MAX_SB], t_full[2], t_empty[2], r_full;
   uint32_t tmem_slot, pad;
   uint32_t mask[8];       // halo bits of the 256 pixels of the tile in the epilogue
   float scale[CO], shift[CO];
@@ -83,13 +82,14 @@ convt_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ C
   long long pc1 = 0, pc2 = 0, pc3 = 0;
   if (t == 0) rd::pdl_trigger();
   unsigned char* strips = base;
-  unsigned char* wts = base + OFF_W;
-  unsigned char* sO = base + OFF_O;
-  Misc& M = *reinterpret_cast<Misc*>(base + OFF_MISC);
+  unsigned char* wts = base + P.off_w;
+  unsigned char* sO = base + P.off_o;
+  Misc& M = *reinterpret_cast<Misc*>(base + P.off_misc);
+  const uint32_t NSA = (uint32_t)P.nsa, NSB = (uint32_t)P.nsb;
 
   if (t == 0) {
-    for (int i = 0; i < NSA; ++i) { tc::mbar_init(&M.a_full[i], 1); tc::mbar_init(&M.a_empty[i], 1); }
-    for (int i = 0; i < NSB; ++i) { tc::mbar_init(&M.b_full[i], 1); tc::mbar_init(&M.b_empty[i], 1); }
+    for (int i = 0; i < MAX_SA; ++i) { tc::mbar_init(&M.a_full[i], 1); tc::mbar_init(&M.a_empty[i], 1); }
+    for (int i = 0; i < MAX_SB; ++i) { tc::mbar_init(&M.b_full[i], 1); tc::mbar_init(&M.b_empty[i], 1); }
     for (int i = 0; i < 2; ++i) { tc::mbar_init(&M.t_full[i], 1); tc::mbar_init(&M.t_empty[i], 8); }
     tc::mbar_init(&M.r_full, 1);
     tc::fence_mbar_init();
@@ -338,7 +338,17 @@ int RD_ACT_FN(rd_convt_run_, )(const void* x_pad, const void* w_packed, const fl
   int dev = 0, sms = 0;
   RD_CUDA(cudaGetDevice(&dev));
   RD_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-  const size_t smem = (size_t)OFF_MISC + sizeof(Misc) + 1024;
+  {
+    // 227 KB: strips 33 KB each, weight tiles 16 KB each, staging 64 KB.  Default 3 strips + 3 weight tiles (the MMA warp
+    // waited ~2 k of 16 k cycles per tile on the strip / weight barriers with 2 + 5); RD_CONVT_RINGS=ab overrides.
+    P.nsa = 3; P.nsb = 3;
+    const char* e = getenv("RD_CONVT_RINGS");
+    if (e && e[0] >= '2' && e[0] <= '3' && e[1] >= '2' && e[1] <= '5') { P.nsa = e[0] - '0'; P.nsb = e[1] - '0'; }
+    P.off_w = P.nsa * STRIP_BYTES;
+    P.off_o = P.off_w + P.nsb * WT_BYTES;
+    P.off_misc = P.off_o + 2 * HALF_BYTES;
+  }
+  const size_t smem = (size_t)P.off_misc + sizeof(Misc) + 1024;
   RD_REQUIRE(smem <= 227 * 1024, "rd_conv(T): shared memory layout exceeds 227 KB (%zu)", smem);
   RD_CUDA(rd::smem_optin(convt_kernel<false>, smem));
   RD_CUDA(rd::smem_optin(convt_kernel<true>, smem));
