@@ -339,9 +339,10 @@ int RD_ACT_FN(rd_convt_run_, )(const void* x_pad, const void* w_packed, const fl
   RD_CUDA(cudaGetDevice(&dev));
   RD_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
   {
-    // 227 KB: strips 33 KB each, weight tiles 16 KB each, staging 64 KB.  Default 3 strips + 3 weight tiles (the MMA warp
-    // waited ~2 k of 16 k cycles per tile on the strip / weight barriers with 2 + 5); RD_CONVT_RINGS=ab overrides.
-    P.nsa = 3; P.nsb = 3;
+    // 227 KB: strips 33 KB each, weight tiles 16 KB each, staging 64 KB.  2 strips + 5 weight tiles; 2+4 and 3+3 measured
+    // within 2 % (RD_CONVT_RINGS=ab overrides): the MMA warp's remaining waits (~4 k of 12 k cycles per tile) are the
+    // L2 -> shared-memory stream itself (488 KB per tile and SM, 59 % of it the weight tiles every CTA re-reads).
+    P.nsa = 2; P.nsb = 5;
     const char* e = getenv("RD_CONVT_RINGS");
     if (e && e[0] >= '2' && e[0] <= '3' && e[1] >= '2' && e[1] <= '5') { P.nsa = e[0] - '0'; P.nsb = e[1] - '0'; }
     P.off_w = P.nsa * STRIP_BYTES;
