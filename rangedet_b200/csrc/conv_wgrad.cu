@@ -260,7 +260,15 @@ static int make_plan(Plan& P, int N, int H, int W, int CA, int CB, int ksize, in
   P.a_bytes = P.a_units * TM * P.ch_unit * 2;
   P.b_bytes = P.b_units * b_px * P.ch_unit * 2;
   P.stage_bytes = ((P.a_units * P.a_unit_bytes + P.b_units * P.b_unit_bytes + 1023) / 1024) * 1024;
-  P.nstages = (220 * 1024) / P.stage_bytes;
+  {
+    static int cap_kb = -1;   // RD_WGRAD_SMEM_KB: cap of the operand ring (tuning: co-residency with the BatchNorm passes)
+    if (cap_kb < 0) {
+      const char* e = getenv("RD_WGRAD_SMEM_KB");
+      cap_kb = e ? atoi(e) : 0;
+      if (cap_kb < 32 || cap_kb > 220) cap_kb = 220;
+    }
+    P.nstages = (cap_kb * 1024) / P.stage_bytes;
+  }
   if (P.nstages > MAX_STAGES) P.nstages = MAX_STAGES;
   RD_REQUIRE(P.nstages >= 2, "rd_conv2d_wgrad: stage of %d bytes does not fit twice in shared memory", P.stage_bytes);
   int cols = 32;
