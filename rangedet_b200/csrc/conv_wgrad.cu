@@ -268,6 +268,7 @@ static int make_plan(Plan& P, int N, int H, int W, int CA, int CB, int ksize, in
       if (cap_kb < 32 || cap_kb > 220) cap_kb = 220;
     }
     P.nstages = (cap_kb * 1024) / P.stage_bytes;
+    if (P.nstages < 2) P.nstages = (220 * 1024) / P.stage_bytes;   // a cap below two stages is ignored
   }
   if (P.nstages > MAX_STAGES) P.nstages = MAX_STAGES;
   RD_REQUIRE(P.nstages >= 2, "rd_conv2d_wgrad: stage of %d bytes does not fit twice in shared memory", P.stage_bytes);
