@@ -55,6 +55,7 @@ struct Params {
   int p_first;            // first interior pixel = Wp + 1
   int ntiles;
   int relu, has_res;
+  int cout;               // 128, or 64: the weight tile's rows 64..127 are then TMA zero fill and TMEM lanes 64..127 idle
   int nsa, nsb;           // strip / weight ring stages
   int off_w, off_o, off_misc;
 };
@@ -103,7 +104,7 @@ convt_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ C
     tc::tmem_relinquish();
   }
   rd::pdl_wait();   // everything above touched only shared memory / TMEM / kernel parameters
-  for (int c = t; c < CO; c += NTHREADS) {
+  for (int c = t; c < P.cout; c += NTHREADS) {
     M.scale[c] = scale ? __ldg(scale + c) : 1.f;
     M.shift[c] = shift ? __ldg(shift + c) : 0.f;
   }
@@ -196,7 +197,9 @@ convt_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ C
     const int c = q4 * 32 + lane;
     const uint32_t lane_sel = (uint32_t)(q4 * 32) << 16;
     const bool leader = (warp == 2 && lane == 0);
-    const float sc = M.scale[c], sh = M.shift[c];
+    const bool live = c < P.cout;                 // whole warps: q4 >= 2 idles when Cout == 64 (it still joins every barrier)
+    const int nh = P.cout / KC;                   // 64-channel halves of the staging tile in use
+    const float sc = live ? M.scale[c] : 0.f, sh = live ? M.shift[c] : 0.f;
     const uint32_t odd = (uint32_t)(lane & 1);
     const uint32_t sel = odd ? 0x3276u : 0x5410u; // odd: (partner.hi, mine.hi) = channels (c-1, c) of pixel j+1; even: (mine.lo, partner.lo)
     unsigned char* my_row = sO + (c >> 6) * HALF_BYTES + odd * 128 + (c & 6) * 2;   // word (c & ~1) of row j + odd
@@ -222,9 +225,8 @@ convt_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ C
       tma::named_bar_sync(BAR_EPI, 256);
       if (P.has_res) {                            // the other consumer's gradient / residual lands in the staging tile
         if (leader) {
-          tc::mbar_arrive_expect_tx(&M.r_full, (uint32_t)(2 * HALF_BYTES));
-          tma::load_2d(sO, &tm_r, &M.r_full, 0, p0);
-          tma::load_2d(sO + HALF_BYTES, &tm_r, &M.r_full, KC, p0);
+          tc::mbar_arrive_expect_tx(&M.r_full, (uint32_t)(nh * HALF_BYTES));
+          for (int hf = 0; hf < nh; ++hf) tma::load_2d(sO + hf * HALF_BYTES, &tm_r, &M.r_full, hf * KC, p0);
         }
         tc::mbar_wait(&M.r_full, it & 1);
       }
@@ -237,7 +239,7 @@ convt_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ C
       pc1 += e2 - e1;
       const uint32_t t_acc = tmem_base + lane_sel + buf * (uint32_t)TN + (uint32_t)(half * 128);
 #pragma unroll 1
-      for (int ch = 0; ch < 4; ++ch) {
+      for (int ch = 0; ch < (live ? 4 : 0); ++ch) {
         float v[32];
         tc::tmem_ld_x32(t_acc + (uint32_t)(ch * 32), v);
         const uint32_t mbits = M.mask[half * 4 + ch];
@@ -270,8 +272,7 @@ convt_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ C
       pc3 += tick() - e2;
       tma::named_bar_sync(BAR_EPI, 256);
       if (leader) {
-        tma::store_2d(&tm_y, sO, 0, p0);
-        tma::store_2d(&tm_y, sO + HALF_BYTES, KC, p0);
+        for (int hf = 0; hf < nh; ++hf) tma::store_2d(&tm_y, sO + hf * HALF_BYTES, hf * KC, p0);
         tma::store_commit();
       }
     }
@@ -282,10 +283,10 @@ convt_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ C
       prof[blockIdx.x * 8 + 6] = pc2;
       prof[blockIdx.x * 8 + 7] = pc3;
     }
-    if (stats != nullptr) {   // partial[(which * 128 + channel) * STATS_STRIDE + slot], slot = 2 * CTA + pixel half
+    if (stats != nullptr && live) {   // partial[(which * Cout + channel) * STATS_STRIDE + slot], slot = 2 * CTA + pixel half
       const int slot = (int)blockIdx.x * 2 + half;
       stats[(int64_t)c * STATS_STRIDE + slot] = s_sum;
-      stats[(int64_t)(CO + c) * STATS_STRIDE + slot] = s_sq;
+      stats[(int64_t)(P.cout + c) * STATS_STRIDE + slot] = s_sq;
     }
   }
   tc::tc_fence_before();
@@ -296,14 +297,16 @@ convt_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ C
 }  // namespace convt_<storage type>
 namespace convt = RD_ACT_NS(convt);
 
-// Called by conv_tc.cu's dispatcher (same storage-type pass).  y = relu?(conv3x3(x) * scale + shift + residual), Cout = 128.
+// Called by conv_tc.cu's dispatcher (same storage-type pass).  y = relu?(conv3x3(x) * scale + shift + residual), Cout = 128 or 64.
 int RD_ACT_FN(rd_convt_run_, )(const void* x_pad, const void* w_packed, const float* scale, const float* shift,
-                               const void* residual_pad, void* y_pad, int N, int H, int W, int Cin, int relu,
+                               const void* residual_pad, void* y_pad, int N, int H, int W, int Cin, int Cout, int relu,
                                cudaStream_t stream, float* stats, int* stats_slots) {
   using namespace convt;
+  RD_REQUIRE(Cout == 64 || Cout == 128, "rd_conv(T): Cout must be 64 or 128");
   Params P;
   memset(&P, 0, sizeof(P));
   P.kh = Cin / KC;
+  P.cout = Cout;
   P.Wp = W + 2;
   P.Hp = H + 2;
   const int64_t total = (int64_t)N * P.Hp * P.Wp;
@@ -323,14 +326,15 @@ int RD_ACT_FN(rd_convt_run_, )(const void* x_pad, const void* w_packed, const fl
     if (tma::make_map(&tm_x2, RD_ACT_TMA_TYPE, x_pad, 2, d, s, b2, CU_TENSOR_MAP_SWIZZLE_128B)) return 1;
   }
   {
-    const uint64_t d[3] = {(uint64_t)Cin, (uint64_t)CO, 9u};
-    const uint64_t s[2] = {(uint64_t)Cin * 2, (uint64_t)Cin * CO * 2};
+    // box of 128 rows on a map with Cout rows: with Cout == 64 the upper half of every weight tile is TMA zero fill
+    const uint64_t d[3] = {(uint64_t)Cin, (uint64_t)Cout, 9u};
+    const uint64_t s[2] = {(uint64_t)Cin * 2, (uint64_t)Cin * Cout * 2};
     const uint32_t b[3] = {(uint32_t)KC, (uint32_t)CO, 1u};
     if (tma::make_map(&tm_w, RD_ACT_TMA_TYPE, w_packed, 3, d, s, b, CU_TENSOR_MAP_SWIZZLE_128B)) return 1;
   }
   {
-    const uint64_t d[2] = {(uint64_t)CO, (uint64_t)total};
-    const uint64_t s[1] = {(uint64_t)CO * 2};
+    const uint64_t d[2] = {(uint64_t)Cout, (uint64_t)total};
+    const uint64_t s[1] = {(uint64_t)Cout * 2};
     const uint32_t b[2] = {(uint32_t)KC, (uint32_t)TN};
     if (tma::make_map(&tm_y, RD_ACT_TMA_TYPE, y_pad, 2, d, s, b, CU_TENSOR_MAP_SWIZZLE_128B)) return 1;
     if (tma::make_map(&tm_r, RD_ACT_TMA_TYPE, residual_pad ? residual_pad : y_pad, 2, d, s, b, CU_TENSOR_MAP_SWIZZLE_128B)) return 1;

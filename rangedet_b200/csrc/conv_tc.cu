@@ -33,7 +33,7 @@
 
 // conv_t.cu: 3x3 / stride 1 / Cout = 128 in the transposed GEMM orientation (M = Cout, N = 256 pixels)
 int RD_ACT_FN(rd_convt_run_, )(const void* x_pad, const void* w_packed, const float* scale, const float* shift,
-                               const void* residual_pad, void* y_pad, int N, int H, int W, int Cin, int relu,
+                               const void* residual_pad, void* y_pad, int N, int H, int W, int Cin, int Cout, int relu,
                                cudaStream_t stream, float* stats, int* stats_slots);
 
 namespace RD_ACT_NS(conv) {
@@ -483,9 +483,11 @@ static int run(int mode, const void* x_pad, const void* w_packed, const float* s
     // 3x3 stride-1 convolutions with 128 output channels (head towers, res2 / res3a / res3 / agg2 and their data
     // gradients) take the transposed orientation of conv_t.cu: 96 instead of 128 B/clk of shared-memory operand reads per
     // MMA, tiles over the flattened pixel grid.  RD_CONV_T=0 keeps them here (A/B timing, cross-check).
-    if (rd::conv_t_enabled() && mode == 0 && ksize == 3 && stride_w == 1 && Cout == 128 && y_ctotal == Cout && !res_after_relu)
-      return RD_ACT_FN(rd_convt_run_, )(x_pad, w_packed, scale, shift, residual_pad, y_pad, N, H, W_in, Cin, relu, stream, stats,
-                                        stats_slots);
+    static const int t64 = [] { const char* e = getenv("RD_CONV_T64"); return (e && e[0] == '0') ? 0 : 1; }();
+    if (rd::conv_t_enabled() && mode == 0 && ksize == 3 && stride_w == 1 && (Cout == 128 || (Cout == 64 && t64)) &&
+        y_ctotal == Cout && !res_after_relu)
+      return RD_ACT_FN(rd_convt_run_, )(x_pad, w_packed, scale, shift, residual_pad, y_pad, N, H, W_in, Cin, Cout, relu, stream,
+                                        stats, stats_slots);
   }
   Params P;
   memset(&P, 0, sizeof(P));

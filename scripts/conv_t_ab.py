@@ -5,11 +5,11 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from rangedet_b200 import _lib, ops
 dev, DT = "cuda", torch.float16
 g = torch.Generator(device=dev).manual_seed(0)
-for (ci, w) in [(128, 2656), (128, 1328), (128, 664), (128, 332), (128, 166), (64, 1328), (256, 664)]:
+for (ci, w, co) in [(128, 2656, 128), (128, 664, 128), (64, 2656, 64), (64, 1328, 64), (128, 1328, 64)]:
     B, H = 2, 64
     x = ops.to_nhwc_padded(torch.randn((B, ci, H, w), device=dev, generator=g), dtype=DT)
-    wt = ops.pack_conv_weight(torch.randn((128, ci, 3, 3), device=dev, generator=g) * 0.03, dtype=DT)
-    y = torch.zeros((B, H + 2, w + 2, 128), device=dev, dtype=DT)
+    wt = ops.pack_conv_weight(torch.randn((co, ci, 3, 3), device=dev, generator=g) * 0.03, dtype=DT)
+    y = torch.zeros((B, H + 2, w + 2, co), device=dev, dtype=DT)
     res = {}
     for on in (True, False):
         _lib.set_conv_t(on)
@@ -21,6 +21,6 @@ for (ci, w) in [(128, 2656), (128, 1328), (128, 664), (128, 332), (128, 166), (6
             for _ in range(20): fn()
             b.record(); torch.cuda.synchronize()
             us = a.elapsed_time(b) / 20 * 1e3
-            res["%s_%s" % ("T" if on else "P", fn_name)] = {"us": round(us, 1), "TFLOPs": round(2.0 * B * H * w * ci * 128 * 9 / us / 1e6, 1)}
+            res["%s_%s" % ("T" if on else "P", fn_name)] = {"us": round(us, 1), "TFLOPs": round(2.0 * B * H * w * ci * co * 9 / us / 1e6, 1)}
     _lib.set_conv_t(True)
-    print(json.dumps({"Cin": ci, "W": w, **res}), flush=True)
+    print(json.dumps({"Cin": ci, "Cout": co, "W": w, **res}), flush=True)

@@ -1,5 +1,5 @@
 #!/bin/bash
-for r in 25 33 34 24; do
+for r in 25; do
   echo "== rings $r"
   RD_CONVT_RINGS=$r timeout 300 python scripts/conv_t_ab.py 2>&1 | python -c "
 import sys, json

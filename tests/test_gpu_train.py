@@ -547,21 +547,22 @@ def test_conv_epilogue_batch_statistics(ops, shape, dtype):
 
 
 @pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16], ids=["bf16", "f16"])
+@pytest.mark.parametrize("Co", [128, 64])
 @pytest.mark.parametrize("shape", [(1, 128, 4, 131, False, False), (2, 128, 7, 300, True, True), (1, 64, 3, 64, False, True),
                                    (2, 256, 5, 166, True, False), (1, 128, 1, 1, False, False), (2, 128, 64, 2656, True, True),
                                    (3, 128, 2, 257, False, False)])
-def test_conv_transposed_orientation_matches_pixel_major_kernel(ops, shape, dtype):
-    """csrc/conv_t.cu (M = Cout = 128, N = 256 flattened pixels) against csrc/conv_tc.cu (M = 128 pixels of a row) on the same
-    operands: 3x3 stride 1, Cout 128, with scale / shift / ReLU / residual, with the fused batch statistics, at widths
+def test_conv_transposed_orientation_matches_pixel_major_kernel(ops, shape, dtype, Co):
+    """csrc/conv_t.cu (M = Cout, N = 256 flattened pixels) against csrc/conv_tc.cu (M = 128 pixels of a row) on the same
+    operands: 3x3 stride 1, Cout 128 and 64, with scale / shift / ReLU / residual, with the fused batch statistics, at widths
     that put tile borders everywhere (1, 64, 131, 166, 257, 300, 2656) -- and against torch."""
     from rangedet_b200 import _lib
     N, Ci, H, W, res, relu = shape
     g = torch.Generator(device="cuda").manual_seed(31)
     rnd = lambda t: t.to(dtype).float()
     x = rnd(torch.randn((N, Ci, H, W), device="cuda", generator=g))
-    w = rnd(torch.randn((128, Ci, 3, 3), device="cuda", generator=g) * (2.0 / (Ci * 9)) ** 0.5)
-    scale, shift = torch.rand(128, device="cuda", generator=g) + 0.5, torch.randn(128, device="cuda", generator=g) * 0.2
-    r = rnd(torch.randn((N, 128, H, W), device="cuda", generator=g)) if res else None
+    w = rnd(torch.randn((Co, Ci, 3, 3), device="cuda", generator=g) * (2.0 / (Ci * 9)) ** 0.5)
+    scale, shift = torch.rand(Co, device="cuda", generator=g) + 0.5, torch.randn(Co, device="cuda", generator=g) * 0.2
+    r = rnd(torch.randn((N, Co, H, W), device="cuda", generator=g)) if res else None
     xp, wp = ops.to_nhwc_padded(x, dtype=dtype), ops.pack_conv_weight(w, dtype=dtype)
     rp = ops.to_nhwc_padded(r, dtype=dtype) if res else None
     outs, stats = {}, {}
@@ -570,7 +571,7 @@ def test_conv_transposed_orientation_matches_pixel_major_kernel(ops, shape, dtyp
         try:
             outs[on] = ops.conv2d_nhwc(xp, wp, scale, shift, relu=relu, residual_pad=rp)
             z, part, nslots = ops.conv2d_nhwc_stats(xp, wp)
-            stats[on] = (z, ops.bn_train_finalize(part, nslots, N, H, W, 128))
+            stats[on] = (z, ops.bn_train_finalize(part, nslots, N, H, W, Co))
             torch.cuda.synchronize()
         finally:
             _lib.set_conv_t(prev)
