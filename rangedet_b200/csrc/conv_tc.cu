@@ -483,7 +483,9 @@ static int run(int mode, const void* x_pad, const void* w_packed, const float* s
     // 3x3 stride-1 convolutions with 128 output channels (head towers, res2 / res3a / res3 / agg2 and their data
     // gradients) take the transposed orientation of conv_t.cu: 96 instead of 128 B/clk of shared-memory operand reads per
     // MMA, tiles over the flattened pixel grid.  RD_CONV_T=0 keeps them here (A/B timing, cross-check).
-    static const int t64 = [] { const char* e = getenv("RD_CONV_T64"); return (e && e[0] == '0') ? 0 : 1; }();
+    // Cout == 64 also runs there (upper half of the weight tile zero-filled by TMA), but half of every M128 MMA is then
+    // wasted and it measured SLOWER than the pixel-major kernel (64->64 @2x64x2656: 47.8 vs 35.6 us): opt-in only.
+    static const int t64 = [] { const char* e = getenv("RD_CONV_T64"); return (e && e[0] == '1') ? 1 : 0; }();
     if (rd::conv_t_enabled() && mode == 0 && ksize == 3 && stride_w == 1 && (Cout == 128 || (Cout == 64 && t64)) &&
         y_ctotal == Cout && !res_after_relu)
       return RD_ACT_FN(rd_convt_run_, )(x_pad, w_packed, scale, shift, residual_pad, y_pad, N, H, W_in, Cin, Cout, relu, stream,
