@@ -279,13 +279,14 @@ struct Counters {
   int nb_total;    // neighbour entries
   int nb_overflow;
   unsigned min_x, min_y, max_x, max_y, max_ext;  // order-preserving encodings of floats
+  int cand_overflow;   // the candidate lists of the parallel path do not fit their reservation: use the sequential scan
 };
 
 struct Layout {
   size_t keys_in, keys_out, idx_in, order, bx, aabb, hashr, cell_id, cell_id_s, rank_in, cell_rank,
       cell_start, cell_end, params, counters, kept_rank, nb_start, nb_list, theta, theta_s, theta_rank,
-      aabb_c, hash_c, th_range, cub_temp, total;
-  size_t cub_bytes, nb_cap;
+      aabb_c, hash_c, th_range, cand_cnt, cand_off, cand_j, cand_flag, cub_temp, total;
+  size_t cub_bytes, nb_cap, cand_cap;
 };
 
 __host__ inline size_t al(size_t x) { return (x + 255) & ~(size_t)255; }
@@ -306,6 +307,10 @@ __host__ inline Layout make_layout(int n) {
   L.theta = take(N * 4); L.theta_s = take(N * 4); L.theta_rank = take(N * 4);
   L.aabb_c = take(N * 16); L.hash_c = take(N * 8);   // AABB / hash range in CELL order (aligned with cell_rank)
   L.th_range = take(N * 6 * 4);                      // per box: [first, last) of its three theta segments
+  // parallel path: candidate pairs (i, j > i) of ALL boxes, 64 per box on average; beyond that the sequential scan runs
+  L.cand_cap = N * 64 + 65536;
+  L.cand_cnt = take((N + 1) * 4); L.cand_off = take((N + 1) * 4);
+  L.cand_j = take(L.cand_cap * 4); L.cand_flag = take(L.cand_cap);
   L.cub_bytes = (size_t)(16u << 20) + N * 32;
   L.cub_temp = take(L.cub_bytes);
   L.total = o;
@@ -328,7 +333,7 @@ __device__ __forceinline__ float ord2f(unsigned o) {
 __global__ void init_kernel(const float* __restrict__ dets, int n, float* keys, int* idx, Counters* ctr) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i == 0) {
-    ctr->kept = 0; ctr->nb_total = 0; ctr->nb_overflow = 0;
+    ctr->kept = 0; ctr->nb_total = 0; ctr->nb_overflow = 0; ctr->cand_overflow = 0;
     ctr->min_x = 0xffffffffu; ctr->min_y = 0xffffffffu; ctr->max_x = 0u; ctr->max_y = 0u; ctr->max_ext = 0u;
   }
   if (i < n) {
@@ -488,6 +493,194 @@ __global__ void theta_range_kernel(const float* __restrict__ theta, const float*
 }
 
 constexpr int NSEG = 12;   // candidate segments of one kept box: 9 grid cells + 3 theta ranges
+
+// ---------------------------------------------------------------------------------------------------------------
+// Parallel path.  The reference's loop (nms.h:497-517) evaluates box i against later boxes only when i is kept, one i
+// after the other.  Which later boxes i WOULD suppress / take as voting neighbours does not depend on that order, so
+// the expensive part -- the half-plane-intersection IoU of every candidate pair -- is computed for ALL boxes at once,
+// one warp per box; what stays sequential is a walk over the kept boxes that only flips bitmap bits:
+//   cand_count_kernel   candidates of box i = later boxes in its 12 segments that pass the AABB / hash tests
+//   (exclusive scan)    -> cand_off
+//   cand_eval_kernel    compact them (rank order within a segment), evaluate overlap(box_i, box_j): flag bit 0
+//                       ovr >= thresh (suppress, nms.h:511), bit 1 ovr > thresh_vote (neighbour, :513)
+//   resolve_kernel      one CTA: next unsuppressed rank i is kept; for its candidates j still unsuppressed: set the
+//                       suppress bit / append the neighbour -- exactly the state the reference sees when it reaches i
+// Same candidate set, same overlap(box_i, box_j) argument order, same suppression semantics as the sequential scan:
+// keep indices and neighbour sets are identical (the merge kernel restores rank order of the neighbours).
+// ---------------------------------------------------------------------------------------------------------------
+struct SegInfo {
+  int start[NSEG];
+  int off[NSEG + 1];
+};
+
+// segments of box ri, filled by lanes 0..11 of the calling warp and broadcast through shuffles
+__device__ __forceinline__ void warp_segments(int ri, const GridParams& gp, const float4& ai, const int* __restrict__ cell_start,
+                                              const int* __restrict__ cell_end, const int* __restrict__ th_range, int lane,
+                                              int& my_start, int& my_len) {
+  int cx, cy;
+  cell_of(gp, ai.x, ai.y, &cx, &cy);
+  int s0 = 0, len = 0;
+  if (lane < 9) {
+    const int yy = cy + lane / 3 - 1, xx = cx + lane % 3 - 1;
+    if (yy >= 0 && yy < gp.ny && xx >= 0 && xx < gp.nx) {
+      const int c = yy * gp.nx + xx;
+      s0 = cell_start[c];
+      len = cell_end[c] - s0;
+    }
+  } else if (lane < NSEG) {
+    s0 = th_range[(size_t)ri * 6 + 2 * (lane - 9)];
+    len = th_range[(size_t)ri * 6 + 2 * (lane - 9) + 1] - s0;
+  }
+  my_start = s0;
+  my_len = len > 0 ? len : 0;
+}
+
+// candidate test of entry e of segment q for box ri; returns the candidate's rank or -1
+__device__ __forceinline__ int cand_test(int q, int e, int ri, const float4& ai, const short4& hi_key,
+                                         const int* __restrict__ cell_rank, const float4* __restrict__ aabb_c,
+                                         const short4* __restrict__ hash_c, const int* __restrict__ theta_rank,
+                                         const float4* __restrict__ aabb, const short4* __restrict__ hashr) {
+  if (q < 9) {
+    const int rb = cell_rank[e];
+    if (rb <= ri) return -1;
+    const float4 ab = aabb_c[e];
+    const bool near = !(ai.z < ab.x || ab.z < ai.x || ai.w < ab.y || ab.w < ai.y);
+    return (near && share_key(hi_key, hash_c[e])) ? rb : -1;
+  }
+  const int rb = theta_rank[e];
+  if (rb <= ri) return -1;
+  const float4 ab = aabb[rb];
+  const bool near = !(ai.z < ab.x || ab.z < ai.x || ai.w < ab.y || ab.w < ai.y);
+  return (!near && share_key(hi_key, hashr[rb])) ? rb : -1;
+}
+
+constexpr int CAND_WARPS = 8;   // boxes per CTA of the two candidate kernels
+
+template <bool EVAL>
+__global__ void __launch_bounds__(CAND_WARPS * 32)
+cand_kernel(const float* __restrict__ bx, const float4* __restrict__ aabb, const short4* __restrict__ hashr,
+            const int* __restrict__ cell_rank, const int* __restrict__ cell_start, const int* __restrict__ cell_end,
+            const float4* __restrict__ aabb_c, const short4* __restrict__ hash_c, const int* __restrict__ th_range,
+            const int* __restrict__ theta_rank, const GridParams* gpp, int n, float thresh, float thresh_vote, int is3d,
+            int* __restrict__ cand_cnt, const int* __restrict__ cand_off, int* __restrict__ cand_j,
+            unsigned char* __restrict__ cand_flag, int cand_cap, Counters* ctr) {
+  const int lane = threadIdx.x & 31;
+  const int ri = blockIdx.x * CAND_WARPS + (threadIdx.x >> 5);
+  if (ri >= n) return;
+  const GridParams gp = *gpp;
+  const float4 ai = aabb[ri];
+  const short4 hi_key = hashr[ri];
+  int my_start, my_len;
+  warp_segments(ri, gp, ai, cell_start, cell_end, th_range, lane, my_start, my_len);
+  int base = 0;
+  if (EVAL) {
+    base = cand_off[ri];
+    if (ctr->cand_overflow || cand_off[n] > cand_cap) {   // uniform: the host falls back to the sequential scan
+      if (ri == 0 && lane == 0) ctr->cand_overflow = 1;
+      return;
+    }
+  }
+  int count = 0;
+  for (int q = 0; q < NSEG; ++q) {
+    const int s0 = __shfl_sync(0xffffffffu, my_start, q), len = __shfl_sync(0xffffffffu, my_len, q);
+    for (int b0 = 0; b0 < len; b0 += 32) {
+      const int e = b0 + lane;
+      const int rb = e < len ? cand_test(q, s0 + e, ri, ai, hi_key, cell_rank, aabb_c, hash_c, theta_rank, aabb, hashr) : -1;
+      const unsigned hit = __ballot_sync(0xffffffffu, rb >= 0);
+      if (EVAL && rb >= 0) cand_j[base + count + __popc(hit & ((1u << lane) - 1u))] = rb;
+      count += __popc(hit);
+    }
+  }
+  if (!EVAL) {
+    if (lane == 0) cand_cnt[ri] = count;
+    return;
+  }
+  __syncwarp();
+  float bi[D];
+#pragma unroll
+  for (int k = 0; k < D; ++k) bi[k] = bx[(size_t)ri * D + k];
+  for (int k = lane; k < count; k += 32) {   // one pair per lane
+    const int rb = cand_j[base + k];
+    float bj[D];
+#pragma unroll
+    for (int u = 0; u < D; ++u) bj[u] = bx[(size_t)rb * D + u];
+    Checker chk;
+    const float ovr = chk.overlap(bi, bj, is3d != 0);
+    cand_flag[base + k] = (unsigned char)((ovr >= thresh ? 1 : 0) | (ovr > thresh_vote ? 2 : 0));
+  }
+}
+
+// ONE CTA.  Dynamic shared memory: suppression bitmap.  Per kept box: two loads for its candidate range, one coalesced
+// sweep over (rank, flags) -- no geometry on this critical path any more.
+__global__ void __launch_bounds__(512, 1)
+resolve_kernel(const int* __restrict__ cand_off, const int* __restrict__ cand_j, const unsigned char* __restrict__ cand_flag,
+               int n, int* __restrict__ kept_rank, int* __restrict__ nb_start, int* __restrict__ nb_list, int nb_cap,
+               Counters* ctr) {
+  extern __shared__ unsigned bitmap[];
+  __shared__ int s_cur, s_nb;
+  const int t = threadIdx.x;
+  const int nwords = (n + 31) >> 5;
+  if (ctr->cand_overflow) return;
+  for (int w = t; w < nwords; w += blockDim.x) bitmap[w] = 0u;
+  if (t == 0) { s_cur = 0; s_nb = 0; }
+  int K = 0;
+  __syncthreads();
+  while (true) {
+    const int ri = s_cur;
+    if (ri < 0 || ri >= n) break;
+    const int nb0 = s_nb;
+    if (t == 0) {
+      kept_rank[K] = ri;
+      nb_start[K] = nb0 < nb_cap ? nb0 : nb_cap;
+    }
+    const int c0 = cand_off[ri], c1 = cand_off[ri + 1];
+    __syncthreads();   // everyone has read s_cur / s_nb
+    for (int k = c0 + t; k < c1; k += blockDim.x) {
+      const unsigned f = cand_flag[k];
+      if (f == 0u) continue;
+      const int rb = cand_j[k];
+      // state of j when the reference reaches box i: bits set by EARLIER kept boxes (a candidate occurs once per box, so
+      // the bits set in this sweep belong to other candidates and are never read here)
+      if ((bitmap[rb >> 5] >> (rb & 31)) & 1u) continue;                 // suppressed before: skipped (nms.h:503)
+      if (f & 1u) atomicOr(&bitmap[rb >> 5], 1u << (rb & 31));           // nms.h:511
+      if (f & 2u) {                                                      // nms.h:513
+        const int pos = atomicAdd(&s_nb, 1);
+        if (pos < nb_cap) nb_list[pos] = rb;
+        else ctr->nb_overflow = 1;
+      }
+    }
+    __syncthreads();
+    ++K;
+    if (t < 32) {   // next unsuppressed rank > ri
+      int found = -1;
+      const int w0 = (ri + 1) >> 5;
+      const unsigned first_mask = ~0u << ((ri + 1) & 31);
+      for (int wb = w0; wb < nwords && found < 0; wb += 32) {
+        const int w = wb + t;
+        unsigned free_bits = 0u;
+        if (w < nwords) {
+          free_bits = ~bitmap[w];
+          if (w == w0) free_bits &= first_mask;
+          if (w == nwords - 1 && (n & 31)) free_bits &= (1u << (n & 31)) - 1u;
+        }
+        if (ri + 1 >= n) free_bits = 0u;
+        const unsigned ball = __ballot_sync(0xffffffffu, free_bits != 0u);
+        if (ball) {
+          const int src = __ffs(ball) - 1;
+          const unsigned fb = __shfl_sync(0xffffffffu, free_bits, src);
+          found = ((wb + src) << 5) + (__ffs(fb) - 1);
+        }
+      }
+      if (t == 0) s_cur = found;
+    }
+    __syncthreads();
+  }
+  if (t == 0) {
+    nb_start[K] = s_nb < nb_cap ? s_nb : nb_cap;
+    ctr->kept = K;
+    ctr->nb_total = s_nb;
+  }
+}
 
 struct GreedySmem {
   int seg_start[NSEG];     // first entry of each segment (cell-sorted resp. theta-sorted array)
@@ -808,15 +1001,53 @@ int rd_wnms_4c(const float* dets, int n, float thresh, float thresh_vote, int is
   cell_gather_kernel<<<nb, TB, 0, st>>>(cell_rank, aabb, hashr, n, aabb_c, hash_c);
   theta_range_kernel<<<nb, TB, 0, st>>>(theta, theta_s, n, th_range);
   rd::count_launch(3);
-  RD_CUDA(rd::smem_optin(greedy_kernel, bitmap_bytes));
-  greedy_kernel<<<1, NT, bitmap_bytes, st>>>(bx, aabb, hashr, cell_rank, cell_start, cell_end, aabb_c, hash_c, th_range,
-                                             theta_rank, gp, n, thresh,
-                                             thresh_vote, is_3d, kept_rank, nb_start, nb_list, (int)L.nb_cap, ctr);
-  rd::count_launch();
-  if (rd::check_launch("rd_wnms_4c(greedy)")) return 1;
+  // Parallel path (default for n >= 2048): adjacency of all boxes in parallel, then the light sequential walk.
+  // RD_WNMS_PARALLEL=0 forces the single-CTA scan; it is also the fallback when the candidate lists overflow.
+  static const int par_env = [] { const char* e = getenv("RD_WNMS_PARALLEL"); return e ? atoi(e) : -1; }();
+  bool parallel = par_env < 0 ? n >= 2048 : par_env != 0;
+  int* cand_cnt = (int*)(ws + L.cand_cnt);
+  int* cand_off = (int*)(ws + L.cand_off);
+  int* cand_j = (int*)(ws + L.cand_j);
+  unsigned char* cand_flag = (unsigned char*)(ws + L.cand_flag);
+  auto run_greedy = [&]() -> int {
+    RD_CUDA(rd::smem_optin(greedy_kernel, bitmap_bytes));
+    greedy_kernel<<<1, NT, bitmap_bytes, st>>>(bx, aabb, hashr, cell_rank, cell_start, cell_end, aabb_c, hash_c, th_range,
+                                               theta_rank, gp, n, thresh, thresh_vote, is_3d, kept_rank, nb_start, nb_list,
+                                               (int)L.nb_cap, ctr);
+    rd::count_launch();
+    return rd::check_launch("rd_wnms_4c(greedy)");
+  };
+  if (parallel) {
+    const int nbw = (n + CAND_WARPS - 1) / CAND_WARPS;
+    cand_kernel<false><<<nbw, CAND_WARPS * 32, 0, st>>>(bx, aabb, hashr, cell_rank, cell_start, cell_end, aabb_c, hash_c, th_range,
+                                                        theta_rank, gp, n, thresh, thresh_vote, is_3d, cand_cnt, cand_off, cand_j,
+                                                        cand_flag, (int)L.cand_cap, ctr);
+    RD_CUDA(cudaMemsetAsync(cand_cnt + n, 0, 4, st));
+    {
+      size_t need = 0;
+      RD_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, need, cand_cnt, cand_off, n + 1, st));
+      RD_REQUIRE(need <= L.cub_bytes, "rd_wnms_4c: CUB temp storage %zu exceeds reserved %zu", need, L.cub_bytes);
+      size_t tb = L.cub_bytes;
+      RD_CUDA(cub::DeviceScan::ExclusiveSum(cub_temp, tb, cand_cnt, cand_off, n + 1, st));
+    }
+    cand_kernel<true><<<nbw, CAND_WARPS * 32, 0, st>>>(bx, aabb, hashr, cell_rank, cell_start, cell_end, aabb_c, hash_c, th_range,
+                                                       theta_rank, gp, n, thresh, thresh_vote, is_3d, cand_cnt, cand_off, cand_j,
+                                                       cand_flag, (int)L.cand_cap, ctr);
+    RD_CUDA(rd::smem_optin(resolve_kernel, bitmap_bytes));
+    resolve_kernel<<<1, 512, bitmap_bytes, st>>>(cand_off, cand_j, cand_flag, n, kept_rank, nb_start, nb_list, (int)L.nb_cap, ctr);
+    rd::count_launch(5);
+    if (rd::check_launch("rd_wnms_4c(parallel)")) return 1;
+  } else {
+    if (run_greedy()) return 1;
+  }
   Counters h;
   RD_CUDA(cudaMemcpyAsync(&h, ctr, sizeof(Counters), cudaMemcpyDeviceToHost, st));
   RD_CUDA(cudaStreamSynchronize(st));
+  if (parallel && h.cand_overflow) {   // more than 64 candidate pairs per box on average: the sequential scan needs no lists
+    if (run_greedy()) return 1;
+    RD_CUDA(cudaMemcpyAsync(&h, ctr, sizeof(Counters), cudaMemcpyDeviceToHost, st));
+    RD_CUDA(cudaStreamSynchronize(st));
+  }
   RD_REQUIRE(!h.nb_overflow, "rd_wnms_4c: neighbour list overflow (thresh > thresh_vote with very dense boxes)");
   if (h.kept > 0) {
     merge_kernel<<<(h.kept + 127) / 128, 128, 0, st>>>(bx, order, kept_rank, nb_start, nb_list, ctr, out_dets, keep_inds);
