@@ -307,8 +307,9 @@ __host__ inline Layout make_layout(int n) {
   L.theta = take(N * 4); L.theta_s = take(N * 4); L.theta_rank = take(N * 4);
   L.aabb_c = take(N * 16); L.hash_c = take(N * 8);   // AABB / hash range in CELL order (aligned with cell_rank)
   L.th_range = take(N * 6 * 4);                      // per box: [first, last) of its three theta segments
-  // parallel path: candidate pairs (i, j > i) of ALL boxes, 64 per box on average; beyond that the sequential scan runs
-  L.cand_cap = N * 64 + 65536;
+  // parallel path: candidate pairs (i, j > i) of ALL boxes, 320 per box on average (cfg-3: 100 k boxes on 150 m x 150 m
+  // have ~220 later boxes with overlapping AABBs each); beyond that the sequential scan runs.  5 bytes per pair.
+  L.cand_cap = N * 320 + 65536;
   L.cand_cnt = take((N + 1) * 4); L.cand_off = take((N + 1) * 4);
   L.cand_j = take(L.cand_cap * 4); L.cand_flag = take(L.cand_cap);
   L.cub_bytes = (size_t)(16u << 20) + N * 32;
@@ -1043,7 +1044,7 @@ int rd_wnms_4c(const float* dets, int n, float thresh, float thresh_vote, int is
   Counters h;
   RD_CUDA(cudaMemcpyAsync(&h, ctr, sizeof(Counters), cudaMemcpyDeviceToHost, st));
   RD_CUDA(cudaStreamSynchronize(st));
-  if (parallel && h.cand_overflow) {   // more than 64 candidate pairs per box on average: the sequential scan needs no lists
+  if (parallel && h.cand_overflow) {   // more than 320 candidate pairs per box on average: the sequential scan needs no lists
     if (run_greedy()) return 1;
     RD_CUDA(cudaMemcpyAsync(&h, ctr, sizeof(Counters), cudaMemcpyDeviceToHost, st));
     RD_CUDA(cudaStreamSynchronize(st));

@@ -175,19 +175,19 @@ def test_wnms_vs_oracle_large(ops, orc):
 
 def test_wnms_parallel_path_3d_thresholds_and_overflow_fallback(ops, orc):
     """n >= 2048 takes the parallel path (adjacency of all boxes, then the light sequential walk); a cloud so dense that it
-    overflows the candidate reservation (64 pairs per box on average) must fall back to the sequential scan; both bit-exact,
+    overflows the candidate reservation (320 pairs per box on average) must fall back to the sequential scan; both bit-exact,
     also with the 3-D overlap, other thresholds and hash scales."""
     dets = synth.wnms_dets(6000, seed=21, clustered=True)
     for th, tv, is3d, hs in [(0.1, 0.5, True, 100), (0.3, 0.7, False, 100), (0.05, 0.2, False, 13)]:
         wo, wk = orc.wnms_4c(dets, th, tv, is3d, hs)
         go, gk = ops.wnms_4c_device(cu(dets), th, tv, is3d, hs)
         assert np.array_equal(gk.cpu().numpy(), wk) and np.array_equal(go.cpu().numpy(), wo, equal_nan=True), (th, tv, is3d, hs)
-    # dense: 3000 boxes around 12 centres -> ~250 mutually near boxes each, far more than 64 candidates per box
+    # dense: 4000 boxes around 3 centres -> ~1300 mutually near boxes each, far more than 320 candidates per box
     rng = np.random.default_rng(5)
-    b7 = synth.boxes7(3000, seed=6, clustered=False)
-    centres = rng.uniform(-40, 40, (12, 2)).astype(np.float32)
-    b7[:, :2] = centres[rng.integers(0, 12, 3000)] + rng.normal(0, 0.8, (3000, 2)).astype(np.float32)
-    dense = synth.corners10_to_dets12(synth.boxes7_to_corners10(b7).astype(np.float32), synth.distinct_scores(3000, seed=7))
+    b7 = synth.boxes7(4000, seed=6, clustered=False)
+    centres = rng.uniform(-40, 40, (3, 2)).astype(np.float32)
+    b7[:, :2] = centres[rng.integers(0, 3, 4000)] + rng.normal(0, 0.8, (4000, 2)).astype(np.float32)
+    dense = synth.corners10_to_dets12(synth.boxes7_to_corners10(b7).astype(np.float32), synth.distinct_scores(4000, seed=7))
     wo, wk = orc.wnms_4c(dense, 0.1, 0.5, False, 100)
     go, gk = ops.wnms_4c_device(cu(dense), 0.1, 0.5, False, 100)
     assert np.array_equal(gk.cpu().numpy(), wk) and np.array_equal(go.cpu().numpy(), wo, equal_nan=True)
