@@ -107,6 +107,7 @@ struct SRing {
   const act_t* src[3];
   int nt;
   int my_units;
+  int rev;   // 1: walk the units from the far end of the tensor (see stream_rev())
 
   __device__ __forceinline__ void init(unsigned char* dsm, uint64_t* bars, const SGeo& G) {
     buf = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(dsm) + 127) & ~(uintptr_t)127);
@@ -122,8 +123,12 @@ struct SRing {
     if (threadIdx.x == 0)
       for (int k = 0; k < STAGES && k < my_units; ++k) issue(G, k);
   }
+  __device__ __forceinline__ int unit_of(const SGeo& G, int k) const {
+    const int u = (int)blockIdx.x + k * (int)gridDim.x;
+    return rev ? G.nunits - 1 - u : u;
+  }
   __device__ __forceinline__ void issue(const SGeo& G, int k) {
-    const SUnit U = s_unit(G, (int)blockIdx.x + k * (int)gridDim.x);
+    const SUnit U = s_unit(G, unit_of(G, k));
     const int stage = k % STAGES;
     const uint32_t bytes = (uint32_t)U.npx * G.C * 2;
     s_mbar_expect_tx(&full[stage], bytes * nt);
@@ -164,12 +169,13 @@ __device__ __forceinline__ void s_block_reduce_store(const float (&s)[8], const 
 
 // ---- forward statistics ------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(SNT, 1) s_stats_kernel(const act_t* __restrict__ z, SGeo G,
-                                                         float* __restrict__ partial) {
+                                                         float* __restrict__ partial, int rev) {
   extern __shared__ unsigned char dsm[];
   __shared__ uint64_t bars[STAGES];
   SRing R;
   R.src[0] = z; R.src[1] = nullptr; R.src[2] = nullptr;
   R.nt = 1;
+  R.rev = rev;
   R.init(dsm, bars, G);
   const int t = threadIdx.x, cg = t % G.cgs, pl = t / G.cgs;
   const bool act = pl < G.ppb;
@@ -177,7 +183,7 @@ __global__ void __launch_bounds__(SNT, 1) s_stats_kernel(const act_t* __restrict
 #pragma unroll
   for (int i = 0; i < 8; ++i) s[i] = q[i] = 0.f;
   for (int k = 0; k < R.my_units; ++k) {
-    const SUnit U = s_unit(G, (int)blockIdx.x + k * (int)gridDim.x);
+    const SUnit U = s_unit(G, R.unit_of(G, k));
     R.acquire(k);
     const uint4* sz = R.wait(G, k, 0);
     if (act) {
@@ -199,7 +205,7 @@ __global__ void __launch_bounds__(SNT, 1) s_fwd_apply_kernel(const act_t* __rest
                                                              const float* __restrict__ coef,
                                                              const act_t* __restrict__ rb,
                                                              const act_t* __restrict__ ra,
-                                                             act_t* __restrict__ y, SGeo G, int relu) {
+                                                             act_t* __restrict__ y, SGeo G, int relu, int rev) {
   extern __shared__ unsigned char dsm[];
   __shared__ uint64_t bars[STAGES];
   SRing R;
@@ -211,6 +217,7 @@ __global__ void __launch_bounds__(SNT, 1) s_fwd_apply_kernel(const act_t* __rest
   const int i_ra = ra ? nt : -1;
   if (ra) R.src[nt++] = ra;
   R.nt = nt;
+  R.rev = rev;
   R.init(dsm, bars, G);
   const int t = threadIdx.x, cg = t % G.cgs, pl = t / G.cgs;
   const bool act = pl < G.ppb;
@@ -218,7 +225,7 @@ __global__ void __launch_bounds__(SNT, 1) s_fwd_apply_kernel(const act_t* __rest
 #pragma unroll
   for (int i = 0; i < 8; ++i) { a[i] = coef[cg * 8 + i]; b[i] = coef[G.C + cg * 8 + i]; }
   for (int k = 0; k < R.my_units; ++k) {
-    const SUnit U = s_unit(G, (int)blockIdx.x + k * (int)gridDim.x);
+    const SUnit U = s_unit(G, R.unit_of(G, k));
     R.acquire(k);
     const uint4* sz = R.wait(G, k, 0);
     const uint4* srb = i_rb >= 0 ? R.wait(G, k, i_rb) : nullptr;
@@ -257,12 +264,13 @@ __global__ void __launch_bounds__(SNT, 1) s_bwd_reduce_kernel(const act_t* __res
                                                               const act_t* __restrict__ ym,
                                                               const act_t* __restrict__ z,
                                                               const float* __restrict__ coef, SGeo G, int mask_mode,
-                                                              float* __restrict__ partial) {
+                                                              float* __restrict__ partial, int rev) {
   extern __shared__ unsigned char dsm[];
   __shared__ uint64_t bars[STAGES];
   SRing R;
   R.src[0] = dy; R.src[1] = z; R.src[2] = mask_mode == 1 ? ym : nullptr;
   R.nt = mask_mode == 1 ? 3 : 2;
+  R.rev = rev;
   R.init(dsm, bars, G);
   const int t = threadIdx.x, cg = t % G.cgs, pl = t / G.cgs;
   const bool act = pl < G.ppb;
@@ -275,7 +283,7 @@ __global__ void __launch_bounds__(SNT, 1) s_bwd_reduce_kernel(const act_t* __res
     s[i] = q[i] = 0.f;
   }
   for (int k = 0; k < R.my_units; ++k) {
-    const SUnit U = s_unit(G, (int)blockIdx.x + k * (int)gridDim.x);
+    const SUnit U = s_unit(G, R.unit_of(G, k));
     R.acquire(k);
     const uint4* sd = R.wait(G, k, 0);
     const uint4* sz = R.wait(G, k, 1);
@@ -304,12 +312,13 @@ __global__ void __launch_bounds__(SNT, 1) s_bwd_apply_kernel(const act_t* __rest
                                                              const float* __restrict__ coef,
                                                              const float* __restrict__ coef2, SGeo G, int mask_mode,
                                                              act_t* __restrict__ dz, int dz_halo,
-                                                             act_t* __restrict__ g_out) {
+                                                             act_t* __restrict__ g_out, int rev) {
   extern __shared__ unsigned char dsm[];
   __shared__ uint64_t bars[STAGES];
   SRing R;
   R.src[0] = dy; R.src[1] = z; R.src[2] = mask_mode == 1 ? ym : nullptr;
   R.nt = mask_mode == 1 ? 3 : 2;
+  R.rev = rev;
   R.init(dsm, bars, G);
   const int t = threadIdx.x, cg = t % G.cgs, pl = t / G.cgs;
   const bool act = pl < G.ppb;
@@ -323,7 +332,7 @@ __global__ void __launch_bounds__(SNT, 1) s_bwd_apply_kernel(const act_t* __rest
     c2[i] = coef2[G.C + cg * 8 + i];
   }
   for (int k = 0; k < R.my_units; ++k) {
-    const SUnit U = s_unit(G, (int)blockIdx.x + k * (int)gridDim.x);
+    const SUnit U = s_unit(G, R.unit_of(G, k));
     R.acquire(k);
     const uint4* sd = R.wait(G, k, 0);
     const uint4* sz = R.wait(G, k, 1);
@@ -354,6 +363,20 @@ static bool stream_enabled() {
     v = (e && e[0] == '0') ? 0 : 1;
   }
   return v == 1;
+}
+
+// Walk order of the units.  A tensor of the training step is 45-90 MB and the L2 holds 126 MB: a pass that starts where
+// its producer (or the previous pass over the same tensors) stopped finds the most recently touched part still in L2,
+// a pass that starts at the same end finds it evicted.  The convolutions write ascending; the forward apply and the
+// backward reduce walk descending, the backward apply ascending again.  RD_BN_REV=<bitmask> overrides
+// (1 stats, 2 fwd apply, 4 bwd reduce, 8 bwd apply).
+static int stream_rev(int which) {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("RD_BN_REV");
+    v = e ? atoi(e) : 6;
+  }
+  return (v >> which) & 1;
 }
 
 template <typename K>

@@ -470,7 +470,7 @@ int RD_ACT_FN(rd_bn_train_stats_nhwc_, )(const void* z_pad, int N, int H, int W,
     if (bn::stream_prepare(bn::s_stats_kernel, smem)) return 1;
     grid = bn::stream_grid(sg);
     RD_CUDA(rd::launch(bn::s_stats_kernel, dim3(grid), dim3(bn::SNT), smem, s, static_cast<const act_t*>(z_pad), sg,
-                       static_cast<float*>(workspace)));
+                       static_cast<float*>(workspace), bn::stream_rev(0)));
   } else {
     bn::stats_kernel<<<grid, g.ppb * g.cgs, 0, s>>>(static_cast<const act_t*>(z_pad), g, 1,
                                                      static_cast<float*>(workspace));
@@ -513,7 +513,8 @@ int RD_ACT_FN(rd_bn_act_fwd_nhwc_, )(const void* z_pad, const float* coef, const
     if (bn::stream_prepare(bn::s_fwd_apply_kernel, smem)) return 1;
     RD_CUDA(rd::launch(bn::s_fwd_apply_kernel, dim3(bn::stream_grid(sg)), dim3(bn::SNT), smem, rd::as_stream(stream),
                        static_cast<const act_t*>(z_pad), coef, static_cast<const act_t*>(res_before),
-                       static_cast<const act_t*>(res_after), static_cast<act_t*>(y_pad), sg, relu ? 1 : 0));
+                       static_cast<const act_t*>(res_after), static_cast<act_t*>(y_pad), sg, relu ? 1 : 0,
+                       bn::stream_rev(1)));
   } else {
     bn::fwd_apply_kernel<<<grid, g.ppb * g.cgs, 0, rd::as_stream(stream)>>>(
         static_cast<const act_t*>(z_pad), coef, static_cast<const act_t*>(res_before),
@@ -549,11 +550,12 @@ int RD_ACT_FN(rd_bn_act_bwd_nhwc_, )(const void* dy_pad, const void* y_mask_pad,
     const size_t smem = bn::sgeo_smem(sg, nt);
     if (bn::stream_prepare(bn::s_bwd_reduce_kernel, smem) || bn::stream_prepare(bn::s_bwd_apply_kernel, smem)) return 1;
     const int sgrid = bn::stream_grid(sg);
-    RD_CUDA(rd::launch(bn::s_bwd_reduce_kernel, dim3(sgrid), dim3(bn::SNT), smem, s, dy, ym, z, coef, sg, mask_mode, partial));
+    RD_CUDA(rd::launch(bn::s_bwd_reduce_kernel, dim3(sgrid), dim3(bn::SNT), smem, s, dy, ym, z, coef, sg, mask_mode, partial,
+                       bn::stream_rev(2)));
     RD_CUDA_LAUNCH_FINALIZE(bn::bwd_finalize_kernel, s, partial, sgrid, C, (double)N * H * W, coef, coef2, dgamma,
                                                             dbeta);
     RD_CUDA(rd::launch(bn::s_bwd_apply_kernel, dim3(sgrid), dim3(bn::SNT), smem, s, dy, ym, z, coef, (const float*)coef2, sg,
-                       mask_mode, static_cast<act_t*>(dz_pad), dz_halo_w, static_cast<act_t*>(g_out_pad)));
+                       mask_mode, static_cast<act_t*>(dz_pad), dz_halo_w, static_cast<act_t*>(g_out_pad), bn::stream_rev(3)));
   } else {
     bn::bwd_reduce_kernel<<<grid, g.ppb * g.cgs, 0, s>>>(dy, ym, z, coef, g, mask_mode, partial);
     RD_CUDA_LAUNCH_FINALIZE(bn::bwd_finalize_kernel, s, partial, grid, C, (double)N * H * W, coef, coef2, dgamma,
