@@ -302,6 +302,12 @@ int rd_nchw_f32_to_nhwc_bf16(const float* src, void* dst_pad, int N, int H, int 
  *   (0 for *_bias / *_beta like Optimizer.set_wd_mult). */
 int rd_gather_f32_to_bf16(const float* src, const int* idx, void* dst, int64_t n, rd_stream_t stream);
 int rd_gather_f32(const float* src, const int* idx, float* dst, int64_t n, rd_stream_t stream);
+/* Channel-slice copy between two pixel-major tensors of 2-byte elements (either storage type): for each of npix pixels
+ * dst[p][dst_off + c] = src[p][src_off + c], c < nchan; counts and offsets multiples of 8.  This is the
+ * mx.sym.concat(data, agg3) feeding the level-0 head towers (rangedet/symbol/head/builder.py:198-266 via
+ * dla_backbone.py:150-161), written straight into the 128-channel operand buffer. */
+int rd_copy_channels_16b(const void* src, int src_ctotal, int src_off, void* dst, int dst_ctotal, int dst_off, int nchan,
+                         int64_t npix, rd_stream_t stream);
 int rd_sgd_mom_update(float* weight, const float* grad, float* mom, const float* wd, const float* hyper,
                       int64_t n, rd_stream_t stream);
 

@@ -63,6 +63,7 @@ SIGNATURES = {
     "rd_nchw_f32_to_nhwc_bf16": (_i, [_vp, _vp] + [_i] * 6 + [_vp]),
     "rd_gather_f32_to_bf16": (_i, [_vp, _vp, _vp, _i64, _vp]),
     "rd_gather_f32": (_i, [_vp, _vp, _vp, _i64, _vp]),
+    "rd_copy_channels_16b": (_i, [_vp, _i, _i, _vp, _i, _i, _i, _i64, _vp]),
     "rd_sgd_mom_update": (_i, [_vp] * 5 + [_i64, _vp]),
     # fp16-storage twins of every *bf16* entry point (same arguments)
     "rd_meta_kernel_fwd_nhwc_f16": (_i, [_vp] * 8 + [_i, _vp] + [_i] * 4 + [_vp]),

@@ -139,4 +139,39 @@ int RD_ACT_FN(rd_nchw_f32_to_nhwc_, )(const float* src, void* dst_pad, int N, in
   return rd::check_launch(RD_ACT_FN_STR(rd_nchw_f32_to_nhwc_, ) "");
 }
 
+#ifndef RD_ACT_F16
+// dst[p][dst_off + c] = src[p][src_off + c], c < nchan, for every pixel p of two pixel-major tensors: 16-byte chunks,
+// a warp covers consecutive chunks of consecutive pixels (channel concatenation without a strided framework copy)
+namespace lay_any {
+__global__ void __launch_bounds__(256) copy_channels_kernel(const uint4* __restrict__ src, uint4* __restrict__ dst,
+                                                            int64_t npix, int src_q, int src_off_q, int dst_q,
+                                                            int dst_off_q, int nq) {
+  const int64_t total = npix * nq;
+  for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < total; i += (int64_t)gridDim.x * 256) {
+    const int64_t p = i / nq;
+    const int q = (int)(i - p * nq);
+    dst[p * dst_q + dst_off_q + q] = __ldg(src + p * src_q + src_off_q + q);
+  }
+}
+}  // namespace lay_any
+
+int rd_copy_channels_16b(const void* src, int src_ctotal, int src_off, void* dst, int dst_ctotal, int dst_off, int nchan,
+                         int64_t npix, rd_stream_t stream) {
+  RD_REQUIRE(src && dst, "rd_copy_channels_16b: null pointer");
+  RD_REQUIRE(npix > 0 && nchan > 0 && nchan % 8 == 0 && src_ctotal % 8 == 0 && dst_ctotal % 8 == 0 && src_off % 8 == 0 &&
+                 dst_off % 8 == 0 && src_off >= 0 && dst_off >= 0 && src_off + nchan <= src_ctotal &&
+                 dst_off + nchan <= dst_ctotal,
+             "rd_copy_channels_16b: channel counts and offsets must be multiples of 8 (2-byte elements) and in range");
+  if (rd_check_device()) return 1;
+  const int64_t total = npix * (nchan / 8);
+  const int64_t want = (total + 255) / 256;
+  const int grid = (int)(want < 148 * 16 ? want : 148 * 16);
+  lay_any::copy_channels_kernel<<<grid, 256, 0, rd::as_stream(stream)>>>(
+      static_cast<const uint4*>(src), static_cast<uint4*>(dst), npix, src_ctotal / 8, src_off / 8, dst_ctotal / 8,
+      dst_off / 8, nchan / 8);
+  rd::count_launch();
+  return rd::check_launch("rd_copy_channels_16b");
+}
+#endif
+
 }  // extern "C"

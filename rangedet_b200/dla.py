@@ -148,8 +148,8 @@ class DLABackbone(object):
         agg3 = self.agg_stage("agg3", agg1, agg2a)
         c = data.shape[1]
         cat = self.pool.get("data_concat", agg3.shape[:3] + (128,), agg3.device)  # concat(data, agg3): 72 of 128 ch
-        cat[..., :c] = x[..., :c]
-        cat[..., c:c + 64] = agg3
+        ops.copy_channels(x, 0, cat, 0, c)
+        ops.copy_channels(agg3, 0, cat, c, 64)
         return [cat, agg2a, agg2]
 
 

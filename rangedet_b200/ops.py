@@ -774,6 +774,21 @@ def add_nhwc(x0_pad, x1_pad, out=None):
     return out
 
 
+def copy_channels(src_pad, src_off, dst_pad, dst_off, nchan):
+    """dst_pad[..., dst_off:dst_off+nchan] = src_pad[..., src_off:src_off+nchan] (haloed NHWC, same N/H/W, halo included):
+    channel concatenation into an operand buffer.  Offsets and counts multiples of 8."""
+    _chk_nhwc(src_pad, "src_pad")
+    _chk_nhwc(dst_pad, "dst_pad", src_pad)
+    if src_pad.shape[:3] != dst_pad.shape[:3]:
+        raise ValueError("copy_channels: pixel grids differ")
+    npix = src_pad.shape[0] * src_pad.shape[1] * src_pad.shape[2]
+    with torch.cuda.device(src_pad.device):
+        st = _lib.lib().rd_copy_channels_16b(_p(src_pad), src_pad.shape[3], src_off, _p(dst_pad), dst_pad.shape[3], dst_off,
+                                             nchan, npix, _stream())
+    _lib.check(st, "copy_channels")
+    return dst_pad
+
+
 def nhwc_to_nchw(src_pad, channels=None, tap_major=False, out=None):
     """haloed NHWC bf16 -> (N,C,H,W) fp32 (first `channels` channels); tap_major: NHWC k*(C/9)+c -> NCHW c*9+k."""
     _chk_nhwc(src_pad, "src_pad")

@@ -48,6 +48,9 @@ def pack_operand(w, kind, ci_p, co_p, S=1, dtype=torch.bfloat16):
         return ops.pack_conv_weight(ops.tap_major_weight(w, w.shape[1] // 9), ci_p, co_p, dtype)
     if kind == "dgrad":        # stride 1: flipped taps, transposed channels: [tap][ci][co]
         return ops.pack_conv_weight(w.flip(2, 3).transpose(0, 1), co_p, ci_p, dtype)
+    if kind.startswith("dgrad@"):   # "dgrad@lo:hi": data gradient of input channels [lo, hi) only
+        lo, hi = (int(v) for v in kind[6:].split(":"))
+        return ops.pack_conv_weight(w[:, lo:hi].flip(2, 3).transpose(0, 1), co_p, ci_p, dtype)
     if kind == "dgrad_tapmajor":
         return ops.pack_conv_weight(ops.tap_major_weight(w, w.shape[1] // 9).transpose(0, 1), co_p, ci_p, dtype)
     if kind == "dgrad_s2":     # W-stride 2: transposed conv (3,3)/(1,2), taps not flipped; 1x1 -> centre tap
@@ -320,7 +323,9 @@ class TrainGraph(object):
             self.pgrads[name] = None
 
     # ---- layers -----------------------------------------------------------------------------------------
-    def conv_bn(self, x, wname, bnname, stride_w=1, relu=True, res_before=None, kinds=("fwd", "dgrad")):
+    def conv_bn(self, x, wname, bnname, stride_w=1, relu=True, res_before=None, kinds=("fwd", "dgrad"), dx_channels=None):
+        """dx_channels = (lo, hi, t): x is a channel concatenation whose channels [lo, hi) are the tensor t and whose other
+        channels need no gradient -- the backward computes the data gradient of that slice only, straight into grad(t)."""
         P = self.P
         w = P[wname + "_weight"]
         co, ci, k = w.shape[0], w.shape[1], w.shape[2]
@@ -360,6 +365,12 @@ class TrainGraph(object):
                 self._pg(wname + "_weight", G, lambda t: t[0, :co, :ci].reshape(co, 9, C).transpose(1, 2).reshape(co, ci, 1, 1))
             else:
                 self._pg(wname + "_weight", G, lambda t: t[:, :co, :ci].reshape(k, k, co, ci).permute(2, 3, 0, 1))
+            if dx_channels is not None:
+                lo, hi, t = dx_channels
+                assert stride_w == 1 and k == 3 and hi - lo == t.shape[3]
+                self.grads[id(t)] = ops.conv2d_nhwc(dz, self._w(wname, "dgrad@%d:%d" % (lo, hi), hi - lo, co_p), relu=False,
+                                                    residual_pad=self.grads.pop(id(t), None), out=self._buf("dx", t.shape))
+                return
             if id(x) in self.nograd:
                 return
             old = self.grads.pop(id(x), None)
@@ -537,24 +548,20 @@ class TrainGraph(object):
         agg2a = self.agg_stage("agg2a", res2a, agg2)
         agg3 = self.agg_stage("agg3", agg1, agg2a)
         cat = self._buf("data_concat", agg3.shape[:3] + (128,))  # concat(data, agg3): 72 of 128 channels
-        cat[..., :c] = x[..., :c]
-        cat[..., c:c + 64] = agg3
-
-        def cat_bwd():
-            dcat = self.grads.pop(id(cat))
-            self._acc(agg3, dcat[..., c:c + 64].contiguous())
-
-        self.tape.append(cat_bwd)
+        ops.copy_channels(x, 0, cat, 0, c)          # c = 8 input channels
+        ops.copy_channels(agg3, 0, cat, c, 64)
         self.head_tape_start = len(self.tape)     # tape entries from here on belong to the RPN head towers
         self.head_bwd = []
         cls_logit, bbox_delta = [], []
         for lvl, f in enumerate([cat, agg2a, agg2]):
             t_c = t_r = f
+            # level 0 reads concat(data, agg3): only the agg3 channels carry a gradient (builder.py:198-266)
+            dxc = (c, c + 64, agg3) if lvl == 0 else None
             for i in range(4):
                 n = "rpn_cls_conv_%d_lvl_%d" % (i, lvl)
-                t_c = self.conv_bn(t_c, n, n + "_bn")
+                t_c = self.conv_bn(t_c, n, n + "_bn", dx_channels=dxc if i == 0 else None)
                 n = "rpn_reg_conv_%d_lvl_%d" % (i, lvl)
-                t_r = self.conv_bn(t_r, n, n + "_bn")
+                t_r = self.conv_bn(t_r, n, n + "_bn", dx_channels=dxc if i == 0 else None)
             o, b = self.head_out(t_c, "rpn_cls_logit_lvl_%d" % lvl, 1)
             cls_logit.append(o)
             self.head_bwd.append(("cls", lvl, b, len(self.tape)))

@@ -176,6 +176,11 @@ def add_nhwc(x0_pad, x1_pad, out=None):
     return _store(torch.zeros_like(x0_pad) if out is None else out, _nchw(x0_pad) + _nchw(x1_pad))
 
 
+def copy_channels(src_pad, src_off, dst_pad, dst_off, nchan):
+    dst_pad[..., dst_off:dst_off + nchan] = src_pad[..., src_off:src_off + nchan]
+    return dst_pad
+
+
 def _tap_major_to_ref(x, C9):
     """NCHW channels k*C+c -> c*9+k."""
     C = C9 // 9

@@ -400,6 +400,26 @@ def test_layout_conversions(ops, C, Cp, tap):
     assert torch.equal(back, x)
 
 
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16])
+def test_copy_channels_is_the_concat(ops, dtype):
+    """concat(data, agg3) into the 128-channel operand buffer of the level-0 head towers: bit copies, nothing else touched."""
+    N, H, W = 2, 5, 83
+    g = torch.Generator(device="cuda").manual_seed(3)
+    x = torch.randn((N, H + 2, W + 2, 64), device="cuda", generator=g).to(dtype)
+    a = torch.randn((N, H + 2, W + 2, 64), device="cuda", generator=g).to(dtype)
+    cat = torch.full((N, H + 2, W + 2, 128), 7.0, device="cuda", dtype=dtype)
+    ops.copy_channels(x, 0, cat, 0, 8)
+    ops.copy_channels(a, 0, cat, 8, 64)
+    assert torch.equal(cat[..., :8], x[..., :8]) and torch.equal(cat[..., 8:72], a)
+    assert bool((cat[..., 72:] == 7.0).all())
+    ops.copy_channels(a, 16, cat, 96, 32)
+    assert torch.equal(cat[..., 96:], a[..., 16:48]) and bool((cat[..., 72:96] == 7.0).all())
+    with pytest.raises(RuntimeError):
+        ops.copy_channels(a, 4, cat, 0, 8)      # offsets must be multiples of 8
+    with pytest.raises(RuntimeError):
+        ops.copy_channels(a, 0, cat, 120, 16)   # out of range
+
+
 # ---------------------------------------------------------------------------------------------
 # fp16 storage (the reference's training type, config:35): the same kernels compiled with the other storage type.
 # Operands rounded to fp16, torch fp32 reference on the same rounded operands; outputs carry one fp16 rounding
