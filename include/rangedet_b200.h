@@ -64,6 +64,21 @@ int rd_meta_kernel_fwd_nhwc_bf16(const float* data, const float* coord, const fl
                                  const float* w1, const float* b1, const float* scale, const float* shift,
                                  int relu, void* y_pad, int B, int C, int H, int W, rd_stream_t stream);
 
+/* Backward of the Meta-Kernel inside the training graph: grad_out arrives as the zero-haloed NHWC tensor
+ * [B][H+2][W+2][9C] with TAP-MAJOR channels (k*C + c) -- the layout rd_meta_kernel_fwd_nhwc_* writes and the BatchNorm
+ * backward (rd_bn_act_bwd_*) returns -- instead of the (B, 9C, H, W) fp32 tensor of the reference op boundary
+ * (rangedet/symbol/backbone/meta_kernel.py:232-239): half the gradient bytes and no layout pass in between.  Same
+ * arithmetic as rd_meta_kernel_bwd on the widened values (bit-identical results).  C == 64, W % 4 == 0.  grad_data may be
+ * NULL (input needs no gradient); the four parameter gradients may be NULL together. */
+int rd_meta_kernel_bwd_nhwc_bf16(const void* grad_out_pad, const float* data, const float* coord, const float* w0,
+                                 const float* b0, const float* w1, const float* b1, float* grad_data, float* grad_w0,
+                                 float* grad_b0, float* grad_w1, float* grad_b1, void* workspace, size_t workspace_bytes,
+                                 int B, int C, int H, int W, rd_stream_t stream);
+int rd_meta_kernel_bwd_nhwc_f16(const void* grad_out_pad, const float* data, const float* coord, const float* w0,
+                                const float* b0, const float* w1, const float* b1, float* grad_data, float* grad_w0,
+                                float* grad_b0, float* grad_w1, float* grad_b1, void* workspace, size_t workspace_bytes,
+                                int B, int C, int H, int W, rd_stream_t stream);
+
 /* The two halves of rd_meta_kernel_bwd, separately callable (grad_req 'null' on either side). */
 int rd_meta_kernel_bwd_data(const float* grad_out, const float* coord, const float* w0,
                             const float* b0, const float* w1, const float* b1, float* grad_data,

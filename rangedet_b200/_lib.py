@@ -29,6 +29,8 @@ SIGNATURES = {
     "rd_meta_kernel_fwd_nhwc_bf16": (_i, [_vp] * 8 + [_i, _vp] + [_i] * 4 + [_vp]),
     "rd_meta_kernel_bwd_workspace_bytes": (_sz, [_i] * 4),
     "rd_meta_kernel_bwd": (_i, [_vp] * 12 + [_vp, _sz] + [_i] * 5 + [_vp]),
+    "rd_meta_kernel_bwd_nhwc_bf16": (_i, [_vp] * 12 + [_vp, _sz] + [_i] * 4 + [_vp]),
+    "rd_meta_kernel_bwd_nhwc_f16": (_i, [_vp] * 12 + [_vp, _sz] + [_i] * 4 + [_vp]),
     "rd_meta_kernel_bwd_data": (_i, [_vp] * 7 + [_i] * 5 + [_vp]),
     "rd_meta_kernel_bwd_params": (_i, [_vp] * 11 + [_vp, _sz] + [_i] * 5 + [_vp]),
     "rd_decode_3d_bbox": (_i, [_vp, _vp, _vp, _i64, _i, _vp]),

@@ -489,7 +489,59 @@ int rd_meta_kernel_bwd_params_ws(const float* grad_out, const float* data, const
                                  const float* b0, const float* w1, float* partial, int* nparts, int B, int C, int H,
                                  int W, cudaStream_t stream);
 
+int rd_meta_kernel_bwd_data_ws_nhwc(const void* grad_out_pad, int gof, const float* coord, const float* w0, const float* b0,
+                                    const float* w1, const float* b1, float* grad_data, int B, int C, int H, int W,
+                                    cudaStream_t stream);
+int rd_meta_kernel_bwd_params_ws_nhwc(const void* grad_out_pad, int gof, const float* data, const float* coord,
+                                      const float* w0, const float* b0, const float* w1, float* partial, int* nparts, int B,
+                                      int C, int H, int W, cudaStream_t stream);
+
+// Backward from the haloed NHWC tap-major gradient (the layout rd_meta_kernel_fwd_nhwc_* writes and the BatchNorm backward
+// of the training graph hands back): both kernels read the 2-byte tensor directly.
+static int meta_bwd_nhwc(const char* who, const void* grad_out_pad, int gof, const float* data, const float* coord,
+                         const float* w0, const float* b0, const float* w1, const float* b1, float* grad_data, float* grad_w0,
+                         float* grad_b0, float* grad_w1, float* grad_b1, void* workspace, size_t workspace_bytes, int B,
+                         int C, int H, int W, rd_stream_t stream) {
+  RD_REQUIRE(B > 0 && H > 0 && W > 0, "%s: bad shape B=%d H=%d W=%d", who, B, H, W);
+  RD_REQUIRE(C == 64 && W % 4 == 0, "%s: needs C == 64 and W %% 4 == 0 (got C=%d W=%d)", who, C, W);
+  RD_REQUIRE(grad_out_pad && data && coord && w0 && b0 && w1 && b1, "%s: null input pointer", who);
+  const bool want_params = grad_w0 || grad_b0 || grad_w1 || grad_b1;
+  RD_REQUIRE(!want_params || (grad_w0 && grad_b0 && grad_w1 && grad_b1), "%s: the four parameter gradients go together", who);
+  RD_REQUIRE(grad_data || want_params, "%s: nothing to compute", who);
+  RD_REQUIRE((reinterpret_cast<uintptr_t>(grad_out_pad) & 15) == 0 && (reinterpret_cast<uintptr_t>(data) & 15) == 0 &&
+                 (reinterpret_cast<uintptr_t>(grad_data) & 15) == 0,
+             "%s: tensors must be 16-byte aligned", who);
+  if (rd_check_device()) return 1;
+  cudaStream_t st = rd::as_stream(stream);
+  if (grad_data && rd_meta_kernel_bwd_data_ws_nhwc(grad_out_pad, gof, coord, w0, b0, w1, b1, grad_data, B, C, H, W, st)) return 1;
+  if (!want_params) return 0;
+  RD_REQUIRE(workspace && workspace_bytes >= rd_meta_kernel_bwd_workspace_bytes(B, C, H, W), "%s: workspace too small (%zu < %zu)",
+             who, workspace_bytes, rd_meta_kernel_bwd_workspace_bytes(B, C, H, W));
+  float* partial = static_cast<float*>(workspace);
+  int nparts = 0;
+  if (rd_meta_kernel_bwd_params_ws_nhwc(grad_out_pad, gof, data, coord, w0, b0, w1, partial, &nparts, B, C, H, W, st)) return 1;
+  const int nout = C * mk::HID + C + mk::HID * 4;
+  mk::meta_bwd_param_reduce_kernel<<<(nout + 255) / 256, 256, 0, st>>>(partial, nparts, C, grad_w0, grad_b0, grad_w1, grad_b1);
+  rd::count_launch();
+  return rd::check_launch(who);
+}
+
 extern "C" {
+
+int rd_meta_kernel_bwd_nhwc_bf16(const void* grad_out_pad, const float* data, const float* coord, const float* w0,
+                                 const float* b0, const float* w1, const float* b1, float* grad_data, float* grad_w0,
+                                 float* grad_b0, float* grad_w1, float* grad_b1, void* workspace, size_t workspace_bytes,
+                                 int B, int C, int H, int W, rd_stream_t stream) {
+  return meta_bwd_nhwc("rd_meta_kernel_bwd_nhwc_bf16", grad_out_pad, 1, data, coord, w0, b0, w1, b1, grad_data, grad_w0, grad_b0,
+                       grad_w1, grad_b1, workspace, workspace_bytes, B, C, H, W, stream);
+}
+int rd_meta_kernel_bwd_nhwc_f16(const void* grad_out_pad, const float* data, const float* coord, const float* w0,
+                                const float* b0, const float* w1, const float* b1, float* grad_data, float* grad_w0,
+                                float* grad_b0, float* grad_w1, float* grad_b1, void* workspace, size_t workspace_bytes,
+                                int B, int C, int H, int W, rd_stream_t stream) {
+  return meta_bwd_nhwc("rd_meta_kernel_bwd_nhwc_f16", grad_out_pad, 2, data, coord, w0, b0, w1, b1, grad_data, grad_w0, grad_b0,
+                       grad_w1, grad_b1, workspace, workspace_bytes, B, C, H, W, stream);
+}
 
 int rd_meta_kernel_fwd(const float* data, const float* coord, const float* w0, const float* b0,
                        const float* w1, const float* b1, float* out, int B, int C, int H, int W,

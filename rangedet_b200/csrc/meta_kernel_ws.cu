@@ -44,6 +44,23 @@ constexpr int NS_D = 3, NS_O = 2, NS_A = 2, NS_T = 4;
 constexpr uint32_t TMEM_COLS = NS_T * C;     // 256
 constexpr int BAR_HID = 1, BAR_EPI = 2;      // named barriers (0 = __syncthreads)
 
+// eight 2-byte floats (FMT 1: bf16, 2: fp16) -> fp32
+template <int FMT>
+__device__ __forceinline__ void unpack8_2b(const uint4& q, float* f) {
+  const uint32_t w[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    if (FMT == 1) {
+      f[2 * i] = __uint_as_float(w[i] << 16);
+      f[2 * i + 1] = __uint_as_float(w[i] & 0xffff0000u);
+    } else {
+      const float2 v = __half22float2(*reinterpret_cast<const __half2*>(&w[i]));
+      f[2 * i] = v.x;
+      f[2 * i + 1] = v.y;
+    }
+  }
+}
+
 struct Smem {
   alignas(1024) float dtile[NS_D][C * DTW];
   alignas(1024) float otile[NS_O][C * TW];
@@ -62,7 +79,12 @@ struct Smem {
 //         (dla_backbone.py:92-94): y = relu(out * scale + shift) written as haloed NHWC bf16 with
 //         TAP-MAJOR channels (k*64 + c) -- the aggregation 1x1 conv's weight is permuted to match --
 //         so each tap is one 64-channel x 128-pixel 128B-swizzled TMA store.
-template <int MODE, bool PROF>
+//
+// GOF (MODE 1 only): storage of grad_out.  0: (B, C*9, H, W) fp32, channel c*9+k -- the reference op boundary
+// (meta_kernel.py:232-239).  1 / 2: haloed NHWC bf16 / fp16 with TAP-MAJOR channels (k*64 + c), which is what the
+// BatchNorm backward of the training graph writes: the tap box is then [136 px][64 ch] x 2 B with the 128-byte swizzle
+// (half the bytes, and eight 16-byte shared loads per tap and thread instead of 64 scalar ones).
+template <int MODE, bool PROF, int GOF = 0>
 __global__ void __launch_bounds__(NTHREADS, 1)
 meta_ws_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant__ CUtensorMap tm_out,
                const float* __restrict__ coord, const float* __restrict__ w0, const float* __restrict__ b0,
@@ -145,8 +167,9 @@ meta_ws_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant_
           pa += tick() - ta;
           const int hh = h + dy;
           if (hh >= 0 && hh < H) {
-            tc::mbar_arrive_expect_tx(&S.d_full[s], IN_BYTES);
+            tc::mbar_arrive_expect_tx(&S.d_full[s], GOF ? IN_BYTES / 2 : IN_BYTES);
             if (MODE != 1) tma::load_3d(S.dtile[s], &tm_in, &S.d_full[s], bs, hh, b * C);
+            else if (GOF) tma::load_4d(S.dtile[s], &tm_in, &S.d_full[s], (8 - u) * C, bs + 1, hh + 1, b);
             else tma::load_4d(S.dtile[s], &tm_in, &S.d_full[s], bs, hh, 8 - u, b * C);
           } else {
             tc::mbar_arrive(&S.d_full[s]);  // row outside the image: nothing to load, consumers use 0
@@ -405,8 +428,22 @@ meta_ws_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant_
 #pragma unroll
           for (int half = 0; half < 2; ++half) {
             float d[32];
+            if (GOF) {   // [px][64 ch] 2-byte elements, 16-byte chunk j of row r stored at chunk j ^ (r & 7)
+              const int r = ok ? col : 0;
+              const unsigned char* rowp = reinterpret_cast<const unsigned char*>(S.dtile[sd]) + r * 128;
 #pragma unroll
-            for (int i = 0; i < 32; ++i) d[i] = ok ? dt[(half * 32 + i) * DTW] : 0.f;
+              for (int j = 0; j < 4; ++j) {
+                const uint4 q = *reinterpret_cast<const uint4*>(rowp + (((half * 4 + j) ^ (r & 7)) << 4));
+                unpack8_2b<GOF>(q, d + j * 8);
+              }
+              if (!ok) {
+#pragma unroll
+                for (int i = 0; i < 32; ++i) d[i] = 0.f;
+              }
+            } else {
+#pragma unroll
+              for (int i = 0; i < 32; ++i) d[i] = ok ? dt[(half * 32 + i) * DTW] : 0.f;
+            }
             float v[32];
             tc::tmem_ld_x32(tmem_base + lane_sel + st * C + half * 32, v);
 #pragma unroll
@@ -453,9 +490,10 @@ meta_ws_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant_
   if (warp == 1) tc::tmem_dealloc(tmem_base, TMEM_COLS);
 }
 
-inline int launch(int mode, const float* tap_src, void* dst, const float* coord, const float* w0, const float* b0,
+inline int launch(int mode, const void* tap_src_v, void* dst, const float* coord, const float* w0, const float* b0,
                   const float* w1, const float* b1, const float* ep_scale, const float* ep_shift, int ep_relu, int B,
-                  int Cc, int H, int W, cudaStream_t stream) {
+                  int Cc, int H, int W, cudaStream_t stream, int gof = 0) {
+  const float* tap_src = static_cast<const float*>(tap_src_v);
   RD_REQUIRE(Cc == C, "Meta-Kernel impl 3 (TMA/tcgen05) is specialised for C == 64 (got %d)", Cc);
   RD_REQUIRE(W % 4 == 0, "Meta-Kernel impl 3 needs W %% 4 == 0 (TMA row stride must be a multiple of 16 B); W=%d", W);
   RD_REQUIRE((reinterpret_cast<uintptr_t>(tap_src) & 15) == 0 && (reinterpret_cast<uintptr_t>(dst) & 15) == 0,
@@ -478,7 +516,17 @@ inline int launch(int mode, const float* tap_src, void* dst, const float* coord,
     if (tma::make_map(&tm_in, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, tap_src, 3, d3, s3, b3in, CU_TENSOR_MAP_SWIZZLE_NONE)) return 1;
     if (tma::make_map(&tm_out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, dst, 4, d4, s4, b4, CU_TENSOR_MAP_SWIZZLE_NONE)) return 1;
   } else if (mode == 1) {
-    if (tma::make_map(&tm_in, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, tap_src, 4, d4, s4, b4in, CU_TENSOR_MAP_SWIZZLE_NONE)) return 1;
+    if (gof) {   // whole haloed NHWC tensor (9C, W+2, H+2, B): pixel (h, w) sits at (w+1, h+1); the halo is zero
+      const uint64_t Wp = (uint64_t)W + 2, Hp = (uint64_t)H + 2, CO = 9u * C;
+      const uint64_t dn[4] = {CO, Wp, Hp, (uint64_t)B};
+      const uint64_t sn[3] = {CO * 2, Wp * CO * 2, Hp * Wp * CO * 2};
+      const uint32_t bn[4] = {(uint32_t)C, (uint32_t)DTW, 1u, 1u};
+      if (tma::make_map(&tm_in, gof == 1 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, tap_src_v, 4, dn,
+                        sn, bn, CU_TENSOR_MAP_SWIZZLE_128B))
+        return 1;
+    } else if (tma::make_map(&tm_in, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, tap_src, 4, d4, s4, b4in, CU_TENSOR_MAP_SWIZZLE_NONE)) {
+      return 1;
+    }
     if (tma::make_map(&tm_out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, dst, 3, d3, s3, b3, CU_TENSOR_MAP_SWIZZLE_NONE)) return 1;
   } else {
     if (tma::make_map(&tm_in, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, tap_src, 3, d3, s3, b3in, CU_TENSOR_MAP_SWIZZLE_NONE)) return 1;
@@ -508,6 +556,8 @@ inline int launch(int mode, const float* tap_src, void* dst, const float* coord,
   RD_CUDA(rd::smem_optin(meta_ws_kernel<2, false>, smem));
   RD_CUDA(rd::smem_optin(meta_ws_kernel<0, true>, smem));
   RD_CUDA(rd::smem_optin(meta_ws_kernel<1, true>, smem));
+  RD_CUDA(rd::smem_optin(meta_ws_kernel<1, false, 1>, smem));
+  RD_CUDA(rd::smem_optin(meta_ws_kernel<1, false, 2>, smem));
 #define RD_MKWS_LAUNCH(M, PR, SC, SH, RELU)                                                                              \
   meta_ws_kernel<M, PR><<<(unsigned)grid, NTHREADS, smem, stream>>>(tm_in, tm_out, coord, w0, b0, w1, b1, SC, SH, RELU, B, H, \
                                                                     W, tiles_w, (int)ntiles, d_prof)
@@ -516,13 +566,20 @@ inline int launch(int mode, const float* tap_src, void* dst, const float* coord,
     else RD_MKWS_LAUNCH(0, false, nullptr, nullptr, 0);
   } else if (mode == 2) {
     RD_MKWS_LAUNCH(2, false, ep_scale, ep_shift, ep_relu);
+  } else if (gof) {
+    if (gof == 1)
+      meta_ws_kernel<1, false, 1><<<(unsigned)grid, NTHREADS, smem, stream>>>(tm_in, tm_out, coord, w0, b0, w1, b1, nullptr, nullptr,
+                                                                              0, B, H, W, tiles_w, (int)ntiles, d_prof);
+    else
+      meta_ws_kernel<1, false, 2><<<(unsigned)grid, NTHREADS, smem, stream>>>(tm_in, tm_out, coord, w0, b0, w1, b1, nullptr, nullptr,
+                                                                              0, B, H, W, tiles_w, (int)ntiles, d_prof);
   } else {
     if (want_prof) RD_MKWS_LAUNCH(1, true, nullptr, nullptr, 0);
     else RD_MKWS_LAUNCH(1, false, nullptr, nullptr, 0);
   }
 #undef RD_MKWS_LAUNCH
   rd::count_launch();
-  if (want_prof && mode != 2) {  // diagnostic: synchronous, prints mean cycles per tile and role
+  if (want_prof && mode != 2 && !gof) {  // diagnostic: synchronous, prints mean cycles per tile and role
     RD_CUDA(cudaStreamSynchronize(stream));
     static long long hbuf[1024 * 16];
     RD_CUDA(cudaMemcpy(hbuf, d_prof, sizeof(long long) * 16 * grid, cudaMemcpyDeviceToHost));
@@ -550,6 +607,13 @@ int rd_meta_kernel_bwd_data_ws(const float* grad_out, const float* coord, const 
                                const float* w1, const float* b1, float* grad_data, int B, int C, int H, int W,
                                cudaStream_t stream) {
   return mkws::launch(1, grad_out, grad_data, coord, w0, b0, w1, b1, nullptr, nullptr, 0, B, C, H, W, stream);
+}
+
+// grad_data from the haloed NHWC tap-major gradient (gof 1: bf16, 2: fp16)
+int rd_meta_kernel_bwd_data_ws_nhwc(const void* grad_out_pad, int gof, const float* coord, const float* w0, const float* b0,
+                                    const float* w1, const float* b1, float* grad_data, int B, int C, int H, int W,
+                                    cudaStream_t stream) {
+  return mkws::launch(1, grad_out_pad, grad_data, coord, w0, b0, w1, b1, nullptr, nullptr, 0, B, C, H, W, stream, gof);
 }
 
 extern "C" int rd_meta_kernel_fwd_nhwc_bf16(const float* data, const float* coord, const float* w0, const float* b0,

@@ -58,7 +58,26 @@ struct Smem {
 
 // PROF: diagnostic instantiation (RD_MK_PROF=1).  It must be a template parameter: with 576 threads the
 // register cap is 96, and the eight 64-bit cycle counters of a runtime switch spilled (0.57 -> 0.80 ms).
-template <bool PROF>
+// GOF: storage of grad_out -- 0: (B, C*9, H, W) fp32 (reference op boundary); 1 / 2: haloed NHWC bf16 / fp16 with tap-major
+// channels (see meta_kernel_ws.cu): the tap tile is then [128 px][64 ch] x 2 B, 128-byte swizzled, and a builder thread
+// fetches its 16 channels with two 16-byte shared loads.
+template <int FMT>
+__device__ __forceinline__ void unpack8_2b(const uint4& q, float* f) {
+  const uint32_t w[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    if (FMT == 1) {
+      f[2 * i] = __uint_as_float(w[i] << 16);
+      f[2 * i + 1] = __uint_as_float(w[i] & 0xffff0000u);
+    } else {
+      const float2 v = __half22float2(*reinterpret_cast<const __half2*>(&w[i]));
+      f[2 * i] = v.x;
+      f[2 * i + 1] = v.y;
+    }
+  }
+}
+
+template <bool PROF, int GOF = 0>
 __global__ void __launch_bounds__(NTHREADS, 1)
 meta_ws_params_kernel(const __grid_constant__ CUtensorMap tm_go, const __grid_constant__ CUtensorMap tm_data,
                       const float* __restrict__ coord, const float* __restrict__ w0, const float* __restrict__ b0,
@@ -145,8 +164,9 @@ meta_ws_params_kernel(const __grid_constant__ CUtensorMap tm_go, const __grid_co
           const long long tb = tick();
           tc::mbar_wait(&S.go_empty[s], ph ^ 1);
           q0 += tick() - tb;
-          tc::mbar_arrive_expect_tx(&S.go_full[s], GO_BYTES);
-          tma::load_4d(S.go[s], &tm_go, &S.go_full[s], w0px, h, k, b * C);
+          tc::mbar_arrive_expect_tx(&S.go_full[s], GOF ? GO_BYTES / 2 : GO_BYTES);
+          if (GOF) tma::load_4d(S.go[s], &tm_go, &S.go_full[s], k * C, w0px + 1, h + 1, b);
+          else tma::load_4d(S.go[s], &tm_go, &S.go_full[s], w0px, h, k, b * C);
         }
       }
       if (PROF) { prof[blockIdx.x * 16 + 0] = tick() - t_begin; prof[blockIdx.x * 16 + 1] = q0; prof[blockIdx.x * 16 + 2] = q1; }
@@ -325,10 +345,15 @@ meta_ws_params_kernel(const __grid_constant__ CUtensorMap tm_go, const __grid_co
 #pragma unroll
         for (int cq = 0; cq < NCQ; ++cq) {  // 8 channels per 16-byte chunk; this thread: chunks NCQ*hf ..
           float gv[8], dv[8];
+          if (GOF) {
+            const uint4 q = *reinterpret_cast<const uint4*>(reinterpret_cast<const unsigned char*>(S.go[sg]) + px * 128 +
+                                                            (((hf * NCQ + cq) ^ (px & 7)) << 4));
+            unpack8_2b<GOF>(q, gv);
+          }
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
             const int c = (hf * NCQ + cq) * 8 + i;
-            gv[i] = gt[c * TW];
+            if (!GOF) gv[i] = gt[c * TW];
             dv[i] = ok ? dt[c * DTW] : 0.f;
           }
 #pragma unroll
@@ -429,9 +454,25 @@ meta_ws_params_kernel(const __grid_constant__ CUtensorMap tm_go, const __grid_co
 }  // namespace mkwp
 
 // partial must hold gridDim rows of NOUT floats; returns the number of rows written in *nparts
+static int params_launch(const void* grad_out, int gof, const float* data, const float* coord, const float* w0,
+                         const float* b0, const float* w1, float* partial, int* nparts, int B, int C, int H, int W,
+                         cudaStream_t stream);
+
 int rd_meta_kernel_bwd_params_ws(const float* grad_out, const float* data, const float* coord, const float* w0,
                                  const float* b0, const float* w1, float* partial, int* nparts, int B, int C, int H,
                                  int W, cudaStream_t stream) {
+  return params_launch(grad_out, 0, data, coord, w0, b0, w1, partial, nparts, B, C, H, W, stream);
+}
+// grad_out as the haloed NHWC tap-major gradient (gof 1: bf16, 2: fp16)
+int rd_meta_kernel_bwd_params_ws_nhwc(const void* grad_out_pad, int gof, const float* data, const float* coord,
+                                      const float* w0, const float* b0, const float* w1, float* partial, int* nparts, int B,
+                                      int C, int H, int W, cudaStream_t stream) {
+  return params_launch(grad_out_pad, gof, data, coord, w0, b0, w1, partial, nparts, B, C, H, W, stream);
+}
+
+static int params_launch(const void* grad_out, int gof, const float* data, const float* coord, const float* w0,
+                         const float* b0, const float* w1, float* partial, int* nparts, int B, int C, int H, int W,
+                         cudaStream_t stream) {
   using namespace mkwp;
   RD_REQUIRE(C == mkwp::C, "Meta-Kernel impl 3 (TMA/tcgen05) is specialised for C == 64 (got %d)", C);
   RD_REQUIRE(W % 4 == 0, "Meta-Kernel impl 3 needs W %% 4 == 0; W=%d", W);
@@ -446,7 +487,17 @@ int rd_meta_kernel_bwd_params_ws(const float* grad_out, const float* data, const
   const uint64_t d4[4] = {(uint64_t)W, (uint64_t)H, 9u, (uint64_t)B * C};
   const uint64_t s4[3] = {(uint64_t)W * 4, plane, plane * 9};
   const uint32_t b4[4] = {(uint32_t)TW, 1u, 1u, (uint32_t)C};
-  if (tma::make_map(&tm_go, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, grad_out, 4, d4, s4, b4, CU_TENSOR_MAP_SWIZZLE_NONE)) return 1;
+  if (gof) {   // whole haloed NHWC tensor (9C, W+2, H+2, B): pixel (h, w) sits at (w+1, h+1)
+    const uint64_t Wp = (uint64_t)W + 2, Hp = (uint64_t)H + 2, CO = 9u * mkwp::C;
+    const uint64_t dn[4] = {CO, Wp, Hp, (uint64_t)B};
+    const uint64_t sn[3] = {CO * 2, Wp * CO * 2, Hp * Wp * CO * 2};
+    const uint32_t bn[4] = {(uint32_t)mkwp::C, (uint32_t)TW, 1u, 1u};
+    if (tma::make_map(&tm_go, gof == 1 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, grad_out, 4, dn, sn,
+                      bn, CU_TENSOR_MAP_SWIZZLE_128B))
+      return 1;
+  } else if (tma::make_map(&tm_go, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, grad_out, 4, d4, s4, b4, CU_TENSOR_MAP_SWIZZLE_NONE)) {
+    return 1;
+  }
   if (tma::make_map(&tm_data, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, data, 3, d3, s3, b3in, CU_TENSOR_MAP_SWIZZLE_NONE)) return 1;
   int dev = 0, sms = 0;
   RD_CUDA(cudaGetDevice(&dev));
@@ -455,6 +506,8 @@ int rd_meta_kernel_bwd_params_ws(const float* grad_out, const float* data, const
   const int64_t grid = ntiles < sms ? ntiles : sms;
   RD_CUDA(rd::smem_optin(meta_ws_params_kernel<false>, smem));
   RD_CUDA(rd::smem_optin(meta_ws_params_kernel<true>, smem));
+  RD_CUDA(rd::smem_optin(meta_ws_params_kernel<false, 1>, smem));
+  RD_CUDA(rd::smem_optin(meta_ws_params_kernel<false, 2>, smem));
   static const bool want_prof = [] { const char* e = getenv("RD_MK_PROF"); return e && e[0] == '1'; }();
   long long* d_prof = nullptr;
   if (want_prof) {
@@ -463,14 +516,20 @@ int rd_meta_kernel_bwd_params_ws(const float* grad_out, const float* data, const
     RD_CUDA(cudaMemsetAsync(buf, 0, 1024 * 16 * sizeof(long long), stream));
     d_prof = buf;
   }
-  if (want_prof)
+  if (gof == 1)
+    meta_ws_params_kernel<false, 1><<<(unsigned)grid, NTHREADS, smem, stream>>>(tm_go, tm_data, coord, w0, b0, w1, partial, B,
+                                                                                 H, W, tiles_w, (int)ntiles, nullptr);
+  else if (gof == 2)
+    meta_ws_params_kernel<false, 2><<<(unsigned)grid, NTHREADS, smem, stream>>>(tm_go, tm_data, coord, w0, b0, w1, partial, B,
+                                                                                 H, W, tiles_w, (int)ntiles, nullptr);
+  else if (want_prof)
     meta_ws_params_kernel<true><<<(unsigned)grid, NTHREADS, smem, stream>>>(tm_go, tm_data, coord, w0, b0, w1, partial, B, H,
                                                                              W, tiles_w, (int)ntiles, d_prof);
   else
     meta_ws_params_kernel<false><<<(unsigned)grid, NTHREADS, smem, stream>>>(tm_go, tm_data, coord, w0, b0, w1, partial, B,
                                                                               H, W, tiles_w, (int)ntiles, nullptr);
   rd::count_launch();
-  if (want_prof) {  // diagnostic: synchronous, mean cycles per TAP and role
+  if (want_prof && !gof) {  // diagnostic: synchronous, mean cycles per TAP and role
     RD_CUDA(cudaStreamSynchronize(stream));
     static long long hbuf[1024 * 16];
     RD_CUDA(cudaMemcpy(hbuf, d_prof, sizeof(long long) * 16 * grid, cudaMemcpyDeviceToHost));

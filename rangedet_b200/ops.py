@@ -121,6 +121,35 @@ def meta_kernel_backward(grad_out, data, coord, w0, b0, w1, b1, impl=IMPL_DEFAUL
     return gd, gw0, gb0, gw1, gb1
 
 
+def meta_kernel_backward_nhwc(grad_out_pad, data, coord, w0, b0, w1, b1, need_data_grad=True):
+    """meta_kernel_backward fed the gradient in the layout meta_kernel_forward_nhwc writes: grad_out_pad (B,H+2,W+2,9C)
+    zero-haloed bf16 / fp16, tap-major channels k*C+c.  Both kernels read the 2-byte tensor directly (no (B,9C,H,W) fp32
+    intermediate); results are bit-identical to meta_kernel_backward on the converted tensor.
+    -> (grad_data or None, grad_w0, grad_b0, grad_w1, grad_b1)."""
+    data = _chk(data, "data", 4)
+    coord = _chk(coord, "coord", 4)
+    B, C, H, W = data.shape
+    _chk_nhwc(grad_out_pad, "grad_out_pad")
+    if tuple(grad_out_pad.shape) != (B, H + 2, W + 2, 9 * C):
+        raise ValueError("grad_out_pad must be (B,H+2,W+2,9C)")
+    w0 = _chk(w0.reshape(w0.shape[0], -1), "w0", 2)
+    w1 = _chk(w1.reshape(w1.shape[0], -1), "w1", 2)
+    b0, b1 = _chk(b0, "b0", 1), _chk(b1, "b1", 1)
+    L = _lib.lib()
+    dev = data.device
+    gd = torch.empty_like(data) if need_data_grad else None
+    gw0, gb0 = torch.empty((32, 3), device=dev), torch.empty((32,), device=dev)
+    gw1, gb1 = torch.empty((C, 32), device=dev), torch.empty((C,), device=dev)
+    nbytes = int(L.rd_meta_kernel_bwd_workspace_bytes(B, C, H, W))
+    ws = torch.empty((max(nbytes, 4) + 3) // 4, device=dev, dtype=torch.float32)
+    with torch.cuda.device(dev):
+        st = _lib.act_fn("rd_meta_kernel_bwd_nhwc_bf16", grad_out_pad.dtype)(
+            _p(grad_out_pad), _p(data), _p(coord), _p(w0), _p(b0), _p(w1), _p(b1), _p(gd) if gd is not None else None,
+            _p(gw0), _p(gb0), _p(gw1), _p(gb1), _p(ws), ctypes.c_size_t(ws.numel() * 4), B, C, H, W, _stream())
+    _lib.check(st, "meta_kernel_backward_nhwc")
+    return gd, gw0, gb0, gw1, gb1
+
+
 class MetaKernelFunction(torch.autograd.Function):
     @staticmethod
     def forward(ctx, data, coord, w0, b0, w1, b1, impl):

@@ -500,11 +500,11 @@ class TrainGraph(object):
             dm, dgamma, dbeta, _ = ops.bn_act_bwd(da, m, coef, 2, dz_out=self._buf("dmeta", m.shape), dgb_out=dgb)
             self._pg(bn + "_gamma", dgb, lambda t: untm(t[0]))
             self._pg(bn + "_beta", dgb, lambda t: untm(t[1]))
-            # back to the reference op boundary: grad_out (B, 576 = c*9+k, H, W) fp32
-            go = ops.nhwc_to_nchw(dm, tap_major=True)
-            gd, gw0, gb0, gw1, gb1 = ops.meta_kernel_backward(go, feat, coord, *mlp)
+            # the Meta-Kernel backward reads the NHWC tap-major gradient as it is (the reference op boundary would be
+            # grad_out (B, 576 = c*9+k, H, W) fp32: a 2x larger tensor and a layout pass)
+            gd, gw0, gb0, gw1, gb1 = ops.meta_kernel_backward_nhwc(dm, feat, coord, *mlp)
             if self.debug is not None:
-                self.debug.update(meta_da=da, meta_dm=dm, meta_go=go, meta_gd=gd, meta_m=m, meta_a=a)
+                self.debug.update(meta_da=da, meta_dm=dm, meta_gd=gd, meta_m=m, meta_a=a)
             self._pg(name + "_2656_mlp0_weight", gw0, lambda t: t.reshape(32, 3, 1, 1), copy=True)
             self._pg(name + "_2656_mlp0_bias", gb0, copy=True)
             self._pg(name + "_2656_mlp1_weight", gw1, lambda t: t.reshape(-1, 32, 1, 1), copy=True)

@@ -225,6 +225,12 @@ def meta_kernel_backward(grad_out, data, coord, w0, b0, w1, b1, impl=0):
     return r[1], r[2], r[3], r[4], r[5]
 
 
+def meta_kernel_backward_nhwc(grad_out_pad, data, coord, w0, b0, w1, b1, need_data_grad=True):
+    go = nhwc_to_nchw(grad_out_pad, tap_major=True).to(data.dtype)
+    r = meta_kernel_backward(go, data, coord, w0, b0, w1, b1)
+    return (r[0] if need_data_grad else None,) + tuple(r[1:])
+
+
 def gather_to_bf16(src, idx, out):
     out.copy_(torch.where(idx >= 0, src[idx.clamp(min=0).long()], torch.zeros((), dtype=src.dtype)).to(out.dtype))
     return out

@@ -401,6 +401,28 @@ def test_meta_kernel_fused_nhwc_output(ops):
     report(test="meta_fwd_nhwc_fused", rel_err=rel_err(got.numpy(), want.numpy()))
 
 
+@pytest.mark.parametrize("dtype", [torch.float16, torch.bfloat16])
+@pytest.mark.parametrize("shape", [(2, 6, 300, 304), (1, 64, 2650, 2656)])
+def test_meta_kernel_backward_from_nhwc_gradient(ops, dtype, shape):
+    """The training graph's Meta-Kernel backward reads the haloed NHWC tap-major gradient (2-byte storage) directly:
+    same arithmetic on the widened values as the (B,9C,H,W) fp32 op-boundary path, so every output is bit-identical to
+    meta_kernel_backward fed the converted tensor (which the oracle tests above pin)."""
+    B, H, W, wpad = shape
+    C = 64
+    data, coord, (w0, b0, w1, b1) = _mk_inputs(B, C, H, W, wpad, seed=77)
+    g = torch.Generator(device="cuda").manual_seed(5)
+    go_pad = torch.zeros((B, H + 2, wpad + 2, 9 * C), device="cuda", dtype=dtype)
+    go_pad[:, 1:-1, 1:-1] = torch.randn((B, H, wpad, 9 * C), device="cuda", generator=g).to(dtype)
+    args = [cu(x) for x in (data, coord, w0, b0, w1, b1)]
+    want = ops.meta_kernel_backward(ops.nhwc_to_nchw(go_pad, tap_major=True), *args, impl=3)
+    got = ops.meta_kernel_backward_nhwc(go_pad, *args)
+    for name, a, b in zip(("grad_data", "grad_w0", "grad_b0", "grad_w1", "grad_b1"), got, want):
+        assert torch.equal(a, b), (name, float((a - b).abs().max()))
+    only_p = ops.meta_kernel_backward_nhwc(go_pad, *args, need_data_grad=False)
+    assert only_p[0] is None and all(torch.equal(a, b) for a, b in zip(only_p[1:], want[1:]))
+    report(test="meta_bwd_nhwc", dtype=str(dtype), shape=list(shape), bit_identical=True)
+
+
 def test_meta_kernel_class_surface(ops):
     from rangedet_b200.meta_kernel import MetaKernel
     mk = MetaKernel(num_batch=1, feat_height=8, feat_width=64, fp16=False)
