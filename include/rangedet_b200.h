@@ -380,7 +380,8 @@ int rd_gather_f32_to_f16(const float* src, const int* idx, void* dst, int64_t n,
 int rd_set_pdl(int on);
 /* 3x3 / stride-1 convolutions with 128 output channels run in the transposed GEMM orientation of csrc/conv_t.cu
  * (M = Cout, N = 256 flattened pixels) by default; rd_set_conv_t(0) (or RD_CONV_T=0) keeps them on the M = pixels kernel of
- * csrc/conv_tc.cu.  Same results (same K order); returns the previous setting. */
+ * csrc/conv_tc.cu.  Same results (same K order); returns the previous setting.  on = 160 / 192 / 224 / 256 additionally fixes
+ * the pixel-tile width (default: chosen per tensor shape so that the last round of tiles fills the SMs). */
 int rd_set_conv_t(int on);
 
 /* ---- tcgen05 self-test -------------------------------------------------------------------

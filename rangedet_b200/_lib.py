@@ -131,8 +131,8 @@ def set_pdl(on):
 
 def set_conv_t(on):
     """Transposed-orientation kernel (csrc/conv_t.cu) for 3x3 / stride-1 / Cout-128 convolutions on / off; returns the
-    previous setting."""
-    return bool(lib().rd_set_conv_t(1 if on else 0))
+    previous setting.  on = 160 / 192 / 224 / 256 also fixes the pixel-tile width (default: chosen per shape)."""
+    return int(lib().rd_set_conv_t(int(on)))
 
 
 def launch_count():

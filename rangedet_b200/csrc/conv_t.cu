@@ -36,7 +36,7 @@
 
 namespace RD_ACT_NS(convt) {
 
-constexpr int TN = 256;                       // pixels per tile = MMA N
+constexpr int TN = 256;                       // largest tile (pixels = MMA N); Params::tn (128..256, multiple of 32) is what a launch uses
 constexpr int CO = 128;                       // output channels = MMA M
 constexpr int KC = 64;                        // channels per K-half (one 128B swizzle atom)
 constexpr int STRIP_ROWS = 264;               // 258 pixels used; 256-pixel box + 8-pixel box
@@ -57,6 +57,7 @@ struct Params {
   int relu, has_res;
   int cout;               // 128, or 64: the weight tile's rows 64..127 are then TMA zero fill and TMEM lanes 64..127 idle
   int nsa, nsb;           // strip / weight ring stages
+  int tn;                 // pixels per tile (MMA N): chosen per shape so that the last wave of tiles is full (see pick_tn)
   int off_w, off_o, off_misc;
 };
 
@@ -119,14 +120,14 @@ convt_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ C
     if (lane == 0) {
       uint32_t sa = 0, pa = 1, sb = 0, pb = 1;   // ring positions, parity of the `empty` wait
       for (int tile = blockIdx.x; tile < P.ntiles; tile += gridDim.x) {
-        const int p0 = P.p_first + tile * TN;
+        const int p0 = P.p_first + tile * P.tn;
         for (int q = 0; q < kh; ++q)
           for (int dy = 0; dy < 3; ++dy) {
             const int ps = p0 + (dy - 1) * P.Wp - 1;   // >= 0: p0 >= Wp + 1
             tc::mbar_wait(&M.a_empty[sa], pa);
-            tc::mbar_arrive_expect_tx(&M.a_full[sa], (uint32_t)STRIP_BYTES);
+            tc::mbar_arrive_expect_tx(&M.a_full[sa], (uint32_t)(P.tn + 8) * 128u);
             tma::load_2d(strips + sa * STRIP_BYTES, &tm_x, &M.a_full[sa], q * KC, ps);
-            tma::load_2d(strips + sa * STRIP_BYTES + TN * 128, &tm_x2, &M.a_full[sa], q * KC, ps + TN);
+            tma::load_2d(strips + sa * STRIP_BYTES + P.tn * 128, &tm_x2, &M.a_full[sa], q * KC, ps + P.tn);
             if (++sa == NSA) { sa = 0; pa ^= 1; }
             for (int dx = 0; dx < 3; ++dx) {
               tc::mbar_wait(&M.b_empty[sb], pb);
@@ -140,7 +141,7 @@ convt_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ C
     __syncwarp();
   } else if (warp == 1) {
     // ===== MMA issuer: converged warp, one elected lane issues =====
-    const uint32_t idesc = tc::make_idesc_f16kind(CO, TN, RD_ACT_MMA_FMT);
+    const uint32_t idesc = tc::make_idesc_f16kind(CO, P.tn, RD_ACT_MMA_FMT);
     const uint64_t desc_hi = tc::make_smem_desc(0, 0, 1024, tc::LAYOUT_SW128);  // everything but the address
     const uint32_t strip_lo = tc::smem_u32(strips) >> 4, wt_lo = tc::smem_u32(wts) >> 4;
     const bool leader = tc::elect_one();
@@ -193,7 +194,9 @@ convt_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ C
     //  store in different banks.)
     const int ew = warp - 2;                      // 0..7
     const int q4 = warp & 3;                      // TMEM lane quadrant this warp may read
-    const int half = ew >> 2;                     // pixels [128*half, 128*half + 128) of the tile
+    const int half = ew >> 2;                     // which of the two warps of the quadrant: first / second part of the pixel columns
+    const int nch = P.tn >> 5;                    // 32-column chunks of the tile (4..8)
+    const int ch_lo = half ? (nch + 1) >> 1 : 0, ch_hi = half ? nch : (nch + 1) >> 1;
     const int c = q4 * 32 + lane;
     const uint32_t lane_sel = (uint32_t)(q4 * 32) << 16;
     const bool leader = (warp == 2 && lane == 0);
@@ -208,7 +211,7 @@ convt_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ C
     float s_sum = 0.f, s_sq = 0.f;
     uint32_t it = 0;
     for (int tile = blockIdx.x; tile < P.ntiles; tile += gridDim.x, ++it) {
-      const int p0 = P.p_first + tile * TN;
+      const int p0 = P.p_first + tile * P.tn;
       const uint32_t buf = it & 1;
       const long long e0 = tick();
       if (leader) tma::store_wait_read<0>();      // the previous tile's stores have read the staging tile
@@ -225,7 +228,7 @@ convt_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ C
       tma::named_bar_sync(BAR_EPI, 256);
       if (P.has_res) {                            // the other consumer's gradient / residual lands in the staging tile
         if (leader) {
-          tc::mbar_arrive_expect_tx(&M.r_full, (uint32_t)(nh * HALF_BYTES));
+          tc::mbar_arrive_expect_tx(&M.r_full, (uint32_t)(nh * P.tn) * 128u);
           for (int hf = 0; hf < nh; ++hf) tma::load_2d(sO + hf * HALF_BYTES, &tm_r, &M.r_full, hf * KC, p0);
         }
         tc::mbar_wait(&M.r_full, it & 1);
@@ -237,13 +240,13 @@ convt_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ C
       const long long e2 = tick();
       pc2 += e1 - e0;
       pc1 += e2 - e1;
-      const uint32_t t_acc = tmem_base + lane_sel + buf * (uint32_t)TN + (uint32_t)(half * 128);
+      const uint32_t t_acc = tmem_base + lane_sel + buf * (uint32_t)TN;
 #pragma unroll 1
-      for (int ch = 0; ch < (live ? 4 : 0); ++ch) {
+      for (int ch = ch_lo; ch < (live ? ch_hi : 0); ++ch) {
         float v[32];
         tc::tmem_ld_x32(t_acc + (uint32_t)(ch * 32), v);
-        const uint32_t mbits = M.mask[half * 4 + ch];
-        const int px0 = half * 128 + ch * 32;
+        const uint32_t mbits = M.mask[ch];
+        const int px0 = ch * 32;
 #pragma unroll
         for (int j = 0; j < 32; j += 2) {
           float a0 = fmaf(v[j], sc, sh), a1 = fmaf(v[j + 1], sc, sh);
@@ -297,6 +300,33 @@ convt_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ C
 }  // namespace convt_<storage type>
 namespace convt = RD_ACT_NS(convt);
 
+// Pixels per tile.  One persistent CTA per SM walks the tiles, so the kernel's time is (tiles per CTA, rounded up) x (tile
+// time).  Measured at 128 -> 128, B = 2 (scripts/conv_t_tiles.py): tile time = 2.3 us + 0.0234 us per pixel -- the constant is
+// the 288 KB of weight tiles every CTA re-streams from L2 per tile, ~96 pixels' worth -- so narrower tiles pay only where
+// they save a round: W = 664 is 346 tiles of 256 pixels = 2.3 per SM -> three rounds, at 224 pixels three shorter ones
+// (32.2 -> 30.5 us); W = 332: 160 pixels (24.0 -> 19.3 us); W = 2656 / 1328 stay at 256.  RD_CONVT_TN=<n> or
+// rd_set_conv_t(<n>) fix the width (A/B, tests).
+static int pick_tn(int npx, int sms) {
+  using convt::TN;
+  static int forced = -1;
+  if (forced < 0) {
+    const char* e = getenv("RD_CONVT_TN");
+    forced = e ? atoi(e) : 0;
+    if (forced % 32 || forced < 128 || forced > TN) forced = 0;
+  }
+  if (rd::conv_t_tile()) return rd::conv_t_tile();
+  if (forced) return forced;
+  int best = TN;
+  int64_t best_cost = -1;
+  for (int tn = TN; tn >= 160; tn -= 32) {
+    const int tiles = (npx + tn - 1) / tn;
+    const int rounds = (tiles + sms - 1) / sms;
+    const int64_t cost = (int64_t)rounds * (tn + 96);
+    if (best_cost < 0 || cost < best_cost) { best_cost = cost; best = tn; }
+  }
+  return best;
+}
+
 // Called by conv_tc.cu's dispatcher (same storage-type pass).  y = relu?(conv3x3(x) * scale + shift + residual), Cout = 128 or 64.
 int RD_ACT_FN(rd_convt_run_, )(const void* x_pad, const void* w_packed, const float* scale, const float* shift,
                                const void* residual_pad, void* y_pad, int N, int H, int W, int Cin, int Cout, int relu,
@@ -314,14 +344,18 @@ int RD_ACT_FN(rd_convt_run_, )(const void* x_pad, const void* w_packed, const fl
   P.P_total = (int)total;
   P.p_first = P.Wp + 1;
   const int p_last = P.P_total - P.Wp - 2;   // last interior pixel of the last image
-  P.ntiles = (p_last - P.p_first + 1 + TN - 1) / TN;
+  int dev = 0, sms = 0;
+  RD_CUDA(cudaGetDevice(&dev));
+  RD_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  P.tn = pick_tn(p_last - P.p_first + 1, sms);
+  P.ntiles = (p_last - P.p_first + 1 + P.tn - 1) / P.tn;
   P.relu = relu ? 1 : 0;
   P.has_res = residual_pad ? 1 : 0;
   CUtensorMap tm_x, tm_x2, tm_w, tm_y, tm_r;
   {
     const uint64_t d[2] = {(uint64_t)Cin, (uint64_t)total};
     const uint64_t s[1] = {(uint64_t)Cin * 2};
-    const uint32_t b[2] = {(uint32_t)KC, (uint32_t)TN}, b2[2] = {(uint32_t)KC, 8u};
+    const uint32_t b[2] = {(uint32_t)KC, (uint32_t)P.tn}, b2[2] = {(uint32_t)KC, 8u};
     if (tma::make_map(&tm_x, RD_ACT_TMA_TYPE, x_pad, 2, d, s, b, CU_TENSOR_MAP_SWIZZLE_128B)) return 1;
     if (tma::make_map(&tm_x2, RD_ACT_TMA_TYPE, x_pad, 2, d, s, b2, CU_TENSOR_MAP_SWIZZLE_128B)) return 1;
   }
@@ -335,13 +369,10 @@ int RD_ACT_FN(rd_convt_run_, )(const void* x_pad, const void* w_packed, const fl
   {
     const uint64_t d[2] = {(uint64_t)Cout, (uint64_t)total};
     const uint64_t s[1] = {(uint64_t)Cout * 2};
-    const uint32_t b[2] = {(uint32_t)KC, (uint32_t)TN};
+    const uint32_t b[2] = {(uint32_t)KC, (uint32_t)P.tn};
     if (tma::make_map(&tm_y, RD_ACT_TMA_TYPE, y_pad, 2, d, s, b, CU_TENSOR_MAP_SWIZZLE_128B)) return 1;
     if (tma::make_map(&tm_r, RD_ACT_TMA_TYPE, residual_pad ? residual_pad : y_pad, 2, d, s, b, CU_TENSOR_MAP_SWIZZLE_128B)) return 1;
   }
-  int dev = 0, sms = 0;
-  RD_CUDA(cudaGetDevice(&dev));
-  RD_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
   {
     // 227 KB: strips 33 KB each, weight tiles 16 KB each, staging 64 KB.  2 strips + 5 weight tiles; 2+4 and 3+3 measured
     // within 2 % (RD_CONVT_RINGS=ab overrides): the MMA warp's remaining waits (~4 k of 12 k cycles per tile) are the

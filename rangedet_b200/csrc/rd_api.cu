@@ -49,6 +49,8 @@ bool conv_t_enabled() {
   return g_conv_t != 0;
 }
 
+int conv_t_tile() { return conv_t_enabled() && g_conv_t >= 128 ? g_conv_t : 0; }
+
 }  // namespace rd
 
 extern "C" {
@@ -60,8 +62,8 @@ const char* rd_last_error(void) { return rd::g_err; }
 uint64_t rd_launch_count(void) { return rd::g_launches; }
 
 int rd_set_conv_t(int on) {
-  const int prev = rd::conv_t_enabled() ? 1 : 0;
-  rd::g_conv_t = on ? 1 : 0;
+  const int prev = rd::conv_t_enabled() ? rd::g_conv_t : 0;
+  rd::g_conv_t = (on == 160 || on == 192 || on == 224 || on == 256) ? on : (on ? 1 : 0);
   return prev;
 }
 

@@ -13,6 +13,7 @@ namespace rd {
 void set_error(const char* fmt, ...);
 void count_launch(int n = 1);
 bool pdl_enabled();   // programmatic dependent launch on (default) unless RD_PDL=0
+int conv_t_tile();       // 0: tile width chosen per shape; 160 / 192 / 224 / 256: fixed by rd_set_conv_t (tests, A/B)
 bool conv_t_enabled();   // transposed-orientation kernel for 3x3 / stride 1 / Cout 128 convolutions (default) unless RD_CONV_T=0
 
 // Returns 0 if ok; records the message otherwise.

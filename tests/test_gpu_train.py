@@ -570,7 +570,7 @@ def test_conv_epilogue_batch_statistics(ops, shape, dtype):
 @pytest.mark.parametrize("Co", [128] + ([64] if os.environ.get("RD_CONV_T64") == "1" else []))
 @pytest.mark.parametrize("shape", [(1, 128, 4, 131, False, False), (2, 128, 7, 300, True, True), (1, 64, 3, 64, False, True),
                                    (2, 256, 5, 166, True, False), (1, 128, 1, 1, False, False), (2, 128, 64, 2656, True, True),
-                                   (3, 128, 2, 257, False, False)])
+                                   (3, 128, 2, 257, False, False), (2, 128, 64, 664, False, True), (2, 128, 64, 332, True, False)])
 def test_conv_transposed_orientation_matches_pixel_major_kernel(ops, shape, dtype, Co):
     """csrc/conv_t.cu (M = Cout, N = 256 flattened pixels) against csrc/conv_tc.cu (M = 128 pixels of a row) on the same
     operands: 3x3 stride 1, Cout 128 and 64, with scale / shift / ReLU / residual, with the fused batch statistics, at widths
@@ -586,7 +586,7 @@ def test_conv_transposed_orientation_matches_pixel_major_kernel(ops, shape, dtyp
     xp, wp = ops.to_nhwc_padded(x, dtype=dtype), ops.pack_conv_weight(w, dtype=dtype)
     rp = ops.to_nhwc_padded(r, dtype=dtype) if res else None
     outs, stats = {}, {}
-    for on in (True, False):
+    for on in (True, False, 160, 192, 224, 256):     # True: tile width chosen per shape; then every width forced
         prev = _lib.set_conv_t(on)
         try:
             outs[on] = ops.conv2d_nhwc(xp, wp, scale, shift, relu=relu, residual_pad=rp)
@@ -599,15 +599,18 @@ def test_conv_transposed_orientation_matches_pixel_major_kernel(ops, shape, dtyp
     want = want + r if res else want
     want = torch.relu(want) if relu else want
     ulp = 2 ** -7 if dtype == torch.bfloat16 else 2 ** -10
-    for on in (True, False):
+    for on in outs:
         got = outs[on]
         assert float((ops.from_nhwc_padded(got) - want).abs().max()) <= ulp * float(want.abs().max()) + 2e-2 * (ulp / 2 ** -7), on
         assert float(got[:, 0].float().abs().max()) == 0 and float(got[:, -1].float().abs().max()) == 0          # halo rows
         assert float(got[:, :, 0].float().abs().max()) == 0 and float(got[:, :, -1].float().abs().max()) == 0    # halo columns
-    # same K order in both orientations: identical up to the hardware's in-MMA summation
-    d = (outs[True].float() - outs[False].float()).abs().max()
-    assert float(d) <= ulp * float(want.abs().max()), float(d)
-    assert float((stats[True][0].float() - stats[False][0].float()).abs().max()) <= ulp * float(stats[False][0].float().abs().max())
-    for row in (2, 4):   # mean, var
-        a, b = stats[True][1][row], stats[False][1][row]
-        assert float((a - b).abs().max()) <= 1e-4 * float(b.abs().max()) + 1e-6, row
+    # same K order in both orientations and at every tile width: identical up to the hardware's in-MMA summation
+    for on in outs:
+        if on is False:
+            continue
+        d = (outs[on].float() - outs[False].float()).abs().max()
+        assert float(d) <= ulp * float(want.abs().max()), (on, float(d))
+        assert float((stats[on][0].float() - stats[False][0].float()).abs().max()) <= ulp * float(stats[False][0].float().abs().max())
+        for row in (2, 4):   # mean, var
+            a, b = stats[on][1][row], stats[False][1][row]
+            assert float((a - b).abs().max()) <= 1e-4 * float(b.abs().max()) + 1e-6, (on, row)
