@@ -295,6 +295,23 @@ int rd_bn_train_finalize(const float* partial, int nslots, int N, int H, int W, 
                          const float* beta, float eps, float momentum, float* moving_mean, float* moving_var,
                          float* coef, rd_stream_t stream);
 
+/* The same fusion for the backward pass.  In a conv -> BatchNorm -> ReLU -> conv chain (dla_backbone.py:23-41: conv1 /
+ * bn1 / relu / conv2 of every basic block; builder.py:198-246: the head towers) the gradient dy of the BatchNorm output is
+ * the data gradient of the NEXT convolution and has no other contributor.  rd_conv2d_nhwc_*_bwdstats is that data-gradient
+ * convolution (3x3, stride 1, 128 output channels = the channels of the BatchNorm below; x_pad = the next layer's dz,
+ * w_packed = its flipped / transposed weight) with the two sums the BatchNorm backward needs accumulated by the epilogue
+ * from the gradient it stores: S1 = sum g, S2 = sum g (z - mean), g = dy (bn_mask_mode 0) or dy where z*a + b > 0 (2);
+ * bn_z_pad is the BatchNorm's input z, bn_coef its coefficient block.  rd_bn_act_bwd_apply_* then finishes
+ * rd_bn_act_bwd from those sums (finalize + apply: dz, dgamma, dbeta) -- the separate reduction pass over dy and z
+ * goes away.  sums_partial: rd_bn_workspace_bytes(Cout) bytes; workspace of the apply call: 2*C floats. */
+int rd_conv2d_nhwc_bf16_bwdstats(const void* x_pad, const void* w_packed, void* y_pad, const void* bn_z_pad,
+                                 const float* bn_coef, int bn_mask_mode, int N, int H, int W, int Cin, int Cout,
+                                 float* sums_partial, size_t sums_bytes, int* sums_slots, rd_stream_t stream);
+int rd_bn_act_bwd_apply_nhwc_bf16(const void* dy_pad, const void* y_mask_pad, const void* z_pad, const float* coef,
+                                  int mask_mode, const float* sums_partial, int sums_slots, void* dz_pad,
+                                  int dz_halo_w, void* g_out_pad, float* dgamma, float* dbeta, int N, int H, int W,
+                                  int C, void* workspace, size_t workspace_bytes, rd_stream_t stream);
+
 /* Layout conversions across the Meta-Kernel op boundary (the reference is NCHW throughout; channel
  * index of the (B,9C,H,W) Meta-Kernel tensors is c*9+k, meta_kernel.py:232-239):
  *   src_pad / dst_pad : zero-haloed NHWC bf16 [N][H+2][W+2][C_src or C_dst], interior touched only
@@ -363,6 +380,13 @@ int rd_bn_act_bwd_nhwc_f16(const void* dy_pad, const void* y_mask_pad, const voi
                            int mask_mode, void* dz_pad, int dz_halo_w, void* g_out_pad, float* dgamma,
                            float* dbeta, int N, int H, int W, int C, void* workspace,
                            size_t workspace_bytes, rd_stream_t stream);
+int rd_conv2d_nhwc_f16_bwdstats(const void* x_pad, const void* w_packed, void* y_pad, const void* bn_z_pad,
+                                const float* bn_coef, int bn_mask_mode, int N, int H, int W, int Cin, int Cout,
+                                float* sums_partial, size_t sums_bytes, int* sums_slots, rd_stream_t stream);
+int rd_bn_act_bwd_apply_nhwc_f16(const void* dy_pad, const void* y_mask_pad, const void* z_pad, const float* coef,
+                                 int mask_mode, const float* sums_partial, int sums_slots, void* dz_pad,
+                                 int dz_halo_w, void* g_out_pad, float* dgamma, float* dbeta, int N, int H, int W,
+                                 int C, void* workspace, size_t workspace_bytes, rd_stream_t stream);
 int rd_channel_sums_nhwc_f16(const void* x_pad, int N, int H, int W, int C, float* sums, void* workspace,
                              size_t workspace_bytes, rd_stream_t stream);
 int rd_add_nhwc_f16(const void* x0_pad, const void* x1_pad, void* y_pad, int N, int H, int W, int C,

@@ -51,6 +51,8 @@ SIGNATURES = {
     "rd_conv2d_nhwc_bf16": (_i, [_vp] * 6 + [_i] * 8 + [_vp]),
     "rd_conv2d_nhwc_bf16_slice": (_i, [_vp] * 5 + [_i] * 10 + [_vp]),
     "rd_conv2d_nhwc_bf16_stats": (_i, [_vp] * 3 + [_i] * 7 + [_vp, _sz, ctypes.POINTER(_i), _vp]),
+    "rd_conv2d_nhwc_bf16_bwdstats": (_i, [_vp] * 5 + [_i] * 6 + [_vp, _sz, ctypes.POINTER(_i), _vp]),
+    "rd_bn_act_bwd_apply_nhwc_bf16": (_i, [_vp] * 4 + [_i, _vp, _i, _vp, _i, _vp, _vp, _vp] + [_i] * 4 + [_vp, _sz, _vp]),
     "rd_bn_train_finalize": (_i, [_vp] + [_i] * 5 + [_vp, _vp, _f, _f, _vp, _vp, _vp, _vp]),
     "rd_deconv2d_nhwc_bf16": (_i, [_vp] * 6 + [_i] * 7 + [_vp]),
     "rd_conv2d_wgrad_workspace_bytes": (_sz, [_i] * 7),
@@ -72,6 +74,8 @@ SIGNATURES = {
     "rd_conv2d_nhwc_f16": (_i, [_vp] * 6 + [_i] * 8 + [_vp]),
     "rd_conv2d_nhwc_f16_slice": (_i, [_vp] * 5 + [_i] * 10 + [_vp]),
     "rd_conv2d_nhwc_f16_stats": (_i, [_vp] * 3 + [_i] * 7 + [_vp, _sz, ctypes.POINTER(_i), _vp]),
+    "rd_conv2d_nhwc_f16_bwdstats": (_i, [_vp] * 5 + [_i] * 6 + [_vp, _sz, ctypes.POINTER(_i), _vp]),
+    "rd_bn_act_bwd_apply_nhwc_f16": (_i, [_vp] * 4 + [_i, _vp, _i, _vp, _i, _vp, _vp, _vp] + [_i] * 4 + [_vp, _sz, _vp]),
     "rd_deconv2d_nhwc_f16": (_i, [_vp] * 6 + [_i] * 7 + [_vp]),
     "rd_conv2d_wgrad_nhwc_f16": (_i, [_vp] * 3 + [_i] * 7 + [_vp, _sz, _vp]),
     "rd_bn_train_stats_nhwc_f16": (_i, [_vp] + [_i] * 4 + [_vp, _vp, _f, _f, _vp, _vp, _vp, _vp, _sz, _vp]),

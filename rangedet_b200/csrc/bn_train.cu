@@ -570,6 +570,44 @@ int RD_ACT_FN(rd_bn_act_bwd_nhwc_, )(const void* dy_pad, const void* y_mask_pad,
   return rd::check_launch("rd_bn_act_bwd");
 }
 
+// rd_bn_act_bwd with the two sums already accumulated elsewhere (the epilogue of the convolution that produced dy:
+// rd_conv2d_nhwc_*_bwdstats): finalize + apply only, one full read of dy and z less.
+int RD_ACT_FN(rd_bn_act_bwd_apply_nhwc_, )(const void* dy_pad, const void* y_mask_pad, const void* z_pad, const float* coef,
+                                  int mask_mode, const float* sums_partial, int sums_slots, void* dz_pad, int dz_halo_w,
+                                  void* g_out_pad, float* dgamma, float* dbeta, int N, int H, int W, int C, void* workspace,
+                                  size_t workspace_bytes, rd_stream_t stream) {
+  if (bn::check_shape("rd_bn_act_bwd_apply", N, H, W, C)) return 1;
+  RD_REQUIRE(dy_pad && z_pad && coef && dz_pad && workspace && sums_partial, "rd_bn_act_bwd_apply: null pointer");
+  RD_REQUIRE(sums_slots > 0 && sums_slots <= bn::MAX_BLOCKS, "rd_bn_act_bwd_apply: bad number of partial slots (%d)", sums_slots);
+  RD_REQUIRE(mask_mode >= 0 && mask_mode <= 2, "rd_bn_act_bwd_apply: mask_mode must be 0, 1 or 2");
+  RD_REQUIRE(mask_mode != 1 || y_mask_pad, "rd_bn_act_bwd_apply: mask_mode 1 needs the forward output");
+  RD_REQUIRE(dz_halo_w >= 1 && dz_halo_w <= 8, "rd_bn_act_bwd_apply: dz_halo_w must be in [1,8]");
+  RD_REQUIRE(workspace_bytes >= 2 * (size_t)C * sizeof(float), "rd_bn_act_bwd_apply: workspace too small");
+  if (rd_check_device()) return 1;
+  cudaStream_t s = rd::as_stream(stream);
+  float* coef2 = static_cast<float*>(workspace);
+  const act_t* dy = static_cast<const act_t*>(dy_pad);
+  const act_t* ym = static_cast<const act_t*>(y_mask_pad);
+  const act_t* z = static_cast<const act_t*>(z_pad);
+  RD_CUDA_LAUNCH_FINALIZE(bn::bwd_finalize_kernel, s, sums_partial, sums_slots, C, (double)N * H * W, coef, coef2, dgamma, dbeta);
+  if (bn::stream_enabled()) {
+    const int nt = mask_mode == 1 ? 3 : 2;
+    const bn::SGeo sg = bn::make_sgeo(N, H, W, C, nt);
+    const size_t smem = bn::sgeo_smem(sg, nt);
+    if (bn::stream_prepare(bn::s_bwd_apply_kernel, smem)) return 1;
+    RD_CUDA(rd::launch(bn::s_bwd_apply_kernel, dim3(bn::stream_grid(sg)), dim3(bn::SNT), smem, s, dy, ym, z, coef, (const float*)coef2,
+                       sg, mask_mode, static_cast<act_t*>(dz_pad), dz_halo_w, static_cast<act_t*>(g_out_pad), bn::stream_rev(3)));
+  } else {
+    const bn::Geo g = bn::make_geo(N, H, W, C);
+    const int64_t units = (int64_t)g.N * g.H * g.nseg;
+    const int grid2 = (int)(units < 8 * 148 ? units : 8 * 148);
+    bn::bwd_apply_kernel<<<grid2, g.ppb * g.cgs, 0, s>>>(dy, ym, z, coef, coef2, g, mask_mode, static_cast<act_t*>(dz_pad),
+                                                         dz_halo_w, static_cast<act_t*>(g_out_pad));
+  }
+  rd::count_launch(2);
+  return rd::check_launch("rd_bn_act_bwd_apply");
+}
+
 int RD_ACT_FN(rd_channel_sums_nhwc_, )(const void* x_pad, int N, int H, int W, int C, float* sums, void* workspace,
                               size_t workspace_bytes, rd_stream_t stream) {
   if (bn::check_shape("rd_channel_sums", N, H, W, C)) return 1;

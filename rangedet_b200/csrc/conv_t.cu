@@ -58,6 +58,8 @@ struct Params {
   int cout;               // 128, or 64: the weight tile's rows 64..127 are then TMA zero fill and TMEM lanes 64..127 idle
   int nsa, nsb;           // strip / weight ring stages
   int tn;                 // pixels per tile (MMA N): chosen per shape so that the last wave of tiles is full (see pick_tn)
+  int bstat;              // BatchNorm-backward sums of the layer BELOW in the epilogue (see rd_conv2d_nhwc_*_bwdstats):
+                          // 0 off, 1 g = dy, 2 g = dy where z*a + b > 0 (the ReLU mask recomputed from z)
   int off_w, off_o, off_misc;
 };
 
@@ -75,7 +77,8 @@ __global__ void __launch_bounds__(NTHREADS, 1)
 convt_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_x2,
              const __grid_constant__ CUtensorMap tm_w, const __grid_constant__ CUtensorMap tm_y,
              const __grid_constant__ CUtensorMap tm_r, const float* __restrict__ scale, const float* __restrict__ shift,
-             float* __restrict__ stats, long long* __restrict__ prof, const __grid_constant__ Params P) {
+             float* __restrict__ stats, const float* __restrict__ bcoef, long long* __restrict__ prof,
+             const __grid_constant__ Params P) {
   extern __shared__ unsigned char smem_raw[];
   unsigned char* base = smem_raw + ((1024u - (tc::smem_u32(smem_raw) & 1023u)) & 1023u);
   const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
@@ -203,6 +206,9 @@ convt_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ C
     const bool live = c < P.cout;                 // whole warps: q4 >= 2 idles when Cout == 64 (it still joins every barrier)
     const int nh = P.cout / KC;                   // 64-channel halves of the staging tile in use
     const float sc = live ? M.scale[c] : 0.f, sh = live ? M.shift[c] : 0.f;
+    // BatchNorm below (bstat): a | b | mean rows of its coefficient block
+    const float za = (P.bstat && live) ? __ldg(bcoef + c) : 0.f, zb = (P.bstat && live) ? __ldg(bcoef + P.cout + c) : 0.f;
+    const float zm = (P.bstat && live) ? __ldg(bcoef + 2 * P.cout + c) : 0.f;
     const uint32_t odd = (uint32_t)(lane & 1);
     const uint32_t sel = odd ? 0x3276u : 0x5410u; // odd: (partner.hi, mine.hi) = channels (c-1, c) of pixel j+1; even: (mine.lo, partner.lo)
     unsigned char* my_row = sO + (c >> 6) * HALF_BYTES + odd * 128 + (c & 6) * 2;   // word (c & ~1) of row j + odd
@@ -226,7 +232,8 @@ convt_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ C
         if (lane == 0) M.mask[ew] = bits;
       }
       tma::named_bar_sync(BAR_EPI, 256);
-      if (P.has_res) {                            // the other consumer's gradient / residual lands in the staging tile
+      if (P.has_res || P.bstat) {                 // the other consumer's gradient / residual (or, bstat, the z tile of the
+                                                  // BatchNorm below) lands in the staging tile
         if (leader) {
           tc::mbar_arrive_expect_tx(&M.r_full, (uint32_t)(nh * P.tn) * 128u);
           for (int hf = 0; hf < nh; ++hf) tma::load_2d(sO + hf * HALF_BYTES, &tm_r, &M.r_full, hf * KC, p0);
@@ -250,18 +257,29 @@ convt_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ C
 #pragma unroll
         for (int j = 0; j < 32; j += 2) {
           float a0 = fmaf(v[j], sc, sh), a1 = fmaf(v[j + 1], sc, sh);
-          if (P.has_res) {
-            a0 += act::to_float(*reinterpret_cast<const act_t*>(my_col + (px0 + j) * 128 + ((my_chunk ^ (uint32_t)(j & 7)) << 4)));
-            a1 += act::to_float(*reinterpret_cast<const act_t*>(my_col + (px0 + j + 1) * 128 + ((my_chunk ^ (uint32_t)((j + 1) & 7)) << 4)));
+          float z0 = 0.f, z1 = 0.f;
+          if (P.has_res || P.bstat) {
+            z0 = act::to_float(*reinterpret_cast<const act_t*>(my_col + (px0 + j) * 128 + ((my_chunk ^ (uint32_t)(j & 7)) << 4)));
+            z1 = act::to_float(*reinterpret_cast<const act_t*>(my_col + (px0 + j + 1) * 128 + ((my_chunk ^ (uint32_t)((j + 1) & 7)) << 4)));
           }
+          if (P.has_res) { a0 += z0; a1 += z1; }
           if (P.relu) { a0 = fmaxf(a0, 0.f); a1 = fmaxf(a1, 0.f); }
           if ((mbits >> j) & 1u) a0 = 0.f;        // halo pixels: keep them zero
           if ((mbits >> (j + 1)) & 1u) a1 = 0.f;
           const uint32_t mine = act::pack2(a0, a1);                      // channel c: (pixel j, pixel j + 1)
           float f0, f1;
           act::unpack2(mine, f0, f1);
-          s_sum += f0 + f1;
-          s_sq = fmaf(f0, f0, fmaf(f1, f1, s_sq));
+          if (P.bstat) {   // S1 = sum g, S2 = sum g (z - mean) of the stored gradient (what bn::s_bwd_reduce_kernel would read back)
+            if (P.bstat == 2) {
+              f0 = fmaf(z0, za, zb) > 0.f ? f0 : 0.f;
+              f1 = fmaf(z1, za, zb) > 0.f ? f1 : 0.f;
+            }
+            s_sum += f0 + f1;
+            s_sq = fmaf(f0, z0 - zm, fmaf(f1, z1 - zm, s_sq));
+          } else {
+            s_sum += f0 + f1;
+            s_sq = fmaf(f0, f0, fmaf(f1, f1, s_sq));
+          }
           const uint32_t theirs = __shfl_xor_sync(0xffffffffu, mine, 1);
           const uint32_t word = __byte_perm(mine, theirs, sel);          // channels (c & ~1, +1) of pixel j + odd
           // all lanes of a pair have passed their residual reads of both rows before either writes (shuffle above)
@@ -330,9 +348,12 @@ static int pick_tn(int npx, int sms) {
 // Called by conv_tc.cu's dispatcher (same storage-type pass).  y = relu?(conv3x3(x) * scale + shift + residual), Cout = 128 or 64.
 int RD_ACT_FN(rd_convt_run_, )(const void* x_pad, const void* w_packed, const float* scale, const float* shift,
                                const void* residual_pad, void* y_pad, int N, int H, int W, int Cin, int Cout, int relu,
-                               cudaStream_t stream, float* stats, int* stats_slots) {
+                               cudaStream_t stream, float* stats, int* stats_slots, const void* bn_z, const float* bn_coef,
+                               int bn_mask) {
   using namespace convt;
   RD_REQUIRE(Cout == 64 || Cout == 128, "rd_conv(T): Cout must be 64 or 128");
+  RD_REQUIRE(!bn_z || (!residual_pad && stats && bn_coef && (bn_mask == 0 || bn_mask == 2)),
+             "rd_conv(T): BatchNorm-backward sums need a statistics buffer, the coefficient block, mask_mode 0 or 2, and no residual");
   Params P;
   memset(&P, 0, sizeof(P));
   P.kh = Cin / KC;
@@ -351,6 +372,7 @@ int RD_ACT_FN(rd_convt_run_, )(const void* x_pad, const void* w_packed, const fl
   P.ntiles = (p_last - P.p_first + 1 + P.tn - 1) / P.tn;
   P.relu = relu ? 1 : 0;
   P.has_res = residual_pad ? 1 : 0;
+  P.bstat = bn_z ? (bn_mask == 2 ? 2 : 1) : 0;
   CUtensorMap tm_x, tm_x2, tm_w, tm_y, tm_r;
   {
     const uint64_t d[2] = {(uint64_t)Cin, (uint64_t)total};
@@ -371,7 +393,7 @@ int RD_ACT_FN(rd_convt_run_, )(const void* x_pad, const void* w_packed, const fl
     const uint64_t s[1] = {(uint64_t)Cout * 2};
     const uint32_t b[2] = {(uint32_t)KC, (uint32_t)P.tn};
     if (tma::make_map(&tm_y, RD_ACT_TMA_TYPE, y_pad, 2, d, s, b, CU_TENSOR_MAP_SWIZZLE_128B)) return 1;
-    if (tma::make_map(&tm_r, RD_ACT_TMA_TYPE, residual_pad ? residual_pad : y_pad, 2, d, s, b, CU_TENSOR_MAP_SWIZZLE_128B)) return 1;
+    if (tma::make_map(&tm_r, RD_ACT_TMA_TYPE, residual_pad ? residual_pad : (bn_z ? bn_z : y_pad), 2, d, s, b, CU_TENSOR_MAP_SWIZZLE_128B)) return 1;
   }
   {
     // 227 KB: strips 33 KB each, weight tiles 16 KB each, staging 64 KB.  2 strips + 5 weight tiles; 2+4 and 3+3 measured
@@ -399,7 +421,7 @@ int RD_ACT_FN(rd_convt_run_, )(const void* x_pad, const void* w_packed, const fl
     if (!d_prof) RD_CUDA(cudaMalloc(&d_prof, 1024 * 8 * sizeof(long long)));
     RD_CUDA(cudaMemsetAsync(d_prof, 0, 1024 * 8 * sizeof(long long), stream));
     RD_CUDA(rd::launch(convt_kernel<true>, dim3(grid), dim3(NTHREADS), smem, stream, tm_x, tm_x2, tm_w, tm_y, tm_r, scale, shift, stats,
-                       d_prof, P));
+                       bn_coef, d_prof, P));
     RD_CUDA(cudaStreamSynchronize(stream));
     static long long h[1024 * 8];
     RD_CUDA(cudaMemcpy(h, d_prof, sizeof(long long) * 8 * grid, cudaMemcpyDeviceToHost));
@@ -412,7 +434,7 @@ int RD_ACT_FN(rd_convt_run_, )(const void* x_pad, const void* w_packed, const fl
             m[4] / tiles, m[5] / tiles, m[6] / tiles, m[7] / tiles);
   } else {
     RD_CUDA(rd::launch(convt_kernel<false>, dim3(grid), dim3(NTHREADS), smem, stream, tm_x, tm_x2, tm_w, tm_y, tm_r, scale, shift, stats,
-                       (long long*)nullptr, P));
+                       bn_coef, (long long*)nullptr, P));
   }
   rd::count_launch();
   return rd::check_launch("rd_conv(T)");

@@ -34,7 +34,8 @@
 // conv_t.cu: 3x3 / stride 1 / Cout = 128 in the transposed GEMM orientation (M = Cout, N = 256 pixels)
 int RD_ACT_FN(rd_convt_run_, )(const void* x_pad, const void* w_packed, const float* scale, const float* shift,
                                const void* residual_pad, void* y_pad, int N, int H, int W, int Cin, int Cout, int relu,
-                               cudaStream_t stream, float* stats, int* stats_slots);
+                               cudaStream_t stream, float* stats, int* stats_slots, const void* bn_z = nullptr,
+                               const float* bn_coef = nullptr, int bn_mask = 0);
 
 namespace RD_ACT_NS(conv) {
 
@@ -705,6 +706,22 @@ int RD_ACT_FN(rd_conv2d_nhwc_, _stats)(const void* x_pad, const void* w_packed, 
              "rd_conv2d_nhwc_stats: statistics workspace too small (rd_bn_workspace_bytes(Cout))");
   return conv::run(0, x_pad, w_packed, nullptr, nullptr, nullptr, y_pad, N, H, W, Cin, Cout, ksize, stride_w, 0, 0,
                    rd::as_stream(stream), 0, 0, stats_partial, stats_slots);
+}
+
+// Data-gradient convolution that also accumulates the BatchNorm-backward sums of the layer below (see the header).
+int RD_ACT_FN(rd_conv2d_nhwc_, _bwdstats)(const void* x_pad, const void* w_packed, void* y_pad, const void* bn_z_pad,
+                                          const float* bn_coef, int bn_mask_mode, int N, int H, int W, int Cin, int Cout,
+                                          float* sums_partial, size_t sums_bytes, int* sums_slots, rd_stream_t stream) {
+  RD_REQUIRE(x_pad && w_packed && y_pad && bn_z_pad && bn_coef && sums_partial && sums_slots, "rd_conv2d_nhwc_bwdstats: null pointer");
+  RD_REQUIRE(Cout == 128 && Cin >= 64 && Cin % 64 == 0 && Cin <= 1024,
+             "rd_conv2d_nhwc_bwdstats: 3x3 / stride 1 with 128 output channels only (got %d -> %d)", Cin, Cout);
+  RD_REQUIRE(bn_mask_mode == 0 || bn_mask_mode == 2, "rd_conv2d_nhwc_bwdstats: mask_mode must be 0 or 2");
+  RD_REQUIRE(N > 0 && H > 0 && W > 0, "rd_conv2d_nhwc_bwdstats: bad shape");
+  RD_REQUIRE(sums_bytes >= (size_t)conv::STATS_STRIDE * 2 * (size_t)Cout * sizeof(float),
+             "rd_conv2d_nhwc_bwdstats: sums workspace too small (rd_bn_workspace_bytes(Cout))");
+  if (rd_check_device()) return 1;
+  return RD_ACT_FN(rd_convt_run_, )(x_pad, w_packed, nullptr, nullptr, nullptr, y_pad, N, H, W, Cin, Cout, 0, rd::as_stream(stream),
+                                    sums_partial, sums_slots, bn_z_pad, bn_coef, bn_mask_mode);
 }
 
 int RD_ACT_FN(rd_conv2d_nhwc_, _slice)(const void* x_pad, const void* w_packed, const float* scale, const float* shift,

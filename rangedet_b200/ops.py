@@ -599,6 +599,39 @@ def conv2d_nhwc_stats(x_pad, w_packed, out=None, stride_w=1, ws=None):
     return out, ws, slots.value
 
 
+def conv_bwdstats_supported(cin, cout, ksize=3, stride_w=1):
+    """Whether conv2d_nhwc_bwdstats handles this data-gradient convolution (the transposed-orientation kernel's shapes)."""
+    return ksize == 3 and stride_w == 1 and cout == 128 and cin % 64 == 0 and 64 <= cin <= 1024
+
+
+def conv2d_nhwc_bwdstats(x_pad, w_packed, bn_z_pad, bn_coef, bn_mask_mode, out=None, ws=None):
+    """Data-gradient convolution dy = conv3x3(x) whose epilogue also accumulates the sums of the BatchNorm backward of the
+    layer below (z = bn_z_pad, coefficients bn_coef, ReLU mask recomputed from z when bn_mask_mode == 2).
+    Returns (dy, sums, nslots) for bn_act_bwd(..., sums=(sums, nslots))."""
+    N, Hp, Wp, Cin = x_pad.shape
+    if w_packed.shape[0] != 9:
+        raise ValueError("conv2d_nhwc_bwdstats: 3x3 kernels only")
+    H, W = Hp - 2, Wp - 2
+    x_pad, w_packed, _, _, _, out = _conv_common(x_pad, w_packed, None, None, None, out, W, "conv2d_nhwc_bwdstats")
+    _chk_nhwc(bn_z_pad, "bn_z_pad", x_pad)
+    Cout = w_packed.shape[1]
+    if tuple(bn_z_pad.shape) != (N, Hp, Wp, Cout):
+        raise ValueError("conv2d_nhwc_bwdstats: bn_z_pad must have the output's shape")
+    L = _lib.lib()
+    nb = int(L.rd_bn_workspace_bytes(Cout))
+    if ws is None:
+        ws = torch.empty(nb // 4, device=x_pad.device, dtype=torch.float32)
+    if ws.dtype != torch.float32 or ws.numel() * 4 < nb:
+        raise ValueError("conv2d_nhwc_bwdstats: sums workspace needs %d bytes of float32" % nb)
+    slots = ctypes.c_int(0)
+    with torch.cuda.device(x_pad.device):
+        st = _lib.act_fn("rd_conv2d_nhwc_bf16_bwdstats", x_pad.dtype)(_p(x_pad), _p(w_packed), _p(out), _p(bn_z_pad), _p(bn_coef),
+                                                                      int(bn_mask_mode), N, H, W, Cin, Cout, _p(ws),
+                                                                      ctypes.c_size_t(ws.numel() * 4), ctypes.byref(slots), _stream())
+    _lib.check(st, "conv2d_nhwc_bwdstats")
+    return out, ws, slots.value
+
+
 def bn_train_finalize(partial, nslots, N, H, W, C, gamma=None, beta=None, moving_mean=None, moving_var=None, eps=None,
                       momentum=None, coef=None):
     """Partial sums (conv2d_nhwc_stats) -> coef (6,C) fp32 as bn_train_stats returns; moving statistics updated in place."""
@@ -745,9 +778,10 @@ def bn_act_fwd(z_pad, coef, relu=True, res_before=None, res_after=None, out=None
 
 
 def bn_act_bwd(dy_pad, z_pad, coef, mask_mode, y_mask=None, dz_halo_w=1, dz_out=None, want_g=False, g_out=None,
-               dgb_out=None):
+               dgb_out=None, sums=None):
     """Backward of bn_act_fwd w.r.t. z, gamma, beta (and the masked gradient g that flows into res_before).
-    Returns (dz, dgamma, dbeta, g or None).  dz has a W halo of dz_halo_w pixels."""
+    Returns (dz, dgamma, dbeta, g or None).  dz has a W halo of dz_halo_w pixels.  sums = (partial, nslots) from
+    conv2d_nhwc_bwdstats: the reduction pass is skipped."""
     _chk_nhwc(dy_pad, "dy_pad")
     _chk_nhwc(z_pad, "z_pad", dy_pad)
     N, Hp, Wp, C = z_pad.shape
@@ -766,9 +800,14 @@ def bn_act_bwd(dy_pad, z_pad, coef, mask_mode, y_mask=None, dz_halo_w=1, dz_out=
     ws = _workspace(nb, z_pad.device, "bn")
     opt = lambda t: _p(t) if t is not None else None
     with torch.cuda.device(z_pad.device):
-        st = _lib.act_fn("rd_bn_act_bwd_nhwc_bf16", z_pad.dtype)(_p(dy_pad), opt(y_mask), _p(z_pad), _p(coef), int(mask_mode), _p(dz_out),
-                                       int(dz_halo_w), opt(g_out), _p(dgamma), _p(dbeta), N, H, W, C, _p(ws), nb,
-                                       _stream())
+        if sums is not None:
+            st = _lib.act_fn("rd_bn_act_bwd_apply_nhwc_bf16", z_pad.dtype)(
+                _p(dy_pad), opt(y_mask), _p(z_pad), _p(coef), int(mask_mode), _p(sums[0]), int(sums[1]), _p(dz_out), int(dz_halo_w),
+                opt(g_out), _p(dgamma), _p(dbeta), N, H, W, C, _p(ws), nb, _stream())
+        else:
+            st = _lib.act_fn("rd_bn_act_bwd_nhwc_bf16", z_pad.dtype)(_p(dy_pad), opt(y_mask), _p(z_pad), _p(coef), int(mask_mode),
+                                                                     _p(dz_out), int(dz_halo_w), opt(g_out), _p(dgamma), _p(dbeta),
+                                                                     N, H, W, C, _p(ws), nb, _stream())
     _lib.check(st, "bn_act_bwd")
     return dz_out, dgamma, dbeta, g_out
 

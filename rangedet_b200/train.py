@@ -116,6 +116,12 @@ class TrainGraph(object):
         self.use_meta = use_meta
         self.act_dtype = act_dtype
         self.fuse_stats = True     # BatchNorm batch statistics in the conv epilogue (False: separate rd_bn_train_stats pass)
+        # BatchNorm-backward sums in the epilogue of the data-gradient conv above: True / False / "auto".  Measured per layer
+        # width at B=2, 128 channels (scripts/bwdsums_ab.py, conv + BN backward, separate -> fused): W=664 57.4 -> 54.8 us,
+        # W=1328 91.6 -> 91.6, W=2656 158 -> 163, W=332 43.5 -> 46.4 -- the conv's epilogue (z tile through the staging
+        # buffer it also stores from) pays back what the BN pass saves, except in the middle: "auto" fuses there only.
+        self.fuse_bwd_sums = "auto"
+        self.bn_below, self.bsums = {}, {}
         self._stats_bufs = {}
         self.pool = _Pool(device, act_dtype)
         self.packed = {}
@@ -259,6 +265,7 @@ class TrainGraph(object):
     def begin(self):
         """Start a new step: empty tape, no gradients."""
         self.tape, self.grads, self.pgrads, self.nograd, self._n = [], {}, {}, set(), 0
+        self.bn_below, self.bsums = {}, {}
         self._gn = 0
         if self.arena is None:
             self.g_sizes = []
@@ -323,9 +330,12 @@ class TrainGraph(object):
             self.pgrads[name] = None
 
     # ---- layers -----------------------------------------------------------------------------------------
-    def conv_bn(self, x, wname, bnname, stride_w=1, relu=True, res_before=None, kinds=("fwd", "dgrad"), dx_channels=None):
+    def conv_bn(self, x, wname, bnname, stride_w=1, relu=True, res_before=None, kinds=("fwd", "dgrad"), dx_channels=None,
+                sole_consumer=False):
         """dx_channels = (lo, hi, t): x is a channel concatenation whose channels [lo, hi) are the tensor t and whose other
-        channels need no gradient -- the backward computes the data gradient of that slice only, straight into grad(t)."""
+        channels need no gradient -- the backward computes the data gradient of that slice only, straight into grad(t).
+        sole_consumer: nothing else reads x, so this layer's data gradient IS grad(x); if x is the output of a conv_bn
+        without residual, its BatchNorm-backward sums are accumulated by this layer's data-gradient kernel."""
         P = self.P
         w = P[wname + "_weight"]
         co, ci, k = w.shape[0], w.shape[1], w.shape[2]
@@ -344,17 +354,24 @@ class TrainGraph(object):
             coef = ops.bn_train_stats(z, P[bnname + "_gamma"], P[bnname + "_beta"], P[bnname + "_moving_mean"],
                                       P[bnname + "_moving_var"])
         y = ops.bn_act_fwd(z, coef, relu=relu, res_before=res_before, out=self._buf("y", z.shape))
+        # ReLU mask: without a residual the pre-activation is z*a+b, recomputed from the z the kernels read
+        # anyway (mask_mode 2) -- saves one full read of y in each of the two backward passes
+        mm = 0 if not relu else (2 if res_before is None else 1)
+        if res_before is None:
+            self.bn_below[id(y)] = (z, coef, mm)
+        want = self.fuse_bwd_sums
+        if want == "auto":
+            want = 50000 <= N * (Hp - 2) * (Wp - 2) <= 130000
+        below = self.bn_below.get(id(x)) if (sole_consumer and want and dx_channels is None and stride_w == 1 and k == 3
+                                             and ops.conv_bwdstats_supported(co_p, ci_p)) else None
 
         def bwd():
             dy = self.grads.pop(id(y))
             dgb = self._gbuf((2, co_p))
-            # ReLU mask: without a residual the pre-activation is z*a+b, recomputed from the z the kernels read
-            # anyway (mask_mode 2) -- saves one full read of y in each of the two backward passes
-            mm = 0 if not relu else (2 if res_before is None else 1)
             dz, dgamma, dbeta, g = ops.bn_act_bwd(dy, z, coef, mm, y_mask=y if mm == 1 else None, dz_out=self._buf("dz", z.shape),
                                                   want_g=res_before is not None and relu,
                                                   g_out=self._buf("g", z.shape) if (res_before is not None and relu) else None,
-                                                  dgb_out=dgb)
+                                                  dgb_out=dgb, sums=self.bsums.pop(id(y), None))
             if res_before is not None:
                 self._acc(res_before, g if relu else dy)
             self._pg(bnname + "_gamma", dgb, lambda t: t[0, :co])
@@ -384,6 +401,11 @@ class TrainGraph(object):
                     cs = 128 if ci_p - c0 >= 128 else 64
                     ops.conv2d_nhwc_slice(dz, wt[:, c0:c0 + cs].contiguous(), dx, c0)
                     c0 += cs
+            elif below is not None and old is None:
+                # grad(x) is complete with this kernel: it also accumulates the sums of the BatchNorm that produced x
+                dx, part, nslots = ops.conv2d_nhwc_bwdstats(dz, self._w(wname, kinds[1], ci_p, co_p), below[0], below[1], below[2],
+                                                            out=self._buf("dx", x.shape), ws=self._stats_ws(ci_p))
+                self.bsums[id(x)] = (part, nslots)
             elif stride_w == 1:
                 dx = ops.conv2d_nhwc(dz, self._w(wname, kinds[1], ci_p, co_p), relu=False, residual_pad=old,
                                      out=self._buf("dx", x.shape))
@@ -520,7 +542,7 @@ class TrainGraph(object):
         else:
             r1 = self.conv_bn(x, name + "_conv1", name + "_bn1")
         sc = self.conv_bn(x, name + "_sc", name + "_sc_bn", stride_w=stride_w, relu=False) if proj else x
-        return self.conv_bn(r1, name + "_conv2", name + "_bn2", stride_w=stride_w, relu=True, res_before=sc)
+        return self.conv_bn(r1, name + "_conv2", name + "_bn2", stride_w=stride_w, relu=True, res_before=sc, sole_consumer=True)
 
     def res_stage(self, x, coord, name, stride_w):
         x = self.basicblock(x, coord, name + "_unit1", stride_w, True)
@@ -559,9 +581,9 @@ class TrainGraph(object):
             dxc = (c, c + 64, agg3) if lvl == 0 else None
             for i in range(4):
                 n = "rpn_cls_conv_%d_lvl_%d" % (i, lvl)
-                t_c = self.conv_bn(t_c, n, n + "_bn", dx_channels=dxc if i == 0 else None)
+                t_c = self.conv_bn(t_c, n, n + "_bn", dx_channels=dxc if i == 0 else None, sole_consumer=i > 0)
                 n = "rpn_reg_conv_%d_lvl_%d" % (i, lvl)
-                t_r = self.conv_bn(t_r, n, n + "_bn", dx_channels=dxc if i == 0 else None)
+                t_r = self.conv_bn(t_r, n, n + "_bn", dx_channels=dxc if i == 0 else None, sole_consumer=i > 0)
             o, b = self.head_out(t_c, "rpn_cls_logit_lvl_%d" % lvl, 1)
             cls_logit.append(o)
             self.head_bwd.append(("cls", lvl, b, len(self.tape)))
@@ -694,7 +716,7 @@ class GraphedTrainStep(object):
     def __init__(self, params, batch, H, W, lr, momentum=0.9, wd=1e-5, clip_gradient=35.0, rescale_grad=1.0 / 128.0,
                  device="cuda", use_meta=True, allreduce=None, world_size=1, with_loss=True, overlap_wgrad=True,
                  loss_hyper=None, gt_name="gt_bbox_veh_for_iou_pred", capture=True, act_dtype=torch.bfloat16,
-                 overlap_allreduce=True, fuse_stats=True):
+                 overlap_allreduce=True, fuse_stats=True, fuse_bwd_sums="auto"):
         self.P = params
         self.allreduce = allreduce
         self.with_loss = with_loss
@@ -721,6 +743,7 @@ class GraphedTrainStep(object):
                                   device=device)
         self.tg = TrainGraph(params, device, use_meta, act_dtype)
         self.tg.fuse_stats = bool(fuse_stats)     # False: separate rd_bn_train_stats pass after every conv (A/B timing)
+        self.tg.fuse_bwd_sums = fuse_bwd_sums     # True / False / "auto" (TrainGraph.__init__)
         self.act_dtype = act_dtype
         self.capture = capture    # False: same buffers and flat plumbing, kernels launched eagerly (debugging)
         if overlap_wgrad and capture:

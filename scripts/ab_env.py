@@ -19,7 +19,10 @@ T = synth.rpn_targets(B, seed=500)
 g = torch.Generator(device=dev).manual_seed(600)
 data = torch.randn((B, 8, H, W), device=dev, generator=g)
 coord = torch.from_numpy(synth.range_image_coords(B, seed=700)).to(dev)
-step = train.GraphedTrainStep(make_params(seed=0, device=dev), B, H, W, lr=0.0125, device=dev, act_dtype=torch.float16)
+kw = {}
+if os.environ.get("AB_BWD_SUMS"):
+    kw["fuse_bwd_sums"] = {"0": False, "1": True, "auto": "auto"}[os.environ["AB_BWD_SUMS"]]
+step = train.GraphedTrainStep(make_params(seed=0, device=dev), B, H, W, lr=0.0125, device=dev, act_dtype=torch.float16, **kw)
 step.set_targets(T)
 for _ in range(5):
     step.train_step(data, coord)

@@ -10,8 +10,8 @@ bf16-rounded operands and rounds its bf16 outputs once, like the kernels.  The p
 import torch
 import torch.nn.functional as F
 
-from rangedet_b200.ops import (ACT_DTYPES, BN_EPS, BN_MOMENTUM, IMPL_DEFAULT, from_nhwc_padded, pack_conv_weight,  # noqa: F401
-                               pack_deconv_weight, tap_major_weight, to_nhwc_padded)  # (pure torch helpers of the real module)
+from rangedet_b200.ops import (ACT_DTYPES, BN_EPS, BN_MOMENTUM, IMPL_DEFAULT, conv_bwdstats_supported, from_nhwc_padded,  # noqa: F401
+                               pack_conv_weight, pack_deconv_weight, tap_major_weight, to_nhwc_padded)  # (pure torch helpers of the real module)
 
 bf16 = torch.bfloat16
 COMPUTE = torch.float32      # arithmetic type of the emulated kernels
@@ -67,6 +67,11 @@ def conv2d_nhwc_stats(x_pad, w_packed, out=None, stride_w=1, ws=None):
     """Emulation of the fused conv + batch-statistics call: the 'partials' handed to bn_train_finalize are z itself."""
     z = conv2d_nhwc(x_pad, w_packed, relu=False, out=out, stride_w=stride_w)
     return z, z, -1
+
+
+def conv2d_nhwc_bwdstats(x_pad, w_packed, bn_z_pad, bn_coef, bn_mask_mode, out=None, ws=None):
+    """Emulation of the data-gradient conv with fused BatchNorm-backward sums: the 'sums' are recomputed by bn_act_bwd."""
+    return conv2d_nhwc(x_pad, w_packed, relu=False, out=out), None, -1
 
 
 def bn_train_finalize(partial, nslots, N, H, W, C, gamma=None, beta=None, moving_mean=None, moving_var=None, eps=None,
@@ -141,7 +146,8 @@ def bn_act_fwd(z_pad, coef, relu=True, res_before=None, res_after=None, out=None
     return _store(torch.zeros_like(z_pad) if out is None else out, y)
 
 
-def bn_act_bwd(dy_pad, z_pad, coef, mask_mode, y_mask=None, dz_halo_w=1, dz_out=None, want_g=False, g_out=None, dgb_out=None):
+def bn_act_bwd(dy_pad, z_pad, coef, mask_mode, y_mask=None, dz_halo_w=1, dz_out=None, want_g=False, g_out=None, dgb_out=None,
+               sums=None):
     g, z = _nchw(dy_pad), _nchw(z_pad)
     a, b, mean, invstd = [coef[i].view(1, -1, 1, 1) for i in range(4)]
     if mask_mode == 1:

@@ -401,6 +401,35 @@ def test_layout_conversions(ops, C, Cp, tap):
 
 
 @pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16])
+@pytest.mark.parametrize("mask_mode", [2, 0])
+@pytest.mark.parametrize("shape", [(2, 128, 7, 300), (1, 64, 3, 131), (2, 128, 64, 664)])
+def test_conv_epilogue_batchnorm_backward_sums(ops, shape, mask_mode, dtype):
+    """Data-gradient conv with the BatchNorm-backward sums of the layer below in its epilogue + apply-only BN backward
+    == plain conv followed by the three-pass rd_bn_act_bwd: same dy bits, dz within one storage rounding, dgamma / dbeta
+    to fp32 summation-order noise."""
+    N, Ci, H, W = shape
+    C = 128
+    g = torch.Generator(device="cuda").manual_seed(17)
+    rnd = lambda t: t.to(dtype).float()
+    dz_up = ops.to_nhwc_padded(rnd(torch.randn((N, Ci, H, W), device="cuda", generator=g)), dtype=dtype)   # gradient entering from above
+    wp = ops.pack_conv_weight(rnd(torch.randn((C, Ci, 3, 3), device="cuda", generator=g) * (2.0 / (Ci * 9)) ** 0.5), dtype=dtype)
+    z = ops.to_nhwc_padded(rnd(torch.randn((N, C, H, W), device="cuda", generator=g)), dtype=dtype)         # BN input of the layer below
+    gamma, beta = torch.rand(C, device="cuda", generator=g) + 0.5, torch.randn(C, device="cuda", generator=g) * 0.3
+    coef = ops.bn_train_stats(z, gamma, beta)
+    dy_ref = ops.conv2d_nhwc(dz_up, wp, relu=False)
+    dz_ref, dga_ref, dbe_ref, _ = ops.bn_act_bwd(dy_ref, z, coef, mask_mode)
+    dy, sums, nslots = ops.conv2d_nhwc_bwdstats(dz_up, wp, z, coef, mask_mode)
+    dz, dga, dbe, _ = ops.bn_act_bwd(dy, z, coef, mask_mode, sums=(sums, nslots))
+    ulp = 2 ** -7 if dtype == torch.bfloat16 else 2 ** -10
+    assert float((dy.float() - dy_ref.float()).abs().max()) <= ulp * float(dy_ref.float().abs().max())   # same kernel family, same K order
+    for a, b in ((dga, dga_ref), (dbe, dbe_ref)):
+        assert float((a - b).abs().max()) <= 2e-4 * float(b.abs().max()) + 1e-5
+    assert float((dz.float() - dz_ref.float()).abs().max()) <= 2 * ulp * float(dz_ref.float().abs().max()) + 1e-6
+    with pytest.raises(RuntimeError):
+        ops.conv2d_nhwc_bwdstats(dz_up, wp, z, coef, 1)      # the y-masked form needs the forward output: not fused
+
+
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16])
 def test_copy_channels_is_the_concat(ops, dtype):
     """concat(data, agg3) into the 128-channel operand buffer of the level-0 head towers: bit copies, nothing else touched."""
     N, H, W = 2, 5, 83
