@@ -44,8 +44,7 @@ constexpr int STRIP_BYTES = STRIP_ROWS * 128; // 33792
 constexpr int WT_BYTES = CO * 128;            // 16384: one tap, one K-half
 constexpr int HALF_BYTES = TN * 128;          // 32768: staging tile of 64 channels
 constexpr int MAX_SA = 3, MAX_SB = 5;        // ring depths are chosen on the host (Params::nsa / nsb)
-constexpr int NTHREADS = 320;                // warp 0 producer, warp 1 MMA, warps 2-9 epilogue
-constexpr int BAR_EPI = 1;
+constexpr int NTHREADS = 352;                // warp 0 producer, warp 1 MMA, warps 2-9 epilogue, warp 10 staging DMA
 constexpr int STATS_STRIDE = 1184;            // = bn::MAX_BLOCKS
 
 struct Params {
@@ -64,9 +63,13 @@ struct Params {
 };
 
 struct Misc {
-  uint64_t a_full[MAX_SA], a_empty[MAX_SA], b_full[MAX_SB], b_empty[MAX_SB], t_full[2], t_empty[2], r_full;
+  uint64_t a_full[MAX_SA], a_empty[MAX_SA], b_full[MAX_SB], b_empty[MAX_SB], t_full[2], t_empty[2];
+  uint64_t r_full[2];     // staging region (first / second part of the tile's pixels) writable: previous store has read it and,
+                          // with a residual / z tile, that tile has landed
+  uint64_t s_done[2];     // staging region complete: all eight epilogue warps have written their part
   uint32_t tmem_slot, pad;
-  uint32_t mask[8];       // halo bits of the 256 pixels of the tile in the epilogue
+  uint32_t mask[2][8];    // halo bits of the tile's pixels, one word per 32-column chunk, double-buffered by tile parity: written
+                          // by the DMA warp before it hands region A over (mbarrier release / acquire orders it)
   float scale[CO], shift[CO];
 };
 
@@ -75,8 +78,9 @@ struct Misc {
 template <bool PROF>
 __global__ void __launch_bounds__(NTHREADS, 1)
 convt_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_x2,
-             const __grid_constant__ CUtensorMap tm_w, const __grid_constant__ CUtensorMap tm_y,
-             const __grid_constant__ CUtensorMap tm_r, const float* __restrict__ scale, const float* __restrict__ shift,
+             const __grid_constant__ CUtensorMap tm_w, const __grid_constant__ CUtensorMap tm_yA,
+             const __grid_constant__ CUtensorMap tm_yB, const __grid_constant__ CUtensorMap tm_rA,
+             const __grid_constant__ CUtensorMap tm_rB, const float* __restrict__ scale, const float* __restrict__ shift,
              float* __restrict__ stats, const float* __restrict__ bcoef, long long* __restrict__ prof,
              const __grid_constant__ Params P) {
   extern __shared__ unsigned char smem_raw[];
@@ -96,12 +100,13 @@ convt_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ C
     for (int i = 0; i < MAX_SA; ++i) { tc::mbar_init(&M.a_full[i], 1); tc::mbar_init(&M.a_empty[i], 1); }
     for (int i = 0; i < MAX_SB; ++i) { tc::mbar_init(&M.b_full[i], 1); tc::mbar_init(&M.b_empty[i], 1); }
     for (int i = 0; i < 2; ++i) { tc::mbar_init(&M.t_full[i], 1); tc::mbar_init(&M.t_empty[i], 8); }
-    tc::mbar_init(&M.r_full, 1);
+    for (int i = 0; i < 2; ++i) { tc::mbar_init(&M.r_full[i], 1); tc::mbar_init(&M.s_done[i], 8); }
     tc::fence_mbar_init();
     tma::prefetch_map(&tm_x);
     tma::prefetch_map(&tm_x2);
     tma::prefetch_map(&tm_w);
-    tma::prefetch_map(&tm_y);
+    tma::prefetch_map(&tm_yA);
+    tma::prefetch_map(&tm_yB);
   }
   if (warp == 1) {
     tc::tmem_alloc(&M.tmem_slot, 512);
@@ -188,23 +193,25 @@ convt_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ C
       prof[blockIdx.x * 8 + 2] = pc2;
       prof[blockIdx.x * 8 + 3] = pc3;
     }
-  } else {
+  } else if (warp < 10) {
     // ===== epilogue: thread = TMEM lane = output channel; EIGHT warps, two per TMEM lane quadrant =====
     // (One warp per scheduler cannot hide its own latencies: the first version, four warps writing 2-byte elements, spent
-    //  14.4 k cycles per tile against 9.2 k of MMA time.  Now warps w and w+4 share a quadrant and split the tile's pixel
+    //  14.4 k cycles per tile against 9.2 k of MMA time.  Now warps w and w+4 share a quadrant and split the pixel
     //  columns, values are rounded in pairs, and lane pairs (c, c+1) swap halves so that every store is a 4-byte word
     //  [pixel][c, c+1] -- 16 lanes cover 64 contiguous bytes of a row, the 128B swizzle keeps the two rows of a warp-wide
     //  store in different banks.)
+    // The tile's pixels are handled as TWO staging regions (first / second half of the 32-column chunks).  The DMA warp
+    // stores region A and reloads it for the next tile (residual / z tile) while these warps work on region B, and vice
+    // versa: no epilogue warp ever waits for a TMA store to drain or for a residual load issued just now -- with a single
+    // region those two waits were 2.3 k (plain) / 5.3 k (residual) of ~12-16 k cycles per tile (RD_CONVT_PROF=1).
     const int ew = warp - 2;                      // 0..7
     const int q4 = warp & 3;                      // TMEM lane quadrant this warp may read
-    const int half = ew >> 2;                     // which of the two warps of the quadrant: first / second part of the pixel columns
+    const int half = ew >> 2;                     // which of the two warps of the quadrant
     const int nch = P.tn >> 5;                    // 32-column chunks of the tile (4..8)
-    const int ch_lo = half ? (nch + 1) >> 1 : 0, ch_hi = half ? nch : (nch + 1) >> 1;
+    const int nA = (nch + 1) >> 1;                // chunks of region A
     const int c = q4 * 32 + lane;
     const uint32_t lane_sel = (uint32_t)(q4 * 32) << 16;
-    const bool leader = (warp == 2 && lane == 0);
-    const bool live = c < P.cout;                 // whole warps: q4 >= 2 idles when Cout == 64 (it still joins every barrier)
-    const int nh = P.cout / KC;                   // 64-channel halves of the staging tile in use
+    const bool live = c < P.cout;                 // whole warps: q4 >= 2 idles when Cout == 64 (it still arrives on every barrier)
     const float sc = live ? M.scale[c] : 0.f, sh = live ? M.shift[c] : 0.f;
     // BatchNorm below (bstat): a | b | mean rows of its coefficient block
     const float za = (P.bstat && live) ? __ldg(bcoef + c) : 0.f, zb = (P.bstat && live) ? __ldg(bcoef + P.cout + c) : 0.f;
@@ -217,98 +224,142 @@ convt_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ C
     float s_sum = 0.f, s_sq = 0.f;
     uint32_t it = 0;
     for (int tile = blockIdx.x; tile < P.ntiles; tile += gridDim.x, ++it) {
-      const int p0 = P.p_first + tile * P.tn;
       const uint32_t buf = it & 1;
-      const long long e0 = tick();
-      if (leader) tma::store_wait_read<0>();      // the previous tile's stores have read the staging tile
-      {  // halo bits of the tile's 256 pixels: warp ew covers pixels [32 ew, 32 ew + 32)
-        const int p = p0 + ew * 32 + lane;
-        bool halo = true;
-        if (p < P.P_total) {
-          const int col = p % P.Wp, row = (p / P.Wp) % P.Hp;
-          halo = col == 0 || col == P.Wp - 1 || row == 0 || row == P.Hp - 1;
-        }
-        const unsigned bits = __ballot_sync(0xffffffffu, halo);
-        if (lane == 0) M.mask[ew] = bits;
-      }
-      tma::named_bar_sync(BAR_EPI, 256);
-      if (P.has_res || P.bstat) {                 // the other consumer's gradient / residual (or, bstat, the z tile of the
-                                                  // BatchNorm below) lands in the staging tile
-        if (leader) {
-          tc::mbar_arrive_expect_tx(&M.r_full, (uint32_t)(nh * P.tn) * 128u);
-          for (int hf = 0; hf < nh; ++hf) tma::load_2d(sO + hf * HALF_BYTES, &tm_r, &M.r_full, hf * KC, p0);
-        }
-        tc::mbar_wait(&M.r_full, it & 1);
-      }
-      const long long e1 = tick();
-      tc::mbar_wait(&M.t_full[buf], (it >> 1) & 1);
-      __syncwarp();
-      tc::tc_fence_after();
-      const long long e2 = tick();
-      pc2 += e1 - e0;
-      pc1 += e2 - e1;
       const uint32_t t_acc = tmem_base + lane_sel + buf * (uint32_t)TN;
 #pragma unroll 1
-      for (int ch = ch_lo; ch < (live ? ch_hi : 0); ++ch) {
-        float v[32];
-        tc::tmem_ld_x32(t_acc + (uint32_t)(ch * 32), v);
-        const uint32_t mbits = M.mask[ch];
-        const int px0 = ch * 32;
-#pragma unroll
-        for (int j = 0; j < 32; j += 2) {
-          float a0 = fmaf(v[j], sc, sh), a1 = fmaf(v[j + 1], sc, sh);
-          float z0 = 0.f, z1 = 0.f;
-          if (P.has_res || P.bstat) {
-            z0 = act::to_float(*reinterpret_cast<const act_t*>(my_col + (px0 + j) * 128 + ((my_chunk ^ (uint32_t)(j & 7)) << 4)));
-            z1 = act::to_float(*reinterpret_cast<const act_t*>(my_col + (px0 + j + 1) * 128 + ((my_chunk ^ (uint32_t)((j + 1) & 7)) << 4)));
-          }
-          if (P.has_res) { a0 += z0; a1 += z1; }
-          if (P.relu) { a0 = fmaxf(a0, 0.f); a1 = fmaxf(a1, 0.f); }
-          if ((mbits >> j) & 1u) a0 = 0.f;        // halo pixels: keep them zero
-          if ((mbits >> (j + 1)) & 1u) a1 = 0.f;
-          const uint32_t mine = act::pack2(a0, a1);                      // channel c: (pixel j, pixel j + 1)
-          float f0, f1;
-          act::unpack2(mine, f0, f1);
-          if (P.bstat) {   // S1 = sum g, S2 = sum g (z - mean) of the stored gradient (what bn::s_bwd_reduce_kernel would read back)
-            if (P.bstat == 2) {
-              f0 = fmaf(z0, za, zb) > 0.f ? f0 : 0.f;
-              f1 = fmaf(z1, za, zb) > 0.f ? f1 : 0.f;
-            }
-            s_sum += f0 + f1;
-            s_sq = fmaf(f0, z0 - zm, fmaf(f1, z1 - zm, s_sq));
-          } else {
-            s_sum += f0 + f1;
-            s_sq = fmaf(f0, f0, fmaf(f1, f1, s_sq));
-          }
-          const uint32_t theirs = __shfl_xor_sync(0xffffffffu, mine, 1);
-          const uint32_t word = __byte_perm(mine, theirs, sel);          // channels (c & ~1, +1) of pixel j + odd
-          // all lanes of a pair have passed their residual reads of both rows before either writes (shuffle above)
-          *reinterpret_cast<uint32_t*>(my_row + (px0 + j) * 128 + (((my_chunk ^ odd) ^ (uint32_t)(j & 7)) << 4)) = word;
+      for (int sub = 0; sub < 2; ++sub) {
+        const int s0 = sub ? nA : 0, n = sub ? nch - nA : nA;
+        const int lo = s0 + (half ? (n + 1) >> 1 : 0), hi = s0 + (half ? n : (n + 1) >> 1);
+        const long long e0 = tick();
+        tc::mbar_wait(&M.r_full[sub], it & 1);
+        const long long e1 = tick();
+        pc2 += e1 - e0;
+        if (sub == 0) {
+          tc::mbar_wait(&M.t_full[buf], (it >> 1) & 1);
+          __syncwarp();
+          tc::tc_fence_after();
+          pc1 += tick() - e1;
         }
-      }
-      tc::tc_fence_before();
-      tc::fence_proxy_async_smem();
-      __syncwarp();
-      if (lane == 0) tc::mbar_arrive(&M.t_empty[buf]);
-      pc3 += tick() - e2;
-      tma::named_bar_sync(BAR_EPI, 256);
-      if (leader) {
-        for (int hf = 0; hf < nh; ++hf) tma::store_2d(&tm_y, sO + hf * HALF_BYTES, hf * KC, p0);
-        tma::store_commit();
+        const long long e2 = tick();
+#pragma unroll 1
+        for (int ch = lo; ch < (live ? hi : lo); ++ch) {
+          const uint32_t mbits = M.mask[it & 1][ch];
+          float v[32];
+          tc::tmem_ld_x32(t_acc + (uint32_t)(ch * 32), v);
+          const int px0 = ch * 32;
+#pragma unroll
+          for (int j = 0; j < 32; j += 2) {
+            float a0 = fmaf(v[j], sc, sh), a1 = fmaf(v[j + 1], sc, sh);
+            float z0 = 0.f, z1 = 0.f;
+            if (P.has_res || P.bstat) {
+              z0 = act::to_float(*reinterpret_cast<const act_t*>(my_col + (px0 + j) * 128 + ((my_chunk ^ (uint32_t)(j & 7)) << 4)));
+              z1 = act::to_float(*reinterpret_cast<const act_t*>(my_col + (px0 + j + 1) * 128 + ((my_chunk ^ (uint32_t)((j + 1) & 7)) << 4)));
+            }
+            if (P.has_res) { a0 += z0; a1 += z1; }
+            if (P.relu) { a0 = fmaxf(a0, 0.f); a1 = fmaxf(a1, 0.f); }
+            if ((mbits >> j) & 1u) a0 = 0.f;        // halo pixels: keep them zero
+            if ((mbits >> (j + 1)) & 1u) a1 = 0.f;
+            const uint32_t mine = act::pack2(a0, a1);                      // channel c: (pixel j, pixel j + 1)
+            float f0, f1;
+            act::unpack2(mine, f0, f1);
+            if (P.bstat) {   // S1 = sum g, S2 = sum g (z - mean) of the stored gradient (what bn::s_bwd_reduce_kernel would read back)
+              if (P.bstat == 2) {
+                f0 = fmaf(z0, za, zb) > 0.f ? f0 : 0.f;
+                f1 = fmaf(z1, za, zb) > 0.f ? f1 : 0.f;
+              }
+              s_sum += f0 + f1;
+              s_sq = fmaf(f0, z0 - zm, fmaf(f1, z1 - zm, s_sq));
+            } else {
+              s_sum += f0 + f1;
+              s_sq = fmaf(f0, f0, fmaf(f1, f1, s_sq));
+            }
+            const uint32_t theirs = __shfl_xor_sync(0xffffffffu, mine, 1);
+            const uint32_t word = __byte_perm(mine, theirs, sel);          // channels (c & ~1, +1) of pixel j + odd
+            // all lanes of a pair have passed their residual reads of both rows before either writes (shuffle above)
+            *reinterpret_cast<uint32_t*>(my_row + (px0 + j) * 128 + (((my_chunk ^ odd) ^ (uint32_t)(j & 7)) << 4)) = word;
+          }
+        }
+        if (sub == 1) tc::tc_fence_before();
+        tc::fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) {
+          tc::mbar_arrive(&M.s_done[sub]);
+          if (sub == 1) tc::mbar_arrive(&M.t_empty[buf]);
+        }
+        pc3 += tick() - e2;
       }
     }
-    if (leader) tma::store_wait_all<0>();
-    if (PROF && leader) {
+    if (PROF && warp == 2 && lane == 0) {
       prof[blockIdx.x * 8 + 4] = tick() - t_begin;
       prof[blockIdx.x * 8 + 5] = pc1;
       prof[blockIdx.x * 8 + 6] = pc2;
       prof[blockIdx.x * 8 + 7] = pc3;
     }
-    if (stats != nullptr && live) {   // partial[(which * Cout + channel) * STATS_STRIDE + slot], slot = 2 * CTA + pixel half
+    if (stats != nullptr && live) {   // partial[(which * Cout + channel) * STATS_STRIDE + slot], slot = 2 * CTA + warp of the quadrant
       const int slot = (int)blockIdx.x * 2 + half;
       stats[(int64_t)c * STATS_STRIDE + slot] = s_sum;
       stats[(int64_t)(P.cout + c) * STATS_STRIDE + slot] = s_sq;
     }
+  } else {
+    // ===== staging DMA (one thread): per region, TMA store once the epilogue warps are done with it, then -- as soon as
+    // the store has read the shared memory -- hand the region back for the next tile, loaded with that tile's residual /
+    // z rows if the launch has any =====
+    const int nch = P.tn >> 5, nA = (nch + 1) >> 1;
+    const int nh = P.cout / KC;                 // 64-channel halves of the staging tile in use
+    const int px_of[2] = {0, nA * 32}, npx[2] = {nA * 32, (nch - nA) * 32};
+    // halo bits of tile_ (whole warp: lane = pixel of a chunk) -> M.mask[parity]
+    auto halo_mask = [&](int tile_, uint32_t parity) {
+      for (int ch = 0; ch < nch; ++ch) {
+        const int p = P.p_first + tile_ * P.tn + ch * 32 + lane;
+        bool halo = true;
+        if (p < P.P_total) {
+          const int col = p % P.Wp, row = (p / P.Wp) % P.Hp;
+          halo = col == 0 || col == P.Wp - 1 || row == 0 || row == P.Hp - 1;
+        }
+        const uint32_t bits = __ballot_sync(0xffffffffu, halo);
+        if (lane == 0) M.mask[parity][ch] = bits;
+      }
+    };
+    auto hand_over = [&](int sub, int tile_) {   // lane 0
+      if (P.has_res || P.bstat) {
+        tc::mbar_arrive_expect_tx(&M.r_full[sub], (uint32_t)(nh * npx[sub]) * 128u);
+        for (int hf = 0; hf < nh; ++hf)
+          tma::load_2d(sO + hf * HALF_BYTES + px_of[sub] * 128, sub ? &tm_rB : &tm_rA, &M.r_full[sub], hf * KC,
+                       P.p_first + tile_ * P.tn + px_of[sub]);
+      } else {
+        tc::mbar_arrive(&M.r_full[sub]);
+      }
+    };
+    if ((int)blockIdx.x < P.ntiles) {
+      halo_mask(blockIdx.x, 0);
+      if (lane == 0) {
+        hand_over(0, blockIdx.x);
+        hand_over(1, blockIdx.x);
+      }
+    }
+    uint32_t it = 0;
+    for (int tile = blockIdx.x; tile < P.ntiles; tile += gridDim.x, ++it) {
+      const int p0 = P.p_first + tile * P.tn;
+      const int next = tile + (int)gridDim.x;
+      // mask[(it + 1) & 1] was last read for tile it - 1, whose epilogue is over: the warps have all arrived on
+      // s_done[1] of that tile, which lane 0 waited for before coming here
+      if (next < P.ntiles) halo_mask(next, (it + 1) & 1);
+      if (lane == 0) {
+        for (int sub = 0; sub < 2; ++sub) {
+          tc::mbar_wait(&M.s_done[sub], it & 1);
+          for (int hf = 0; hf < nh; ++hf)
+            tma::store_2d(sub ? &tm_yB : &tm_yA, sO + hf * HALF_BYTES + px_of[sub] * 128, hf * KC, p0 + px_of[sub]);
+          tma::store_commit();
+          if (next < P.ntiles) {
+            tma::store_wait_read<0>();
+            hand_over(sub, next);
+          }
+        }
+      }
+      __syncwarp();
+    }
+    if (lane == 0) tma::store_wait_all<0>();
+    __syncwarp();
   }
   tc::tc_fence_before();
   __syncthreads();
@@ -373,7 +424,7 @@ int RD_ACT_FN(rd_convt_run_, )(const void* x_pad, const void* w_packed, const fl
   P.relu = relu ? 1 : 0;
   P.has_res = residual_pad ? 1 : 0;
   P.bstat = bn_z ? (bn_mask == 2 ? 2 : 1) : 0;
-  CUtensorMap tm_x, tm_x2, tm_w, tm_y, tm_r;
+  CUtensorMap tm_x, tm_x2, tm_w, tm_yA, tm_yB, tm_rA, tm_rB;
   {
     const uint64_t d[2] = {(uint64_t)Cin, (uint64_t)total};
     const uint64_t s[1] = {(uint64_t)Cin * 2};
@@ -391,9 +442,13 @@ int RD_ACT_FN(rd_convt_run_, )(const void* x_pad, const void* w_packed, const fl
   {
     const uint64_t d[2] = {(uint64_t)Cout, (uint64_t)total};
     const uint64_t s[1] = {(uint64_t)Cout * 2};
-    const uint32_t b[2] = {(uint32_t)KC, (uint32_t)P.tn};
-    if (tma::make_map(&tm_y, RD_ACT_TMA_TYPE, y_pad, 2, d, s, b, CU_TENSOR_MAP_SWIZZLE_128B)) return 1;
-    if (tma::make_map(&tm_r, RD_ACT_TMA_TYPE, residual_pad ? residual_pad : (bn_z ? bn_z : y_pad), 2, d, s, b, CU_TENSOR_MAP_SWIZZLE_128B)) return 1;
+    const int nch = P.tn / 32, nA = (nch + 1) / 2;   // the two staging regions of a tile (see the epilogue)
+    const uint32_t bA[2] = {(uint32_t)KC, (uint32_t)(nA * 32)}, bB[2] = {(uint32_t)KC, (uint32_t)((nch - nA) * 32)};
+    const void* rsrc = residual_pad ? residual_pad : (bn_z ? bn_z : y_pad);
+    if (tma::make_map(&tm_yA, RD_ACT_TMA_TYPE, y_pad, 2, d, s, bA, CU_TENSOR_MAP_SWIZZLE_128B)) return 1;
+    if (tma::make_map(&tm_yB, RD_ACT_TMA_TYPE, y_pad, 2, d, s, bB, CU_TENSOR_MAP_SWIZZLE_128B)) return 1;
+    if (tma::make_map(&tm_rA, RD_ACT_TMA_TYPE, rsrc, 2, d, s, bA, CU_TENSOR_MAP_SWIZZLE_128B)) return 1;
+    if (tma::make_map(&tm_rB, RD_ACT_TMA_TYPE, rsrc, 2, d, s, bB, CU_TENSOR_MAP_SWIZZLE_128B)) return 1;
   }
   {
     // 227 KB: strips 33 KB each, weight tiles 16 KB each, staging 64 KB.  2 strips + 5 weight tiles; 2+4 and 3+3 measured
@@ -420,7 +475,7 @@ int RD_ACT_FN(rd_convt_run_, )(const void* x_pad, const void* w_packed, const fl
     static long long* d_prof = nullptr;
     if (!d_prof) RD_CUDA(cudaMalloc(&d_prof, 1024 * 8 * sizeof(long long)));
     RD_CUDA(cudaMemsetAsync(d_prof, 0, 1024 * 8 * sizeof(long long), stream));
-    RD_CUDA(rd::launch(convt_kernel<true>, dim3(grid), dim3(NTHREADS), smem, stream, tm_x, tm_x2, tm_w, tm_y, tm_r, scale, shift, stats,
+    RD_CUDA(rd::launch(convt_kernel<true>, dim3(grid), dim3(NTHREADS), smem, stream, tm_x, tm_x2, tm_w, tm_yA, tm_yB, tm_rA, tm_rB, scale, shift, stats,
                        bn_coef, d_prof, P));
     RD_CUDA(cudaStreamSynchronize(stream));
     static long long h[1024 * 8];
@@ -430,10 +485,10 @@ int RD_ACT_FN(rd_convt_run_, )(const void* x_pad, const void* w_packed, const fl
       for (int k = 0; k < 8; ++k) m[k] += (double)h[b * 8 + k] / grid;
     const double tiles = (double)P.ntiles / grid;
     fprintf(stderr, "[rd_conv(T) prof] Cin=%d tiles/cta=%.1f | per tile: mma %.0f (wait a_full %.0f, b_full %.0f, t_empty %.0f) | epi %.0f "
-            "(wait t_full %.0f, store+mask+bar %.0f, body %.0f)\n", Cin, tiles, m[0] / tiles, m[1] / tiles, m[2] / tiles, m[3] / tiles,
+            "(wait t_full %.0f, wait region %.0f, body %.0f)\n", Cin, tiles, m[0] / tiles, m[1] / tiles, m[2] / tiles, m[3] / tiles,
             m[4] / tiles, m[5] / tiles, m[6] / tiles, m[7] / tiles);
   } else {
-    RD_CUDA(rd::launch(convt_kernel<false>, dim3(grid), dim3(NTHREADS), smem, stream, tm_x, tm_x2, tm_w, tm_y, tm_r, scale, shift, stats,
+    RD_CUDA(rd::launch(convt_kernel<false>, dim3(grid), dim3(NTHREADS), smem, stream, tm_x, tm_x2, tm_w, tm_yA, tm_yB, tm_rA, tm_rB, scale, shift, stats,
                        bn_coef, (long long*)nullptr, P));
   }
   rd::count_launch();

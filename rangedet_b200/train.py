@@ -363,7 +363,7 @@ class TrainGraph(object):
             self.bn_below[id(y)] = (z, coef, mm)
         want = self.fuse_bwd_sums
         if want == "auto":
-            want = 50000 <= N * (Hp - 2) * (Wp - 2) <= 130000
+            want = N * (Hp - 2) * (Wp - 2) >= 50000
         below = self.bn_below.get(id(x)) if (sole_consumer and want and dx_channels is None and stride_w == 1 and k == 3
                                              and ops.conv_bwdstats_supported(co_p, ci_p)) else None
 
