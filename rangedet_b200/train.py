@@ -116,13 +116,12 @@ class TrainGraph(object):
         self.use_meta = use_meta
         self.act_dtype = act_dtype
         self.fuse_stats = True     # BatchNorm batch statistics in the conv epilogue (False: separate rd_bn_train_stats pass)
-        # BatchNorm-backward sums in the epilogue of the data-gradient conv above: True / False / "auto".  Alone, per layer
-        # width at B=2, 128 channels (scripts/bwdsums_ab.py, conv + BN backward, separate -> fused): W=664 57.4 -> 54.8 us,
-        # W=1328 91.6 -> 91.6, W=2656 158 -> 163, W=332 43.5 -> 46.4 -- the conv's epilogue (z tile through the staging
-        # buffer it also stores from) pays back what the BN pass saves ("auto" fuses only in the middle).  Inside the step,
-        # where the BN passes share HBM with the weight-gradient stream, fusing everywhere wins: 17.32 -> 17.21 ms
-        # (profiles/r02_ab_bwdsums.jsonl); hence True.
-        self.fuse_bwd_sums = True
+        # BatchNorm-backward sums in the epilogue of the data-gradient conv above: True / False / "auto".  Per layer width at
+        # B=2, 128 channels (scripts/bwdsums_ab.py, conv + BN backward, separate -> fused, profiles/r02_bwdsums_per_shape.jsonl):
+        # W=2656 153 -> 143 us, W=1328 89 -> 81, W=664 56 -> 51, W=332 43 -> 46, W=166 43 -> 47 (single-tile launches: the extra
+        # z tile is pure latency there).  "auto" = layers of at least 50 000 pixels; whole step 17.16 (off) / 17.00 (all) /
+        # 16.95 ms (auto), profiles/r02_ab_bwdsums.jsonl.
+        self.fuse_bwd_sums = "auto"
         self.bn_below, self.bsums = {}, {}
         self._stats_bufs = {}
         self.pool = _Pool(device, act_dtype)
@@ -718,7 +717,7 @@ class GraphedTrainStep(object):
     def __init__(self, params, batch, H, W, lr, momentum=0.9, wd=1e-5, clip_gradient=35.0, rescale_grad=1.0 / 128.0,
                  device="cuda", use_meta=True, allreduce=None, world_size=1, with_loss=True, overlap_wgrad=True,
                  loss_hyper=None, gt_name="gt_bbox_veh_for_iou_pred", capture=True, act_dtype=torch.bfloat16,
-                 overlap_allreduce=True, fuse_stats=True, fuse_bwd_sums=True):
+                 overlap_allreduce=True, fuse_stats=True, fuse_bwd_sums="auto"):
         self.P = params
         self.allreduce = allreduce
         self.with_loss = with_loss
