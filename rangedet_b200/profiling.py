@@ -39,6 +39,12 @@ def _conv_stats(x, w, out=None, stride_w=1, ws=None):
     return key + " +stats", fl, by
 
 
+def _conv_bwdstats(x, w, bn_z, bn_coef, bn_mask_mode, out=None, ws=None):
+    key, fl, by = _conv(x, w)
+    N, H, W, Co = _nhwc(bn_z)
+    return key + " +bwd sums", fl, by + _E * N * H * W * Co      # + the z tile of the BatchNorm below
+
+
 def _finalize(partial, nslots, N, H, W, C, *a, **k):
     return ("C%d" % C, 0.0, 4.0 * nslots * 2 * C)
 
@@ -76,10 +82,12 @@ def _bn_fwd(z, coef, relu=True, res_before=None, res_after=None, out=None):
     return ("C%d @%d res%d" % (C, W, nres), 0.0, _E * N * H * W * C * (2 + nres))
 
 
-def _bn_bwd(dy, z, coef, mask_mode, y_mask=None, dz_halo_w=1, dz_out=None, want_g=False, g_out=None, dgb_out=None):
+def _bn_bwd(dy, z, coef, mask_mode, y_mask=None, dz_halo_w=1, dz_out=None, want_g=False, g_out=None, dgb_out=None, sums=None):
     N, H, W, C = _nhwc(z)
     rd = 2 + (1 if (mask_mode == 1 and y_mask is not None) else 0)    # dy, z (, y): read by the reduction AND the apply pass
-    return ("C%d @%d mask%d" % (C, W, mask_mode), 0.0, _E * N * H * W * C * (2 * rd + 1 + (1 if want_g else 0)))
+    passes = 1 if sums is not None else 2                              # sums from the conv above: apply pass only
+    return ("C%d @%d mask%d%s" % (C, W, mask_mode, " apply" if sums is not None else ""), 0.0,
+            _E * N * H * W * C * (passes * rd + 1 + (1 if want_g else 0)))
 
 
 def _sums(x, out=None):
@@ -114,6 +122,17 @@ def _meta_bwd(go, data, coord, *a, **k):
     return ("C%d @%d" % (C, W), 3 * 39.2e3 * B * H * W, B * H * W * (9 * C * 4 + C * 4 + 12 + C * 4))
 
 
+def _meta_bwd_nhwc(go_pad, data, coord, *a, **k):
+    B, C, H, W = data.shape
+    # grad_out as the NHWC 2-byte tensor, read by both kernels; data + coord in, grad_data out
+    return ("C%d @%d nhwc" % (C, W), 3 * 39.2e3 * B * H * W, B * H * W * (9 * C * _E + C * 4 + 12 + C * 4))
+
+
+def _copy_ch(src, src_off, dst, dst_off, nchan):
+    N, Hp, Wp, _ = src.shape
+    return ("C%d" % nchan, 0.0, 2.0 * _E * N * Hp * Wp * nchan)
+
+
 def _loss(cls_logit, reg_delta, *a, **k):
     B, _, H, W = reg_delta.shape
     return ("@%d" % W, 0.0, 224.0 * B * H * W)
@@ -131,12 +150,14 @@ def _sgd(weight, *a):
 # against the measured copy bandwidth
 OPS = OrderedDict([
     ("conv2d_nhwc", ("conv", _conv)), ("conv2d_nhwc_stats", ("conv", _conv_stats)), ("bn_train_finalize", ("bn", _finalize)),
+    ("conv2d_nhwc_bwdstats", ("conv", _conv_bwdstats)),
     ("conv2d_nhwc_slice", ("conv", _slice)), ("deconv2d_nhwc", ("conv", _deconv)),
     ("conv2d_wgrad", ("wgrad", _wgrad)),
     ("bn_train_stats", ("bn", _stats)), ("bn_act_fwd", ("bn", _bn_fwd)), ("bn_act_bwd", ("bn", _bn_bwd)),
     ("channel_sums", ("bn", _sums)), ("add_nhwc", ("bn", _add)),
-    ("nhwc_to_nchw", ("layout", _to_nchw)), ("nchw_to_nhwc", ("layout", _to_nhwc)),
+    ("nhwc_to_nchw", ("layout", _to_nchw)), ("nchw_to_nhwc", ("layout", _to_nhwc)), ("copy_channels", ("layout", _copy_ch)),
     ("meta_kernel_forward_nhwc", ("meta", _meta_fwd)), ("meta_kernel_backward", ("meta", _meta_bwd)),
+    ("meta_kernel_backward_nhwc", ("meta", _meta_bwd_nhwc)),
     ("rpn_loss", ("loss", _loss)),
     ("gather_to_bf16", ("optim", _gather)), ("gather_f32", ("optim", _gather)), ("sgd_mom_update", ("optim", _sgd)),
 ])
