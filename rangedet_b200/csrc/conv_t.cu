@@ -21,7 +21,7 @@
 //             are row-shifted views of it), and the 128 x 64 weight tile of every tap, through two rings
 //   warp 1    MMA issuer (converged warp, elected lane): 4 x tcgen05.mma M128 N256 K16 per tap and K-half, fp32
 //             accumulators double-buffered in all 512 TMEM columns
-//   warps 2-9 epilogue (two per TMEM lane quadrant, each 128 of the tile's pixel columns): thread = TMEM lane = OUTPUT
+//   warps 2-17 epilogue (four per TMEM lane quadrant, the tile's 32-column chunks dealt among them): thread = TMEM lane = OUTPUT
 //             CHANNEL; scale / shift / residual / ReLU, halo mask, storage rounding in pixel pairs, lane pairs swap halves so
 //             that 4-byte words [pixel][c, c+1] go into a [pixel][channel] 128B-swizzled staging tile -> two TMA stores;
 //             the BatchNorm batch statistics of the stored values are plain per-thread sums here.
@@ -44,7 +44,8 @@ constexpr int STRIP_BYTES = STRIP_ROWS * 128; // 33792
 constexpr int WT_BYTES = CO * 128;            // 16384: one tap, one K-half
 constexpr int HALF_BYTES = TN * 128;          // 32768: staging tile of 64 channels
 constexpr int MAX_SA = 3, MAX_SB = 5;        // ring depths are chosen on the host (Params::nsa / nsb)
-constexpr int NTHREADS = 352;                // warp 0 producer, warp 1 MMA, warps 2-9 epilogue, warp 10 staging DMA
+constexpr int EPI_WARPS = 16;                // four per TMEM lane quadrant
+constexpr int NTHREADS = (3 + EPI_WARPS) * 32;   // warp 0 producer, warp 1 MMA, warps 2-17 epilogue, warp 18 staging DMA
 constexpr int STATS_STRIDE = 1184;            // = bn::MAX_BLOCKS
 
 struct Params {
@@ -66,7 +67,7 @@ struct Misc {
   uint64_t a_full[MAX_SA], a_empty[MAX_SA], b_full[MAX_SB], b_empty[MAX_SB], t_full[2], t_empty[2];
   uint64_t r_full[2];     // staging region (first / second part of the tile's pixels) writable: previous store has read it and,
                           // with a residual / z tile, that tile has landed
-  uint64_t s_done[2];     // staging region complete: all eight epilogue warps have written their part
+  uint64_t s_done[2];     // staging region complete: all epilogue warps have written their part
   uint32_t tmem_slot, pad;
   uint32_t mask[2][8];    // halo bits of the tile's pixels, one word per 32-column chunk, double-buffered by tile parity: written
                           // by the DMA warp before it hands region A over (mbarrier release / acquire orders it)
@@ -99,8 +100,8 @@ convt_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ C
   if (t == 0) {
     for (int i = 0; i < MAX_SA; ++i) { tc::mbar_init(&M.a_full[i], 1); tc::mbar_init(&M.a_empty[i], 1); }
     for (int i = 0; i < MAX_SB; ++i) { tc::mbar_init(&M.b_full[i], 1); tc::mbar_init(&M.b_empty[i], 1); }
-    for (int i = 0; i < 2; ++i) { tc::mbar_init(&M.t_full[i], 1); tc::mbar_init(&M.t_empty[i], 8); }
-    for (int i = 0; i < 2; ++i) { tc::mbar_init(&M.r_full[i], 1); tc::mbar_init(&M.s_done[i], 8); }
+    for (int i = 0; i < 2; ++i) { tc::mbar_init(&M.t_full[i], 1); tc::mbar_init(&M.t_empty[i], EPI_WARPS); }
+    for (int i = 0; i < 2; ++i) { tc::mbar_init(&M.r_full[i], 1); tc::mbar_init(&M.s_done[i], EPI_WARPS); }
     tc::fence_mbar_init();
     tma::prefetch_map(&tm_x);
     tma::prefetch_map(&tm_x2);
@@ -193,20 +194,23 @@ convt_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ C
       prof[blockIdx.x * 8 + 2] = pc2;
       prof[blockIdx.x * 8 + 3] = pc3;
     }
-  } else if (warp < 10) {
-    // ===== epilogue: thread = TMEM lane = output channel; EIGHT warps, two per TMEM lane quadrant =====
-    // (One warp per scheduler cannot hide its own latencies: the first version, four warps writing 2-byte elements, spent
-    //  14.4 k cycles per tile against 9.2 k of MMA time.  Now warps w and w+4 share a quadrant and split the pixel
-    //  columns, values are rounded in pairs, and lane pairs (c, c+1) swap halves so that every store is a 4-byte word
+  } else if (warp < 2 + EPI_WARPS) {
+    // ===== epilogue: thread = TMEM lane = output channel; SIXTEEN warps, four per TMEM lane quadrant =====
+    // (The body is a chain of TMEM load -> shared-memory read -> convert -> shuffle -> shared-memory write latencies: four
+    //  warps writing 2-byte elements spent 14.4 k cycles per tile against 9.2 k of MMA time, eight warps 8.2 k (plain) /
+    //  10.7 k (residual) / 12.8 k (BN-backward sums), sixteen 5.1 / 6.9 / 8.7 k -- every variant is now behind the MMA
+    //  warp's 11 k.  The warps of a quadrant take the 32-column chunks round-robin, values are rounded in pairs, and lane
+    //  pairs (c, c+1) swap halves so that every store is a 4-byte word
     //  [pixel][c, c+1] -- 16 lanes cover 64 contiguous bytes of a row, the 128B swizzle keeps the two rows of a warp-wide
     //  store in different banks.)
     // The tile's pixels are handled as TWO staging regions (first / second half of the 32-column chunks).  The DMA warp
     // stores region A and reloads it for the next tile (residual / z tile) while these warps work on region B, and vice
     // versa: no epilogue warp ever waits for a TMA store to drain or for a residual load issued just now -- with a single
     // region those two waits were 2.3 k (plain) / 5.3 k (residual) of ~12-16 k cycles per tile (RD_CONVT_PROF=1).
-    const int ew = warp - 2;                      // 0..7
+    const int ew = warp - 2;                      // 0..EPI_WARPS-1
     const int q4 = warp & 3;                      // TMEM lane quadrant this warp may read
-    const int half = ew >> 2;                     // which of the two warps of the quadrant
+    const int part = ew >> 2;                     // which of the quadrant's warps: chunks are dealt round-robin among them
+    constexpr int NPART = EPI_WARPS / 4;
     const int nch = P.tn >> 5;                    // 32-column chunks of the tile (4..8)
     const int nA = (nch + 1) >> 1;                // chunks of region A
     const int c = q4 * 32 + lane;
@@ -229,7 +233,7 @@ convt_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ C
 #pragma unroll 1
       for (int sub = 0; sub < 2; ++sub) {
         const int s0 = sub ? nA : 0, n = sub ? nch - nA : nA;
-        const int lo = s0 + (half ? (n + 1) >> 1 : 0), hi = s0 + (half ? n : (n + 1) >> 1);
+        const int lo = s0 + part, hi = s0 + n;
         const long long e0 = tick();
         tc::mbar_wait(&M.r_full[sub], it & 1);
         const long long e1 = tick();
@@ -242,7 +246,7 @@ convt_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ C
         }
         const long long e2 = tick();
 #pragma unroll 1
-        for (int ch = lo; ch < (live ? hi : lo); ++ch) {
+        for (int ch = lo; ch < (live ? hi : lo); ch += NPART) {
           const uint32_t mbits = M.mask[it & 1][ch];
           float v[32];
           tc::tmem_ld_x32(t_acc + (uint32_t)(ch * 32), v);
@@ -295,8 +299,8 @@ convt_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ C
       prof[blockIdx.x * 8 + 6] = pc2;
       prof[blockIdx.x * 8 + 7] = pc3;
     }
-    if (stats != nullptr && live) {   // partial[(which * Cout + channel) * STATS_STRIDE + slot], slot = 2 * CTA + warp of the quadrant
-      const int slot = (int)blockIdx.x * 2 + half;
+    if (stats != nullptr && live) {   // partial[(which * Cout + channel) * STATS_STRIDE + slot], slot = NPART * CTA + warp of the quadrant
+      const int slot = (int)blockIdx.x * NPART + part;
       stats[(int64_t)c * STATS_STRIDE + slot] = s_sum;
       stats[(int64_t)(P.cout + c) * STATS_STRIDE + slot] = s_sq;
     }
@@ -467,8 +471,9 @@ int RD_ACT_FN(rd_convt_run_, )(const void* x_pad, const void* w_packed, const fl
   RD_CUDA(rd::smem_optin(convt_kernel<true>, smem));
   const int grid = P.ntiles < sms ? P.ntiles : sms;
   if (stats) {
-    RD_REQUIRE(2 * grid <= STATS_STRIDE, "rd_conv(T) stats: %d partial slots exceed %d", 2 * grid, STATS_STRIDE);
-    if (stats_slots) *stats_slots = 2 * grid;
+    constexpr int NPART = EPI_WARPS / 4;
+    RD_REQUIRE(NPART * grid <= STATS_STRIDE, "rd_conv(T) stats: %d partial slots exceed %d", NPART * grid, STATS_STRIDE);
+    if (stats_slots) *stats_slots = NPART * grid;
   }
   static const bool want_prof = [] { const char* e = getenv("RD_CONVT_PROF"); return e && e[0] == '1'; }();
   if (want_prof) {   // diagnostic: per-role cycle counters, synchronous, printed to stderr

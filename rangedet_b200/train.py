@@ -118,10 +118,11 @@ class TrainGraph(object):
         self.fuse_stats = True     # BatchNorm batch statistics in the conv epilogue (False: separate rd_bn_train_stats pass)
         # BatchNorm-backward sums in the epilogue of the data-gradient conv above: True / False / "auto".  Per layer width at
         # B=2, 128 channels (scripts/bwdsums_ab.py, conv + BN backward, separate -> fused, profiles/r02_bwdsums_per_shape.jsonl):
-        # W=2656 153 -> 143 us, W=1328 89 -> 81, W=664 56 -> 51, W=332 43 -> 46, W=166 43 -> 47 (single-tile launches: the extra
-        # z tile is pure latency there).  "auto" = layers of at least 50 000 pixels; whole step 17.16 (off) / 17.00 (all) /
-        # 16.95 ms (auto), profiles/r02_ab_bwdsums.jsonl.
-        self.fuse_bwd_sums = "auto"
+        # W=2656 151 -> 130 us, W=1328 87 -> 77, W=664 55 -> 45, W=332 43 -> 46, W=166 43 -> 45 (single-tile launches: the extra
+        # z tile is pure latency there; "auto" = layers of at least 50 000 pixels).  Whole step: 17.16 (off) / 16.67 (all) /
+        # 16.70 ms (auto), profiles/r02_ab_bwdsums.jsonl -- inside the step the BN passes share HBM with the weight-gradient
+        # stream, so even the narrow layers come out ahead: True.
+        self.fuse_bwd_sums = True
         self.bn_below, self.bsums = {}, {}
         self._stats_bufs = {}
         self.pool = _Pool(device, act_dtype)
@@ -717,7 +718,7 @@ class GraphedTrainStep(object):
     def __init__(self, params, batch, H, W, lr, momentum=0.9, wd=1e-5, clip_gradient=35.0, rescale_grad=1.0 / 128.0,
                  device="cuda", use_meta=True, allreduce=None, world_size=1, with_loss=True, overlap_wgrad=True,
                  loss_hyper=None, gt_name="gt_bbox_veh_for_iou_pred", capture=True, act_dtype=torch.bfloat16,
-                 overlap_allreduce=True, fuse_stats=True, fuse_bwd_sums="auto"):
+                 overlap_allreduce=True, fuse_stats=True, fuse_bwd_sums=True):
         self.P = params
         self.allreduce = allreduce
         self.with_loss = with_loss
