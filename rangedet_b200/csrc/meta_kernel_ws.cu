@@ -31,7 +31,8 @@ namespace mkws {
 
 constexpr int HID = 32, CCH = 3, C = 64;
 constexpr int TW = 128, ROW = TW + 2;
-constexpr int NTHREADS = 320;                // 10 warps
+constexpr int EPI_WARPS = 8;                 // two per TMEM lane quadrant: each takes 32 of the 64 channel columns
+constexpr int NTHREADS = (6 + EPI_WARPS) * 32;   // warp 0 TMA, warp 1 MMA, warps 2-5 hidden layer, warps 6-13 epilogue
 constexpr int A_CHUNK = TW * 16;             // one 16-byte K-chunk over 128 rows
 constexpr int A_BYTES = 8 * A_CHUNK;         // h_hi (4 chunks) | h_lo (4 chunks)
 constexpr int B_CHUNK = C * 16;
@@ -105,9 +106,9 @@ meta_ws_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant_
 
   // ---- setup ---------------------------------------------------------------------------------
   if (t == 0) {
-    for (int i = 0; i < NS_D; ++i) { tc::mbar_init(&S.d_full[i], 1); tc::mbar_init(&S.d_empty[i], 4); }
+    for (int i = 0; i < NS_D; ++i) { tc::mbar_init(&S.d_full[i], 1); tc::mbar_init(&S.d_empty[i], EPI_WARPS); }
     for (int i = 0; i < NS_A; ++i) { tc::mbar_init(&S.a_full[i], 4); tc::mbar_init(&S.a_empty[i], 1); }
-    for (int i = 0; i < NS_T; ++i) { tc::mbar_init(&S.t_full[i], 1); tc::mbar_init(&S.t_empty[i], 4); }
+    for (int i = 0; i < NS_T; ++i) { tc::mbar_init(&S.t_full[i], 1); tc::mbar_init(&S.t_empty[i], EPI_WARPS); }
     tc::fence_mbar_init();
     tma::prefetch_map(&tm_in);
     tma::prefetch_map(&tm_out);
@@ -313,19 +314,23 @@ meta_ws_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant_
       prof[blockIdx.x * 16 + 4] = pb;
     }
   } else {
-    // ===== epilogue (128 threads, thread = TMEM lane = pixel) =====
+    // ===== epilogue (256 threads: thread = TMEM lane = pixel, two warps per lane quadrant, 32 channel columns each) =====
+    // (Four warps -- one per scheduler -- spent 9.7 k of 17 k cycles per tile in this body with nothing to switch to while
+    //  a TMEM load or a shared-memory round trip was in flight; the MMA warp waited 8.3 k on t_empty.)
     const int q4 = warp & 3;                 // TMEM lane quadrant this warp may read
     const int px = q4 * 32 + lane;
+    const int half = (warp - 6) >> 2;        // channel columns [32 half, 32 half + 32)
     const uint32_t lane_sel = (uint32_t)(q4 * 32) << 16;
     const bool leader = (warp == 6 && lane == 0);
+    constexpr int EPI_THREADS = EPI_WARPS * 32;
     uint32_t g = 0, n_store = 0;
-    float gd[MODE == 1 ? C : 1];
+    float gd[MODE == 1 ? C / 2 : 1];
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
       const int wt = tile % tiles_w, h = (tile / tiles_w) % H, b = tile / (tiles_w * H);
       const int w0px = wt * TW;
       if (MODE == 1) {
 #pragma unroll
-        for (int i = 0; i < C; ++i) gd[i] = 0.f;
+        for (int i = 0; i < C / 2; ++i) gd[i] = 0.f;
       }
       const int bs = w0px >= 4 ? w0px - 4 : 0;
       for (int k = 0; k < 9; ++k, ++g) {
@@ -350,12 +355,11 @@ meta_ws_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant_
         if (MODE == 2) {
           const uint32_t so = n_store % NS_O;
           if (leader) tma::store_wait_read<NS_O - 1>();
-          tma::named_bar_sync(BAR_EPI, 128);
+          tma::named_bar_sync(BAR_EPI, EPI_THREADS);
           unsigned char* ot = reinterpret_cast<unsigned char*>(S.otile[so]);  // [128 px][64 ch] bf16, 128B swizzle
           const float* esc = ep_scale + k * C;
           const float* esh = ep_shift + k * C;
-#pragma unroll
-          for (int half = 0; half < 2; ++half) {
+          {
             float d[32];
 #pragma unroll
             for (int i = 0; i < 32; ++i) d[i] = ok ? dt[(half * 32 + i) * DTW] : 0.f;
@@ -383,7 +387,7 @@ meta_ws_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant_
             tc::mbar_arrive(&S.t_empty[st]);
             if (last_use) tc::mbar_arrive(&S.d_empty[sd]);
           }
-          tma::named_bar_sync(BAR_EPI, 128);
+          tma::named_bar_sync(BAR_EPI, EPI_THREADS);
           if (leader) {
             tma::store_4d(&tm_out, ot, k * C, w0px, h, b);
             tma::store_commit();
@@ -392,12 +396,11 @@ meta_ws_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant_
         } else if (MODE == 0) {
           const uint32_t so = n_store % NS_O;
           if (leader) tma::store_wait_read<NS_O - 1>();  // the store that last used otile[so] has read it
-          tma::named_bar_sync(BAR_EPI, 128);
+          tma::named_bar_sync(BAR_EPI, EPI_THREADS);
           const long long e3 = tick();
           pc += e3 - e2;
           float* ot = S.otile[so];
-#pragma unroll
-          for (int half = 0; half < 2; ++half) {
+          {
             // all 32 tap-tile loads first: the stores below may alias them as far as the compiler
             // knows, so interleaving would expose the full shared-memory latency per element
             float d[32];
@@ -417,7 +420,7 @@ meta_ws_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant_
             tc::mbar_arrive(&S.t_empty[st]);
             if (last_use) tc::mbar_arrive(&S.d_empty[sd]);
           }
-          tma::named_bar_sync(BAR_EPI, 128);
+          tma::named_bar_sync(BAR_EPI, EPI_THREADS);
           if (leader) {
             tma::store_4d(&tm_out, ot, w0px, h, k, b * C);
             tma::store_commit();
@@ -425,8 +428,7 @@ meta_ws_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant_
           pe += tick() - e4;
           ++n_store;
         } else {
-#pragma unroll
-          for (int half = 0; half < 2; ++half) {
+          {
             float d[32];
             if (GOF) {   // [px][64 ch] 2-byte elements, 16-byte chunk j of row r stored at chunk j ^ (r & 7)
               const int r = ok ? col : 0;
@@ -447,7 +449,7 @@ meta_ws_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant_
             float v[32];
             tc::tmem_ld_x32(tmem_base + lane_sel + st * C + half * 32, v);
 #pragma unroll
-            for (int i = 0; i < 32; ++i) gd[half * 32 + i] = fmaf(d[i], v[i], gd[half * 32 + i]);
+            for (int i = 0; i < 32; ++i) gd[i] = fmaf(d[i], v[i], gd[i]);
           }
           tc::tc_fence_before();
           __syncwarp();
@@ -460,12 +462,12 @@ meta_ws_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant_
       if (MODE == 1) {  // one output tile per image tile
         const uint32_t so = n_store % NS_O;
         if (leader) tma::store_wait_read<NS_O - 1>();
-        tma::named_bar_sync(BAR_EPI, 128);
+        tma::named_bar_sync(BAR_EPI, EPI_THREADS);
         float* ot = S.otile[so];
 #pragma unroll
-        for (int c = 0; c < C; ++c) ot[c * TW + px] = gd[c];
+        for (int c = 0; c < C / 2; ++c) ot[(half * 32 + c) * TW + px] = gd[c];
         tc::fence_proxy_async_smem();
-        tma::named_bar_sync(BAR_EPI, 128);
+        tma::named_bar_sync(BAR_EPI, EPI_THREADS);
         if (leader) {
           tma::store_3d(&tm_out, ot, w0px, h, b * C);
           tma::store_commit();
