@@ -272,7 +272,7 @@ def train_leg(args, rank, world, dev, B, dtype, steps, warmup, with_clocks):
     per_step = sum(step.launches.values()) if step.launches else None
     res = {"value": B * world * steps / (ms * 1e-3), "ms_per_step": ms / steps, "steps": steps, "batch_per_gpu": B,
            "parameters": int(step.flatP.numel()), "allreduce_bytes": int(step.flat.numel() * 4) if world > 1 else 0,
-           "allreduce": ("three buckets, asynchronous, each overlapping the backward of the next: " + ", ".join(
+           "allreduce": ("%d buckets, asynchronous, each overlapping the backward of the next: " % len(step.bucket_ranges) + ", ".join(
                "%.1f MB" % (sum(hi - lo for lo, hi in rs) * 4 / 1e6) for rs in step.bucket_ranges)) if step.split_bwd else "none",
            "algorithmic_TFLOPs_per_gpu": FLOP_STEP_PER_FRAME * B / (ms / steps * 1e-3) / 1e12,
            "launches_per_step": per_step, "launches_by_graph": step.launches,

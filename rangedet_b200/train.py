@@ -562,6 +562,7 @@ class TrainGraph(object):
         x = ops.nchw_to_nhwc(data.contiguous(), self._buf("data", (data.shape[0], data.shape[2] + 2, data.shape[3] + 2, 64)))
         self.nograd.add(id(x))
         res1 = self.res_stage(x, coord, "res1", 1)
+        self.low_tape_start = len(self.tape)      # res2a, res2: bucket 2; res1 (before this mark): bucket 3, the last of the backward
         res2a = self.res_stage(res1, None, "res2a", 2)
         res2 = self.res_stage(res2a, None, "res2", 2)
         self.mid_tape_start = len(self.tape)      # res3a, res3 and the aggregation stages: bucket 1 of the backward
@@ -606,19 +607,22 @@ class TrainGraph(object):
         return self.pgrads
 
     # ---- backward in buckets (flat mode): gradient exchange overlapping the rest of the backward ----------------
-    N_BUCKETS = 3
+    N_BUCKETS = 4
 
     @staticmethod
     def bucket_of(name):
         """Backward runs head -> aggregation stages -> res3 -> res3a -> res2 -> res2a -> res1.  Bucket 0: the RPN head
         (`rpn_*`, 13.1 MB of gradients); bucket 1: aggregation stages + res3 / res3a (large parameters, early and cheap
-        backward, 18.3 MB); bucket 2: res2 / res2a / res1 incl. the Meta-Kernel unit (5.2 MB, the last kernels of the
-        backward) -- so only the smallest exchange is left exposed after the backward."""
+        backward, 18.9 MB); bucket 2: res2 / res2a (4.3 MB); bucket 3: res1 incl. the Meta-Kernel unit -- 0.4 MB of
+        parameters behind the longest stretch of the backward (the 2656-wide layers), so the res2 / res2a exchange hides
+        behind it and only a latency-sized exchange is left exposed after the backward."""
         if name.startswith("rpn_"):
             return 0
         if name.startswith(("agg", "res3_", "res3a_")):
             return 1
-        return 2
+        if name.startswith(("res2_", "res2a_")):
+            return 2
+        return 3
 
     def bucket_ranges(self):
         """-> [[(lo, hi), ...] per bucket]: contiguous element ranges of the name-sorted flat buffers."""
@@ -634,17 +638,19 @@ class TrainGraph(object):
         return out
 
     def backward_bucket(self, k, d_cls=None, d_reg=None):
-        """Bucket k of backward() (call 0, 1, 2 in order): its slice of the tape, then its parameter gradients gathered
-        into their ranges of flat_g.  Flat mode only."""
-        s1, s2 = self.mid_tape_start, self.head_tape_start
+        """Bucket k of backward() (call 0 .. N_BUCKETS-1 in order): its slice of the tape, then its parameter gradients
+        gathered into their ranges of flat_g.  Flat mode only."""
+        s0, s1, s2 = self.low_tape_start, self.mid_tape_start, self.head_tape_start
         if k == 0:
             for kind, lvl, b, _ in self.head_bwd:
                 b(d_cls[lvl] if kind == "cls" else d_reg[lvl])
             seg = self.tape[s2:]
         elif k == 1:
             seg = self.tape[s1:s2]
+        elif k == 2:
+            seg = self.tape[s0:s1]
         else:
-            seg = self.tape[:s1]
+            seg = self.tape[:s0]
         for fn in reversed(seg):
             fn()
         self._join_side()
@@ -711,8 +717,8 @@ class GraphedTrainStep(object):
     `allreduce` given, the flat gradient buffer is summed across ranks between backward and update and averaged through
     rescale_grad / world_size (the reference: hvd.DistributedOptimizer, tools/train.py:364-368).  `allreduce(view)` must
     SUM the given contiguous view of the flat buffer over ranks; it may return a handle with `.wait()` (e.g.
-    dist.all_reduce(..., async_op=True)): with world_size > 1 the captured backward is then split into three buckets (head |
-    aggregation stages + res3 / res3a | res2 / res2a / res1, TrainGraph.bucket_of) and each bucket's exchange overlaps the
+    dist.all_reduce(..., async_op=True)): with world_size > 1 the captured backward is then split into four buckets (head |
+    aggregation stages + res3 / res3a | res2 / res2a | res1, TrainGraph.bucket_of) and each bucket's exchange overlaps the
     backward kernels of the buckets after it; only the last, smallest one (5 MB) is exposed."""
 
     def __init__(self, params, batch, H, W, lr, momentum=0.9, wd=1e-5, clip_gradient=35.0, rescale_grad=1.0 / 128.0,

@@ -126,13 +126,13 @@ def test_flat_mode_gathers_reproduce_the_per_tensor_path(cpu_train):
     tg.enable_flat(flatP, offsets, flat_g, run_step)
     assert tg.no_grad_params == sorted(k for k in names if k.startswith("res1_unit2_conv1") or k.startswith("res1_unit2_bn1"))
     run_step()                                                 # flat mode: one gather in, one gather out
-    # backward in buckets (head | aggregation stages + res3 / res3a | res2 / res2a / res1): the same flat gradient, bucket
+    # backward in buckets (head | aggregation stages + res3 / res3a | res2 / res2a | res1): the same flat gradient, bucket
     # by bucket -- what the overlapped all-reduces of GraphedTrainStep exchange
     whole = flat_g.clone()
     ranges = tg.bucket_ranges()
     covered = sorted(r for rs in ranges for r in rs)
     assert covered[0][0] == 0 and covered[-1][1] == flat_g.numel() and all(a[1] == b[0] for a, b in zip(covered, covered[1:]))
-    assert len(ranges[0]) == 1 and len(ranges[1]) == 2 and len(ranges[2]) == 1      # rpn_* | agg*, res3* | res1..res2a
+    assert [len(r) for r in ranges] == [1, 2, 1, 1]      # rpn_* | agg*, res3* | res2* | res1*
     tg.refresh()
     tg.forward(data, coord)
     flat_g.zero_()
