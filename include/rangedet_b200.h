@@ -134,6 +134,24 @@ int rd_rpn_loss(const float* cls_logit, const float* reg_delta, const float* pc,
                 float smooth_l1_scalar, float cls_grad_scale, float reg_loss_weight, float reg_grad_scale,
                 float* iou_target, float* cls_loss, float* reg_loss, float* d_cls, float* d_reg,
                 void* workspace, size_t workspace_bytes, rd_stream_t stream);
+/* The same, with the head outputs and their gradients in the layout the head convolutions read and write (training graph):
+ * cls_pad / reg_pad = zero-haloed NHWC [B][H+2][W+2][cpad] of bf16 / fp16, logit = channel 0 of cls_pad, deltas = channels
+ * 0..7 of reg_pad (the 1x1 head convs of builder.py:247-262 with their channels padded to cpad); the gradients are
+ * written, rounded to the storage type, to the same channels of dcls_pad / dreg_pad and nothing else is touched (their
+ * other channels and halos must be zero).  Replaces rd_nhwc_*_to_nchw_f32 -> rd_rpn_loss -> rd_nchw_f32_to_nhwc_* per
+ * head output: same values (the fp32 planar tensors only ever held widened 16-bit numbers). */
+int rd_rpn_loss_nhwc_bf16(const void* cls_pad, const void* reg_pad, int H, int W, int cpad, const float* pc,
+                          const float* gt, const float* mask, const float* reg_target, const float* reg_weight,
+                          const float* reg_norm_weight, int B, int G, int iou_type, float alpha, float gamma,
+                          float smooth_l1_scalar, float cls_grad_scale, float reg_loss_weight, float reg_grad_scale,
+                          float* iou_target, float* cls_loss, float* reg_loss, void* dcls_pad, void* dreg_pad,
+                          void* workspace, size_t workspace_bytes, rd_stream_t stream);
+int rd_rpn_loss_nhwc_f16(const void* cls_pad, const void* reg_pad, int H, int W, int cpad, const float* pc,
+                         const float* gt, const float* mask, const float* reg_target, const float* reg_weight,
+                         const float* reg_norm_weight, int B, int G, int iou_type, float alpha, float gamma,
+                         float smooth_l1_scalar, float cls_grad_scale, float reg_loss_weight, float reg_grad_scale,
+                         float* iou_target, float* cls_loss, float* reg_loss, void* dcls_pad, void* dreg_pad,
+                         void* workspace, size_t workspace_bytes, rd_stream_t stream);
 
 /* ---- Training-target assignment (data-loader side of the training graph) -------------------------
  * Replace processing_cxx.assign3D_v2 / get_point_num (operator_cxx/src_cxx/assigner.h:11-87, :89-109; called from

@@ -38,6 +38,8 @@ SIGNATURES = {
     "rd_batch_rotated_iou_max": (_i, [_vp, _vp, _vp, _i, _i64, _i, _i, _vp]),
     "rd_rpn_loss_workspace_bytes": (_sz, []),
     "rd_rpn_loss": (_i, [_vp] * 8 + [_i, _i64, _i, _i] + [_f] * 6 + [_vp] * 5 + [_vp, _sz, _vp]),
+    "rd_rpn_loss_nhwc_bf16": (_i, [_vp, _vp, _i, _i, _i] + [_vp] * 6 + [_i, _i, _i] + [_f] * 6 + [_vp] * 5 + [_vp, _sz, _vp]),
+    "rd_rpn_loss_nhwc_f16": (_i, [_vp, _vp, _i, _i, _i] + [_vp] * 6 + [_i, _i, _i] + [_f] * 6 + [_vp] * 5 + [_vp, _sz, _vp]),
     "rd_assign3d_v2": (_i, [_vp] * 6 + [_f] * 7 + [_i64, _i, _vp, _vp]),
     "rd_get_point_num_workspace_bytes": (_sz, []),
     "rd_get_point_num": (_i, [_vp, _i64, _vp, _vp, _sz, _vp]),

@@ -19,6 +19,8 @@
 //
 // Compiled with -fmad=false like decode_iou.cu: the decode + IoU arithmetic is the same operation sequence,
 // so the IoU target is bit-identical to rd_decode_3d_bbox -> rd_batch_rotated_iou_max.
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <math.h>
 
 #include "../../include/rangedet_b200.h"
@@ -104,10 +106,29 @@ struct LossParams {
   int64_t N;
   int G;
   float alpha, gamma, sl1_sigma2, cls_grad_scale, reg_loss_weight, reg_grad_scale;
+  // IOF != 0 (rd_rpn_loss_nhwc_*): the head outputs and their gradients in the layout the head convolutions use -- zero-haloed
+  // NHWC [B][H+2][W+2][cpad] of 2-byte floats, logit = channel 0 of cls_pad, deltas = channels 0..7 of reg_pad; the
+  // gradients go to the same channels of dcls_pad / dreg_pad (other channels untouched: they stay zero)
+  const void *cls_pad, *reg_pad;
+  void *dcls_pad, *dreg_pad;
+  int H, W, cpad;
 };
 
+// 2-byte storage <-> fp32 (IOF 1: bf16, 2: fp16)
+template <int IOF>
+__device__ __forceinline__ float ld2(const void* base, int64_t i) {
+  if (IOF == 1) return __bfloat162float(static_cast<const __nv_bfloat16*>(base)[i]);
+  return __half2float(static_cast<const __half*>(base)[i]);
+}
+template <int IOF>
+__device__ __forceinline__ unsigned short st2(float v) {
+  if (IOF == 1) { const __nv_bfloat16 h = __float2bfloat16_rn(v); return *reinterpret_cast<const unsigned short*>(&h); }
+  const __half h = __float2half_rn(v);
+  return *reinterpret_cast<const unsigned short*>(&h);
+}
+
 // ---- stage 2: one thread per pixel ----------------------------------------------------------------------
-template <bool IOU_3D>
+template <bool IOU_3D, int IOF>
 __global__ void __launch_bounds__(LOSS_THREADS)
 rpn_loss_kernel(const LossParams p) {
   __shared__ Box2 sg[IOU_3D ? 1 : LOSS_GCHUNK];
@@ -135,7 +156,18 @@ rpn_loss_kernel(const LossParams p) {
   float mz = 0.f, mh = 0.f;
   if (active) {
 #pragma unroll
-    for (int k = 0; k < 8; ++k) d[k] = __ldg(p.reg_delta + ((int64_t)b * 8 + k) * N + n);  // planar: the transpose is free
+    for (int k = 0; k < 8; ++k) d[k] = 0.f;
+    if (IOF == 0) {
+#pragma unroll
+      for (int k = 0; k < 8; ++k) d[k] = __ldg(p.reg_delta + ((int64_t)b * 8 + k) * N + n);  // planar: the transpose is free
+    } else {   // one 16-byte load: the eight deltas of this pixel
+      const int hh = (int)(n / p.W), ww = (int)(n % p.W);
+      const int64_t e = (((int64_t)b * (p.H + 2) + hh + 1) * (p.W + 2) + ww + 1) * p.cpad;
+      const uint4 q = __ldg(reinterpret_cast<const uint4*>(static_cast<const unsigned short*>(p.reg_pad) + e));
+      const unsigned short* h8 = reinterpret_cast<const unsigned short*>(&q);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) d[k] = ld2<IOF>(h8, k);
+    }
     const float* q = p.pc + ((int64_t)b * N + n) * 3;
     decode_box(d, __ldg(q), __ldg(q + 1), v);
     if (!IOU_3D) {
@@ -241,10 +273,12 @@ rpn_loss_kernel(const LossParams p) {
   const float t = best;  // IoU target in [0,1]
   const int64_t i1 = (int64_t)b * N + n;
   if (p.iou_target) p.iou_target[i1] = t;
+  // element offset of this pixel's channel 0 in the haloed NHWC head tensors (IOF != 0)
+  const int64_t epad = IOF ? (((int64_t)b * (p.H + 2) + (int)(n / p.W) + 1) * (p.W + 2) + (int)(n % p.W) + 1) * p.cpad : 0;
 
   // ---- varifocal loss (loss.py:4-30) and its derivative w.r.t. the logit ----
   {
-    const float x = __ldg(p.cls_logit + i1);
+    const float x = IOF ? ld2<IOF>(p.cls_pad, epad) : __ldg(p.cls_logit + i1);
     const float m = __ldg(p.mask + i1);
     const float pr = 1.0f / (1.0f + expf(-x));                    // mx.sym.sigmoid
     const float ge = x >= 0.f ? 1.f : 0.f;
@@ -282,11 +316,13 @@ rpn_loss_kernel(const LossParams p) {
     }
     const float w = m / s_norm[0];
     if (p.cls_loss) p.cls_loss[i1] = loss * m / s_norm[0];
-    if (p.d_cls) p.d_cls[i1] = p.cls_grad_scale * (dloss * w);
+    if (IOF) static_cast<unsigned short*>(p.dcls_pad)[epad] = st2<IOF>(p.cls_grad_scale * (dloss * w));
+    else if (p.d_cls) p.d_cls[i1] = p.cls_grad_scale * (dloss * w);
   }
 
   // ---- normalised smooth-L1 (builder.py:381-422; mx smooth_l1: sigma^2 = scalar^2) ----
   const float s2 = p.sl1_sigma2, is2 = 1.0f / s2;
+  unsigned short dq[8];
 #pragma unroll
   for (int k = 0; k < 8; ++k) {
     const int64_t i8 = ((int64_t)b * 8 + k) * N + n;
@@ -304,7 +340,15 @@ rpn_loss_kernel(const LossParams p) {
       g = s2 * df;
     }
     if (p.reg_loss) p.reg_loss[i8] = l * w / s_norm[1] * p.reg_loss_weight;
-    if (p.d_reg) p.d_reg[i8] = p.reg_grad_scale * (g * w / s_norm[1] * p.reg_loss_weight);
+    if (IOF) dq[k] = st2<IOF>(p.reg_grad_scale * (g * w / s_norm[1] * p.reg_loss_weight));
+    else if (p.d_reg) p.d_reg[i8] = p.reg_grad_scale * (g * w / s_norm[1] * p.reg_loss_weight);
+  }
+  if (IOF) {
+    uint4 q;
+    unsigned short* h8 = reinterpret_cast<unsigned short*>(&q);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) h8[k] = dq[k];
+    *reinterpret_cast<uint4*>(static_cast<unsigned short*>(p.dreg_pad) + epad) = q;
   }
 }
 
@@ -314,21 +358,30 @@ extern "C" {
 
 size_t rd_rpn_loss_workspace_bytes(void) { return 2 * SUM_BLOCKS * sizeof(double); }
 
-int rd_rpn_loss(const float* cls_logit, const float* reg_delta, const float* pc, const float* gt,
-                const float* mask, const float* reg_target, const float* reg_weight,
-                const float* reg_norm_weight, int B, int64_t N, int G, int iou_type, float alpha, float gamma,
-                float smooth_l1_scalar, float cls_grad_scale, float reg_loss_weight, float reg_grad_scale,
-                float* iou_target, float* cls_loss, float* reg_loss, float* d_cls, float* d_reg,
-                void* workspace, size_t workspace_bytes, rd_stream_t stream) {
-  RD_REQUIRE(iou_type == 0 || iou_type == 1, "rd_rpn_loss: iou_type must be 0 (bev) or 1 (3d)");
-  RD_REQUIRE(B >= 0 && N >= 0 && G >= 1, "rd_rpn_loss: bad sizes B=%d G=%d", B, G);
-  RD_REQUIRE(smooth_l1_scalar > 0.f, "rd_rpn_loss: smooth_l1_scalar must be positive");
+// iof 0: fp32 planar head tensors (the reference op boundary); 1 / 2: haloed NHWC bf16 / fp16 head tensors
+static int loss_run(const char* who, int iof, const float* cls_logit, const float* reg_delta, const void* cls_pad,
+                    const void* reg_pad, int H, int W, int cpad, const float* pc, const float* gt, const float* mask,
+                    const float* reg_target, const float* reg_weight, const float* reg_norm_weight, int B, int64_t N, int G,
+                    int iou_type, float alpha, float gamma, float smooth_l1_scalar, float cls_grad_scale,
+                    float reg_loss_weight, float reg_grad_scale, float* iou_target, float* cls_loss, float* reg_loss,
+                    float* d_cls, float* d_reg, void* dcls_pad, void* dreg_pad, void* workspace, size_t workspace_bytes,
+                    rd_stream_t stream) {
+  RD_REQUIRE(iou_type == 0 || iou_type == 1, "%s: iou_type must be 0 (bev) or 1 (3d)", who);
+  RD_REQUIRE(B >= 0 && N >= 0 && G >= 1, "%s: bad sizes B=%d G=%d", who, B, G);
+  RD_REQUIRE(smooth_l1_scalar > 0.f, "%s: smooth_l1_scalar must be positive", who);
   if (B == 0 || N == 0) return 0;
-  RD_REQUIRE(cls_logit && reg_delta && pc && gt && mask && reg_target && reg_weight && reg_norm_weight,
-             "rd_rpn_loss: null input pointer");
-  RD_REQUIRE(B <= 65535, "rd_rpn_loss: B too large");
-  RD_REQUIRE(workspace && workspace_bytes >= rd_rpn_loss_workspace_bytes(), "rd_rpn_loss: workspace too small");
-  RD_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 7) == 0, "rd_rpn_loss: workspace must be 8-byte aligned");
+  RD_REQUIRE(pc && gt && mask && reg_target && reg_weight && reg_norm_weight, "%s: null input pointer", who);
+  if (iof == 0) {
+    RD_REQUIRE(cls_logit && reg_delta, "%s: null input pointer", who);
+  } else {
+    RD_REQUIRE(cls_pad && reg_pad && dcls_pad && dreg_pad, "%s: null head tensor", who);
+    RD_REQUIRE(H > 0 && W > 0 && (int64_t)H * W == N && cpad >= 8 && cpad % 8 == 0, "%s: bad head tensor shape", who);
+    RD_REQUIRE(((reinterpret_cast<uintptr_t>(reg_pad) | reinterpret_cast<uintptr_t>(dreg_pad)) & 15) == 0,
+               "%s: head tensors must be 16-byte aligned", who);
+  }
+  RD_REQUIRE(B <= 65535, "%s: B too large", who);
+  RD_REQUIRE(workspace && workspace_bytes >= rd_rpn_loss_workspace_bytes(), "%s: workspace too small", who);
+  RD_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 7) == 0, "%s: workspace must be 8-byte aligned", who);
   if (rd_check_device()) return 1;
   cudaStream_t st = rd::as_stream(stream);
   double* partial = static_cast<double*>(workspace);
@@ -342,13 +395,52 @@ int rd_rpn_loss(const float* cls_logit, const float* reg_delta, const float* pc,
   p.N = N; p.G = G;
   p.alpha = alpha; p.gamma = gamma; p.sl1_sigma2 = smooth_l1_scalar * smooth_l1_scalar;
   p.cls_grad_scale = cls_grad_scale; p.reg_loss_weight = reg_loss_weight; p.reg_grad_scale = reg_grad_scale;
+  p.cls_pad = cls_pad; p.reg_pad = reg_pad; p.dcls_pad = dcls_pad; p.dreg_pad = dreg_pad;
+  p.H = H; p.W = W; p.cpad = cpad;
   dim3 grid((unsigned)((N + LOSS_THREADS - 1) / LOSS_THREADS), (unsigned)B);
-  if (iou_type == 0)
-    rpn_loss_kernel<false><<<grid, LOSS_THREADS, 0, st>>>(p);
-  else
-    rpn_loss_kernel<true><<<grid, LOSS_THREADS, 0, st>>>(p);
+#define RD_LOSS_LAUNCH(I3, IO) rpn_loss_kernel<I3, IO><<<grid, LOSS_THREADS, 0, st>>>(p)
+  if (iou_type == 0) {
+    if (iof == 0) RD_LOSS_LAUNCH(false, 0); else if (iof == 1) RD_LOSS_LAUNCH(false, 1); else RD_LOSS_LAUNCH(false, 2);
+  } else {
+    if (iof == 0) RD_LOSS_LAUNCH(true, 0); else if (iof == 1) RD_LOSS_LAUNCH(true, 1); else RD_LOSS_LAUNCH(true, 2);
+  }
+#undef RD_LOSS_LAUNCH
   rd::count_launch(2);
-  return rd::check_launch("rd_rpn_loss");
+  return rd::check_launch(who);
+}
+
+int rd_rpn_loss(const float* cls_logit, const float* reg_delta, const float* pc, const float* gt,
+                const float* mask, const float* reg_target, const float* reg_weight,
+                const float* reg_norm_weight, int B, int64_t N, int G, int iou_type, float alpha, float gamma,
+                float smooth_l1_scalar, float cls_grad_scale, float reg_loss_weight, float reg_grad_scale,
+                float* iou_target, float* cls_loss, float* reg_loss, float* d_cls, float* d_reg,
+                void* workspace, size_t workspace_bytes, rd_stream_t stream) {
+  return loss_run("rd_rpn_loss", 0, cls_logit, reg_delta, nullptr, nullptr, 0, 0, 0, pc, gt, mask, reg_target, reg_weight,
+                  reg_norm_weight, B, N, G, iou_type, alpha, gamma, smooth_l1_scalar, cls_grad_scale, reg_loss_weight,
+                  reg_grad_scale, iou_target, cls_loss, reg_loss, d_cls, d_reg, nullptr, nullptr, workspace, workspace_bytes,
+                  stream);
+}
+
+int rd_rpn_loss_nhwc_bf16(const void* cls_pad, const void* reg_pad, int H, int W, int cpad, const float* pc, const float* gt,
+                          const float* mask, const float* reg_target, const float* reg_weight, const float* reg_norm_weight,
+                          int B, int G, int iou_type, float alpha, float gamma, float smooth_l1_scalar, float cls_grad_scale,
+                          float reg_loss_weight, float reg_grad_scale, float* iou_target, float* cls_loss, float* reg_loss,
+                          void* dcls_pad, void* dreg_pad, void* workspace, size_t workspace_bytes, rd_stream_t stream) {
+  return loss_run("rd_rpn_loss_nhwc_bf16", 1, nullptr, nullptr, cls_pad, reg_pad, H, W, cpad, pc, gt, mask, reg_target,
+                  reg_weight, reg_norm_weight, B, (int64_t)H * W, G, iou_type, alpha, gamma, smooth_l1_scalar, cls_grad_scale,
+                  reg_loss_weight, reg_grad_scale, iou_target, cls_loss, reg_loss, nullptr, nullptr, dcls_pad, dreg_pad,
+                  workspace, workspace_bytes, stream);
+}
+
+int rd_rpn_loss_nhwc_f16(const void* cls_pad, const void* reg_pad, int H, int W, int cpad, const float* pc, const float* gt,
+                         const float* mask, const float* reg_target, const float* reg_weight, const float* reg_norm_weight,
+                         int B, int G, int iou_type, float alpha, float gamma, float smooth_l1_scalar, float cls_grad_scale,
+                         float reg_loss_weight, float reg_grad_scale, float* iou_target, float* cls_loss, float* reg_loss,
+                         void* dcls_pad, void* dreg_pad, void* workspace, size_t workspace_bytes, rd_stream_t stream) {
+  return loss_run("rd_rpn_loss_nhwc_f16", 2, nullptr, nullptr, cls_pad, reg_pad, H, W, cpad, pc, gt, mask, reg_target,
+                  reg_weight, reg_norm_weight, B, (int64_t)H * W, G, iou_type, alpha, gamma, smooth_l1_scalar, cls_grad_scale,
+                  reg_loss_weight, reg_grad_scale, iou_target, cls_loss, reg_loss, nullptr, nullptr, dcls_pad, dreg_pad,
+                  workspace, workspace_bytes, stream);
 }
 
 }  // extern "C"

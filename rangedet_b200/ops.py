@@ -352,6 +352,49 @@ def rpn_loss(cls_logit, reg_delta, pc, gt_bbox, mask, reg_target, reg_weight, re
     return o
 
 
+def rpn_loss_nhwc(cls_pad, reg_pad, pc, gt_bbox, mask, reg_target, reg_weight, reg_norm_weight, dcls_pad, dreg_pad,
+                  iou_type="bev", alpha=1.0, gamma=2.0, smooth_l1_scalar=3.0, scale_loss_shift=128.0, cls_loss_weight=10.0,
+                  reg_loss_weight=8.0, want_loss=True, out=None):
+    """rpn_loss on the head tensors as the head convolutions hold them: cls_pad / reg_pad (B,H+2,W+2,cpad) zero-haloed
+    NHWC bf16 / fp16 (logit = channel 0, deltas = channels 0..7); the gradients are written into the same channels of
+    dcls_pad / dreg_pad (whose other channels and halo must be zero).  The other arguments and the loss outputs are
+    those of rpn_loss; -> dict(iou_target, cls_loss, reg_loss)."""
+    if iou_type not in ("bev", "3d"):
+        raise ValueError("Unknown iou type!")
+    _chk_nhwc(cls_pad, "cls_pad")
+    for t, n in ((reg_pad, "reg_pad"), (dcls_pad, "dcls_pad"), (dreg_pad, "dreg_pad")):
+        _chk_nhwc(t, n, cls_pad)
+        if t.shape != cls_pad.shape:
+            raise ValueError("rpn_loss_nhwc: %s must have the shape of cls_pad" % n)
+    B, Hp, Wp, cpad = cls_pad.shape
+    H, W = Hp - 2, Wp - 2
+    N = H * W
+    pc = _chk(pc, "pc", 3, 3)
+    gt = _chk(gt_bbox, "gt_bbox", 3, 8 if iou_type == "bev" else 7)
+    m = _chk(mask, "mask")
+    rt, rw, rn = _chk(reg_target, "reg_target", 4), _chk(reg_weight, "reg_weight", 4), _chk(reg_norm_weight, "reg_norm_weight", 4)
+    if tuple(pc.shape[:2]) != (B, N) or gt.shape[0] != B or m.numel() != B * N or any(tuple(t.shape) != (B, 8, H, W) for t in (rt, rw, rn)):
+        raise ValueError("rpn_loss_nhwc: inconsistent shapes")
+    dev = cls_pad.device
+    o = dict(out) if out is not None else {}
+    for k, shp in (("iou_target", (B, 1, H, W)), ("cls_loss", (B, 1, H, W)), ("reg_loss", (B, 8, H, W))):
+        if k not in o:
+            o[k] = torch.empty(shp, device=dev) if want_loss else None
+    L = _lib.lib()
+    ws = _workspace(int(L.rd_rpn_loss_workspace_bytes()), dev, "rpn_loss")
+    nul = ctypes.c_void_p(0)
+    pp = lambda t: nul if t is None else _p(t)
+    with torch.cuda.device(dev):
+        st = _lib.act_fn("rd_rpn_loss_nhwc_bf16", cls_pad.dtype)(
+            _p(cls_pad), _p(reg_pad), H, W, cpad, _p(pc), _p(gt), _p(m), _p(rt), _p(rw), _p(rn), B, gt.shape[1],
+            0 if iou_type == "bev" else 1, float(alpha), float(gamma), float(smooth_l1_scalar),
+            float(scale_loss_shift * cls_loss_weight), float(reg_loss_weight), float(scale_loss_shift),
+            pp(o["iou_target"]), pp(o["cls_loss"]), pp(o["reg_loss"]), _p(dcls_pad), _p(dreg_pad),
+            _p(ws), ctypes.c_size_t(ws.numel()), _stream())
+    _lib.check(st, "rpn_loss_nhwc")
+    return o
+
+
 def assign3d_v2_device(pc, bbox, bbox_center, bbox_radius, mask, is_in_nlz, max_x, min_x, max_y, min_y, max_z, min_z,
                        max_dist):
     """Device-resident assign3D_v2 (operator_cxx/src_cxx/assigner.h:11-87): pc (N,3), bbox (M,24), bbox_center (M,3),

@@ -138,6 +138,11 @@ def _loss(cls_logit, reg_delta, *a, **k):
     return ("@%d" % W, 0.0, 224.0 * B * H * W)
 
 
+def _loss_nhwc(cls_pad, reg_pad, *a, **k):
+    B, Hp, Wp, _ = reg_pad.shape
+    return ("@%d nhwc" % (Wp - 2), 0.0, 190.0 * B * (Hp - 2) * (Wp - 2))
+
+
 def _gather(src, idx, out):
     return ("n%d" % idx.numel(), 0.0, idx.numel() * (4 + 4 + out.element_size()))
 
@@ -158,7 +163,7 @@ OPS = OrderedDict([
     ("nhwc_to_nchw", ("layout", _to_nchw)), ("nchw_to_nhwc", ("layout", _to_nhwc)), ("copy_channels", ("layout", _copy_ch)),
     ("meta_kernel_forward_nhwc", ("meta", _meta_fwd)), ("meta_kernel_backward", ("meta", _meta_bwd)),
     ("meta_kernel_backward_nhwc", ("meta", _meta_bwd_nhwc)),
-    ("rpn_loss", ("loss", _loss)),
+    ("rpn_loss", ("loss", _loss)), ("rpn_loss_nhwc", ("loss", _loss_nhwc)),
     ("gather_to_bf16", ("optim", _gather)), ("gather_f32", ("optim", _gather)), ("sgd_mom_update", ("optim", _sgd)),
 ])
 BOUND = {"conv": "tensor", "wgrad": "tensor", "bn": "hbm", "layout": "hbm", "meta": "hbm", "loss": "latency", "optim": "hbm"}

@@ -124,6 +124,10 @@ class TrainGraph(object):
         # stream, so even the narrow layers come out ahead: True.
         self.fuse_bwd_sums = True
         self.bn_below, self.bsums = {}, {}
+        # False: the head outputs stay in the NHWC 16-bit tensors the head convs write (head_nhwc) and forward() returns
+        # (None, None) -- for a loss that reads / writes that layout (rpn_loss_levels_nhwc); head_outputs() converts on demand
+        self.fp32_heads = True
+        self.head_nhwc = []
         self._stats_bufs = {}
         self.pool = _Pool(device, act_dtype)
         self.packed = {}
@@ -476,10 +480,13 @@ class TrainGraph(object):
 
         bias = self._p32((wname, "bias64"), [wname + "_bias"], pad64)
         zp = ops.conv2d_nhwc(x, self._w(wname, "fwd", ci_p, 64), None, bias, relu=False, out=self._buf("z", x.shape[:3] + (64,)))
-        out = ops.nhwc_to_nchw(zp, co)
+        out = ops.nhwc_to_nchw(zp, co) if self.fp32_heads else None
+        dzb = self._buf("dz", zp.shape)     # zero-initialised once; only channels < co are ever written
+        self.head_nhwc.append((zp, dzb, co))
 
         def bwd(d_out):
-            dz = ops.nchw_to_nhwc(d_out.contiguous(), self._buf("dz", zp.shape))
+            # d_out None: the gradient is already in dzb (written there by the NHWC loss)
+            dz = dzb if d_out is None else ops.nchw_to_nhwc(d_out.contiguous(), dzb)
             self._pg(wname + "_bias", ops.channel_sums(dz, out=self._gbuf((dz.shape[3],))), lambda t: t[:co])
             G = self._wgrad(dz, x, 1, 1, self._gbuf((1, 64, ci_p)))
             wshape = tuple(P[wname + "_weight"].shape)
@@ -577,6 +584,7 @@ class TrainGraph(object):
         ops.copy_channels(agg3, 0, cat, c, 64)
         self.head_tape_start = len(self.tape)     # tape entries from here on belong to the RPN head towers
         self.head_bwd = []
+        self.head_nhwc = []                       # [(z_pad, dz_pad, channels)] in the order cls lvl 0, reg lvl 0, cls lvl 1, ...
         cls_logit, bbox_delta = [], []
         for lvl, f in enumerate([cat, agg2a, agg2]):
             t_c = t_r = f
@@ -595,11 +603,18 @@ class TrainGraph(object):
             self.head_bwd.append(("reg", lvl, b, len(self.tape)))
         return cls_logit, bbox_delta
 
+    def head_outputs(self):
+        """-> (cls_logit[3], bbox_delta[3]) fp32 NCHW from the NHWC head tensors of the last forward() (what forward()
+        returns itself unless fp32_heads is off)."""
+        cls = [ops.nhwc_to_nchw(z, co) for z, _, co in self.head_nhwc[0::2]]
+        reg = [ops.nhwc_to_nchw(z, co) for z, _, co in self.head_nhwc[1::2]]
+        return cls, reg
+
     def backward(self, d_cls, d_reg):
-        """d_cls[l] (B,1,H,W_l), d_reg[l] (B,8,H,W_l) fp32: gradients of the loss w.r.t. the head outputs.
-        Returns {parameter name: fp32 gradient in the reference's shape}."""
+        """d_cls[l] (B,1,H,W_l), d_reg[l] (B,8,H,W_l) fp32: gradients of the loss w.r.t. the head outputs (None, None: they
+        are already in the NHWC gradient tensors of head_nhwc).  Returns {parameter name: fp32 gradient in the reference's shape}."""
         for kind, lvl, b, _ in self.head_bwd:
-            b(d_cls[lvl] if kind == "cls" else d_reg[lvl])
+            b(None if d_cls is None else (d_cls[lvl] if kind == "cls" else d_reg[lvl]))
         self.run_tape()
         self._join_side()
         if self.flat_grads:   # one launch: every parameter gradient -> the flat (all-reduce) buffer
@@ -643,7 +658,7 @@ class TrainGraph(object):
         s0, s1, s2 = self.low_tape_start, self.mid_tape_start, self.head_tape_start
         if k == 0:
             for kind, lvl, b, _ in self.head_bwd:
-                b(d_cls[lvl] if kind == "cls" else d_reg[lvl])
+                b(None if d_cls is None else (d_cls[lvl] if kind == "cls" else d_reg[lvl]))
             seg = self.tape[s2:]
         elif k == 1:
             seg = self.tape[s1:s2]
@@ -676,6 +691,21 @@ def rpn_loss_levels(cls_logit, bbox_delta, targets, out=None, hyper=LOSS_HYPER, 
                                 targets[gt_name], targets["range_image_mask_s%d" % s],
                                 targets["rpn_reg_target_s%d" % s], targets["rpn_reg_weight_s%d" % s],
                                 targets["reg_normalize_weight_s%d" % s], out=None if out is None else out[lvl], **hyper))
+    return res
+
+
+def rpn_loss_levels_nhwc(head_nhwc, targets, out=None, hyper=LOSS_HYPER, gt_name="gt_bbox_veh_for_iou_pred"):
+    """rpn_loss_levels on TrainGraph.head_nhwc: the loss reads the logits / deltas from the NHWC 16-bit tensors the head
+    convolutions wrote and writes their gradients into the NHWC tensors the head backward reads -- no fp32 planar copies
+    in either direction (same values: those copies only ever held widened 16-bit numbers)."""
+    res = []
+    for lvl, s in enumerate(STRIDES):
+        (zc, dzc, _), (zr, dzr, _) = head_nhwc[2 * lvl], head_nhwc[2 * lvl + 1]
+        o = None if out is None else {k: v for k, v in out[lvl].items() if k in ("iou_target", "cls_loss", "reg_loss")}
+        res.append(ops.rpn_loss_nhwc(zc, zr, targets["pc_vehicle_frame_s%d" % s], targets[gt_name],
+                                     targets["range_image_mask_s%d" % s], targets["rpn_reg_target_s%d" % s],
+                                     targets["rpn_reg_weight_s%d" % s], targets["reg_normalize_weight_s%d" % s], dzc, dzr,
+                                     out=o, **hyper))
     return res
 
 
@@ -724,7 +754,7 @@ class GraphedTrainStep(object):
     def __init__(self, params, batch, H, W, lr, momentum=0.9, wd=1e-5, clip_gradient=35.0, rescale_grad=1.0 / 128.0,
                  device="cuda", use_meta=True, allreduce=None, world_size=1, with_loss=True, overlap_wgrad=True,
                  loss_hyper=None, gt_name="gt_bbox_veh_for_iou_pred", capture=True, act_dtype=torch.bfloat16,
-                 overlap_allreduce=True, fuse_stats=True, fuse_bwd_sums=True):
+                 overlap_allreduce=True, fuse_stats=True, fuse_bwd_sums=True, nhwc_loss=True):
         self.P = params
         self.allreduce = allreduce
         self.with_loss = with_loss
@@ -752,6 +782,10 @@ class GraphedTrainStep(object):
         self.tg = TrainGraph(params, device, use_meta, act_dtype)
         self.tg.fuse_stats = bool(fuse_stats)     # False: separate rd_bn_train_stats pass after every conv (A/B timing)
         self.tg.fuse_bwd_sums = fuse_bwd_sums     # True / False / "auto" (TrainGraph.__init__)
+        # fused loss reading / writing the head tensors in place (NHWC 16-bit): no fp32 planar head outputs or gradients in the
+        # step; `out` converts on demand
+        self.nhwc_loss = bool(nhwc_loss) and with_loss
+        self.tg.fp32_heads = not self.nhwc_loss
         self.act_dtype = act_dtype
         self.capture = capture    # False: same buffers and flat plumbing, kernels launched eagerly (debugging)
         if overlap_wgrad and capture:
@@ -842,22 +876,33 @@ class GraphedTrainStep(object):
         self.launches = dict(fwd=c1 - c0, bwd=c2 - c1, upd=_lib.launch_count() - c2)
         restore_aux()   # capture executes nothing: this undoes the eager warm-up passes
 
+    @property
+    def out(self):
+        """(cls_logit[3], bbox_delta[3]) fp32 NCHW of the last forward; with the NHWC loss they are not part of the step and
+        are converted here, on demand."""
+        return self.tg.head_outputs() if self.nhwc_loss else self._out
+
+    def _loss(self):
+        if self.nhwc_loss:
+            rpn_loss_levels_nhwc(self.tg.head_nhwc, self.targets, out=self.loss_out, hyper=self.loss_hyper, gt_name=self.gt_name)
+        elif self.with_loss:
+            rpn_loss_levels(self._out[0], self._out[1], self.targets, out=self.loss_out, hyper=self.loss_hyper, gt_name=self.gt_name)
+
     def _fwd(self):
         self.tg.refresh()
-        self.out = self.tg.forward(self.data, self.coord)
+        self._out = self.tg.forward(self.data, self.coord)
 
     def _bwd(self):
-        if self.with_loss:
-            rpn_loss_levels(self.out[0], self.out[1], self.targets, out=self.loss_out, hyper=self.loss_hyper, gt_name=self.gt_name)
-        grads = self.tg.backward(self.d_cls, self.d_reg)
+        self._loss()
+        grads = self.tg.backward(*((None, None) if self.nhwc_loss else (self.d_cls, self.d_reg)))
         if not self.tg.flat_grads:
             ks = [k for k in self.names if k in grads]
             torch._foreach_copy_([self.gviews[k] for k in ks], [grads[k].reshape(self.P[k].shape) for k in ks])
 
     def _bwd_bucket(self, k):
-        if k == 0 and self.with_loss:
-            rpn_loss_levels(self.out[0], self.out[1], self.targets, out=self.loss_out, hyper=self.loss_hyper, gt_name=self.gt_name)
-        self.tg.backward_bucket(k, self.d_cls, self.d_reg)
+        if k == 0:
+            self._loss()
+        self.tg.backward_bucket(k, *((None, None) if self.nhwc_loss else (self.d_cls, self.d_reg)))
 
     def _update(self):
         ops.sgd_mom_update(self.flatP, self.flat, self.flat_m, self.flat_wd, self.hyper)

@@ -274,6 +274,19 @@ def rpn_loss(cls_logit, reg_delta, pc, gt_bbox, mask, reg_target, reg_weight, re
     return out
 
 
+def rpn_loss_nhwc(cls_pad, reg_pad, pc, gt_bbox, mask, reg_target, reg_weight, reg_norm_weight, dcls_pad, dreg_pad, out=None, **hyper):
+    """Emulation of the loss on the NHWC head tensors: widen, run the planar emulation, round the gradients back in place."""
+    r = rpn_loss(nhwc_to_nchw(cls_pad, 1), nhwc_to_nchw(reg_pad, 8), pc, gt_bbox, mask, reg_target, reg_weight, reg_norm_weight, **hyper)
+    _store(dcls_pad, r["d_cls"].to(COMPUTE))
+    _store(dreg_pad, r["d_reg"].to(COMPUTE))
+    if out is not None:
+        for k in ("iou_target", "cls_loss", "reg_loss"):
+            if out.get(k) is not None:
+                out[k].copy_(r[k].reshape(out[k].shape))
+        return out
+    return {k: r[k] for k in ("iou_target", "cls_loss", "reg_loss")}
+
+
 def get_sorted_foreground(cls_score, bbox_delta, pc, mask, num_fgs):
     from oracle import sorted_fg_ref
     r = sorted_fg_ref.get_sorted_foreground(cls_score.float().numpy(), bbox_delta.float().numpy(), pc.float().numpy(),

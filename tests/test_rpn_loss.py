@@ -179,3 +179,35 @@ def test_rpn_loss_edge_cases():
     with pytest.raises(ValueError):
         ops.rpn_loss(t["cls_logit"], t["reg_delta"][:, :7], t["pc"], t["gt"], t["mask"], t["reg_target"], t["reg_weight"],
                      t["reg_norm_weight"])
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("dtype", [torch.float16, torch.bfloat16])
+@pytest.mark.parametrize("iou_type", ["bev", "3d"])
+@pytest.mark.parametrize("shape", [(2, 8, 96), (1, 5, 131)])
+def test_rpn_loss_on_the_nhwc_head_tensors_is_the_same_loss(iou_type, shape, dtype):
+    """rd_rpn_loss_nhwc_* (head outputs and gradients in the NHWC 16-bit layout of the head convolutions) == rd_rpn_loss on the
+    widened planar copies: loss tensors and IoU target bit-identical, gradients = the planar gradients rounded to the storage
+    type, written to channel 0 / channels 0..7 only (the other channels, holding a sentinel, and the halo stay untouched)."""
+    from rangedet_b200 import ops
+    B, H, W = shape
+    c = loss_case(B, H, W, seed=0 if shape[2] == 96 else 2, iou_type=iou_type)
+    t = {k: torch.from_numpy(np.ascontiguousarray(v)).cuda() for k, v in c.items()}
+    g = torch.Generator(device="cuda").manual_seed(9)
+    cls_pad = torch.zeros((B, H + 2, W + 2, 64), device="cuda", dtype=dtype)
+    reg_pad = torch.zeros_like(cls_pad)
+    cls_pad[:, 1:-1, 1:-1] = torch.randn((B, H, W, 64), device="cuda", generator=g).to(dtype)       # channels > 0: junk the loss must ignore
+    reg_pad[:, 1:-1, 1:-1] = torch.randn((B, H, W, 64), device="cuda", generator=g).to(dtype)
+    cls_pad[:, 1:-1, 1:-1, 0] = t["cls_logit"][:, 0].to(dtype)
+    reg_pad[:, 1:-1, 1:-1, :8] = t["reg_delta"].permute(0, 2, 3, 1).to(dtype)
+    dcls, dreg = torch.full_like(cls_pad, 7.0), torch.full_like(reg_pad, 7.0)
+    o = ops.rpn_loss_nhwc(cls_pad, reg_pad, t["pc"], t["gt"], t["mask"], t["reg_target"], t["reg_weight"], t["reg_norm_weight"],
+                          dcls, dreg, iou_type=iou_type, **HYP)
+    want = ops.rpn_loss(ops.nhwc_to_nchw(cls_pad, 1), ops.nhwc_to_nchw(reg_pad, 8), t["pc"], t["gt"], t["mask"], t["reg_target"],
+                        t["reg_weight"], t["reg_norm_weight"], iou_type=iou_type, **HYP)
+    for k in ("iou_target", "cls_loss", "reg_loss"):
+        assert torch.equal(o[k], want[k]), k
+    assert torch.equal(dcls[:, 1:-1, 1:-1, 0], want["d_cls"][:, 0].to(dtype))
+    assert torch.equal(dreg[:, 1:-1, 1:-1, :8], want["d_reg"].permute(0, 2, 3, 1).to(dtype))
+    assert bool((dcls[..., 1:] == 7.0).all()) and bool((dreg[..., 8:] == 7.0).all())
+    assert bool((dcls[:, 0] == 7.0).all()) and bool((dreg[:, :, 0] == 7.0).all())                # halo untouched
