@@ -97,6 +97,49 @@ def test_train_graph_tape_with_bf16_storage_stays_within_the_noise_floor(cpu_tra
     assert e < floor, (e, floor)
 
 
+def test_tape_fuses_the_backward_sums_and_the_sliced_data_gradient_where_it_should(cpu_train, monkeypatch):
+    """Which layers take the fused paths is host logic: conv1 -> bn1 -> relu -> conv2 chains of the 128-channel stride-1 blocks and
+    the head towers hand their BatchNorm-backward sums to the data-gradient conv above (TrainGraph.conv_bn, sole_consumer); the
+    level-0 head towers compute the data gradient of the 64 agg3 channels of concat(data, agg3) only; switching the fusion off
+    changes no gradient."""
+    P, data, coord, d_cls, d_reg = _case(True, B=2, H=8, W=64)
+    calls = {"bwdstats": [], "sums": 0, "slice": []}
+    real_bwdstats, real_bn_bwd, real_conv = fake_ops.conv2d_nhwc_bwdstats, fake_ops.bn_act_bwd, fake_ops.conv2d_nhwc
+
+    def bwdstats(x_pad, w_packed, bn_z_pad, bn_coef, bn_mask_mode, out=None, ws=None):
+        calls["bwdstats"].append((tuple(bn_z_pad.shape), int(bn_mask_mode), int(w_packed.shape[1])))
+        return real_bwdstats(x_pad, w_packed, bn_z_pad, bn_coef, bn_mask_mode, out=out, ws=ws)
+
+    def bn_bwd(*a, **k):
+        calls["sums"] += k.get("sums") is not None
+        return real_bn_bwd(*a, **k)
+
+    def conv(x_pad, w_packed, *a, **k):
+        if w_packed.shape[0] == 9 and x_pad.shape[3] == 128 and w_packed.shape[1] == 64 and x_pad.shape[2] == 64 + 2:
+            calls["slice"].append(tuple(w_packed.shape))
+        return real_conv(x_pad, w_packed, *a, **k)
+
+    monkeypatch.setattr(fake_ops, "conv2d_nhwc_bwdstats", bwdstats)
+    monkeypatch.setattr(fake_ops, "bn_act_bwd", bn_bwd)
+    monkeypatch.setattr(fake_ops, "conv2d_nhwc", conv)
+    grads = {}
+    for fuse in (True, False):
+        tg = cpu_train.TrainGraph({k: v.clone() for k, v in P.items()}, device="cpu", use_meta=True)
+        tg.fuse_bwd_sums = fuse
+        tg.forward(data, coord)
+        grads[fuse] = tg.backward(d_cls, d_reg)
+        if fuse:
+            n_fused = len(calls["bwdstats"])
+            # 12 backbone blocks (the 128-channel stride-1 units of res2a / res2 / res3a / res3 and the aggregation stages) + 18 head layers
+            assert n_fused == 30 and calls["sums"] == n_fused, (n_fused, calls["sums"])
+            assert all(z[3] == 128 and mm == 2 and co == 128 for z, mm, co in calls["bwdstats"])
+            assert len(calls["slice"]) == 2, calls["slice"]        # cls and reg tower of level 0: 128 -> 64 data gradient
+        else:
+            assert len(calls["bwdstats"]) == n_fused and calls["sums"] == n_fused      # nothing added with the fusion off
+    for k in grads[True]:
+        assert torch.equal(grads[True][k], grads[False][k]), k
+
+
 def test_flat_mode_gathers_reproduce_the_per_tensor_path(cpu_train):
     P, data, coord, d_cls, d_reg = _case(True)
     names = sorted(k for k in P if not k.endswith(("_moving_mean", "_moving_var")))
